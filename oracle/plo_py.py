@@ -1,0 +1,322 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes binding of oracle/_build/libplo.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu legs may import this module.  The product
+package (poselib_b200/) never does.  PARITY UNPINNED: the oracle is a restatement of
+PoseLib's CPU path without Eigen, not a build of PoseLib.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libplo.so")
+
+
+class RansacOpt(C.Structure):
+    _fields_ = [("max_iterations", C.c_uint64), ("min_iterations", C.c_uint64),
+                ("dyn_num_trials_mult", C.c_double), ("success_prob", C.c_double),
+                ("seed", C.c_uint64), ("progressive_sampling", C.c_int32),
+                ("score_initial_model", C.c_int32), ("max_prosac_iterations", C.c_uint64)]
+
+    def __init__(self, max_iterations=100000, min_iterations=1000, dyn_num_trials_mult=3.0,
+                 success_prob=0.9999, seed=0, progressive_sampling=False, score_initial_model=False,
+                 max_prosac_iterations=100000):
+        super().__init__(max_iterations, min_iterations, dyn_num_trials_mult, success_prob, seed,
+                         int(progressive_sampling), int(score_initial_model), max_prosac_iterations)
+
+
+class RansacStats(C.Structure):
+    _fields_ = [("refinements", C.c_uint64), ("iterations", C.c_uint64), ("num_inliers", C.c_uint64),
+                ("inlier_ratio", C.c_double), ("model_score", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+LOSS = {"TRIVIAL": 0, "TRUNCATED": 1, "HUBER": 2, "CAUCHY": 3}
+
+
+class BundleOpt(C.Structure):
+    _fields_ = [("max_iterations", C.c_uint64), ("loss_type", C.c_int32), ("pad", C.c_int32),
+                ("loss_scale", C.c_double), ("gradient_tol", C.c_double), ("step_tol", C.c_double),
+                ("relative_cost_tol", C.c_double), ("initial_lambda", C.c_double),
+                ("min_lambda", C.c_double), ("max_lambda", C.c_double)]
+
+    def __init__(self, max_iterations=100, loss_type="CAUCHY", loss_scale=1.0, gradient_tol=1e-12,
+                 step_tol=1e-8, relative_cost_tol=1e-10, initial_lambda=1e-3, min_lambda=1e-10,
+                 max_lambda=1e10):
+        lt = LOSS[loss_type] if isinstance(loss_type, str) else int(loss_type)
+        super().__init__(max_iterations, lt, 0, loss_scale, gradient_tol, step_tol, relative_cost_tol,
+                         initial_lambda, min_lambda, max_lambda)
+
+
+class Counters(C.Structure):
+    _fields_ = [("samples", C.c_uint64), ("hypotheses", C.c_uint64), ("scored_corrs", C.c_uint64),
+                ("lo_calls", C.c_uint64), ("lo_seconds", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (gcc only; seconds)."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.plo_all_inlier_sample_probability.restype = C.c_double
+        _lib.plo_compute_dynamic_max_iter.restype = C.c_uint64
+        for n in ("plo_score_pnp", "plo_score_relpose", "plo_score_fundamental", "plo_score_homography",
+                  "plo_ransac_relpose_batch_mt"):
+            getattr(_lib, n).restype = C.c_double
+    return _lib
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _mask(n):
+    m = np.zeros(n, dtype=np.int8)
+    return m, m.ctypes.data_as(C.c_char_p)
+
+
+# ---- sampler ------------------------------------------------------------------------------------
+def random_ints(seed, n):
+    out = np.zeros(n, dtype=np.int32)
+    lib().plo_random_ints(C.c_uint64(seed), n, out.ctypes.data_as(C.POINTER(C.c_int32)))
+    return out
+
+
+def sample_table(N, K, opt, iters):
+    out = np.zeros((iters, K), dtype=np.uint32)
+    lib().plo_sample_table(C.c_uint64(N), C.c_uint64(K), C.byref(opt), C.c_uint64(iters),
+                           out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return out
+
+
+# ---- loop KATs ----------------------------------------------------------------------------------
+def all_inlier_sample_probability(ni, nd, k):
+    return lib().plo_all_inlier_sample_probability(C.c_uint64(ni), C.c_uint64(nd), C.c_uint64(k))
+
+
+def compute_dynamic_max_iter(ni, nd, k, logp, mult, mn, mx):
+    return lib().plo_compute_dynamic_max_iter(C.c_uint64(ni), C.c_uint64(nd), C.c_uint64(k), C.c_double(logp),
+                                              C.c_double(mult), C.c_uint64(mn), C.c_uint64(mx))
+
+
+def ransac_mock(nd, k, inl, opt):
+    st = RansacStats()
+    lib().plo_ransac_mock(C.c_uint64(nd), C.c_uint64(k), C.c_uint64(inl), C.byref(opt), C.byref(st))
+    return st
+
+
+# ---- solvers (unit bearings, row-per-point arrays) ----------------------------------------------
+def p3p(x, X):
+    xa, xp = _d(x)
+    Xa, Xp = _d(X)
+    out = np.zeros((4, 7))
+    n = lib().plo_p3p(xp, Xp, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out[:n]
+
+
+def relpose_5pt_E(x1, x2):
+    a, ap = _d(x1)
+    b, bp = _d(x2)
+    out = np.zeros((10, 9))
+    n = lib().plo_relpose_5pt_E(ap, bp, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out[:n].reshape(n, 3, 3).transpose(0, 2, 1)  # column-major -> E[r,c]
+
+
+def relpose_5pt(x1, x2):
+    a, ap = _d(x1)
+    b, bp = _d(x2)
+    out = np.zeros((40, 7))
+    n = lib().plo_relpose_5pt(ap, bp, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out[:n]
+
+
+def relpose_7pt(x1, x2):
+    a, ap = _d(x1)
+    b, bp = _d(x2)
+    out = np.zeros((3, 9))
+    n = lib().plo_relpose_7pt(ap, bp, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out[:n].reshape(n, 3, 3).transpose(0, 2, 1)
+
+
+def homography_4pt(x1, x2, check_cheirality=True):
+    a, ap = _d(x1)
+    b, bp = _d(x2)
+    out = np.zeros(9)
+    n = lib().plo_homography_4pt(ap, bp, out.ctypes.data_as(C.POINTER(C.c_double)), int(check_cheirality))
+    return n, out.reshape(3, 3).T
+
+
+def bisect_sturm10(c):
+    ca, cp = _d(c)
+    roots = np.zeros(10)
+    n = lib().plo_bisect_sturm10(cp, roots.ctypes.data_as(C.POINTER(C.c_double)))
+    return roots[:n]
+
+
+def calculate_RFC(F):
+    fa, fp = _d(np.asarray(F).T.reshape(-1))
+    return bool(lib().plo_calculate_RFC(fp))
+
+
+# ---- scorers / masks.  Matrices are passed as F[r,c] numpy arrays; poses as 7-vectors -----------
+def _cm(M):
+    return _d(np.asarray(M, dtype=np.float64).T.reshape(-1))
+
+
+def score(kind, model, a, b, sq_thr):
+    n = len(a)
+    aa, ap = _d(a)
+    ba, bp = _d(b)
+    cnt = C.c_uint64(0)
+    if kind == "pnp":
+        m, mp = _d(model)
+        s = lib().plo_score_pnp(mp, ap, bp, C.c_uint64(n), C.c_double(sq_thr), C.byref(cnt))
+    elif kind == "relpose":
+        m, mp = _d(model)
+        s = lib().plo_score_relpose(mp, ap, bp, C.c_uint64(n), C.c_double(sq_thr), C.byref(cnt))
+    elif kind == "fundamental":
+        m, mp = _cm(model)
+        s = lib().plo_score_fundamental(mp, ap, bp, C.c_uint64(n), C.c_double(sq_thr), C.byref(cnt))
+    else:
+        m, mp = _cm(model)
+        s = lib().plo_score_homography(mp, ap, bp, C.c_uint64(n), C.c_double(sq_thr), C.byref(cnt))
+    return s, cnt.value
+
+
+def inliers(kind, model, a, b, sq_thr):
+    n = len(a)
+    aa, ap = _d(a)
+    ba, bp = _d(b)
+    mask, mkp = _mask(n)
+    if kind == "pnp":
+        m, mp = _d(model)
+        lib().plo_inliers_pnp(mp, ap, bp, C.c_uint64(n), C.c_double(sq_thr), mkp)
+    elif kind == "relpose":
+        m, mp = _d(model)
+        lib().plo_inliers_relpose(mp, ap, bp, C.c_uint64(n), C.c_double(sq_thr), mkp)
+    elif kind == "fundamental":
+        m, mp = _cm(model)
+        lib().plo_inliers_fundamental(mp, ap, bp, C.c_uint64(n), C.c_double(sq_thr), mkp)
+    else:
+        m, mp = _cm(model)
+        lib().plo_inliers_homography(mp, ap, bp, C.c_uint64(n), C.c_double(sq_thr), mkp)
+    return mask
+
+
+# ---- refiners -----------------------------------------------------------------------------------
+def refine(kind, model, a, b, bopt):
+    n = len(a)
+    aa, ap = _d(a)
+    ba, bp = _d(b)
+    bs = np.zeros(7)
+    bsp = bs.ctypes.data_as(C.POINTER(C.c_double))
+    if kind in ("pnp", "relpose"):
+        m = np.array(model, dtype=np.float64).copy()
+        mp = m.ctypes.data_as(C.POINTER(C.c_double))
+        fn = lib().plo_bundle_adjust if kind == "pnp" else lib().plo_refine_relpose
+        fn(ap, bp, C.c_uint64(n), mp, C.byref(bopt), bsp)
+        return m, bs
+    m = np.ascontiguousarray(np.asarray(model, dtype=np.float64).T.reshape(-1)).copy()
+    mp = m.ctypes.data_as(C.POINTER(C.c_double))
+    fn = lib().plo_refine_fundamental if kind == "fundamental" else lib().plo_refine_homography
+    fn(ap, bp, C.c_uint64(n), mp, C.byref(bopt), bsp)
+    return m.reshape(3, 3).T.copy(), bs
+
+
+# ---- RANSAC drivers -----------------------------------------------------------------------------
+def ransac(kind, a, b, ropt, max_error, init=None, rfc=False):
+    """Returns dict(model, inliers, stats, counters).  kind in pnp|relpose|fundamental|homography."""
+    n = len(a)
+    aa, ap = _d(a)
+    ba, bp = _d(b)
+    mask, mkp = _mask(n)
+    st, cn = RansacStats(), Counters()
+    if kind in ("pnp", "relpose"):
+        m = np.array([1, 0, 0, 0, 0, 0, 0] if init is None else init, dtype=np.float64)
+        mp = m.ctypes.data_as(C.POINTER(C.c_double))
+        fn = lib().plo_ransac_pnp if kind == "pnp" else lib().plo_ransac_relpose
+        fn(ap, bp, C.c_uint64(n), C.byref(ropt), C.c_double(max_error), mp, mkp, C.byref(st), C.byref(cn))
+        model = m
+    else:
+        m0 = np.eye(3) if init is None else np.asarray(init, dtype=np.float64)
+        m = np.ascontiguousarray(m0.T.reshape(-1)).copy()
+        mp = m.ctypes.data_as(C.POINTER(C.c_double))
+        if kind == "fundamental":
+            lib().plo_ransac_fundamental(ap, bp, C.c_uint64(n), C.byref(ropt), C.c_double(max_error), int(rfc), mp,
+                                         mkp, C.byref(st), C.byref(cn))
+        else:
+            lib().plo_ransac_homography(ap, bp, C.c_uint64(n), C.byref(ropt), C.c_double(max_error), mp, mkp,
+                                        C.byref(st), C.byref(cn))
+        model = m.reshape(3, 3).T.copy()
+    return {"model": model, "inliers": mask, "stats": st.as_dict(), "counters": cn.as_dict()}
+
+
+def estimate(kind, a, b, ropt, bopt, max_error, cam1=(1, 1, 0, 0), cam2=(1, 1, 0, 0), init=None, rfc=False):
+    n = len(a)
+    aa, ap = _d(a)
+    ba, bp = _d(b)
+    mask, mkp = _mask(n)
+    st, cn = RansacStats(), Counters()
+    c1, c1p = _d(cam1)
+    c2, c2p = _d(cam2)
+    if kind in ("pnp", "relpose"):
+        m = np.array([1, 0, 0, 0, 0, 0, 0] if init is None else init, dtype=np.float64)
+        mp = m.ctypes.data_as(C.POINTER(C.c_double))
+        if kind == "pnp":
+            lib().plo_estimate_absolute_pose(ap, bp, C.c_uint64(n), C.byref(ropt), C.byref(bopt),
+                                             C.c_double(max_error), c1p, mp, mkp, C.byref(st), C.byref(cn))
+        else:
+            lib().plo_estimate_relative_pose(ap, bp, C.c_uint64(n), c1p, c2p, C.byref(ropt), C.byref(bopt),
+                                             C.c_double(max_error), mp, mkp, C.byref(st), C.byref(cn))
+        model = m
+    else:
+        m0 = np.eye(3) if init is None else np.asarray(init, dtype=np.float64)
+        m = np.ascontiguousarray(m0.T.reshape(-1)).copy()
+        mp = m.ctypes.data_as(C.POINTER(C.c_double))
+        if kind == "fundamental":
+            lib().plo_estimate_fundamental(ap, bp, C.c_uint64(n), C.byref(ropt), C.byref(bopt),
+                                           C.c_double(max_error), int(rfc), mp, mkp, C.byref(st), C.byref(cn))
+        else:
+            lib().plo_estimate_homography(ap, bp, C.c_uint64(n), C.byref(ropt), C.byref(bopt),
+                                          C.c_double(max_error), mp, mkp, C.byref(st), C.byref(cn))
+        model = m.reshape(3, 3).T.copy()
+    return {"model": model, "inliers": mask, "stats": st.as_dict(), "counters": cn.as_dict()}
+
+
+def ransac_relpose_batch_mt(x1_list, x2_list, ropts, max_errors, threads):
+    """Many relpose problems, one problem per thread at a time.  Returns (seconds, poses, stats, counters)."""
+    count = len(x1_list)
+    off = np.zeros(count + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(a) for a in x1_list])
+    x1 = np.ascontiguousarray(np.concatenate(x1_list), dtype=np.float64)
+    x2 = np.ascontiguousarray(np.concatenate(x2_list), dtype=np.float64)
+    opts = (RansacOpt * count)(*ropts)
+    me = np.ascontiguousarray(max_errors, dtype=np.float64)
+    poses = np.zeros((count, 7))
+    poses[:, 0] = 1
+    stats = (RansacStats * count)()
+    cnts = (Counters * count)()
+    sec = lib().plo_ransac_relpose_batch_mt(
+        x1.ctypes.data_as(C.POINTER(C.c_double)), x2.ctypes.data_as(C.POINTER(C.c_double)),
+        off.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint64(count), opts,
+        me.ctypes.data_as(C.POINTER(C.c_double)), int(threads), poses.ctypes.data_as(C.POINTER(C.c_double)),
+        stats, cnts)
+    return sec, poses, [s.as_dict() for s in stats], [c.as_dict() for c in cnts]
