@@ -1,0 +1,170 @@
+/* poselib_b200 — C-ABI of the B200-native LO-RANSAC / minimal-solver engine.
+ *
+ * Drop-in boundary for ONE hot path of PoseLib (reference @ a69263d, paths below are relative to the
+ * reference checkout): the LO-RANSAC hypothesis pipeline behind PoseLib/robust.h and PoseLib/solvers/.
+ * The reference has no FFI/plugin mechanism (plain C++ free functions taking std::vector<Eigen::...>), so
+ * every entry point here is the POD restatement of one reference function; the header-only adapter
+ * poselib_b200/adapter/poselib_b200.hpp gives them back their PoseLib signatures.
+ *
+ * Conventions
+ *  - plain pointers + sizes, caller-allocated outputs, no exceptions; return 0 = ok, <0 = error
+ *    (plb_last_error() holds the message).  The reference never reports errors on this path except
+ *    Camera::unproject throwing "NYI" for unknown model ids (misc/camera_models.cc:184-185) -> PLB_ERR_NYI.
+ *  - 2D points: double[2n] AoS (std::vector<Eigen::Vector2d>::data()); 3D points: double[3n];
+ *    3x3 matrices: 9 doubles COLUMN-major (Eigen::Matrix3d); poses: q (w,x,y,z) then t (CameraPose,
+ *    camera_pose.h:40-68).
+ *  - `*_inout` models are read as the initial model iff opt->score_initial_model (robust/ransac.cc:47-50).
+ *  - inliers: char[n] written by the callee (robust/utils.cc:376), may be NULL.
+ *  - too few points: returns 0 with default stats (iterations 0, model_score DBL_MAX)
+ *    (robust/ransac_impl.h:161-163, robust.cc:548-550,716-718).
+ *  - all compute runs on the current CUDA device (plb_set_device); there is NO CPU fallback:
+ *    without a usable device every compute entry point returns PLB_ERR_CUDA.
+ */
+#ifndef POSELIB_B200_H
+#define POSELIB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLB_OK 0
+#define PLB_ERR_CUDA (-1)
+#define PLB_ERR_ARG (-2)
+#define PLB_ERR_NYI (-3)
+
+/* PoseLib/types.h:39-50 RansacOptions */
+typedef struct plb_ransac_opt {
+    uint64_t max_iterations;       /* 100000 */
+    uint64_t min_iterations;       /* 1000 */
+    double dyn_num_trials_mult;    /* 3.0 */
+    double success_prob;           /* 0.9999 */
+    uint64_t seed;                 /* 0 */
+    int32_t progressive_sampling;  /* 0; PROSAC, assumes data sorted */
+    int32_t score_initial_model;   /* 0 */
+    uint64_t max_prosac_iterations; /* 100000 */
+} plb_ransac_opt;
+
+/* PoseLib/types.h:52-58 RansacStats */
+typedef struct plb_ransac_stats {
+    uint64_t refinements;
+    uint64_t iterations;
+    uint64_t num_inliers;
+    double inlier_ratio;
+    double model_score;
+} plb_ransac_stats;
+
+/* PoseLib/types.h:60-95 BundleOptions (fields read by the four in-scope refiners; NIELSEN + LEVENBERG) */
+enum { PLB_LOSS_TRIVIAL = 0, PLB_LOSS_TRUNCATED = 1, PLB_LOSS_HUBER = 2, PLB_LOSS_CAUCHY = 3 };
+typedef struct plb_bundle_opt {
+    uint64_t max_iterations;   /* 100 */
+    int32_t loss_type;         /* PLB_LOSS_CAUCHY */
+    int32_t reserved;
+    double loss_scale;         /* 1.0 */
+    double gradient_tol;       /* 1e-12 */
+    double step_tol;           /* 1e-8 */
+    double relative_cost_tol;  /* 1e-10 */
+    double initial_lambda;     /* 1e-3 */
+    double min_lambda;         /* 1e-10 */
+    double max_lambda;         /* 1e10 */
+} plb_bundle_opt;
+
+/* Counters for the BASELINE metric; not part of the reference structs. */
+typedef struct plb_counters {
+    uint64_t samples;       /* generate_models calls consumed by the loop (== stats.iterations) */
+    uint64_t hypotheses;    /* models passed to score_model inside the loop */
+    uint64_t scored_corrs;  /* hypotheses * N */
+    uint64_t lo_calls;      /* refine_model calls */
+    double lo_seconds;      /* host wall time spent waiting on LO kernels */
+    uint64_t gpu_launches;  /* kernels launched for this call */
+    uint64_t samples_evaluated; /* incl. speculative samples past the serial break point */
+    double gpu_seconds;     /* CUDA-event time of the hypothesis kernels */
+} plb_counters;
+
+/* misc/camera_models.h:59-157 Camera, restricted to the models the path needs (others -> PLB_ERR_NYI) */
+enum { PLB_CAMERA_NULL = -1, PLB_CAMERA_SIMPLE_PINHOLE = 0, PLB_CAMERA_PINHOLE = 1 };
+typedef struct plb_camera {
+    int32_t model_id;
+    int32_t width, height;
+    double params[4]; /* SIMPLE_PINHOLE: f,cx,cy ; PINHOLE: fx,fy,cx,cy ; NULL: none */
+} plb_camera;
+
+void plb_ransac_opt_default(plb_ransac_opt *o);
+void plb_bundle_opt_default(plb_bundle_opt *o);
+const char *plb_last_error(void);
+int plb_device_count(void);          /* CUDA devices visible; 0 if none / driver missing */
+int plb_set_device(int device);      /* device used by subsequent calls from this thread */
+/* precision mode: 0 = exact (fp64 scoring of every hypothesis), 1 = fast (fp32 SMEM-resident screening of
+ * every hypothesis + fp64 confirmation of every candidate that could change the RANSAC state; same results) */
+int plb_set_mode(int mode);
+
+/* ---- robust/ransac.h:39-40,60-61,85-87,99-101 (points already calibrated / normalised) ---------- */
+int plb_ransac_pnp(const double *x_xy, const double *X_xyz, size_t n, const plb_ransac_opt *opt, double max_error,
+                   double pose_inout[7], char *inliers, plb_ransac_stats *stats, plb_counters *counters);
+int plb_ransac_relpose(const double *x1_xy, const double *x2_xy, size_t n, const plb_ransac_opt *opt,
+                       double max_error, double pose_inout[7], char *inliers, plb_ransac_stats *stats,
+                       plb_counters *counters);
+int plb_ransac_fundamental(const double *x1_xy, const double *x2_xy, size_t n, const plb_ransac_opt *opt,
+                           double max_error, int real_focal_check, double F_inout[9], char *inliers,
+                           plb_ransac_stats *stats, plb_counters *counters);
+int plb_ransac_homography(const double *x1_xy, const double *x2_xy, size_t n, const plb_ransac_opt *opt,
+                          double max_error, double H_inout[9], char *inliers, plb_ransac_stats *stats,
+                          plb_counters *counters);
+
+/* ---- PoseLib/robust.h:45-46,68-70,112-113,133-134 (pixel coordinates + cameras) ------------------- */
+int plb_estimate_absolute_pose(const double *points2D, const double *points3D, size_t n,
+                               const plb_ransac_opt *ransac, const plb_bundle_opt *bundle, double max_error,
+                               const plb_camera *camera, double pose_inout[7], char *inliers,
+                               plb_ransac_stats *stats, plb_counters *counters);
+int plb_estimate_relative_pose(const double *x1, const double *x2, size_t n, const plb_camera *camera1,
+                               const plb_camera *camera2, const plb_ransac_opt *ransac,
+                               const plb_bundle_opt *bundle, double max_error, double pose_inout[7], char *inliers,
+                               plb_ransac_stats *stats, plb_counters *counters);
+int plb_estimate_fundamental(const double *x1, const double *x2, size_t n, const plb_ransac_opt *ransac,
+                             const plb_bundle_opt *bundle, double max_error, int real_focal_check,
+                             double F_inout[9], char *inliers, plb_ransac_stats *stats, plb_counters *counters);
+int plb_estimate_homography(const double *x1, const double *x2, size_t n, const plb_ransac_opt *ransac,
+                            const plb_bundle_opt *bundle, double max_error, double H_inout[9], char *inliers,
+                            plb_ransac_stats *stats, plb_counters *counters);
+
+/* ---- PoseLib/solvers/{p3p.h:42, relpose_5pt.h:40-43, relpose_7pt.h:39-40, homography_4pt.h:38-39} ----
+ * Inputs are UNIT bearing vectors, `count` independent instances back to back; one warp solves one
+ * instance.  n_out[i] receives the number of solutions of instance i (the reference's return value);
+ * outputs are padded to the per-solver maximum. */
+int plb_p3p_batch(size_t count, const double *x /*count*3*3*/, const double *X /*count*3*3*/,
+                  double *poses_out /*count*4*7*/, int32_t *n_out);
+int plb_relpose_5pt_batch(size_t count, const double *x1 /*count*5*3*/, const double *x2,
+                          double *E_out /*count*10*9*/, int32_t *n_out);
+int plb_relpose_5pt_poses_batch(size_t count, const double *x1, const double *x2, double *poses_out /*count*40*7*/,
+                                int32_t *n_out);
+int plb_relpose_7pt_batch(size_t count, const double *x1 /*count*7*3*/, const double *x2,
+                          double *F_out /*count*3*9*/, int32_t *n_out);
+int plb_homography_4pt_batch(size_t count, const double *x1 /*count*4*3*/, const double *x2,
+                             double *H_out /*count*9*/, int32_t *n_out, int check_cheirality);
+
+/* ---- batch of independent problems (BASELINE config 5); sharded by the caller across GPUs ---------- */
+enum { PLB_KIND_PNP = 0, PLB_KIND_RELPOSE = 1, PLB_KIND_FUNDAMENTAL = 2, PLB_KIND_HOMOGRAPHY = 3 };
+typedef struct plb_problem {
+    int32_t kind;             /* PLB_KIND_* */
+    int32_t real_focal_check; /* fundamental only */
+    uint64_t n;
+    const double *a;          /* x (pnp) or x1 : 2n doubles */
+    const double *b;          /* X (pnp): 3n doubles ; else x2: 2n doubles */
+    plb_ransac_opt opt;
+    double max_error;         /* in the units of the points (ransac_* level) */
+    double model[9];          /* in/out: pose (7) or matrix (9, column-major) */
+    char *inliers;            /* n bytes or NULL */
+    plb_ransac_stats stats;   /* out */
+    plb_counters counters;    /* out */
+    int32_t status;           /* out: PLB_OK / error */
+    int32_t reserved;
+} plb_problem;
+/* Runs ransac_{pnp,relpose,fundamental,homography} on every problem; `streams` problems are in flight at once. */
+int plb_ransac_batch(plb_problem *problems, size_t count, int streams);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSELIB_B200_H */

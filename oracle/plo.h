@@ -112,7 +112,7 @@ RansacStats ransac_mock(size_t num_data, size_t sample_sz, size_t inlier_count, 
 // ---- robust/bundle.cc entry points (LM refiners) ---------------------------------------------
 struct SimpleCamera { // PINHOLE: fx,fy,cx,cy ; SIMPLE_PINHOLE: f,f,cx,cy ; NULL: 1,1,0,0
     double fx = 1, fy = 1, cx = 0, cy = 0;
-    double focal() const { return (fx + fy) / 2.0; } // camera_models.cc:304-324 (mean of focal_idx)
+    double focal() const { return 0.0 + fx / 2 + fy / 2; } // camera_models.cc:304-324 (mean of focal_idx)
 };
 BundleStats bundle_adjust(const std::vector<Vec2> &x, const std::vector<Vec3> &X, CameraPose *pose,
                           const BundleOptions &opt);

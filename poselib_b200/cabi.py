@@ -1,0 +1,267 @@
+"""ctypes binding of the C-ABI (include/poselib_b200.h) — the call a Python user (or the parity tests) makes.
+
+Every function goes through `libposelib_b200.so`; there is no Python or CPU compute path here.  If the CUDA
+library is missing, import fails loudly; if no GPU is usable, the compute entry points raise PoseLibB200Error.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libposelib_b200.so")
+
+PLB_OK, PLB_ERR_CUDA, PLB_ERR_ARG, PLB_ERR_NYI = 0, -1, -2, -3
+KIND = {"pnp": 0, "relpose": 1, "fundamental": 2, "homography": 3}
+LOSS = {"TRIVIAL": 0, "TRUNCATED": 1, "HUBER": 2, "CAUCHY": 3}
+CAMERA = {"NULL": -1, "SIMPLE_PINHOLE": 0, "PINHOLE": 1}
+
+
+class PoseLibB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"poselib_b200 error {code}: {msg}")
+        self.code = code
+
+
+class RansacOpt(C.Structure):
+    """PoseLib/types.h:39-50"""
+    _fields_ = [("max_iterations", C.c_uint64), ("min_iterations", C.c_uint64),
+                ("dyn_num_trials_mult", C.c_double), ("success_prob", C.c_double),
+                ("seed", C.c_uint64), ("progressive_sampling", C.c_int32),
+                ("score_initial_model", C.c_int32), ("max_prosac_iterations", C.c_uint64)]
+
+    def __init__(self, max_iterations=100000, min_iterations=1000, dyn_num_trials_mult=3.0,
+                 success_prob=0.9999, seed=0, progressive_sampling=False, score_initial_model=False,
+                 max_prosac_iterations=100000):
+        super().__init__(max_iterations, min_iterations, dyn_num_trials_mult, success_prob, seed,
+                         int(progressive_sampling), int(score_initial_model), max_prosac_iterations)
+
+
+class RansacStats(C.Structure):
+    """PoseLib/types.h:52-58"""
+    _fields_ = [("refinements", C.c_uint64), ("iterations", C.c_uint64), ("num_inliers", C.c_uint64),
+                ("inlier_ratio", C.c_double), ("model_score", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class BundleOpt(C.Structure):
+    """PoseLib/types.h:60-95"""
+    _fields_ = [("max_iterations", C.c_uint64), ("loss_type", C.c_int32), ("reserved", C.c_int32),
+                ("loss_scale", C.c_double), ("gradient_tol", C.c_double), ("step_tol", C.c_double),
+                ("relative_cost_tol", C.c_double), ("initial_lambda", C.c_double),
+                ("min_lambda", C.c_double), ("max_lambda", C.c_double)]
+
+    def __init__(self, max_iterations=100, loss_type="CAUCHY", loss_scale=1.0, gradient_tol=1e-12,
+                 step_tol=1e-8, relative_cost_tol=1e-10, initial_lambda=1e-3, min_lambda=1e-10,
+                 max_lambda=1e10):
+        lt = LOSS[loss_type] if isinstance(loss_type, str) else int(loss_type)
+        super().__init__(max_iterations, lt, 0, loss_scale, gradient_tol, step_tol, relative_cost_tol,
+                         initial_lambda, min_lambda, max_lambda)
+
+
+class Counters(C.Structure):
+    _fields_ = [("samples", C.c_uint64), ("hypotheses", C.c_uint64), ("scored_corrs", C.c_uint64),
+                ("lo_calls", C.c_uint64), ("lo_seconds", C.c_double), ("gpu_launches", C.c_uint64),
+                ("samples_evaluated", C.c_uint64), ("gpu_seconds", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Camera(C.Structure):
+    _fields_ = [("model_id", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("params", C.c_double * 4)]
+
+    def __init__(self, model="PINHOLE", params=(1.0, 1.0, 0.0, 0.0), width=0, height=0):
+        mid = CAMERA[model] if isinstance(model, str) else int(model)
+        p = list(params) + [0.0] * (4 - len(params))
+        super().__init__(mid, width, height, (C.c_double * 4)(*p))
+
+
+class Problem(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("real_focal_check", C.c_int32), ("n", C.c_uint64),
+                ("a", C.POINTER(C.c_double)), ("b", C.POINTER(C.c_double)), ("opt", RansacOpt),
+                ("max_error", C.c_double), ("model", C.c_double * 9), ("inliers", C.c_char_p),
+                ("stats", RansacStats), ("counters", Counters), ("status", C.c_int32), ("reserved", C.c_int32)]
+
+
+EXPORTS = [
+    "plb_ransac_opt_default", "plb_bundle_opt_default", "plb_last_error", "plb_device_count", "plb_set_device",
+    "plb_set_mode", "plb_ransac_pnp", "plb_ransac_relpose", "plb_ransac_fundamental", "plb_ransac_homography",
+    "plb_estimate_absolute_pose", "plb_estimate_relative_pose", "plb_estimate_fundamental",
+    "plb_estimate_homography", "plb_p3p_batch", "plb_relpose_5pt_batch", "plb_relpose_5pt_poses_batch",
+    "plb_relpose_7pt_batch", "plb_homography_4pt_batch", "plb_ransac_batch",
+]
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()' "
+        "or make -C poselib_b200/csrc).  There is no CPU fallback.")
+_lib = C.CDLL(LIB_PATH)
+_lib.plb_last_error.restype = C.c_char_p
+_P = C.POINTER(C.c_double)
+
+
+def lib():
+    return _lib
+
+
+def _check(rc):
+    if rc != PLB_OK:
+        raise PoseLibB200Error(rc, _lib.plb_last_error().decode())
+
+
+def device_count():
+    return _lib.plb_device_count()
+
+
+def set_device(i):
+    _check(_lib.plb_set_device(int(i)))
+
+
+def set_mode(mode):
+    _check(_lib.plb_set_mode({"exact": 0, "fast": 1}.get(mode, mode)))
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_P)
+
+
+def _init_model(kind, init):
+    if kind in ("pnp", "relpose"):
+        m = np.array([1, 0, 0, 0, 0, 0, 0] if init is None else init, dtype=np.float64)
+    else:
+        m0 = np.eye(3) if init is None else np.asarray(init, dtype=np.float64)
+        m = np.ascontiguousarray(m0.T.reshape(-1)).copy()  # column-major
+    return m
+
+
+def _model_out(kind, m):
+    return m if kind in ("pnp", "relpose") else m.reshape(3, 3).T.copy()
+
+
+def ransac(kind, a, b, ropt, max_error, init=None, rfc=False):
+    """ransac_pnp / ransac_relpose / ransac_fundamental / ransac_homography (robust/ransac.h).
+    Points are calibrated / normalised; matrices are numpy [r,c].  Returns dict(model, inliers, stats, counters)."""
+    n = len(a)
+    aa, ap = _d(a)
+    ba, bp = _d(b)
+    mask = np.zeros(max(n, 1), dtype=np.int8)
+    st, cn = RansacStats(), Counters()
+    m = _init_model(kind, init)
+    mp = m.ctypes.data_as(_P)
+    mk = mask.ctypes.data_as(C.c_char_p)
+    if kind == "pnp":
+        rc = _lib.plb_ransac_pnp(ap, bp, C.c_size_t(n), C.byref(ropt), C.c_double(max_error), mp, mk, C.byref(st),
+                                 C.byref(cn))
+    elif kind == "relpose":
+        rc = _lib.plb_ransac_relpose(ap, bp, C.c_size_t(n), C.byref(ropt), C.c_double(max_error), mp, mk,
+                                     C.byref(st), C.byref(cn))
+    elif kind == "fundamental":
+        rc = _lib.plb_ransac_fundamental(ap, bp, C.c_size_t(n), C.byref(ropt), C.c_double(max_error), int(rfc), mp,
+                                         mk, C.byref(st), C.byref(cn))
+    else:
+        rc = _lib.plb_ransac_homography(ap, bp, C.c_size_t(n), C.byref(ropt), C.c_double(max_error), mp, mk,
+                                        C.byref(st), C.byref(cn))
+    _check(rc)
+    return {"model": _model_out(kind, m), "inliers": mask[:n], "stats": st.as_dict(), "counters": cn.as_dict()}
+
+
+def estimate(kind, a, b, ropt, bopt, max_error, cam1=None, cam2=None, init=None, rfc=False):
+    """estimate_absolute_pose / estimate_relative_pose / estimate_fundamental / estimate_homography (robust.h)."""
+    n = len(a)
+    aa, ap = _d(a)
+    ba, bp = _d(b)
+    mask = np.zeros(max(n, 1), dtype=np.int8)
+    st, cn = RansacStats(), Counters()
+    m = _init_model(kind, init)
+    mp = m.ctypes.data_as(_P)
+    mk = mask.ctypes.data_as(C.c_char_p)
+    c1 = cam1 if cam1 is not None else Camera("NULL", ())
+    c2 = cam2 if cam2 is not None else Camera("NULL", ())
+    if kind == "pnp":
+        rc = _lib.plb_estimate_absolute_pose(ap, bp, C.c_size_t(n), C.byref(ropt), C.byref(bopt),
+                                             C.c_double(max_error), C.byref(c1), mp, mk, C.byref(st), C.byref(cn))
+    elif kind == "relpose":
+        rc = _lib.plb_estimate_relative_pose(ap, bp, C.c_size_t(n), C.byref(c1), C.byref(c2), C.byref(ropt),
+                                             C.byref(bopt), C.c_double(max_error), mp, mk, C.byref(st), C.byref(cn))
+    elif kind == "fundamental":
+        rc = _lib.plb_estimate_fundamental(ap, bp, C.c_size_t(n), C.byref(ropt), C.byref(bopt),
+                                           C.c_double(max_error), int(rfc), mp, mk, C.byref(st), C.byref(cn))
+    else:
+        rc = _lib.plb_estimate_homography(ap, bp, C.c_size_t(n), C.byref(ropt), C.byref(bopt),
+                                          C.c_double(max_error), mp, mk, C.byref(st), C.byref(cn))
+    _check(rc)
+    return {"model": _model_out(kind, m), "inliers": mask[:n], "stats": st.as_dict(), "counters": cn.as_dict()}
+
+
+# ---- solvers (batched; inputs [count, k, 3] unit bearings) -------------------------------------------
+def _solver(fn, a, b, per_out, extra=()):
+    aa, ap = _d(a)
+    ba, bp = _d(b)
+    count = aa.shape[0]
+    out = np.zeros((count, per_out))
+    n_out = np.zeros(count, dtype=np.int32)
+    _check(fn(C.c_size_t(count), ap, bp, out.ctypes.data_as(_P), n_out.ctypes.data_as(C.POINTER(C.c_int32)), *extra))
+    return out, n_out
+
+
+def p3p_batch(x, X):
+    out, n = _solver(_lib.plb_p3p_batch, x, X, 28)
+    return out.reshape(-1, 4, 7), n
+
+
+def relpose_5pt_batch(x1, x2):
+    out, n = _solver(_lib.plb_relpose_5pt_batch, x1, x2, 90)
+    return out.reshape(-1, 10, 3, 3).transpose(0, 1, 3, 2), n  # column-major -> [r,c]
+
+
+def relpose_5pt_poses_batch(x1, x2):
+    out, n = _solver(_lib.plb_relpose_5pt_poses_batch, x1, x2, 280)
+    return out.reshape(-1, 40, 7), n
+
+
+def relpose_7pt_batch(x1, x2):
+    out, n = _solver(_lib.plb_relpose_7pt_batch, x1, x2, 27)
+    return out.reshape(-1, 3, 3, 3).transpose(0, 1, 3, 2), n
+
+
+def homography_4pt_batch(x1, x2, check_cheirality=True):
+    out, n = _solver(_lib.plb_homography_4pt_batch, x1, x2, 9, (C.c_int(int(check_cheirality)),))
+    return out.reshape(-1, 3, 3).transpose(0, 2, 1), n
+
+
+# ---- batch of problems -------------------------------------------------------------------------------
+def ransac_batch(problems, streams=8):
+    """problems: list of dict(kind, a, b, ransac=RansacOpt, max_error, rfc=False, init=None).
+    Returns list of dict(model, inliers, stats, counters)."""
+    count = len(problems)
+    arr = (Problem * count)()
+    keep = []
+    for i, p in enumerate(problems):
+        aa, ap = _d(p["a"])
+        ba, bp = _d(p["b"])
+        mask = np.zeros(max(len(aa), 1), dtype=np.int8)
+        keep.append((aa, ba, mask))
+        q = arr[i]
+        q.kind = KIND[p["kind"]]
+        q.real_focal_check = int(p.get("rfc", False))
+        q.n = len(aa)
+        q.a, q.b = ap, bp
+        q.opt = p["ransac"]
+        q.max_error = p["max_error"]
+        m = _init_model(p["kind"], p.get("init"))
+        for k in range(len(m)):
+            q.model[k] = m[k]
+        q.inliers = C.cast(mask.ctypes.data_as(C.POINTER(C.c_char)), C.c_char_p)
+    _check(_lib.plb_ransac_batch(arr, C.c_size_t(count), int(streams)))
+    out = []
+    for i, p in enumerate(problems):
+        q = arr[i]
+        kind = p["kind"]
+        m = np.array(q.model[:7] if kind in ("pnp", "relpose") else q.model[:9], dtype=np.float64)
+        out.append({"model": _model_out(kind, m), "inliers": keep[i][2][:q.n].copy(), "stats": q.stats.as_dict(),
+                    "counters": q.counters.as_dict(), "status": q.status})
+    return out

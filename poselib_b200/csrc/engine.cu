@@ -1,0 +1,1057 @@
+// poselib_b200 — host engine + C-ABI (include/poselib_b200.h).
+//
+// The reference runs one serial loop per problem (robust/ransac_impl.h:157-201).  Its sample sequence is a pure
+// function of (seed, N, sample size, PROSAC options) and neither scoring nor refinement touch the RNG, so the engine
+//   1. generates the sample table for a whole round of iterations on the host (robust/sampling.cc restated below),
+//   2. lets the GPU solve + score every sample of the round (one warp per sample, kernels.cu),
+//   3. finds, from the per-model (inlier count, MSAC score) records, every model that improves the best-minimal
+//      state — that sub-sequence does not depend on LO results — and refines all of them in one batched LM launch,
+//   4. replays score_models() (ransac_impl.h:106-154) in iteration order over those records, which reproduces the
+//      serial trajectory exactly: LO triggers, stats, dynamic_max_iter and the break test see the same state as the
+//      reference loop; samples evaluated past the serial break point are discarded.
+// There is no CPU compute path: without a CUDA device every compute entry point fails with PLB_ERR_CUDA.
+#include "../../include/poselib_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace plb {
+
+static thread_local std::string g_err;
+static thread_local int g_device = 0;
+static std::atomic<int> g_mode{0};
+
+#define PLB_CUDA(expr)                                                                                              \
+    do {                                                                                                            \
+        cudaError_t e_ = (expr);                                                                                    \
+        if (e_ != cudaSuccess) {                                                                                    \
+            g_err = std::string(#expr) + ": " + cudaGetErrorString(e_);                                             \
+            return PLB_ERR_CUDA;                                                                                    \
+        }                                                                                                           \
+    } while (0)
+
+// ---- robust/sampling.{h,cc}: splitmix64 sampler, restated for the host side of the engine -------------------------
+struct Sampler {
+    size_t num_data, sample_sz;
+    uint64_t state;
+    bool use_prosac;
+    size_t max_prosac_iterations, sample_k = 0, subset_sz = 0;
+    std::vector<size_t> growth;
+    Sampler(size_t N, size_t K, const plb_ransac_opt &o)
+        : num_data(N), sample_sz(K), state(o.seed), use_prosac(o.progressive_sampling != 0),
+          max_prosac_iterations(o.max_prosac_iterations) {
+        if (use_prosac) init_prosac();
+    }
+    // sampling.cc:37-43 — the reference returns `int`; `% N` then sign-extends (sampling.cc:50)
+    static inline int next_int(uint64_t &st) {
+        st += 0x9e3779b97f4a7c15ULL;
+        uint64_t z = st;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        return (int)(z ^ (z >> 31));
+    }
+    inline void draw(size_t k, size_t N, uint32_t *out) { // sampling.cc:46-61
+        for (size_t i = 0; i < k; ++i) {
+            for (;;) {
+                const size_t v = (size_t)(int64_t)next_int(state) % N;
+                bool dup = false;
+                for (size_t j = 0; j < i; ++j) dup |= (out[j] == (uint32_t)v);
+                if (!dup) {
+                    out[i] = (uint32_t)v;
+                    break;
+                }
+            }
+        }
+    }
+    void init_prosac() { // sampling.cc:105-136
+        growth.assign(std::max(num_data, sample_sz), 0);
+        double T_n = (double)max_prosac_iterations;
+        for (size_t i = 0; i < sample_sz; ++i) T_n *= static_cast<double>(sample_sz - i) / (num_data - i);
+        for (size_t n = 0; n < sample_sz; ++n) growth[n] = 1;
+        size_t T_np = 1;
+        for (size_t n = sample_sz; n < num_data; ++n) {
+            const double T_n_next = T_n * (n + 1.0) / (n + 1.0 - sample_sz);
+            T_np += std::ceil(T_n_next - T_n);
+            growth[n] = T_np;
+            T_n = T_n_next;
+        }
+        sample_k = 1;
+        subset_sz = sample_sz;
+    }
+    inline void next(uint32_t *out) { // sampling.cc:85-103
+        if (use_prosac && sample_k < max_prosac_iterations) {
+            draw(sample_sz - 1, subset_sz - 1, out);
+            out[sample_sz - 1] = (uint32_t)(subset_sz - 1);
+            sample_k++;
+            if (sample_k < max_prosac_iterations && sample_k > growth[subset_sz - 1]) {
+                if (++subset_sz > num_data) subset_sz = num_data;
+            }
+        } else {
+            draw(sample_sz, num_data, out);
+        }
+    }
+};
+
+// ---- robust/ransac_impl.h:43-74 ----------------------------------------------------------------------------
+static double all_inlier_sample_probability(size_t num_inliers, size_t num_data, size_t sample_sz) {
+    if (sample_sz == 0) return 1.0;
+    if (num_inliers < sample_sz || num_data < sample_sz) return 0.0;
+    double p = 1.0;
+    for (size_t i = 0; i < sample_sz; ++i) p *= static_cast<double>(num_inliers - i) / static_cast<double>(num_data - i);
+    return p;
+}
+static size_t compute_dynamic_max_iter(size_t num_inliers, size_t num_data, size_t sample_sz, double log_prob_missing,
+                                       double mult, size_t min_it, size_t max_it) {
+    const double p = all_inlier_sample_probability(num_inliers, num_data, sample_sz);
+    if (p >= 0.9999) return min_it;
+    if (p <= 0.0001) return max_it;
+    const size_t num_iters = static_cast<size_t>(std::ceil(log_prob_missing / std::log(1.0 - p) * mult));
+    return std::max(min_it, std::min(max_it, num_iters));
+}
+
+// ---- device / pinned buffers with grow-only capacity ---------------------------------------------------------
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return PLB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = std::max<size_t>(n, 64);
+        PLB_CUDA(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+        return PLB_OK;
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+template <typename T> struct PinBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return PLB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = std::max<size_t>(n, 64);
+        PLB_CUDA(cudaMallocHost(&p, want * sizeof(T)));
+        cap = want;
+        return PLB_OK;
+    }
+    ~PinBuf() {
+        if (p) cudaFreeHost(p);
+    }
+};
+
+__global__ void k_gather_models(const double *__restrict__ models, const int *__restrict__ slots, int n, int msz,
+                                double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 9) return;
+    const int j = i / 9, k = i % 9;
+    out[i] = (k < msz) ? models[(size_t)slots[j] * msz + k] : 0.0;
+}
+
+struct Engine {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ready = false;
+    int device = -1;
+    DevBuf<double> in_a, in_b, soa64, px64, models, scores, lm_in, model_dev;
+    DevBuf<float> soa32, fscores;
+    DevBuf<uint32_t> samples, counts, fcounts;
+    DevBuf<int> n_models, work, slots;
+    DevBuf<char> mask, subset;
+    DevBuf<LmJobOut> lm_out;
+    PinBuf<double> h_in_a, h_in_b, h_scores, h_lm_in, h_model;
+    PinBuf<uint32_t> h_samples, h_counts;
+    PinBuf<int> h_n_models, h_slots;
+    PinBuf<char> h_mask;
+    PinBuf<LmJobOut> h_lm_out;
+    uint64_t launches = 0;
+
+    int init() {
+        int dev = g_device;
+        if (ready && device == dev) return PLB_OK;
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            g_err = std::string("no usable CUDA device: ") + cudaGetErrorString(e);
+            return PLB_ERR_CUDA;
+        }
+        if (dev >= count) {
+            g_err = "device index out of range";
+            return PLB_ERR_ARG;
+        }
+        PLB_CUDA(cudaSetDevice(dev));
+        if (!stream) PLB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (!ev0) PLB_CUDA(cudaEventCreate(&ev0));
+        if (!ev1) PLB_CUDA(cudaEventCreate(&ev1));
+        device = dev;
+        ready = true;
+        return PLB_OK;
+    }
+};
+static thread_local Engine *g_engine = nullptr;
+static Engine *engine() {
+    if (!g_engine) g_engine = new Engine(); // lives as long as the process (buffers are reused across calls)
+    return g_engine;
+}
+// engines of the batch worker threads, reused across plb_ransac_batch calls
+static std::mutex g_pool_mtx;
+static std::vector<Engine *> g_pool;
+static Engine *pool_engine(size_t i) {
+    std::lock_guard<std::mutex> lk(g_pool_mtx);
+    while (g_pool.size() <= i) g_pool.push_back(new Engine());
+    return g_pool[i];
+}
+
+// LO bundle options of the estimators (estimators/absolute_pose.cc:60-69 etc.): TRUNCATED(max_error), 25 iterations
+static LmParams lo_params(int kind, double max_error) {
+    LmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.max_iterations = 25;
+    p.loss_type = PLB_LOSS_TRUNCATED;
+    p.loss_scale = max_error;
+    p.gradient_tol = 1e-12;
+    p.step_tol = 1e-8;
+    p.relative_cost_tol = 1e-10;
+    p.initial_lambda = 1e-3;
+    p.min_lambda = 1e-10;
+    p.max_lambda = 1e10;
+    p.subset_mode = (kind == KIND_RELPOSE) ? 1 : 0;
+    p.subset_sq_thr = 5 * (max_error * max_error); // estimators/relative_pose.cc:70
+    p.use_camera = 0;
+    p.score_after = 1;
+    return p;
+}
+static LmParams bundle_params(const plb_bundle_opt &b) {
+    LmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.max_iterations = (int)std::min<uint64_t>(b.max_iterations, 1u << 30);
+    p.loss_type = b.loss_type;
+    p.loss_scale = b.loss_scale;
+    p.gradient_tol = b.gradient_tol;
+    p.step_tol = b.step_tol;
+    p.relative_cost_tol = b.relative_cost_tol;
+    p.initial_lambda = b.initial_lambda;
+    p.min_lambda = b.min_lambda;
+    p.max_lambda = b.max_lambda;
+    p.subset_mode = 2;
+    p.score_after = 0;
+    return p;
+}
+
+struct FinalPolish { // the post-RANSAC refinement of PoseLib/robust.cc (estimate_* entry points)
+    bool enabled = false;
+    plb_bundle_opt bundle;
+    size_t min_inliers = 0; // run iff stats.num_inliers > min_inliers
+    // pnp only: refine in pixel*scale coordinates with the rescaled pinhole camera (robust.cc:103-123)
+    const double *px_scaled = nullptr; // 2n doubles (AoS) or null
+    double cam[4] = {1, 1, 0, 0};
+};
+
+// One LO-RANSAC problem, points already calibrated / normalised.  `model` is 7 (pose) or 9 (column-major) doubles.
+static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, const plb_ransac_opt &opt,
+                      double max_error, int rfc, double *model, char *inliers, plb_ransac_stats *stats_out,
+                      plb_counters *cnt_out, const FinalPolish &polish) {
+    Engine &E = *engine();
+    const int K = kind_sample_size(kind), MAXM = kind_max_models(kind), MSZ = kind_model_size(kind);
+    plb_ransac_stats stats;
+    stats.refinements = 0;
+    stats.iterations = 0;
+    stats.num_inliers = 0;
+    stats.inlier_ratio = 0;
+    stats.model_score = std::numeric_limits<double>::max();
+    plb_counters cnt;
+    std::memset(&cnt, 0, sizeof(cnt));
+    // ransac.cc:47-50 etc.: identity unless an initial model is scored
+    if (!opt.score_initial_model) {
+        std::fill(model, model + MSZ, 0.0);
+        if (MSZ == 7) model[0] = 1.0;
+        else model[0] = model[4] = model[8] = 1.0;
+    }
+    if (n_pts > (size_t)std::numeric_limits<int>::max() / 64) {
+        g_err = "too many correspondences";
+        return PLB_ERR_ARG;
+    }
+    if (n_pts == 0) {
+        if (stats_out) *stats_out = stats;
+        if (cnt_out) *cnt_out = cnt;
+        return PLB_OK;
+    }
+    int rc = E.init();
+    if (rc != PLB_OK) return rc;
+    const uint64_t launches0 = E.launches;
+    cudaStream_t st = E.stream;
+    const int n = (int)n_pts;
+    const int n_pad = (n + 31) & ~31;
+    const int b_dim = (kind == KIND_PNP) ? 3 : 2;
+    const int n_arr = 2 + b_dim;
+
+    // ---- upload (pinned staging) + layout transform ---------------------------------------------------------
+    if ((rc = E.h_in_a.ensure(2 * (size_t)n)) || (rc = E.h_in_b.ensure((size_t)b_dim * n)) ||
+        (rc = E.in_a.ensure(2 * (size_t)n)) || (rc = E.in_b.ensure((size_t)b_dim * n)) ||
+        (rc = E.soa64.ensure((size_t)n_arr * n_pad)) || (rc = E.soa32.ensure((size_t)n_arr * n_pad)) ||
+        (rc = E.mask.ensure(n)) || (rc = E.h_mask.ensure(n)) || (rc = E.work.ensure(4)) ||
+        (rc = E.model_dev.ensure(16)) || (rc = E.h_model.ensure(16)))
+        return rc;
+    std::memcpy(E.h_in_a.p, a, sizeof(double) * 2 * n);
+    std::memcpy(E.h_in_b.p, b, sizeof(double) * b_dim * n);
+    PLB_CUDA(cudaMemcpyAsync(E.in_a.p, E.h_in_a.p, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+    PLB_CUDA(cudaMemcpyAsync(E.in_b.p, E.h_in_b.p, sizeof(double) * b_dim * n, cudaMemcpyHostToDevice, st));
+    launch_transpose(E.in_a.p, E.in_b.p, n, b_dim, E.soa64.p, E.soa32.p, n_pad, st);
+    E.launches++;
+    ProblemDev P;
+    std::memset(&P, 0, sizeof(P));
+    for (int c = 0; c < n_arr; ++c) {
+        P.p[c] = E.soa64.p + (size_t)c * n_pad;
+        P.f[c] = E.soa32.p + (size_t)c * n_pad;
+    }
+    P.n = n;
+    P.kind = kind;
+    P.sq_thr = max_error * max_error;
+    P.rfc = rfc;
+
+    const LmParams lo = lo_params(kind, max_error);
+    auto t_lo = std::chrono::steady_clock::now();
+    double lo_wait = 0.0;
+    float gpu_ms_total = 0.f;
+
+    // ---- serial state (ransac_impl.h:99-104,165-171) --------------------------------------------------------
+    size_t best_minimal_inlier_count = 0;
+    double best_minimal_msac_score = std::numeric_limits<double>::max();
+    size_t dynamic_max_iter = opt.max_iterations;
+    const double log_prob_missing_model = std::log(1.0 - opt.success_prob);
+    double best_model[9];
+    std::copy(model, model + MSZ, best_model);
+    const bool enough = n_pts >= (size_t)K; // ransac_impl.h:161-163
+
+    // Runs LM jobs on `njobs` models staged in E.h_lm_in (9 doubles each) and returns with E.h_lm_out filled.
+    auto run_lm_host_models = [&](int njobs, const LmParams &prm, const char *mask_dev, const ProblemDev &PP) -> int {
+        int r;
+        if ((r = E.lm_in.ensure(9 * (size_t)njobs)) || (r = E.lm_out.ensure(njobs)) || (r = E.h_lm_out.ensure(njobs)))
+            return r;
+        if (prm.subset_mode == 1 && (r = E.subset.ensure((size_t)njobs * n))) return r;
+        PLB_CUDA(cudaMemcpyAsync(E.lm_in.p, E.h_lm_in.p, sizeof(double) * 9 * njobs, cudaMemcpyHostToDevice, st));
+        launch_lm(PP, E.lm_in.p, njobs, prm, mask_dev, E.subset.p, E.lm_out.p, st);
+        E.launches++;
+        PLB_CUDA(cudaMemcpyAsync(E.h_lm_out.p, E.lm_out.p, sizeof(LmJobOut) * njobs, cudaMemcpyDeviceToHost, st));
+        auto t0 = std::chrono::steady_clock::now();
+        PLB_CUDA(cudaStreamSynchronize(st));
+        lo_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return PLB_OK;
+    };
+
+    // score_models() for ONE iteration given its records (ransac_impl.h:106-154).
+    //   cnts/scs: per-model records; mdl(i): pointer to model i; lo_result: LmJobOut of the refined last-improving model
+    auto update_dynamic = [&]() {
+        stats.inlier_ratio = static_cast<double>(stats.num_inliers) / static_cast<double>(n_pts);
+        dynamic_max_iter = compute_dynamic_max_iter(stats.num_inliers, n_pts, (size_t)K, log_prob_missing_model,
+                                                    opt.dyn_num_trials_mult, opt.min_iterations, opt.max_iterations);
+    };
+
+    if (enough) {
+        if ((rc = E.h_lm_in.ensure(9 * 64))) return rc;
+        // ---- initial model (ransac_impl.h:173-176) -----------------------------------------------------------
+        if (opt.score_initial_model) {
+            std::copy(model, model + MSZ, E.h_model.p);
+            PLB_CUDA(cudaMemcpyAsync(E.model_dev.p, E.h_model.p, sizeof(double) * MSZ, cudaMemcpyHostToDevice, st));
+            if ((rc = E.counts.ensure(64)) || (rc = E.scores.ensure(64)) || (rc = E.h_counts.ensure(64)) ||
+                (rc = E.h_scores.ensure(64)))
+                return rc;
+            launch_score_models(P, E.model_dev.p, 1, E.counts.p, E.scores.p, st);
+            E.launches++;
+            PLB_CUDA(cudaMemcpyAsync(E.h_counts.p, E.counts.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            PLB_CUDA(cudaMemcpyAsync(E.h_scores.p, E.scores.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+            PLB_CUDA(cudaStreamSynchronize(st));
+            const size_t ic = E.h_counts.p[0];
+            const double sc = E.h_scores.p[0];
+            cnt.hypotheses++;
+            const bool more = ic > best_minimal_inlier_count, better = sc < best_minimal_msac_score;
+            if (more || better) {
+                if (more) best_minimal_inlier_count = ic;
+                if (better) best_minimal_msac_score = sc;
+                if (sc < stats.model_score) {
+                    stats.model_score = sc;
+                    stats.num_inliers = ic;
+                }
+                std::fill(E.h_lm_in.p, E.h_lm_in.p + 9, 0.0);
+                std::copy(model, model + MSZ, E.h_lm_in.p);
+                if ((rc = run_lm_host_models(1, lo, nullptr, P))) return rc;
+                stats.refinements++;
+                cnt.lo_calls++;
+                cnt.hypotheses++;
+                const LmJobOut &o = E.h_lm_out.p[0];
+                if (o.score < stats.model_score) {
+                    stats.model_score = o.score;
+                    stats.num_inliers = o.count;
+                    std::copy(o.model, o.model + MSZ, best_model);
+                }
+                update_dynamic();
+            }
+        }
+
+        // ---- main loop in rounds ---------------------------------------------------------------------------
+        Sampler sampler(n_pts, (size_t)K, opt);
+        size_t it = 0;
+        size_t chunk = 1024;
+        const size_t CHUNK_MAX = 16384;
+        bool broke = false;
+        std::vector<int> imp_slot;   // slots (s*MAXM+m) of improving models in this round
+        std::vector<int> imp_sample; // their sample index within the round
+        std::vector<int> trig;       // indices into imp_* that are the last improving model of their sample
+        while (!broke && it < opt.max_iterations) {
+            // break test at the top of iteration `it` (ransac_impl.h:182); the serial loop stops at the first
+            // it with it > min_it && it > dyn, i.e. at stop_at for the current dyn
+            if (it > opt.min_iterations && it > dynamic_max_iter) {
+                broke = true;
+                break;
+            }
+            const size_t stop_at = std::min<size_t>(opt.max_iterations, std::max(opt.min_iterations, dynamic_max_iter) + 1);
+            size_t B = std::min(chunk, CHUNK_MAX);
+            B = std::min(B, stop_at - it); // stop_at > it here
+
+            chunk = std::min(CHUNK_MAX, chunk * 2);
+
+            if ((rc = E.h_samples.ensure(B * K)) || (rc = E.samples.ensure(B * K)) || (rc = E.n_models.ensure(B)) ||
+                (rc = E.h_n_models.ensure(B)) || (rc = E.counts.ensure(B * MAXM)) || (rc = E.scores.ensure(B * MAXM)) ||
+                (rc = E.h_counts.ensure(B * MAXM)) || (rc = E.h_scores.ensure(B * MAXM)) ||
+                (rc = E.models.ensure(B * MAXM * MSZ)))
+                return rc;
+            for (size_t s = 0; s < B; ++s) sampler.next(E.h_samples.p + s * K);
+            PLB_CUDA(cudaMemcpyAsync(E.samples.p, E.h_samples.p, sizeof(uint32_t) * B * K, cudaMemcpyHostToDevice, st));
+            HypOut out;
+            out.n_models = E.n_models.p;
+            out.counts = E.counts.p;
+            out.scores = E.scores.p;
+            out.models = E.models.p;
+            out.fscores = nullptr;
+            out.fcounts = nullptr;
+            PLB_CUDA(cudaEventRecord(E.ev0, st));
+            launch_hypotheses(P, E.samples.p, (int)B, E.work.p, out, g_mode.load(), st);
+            PLB_CUDA(cudaEventRecord(E.ev1, st));
+            E.launches++;
+            PLB_CUDA(cudaMemcpyAsync(E.h_n_models.p, E.n_models.p, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+            PLB_CUDA(cudaMemcpyAsync(E.h_counts.p, E.counts.p, sizeof(uint32_t) * B * MAXM, cudaMemcpyDeviceToHost, st));
+            PLB_CUDA(cudaMemcpyAsync(E.h_scores.p, E.scores.p, sizeof(double) * B * MAXM, cudaMemcpyDeviceToHost, st));
+            PLB_CUDA(cudaStreamSynchronize(st));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, E.ev0, E.ev1);
+            gpu_ms_total += ms;
+            cnt.samples_evaluated += B;
+
+            // ---- pass 1: which models improve the best-minimal state?  (independent of LO results)
+            imp_slot.clear();
+            imp_sample.clear();
+            trig.clear();
+            {
+                size_t bc = best_minimal_inlier_count;
+                double bs = best_minimal_msac_score;
+                for (size_t s = 0; s < B; ++s) {
+                    const int nm = E.h_n_models.p[s];
+                    int last = -1;
+                    for (int m = 0; m < nm; ++m) {
+                        const size_t slot = s * MAXM + m;
+                        const size_t ic = E.h_counts.p[slot];
+                        const double sc = E.h_scores.p[slot];
+                        const bool more = ic > bc, better = sc < bs;
+                        if (more || better) {
+                            if (more) bc = ic;
+                            if (better) bs = sc;
+                            imp_slot.push_back((int)slot);
+                            imp_sample.push_back((int)s);
+                            last = (int)imp_slot.size() - 1;
+                        }
+                    }
+                    if (last >= 0) trig.push_back(last);
+                }
+            }
+            const int n_imp = (int)imp_slot.size(), n_trig = (int)trig.size();
+            if (n_imp > 0) {
+                // gather improving models, refine the trigger models (batched LO), fetch both
+                if ((rc = E.h_slots.ensure(n_imp + n_trig)) || (rc = E.slots.ensure(n_imp + n_trig)) ||
+                    (rc = E.lm_in.ensure(9 * (size_t)(n_imp + n_trig))) || (rc = E.h_lm_in.ensure(9 * (size_t)(n_imp + n_trig))) ||
+                    (rc = E.lm_out.ensure(n_trig)) || (rc = E.h_lm_out.ensure(n_trig)))
+                    return rc;
+                for (int i = 0; i < n_imp; ++i) E.h_slots.p[i] = imp_slot[i];
+                for (int j = 0; j < n_trig; ++j) E.h_slots.p[n_imp + j] = imp_slot[trig[j]];
+                PLB_CUDA(cudaMemcpyAsync(E.slots.p, E.h_slots.p, sizeof(int) * (n_imp + n_trig), cudaMemcpyHostToDevice, st));
+                const int tot = 9 * (n_imp + n_trig);
+                k_gather_models<<<(tot + 127) / 128, 128, 0, st>>>(E.models.p, E.slots.p, n_imp + n_trig, MSZ, E.lm_in.p);
+                E.launches++;
+                PLB_CUDA(cudaMemcpyAsync(E.h_lm_in.p, E.lm_in.p, sizeof(double) * 9 * n_imp, cudaMemcpyDeviceToHost, st));
+                if (lo.subset_mode == 1 && (rc = E.subset.ensure((size_t)n_trig * n))) return rc;
+                launch_lm(P, E.lm_in.p + 9 * (size_t)n_imp, n_trig, lo, nullptr, E.subset.p, E.lm_out.p, st);
+                E.launches++;
+                PLB_CUDA(cudaMemcpyAsync(E.h_lm_out.p, E.lm_out.p, sizeof(LmJobOut) * n_trig, cudaMemcpyDeviceToHost, st));
+                auto t0 = std::chrono::steady_clock::now();
+                PLB_CUDA(cudaStreamSynchronize(st));
+                lo_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            }
+
+            // ---- pass 2: replay the serial loop over this round ------------------------------------------------
+            int ip = 0, tp = 0; // cursors into imp_* / trig
+            for (size_t s = 0; s < B; ++s, ++it) {
+                if (it > opt.min_iterations && it > dynamic_max_iter) { // ransac_impl.h:182-184
+                    broke = true;
+                    break;
+                }
+                const int nm = E.h_n_models.p[s];
+                cnt.samples++;
+                cnt.hypotheses += nm;
+                bool any = false;
+                while (ip < n_imp && imp_sample[ip] == (int)s) {
+                    const size_t slot = imp_slot[ip];
+                    const size_t ic = E.h_counts.p[slot];
+                    const double sc = E.h_scores.p[slot];
+                    // (more_inliers || better_score) holds by construction; state update as in :117-124
+                    if (ic > best_minimal_inlier_count) best_minimal_inlier_count = ic;
+                    if (sc < best_minimal_msac_score) best_minimal_msac_score = sc;
+                    if (sc < stats.model_score) { // :127-131
+                        stats.model_score = sc;
+                        std::copy(E.h_lm_in.p + 9 * ip, E.h_lm_in.p + 9 * ip + MSZ, best_model);
+                        stats.num_inliers = ic;
+                    }
+                    any = true;
+                    ++ip;
+                }
+                if (any) { // :135-153
+                    const LmJobOut &o = E.h_lm_out.p[tp++];
+                    stats.refinements++;
+                    cnt.lo_calls++;
+                    cnt.hypotheses++;
+                    if (o.score < stats.model_score) {
+                        stats.model_score = o.score;
+                        stats.num_inliers = o.count;
+                        std::copy(o.model, o.model + MSZ, best_model);
+                    }
+                    update_dynamic();
+                }
+            }
+        }
+        stats.iterations = it;
+
+        // ---- final refinement (ransac_impl.h:190-198) ----------------------------------------------------------
+        std::fill(E.h_lm_in.p, E.h_lm_in.p + 9, 0.0);
+        std::copy(best_model, best_model + MSZ, E.h_lm_in.p);
+        if ((rc = run_lm_host_models(1, lo, nullptr, P))) return rc;
+        stats.refinements++;
+        cnt.lo_calls++;
+        cnt.hypotheses++;
+        {
+            const LmJobOut &o = E.h_lm_out.p[0];
+            if (o.score < stats.model_score) { // NB: model_score itself is not updated by the reference here
+                std::copy(o.model, o.model + MSZ, best_model);
+                stats.num_inliers = o.count;
+            }
+        }
+    }
+    (void)t_lo;
+
+    // ---- final inlier mask (ransac.cc:54,151,259,311) -----------------------------------------------------------
+    std::copy(best_model, best_model + MSZ, E.h_model.p);
+    PLB_CUDA(cudaMemcpyAsync(E.model_dev.p, E.h_model.p, sizeof(double) * MSZ, cudaMemcpyHostToDevice, st));
+    launch_inlier_mask(P, E.model_dev.p, P.sq_thr, E.mask.p, st);
+    E.launches++;
+    const bool do_polish = polish.enabled && stats.num_inliers > polish.min_inliers;
+    if (do_polish) {
+        // robust.cc:103-123,296-311,573-588,736-751: LM over the inliers with the user's BundleOptions
+        LmParams bp = bundle_params(polish.bundle);
+        ProblemDev PP = P;
+        if (kind == KIND_PNP && polish.px_scaled) {
+            if ((rc = E.px64.ensure(2 * (size_t)n_pad))) return rc;
+            // stage scaled pixels as SoA (host transposes: O(N) once)
+            if ((rc = E.h_in_a.ensure(2 * (size_t)n_pad))) return rc;
+            for (int k = 0; k < n; ++k) {
+                E.h_in_a.p[k] = polish.px_scaled[2 * k];
+                E.h_in_a.p[n_pad + k] = polish.px_scaled[2 * k + 1];
+            }
+            PLB_CUDA(cudaMemcpyAsync(E.px64.p, E.h_in_a.p, sizeof(double) * 2 * n_pad, cudaMemcpyHostToDevice, st));
+            PP.p[0] = E.px64.p;
+            PP.p[1] = E.px64.p + n_pad;
+            bp.use_camera = 1;
+            for (int i = 0; i < 4; ++i) bp.cam[i] = polish.cam[i];
+        }
+        if ((rc = E.lm_in.ensure(9)) || (rc = E.lm_out.ensure(1)) || (rc = E.h_lm_out.ensure(1))) return rc;
+        std::fill(E.h_lm_in.p, E.h_lm_in.p + 9, 0.0);
+        std::copy(best_model, best_model + MSZ, E.h_lm_in.p);
+        PLB_CUDA(cudaMemcpyAsync(E.lm_in.p, E.h_lm_in.p, sizeof(double) * 9, cudaMemcpyHostToDevice, st));
+        launch_lm(PP, E.lm_in.p, 1, bp, E.mask.p, nullptr, E.lm_out.p, st);
+        E.launches++;
+        PLB_CUDA(cudaMemcpyAsync(E.h_lm_out.p, E.lm_out.p, sizeof(LmJobOut), cudaMemcpyDeviceToHost, st));
+    }
+    PLB_CUDA(cudaMemcpyAsync(E.h_mask.p, E.mask.p, n, cudaMemcpyDeviceToHost, st));
+    PLB_CUDA(cudaStreamSynchronize(st));
+    if (do_polish) std::copy(E.h_lm_out.p[0].model, E.h_lm_out.p[0].model + MSZ, best_model);
+    if (inliers) std::memcpy(inliers, E.h_mask.p, n);
+    std::copy(best_model, best_model + MSZ, model);
+
+    cnt.scored_corrs = cnt.hypotheses * n_pts;
+    cnt.lo_seconds = lo_wait;
+    cnt.gpu_launches = E.launches - launches0;
+    cnt.gpu_seconds = gpu_ms_total * 1e-3;
+    if (stats_out) *stats_out = stats;
+    if (cnt_out) *cnt_out = cnt;
+    return PLB_OK;
+}
+
+// ---- small host-side 3x3 helpers for the estimate_* wrappers (column-major <-> row-major) ---------------------
+struct HM3 {
+    double m[3][3];
+};
+static HM3 hm_identity() {
+    HM3 r;
+    std::memset(&r, 0, sizeof(r));
+    r.m[0][0] = r.m[1][1] = r.m[2][2] = 1;
+    return r;
+}
+static HM3 hm_mul(const HM3 &A, const HM3 &B) {
+    HM3 C;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C.m[i][j] = A.m[i][0] * B.m[0][j] + A.m[i][1] * B.m[1][j] + A.m[i][2] * B.m[2][j];
+    return C;
+}
+static HM3 hm_T(const HM3 &A) {
+    HM3 C;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C.m[i][j] = A.m[j][i];
+    return C;
+}
+static HM3 hm_inv(const HM3 &M) {
+    const double(*m)[3] = M.m;
+    HM3 c;
+    c.m[0][0] = m[1][1] * m[2][2] - m[1][2] * m[2][1];
+    c.m[1][0] = m[1][2] * m[2][0] - m[1][0] * m[2][2];
+    c.m[2][0] = m[1][0] * m[2][1] - m[1][1] * m[2][0];
+    c.m[0][1] = m[0][2] * m[2][1] - m[0][1] * m[2][2];
+    c.m[1][1] = m[0][0] * m[2][2] - m[0][2] * m[2][0];
+    c.m[2][1] = m[0][1] * m[2][0] - m[0][0] * m[2][1];
+    c.m[0][2] = m[0][1] * m[1][2] - m[0][2] * m[1][1];
+    c.m[1][2] = m[0][2] * m[1][0] - m[0][0] * m[1][2];
+    c.m[2][2] = m[0][0] * m[1][1] - m[0][1] * m[1][0];
+    const double det = c.m[0][0] * m[0][0] + c.m[1][0] * m[0][1] + c.m[2][0] * m[0][2];
+    const double id = 1.0 / det;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) c.m[i][j] *= id;
+    return c;
+}
+static double hm_norm(const HM3 &A) {
+    double s = 0;
+    for (int j = 0; j < 3; ++j)
+        for (int i = 0; i < 3; ++i) s += A.m[i][j] * A.m[i][j];
+    return std::sqrt(s);
+}
+static HM3 hm_from_cm(const double *p) {
+    HM3 r;
+    for (int k = 0; k < 9; ++k) r.m[k % 3][k / 3] = p[k];
+    return r;
+}
+static void hm_to_cm(const HM3 &A, double *p) {
+    for (int k = 0; k < 9; ++k) p[k] = A.m[k % 3][k / 3];
+}
+
+// robust/utils.cc:584-644 (shared scale only; the two in-scope callers pass shared_scale = true)
+static double normalize_points(std::vector<double> &x1, std::vector<double> &x2, size_t n, HM3 &T1, HM3 &T2,
+                               bool normalize_centroid) {
+    T1 = hm_identity();
+    T2 = hm_identity();
+    if (normalize_centroid) {
+        double c1[2] = {0, 0}, c2[2] = {0, 0};
+        for (size_t k = 0; k < n; ++k) {
+            c1[0] += x1[2 * k]; c1[1] += x1[2 * k + 1];
+            c2[0] += x2[2 * k]; c2[1] += x2[2 * k + 1];
+        }
+        c1[0] /= n; c1[1] /= n; c2[0] /= n; c2[1] /= n;
+        T1.m[0][2] = -c1[0]; T1.m[1][2] = -c1[1];
+        T2.m[0][2] = -c2[0]; T2.m[1][2] = -c2[1];
+        for (size_t k = 0; k < n; ++k) {
+            x1[2 * k] -= c1[0]; x1[2 * k + 1] -= c1[1];
+            x2[2 * k] -= c2[0]; x2[2 * k + 1] -= c2[1];
+        }
+    }
+    double scale = 0.0;
+    for (size_t k = 0; k < n; ++k) {
+        scale += std::sqrt(x1[2 * k] * x1[2 * k] + x1[2 * k + 1] * x1[2 * k + 1]);
+        scale += std::sqrt(x2[2 * k] * x2[2 * k] + x2[2 * k + 1] * x2[2 * k + 1]);
+    }
+    scale /= std::sqrt(2) * n;
+    for (size_t k = 0; k < 2 * n; ++k) {
+        x1[k] /= scale;
+        x2[k] /= scale;
+    }
+    for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 3; ++c) {
+            T1.m[r][c] *= 1.0 / scale;
+            T2.m[r][c] *= 1.0 / scale;
+        }
+    return scale;
+}
+
+// Camera::unproject + hnormalized for the pinhole family (misc/camera_models.cc:176-188,668-761; .h:98-102)
+static int camera_params(const plb_camera *c, double out[4]) {
+    if (!c) {
+        out[0] = out[1] = 1; out[2] = out[3] = 0;
+        return PLB_OK;
+    }
+    switch (c->model_id) {
+    case PLB_CAMERA_NULL: out[0] = out[1] = 1; out[2] = out[3] = 0; return PLB_OK;
+    case PLB_CAMERA_SIMPLE_PINHOLE: out[0] = out[1] = c->params[0]; out[2] = c->params[1]; out[3] = c->params[2]; return PLB_OK;
+    case PLB_CAMERA_PINHOLE: out[0] = c->params[0]; out[1] = c->params[1]; out[2] = c->params[2]; out[3] = c->params[3]; return PLB_OK;
+    default: g_err = "NYI: camera model not supported by the B200 path (undistort on the host first)"; return PLB_ERR_NYI;
+    }
+}
+static double camera_focal(const plb_camera *c, const double cp[4]) { // Camera::focal() camera_models.cc:304-324
+    if (!c || c->model_id == PLB_CAMERA_NULL) return 1.0;
+    if (c->model_id == PLB_CAMERA_SIMPLE_PINHOLE) return 0.0 + cp[0] / 1;
+    return 0.0 + cp[0] / 2 + cp[1] / 2;
+}
+
+} // namespace plb
+
+using namespace plb;
+
+extern "C" {
+
+void plb_ransac_opt_default(plb_ransac_opt *o) {
+    o->max_iterations = 100000;
+    o->min_iterations = 1000;
+    o->dyn_num_trials_mult = 3.0;
+    o->success_prob = 0.9999;
+    o->seed = 0;
+    o->progressive_sampling = 0;
+    o->score_initial_model = 0;
+    o->max_prosac_iterations = 100000;
+}
+void plb_bundle_opt_default(plb_bundle_opt *o) {
+    o->max_iterations = 100;
+    o->loss_type = PLB_LOSS_CAUCHY;
+    o->reserved = 0;
+    o->loss_scale = 1.0;
+    o->gradient_tol = 1e-12;
+    o->step_tol = 1e-8;
+    o->relative_cost_tol = 1e-10;
+    o->initial_lambda = 1e-3;
+    o->min_lambda = 1e-10;
+    o->max_lambda = 1e10;
+}
+const char *plb_last_error(void) { return g_err.c_str(); }
+int plb_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return c;
+}
+int plb_set_device(int device) {
+    if (device < 0) {
+        g_err = "negative device index";
+        return PLB_ERR_ARG;
+    }
+    g_device = device;
+    return PLB_OK;
+}
+int plb_set_mode(int mode) {
+    if (mode != 0 && mode != 1) {
+        g_err = "mode must be 0 (exact) or 1 (fast)";
+        return PLB_ERR_ARG;
+    }
+    g_mode.store(mode);
+    return PLB_OK;
+}
+
+static int check_ptrs(const void *a, const void *b, const void *opt, const void *model, size_t n) {
+    if (!opt || !model || (n > 0 && (!a || !b))) {
+        g_err = "null argument";
+        return PLB_ERR_ARG;
+    }
+    return PLB_OK;
+}
+
+int plb_ransac_pnp(const double *x, const double *X, size_t n, const plb_ransac_opt *opt, double max_error,
+                   double pose[7], char *inliers, plb_ransac_stats *stats, plb_counters *counters) {
+    if (int r = check_ptrs(x, X, opt, pose, n)) return r;
+    return run_ransac(KIND_PNP, x, X, n, *opt, max_error, 0, pose, inliers, stats, counters, FinalPolish());
+}
+int plb_ransac_relpose(const double *x1, const double *x2, size_t n, const plb_ransac_opt *opt, double max_error,
+                       double pose[7], char *inliers, plb_ransac_stats *stats, plb_counters *counters) {
+    if (int r = check_ptrs(x1, x2, opt, pose, n)) return r;
+    return run_ransac(KIND_RELPOSE, x1, x2, n, *opt, max_error, 0, pose, inliers, stats, counters, FinalPolish());
+}
+int plb_ransac_fundamental(const double *x1, const double *x2, size_t n, const plb_ransac_opt *opt, double max_error,
+                           int real_focal_check, double F[9], char *inliers, plb_ransac_stats *stats,
+                           plb_counters *counters) {
+    if (int r = check_ptrs(x1, x2, opt, F, n)) return r;
+    return run_ransac(KIND_FUND, x1, x2, n, *opt, max_error, real_focal_check, F, inliers, stats, counters,
+                      FinalPolish());
+}
+int plb_ransac_homography(const double *x1, const double *x2, size_t n, const plb_ransac_opt *opt, double max_error,
+                          double H[9], char *inliers, plb_ransac_stats *stats, plb_counters *counters) {
+    if (int r = check_ptrs(x1, x2, opt, H, n)) return r;
+    return run_ransac(KIND_HOMOG, x1, x2, n, *opt, max_error, 0, H, inliers, stats, counters, FinalPolish());
+}
+
+// PoseLib/robust.cc:36-126 (no focal estimation)
+int plb_estimate_absolute_pose(const double *points2D, const double *points3D, size_t n, const plb_ransac_opt *ransac,
+                               const plb_bundle_opt *bundle, double max_error, const plb_camera *camera,
+                               double pose[7], char *inliers, plb_ransac_stats *stats, plb_counters *counters) {
+    if (int r = check_ptrs(points2D, points3D, ransac, pose, n)) return r;
+    if (!bundle) {
+        g_err = "null bundle options";
+        return PLB_ERR_ARG;
+    }
+    double cp[4];
+    if (int r = camera_params(camera, cp)) return r;
+    std::vector<double> norm(2 * n), px(2 * n);
+    for (size_t k = 0; k < n; ++k) {
+        norm[2 * k] = (points2D[2 * k] - cp[2]) / cp[0];
+        norm[2 * k + 1] = (points2D[2 * k + 1] - cp[3]) / cp[1];
+    }
+    const double scale = 1.0 / camera_focal(camera, cp);
+    FinalPolish fp;
+    fp.enabled = true;
+    fp.bundle = *bundle;
+    fp.bundle.loss_scale = bundle->loss_scale * scale;
+    fp.min_inliers = 3;
+    for (size_t k = 0; k < 2 * n; ++k) px[k] = points2D[k] * scale;
+    fp.px_scaled = px.data();
+    for (int i = 0; i < 4; ++i) fp.cam[i] = cp[i] * scale; // Camera::rescale (camera_models.cc:432-454)
+    if (camera == nullptr || camera->model_id == PLB_CAMERA_NULL) {
+        fp.cam[0] = fp.cam[1] = 1.0; // empty params: rescale is a no-op and the null projection is used
+        fp.cam[2] = fp.cam[3] = 0.0;
+        fp.px_scaled = nullptr;
+    }
+    return run_ransac(KIND_PNP, norm.data(), points3D, n, *ransac, max_error * scale, 0, pose, inliers, stats,
+                      counters, fp);
+}
+// PoseLib/robust.cc:242-314 (tangent_sampson == false)
+int plb_estimate_relative_pose(const double *x1, const double *x2, size_t n, const plb_camera *camera1,
+                               const plb_camera *camera2, const plb_ransac_opt *ransac, const plb_bundle_opt *bundle,
+                               double max_error, double pose[7], char *inliers, plb_ransac_stats *stats,
+                               plb_counters *counters) {
+    if (int r = check_ptrs(x1, x2, ransac, pose, n)) return r;
+    if (!bundle) {
+        g_err = "null bundle options";
+        return PLB_ERR_ARG;
+    }
+    double c1[4], c2[4];
+    if (int r = camera_params(camera1, c1)) return r;
+    if (int r = camera_params(camera2, c2)) return r;
+    const double scale = 0.5 * (1.0 / camera_focal(camera1, c1) + 1.0 / camera_focal(camera2, c2));
+    std::vector<double> a(2 * n), b(2 * n);
+    for (size_t k = 0; k < n; ++k) {
+        a[2 * k] = (x1[2 * k] - c1[2]) / c1[0];
+        a[2 * k + 1] = (x1[2 * k + 1] - c1[3]) / c1[1];
+        b[2 * k] = (x2[2 * k] - c2[2]) / c2[0];
+        b[2 * k + 1] = (x2[2 * k + 1] - c2[3]) / c2[1];
+    }
+    FinalPolish fp;
+    fp.enabled = true;
+    fp.bundle = *bundle;
+    fp.bundle.loss_scale = bundle->loss_scale * scale;
+    fp.min_inliers = 5;
+    return run_ransac(KIND_RELPOSE, a.data(), b.data(), n, *ransac, max_error * scale, 0, pose, inliers, stats,
+                      counters, fp);
+}
+// PoseLib/robust.cc:544-594
+int plb_estimate_fundamental(const double *x1, const double *x2, size_t n, const plb_ransac_opt *ransac,
+                             const plb_bundle_opt *bundle, double max_error, int real_focal_check, double F[9],
+                             char *inliers, plb_ransac_stats *stats, plb_counters *counters) {
+    if (int r = check_ptrs(x1, x2, ransac, F, n)) return r;
+    if (!bundle) {
+        g_err = "null bundle options";
+        return PLB_ERR_ARG;
+    }
+    if (n < 7) {
+        if (stats) {
+            stats->refinements = stats->iterations = stats->num_inliers = 0;
+            stats->inlier_ratio = 0;
+            stats->model_score = std::numeric_limits<double>::max();
+        }
+        if (counters) std::memset(counters, 0, sizeof(*counters));
+        return PLB_OK;
+    }
+    std::vector<double> a(x1, x1 + 2 * n), b(x2, x2 + 2 * n);
+    HM3 T1, T2;
+    const double scale = normalize_points(a, b, n, T1, T2, !real_focal_check);
+    FinalPolish fp;
+    fp.enabled = true;
+    fp.bundle = *bundle;
+    fp.bundle.loss_scale = bundle->loss_scale / scale;
+    fp.min_inliers = 7;
+    if (ransac->score_initial_model) { // robust.cc:566-569
+        HM3 Fm = hm_mul(hm_mul(hm_inv(hm_T(T2)), hm_from_cm(F)), hm_inv(T1));
+        const double nf = hm_norm(Fm);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Fm.m[i][j] /= nf;
+        hm_to_cm(Fm, F);
+    }
+    int rc = run_ransac(KIND_FUND, a.data(), b.data(), n, *ransac, max_error / scale, real_focal_check, F, inliers,
+                        stats, counters, fp);
+    if (rc != PLB_OK) return rc;
+    HM3 Fm = hm_mul(hm_mul(hm_T(T2), hm_from_cm(F)), T1); // robust.cc:590-591
+    const double nf = hm_norm(Fm);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Fm.m[i][j] /= nf;
+    hm_to_cm(Fm, F);
+    return PLB_OK;
+}
+// PoseLib/robust.cc:712-757
+int plb_estimate_homography(const double *x1, const double *x2, size_t n, const plb_ransac_opt *ransac,
+                            const plb_bundle_opt *bundle, double max_error, double H[9], char *inliers,
+                            plb_ransac_stats *stats, plb_counters *counters) {
+    if (int r = check_ptrs(x1, x2, ransac, H, n)) return r;
+    if (!bundle) {
+        g_err = "null bundle options";
+        return PLB_ERR_ARG;
+    }
+    if (n < 4) {
+        if (stats) {
+            stats->refinements = stats->iterations = stats->num_inliers = 0;
+            stats->inlier_ratio = 0;
+            stats->model_score = std::numeric_limits<double>::max();
+        }
+        if (counters) std::memset(counters, 0, sizeof(*counters));
+        return PLB_OK;
+    }
+    std::vector<double> a(x1, x1 + 2 * n), b(x2, x2 + 2 * n);
+    HM3 T1, T2;
+    const double scale = normalize_points(a, b, n, T1, T2, true);
+    FinalPolish fp;
+    fp.enabled = true;
+    fp.bundle = *bundle;
+    fp.bundle.loss_scale = bundle->loss_scale / scale;
+    fp.min_inliers = 4;
+    if (ransac->score_initial_model) { // robust.cc:729-732
+        HM3 Hm = hm_mul(hm_mul(T2, hm_from_cm(H)), hm_inv(T1));
+        const double nh = hm_norm(Hm);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Hm.m[i][j] /= nh;
+        hm_to_cm(Hm, H);
+    }
+    int rc = run_ransac(KIND_HOMOG, a.data(), b.data(), n, *ransac, max_error / scale, 0, H, inliers, stats, counters,
+                        fp);
+    if (rc != PLB_OK) return rc;
+    HM3 Hm = hm_mul(hm_mul(hm_inv(T2), hm_from_cm(H)), T1); // robust.cc:753-754
+    const double nh = hm_norm(Hm);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Hm.m[i][j] /= nh;
+    hm_to_cm(Hm, H);
+    return PLB_OK;
+}
+
+// ---- solvers ------------------------------------------------------------------------------------------------
+static int solver_batch(int kind, int variant, size_t count, const double *a, size_t a_sz, const double *b,
+                        size_t b_sz, double *out, size_t out_sz, int32_t *n_out, int flags) {
+    if (count == 0) return PLB_OK;
+    if (!a || !b || !out || !n_out) {
+        g_err = "null argument";
+        return PLB_ERR_ARG;
+    }
+    Engine &E = *engine();
+    int rc = E.init();
+    if (rc != PLB_OK) return rc;
+    DevBuf<double> da, db, dout;
+    DevBuf<int> dn;
+    if ((rc = da.ensure(count * a_sz)) || (rc = db.ensure(count * b_sz)) || (rc = dout.ensure(count * out_sz)) ||
+        (rc = dn.ensure(count)))
+        return rc;
+    PLB_CUDA(cudaMemcpyAsync(da.p, a, sizeof(double) * count * a_sz, cudaMemcpyHostToDevice, E.stream));
+    PLB_CUDA(cudaMemcpyAsync(db.p, b, sizeof(double) * count * b_sz, cudaMemcpyHostToDevice, E.stream));
+    launch_solver_batch(kind, variant, count, da.p, db.p, dout.p, dn.p, flags, E.stream);
+    E.launches++;
+    PLB_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * count * out_sz, cudaMemcpyDeviceToHost, E.stream));
+    PLB_CUDA(cudaMemcpyAsync(n_out, dn.p, sizeof(int) * count, cudaMemcpyDeviceToHost, E.stream));
+    PLB_CUDA(cudaStreamSynchronize(E.stream));
+    PLB_CUDA(cudaGetLastError());
+    return PLB_OK;
+}
+int plb_p3p_batch(size_t count, const double *x, const double *X, double *poses_out, int32_t *n_out) {
+    return solver_batch(KIND_PNP, 0, count, x, 9, X, 9, poses_out, 28, n_out, 0);
+}
+int plb_relpose_5pt_batch(size_t count, const double *x1, const double *x2, double *E_out, int32_t *n_out) {
+    return solver_batch(KIND_RELPOSE, 0, count, x1, 15, x2, 15, E_out, 90, n_out, 0);
+}
+int plb_relpose_5pt_poses_batch(size_t count, const double *x1, const double *x2, double *poses_out, int32_t *n_out) {
+    return solver_batch(KIND_RELPOSE, 1, count, x1, 15, x2, 15, poses_out, 280, n_out, 0);
+}
+int plb_relpose_7pt_batch(size_t count, const double *x1, const double *x2, double *F_out, int32_t *n_out) {
+    return solver_batch(KIND_FUND, 0, count, x1, 21, x2, 21, F_out, 27, n_out, 0);
+}
+int plb_homography_4pt_batch(size_t count, const double *x1, const double *x2, double *H_out, int32_t *n_out,
+                             int check_cheirality) {
+    return solver_batch(KIND_HOMOG, 0, count, x1, 12, x2, 12, H_out, 9, n_out, check_cheirality);
+}
+
+// ---- batch of problems: `streams` host threads, each with its own engine/stream ------------------------------
+int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
+    if (count == 0) return PLB_OK;
+    if (!problems) {
+        g_err = "null argument";
+        return PLB_ERR_ARG;
+    }
+    if (plb_device_count() == 0) {
+        g_err = "no usable CUDA device";
+        return PLB_ERR_CUDA;
+    }
+    const int nthreads = std::max(1, std::min<int>(streams, (int)count));
+    const int dev = g_device;
+    std::atomic<size_t> next(0);
+    std::atomic<int> first_err(PLB_OK);
+    std::string err_msg;
+    std::mutex mtx;
+    auto work = [&](int tid) {
+        g_device = dev;
+        g_engine = pool_engine((size_t)dev * 1024 + tid);
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= count) break;
+            plb_problem &p = problems[i];
+            int rc;
+            switch (p.kind) {
+            case PLB_KIND_PNP:
+                rc = plb_ransac_pnp(p.a, p.b, p.n, &p.opt, p.max_error, p.model, p.inliers, &p.stats, &p.counters);
+                break;
+            case PLB_KIND_RELPOSE:
+                rc = plb_ransac_relpose(p.a, p.b, p.n, &p.opt, p.max_error, p.model, p.inliers, &p.stats, &p.counters);
+                break;
+            case PLB_KIND_FUNDAMENTAL:
+                rc = plb_ransac_fundamental(p.a, p.b, p.n, &p.opt, p.max_error, p.real_focal_check, p.model, p.inliers,
+                                            &p.stats, &p.counters);
+                break;
+            case PLB_KIND_HOMOGRAPHY:
+                rc = plb_ransac_homography(p.a, p.b, p.n, &p.opt, p.max_error, p.model, p.inliers, &p.stats, &p.counters);
+                break;
+            default: rc = PLB_ERR_ARG; g_err = "unknown problem kind";
+            }
+            p.status = rc;
+            if (rc != PLB_OK) {
+                int exp = PLB_OK;
+                if (first_err.compare_exchange_strong(exp, rc)) {
+                    std::lock_guard<std::mutex> lk(mtx);
+                    err_msg = g_err;
+                }
+            }
+        }
+        g_engine = nullptr; // the pooled engine outlives the thread
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
+    if (first_err.load() != PLB_OK) g_err = err_msg;
+    return first_err.load();
+}
+
+} // extern "C"

@@ -1,0 +1,1265 @@
+// poselib_b200 — CUDA kernels of the LO-RANSAC hot path for sm_100a (B200).
+//
+//   k_transpose        caller AoS doubles -> SoA fp64 (+ fp32 copy) in HBM, coalesced both ways
+//   k_hyp<KIND>        persistent, one warp = one minimal sample: gather -> minimal solve -> MSAC score of every
+//                      model over all correspondences (lanes stride the SoA arrays, warp-shuffle reduction)
+//   k_score_models     exact rescoring of explicit models (initial model, fast-mode confirmation)
+//   k_lm<KIND>         Levenberg-Marquardt refit (LO step + final polish): one CTA per job, block-wide reductions of
+//                      the normal equations, scalar LM logic on thread 0
+//   k_inlier_mask      final inlier masks
+//   k_solver_batch     the solvers/*.h surface: one warp per instance
+//
+// Compiled with -fmad=false (see device_math.cuh).  Reference citations are relative to /root/reference.
+#include "kernels.cuh"
+#include "solvers.cuh"
+
+namespace plb {
+
+// ============================================================================================================
+// layout transform
+// ============================================================================================================
+__global__ void k_transpose(const double *__restrict__ a, const double *__restrict__ b, int n, int b_dim,
+                            double *__restrict__ s64, float *__restrict__ s32, int n_pad) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pad) return;
+    const bool live = k < n;
+    const int idx = live ? k : (n - 1); // pad by repeating the last point (never read by the kernels)
+    const double a0 = a[2 * idx], a1 = a[2 * idx + 1];
+    s64[0 * (size_t)n_pad + k] = a0;
+    s64[1 * (size_t)n_pad + k] = a1;
+    s32[0 * (size_t)n_pad + k] = (float)a0;
+    s32[1 * (size_t)n_pad + k] = (float)a1;
+    for (int c = 0; c < b_dim; ++c) {
+        const double v = b[(size_t)b_dim * idx + c];
+        s64[(2 + c) * (size_t)n_pad + k] = v;
+        s32[(2 + c) * (size_t)n_pad + k] = (float)v;
+    }
+}
+void launch_transpose(const double *in_a, const double *in_b, int n, int b_dim, double *soa64, float *soa32,
+                      int n_pad, cudaStream_t stream) {
+    const int threads = 256;
+    k_transpose<<<(n_pad + threads - 1) / threads, threads, 0, stream>>>(in_a, in_b, n, b_dim, soa64, soa32, n_pad);
+}
+
+// ============================================================================================================
+// exact fp64 MSAC scoring of one model by one warp
+// ============================================================================================================
+template <int KIND> struct ModelCtx;
+
+// reprojection error with z2 <= 0 skip (robust/utils.cc:36-63)
+template <> struct ModelCtx<KIND_PNP> {
+    double P[12];
+    PLB_DEV void init(const double *m) {
+        const m3 R = quat_to_rot(m);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            P[4 * r + 0] = R(r, 0); P[4 * r + 1] = R(r, 1); P[4 * r + 2] = R(r, 2); P[4 * r + 3] = m[4 + r];
+        }
+    }
+};
+// Sampson error + cheirality on candidates under threshold (robust/utils.cc:158-201)
+template <> struct ModelCtx<KIND_RELPOSE> {
+    double E[9];
+    double q[4], t[3];
+    PLB_DEV void init(const double *m) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = m[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) t[i] = m[4 + i];
+        const m3 Em = essential_from_pose(q, t);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) E[i] = Em.a[i];
+    }
+};
+// Sampson error (robust/utils.cc:204-239); model is column-major
+template <> struct ModelCtx<KIND_FUND> {
+    double E[9];
+    PLB_DEV void init(const double *m) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) E[3 * (k % 3) + k / 3] = m[k];
+    }
+};
+// one-way transfer error (robust/utils.cc:300-329); model is column-major
+template <> struct ModelCtx<KIND_HOMOG> {
+    double H[9];
+    PLB_DEV void init(const double *m) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) H[3 * (k % 3) + k / 3] = m[k];
+    }
+};
+
+PLB_DEV double sampson_r2(const double *E, double x1_0, double x1_1, double x2_0, double x2_1) {
+    const double Ex1_0 = E[0] * x1_0 + E[1] * x1_1 + E[2];
+    const double Ex1_1 = E[3] * x1_0 + E[4] * x1_1 + E[5];
+    const double Ex1_2 = E[6] * x1_0 + E[7] * x1_1 + E[8];
+    const double Ex2_0 = E[0] * x2_0 + E[3] * x2_1 + E[6];
+    const double Ex2_1 = E[1] * x2_0 + E[4] * x2_1 + E[7];
+    const double C = x2_0 * Ex1_0 + x2_1 * Ex1_1 + Ex1_2;
+    const double Cx = Ex1_0 * Ex1_0 + Ex1_1 * Ex1_1;
+    const double Cy = Ex2_0 * Ex2_0 + Ex2_1 * Ex2_1;
+    return C * C / (Cx + Cy);
+}
+PLB_DEV double homography_r2(const double *H, double x1_0, double x1_1, double x2_0, double x2_1) {
+    const double Hx1_0 = H[0] * x1_0 + H[1] * x1_1 + H[2];
+    const double Hx1_1 = H[3] * x1_0 + H[4] * x1_1 + H[5];
+    const double inv_Hx1_2 = 1.0 / (H[6] * x1_0 + H[7] * x1_1 + H[8]);
+    const double r0 = Hx1_0 * inv_Hx1_2 - x2_0;
+    const double r1 = Hx1_1 * inv_Hx1_2 - x2_1;
+    return r0 * r0 + r1 * r1;
+}
+
+// Returns (count, score) of `model` over all correspondences; the result is identical on every lane.
+// The summation order (lane-strided partial sums, xor-butterfly) is fixed, so the same model always gets the same
+// score bits wherever it is scored (hypothesis kernel, LO kernel, explicit rescoring).
+template <int KIND>
+PLB_DEV void warp_score(const ProblemDev &P, const double *model, double sq_thr, int lane, uint32_t &count_out,
+                        double &score_out) {
+    ModelCtx<KIND> C;
+    C.init(model);
+    const int n = P.n;
+    uint32_t cnt = 0;
+    double score = 0.0;
+    if (KIND == KIND_PNP) {
+        const double *__restrict__ xx = P.p[0], *__restrict__ xy = P.p[1];
+        const double *__restrict__ Xx = P.p[2], *__restrict__ Xy = P.p[3], *__restrict__ Xz = P.p[4];
+        const double *Pm = reinterpret_cast<const double *>(&C);
+        for (int k = lane; k < n; k += 32) {
+            const double X0 = Xx[k], X1 = Xy[k], X2 = Xz[k];
+            const double x0 = xx[k], x1 = xy[k];
+            const double z0 = Pm[0] * X0 + Pm[1] * X1 + Pm[2] * X2 + Pm[3];
+            const double z1 = Pm[4] * X0 + Pm[5] * X1 + Pm[6] * X2 + Pm[7];
+            const double z2 = Pm[8] * X0 + Pm[9] * X1 + Pm[10] * X2 + Pm[11];
+            if (z2 <= 0.0) continue;
+            const double inv_z2 = 1.0 / z2;
+            const double r_0 = z0 * inv_z2 - x0;
+            const double r_1 = z1 * inv_z2 - x1;
+            const double r_sq = r_0 * r_0 + r_1 * r_1;
+            if (r_sq < sq_thr) {
+                ++cnt;
+                score += r_sq;
+            }
+        }
+        cnt = warp_sum_u(cnt);
+        score = warp_sum(score);
+        score += (double)(n - (int)cnt) * sq_thr;
+    } else {
+        const double *__restrict__ ax = P.p[0], *__restrict__ ay = P.p[1];
+        const double *__restrict__ bx = P.p[2], *__restrict__ by = P.p[3];
+        const double *M = reinterpret_cast<const double *>(&C); // first 9 doubles: E / F / H row-major
+        for (int k = lane; k < n; k += 32) {
+            const double x1_0 = ax[k], x1_1 = ay[k], x2_0 = bx[k], x2_1 = by[k];
+            double r2;
+            if (KIND == KIND_HOMOG) r2 = homography_r2(M, x1_0, x1_1, x2_0, x2_1);
+            else r2 = sampson_r2(M, x1_0, x1_1, x2_0, x2_1);
+            bool inl = r2 < sq_thr;
+            if (KIND == KIND_RELPOSE) {
+                if (inl) inl = cheirality_ok(M + 9, M + 13, bearing(x1_0, x1_1), bearing(x2_0, x2_1), 0.01);
+            }
+            if (inl) {
+                ++cnt;
+                score += r2;
+            } else {
+                score += sq_thr;
+            }
+        }
+        cnt = warp_sum_u(cnt);
+        score = warp_sum(score);
+    }
+    count_out = cnt;
+    score_out = score;
+}
+
+// ============================================================================================================
+// fused hypothesis kernel
+// ============================================================================================================
+constexpr int HYP_WARPS = 8;
+
+template <int KIND> struct HypScratch;
+template <> struct HypScratch<KIND_PNP> {
+    double models[4 * 7];
+};
+template <> struct HypScratch<KIND_RELPOSE> {
+    Scratch5 s5;
+    double xs[30]; // x1s[15], x2s[15]
+    double models[40 * 7];
+};
+template <> struct HypScratch<KIND_FUND> {
+    Scratch7 s7;
+    double xs[42];
+    double models[3 * 9];
+};
+template <> struct HypScratch<KIND_HOMOG> {
+    double models[9];
+};
+
+// Gathers the sample and runs the minimal solver; models land in W->models.  Returns the number of models.
+template <int KIND>
+PLB_DEV int warp_generate_models(const ProblemDev &P, const uint32_t *sample, HypScratch<KIND> *W,
+                                 const MonoTables *T, int lane) {
+    if (KIND == KIND_PNP) {
+        d3 xs[3], Xs[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const uint32_t id = sample[i];
+            xs[i] = bearing(P.p[0][id], P.p[1][id]);
+            Xs[i] = mk(P.p[2][id], P.p[3][id], P.p[4][id]);
+        }
+        return solve_p3p(xs, Xs, reinterpret_cast<double *>(W), lane);
+    } else if (KIND == KIND_HOMOG) {
+        d3 a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t id = sample[i];
+            a[i] = bearing(P.p[0][id], P.p[1][id]);
+            b[i] = bearing(P.p[2][id], P.p[3][id]);
+        }
+        return solve_h4(a, b, reinterpret_cast<double *>(W), lane, true);
+    } else if (KIND == KIND_RELPOSE) {
+        HypScratch<KIND_RELPOSE> *S = reinterpret_cast<HypScratch<KIND_RELPOSE> *>(W);
+        if (lane < 10) {
+            const int i = lane % 5, side = lane / 5;
+            const uint32_t id = sample[i];
+            const d3 v = bearing(P.p[2 * side][id], P.p[2 * side + 1][id]);
+            double *o = S->xs + 15 * side + 3 * i;
+            o[0] = v.x; o[1] = v.y; o[2] = v.z;
+        }
+        __syncwarp();
+        return solve_5pt_poses(S->xs, S->xs + 15, &S->s5, T, S->models, lane);
+    } else {
+        HypScratch<KIND_FUND> *S = reinterpret_cast<HypScratch<KIND_FUND> *>(W);
+        if (lane < 14) {
+            const int i = lane % 7, side = lane / 7;
+            const uint32_t id = sample[i];
+            const d3 v = bearing(P.p[2 * side][id], P.p[2 * side + 1][id]);
+            double *o = S->xs + 21 * side + 3 * i;
+            o[0] = v.x; o[1] = v.y; o[2] = v.z;
+        }
+        __syncwarp();
+        int nm = solve_7pt(S->xs, S->xs + 21, &S->s7, S->models, lane);
+        if (P.rfc) {
+            // estimators/relative_pose.cc:393-398: drop models failing the real-focal check, order preserved
+            bool keep = false;
+            double f[9];
+            if (lane < nm) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) f[k] = S->models[9 * lane + k];
+                keep = rfc_ok(f);
+            }
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();
+            if (keep) {
+                const int pos = __popc(km & ((1u << lane) - 1u));
+#pragma unroll
+                for (int k = 0; k < 9; ++k) S->models[9 * pos + k] = f[k];
+            }
+            __syncwarp();
+            nm = __popc(km);
+        }
+        return nm;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(HYP_WARPS * 32)
+    k_hyp(const ProblemDev P, const uint32_t *__restrict__ samples, int n_samples, int *work_counter, HypOut out) {
+    constexpr int K = (KIND == KIND_PNP) ? 3 : (KIND == KIND_RELPOSE) ? 5 : (KIND == KIND_FUND) ? 7 : 4;
+    constexpr int MAXM = (KIND == KIND_PNP) ? 4 : (KIND == KIND_RELPOSE) ? 40 : (KIND == KIND_FUND) ? 3 : 1;
+    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MonoTables *T = reinterpret_cast<MonoTables *>(smem_raw);
+    HypScratch<KIND> *Wall = reinterpret_cast<HypScratch<KIND> *>(smem_raw + 256);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    HypScratch<KIND> *W = Wall + warp;
+    if (KIND == KIND_RELPOSE) {
+        if (threadIdx.x == 0) fill_tables(T);
+        __syncthreads();
+    }
+    for (;;) {
+        int s = 0;
+        if (lane == 0) s = atomicAdd(work_counter, 1);
+        s = __shfl_sync(0xffffffffu, s, 0);
+        if (s >= n_samples) break;
+        uint32_t sample[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) sample[i] = samples[(size_t)s * K + i];
+        const int nm = warp_generate_models<KIND>(P, sample, W, T, lane);
+        if (lane == 0) out.n_models[s] = nm;
+        const double *models = W->models;
+        for (int m = 0; m < nm; ++m) {
+            uint32_t cnt;
+            double score;
+            warp_score<KIND>(P, models + MSZ * m, P.sq_thr, lane, cnt, score);
+            const size_t slot = (size_t)s * MAXM + m;
+            if (lane == 0) {
+                out.counts[slot] = cnt;
+                out.scores[slot] = score;
+            }
+            if (lane < MSZ) out.models[slot * MSZ + lane] = models[MSZ * m + lane];
+        }
+        __syncwarp();
+    }
+}
+
+template <int KIND> static size_t hyp_smem_bytes() { return 256 + sizeof(HypScratch<KIND>) * HYP_WARPS; }
+
+static int g_sm_count = 0;
+static int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+template <int KIND> static int hyp_blocks_per_sm() {
+    static int cached = -1;
+    if (cached < 0) {
+        const size_t smem = hyp_smem_bytes<KIND>();
+        cudaFuncSetAttribute(k_hyp<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_hyp<KIND>, HYP_WARPS * 32, smem);
+        cached = nb > 0 ? nb : 1;
+    }
+    return cached;
+}
+int hyp_kernel_blocks(int kind) {
+    int per = 1;
+    switch (kind) {
+    case KIND_PNP: per = hyp_blocks_per_sm<KIND_PNP>(); break;
+    case KIND_RELPOSE: per = hyp_blocks_per_sm<KIND_RELPOSE>(); break;
+    case KIND_FUND: per = hyp_blocks_per_sm<KIND_FUND>(); break;
+    default: per = hyp_blocks_per_sm<KIND_HOMOG>(); break;
+    }
+    return per * sm_count();
+}
+
+template <int KIND>
+static void launch_hyp_t(const ProblemDev &P, const uint32_t *samples, int n_samples, int *work_counter,
+                         const HypOut &out, cudaStream_t stream) {
+    // persistent grid: a multiple of the SM count (resident CTAs per SM from the occupancy API), never more CTAs
+    // than there is work for
+    int blocks = hyp_blocks_per_sm<KIND>() * sm_count();
+    const int need = (n_samples + HYP_WARPS - 1) / HYP_WARPS;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    k_hyp<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(P, samples, n_samples, work_counter, out);
+}
+void launch_hypotheses(const ProblemDev &P, const uint32_t *samples, int n_samples, int *work_counter,
+                       const HypOut &out, int mode, cudaStream_t stream) {
+    (void)mode;
+    cudaMemsetAsync(work_counter, 0, sizeof(int), stream);
+    switch (P.kind) {
+    case KIND_PNP: launch_hyp_t<KIND_PNP>(P, samples, n_samples, work_counter, out, stream); break;
+    case KIND_RELPOSE: launch_hyp_t<KIND_RELPOSE>(P, samples, n_samples, work_counter, out, stream); break;
+    case KIND_FUND: launch_hyp_t<KIND_FUND>(P, samples, n_samples, work_counter, out, stream); break;
+    default: launch_hyp_t<KIND_HOMOG>(P, samples, n_samples, work_counter, out, stream); break;
+    }
+}
+
+// ============================================================================================================
+// explicit model scoring
+// ============================================================================================================
+template <int KIND>
+__global__ void k_score_models(const ProblemDev P, const double *__restrict__ models, int n_models,
+                               uint32_t *counts, double *scores) {
+    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int m = gw; m < n_models; m += nw) {
+        double mdl[MSZ];
+#pragma unroll
+        for (int k = 0; k < MSZ; ++k) mdl[k] = models[(size_t)m * MSZ + k];
+        uint32_t cnt;
+        double score;
+        warp_score<KIND>(P, mdl, P.sq_thr, lane, cnt, score);
+        if (lane == 0) {
+            counts[m] = cnt;
+            scores[m] = score;
+        }
+    }
+}
+void launch_score_models(const ProblemDev &P, const double *models, int n_models, uint32_t *counts, double *scores,
+                         cudaStream_t stream) {
+    if (n_models <= 0) return;
+    const int threads = 128;
+    int blocks = (n_models * 32 + threads - 1) / threads;
+    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    switch (P.kind) {
+    case KIND_PNP: k_score_models<KIND_PNP><<<blocks, threads, 0, stream>>>(P, models, n_models, counts, scores); break;
+    case KIND_RELPOSE: k_score_models<KIND_RELPOSE><<<blocks, threads, 0, stream>>>(P, models, n_models, counts, scores); break;
+    case KIND_FUND: k_score_models<KIND_FUND><<<blocks, threads, 0, stream>>>(P, models, n_models, counts, scores); break;
+    default: k_score_models<KIND_HOMOG><<<blocks, threads, 0, stream>>>(P, models, n_models, counts, scores); break;
+    }
+}
+void launch_rescore_slots(const ProblemDev &, const HypOut &, const int *, int, cudaStream_t) {}
+
+// ============================================================================================================
+// inlier masks
+// ============================================================================================================
+template <int KIND>
+__global__ void k_inlier_mask(const ProblemDev P, const double *__restrict__ model, double sq_thr, char *mask) {
+    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    double mdl[MSZ];
+#pragma unroll
+    for (int k = 0; k < MSZ; ++k) mdl[k] = model[k];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P.n) return;
+    if (KIND == KIND_PNP) {
+        // robust/utils.cc:374-383: Z = R*X + t ; r2 = |Z.hnormalized() - x|^2 ; inlier iff r2 < thr && Z(2) > 0
+        const m3 R = quat_to_rot(mdl);
+        const d3 Z = mvec(R, mk(P.p[2][k], P.p[3][k], P.p[4][k])) + mk(mdl[4], mdl[5], mdl[6]);
+        const double d0 = Z.x / Z.z - P.p[0][k], d1 = Z.y / Z.z - P.p[1][k];
+        const double r2 = d0 * d0 + d1 * d1;
+        mask[k] = (r2 < sq_thr && Z.z > 0.0) ? 1 : 0;
+    } else {
+        ModelCtx<KIND> C;
+        C.init(mdl);
+        const double *M = reinterpret_cast<const double *>(&C);
+        const double x1_0 = P.p[0][k], x1_1 = P.p[1][k], x2_0 = P.p[2][k], x2_1 = P.p[3][k];
+        double r2;
+        if (KIND == KIND_HOMOG) r2 = homography_r2(M, x1_0, x1_1, x2_0, x2_1);
+        else r2 = sampson_r2(M, x1_0, x1_1, x2_0, x2_1);
+        bool inl = r2 < sq_thr;
+        if (KIND == KIND_RELPOSE && inl)
+            inl = cheirality_ok(M + 9, M + 13, bearing(x1_0, x1_1), bearing(x2_0, x2_1), 0.01);
+        mask[k] = inl ? 1 : 0;
+    }
+}
+void launch_inlier_mask(const ProblemDev &P, const double *model, double sq_thr, char *mask, cudaStream_t stream) {
+    const int threads = 256, blocks = (P.n + threads - 1) / threads;
+    switch (P.kind) {
+    case KIND_PNP: k_inlier_mask<KIND_PNP><<<blocks, threads, 0, stream>>>(P, model, sq_thr, mask); break;
+    case KIND_RELPOSE: k_inlier_mask<KIND_RELPOSE><<<blocks, threads, 0, stream>>>(P, model, sq_thr, mask); break;
+    case KIND_FUND: k_inlier_mask<KIND_FUND><<<blocks, threads, 0, stream>>>(P, model, sq_thr, mask); break;
+    default: k_inlier_mask<KIND_HOMOG><<<blocks, threads, 0, stream>>>(P, model, sq_thr, mask); break;
+    }
+}
+
+// ============================================================================================================
+// Levenberg-Marquardt refit: one CTA per job
+// ============================================================================================================
+constexpr int LM_THREADS = 512;
+constexpr int LM_WARPS = LM_THREADS / 32;
+
+struct LossFn { // robust/robust_loss.h:41-67,125-136
+    int type;
+    double thr, sq_thr, inv_sq_thr;
+    PLB_DEV double loss(double r2) const {
+        switch (type) {
+        case 1: return fmin(r2, sq_thr);
+        case 2: {
+            const double r = sqrt(r2);
+            return (r <= thr) ? r2 : thr * (2.0 * r - thr);
+        }
+        case 3: return sq_thr * log1p(r2 * inv_sq_thr);
+        default: return r2;
+        }
+    }
+    PLB_DEV double weight(double r2) const {
+        switch (type) {
+        case 1: return (r2 < sq_thr) ? 1.0 : 0.0;
+        case 2: {
+            const double r = sqrt(r2);
+            return (r <= thr) ? 1.0 : thr / r;
+        }
+        case 3: return fmax(2.2250738585072014e-308, 1.0 / (1.0 + r2 * inv_sq_thr));
+        default: return 1.0;
+        }
+    }
+};
+
+template <int KIND> struct LmDims;
+template <> struct LmDims<KIND_PNP> { static constexpr int NP = 6, CTX = 12; };
+template <> struct LmDims<KIND_RELPOSE> { static constexpr int NP = 5, CTX = 9 + 45; };
+template <> struct LmDims<KIND_FUND> { static constexpr int NP = 7, CTX = 9 + 63; };
+template <> struct LmDims<KIND_HOMOG> { static constexpr int NP = 8, CTX = 18; };
+
+// one-sided Jacobi SVD of a 3x3 (stands in for Eigen::JacobiSVD, optim_utils.h:59-73).  Row-major in/out.
+PLB_DEV void svd3_dev(const m3 &F, m3 &U, double *s, m3 &V) {
+    m3 A = F;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) V.a[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int i = 0; i < 3; ++i) {
+                    alpha += A(i, p) * A(i, p);
+                    beta += A(i, q) * A(i, q);
+                    gamma += A(i, p) * A(i, q);
+                }
+                if (gamma == 0.0) continue;
+                off = fmax(off, fabs(gamma) / sqrt(alpha * beta + 1e-300));
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double t = ((zeta >= 0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                for (int i = 0; i < 3; ++i) {
+                    const double ap = A(i, p), aq = A(i, q);
+                    A(i, p) = c * ap - sn * aq;
+                    A(i, q) = sn * ap + c * aq;
+                    const double vp = V(i, p), vq = V(i, q);
+                    V(i, p) = c * vp - sn * vq;
+                    V(i, q) = sn * vp + c * vq;
+                }
+            }
+        if (off < 1e-16) break;
+    }
+    double sv[3];
+    for (int j = 0; j < 3; ++j) sv[j] = sqrt(dot(mcol(A, j), mcol(A, j)));
+    int idx[3] = {0, 1, 2};
+    // sort descending (3 elements)
+    if (sv[idx[1]] > sv[idx[0]]) { int t = idx[0]; idx[0] = idx[1]; idx[1] = t; }
+    if (sv[idx[2]] > sv[idx[1]]) { int t = idx[1]; idx[1] = idx[2]; idx[2] = t; }
+    if (sv[idx[1]] > sv[idx[0]]) { int t = idx[0]; idx[0] = idx[1]; idx[1] = t; }
+    m3 Vs, Us;
+    for (int j = 0; j < 3; ++j) {
+        s[j] = sv[idx[j]];
+        set_col(Vs, j, mcol(V, idx[j]));
+        if (s[j] > 0) set_col(Us, j, mcol(A, idx[j]) / s[j]);
+        else set_col(Us, j, mk(0, 0, 0));
+    }
+    if (!(s[2] > 1e-14 * s[0])) set_col(Us, 2, cross(mcol(Us, 0), mcol(Us, 1)));
+    if (!(s[1] > 0)) {
+        const d3 u0 = mcol(Us, 0);
+        const d3 e = (fabs(u0.x) < 0.9) ? mk(1, 0, 0) : mk(0, 1, 0);
+        const d3 u1 = unit(cross(u0, e));
+        set_col(Us, 1, u1);
+        set_col(Us, 2, cross(u0, u1));
+    }
+    U = Us;
+    V = Vs;
+}
+
+// F (row-major) from the factorised representation (qU,qV,sigma)  (optim_utils.h:74-78)
+PLB_DEV m3 ff_to_F(const double *par) {
+    const m3 U = quat_to_rot(par), V = quat_to_rot(par + 4);
+    const double sigma = par[8];
+    m3 F;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) F(r, c) = U(r, 0) * V(c, 0) + sigma * U(r, 1) * V(c, 1);
+    return F;
+}
+
+// Builds the evaluation context of the current parameters (executed by thread 0).
+//   PNP     : ctx[0..8] = R row-major, ctx[9..11] = t
+//   RELPOSE : ctx[0..8] = E row-major, ctx[9 + 5*m + p] = d vec(E)_m / d param_p (vec column-major), tb = tangent basis
+//   FUND    : ctx[0..8] = F row-major, ctx[9 + 7*m + p]
+//   HOMOG   : ctx[0..8] = H row-major, ctx[9..17] = adj(H) row-major
+template <int KIND> PLB_DEV void lm_build_ctx(const double *par, double *ctx, double *tb, bool with_jac) {
+    if (KIND == KIND_PNP) {
+        const m3 R = quat_to_rot(par);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) ctx[k] = R.a[k];
+        ctx[9] = par[4]; ctx[10] = par[5]; ctx[11] = par[6];
+    } else if (KIND == KIND_RELPOSE) {
+        const m3 E = essential_from_pose(par, par + 4);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) ctx[k] = E.a[k];
+        if (with_jac) {
+            const m3 R = quat_to_rot(par);
+            const d3 t = mk(par[4], par[5], par[6]);
+            // tangent basis (optim/relative.h:62-82)
+            d3 b0;
+            const double ax = fabs(t.x), ay = fabs(t.y), az = fabs(t.z);
+            if (ax < ay) {
+                if (ax < az) b0 = unit(cross(t, mk(1, 0, 0)));
+                else b0 = unit(cross(t, mk(0, 0, 1)));
+            } else {
+                if (ay < az) b0 = unit(cross(t, mk(0, 1, 0)));
+                else b0 = unit(cross(t, mk(0, 0, 1)));
+            }
+            const d3 b1 = unit(cross(b0, t));
+            tb[0] = b0.x; tb[1] = b1.x; tb[2] = b0.y; tb[3] = b1.y; tb[4] = b0.z; tb[5] = b1.z;
+            // d vec(E) / d(rotation, translation)  (optim/relative.h:39-60)
+            const d3 e0 = mcol(E, 0), e1 = mcol(E, 1), e2 = mcol(E, 2);
+            const double e0a[3] = {e0.x, e0.y, e0.z}, e1a[3] = {e1.x, e1.y, e1.z}, e2a[3] = {e2.x, e2.y, e2.z};
+            double *D = ctx + 9;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                D[5 * r + 0] = 0.0;           D[5 * r + 1] = -e2a[r];          D[5 * r + 2] = e1a[r];
+                D[5 * (3 + r) + 0] = e2a[r];  D[5 * (3 + r) + 1] = 0.0;        D[5 * (3 + r) + 2] = -e0a[r];
+                D[5 * (6 + r) + 0] = -e1a[r]; D[5 * (6 + r) + 1] = e0a[r];     D[5 * (6 + r) + 2] = 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const d3 v0 = cross(b0, mcol(R, c)), v1 = cross(b1, mcol(R, c));
+                D[5 * (3 * c + 0) + 3] = v0.x; D[5 * (3 * c + 0) + 4] = v1.x;
+                D[5 * (3 * c + 1) + 3] = v0.y; D[5 * (3 * c + 1) + 4] = v1.y;
+                D[5 * (3 * c + 2) + 3] = v0.z; D[5 * (3 * c + 2) + 4] = v1.z;
+            }
+        }
+    } else if (KIND == KIND_FUND) {
+        const m3 F = ff_to_F(par);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) ctx[k] = F.a[k];
+        if (with_jac) {
+            const m3 U = quat_to_rot(par), V = quat_to_rot(par + 4);
+            double *D = ctx + 9;
+            // optim/fundamental.h:68-77: U' = exp([w]x)U -> [e_k]x F ; V' = exp([w]x)V -> -F[e_k]x ; sigma -> u1 v1^T
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const int m = 3 * c + r;
+                    const double f0 = F(0, c), f1 = F(1, c), f2 = F(2, c);
+                    D[7 * m + 0] = (r == 0) ? 0.0 : (r == 1 ? -f2 : f1);
+                    D[7 * m + 1] = (r == 0) ? f2 : (r == 1 ? 0.0 : -f0);
+                    D[7 * m + 2] = (r == 0) ? -f1 : (r == 1 ? f0 : 0.0);
+                    const double g0 = F(r, 0), g1 = F(r, 1), g2 = F(r, 2);
+                    D[7 * m + 3] = (c == 0) ? 0.0 : (c == 1 ? -g2 : g1);
+                    D[7 * m + 4] = (c == 0) ? g2 : (c == 1 ? 0.0 : -g0);
+                    D[7 * m + 5] = (c == 0) ? -g1 : (c == 1 ? g0 : 0.0);
+                    D[7 * m + 6] = U(r, 1) * V(c, 1);
+                }
+        }
+    } else {
+        // par is column-major H
+        m3 H;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) H.a[3 * (k % 3) + k / 3] = par[k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) ctx[k] = H.a[k];
+        double *G = ctx + 9; // adjugate (optim/homography.h:160-175)
+        G[0] = H(1, 1) * H(2, 2) - H(1, 2) * H(2, 1);
+        G[1] = H(0, 2) * H(2, 1) - H(0, 1) * H(2, 2);
+        G[2] = H(0, 1) * H(1, 2) - H(0, 2) * H(1, 1);
+        G[3] = H(1, 2) * H(2, 0) - H(1, 0) * H(2, 2);
+        G[4] = H(0, 0) * H(2, 2) - H(0, 2) * H(2, 0);
+        G[5] = H(0, 2) * H(1, 0) - H(0, 0) * H(1, 2);
+        G[6] = H(1, 0) * H(2, 1) - H(1, 1) * H(2, 0);
+        G[7] = H(0, 1) * H(2, 0) - H(0, 0) * H(2, 1);
+        G[8] = H(0, 0) * H(1, 1) - H(0, 1) * H(1, 0);
+    }
+}
+
+// parameter update  (optim/absolute.h:146-160, relative.h:152-157, fundamental.h:106-112, homography.h:157-161)
+template <int KIND> PLB_DEV void lm_step(const double *par, const double *dp, const double *tb, double *out) {
+    if (KIND == KIND_PNP) {
+        double e[4];
+        quat_exp(mk(dp[0], dp[1], dp[2]), e);
+        quat_mul(par, e, out);
+        const d3 rt = quat_rotate(par, mk(dp[3], dp[4], dp[5]));
+        out[4] = par[4] + rt.x; out[5] = par[5] + rt.y; out[6] = par[6] + rt.z;
+    } else if (KIND == KIND_RELPOSE) {
+        double e[4];
+        quat_exp(mk(dp[0], dp[1], dp[2]), e);
+        quat_mul(par, e, out);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) out[4 + r] = par[4 + r] + (tb[2 * r] * dp[3] + tb[2 * r + 1] * dp[4]);
+    } else if (KIND == KIND_FUND) {
+        double e[4];
+        quat_exp(mk(dp[0], dp[1], dp[2]), e);
+        quat_mul(e, par, out);
+        quat_exp(mk(dp[3], dp[4], dp[5]), e);
+        quat_mul(e, par + 4, out + 4);
+        out[8] = par[8] + dp[6];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[k] = par[k] + dp[k];
+        out[8] = par[8];
+    }
+}
+
+// Sampson residual and its derivative wrt vec(E) (column-major)   (optim/relative.h:118-149)
+PLB_DEV void sampson_res_dF(const double *E, double a0, double a1, double b0, double b1, double &r, double *dF) {
+    const double Ex0 = E[0] * a0 + E[1] * a1 + E[2] * 1.0;
+    const double Ex1 = E[3] * a0 + E[4] * a1 + E[5] * 1.0;
+    const double Ex2 = E[6] * a0 + E[7] * a1 + E[8] * 1.0;
+    const double C = b0 * Ex0 + b1 * Ex1 + 1.0 * Ex2;
+    const double J0 = E[0] * b0 + E[3] * b1 + E[6];
+    const double J1 = E[1] * b0 + E[4] * b1 + E[7];
+    const double J2 = E[0] * a0 + E[1] * a1 + E[2];
+    const double J3 = E[3] * a0 + E[4] * a1 + E[5];
+    const double nJ = sqrt(J0 * J0 + J1 * J1 + J2 * J2 + J3 * J3);
+    const double inv = 1.0 / nJ;
+    r = C * inv;
+    const double s = C * inv * inv;
+    dF[0] = a0 * b0 - s * (J2 * a0 + J0 * b0);
+    dF[1] = a0 * b1 - s * (J3 * a0 + J0 * b1);
+    dF[2] = a0 - s * (J0);
+    dF[3] = a1 * b0 - s * (J2 * a1 + J1 * b0);
+    dF[4] = a1 * b1 - s * (J3 * a1 + J1 * b1);
+    dF[5] = a1 - s * (J1);
+    dF[6] = b0 - s * (J2);
+    dF[7] = b1 - s * (J3);
+    dF[8] = 1.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dF[k] *= inv;
+}
+// residual only (optim/relative.h:98-105)
+PLB_DEV double sampson_res(const double *E, double a0, double a1, double b0, double b1) {
+    const double Ex0 = E[0] * a0 + E[1] * a1 + E[2] * 1.0;
+    const double Ex1 = E[3] * a0 + E[4] * a1 + E[5] * 1.0;
+    const double Ex2 = E[6] * a0 + E[7] * a1 + E[8] * 1.0;
+    const double C = b0 * Ex0 + b1 * Ex1 + 1.0 * Ex2;
+    const double n1 = Ex0 * Ex0 + Ex1 * Ex1;
+    const double t0 = E[0] * b0 + E[3] * b1 + E[6] * 1.0;
+    const double t1 = E[1] * b0 + E[4] * b1 + E[7] * 1.0;
+    return C / sqrt(n1 + (t0 * t0 + t1 * t1));
+}
+
+template <int NP> struct JacAcc {
+    static constexpr int NT = NP * (NP + 1) / 2;
+    double jtj[NT];
+    double jtr[NP];
+    double cnt;
+    PLB_DEV void zero() {
+#pragma unroll
+        for (int i = 0; i < NT; ++i) jtj[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) jtr[i] = 0.0;
+        cnt = 0.0;
+    }
+    // 1-dim residual (jacobian_accumulator.h:125-141)
+    PLB_DEV void add1(const LossFn &L, double res, const double *J) {
+        const double w = L.weight(res * res);
+        if (w == 0) return;
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < NP; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) jtj[t++] += w * (J[i] * J[j]);
+        const double wr = w * res;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) jtr[i] += wr * J[i];
+        cnt += 1.0;
+    }
+    // 2-dim residual (jacobian_accumulator.h:87-104)
+    PLB_DEV void add2(const LossFn &L, double r0, double r1, const double *J0, const double *J1) {
+        const double w = L.weight(r0 * r0 + r1 * r1);
+        if (w == 0) return;
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < NP; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) jtj[t++] += w * (J0[i] * J0[j] + J1[i] * J1[j]);
+        const double wr0 = w * r0, wr1 = w * r1;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) jtr[i] += J0[i] * wr0 + J1[i] * wr1;
+        cnt += 1.0;
+    }
+};
+
+struct LmShared {
+    double par[9], par_new[9];
+    double ctx[80];
+    double tb[6];
+    double red[LM_WARPS][48];
+    double sums[48];
+    int flag;     // loop control broadcast
+    int use_new;  // evaluate par_new (residual pass) or par
+};
+
+// block-wide deterministic sum of NV per-thread values -> S->sums[0..NV)
+template <int NV> PLB_DEV void block_sum(LmShared *S, const double *v) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double s = warp_sum(v[i]);
+        if (lane == 0) S->red[warp][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int w = 0; w < LM_WARPS; ++w) s += S->red[w][threadIdx.x];
+        S->sums[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// thread 0 -> whole CTA broadcast of a small integer (two barriers: the slot can be reused right away)
+PLB_DEV int block_bcast(LmShared *S, int v) {
+    if (threadIdx.x == 0) S->flag = v;
+    __syncthreads();
+    const int r = S->flag;
+    __syncthreads();
+    return r;
+}
+
+// residual pass: sum of robust losses + row count  (compute_residual of the four refiners)
+template <int KIND>
+PLB_DEV void lm_residual_pass(const ProblemDev &P, const LmParams &prm, const LossFn &L, const char *mask,
+                              LmShared *S) {
+    const double *ctx = S->ctx;
+    double acc[2] = {0.0, 0.0};
+    for (int k = threadIdx.x; k < P.n; k += LM_THREADS) {
+        if (mask && !mask[k]) continue;
+        if (KIND == KIND_PNP) {
+            const double X0 = P.p[2][k], X1 = P.p[3][k], X2 = P.p[4][k];
+            const double Z0 = ctx[0] * X0 + ctx[1] * X1 + ctx[2] * X2 + ctx[9];
+            const double Z1 = ctx[3] * X0 + ctx[4] * X1 + ctx[5] * X2 + ctx[10];
+            const double Z2 = ctx[6] * X0 + ctx[7] * X1 + ctx[8] * X2 + ctx[11];
+            if (Z2 < 0) continue;
+            double xp0, xp1;
+            if (prm.use_camera) {
+                xp0 = prm.cam[0] * Z0 / Z2 + prm.cam[2];
+                xp1 = prm.cam[1] * Z1 / Z2 + prm.cam[3];
+            } else {
+                xp0 = Z0 / Z2;
+                xp1 = Z1 / Z2;
+            }
+            const double r0 = xp0 - P.p[0][k], r1 = xp1 - P.p[1][k];
+            acc[0] += L.loss(r0 * r0 + r1 * r1);
+            acc[1] += 1.0;
+        } else if (KIND == KIND_HOMOG) {
+            const double a0 = P.p[0][k], a1 = P.p[1][k], b0 = P.p[2][k], b1 = P.p[3][k];
+            const double *H = ctx, *G = ctx + 9;
+            const double Hx0 = H[0] * a0 + H[1] * a1 + H[2];
+            const double Hx1 = H[3] * a0 + H[4] * a1 + H[5];
+            const double iw = 1.0 / (H[6] * a0 + H[7] * a1 + H[8]);
+            const double r0 = Hx0 * iw - b0, r1 = Hx1 * iw - b1;
+            acc[0] += L.loss(r0 * r0 + r1 * r1);
+            const double Gx0 = G[0] * b0 + G[1] * b1 + G[2];
+            const double Gx1 = G[3] * b0 + G[4] * b1 + G[5];
+            const double iv = 1.0 / (G[6] * b0 + G[7] * b1 + G[8]);
+            const double s0 = Gx0 * iv - a0, s1 = Gx1 * iv - a1;
+            acc[0] += L.loss(s0 * s0 + s1 * s1);
+            acc[1] += 2.0;
+        } else {
+            const double r = sampson_res(ctx, P.p[0][k], P.p[1][k], P.p[2][k], P.p[3][k]);
+            acc[0] += L.loss(r * r);
+            acc[1] += 1.0;
+        }
+    }
+    block_sum<2>(S, acc);
+}
+
+// Jacobian pass: JtJ (lower triangle, row-major packed), Jtr, count of rows with non-zero weight
+template <int KIND>
+PLB_DEV void lm_jacobian_pass(const ProblemDev &P, const LmParams &prm, const LossFn &L, const char *mask,
+                              LmShared *S) {
+    constexpr int NP = LmDims<KIND>::NP;
+    const double *ctx = S->ctx;
+    JacAcc<NP> A;
+    A.zero();
+    for (int k = threadIdx.x; k < P.n; k += LM_THREADS) {
+        if (mask && !mask[k]) continue;
+        if (KIND == KIND_PNP) {
+            const double X0 = P.p[2][k], X1 = P.p[3][k], X2 = P.p[4][k];
+            const double Z0 = ctx[0] * X0 + ctx[1] * X1 + ctx[2] * X2 + ctx[9];
+            const double Z1 = ctx[3] * X0 + ctx[4] * X1 + ctx[5] * X2 + ctx[10];
+            const double Z2 = ctx[6] * X0 + ctx[7] * X1 + ctx[8] * X2 + ctx[11];
+            if (Z2 < 0) continue;
+            double zp0, zp1, Jp[2][3];
+            if (prm.use_camera) { // PinholeCameraModel::project_with_jac (camera_models.cc:672-685)
+                const double inv_z = 1.0 / Z2;
+                const double px = prm.cam[0] * Z0 * inv_z, py = prm.cam[1] * Z1 * inv_z;
+                zp0 = px + prm.cam[2];
+                zp1 = py + prm.cam[3];
+                Jp[0][0] = prm.cam[0] * inv_z; Jp[0][1] = 0.0; Jp[0][2] = -px * inv_z;
+                Jp[1][0] = 0.0; Jp[1][1] = prm.cam[1] * inv_z; Jp[1][2] = -py * inv_z;
+            } else { // NullCameraModel (camera_models.cc:2708-2722)
+                zp0 = Z0 / Z2;
+                zp1 = Z1 / Z2;
+                const double z_inv = 1.0 / Z2;
+                Jp[0][0] = z_inv; Jp[0][1] = 0.0; Jp[0][2] = -zp0 * z_inv;
+                Jp[1][0] = 0.0; Jp[1][1] = z_inv; Jp[1][2] = -zp1 * z_inv;
+            }
+            const double r0 = zp0 - P.p[0][k], r1 = zp1 - P.p[1][k];
+            double J[2][6];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                double dZ[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) dZ[c] = Jp[a][0] * ctx[c] + Jp[a][1] * ctx[3 + c] + Jp[a][2] * ctx[6 + c];
+                J[a][0] = -X2 * dZ[1] + X1 * dZ[2];
+                J[a][1] = X2 * dZ[0] - X0 * dZ[2];
+                J[a][2] = -X1 * dZ[0] + X0 * dZ[1];
+                J[a][3] = dZ[0]; J[a][4] = dZ[1]; J[a][5] = dZ[2];
+            }
+            A.add2(L, r0, r1, J[0], J[1]);
+        } else if (KIND == KIND_HOMOG) {
+            const double a0 = P.p[0][k], a1 = P.p[1][k], b0 = P.p[2][k], b1 = P.p[3][k];
+            const double *H = ctx, *G = ctx + 9;
+            // forward transfer (optim/homography.h:107-123); parameters = H00,H10,H20,H01,H11,H21,H02,H12
+            const double Hx0 = H[0] * a0 + H[1] * a1 + H[2];
+            const double Hx1 = H[3] * a0 + H[4] * a1 + H[5];
+            const double iw = 1.0 / (H[6] * a0 + H[7] * a1 + H[8]);
+            const double z0 = Hx0 * iw, z1 = Hx1 * iw;
+            double J0[8] = {a0, 0.0, -a0 * z0, a1, 0.0, -a1 * z0, 1.0, 0.0};
+            double J1[8] = {0.0, a0, -a0 * z1, 0.0, a1, -a1 * z1, 0.0, 1.0};
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                J0[m] = J0[m] * iw;
+                J1[m] = J1[m] * iw;
+            }
+            A.add2(L, z0 - b0, z1 - b1, J0, J1);
+            // backward transfer through adj(H) (optim/homography.h:125-152):  y = pi(G x2),
+            // dy_i/dH_k = ( (dG/dH_k x2)_i - y_i (dG/dH_k x2)_2 ) / (G x2)_2
+            const double Gx0 = G[0] * b0 + G[1] * b1 + G[2];
+            const double Gx1 = G[3] * b0 + G[4] * b1 + G[5];
+            const double iv = 1.0 / (G[6] * b0 + G[7] * b1 + G[8]);
+            const double y0 = Gx0 * iv, y1 = Gx1 * iv;
+            const double y0b1 = y0 * b1, y0b0 = y0 * b0, y1b1 = y1 * b1, y1b0 = y1 * b0;
+            const double H00 = H[0], H01 = H[1], H02 = H[2], H10 = H[3], H11 = H[4], H12 = H[5], H20 = H[6],
+                         H21 = H[7], H22 = H[8];
+            double K0[8], K1[8];
+            K0[0] = H21 * y0b1 - H11 * y0;
+            K0[1] = H01 * y0 - H21 * y0b0;
+            K0[2] = H11 * y0b0 - H01 * y0b1;
+            K0[3] = H12 - H22 * b1 + H10 * y0 - H20 * y0b1;
+            K0[4] = H22 * b0 - H02 - H00 * y0 + H20 * y0b0;
+            K0[5] = H02 * b1 - H12 * b0 + H00 * y0b1 - H10 * y0b0;
+            K0[6] = H21 * b1 - H11;
+            K0[7] = H01 - H21 * b0;
+            K1[0] = H22 * b1 - H12 - H11 * y1 + H21 * y1b1;
+            K1[1] = H02 - H22 * b0 + H01 * y1 - H21 * y1b0;
+            K1[2] = H12 * b0 - H02 * b1 - H01 * y1b1 + H11 * y1b0;
+            K1[3] = H10 * y1 - H20 * y1b1;
+            K1[4] = H20 * y1b0 - H00 * y1;
+            K1[5] = H00 * y1b1 - H10 * y1b0;
+            K1[6] = H10 - H20 * b1;
+            K1[7] = H20 * b0 - H00;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                K0[m] = K0[m] * iv;
+                K1[m] = K1[m] * iv;
+            }
+            A.add2(L, y0 - a0, y1 - a1, K0, K1);
+        } else {
+            double r, dF[9], J[NP];
+            sampson_res_dF(ctx, P.p[0][k], P.p[1][k], P.p[2][k], P.p[3][k], r, dF);
+            const double *D = ctx + 9;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                double s = 0.0;
+#pragma unroll
+                for (int m = 0; m < 9; ++m) s += dF[m] * D[NP * m + p];
+                J[p] = s;
+            }
+            A.add1(L, r, J);
+        }
+    }
+    constexpr int NV = JacAcc<NP>::NT + NP + 1;
+    double v[NV];
+#pragma unroll
+    for (int i = 0; i < JacAcc<NP>::NT; ++i) v[i] = A.jtj[i];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) v[JacAcc<NP>::NT + i] = A.jtr[i];
+    v[NV - 1] = A.cnt;
+    block_sum<NV>(S, v);
+}
+
+// lower Cholesky solve of (A) x = rhs, only the lower triangle of A read (jacobian_accumulator.h:145-154)
+template <int NP> PLB_DEV void llt_solve(const double *A, const double *rhs, double *x) {
+    double Lm[NP * NP];
+    for (int j = 0; j < NP; ++j) {
+        double d = A[j * NP + j];
+        for (int k = 0; k < j; ++k) d -= Lm[j * NP + k] * Lm[j * NP + k];
+        const double ljj = sqrt(d);
+        Lm[j * NP + j] = ljj;
+        for (int i = j + 1; i < NP; ++i) {
+            double s = A[i * NP + j];
+            for (int k = 0; k < j; ++k) s -= Lm[i * NP + k] * Lm[j * NP + k];
+            Lm[i * NP + j] = s / ljj;
+        }
+    }
+    double y[NP];
+    for (int i = 0; i < NP; ++i) {
+        double s = rhs[i];
+        for (int k = 0; k < i; ++k) s -= Lm[i * NP + k] * y[k];
+        y[i] = s / Lm[i * NP + i];
+    }
+    for (int i = NP - 1; i >= 0; --i) {
+        double s = y[i];
+        for (int k = i + 1; k < NP; ++k) s -= Lm[k * NP + i] * x[k];
+        x[i] = s / Lm[i * NP + i];
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(LM_THREADS)
+    k_lm(const ProblemDev P, const double *__restrict__ models_in, const LmParams prm, const char *mask_in,
+         char *subset_scratch, LmJobOut *outs) {
+    constexpr int NP = LmDims<KIND>::NP;
+    constexpr int NT = NP * (NP + 1) / 2;
+    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    __shared__ LmShared S;
+    const int job = blockIdx.x;
+    const double *min = models_in + (size_t)job * 9;
+    LmJobOut *out = outs + job;
+    LossFn L;
+    L.type = prm.loss_type;
+    L.thr = prm.loss_scale;
+    L.sq_thr = prm.loss_scale * prm.loss_scale;
+    L.inv_sq_thr = 1.0 / L.sq_thr;
+
+    const char *mask = (prm.subset_mode == 2) ? mask_in : nullptr;
+    bool untouched = false;
+    // ---- relpose LO subset: inliers of the start pose at 5*thr^2 (estimators/relative_pose.cc:62-86)
+    if (KIND == KIND_RELPOSE && prm.subset_mode == 1) {
+        char *mymask = subset_scratch + (size_t)job * P.n;
+        ModelCtx<KIND_RELPOSE> C;
+        C.init(min);
+        const double *M = reinterpret_cast<const double *>(&C);
+        double c[1] = {0.0};
+        for (int k = threadIdx.x; k < P.n; k += LM_THREADS) {
+            const double a0 = P.p[0][k], a1 = P.p[1][k], b0 = P.p[2][k], b1 = P.p[3][k];
+            bool inl = sampson_r2(M, a0, a1, b0, b1) < prm.subset_sq_thr;
+            if (inl) inl = cheirality_ok(M + 9, M + 13, bearing(a0, a1), bearing(b0, b1), 0.01);
+            mymask[k] = inl ? 1 : 0;
+            c[0] += inl ? 1.0 : 0.0;
+        }
+        block_sum<1>(&S, c);
+        untouched = !(S.sums[0] > 5.0);
+        mask = mymask;
+        __syncthreads();
+    }
+
+    // ---- initial parameters
+    if (threadIdx.x == 0) {
+        if (KIND == KIND_FUND) {
+            m3 F, U, V;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) F.a[3 * (k % 3) + k / 3] = min[k];
+            double s[3];
+            svd3_dev(F, U, s, V);
+            if (det3(U) < 0)
+                for (int k = 0; k < 9; ++k) U.a[k] = -U.a[k];
+            if (det3(V) < 0)
+                for (int k = 0; k < 9; ++k) V.a[k] = -V.a[k];
+            rot_to_quat(U, S.par);
+            rot_to_quat(V, S.par + 4);
+            S.par[8] = s[1] / s[0];
+        } else {
+            for (int k = 0; k < MSZ; ++k) S.par[k] = min[k];
+            for (int k = MSZ; k < 9; ++k) S.par[k] = 0.0;
+        }
+    }
+    __syncthreads();
+
+    int iterations = 0;
+    double cost = 0.0, initial_cost = 0.0;
+    if (!untouched) {
+        // thread-0 LM state (optim/lm_impl.h:56-140); rc mirrors NormalAccumulator::residual_count
+        double lambda = prm.initial_lambda, nu = 2.0, rc = 0.0;
+        double JtJ[NP * NP], Jtr[NP], sol[NP];
+        bool recompute_jac = true;
+        if (threadIdx.x == 0) lm_build_ctx<KIND>(S.par, S.ctx, S.tb, false);
+        __syncthreads();
+        lm_residual_pass<KIND>(P, prm, L, mask, &S);
+        if (threadIdx.x == 0) {
+            rc = S.sums[1];
+            cost = S.sums[0] * (1.0 / fmax(1.0, rc));
+            initial_cost = cost;
+        }
+        for (int it = 0; it < prm.max_iterations; ++it) {
+            iterations = it;
+            const int do_jac = block_bcast(&S, recompute_jac ? 1 : 0);
+            if (do_jac) {
+                if (threadIdx.x == 0) lm_build_ctx<KIND>(S.par, S.ctx, S.tb, true);
+                __syncthreads();
+                lm_jacobian_pass<KIND>(P, prm, L, mask, &S);
+            }
+            int stop = 0;
+            if (threadIdx.x == 0) {
+                if (recompute_jac) {
+                    int t = 0;
+                    for (int i = 0; i < NP; ++i)
+                        for (int j = 0; j <= i; ++j) JtJ[i * NP + j] = S.sums[t++];
+                    for (int i = 0; i < NP; ++i) Jtr[i] = S.sums[NT + i];
+                    rc = S.sums[NT + NP];
+                    double g = 0.0;
+                    for (int i = 0; i < NP; ++i) g += Jtr[i] * Jtr[i];
+                    const double grad_norm = (1.0 / fmax(1.0, rc)) * sqrt(g);
+                    if (grad_norm < prm.gradient_tol) stop = 1;
+                }
+                if (!stop) {
+                    const double scale = 1.0 / fmax(1.0, rc);
+                    double Am[NP * NP], rhs[NP];
+                    for (int i = 0; i < NP; ++i)
+                        for (int j = 0; j <= i; ++j) Am[i * NP + j] = scale * JtJ[i * NP + j];
+                    for (int i = 0; i < NP; ++i) Am[i * NP + i] += lambda;
+                    for (int i = 0; i < NP; ++i) rhs[i] = -(scale * Jtr[i]);
+                    llt_solve<NP>(Am, rhs, sol);
+                    double sn = 0.0;
+                    for (int i = 0; i < NP; ++i) sn += sol[i] * sol[i];
+                    if (sqrt(sn) < prm.step_tol) stop = 1;
+                }
+                if (!stop) {
+                    lm_step<KIND>(S.par, sol, S.tb, S.par_new);
+                    double ctx_save_tb[6];
+                    for (int i = 0; i < 6; ++i) ctx_save_tb[i] = S.tb[i];
+                    lm_build_ctx<KIND>(S.par_new, S.ctx, ctx_save_tb, false);
+                }
+            }
+            if (block_bcast(&S, stop)) break;
+            lm_residual_pass<KIND>(P, prm, L, mask, &S);
+            int brk = 0;
+            if (threadIdx.x == 0) {
+                rc = S.sums[1];
+                const double cost_new = S.sums[0] * (1.0 / fmax(1.0, rc));
+                if (cost_new < cost) {
+                    const double cost_decrease = cost - cost_new;
+                    for (int k = 0; k < 9; ++k) S.par[k] = S.par_new[k];
+                    cost = cost_new;
+                    recompute_jac = true;
+                    const double scale = 1.0 / fmax(1.0, rc);
+                    double pred = 0.0;
+                    for (int i = 0; i < NP; ++i) pred += sol[i] * (lambda * sol[i] + scale * Jtr[i]);
+                    pred = -pred;
+                    if (pred > 0) {
+                        const double rho = cost_decrease / pred;
+                        const double factor = 1.0 - pow(2.0 * rho - 1.0, 3.0);
+                        lambda *= fmax(1.0 / 3.0, factor);
+                    } else {
+                        lambda *= 1.0 / 3.0;
+                    }
+                    nu = 2.0;
+                    lambda = fmax(prm.min_lambda, lambda);
+                    if (cost > 0 && cost_decrease / cost < prm.relative_cost_tol) brk = 1;
+                } else {
+                    recompute_jac = false;
+                    lambda *= nu;
+                    nu *= 2.0;
+                    lambda = fmin(prm.max_lambda, lambda);
+                }
+                if (it + 1 >= prm.max_iterations && !brk) iterations = it + 1;
+            }
+            if (block_bcast(&S, brk)) break;
+        }
+    }
+    // ---- output
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (KIND == KIND_FUND) {
+            if (untouched) {
+                for (int k = 0; k < 9; ++k) out->model[k] = min[k];
+            } else {
+                const m3 F = ff_to_F(S.par);
+                for (int k = 0; k < 9; ++k) out->model[k] = F.a[3 * (k % 3) + k / 3];
+            }
+        } else {
+            for (int k = 0; k < MSZ; ++k) out->model[k] = untouched ? min[k] : S.par[k];
+            for (int k = MSZ; k < 9; ++k) out->model[k] = 0.0;
+        }
+        out->iterations = iterations;
+        out->cost = cost;
+        out->initial_cost = initial_cost;
+        for (int k = 0; k < 9; ++k) S.par_new[k] = out->model[k];
+    }
+    __syncthreads();
+    if (prm.score_after && threadIdx.x < 32) {
+        uint32_t cnt;
+        double score;
+        double mdl[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) mdl[k] = S.par_new[k];
+        warp_score<KIND>(P, mdl, P.sq_thr, threadIdx.x, cnt, score);
+        if (threadIdx.x == 0) {
+            out->count = cnt;
+            out->score = score;
+        }
+    }
+}
+
+void launch_lm(const ProblemDev &P, const double *models_in, int n_jobs, const LmParams &prm, const char *mask,
+               char *subset_scratch, LmJobOut *out, cudaStream_t stream) {
+    if (n_jobs <= 0) return;
+    switch (P.kind) {
+    case KIND_PNP: k_lm<KIND_PNP><<<n_jobs, LM_THREADS, 0, stream>>>(P, models_in, prm, mask, subset_scratch, out); break;
+    case KIND_RELPOSE: k_lm<KIND_RELPOSE><<<n_jobs, LM_THREADS, 0, stream>>>(P, models_in, prm, mask, subset_scratch, out); break;
+    case KIND_FUND: k_lm<KIND_FUND><<<n_jobs, LM_THREADS, 0, stream>>>(P, models_in, prm, mask, subset_scratch, out); break;
+    default: k_lm<KIND_HOMOG><<<n_jobs, LM_THREADS, 0, stream>>>(P, models_in, prm, mask, subset_scratch, out); break;
+    }
+}
+
+// ============================================================================================================
+// direct solver surface: one warp per instance
+// ============================================================================================================
+// variant: 0 = native output (p3p poses / 5pt E / 7pt F / H), 1 = 5pt poses
+template <int KIND, int VARIANT>
+__global__ void __launch_bounds__(HYP_WARPS * 32)
+    k_solver_batch(size_t count, const double *__restrict__ a, const double *__restrict__ b, double *out, int *n_out,
+                   int flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MonoTables *T = reinterpret_cast<MonoTables *>(smem_raw);
+    HypScratch<KIND> *W = reinterpret_cast<HypScratch<KIND> *>(smem_raw + 256) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (KIND == KIND_RELPOSE) {
+        if (threadIdx.x == 0) fill_tables(T);
+        __syncthreads();
+    }
+    const size_t gw = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t i = gw; i < count; i += nw) {
+        if (KIND == KIND_PNP) {
+            d3 xs[3], Xs[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                xs[k] = mk(a[9 * i + 3 * k], a[9 * i + 3 * k + 1], a[9 * i + 3 * k + 2]);
+                Xs[k] = mk(b[9 * i + 3 * k], b[9 * i + 3 * k + 1], b[9 * i + 3 * k + 2]);
+            }
+            double *models = reinterpret_cast<double *>(W);
+            const int n = solve_p3p(xs, Xs, models, lane);
+            if (lane < 28) out[28 * i + lane] = (lane < 7 * n) ? models[lane] : 0.0;
+            if (lane == 0) n_out[i] = n;
+        } else if (KIND == KIND_HOMOG) {
+            d3 xa[4], xb[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                xa[k] = mk(a[12 * i + 3 * k], a[12 * i + 3 * k + 1], a[12 * i + 3 * k + 2]);
+                xb[k] = mk(b[12 * i + 3 * k], b[12 * i + 3 * k + 1], b[12 * i + 3 * k + 2]);
+            }
+            double *models = reinterpret_cast<double *>(W);
+            const int n = solve_h4(xa, xb, models, lane, flags != 0);
+            if (lane < 9) out[9 * i + lane] = n ? models[lane] : 0.0;
+            if (lane == 0) n_out[i] = n;
+        } else if (KIND == KIND_RELPOSE) {
+            HypScratch<KIND_RELPOSE> *S = reinterpret_cast<HypScratch<KIND_RELPOSE> *>(W);
+            if (lane < 30) S->xs[lane] = (lane < 15) ? a[15 * i + lane] : b[15 * i + lane - 15];
+            __syncwarp();
+            if (VARIANT == 0) {
+                const int n = solve_5pt_E(S->xs, S->xs + 15, &S->s5, T, lane);
+                for (int e = lane; e < 90; e += 32) {
+                    const int m = e / 9, k = e % 9; // output column-major
+                    out[90 * i + e] = (m < n) ? S->s5.Es[9 * m + 3 * (k % 3) + k / 3] : 0.0;
+                }
+                if (lane == 0) n_out[i] = n;
+            } else {
+                const int n = solve_5pt_poses(S->xs, S->xs + 15, &S->s5, T, S->models, lane);
+                for (int e = lane; e < 280; e += 32) out[280 * i + e] = (e < 7 * n) ? S->models[e] : 0.0;
+                if (lane == 0) n_out[i] = n;
+            }
+        } else {
+            HypScratch<KIND_FUND> *S = reinterpret_cast<HypScratch<KIND_FUND> *>(W);
+            for (int e = lane; e < 42; e += 32) S->xs[e] = (e < 21) ? a[21 * i + e] : b[21 * i + e - 21];
+            __syncwarp();
+            const int n = solve_7pt(S->xs, S->xs + 21, &S->s7, S->models, lane);
+            if (lane < 27) out[27 * i + lane] = (lane < 9 * n) ? S->models[lane] : 0.0;
+            if (lane == 0) n_out[i] = n;
+        }
+        __syncwarp();
+    }
+}
+
+template <int KIND, int VARIANT>
+static void launch_solver_t(size_t count, const double *a, const double *b, double *out, int *n_out, int flags,
+                            cudaStream_t stream) {
+    const size_t smem = hyp_smem_bytes<KIND>();
+    cudaFuncSetAttribute(k_solver_batch<KIND, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t blocks = (count + HYP_WARPS - 1) / HYP_WARPS;
+    const size_t cap = (size_t)sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_solver_batch<KIND, VARIANT><<<(unsigned)blocks, HYP_WARPS * 32, smem, stream>>>(count, a, b, out, n_out, flags);
+}
+void launch_solver_batch(int kind, int variant, size_t count, const double *a, const double *b, double *out,
+                         int *n_out, int flags, cudaStream_t stream) {
+    if (count == 0) return;
+    switch (kind) {
+    case KIND_PNP: launch_solver_t<KIND_PNP, 0>(count, a, b, out, n_out, flags, stream); break;
+    case KIND_RELPOSE:
+        if (variant == 0) launch_solver_t<KIND_RELPOSE, 0>(count, a, b, out, n_out, flags, stream);
+        else launch_solver_t<KIND_RELPOSE, 1>(count, a, b, out, n_out, flags, stream);
+        break;
+    case KIND_FUND: launch_solver_t<KIND_FUND, 0>(count, a, b, out, n_out, flags, stream); break;
+    default: launch_solver_t<KIND_HOMOG, 0>(count, a, b, out, n_out, flags, stream); break;
+    }
+}
+
+} // namespace plb

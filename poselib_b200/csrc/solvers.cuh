@@ -1,0 +1,1098 @@
+// poselib_b200 — minimal solvers as warp-level device functions (one warp = one minimal sample).
+//
+// p3p and homography_4pt are short closed forms: every lane evaluates the same scalar program (no divergence, no
+// shared memory) and lane 0 publishes the models.  relpose_5pt and relpose_7pt stage their matrices in per-warp
+// shared memory and spread the wide steps (pivoted QR, the 10x20 trace-constraint build, the 10x10 LU with 10
+// right-hand sides, the polynomial products, per-root back-substitution and the 4-way motion decomposition) over
+// the lanes.  Every individual dot product / accumulation keeps the left-to-right order of the reference so results
+// agree with the CPU path to the last bits wherever libm is not involved.
+//
+// Reference (relative to /root/reference): solvers/p3p.cc:39-202 + p3p_common.h; solvers/relpose_5pt.cc:101-409;
+// solvers/relpose_7pt.cc:10-60; solvers/homography_4pt.cc:36-128; misc/sturm.h:47-274; misc/univariate.cc:48-126;
+// misc/essential.cc:103-169.
+#pragma once
+#include "device_math.cuh"
+
+namespace plb {
+
+// ================================ scalar helpers ==========================================================
+// misc/univariate.cc:74-92
+PLB_DEV bool cubic_single_real(double c2, double c1, double c0, double &root) {
+    double a = c1 - c2 * c2 / 3.0;
+    double b = (2.0 * c2 * c2 * c2 - 9.0 * c2 * c1) / 27.0 + c0;
+    double c = b * b / 4.0 + a * a * a / 27.0;
+    if (c != 0) {
+        if (c > 0) {
+            c = sqrt(c);
+            b *= -0.5;
+            root = cbrt(b + c) + cbrt(b - c) - c2 / 3.0;
+            return true;
+        }
+        c = 3.0 * b / (2.0 * a) * sqrt(-3.0 / a);
+        root = 2.0 * sqrt(-a / 3.0) * cos(acos(c) / 3.0) - c2 / 3.0;
+    } else {
+        root = -c2 / 3.0 + (a != 0 ? (3.0 * b / a) : 0);
+    }
+    return false;
+}
+// misc/univariate.cc:94-126
+PLB_DEV int cubic_real(double c2, double c1, double c0, double *roots) {
+    double a = c1 - c2 * c2 / 3.0;
+    double b = (2.0 * c2 * c2 * c2 - 9.0 * c2 * c1) / 27.0 + c0;
+    double c = b * b / 4.0 + a * a * a / 27.0;
+    int n;
+    if (a == 0.0 && b == 0.0) {
+        roots[0] = roots[1] = roots[2] = -c2 / 3.0;
+        n = 3;
+    } else if (c > 0) {
+        c = sqrt(c);
+        b *= -0.5;
+        roots[0] = cbrt(b + c) + cbrt(b - c) - c2 / 3.0;
+        n = 1;
+    } else {
+        c = 3.0 * b / (2.0 * a) * sqrt(-3.0 / a);
+        const double d = 2.0 * sqrt(-a / 3.0);
+        const double third = acos(c) / 3.0;
+        roots[0] = d * cos(third) - c2 / 3.0;
+        roots[1] = d * cos(third - 2.09439510239319526263557236234192) - c2 / 3.0;
+        roots[2] = d * cos(third - 4.18879020478639052527114472468384) - c2 / 3.0;
+        n = 3;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (i < n) {
+            const double x = roots[i], x2 = x * x, x3 = x * x2;
+            roots[i] += -(x3 + c2 * x2 + c1 * x + c0) / (3 * x2 + 2 * c2 * x + c1);
+        }
+    }
+    return n;
+}
+// misc/univariate.cc:48-61
+PLB_DEV int quadratic_real(double a, double b, double c, double *roots) {
+    const double disc = b * b - 4 * a * c;
+    if (disc < 0) return 0;
+    const double sq = sqrt(disc);
+    roots[0] = (b > 0) ? (2 * c) / (-b - sq) : (2 * c) / (-b + sq);
+    roots[1] = c / (a * roots[0]);
+    return 2;
+}
+
+// ================================ p3p (Ding et al. CVPR'23) ================================================
+// p3p_common.h:7-29
+PLB_DEV bool p3p_root2real(double b, double c, double &r1, double &r2) {
+    const double v = b * b - 4.0 * c;
+    if (v < -1.0e-12) {
+        r1 = r2 = -0.5 * b;
+        return false;
+    }
+    if (v < 0.0) {
+        r1 = -0.5 * b;
+        r2 = -2;
+        return true;
+    }
+    const double y = sqrt(v);
+    if (b < 0) {
+        r1 = 0.5 * (-b + y);
+        r2 = 0.5 * (-b - y);
+    } else {
+        r1 = 2.0 * c / (-b + y);
+        r2 = 2.0 * c / (-b - y);
+    }
+    return true;
+}
+// p3p_common.h:72-94
+PLB_DEV void p3p_refine_lambda(double &l1, double &l2, double &l3, double a12, double a13, double a23, double b12,
+                               double b13, double b23) {
+    for (int it = 0; it < 5; ++it) {
+        const double r1 = (l1 * l1 - 2.0 * l1 * l2 * b12 + l2 * l2 - a12);
+        const double r2 = (l1 * l1 - 2.0 * l1 * l3 * b13 + l3 * l3 - a13);
+        const double r3 = (l2 * l2 - 2.0 * l2 * l3 * b23 + l3 * l3 - a23);
+        if (fabs(r1) + fabs(r2) + fabs(r3) < 1e-10) return;
+        const double x11 = l1 - l2 * b12, x12 = l2 - l1 * b12;
+        const double x21 = l1 - l3 * b13, x23 = l3 - l1 * b13;
+        const double x32 = l2 - l3 * b23, x33 = l3 - l2 * b23;
+        const double detJ = 0.5 / (x11 * x23 * x32 + x12 * x21 * x33);
+        l1 += (-x23 * x32 * r1 - x12 * x33 * r2 + x12 * x23 * r3) * detJ;
+        l2 += (-x21 * x33 * r1 + x11 * x33 * r2 - x11 * x23 * r3) * detJ;
+        l3 += (x21 * x32 * r1 - x11 * x32 * r2 - x12 * x21 * r3) * detJ;
+    }
+}
+
+// Solves one P3P instance.  xs: 3 unit bearings, Xs: 3 world points.  Writes up to 4 poses (7 doubles each) to
+// `out` (lane 0 writes) and returns the count (uniform across the warp).   p3p.cc:39-202
+PLB_DEV int solve_p3p(const d3 *xs, const d3 *Xs, double *out, int lane) {
+    d3 x0 = xs[0], x1 = xs[1], x2 = xs[2];
+    d3 P0 = Xs[0], P1 = Xs[1], P2 = Xs[2];
+    d3 X01 = P0 - P1, X02 = P0 - P2, X12 = P1 - P2;
+    double a01 = dot(X01, X01), a02 = dot(X02, X02), a12 = dot(X12, X12);
+    // make |P1-P2| the largest side (p3p.cc:58-73)
+    if (a01 > a02) {
+        if (a01 > a12) {
+            d3 t = x0; x0 = x2; x2 = t;
+            t = P0; P0 = P2; P2 = t;
+            double s = a01; a01 = a12; a12 = s;
+            X01 = -X12;
+            X02 = -X02;
+        }
+    } else if (a02 > a12) {
+        d3 t = x0; x0 = x1; x1 = t;
+        t = P0; P0 = P1; P1 = t;
+        double s = a02; a02 = a12; a12 = s;
+        X01 = -X01;
+        X02 = X12;
+    }
+    const double a12d = 1.0 / a12;
+    const double a = a01 * a12d, b = a02 * a12d;
+    const double m01 = dot(x0, x1), m02 = dot(x0, x2), m12 = dot(x1, x2);
+    const double m12sq = -m12 * m12 + 1.0;
+    const double m02sq = -1.0 + m02 * m02;
+    const double m01sq = -1.0 + m01 * m01;
+    const double ab = a * b, bsq = b * b, asq = a * a;
+    const double m013 = -2.0 + 2.0 * m01 * m02 * m12;
+    const double bsqm12sq = bsq * m12sq, asqm12sq = asq * m12sq, abm12sq = 2.0 * ab * m12sq;
+    const double k3_inv = 1.0 / (bsqm12sq + b * m02sq);
+    const double k2 = k3_inv * ((-1.0 + a) * m02sq + abm12sq + bsqm12sq + b * m013);
+    const double k1 = k3_inv * (asqm12sq + abm12sq + a * m013 + (-1.0 + b) * m01sq);
+    const double k0 = k3_inv * (asqm12sq + a * m01sq);
+    double s;
+    const bool G = cubic_single_real(k2, k1, k0, s);
+    // degenerate conic C = C0 + s*C1 (p3p.cc:103-112), symmetric
+    const double C00 = -a + s * (1 - b), C01 = -m02 * s, C02 = a * m12 + b * m12 * s;
+    const double C11 = s + 1, C12 = -m01, C22 = -a - b * s + 1;
+    // split into two lines (p3p_common.h:31-70)
+    d3 pl, ql;
+    {
+        const double A00 = C12 * C12 - C11 * C22, A11 = C02 * C02 - C00 * C22, A22 = C01 * C01 - C00 * C11;
+        const double A01 = C01 * C22 - C02 * C12, A02 = C02 * C11 - C01 * C12, A12 = C00 * C12 - C02 * C01;
+        d3 v;
+        if (A00 > A11) {
+            if (A00 > A22) v = mk(A00, A01, A02) / sqrt(A00);
+            else v = mk(A02, A12, A22) / sqrt(A22);
+        } else if (A11 > A22) {
+            v = mk(A01, A11, A12) / sqrt(A11);
+        } else {
+            v = mk(A02, A12, A22) / sqrt(A22);
+        }
+        // C + [v]x : first column -> p, first row -> q
+        pl = mk(C00, C01 + v.z, C02 - v.y);
+        ql = mk(C00, C01 - v.z, C02 + v.y);
+    }
+    m3 XX;
+    set_col(XX, 0, X01);
+    set_col(XX, 1, X02);
+    set_col(XX, 2, cross(X01, X02));
+    XX = inv3(XX);
+
+    int n_sols = 0;
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+        const d3 L = (i == 0) ? pl : ql;
+        const double p0 = L.x, p1 = L.y, p2 = L.z;
+        const bool switch_12 = fabs(p0) <= fabs(p1);
+        double w0, w1, cb, cc;
+        if (switch_12) {
+            w0 = -p0 / p1;
+            w1 = -p2 / p1;
+            const double ca = 1.0 / (w1 * w1 - b);
+            cb = 2.0 * (b * m12 - m02 * w1 + w0 * w1) * ca;
+            cc = (w0 * w0 - 2 * m02 * w0 - b + 1.0) * ca;
+        } else {
+            w0 = -p1 / p0;
+            w1 = -p2 / p0;
+            const double ca = 1.0 / (-a * w1 * w1 + 2 * a * m12 * w1 - a + 1);
+            cb = 2 * (a * m12 * w0 - m01 - a * w0 * w1) * ca;
+            cc = (1 - a * w0 * w0) * ca;
+        }
+        double taus[2];
+        if (p3p_root2real(cb, cc, taus[0], taus[1])) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double tau = taus[j];
+                if (tau <= 0) continue;
+                double d0, d1, d2;
+                if (switch_12) {
+                    d2 = sqrt(a12 / (tau * (tau - 2.0 * m12) + 1.0));
+                    d1 = tau * d2;
+                    d0 = (w0 * d2 + w1 * d1);
+                    if (d0 < 0) continue;
+                } else {
+                    d0 = sqrt(a01 / (tau * (tau - 2.0 * m01) + 1.0));
+                    d1 = tau * d0;
+                    d2 = w0 * d0 + w1 * d1;
+                    if (d2 < 0) continue;
+                }
+                p3p_refine_lambda(d0, d1, d2, a01, a02, a12, m01, m02, m12);
+                const d3 v1 = d0 * x0 - d1 * x1;
+                const d3 v2 = d0 * x0 - d2 * x2;
+                m3 YY;
+                set_col(YY, 0, v1);
+                set_col(YY, 1, v2);
+                set_col(YY, 2, cross(v1, v2));
+                const m3 R = mmul(YY, XX);
+                const d3 t = d0 * x0 - mvec(R, P0);
+                double q[4];
+                rot_to_quat(R, q);
+                if (lane == 0) {
+                    double *o = out + 7 * n_sols;
+                    o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3];
+                    o[4] = t.x; o[5] = t.y; o[6] = t.z;
+                }
+                ++n_sols;
+            }
+        }
+        if (n_sols > 0 && G) break;
+    }
+    __syncwarp();
+    return n_sols;
+}
+
+// ================================ homography_4pt (SKS / ACA closed form) ===================================
+// homography_4pt.cc:36-128.  Writes H (9 doubles COLUMN-major) to out; returns 0/1.
+PLB_DEV int solve_h4(const d3 *x1, const d3 *x2, double *out, int lane, bool check_cheirality) {
+    if (check_cheirality) {
+        d3 p = cross(x1[0], x1[1]), q = cross(x2[0], x2[1]);
+        if (dot(p, x1[2]) * dot(q, x2[2]) < 0) return 0;
+        if (dot(p, x1[3]) * dot(q, x2[3]) < 0) return 0;
+        p = cross(x1[2], x1[3]);
+        q = cross(x2[2], x2[3]);
+        if (dot(p, x1[0]) * dot(q, x2[0]) < 0) return 0;
+        if (dot(p, x1[1]) * dot(q, x2[1]) < 0) return 0;
+    }
+    double ax[4], ay[4], bx[4], by[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ax[i] = x1[i].x / x1[i].z;
+        ay[i] = x1[i].y / x1[i].z;
+        bx[i] = x2[i].x / x2[i].z;
+        by[i] = x2[i].y / x2[i].z;
+    }
+    const double sNx = ax[1] - ax[0], sPx = ax[2] - ax[0], sQx = ax[3] - ax[0];
+    const double sNy = ay[1] - ay[0], sPy = ay[2] - ay[0], sQy = ay[3] - ay[0];
+    const double fA1 = sNx * sPy - sNy * sPx;
+    const double Q3x = sPy * sQx - sPx * sQy;
+    const double Q3y = sNx * sQy - sNy * sQx;
+    const double tNx = bx[1] - bx[0], tPx = bx[2] - bx[0], tQx = bx[3] - bx[0];
+    const double tNy = by[1] - by[0], tPy = by[2] - by[0], tQy = by[3] - by[0];
+    const double fA2 = tNx * tPy - tNy * tPx;
+    const double Q4x = tPy * tQx - tPx * tQy;
+    const double Q4y = tNx * tQy - tNy * tQx;
+    const double tt1 = fA1 - Q3x - Q3y;
+    const double C11 = Q3y * Q4x * tt1;
+    const double C22 = Q3x * Q4y * tt1;
+    const double C33 = Q3x * Q3y * (fA2 - Q4x - Q4y);
+    const double C31 = C11 - C33, C32 = C22 - C33;
+    const double tt3 = bx[0] * C33, tt4 = by[0] * C33;
+    const double H1_11 = bx[1] * C11 - tt3, H1_12 = bx[2] * C22 - tt3;
+    const double H1_21 = by[1] * C11 - tt4, H1_22 = by[2] * C22 - tt4;
+    m3 H;
+    H.a[0] = H1_11 * sPy - H1_12 * sNy;
+    H.a[1] = H1_12 * sNx - H1_11 * sPx;
+    H.a[3] = H1_21 * sPy - H1_22 * sNy;
+    H.a[4] = H1_22 * sNx - H1_21 * sPx;
+    H.a[6] = C31 * sPy - C32 * sNy;
+    H.a[7] = C32 * sNx - C31 * sPx;
+    H.a[2] = tt3 * fA1 - H.a[0] * ax[0] - H.a[1] * ay[0];
+    H.a[5] = tt4 * fA1 - H.a[3] * ax[0] - H.a[4] * ay[0];
+    H.a[8] = C33 * fA1 - H.a[6] * ax[0] - H.a[7] * ay[0];
+    double n2 = 0; // Frobenius norm, column-major accumulation like Eigen's squaredNorm
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) n2 += H(r, c) * H(r, c);
+    if (n2 > 0) {
+        const double n = sqrt(n2);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) H.a[k] /= n;
+    }
+    if (fabs(det3(H)) < 1e-8) return 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) out[k] = H(k % 3, k / 3);
+    }
+    __syncwarp();
+    return 1;
+}
+
+// ================================ pivoted Householder nullspace ============================================
+// Restates Eigen's FullPivHouseholderQR::matrixQ() for a 9 x COLS matrix and returns the last (9-COLS) columns of Q,
+// i.e. an orthonormal basis of the left nullspace (relpose_5pt.cc:167-168, relpose_7pt.cc:18-19).
+//   a   : shared, 9*COLS doubles, column-major, destroyed
+//   qn  : shared, (9-COLS)*9 doubles; column j of the basis at qn[9*j .. 9*j+8]
+template <int COLS> PLB_DEV void warp_nullspace_9xC(double *a, double *qn, int lane) {
+    constexpr int ROWS = 9;
+    double tau_k[COLS];
+    int rt_k[COLS];
+    const double precision = 2.220446049250313e-16 * double(COLS);
+    double biggest = 0.0;
+    bool stopped = false;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) {
+        if (stopped) {
+            tau_k[k] = 0.0;
+            rt_k[k] = k;
+            continue;
+        }
+        // ---- pivot: largest |a_rc| in the trailing block, first one in column-major order
+        const int nr = ROWS - k, cnt = nr * (COLS - k);
+        double best = -1.0;
+        int bord = 0x7fffffff;
+        for (int e = lane; e < cnt; e += 32) {
+            const int c = k + e / nr, r = k + e % nr;
+            const double v = fabs(a[c * ROWS + r]);
+            if (v > best) {
+                best = v;
+                bord = e;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oo = __shfl_xor_sync(0xffffffffu, bord, o);
+            if (ob > best || (ob == best && oo < bord)) {
+                best = ob;
+                bord = oo;
+            }
+        }
+        if (k == 0) biggest = best;
+        if (fabs(best) <= fabs(biggest) * precision) {
+            stopped = true;
+            tau_k[k] = 0.0;
+            rt_k[k] = k;
+            continue;
+        }
+        const int cb = k + bord / nr, rb = k + bord % nr;
+        rt_k[k] = rb;
+        if (rb != k && lane >= k && lane < COLS) {
+            const double t = a[lane * ROWS + k];
+            a[lane * ROWS + k] = a[lane * ROWS + rb];
+            a[lane * ROWS + rb] = t;
+        }
+        __syncwarp();
+        if (cb != k && lane < ROWS) {
+            const double t = a[k * ROWS + lane];
+            a[k * ROWS + lane] = a[cb * ROWS + lane];
+            a[cb * ROWS + lane] = t;
+        }
+        __syncwarp();
+        // ---- Householder vector of column k (every lane evaluates the same scalars)
+        double tail_sq = 0.0;
+        for (int r = k + 1; r < ROWS; ++r) tail_sq += a[k * ROWS + r] * a[k * ROWS + r];
+        const double c0 = a[k * ROWS + k];
+        double tau, beta;
+        __syncwarp();
+        if (tail_sq <= 2.2250738585072014e-308) {
+            tau = 0.0;
+            beta = c0;
+            if (lane > k && lane < ROWS) a[k * ROWS + lane] = 0.0;
+        } else {
+            beta = sqrt(c0 * c0 + tail_sq);
+            if (c0 >= 0) beta = -beta;
+            if (lane > k && lane < ROWS) a[k * ROWS + lane] = a[k * ROWS + lane] / (c0 - beta);
+            tau = (beta - c0) / beta;
+        }
+        if (lane == k) a[k * ROWS + k] = beta;
+        tau_k[k] = tau;
+        __syncwarp();
+        // ---- reflect the trailing columns: one lane per column
+        if (tau != 0.0 && lane > k && lane < COLS) {
+            double *col = a + lane * ROWS;
+            const double *v = a + k * ROWS;
+            double tmp = 0.0;
+            for (int r = k + 1; r < ROWS; ++r) tmp += v[r] * col[r];
+            tmp += col[k];
+            col[k] -= tau * tmp;
+            for (int r = k + 1; r < ROWS; ++r) col[r] -= tau * v[r] * tmp;
+        }
+        __syncwarp();
+    }
+    // ---- columns COLS..8 of Q = P_0 H_0 ... P_{COLS-1} H_{COLS-1} applied to unit vectors; one lane per column
+    if (lane < ROWS - COLS) {
+        double q[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) q[r] = (r == COLS + lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = COLS - 1; k >= 0; --k) {
+            const double tau = tau_k[k];
+            const double *v = a + k * ROWS;
+            if (tau != 0.0) {
+                double tmp = 0.0;
+#pragma unroll
+                for (int r = k + 1; r < ROWS; ++r) tmp += v[r] * q[r];
+                tmp += q[k];
+                q[k] -= tau * tmp;
+#pragma unroll
+                for (int r = k + 1; r < ROWS; ++r) q[r] -= tau * v[r] * tmp;
+            }
+            const int rt = rt_k[k];
+            if (rt != k) {
+                // swap q[k] <-> q[rt] with a register-resident select (rt is uniform but dynamic)
+                const double qk = q[k];
+                double qr = 0.0;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r)
+                    if (r == rt) qr = q[r];
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r)
+                    if (r == rt) q[r] = qk;
+                q[k] = qr;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) qn[lane * ROWS + r] = q[r];
+    }
+    __syncwarp();
+}
+
+// ================================ Sturm root isolation, degree 10 ==========================================
+// Scalar (single-lane) restatement of misc/sturm.h:47-274.  The recursion of isolate_roots is unrolled into an
+// explicit interval stack that visits intervals in the same left-to-right depth-first order.
+struct SturmWork {
+    double fvec[21]; // monic polynomial (11) + monic-normalised derivative (10)
+    double svec[30];
+};
+PLB_DEV double sturm_polyval10(const double *f, double x) {
+    double fx = x + f[9];
+#pragma unroll
+    for (int i = 8; i >= 0; --i) fx = x * fx + f[i];
+    return fx;
+}
+PLB_DEV double sturm_polyval9(const double *f, double x) {
+    double fx = x + f[8];
+#pragma unroll
+    for (int i = 7; i >= 0; --i) fx = x * fx + f[i];
+    return fx;
+}
+PLB_DEV int sturm_signchanges(const double *svec, double x) {
+    double f2 = svec[29];
+    double f1 = svec[27] + x * svec[28];
+    int count = ((f1 < 0) != (f2 < 0)) ? 1 : 0;
+#pragma unroll
+    for (int i = 8; i >= 0; --i) {
+        const double f0 = (svec[3 * i] + x * svec[3 * i + 1]) * f1 + svec[3 * i + 2] * f2;
+        count += ((f0 < 0) != (f1 < 0)) ? 1 : 0;
+        f2 = f1;
+        f1 = f0;
+    }
+    return count;
+}
+PLB_DEV void sturm_build_seq(const double *fvec, double *svec) {
+    constexpr int N = 10;
+    double f[3 * N];
+    for (int i = 0; i < 2 * N + 1; ++i) f[i] = fvec[i];
+    int o1 = 0, o2 = N + 1, o3 = 2 * N + 1; // offsets of f1,f2,f3 inside f
+    for (int i = 0; i < N - 1; ++i) {
+        double *f1 = f + o1, *f2 = f + o2, *f3 = f + o3;
+        const double q1 = f1[N - i] * f2[N - 1 - i];
+        const double q0 = f1[N - 1 - i] * f2[N - 1 - i] - f1[N - i] * f2[N - 2 - i];
+        f3[0] = f1[0] - q0 * f2[0];
+        for (int j = 1; j < N - 1 - i; ++j) f3[j] = f1[j] - q1 * f2[j - 1] - q0 * f2[j];
+        const double c = -fabs(f3[N - 2 - i]);
+        const double ci = 1.0 / c;
+        for (int j = 0; j < N - 1 - i; ++j) f3[j] = f3[j] * ci;
+        const int t = o1;
+        o1 = o2;
+        o2 = o3;
+        o3 = t;
+        svec[3 * i] = q0;
+        svec[3 * i + 1] = q1;
+        svec[3 * i + 2] = c;
+    }
+    svec[3 * N - 3] = f[o1 + 0];
+    svec[3 * N - 2] = f[o1 + 1];
+    svec[3 * N - 1] = f[o2 + 0];
+}
+PLB_DEV void sturm_ridders_newton(const double *fvec, double a, double b, double *roots, int &n_roots, double tol) {
+    double fa = sturm_polyval10(fvec, a);
+    double fb = sturm_polyval10(fvec, b);
+    if (!((fa < 0) ^ (fb < 0))) return;
+    for (int iter = 0; iter < 30; ++iter) {
+        if (fabs(a - b) < 1e-3) break;
+        const double c = (a + b) * 0.5;
+        const double fc = sturm_polyval10(fvec, c);
+        const double s = sqrt(fc * fc - fa * fb);
+        if (!s) break;
+        const double d = (fa < fb) ? c + (a - c) * fc / s : c + (c - a) * fc / s;
+        const double fd = sturm_polyval10(fvec, d);
+        if (fd >= 0 ? (fc < 0) : (fc > 0)) {
+            a = c; fa = fc; b = d; fb = fd;
+        } else if (fd >= 0 ? (fa < 0) : (fa > 0)) {
+            b = d; fb = fd;
+        } else {
+            a = d; fa = fd;
+        }
+    }
+    double x = (a + b) * 0.5;
+    for (int iter = 0; iter < 10; ++iter) {
+        const double fx = sturm_polyval10(fvec, x);
+        if (fabs(fx) < tol) break;
+        const double fpx = 10.0 * sturm_polyval9(fvec + 11, x);
+        const double dx = fx / fpx;
+        x = x - dx;
+        if (fabs(dx) < tol) break;
+    }
+    roots[n_roots++] = x;
+}
+// coeffs: 11 ascending coefficients; roots: up to 10, ascending.  w: scratch (shared or local).
+PLB_DEV int sturm_bisect10(const double *coeffs, double *roots, SturmWork *w) {
+    constexpr int N = 10;
+    const double tol = 1e-10;
+    if (coeffs[N] == 0.0) return 0;
+    double *fvec = w->fvec, *svec = w->svec;
+    const double c_inv = 1.0 / coeffs[N];
+    for (int i = 0; i < N; ++i) fvec[i] = coeffs[i] * c_inv;
+    fvec[N] = 1.0;
+    for (int i = 0; i < N - 1; ++i) fvec[N + 1 + i] = fvec[i + 1] * ((i + 1) / double(N));
+    fvec[2 * N] = 1.0;
+    sturm_build_seq(fvec, svec);
+    double mx = 0;
+    for (int i = 0; i < N; ++i) mx = fmax(mx, fabs(fvec[i]));
+    const double r0 = 1.0 + mx;
+    const int s_lo = sturm_signchanges(svec, -r0), s_hi = sturm_signchanges(svec, r0);
+    if (s_lo - s_hi == 0) return 0;
+    int n_roots = 0;
+    // explicit stack of pending right halves.  A right half is only worth visiting if it holds a root (sc-sb >= 1)
+    // or is already narrower than tol (the reference then emits its upper end whatever the count, sturm.h:216-219);
+    // pending intervals are disjoint and each holds >= 1 root, plus at most one terminal-width one: 12 suffice.
+    double st_a[12], st_b[12];
+    int st_sa[12], st_sb[12], st_depth[12];
+    int sp = 0;
+    st_a[0] = -r0; st_b[0] = r0; st_sa[0] = s_lo; st_sb[0] = s_hi; st_depth[0] = 0;
+    sp = 1;
+    while (sp > 0) {
+        --sp;
+        double a = st_a[sp], b = st_b[sp];
+        int sa = st_sa[sp], sb = st_sb[sp], depth = st_depth[sp];
+        // walk down the left spine, pushing right halves
+        for (;;) {
+            if (depth > 300) break;
+            if (b - a < tol) {
+                if (n_roots < 10) roots[n_roots++] = b;
+                break;
+            }
+            const int n_rts = sa - sb;
+            if (n_rts > 1) {
+                const double c = (a + b) * 0.5;
+                const int sc = sturm_signchanges(svec, c);
+                if (sp < 12 && ((sc - sb) >= 1 || (b - c) < tol)) {
+                    st_a[sp] = c; st_b[sp] = b; st_sa[sp] = sc; st_sb[sp] = sb; st_depth[sp] = depth + 1;
+                    ++sp;
+                }
+                b = c;
+                sb = sc;
+                ++depth;
+            } else {
+                if (n_rts == 1 && n_roots < 10) sturm_ridders_newton(fvec, a, b, roots, n_roots, tol);
+                break;
+            }
+        }
+    }
+    return n_roots;
+}
+
+// ================================ relpose_5pt (Nister) =====================================================
+// Monomial tables, filled once per CTA into shared memory (see fill_tables):
+//   quad_idx[i][j]      : index of lin_i*lin_j in [x^2,xy,xz,x,y^2,yz,y,z^2,z,1]       (relpose_5pt.cc:11-12)
+//   cub_n[ci], cub_q/l  : the (quadratic, linear) factor pairs, in (q,l) lexicographic order, whose product is the
+//                         cubic monomial ci of [x^3,y^3,x^2y,xy^2,x^2z,x^2,y^2z,y^2,xyz,xy,xz^2,xz,x,yz^2,yz,y,
+//                         z^3,z^2,z,1]                                                      (relpose_5pt.cc:54-55)
+struct MonoTables {
+    int8_t quad_i[10], quad_j[10]; // the (i<=j) pair of each quadratic monomial
+    int8_t cub_n[20];
+    int8_t cub_q[20][3], cub_l[20][3];
+};
+__device__ __forceinline__ void fill_tables(MonoTables *T) {
+    // executed by one thread
+    const int8_t qexp[10][3] = {{2, 0, 0}, {1, 1, 0}, {1, 0, 1}, {1, 0, 0}, {0, 2, 0},
+                                {0, 1, 1}, {0, 1, 0}, {0, 0, 2}, {0, 0, 1}, {0, 0, 0}};
+    const int8_t cexp[20][3] = {{3, 0, 0}, {0, 3, 0}, {2, 1, 0}, {1, 2, 0}, {2, 0, 1}, {2, 0, 0}, {0, 2, 1},
+                                {0, 2, 0}, {1, 1, 1}, {1, 1, 0}, {1, 0, 2}, {1, 0, 1}, {1, 0, 0}, {0, 1, 2},
+                                {0, 1, 1}, {0, 1, 0}, {0, 0, 3}, {0, 0, 2}, {0, 0, 1}, {0, 0, 0}};
+    const int8_t lexp[4][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
+    int qn = 0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = i; j < 4; ++j) {
+            T->quad_i[qn] = (int8_t)i;
+            T->quad_j[qn] = (int8_t)j;
+            ++qn;
+        }
+    for (int ci = 0; ci < 20; ++ci) {
+        int n = 0;
+        for (int q = 0; q < 10; ++q)
+            for (int l = 0; l < 4; ++l)
+                if (qexp[q][0] + lexp[l][0] == cexp[ci][0] && qexp[q][1] + lexp[l][1] == cexp[ci][1] &&
+                    qexp[q][2] + lexp[l][2] == cexp[ci][2]) {
+                    T->cub_q[ci][n] = (int8_t)q;
+                    T->cub_l[ci][n] = (int8_t)l;
+                    ++n;
+                }
+        T->cub_n[ci] = (int8_t)n;
+    }
+}
+
+// per-warp shared scratch of the 5-point solver (doubles)
+struct Scratch5 {
+    double M[45];       // 9x5 epipolar matrix (col-major); reused
+    double Nb[36];      // Nb[4*k + r]: coefficient of basis r (x,y,z,1) in entry k (col-major) of E
+    double quad[9][10]; // 6 EE^T entries (+3 determinant minors) as quadratics
+    double coeffs[200]; // 10 x 20 (row-major, lda 20)
+    double A[39];       // 3 x 13
+    double cpoly[11];
+    double roots[10];
+    double minors[3][8];
+    SturmWork sturm;
+    double Es[90];      // up to 10 essential matrices, row-major 3x3 each
+    int nroots;
+};
+
+// One quadratic coefficient of  acc + sgn * (a*b)  with linear a,b in accumulation order of the reference.
+PLB_DEV double lin_mul_coef(double acc, const double *a, const double *b, int i, int j, double sgn) {
+    acc = acc + sgn * (a[i] * b[j]);
+    if (i != j) acc = acc + sgn * (a[j] * b[i]);
+    return acc;
+}
+
+// Essential matrices from 5 bearing pairs.  x1s/x2s: shared arrays of 5 unit bearings (3 doubles each).
+// On return S->Es holds nroots row-major E matrices (relpose_5pt.cc:159-395).  Returns nroots (uniform).
+PLB_DEV int solve_5pt_E(const double *x1s, const double *x2s, Scratch5 *S, const MonoTables *T, int lane) {
+    // ---- 9x5 epipolar constraints (:163-166): entry 3a+b of column i = x1[i][a]*x2[i][b]
+    for (int e = lane; e < 45; e += 32) {
+        const int i = e / 9, k = e % 9;
+        S->M[e] = x1s[3 * i + k / 3] * x2s[3 * i + k % 3];
+    }
+    __syncwarp();
+    // ---- nullspace basis (:167-168); qn column r -> Nb[4k+r]
+    warp_nullspace_9xC<5>(S->M, S->coeffs /*tmp: 36 doubles*/, lane);
+    for (int e = lane; e < 36; e += 32) {
+        const int r = e / 9, k = e % 9;
+        S->Nb[4 * k + r] = S->coeffs[9 * r + k];
+    }
+    __syncwarp();
+#define PLB_EE(i, j) (S->Nb + 4 * (3 * (j) + (i)))
+    // ---- quadratic building blocks (:113-123,129-144): 6 entries of EE^T and 3 minors of the last-row expansion
+    for (int e = lane; e < 90; e += 32) {
+        const int blk = e / 10, m = e % 10;
+        const int qi = T->quad_i[m], qj = T->quad_j[m];
+        double v = 0.0;
+        if (blk < 6) {
+            // (i,j) in (0,0),(0,1),(0,2),(1,1),(1,2),(2,2)
+            const int i = (blk < 3) ? 0 : (blk < 5 ? 1 : 2);
+            const int j = (blk < 3) ? blk : (blk < 5 ? blk - 2 : 2);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) v = lin_mul_coef(v, PLB_EE(i, k), PLB_EE(j, k), qi, qj, 1.0);
+        } else {
+            // minors d_t of the cofactor expansion along row 2
+            const int t = blk - 6;
+            const int c1 = (t == 0) ? 1 : (t == 1 ? 2 : 0);
+            const int c2 = (t == 0) ? 2 : (t == 1 ? 0 : 1);
+            v = lin_mul_coef(v, PLB_EE(0, c1), PLB_EE(1, c2), qi, qj, 1.0);
+            v = lin_mul_coef(v, PLB_EE(0, c2), PLB_EE(1, c1), qi, qj, -1.0);
+        }
+        S->quad[blk][m] = v;
+    }
+    __syncwarp();
+    // trace subtraction (:139-144)
+    if (lane < 10) {
+        const double t = 0.5 * (S->quad[0][lane] + S->quad[3][lane] + S->quad[5][lane]);
+        S->quad[0][lane] -= t;
+        S->quad[3][lane] -= t;
+        S->quad[5][lane] -= t;
+    }
+    __syncwarp();
+    // ---- 10 x 20 coefficient matrix (:146-154 rows 0..8, :113-125 row 9)
+    for (int e = lane; e < 200; e += 32) {
+        const int row = e / 20, ci = e % 20;
+        const int np = T->cub_n[ci];
+        double v = 0.0;
+        if (row < 9) {
+            const int i = row / 3, j = row % 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                // symmetric index of EET[i][k]
+                const int lo = i < k ? i : k, hi = i < k ? k : i;
+                const int blk = (lo == 0) ? hi : (lo == 1 ? 2 + hi : 5);
+                const double *Q = S->quad[blk];
+                const double *Lk = PLB_EE(k, j);
+                for (int p = 0; p < np; ++p) v += Q[T->cub_q[ci][p]] * Lk[T->cub_l[ci][p]];
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const double *Q = S->quad[6 + t];
+                const double *Lk = PLB_EE(2, t);
+                for (int p = 0; p < np; ++p) v += Q[T->cub_q[ci][p]] * Lk[T->cub_l[ci][p]];
+            }
+        }
+        S->coeffs[e] = v;
+    }
+    __syncwarp();
+#undef PLB_EE
+    // ---- [A | B] -> A^{-1} B by partial-pivot LU, 10 right-hand sides (:173)
+    {
+        double *C = S->coeffs;
+        for (int k = 0; k < 10; ++k) {
+            int p = k;
+            double best = fabs(C[k * 20 + k]);
+            for (int r = k + 1; r < 10; ++r) {
+                const double v = fabs(C[r * 20 + k]);
+                if (v > best) {
+                    best = v;
+                    p = r;
+                }
+            }
+            __syncwarp();
+            if (best != 0.0) {
+                if (p != k && lane < 20) {
+                    const double t = C[k * 20 + lane];
+                    C[k * 20 + lane] = C[p * 20 + lane];
+                    C[p * 20 + lane] = t;
+                }
+                __syncwarp();
+                const double pv = C[k * 20 + k];
+                __syncwarp();
+                if (lane > k && lane < 10) C[lane * 20 + k] /= pv;
+                __syncwarp();
+            }
+            const int m = 9 - k;
+            for (int e = lane; e < m * m; e += 32) {
+                const int r = k + 1 + e / m, c = k + 1 + e % m;
+                C[r * 20 + c] -= C[r * 20 + k] * C[k * 20 + c];
+            }
+            __syncwarp();
+        }
+        if (lane < 10) {
+            const int c = 10 + lane;
+            for (int r = 1; r < 10; ++r) {
+                double s = C[r * 20 + c];
+                for (int k = 0; k < r; ++k) s -= C[r * 20 + k] * C[k * 20 + c];
+                C[r * 20 + c] = s;
+            }
+            for (int r = 9; r >= 0; --r) {
+                double s = C[r * 20 + c];
+                for (int k = r + 1; k < 10; ++k) s -= C[r * 20 + k] * C[k * 20 + c];
+                C[r * 20 + c] = s / C[r * 20 + r];
+            }
+        }
+        __syncwarp();
+    }
+    // ---- 3 x 13 polynomial matrix (:176-189)
+    for (int e = lane; e < 39; e += 32) {
+        const int i = e / 13, c = e % 13;
+        const double *top = S->coeffs + (4 + 2 * i) * 20 + 10, *bot = S->coeffs + (5 + 2 * i) * 20 + 10;
+        // block g: columns [0..3] <- cols 0..2 ; [4..7] <- cols 3..5 ; [8..12] <- cols 6..9
+        const int g0 = (c < 4) ? 0 : (c < 8 ? 4 : 8), src0 = (c < 4) ? 0 : (c < 8 ? 3 : 6);
+        const int w = (c < 8) ? 3 : 4, o = c - g0;
+        double v = 0.0;
+        if (o >= 1) v = top[src0 + o - 1];
+        if (o < w) v -= bot[src0 + o];
+        S->A[e] = v;
+    }
+    __syncwarp();
+    // ---- det(A(z)) as a degree-10 polynomial, ascending coefficients (:191-352)
+    // p_ij ascending: p_i0[k] = A[i][3-k], p_i1[k] = A[i][7-k], p_i2[k] = A[i][12-k]
+    {
+        const double *A = S->A;
+        auto P = [&](int i, int j, int k) -> double {
+            return (j == 0) ? A[13 * i + 3 - k] : (j == 1 ? A[13 * i + 7 - k] : A[13 * i + 12 - k]);
+        };
+        // minors of rows 1,2: m0 = p11*p22 - p12*p21 (deg 7), m1 = p10*p22 - p12*p20 (deg 7), m2 = p10*p21 - p11*p20 (6)
+        if (lane < 24) {
+            const int t = lane / 8, k = lane % 8;
+            const int ja = (t == 0) ? 1 : 0, jb = (t == 2) ? 1 : 2; // first product p1[ja]*p2[jb]
+            const int da = 3, db = (jb == 2) ? 4 : 3;
+            double v = 0.0;
+            if (k <= da + db) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int i = 0; i <= da; ++i) {
+                    const int j = k - i;
+                    if (j >= 0 && j <= db) s1 += P(1, ja, i) * P(2, jb, j);
+                }
+                // second product p1[jb]*p2[ja]
+                for (int i = 0; i <= db; ++i) {
+                    const int j = k - i;
+                    if (j >= 0 && j <= da) s2 += P(1, jb, i) * P(2, ja, j);
+                }
+                v = s1 - s2;
+            }
+            S->minors[t][k] = v;
+        }
+        __syncwarp();
+        if (lane < 11) {
+            const int k = lane;
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            for (int i = 0; i <= 3; ++i) {
+                const int j = k - i;
+                if (j >= 0 && j <= 7) t0 += P(0, 0, i) * S->minors[0][j];
+            }
+            for (int i = 0; i <= 3; ++i) {
+                const int j = k - i;
+                if (j >= 0 && j <= 7) t1 += P(0, 1, i) * S->minors[1][j];
+            }
+            for (int i = 0; i <= 4; ++i) {
+                const int j = k - i;
+                if (j >= 0 && j <= 6) t2 += P(0, 2, i) * S->minors[2][j];
+            }
+            double c = 0.0;
+            c += t0;
+            c -= t1;
+            c += t2;
+            S->cpoly[k] = c;
+        }
+        __syncwarp();
+    }
+    // ---- real roots by Sturm bracketing (:356): scalar work on lane 0
+    if (lane == 0) S->nroots = sturm_bisect10(S->cpoly, S->roots, &S->sturm);
+    __syncwarp();
+    const int n = S->nroots;
+    // ---- back-substitution, one lane per root (:359-392)
+    if (lane < n) {
+        const double *A = S->A;
+        const double z = S->roots[lane], z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
+        double B[3][2], bb[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            B[r][0] = A[13 * r + 0] * z3 + A[13 * r + 1] * z2 + A[13 * r + 2] * z + A[13 * r + 3];
+            B[r][1] = A[13 * r + 4] * z3 + A[13 * r + 5] * z2 + A[13 * r + 6] * z + A[13 * r + 7];
+            bb[r] = A[13 * r + 8] * z4 + A[13 * r + 9] * z3 + A[13 * r + 10] * z2 + A[13 * r + 11] * z + A[13 * r + 12];
+        }
+        const double det = B[0][0] * B[1][1] - B[0][1] * B[1][0];
+        const double id = 1.0 / det;
+        const double i00 = B[1][1] * id, i01 = -B[0][1] * id, i10 = -B[1][0] * id, i11 = B[0][0] * id;
+        double s0 = i00 * bb[0] + i01 * bb[1], s1 = i10 * bb[0] + i11 * bb[1];
+        if (fabs(B[2][0] * s0 + B[2][1] * s1 - bb[2]) > 1e-6) {
+            // rare fallback (:380-382): column-pivoted Householder least squares on the 3x2 system
+            double Aq[3][2] = {{B[0][0], B[0][1]}, {B[1][0], B[1][1]}, {B[2][0], B[2][1]}};
+            double rhs[3] = {bb[0], bb[1], bb[2]};
+            int p0 = 0, p1 = 1;
+            const double n0 = Aq[0][0] * Aq[0][0] + Aq[1][0] * Aq[1][0] + Aq[2][0] * Aq[2][0];
+            const double n1 = Aq[0][1] * Aq[0][1] + Aq[1][1] * Aq[1][1] + Aq[2][1] * Aq[2][1];
+            if (n1 > n0) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double t = Aq[r][0];
+                    Aq[r][0] = Aq[r][1];
+                    Aq[r][1] = t;
+                }
+                p0 = 1;
+                p1 = 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                double tail_sq = 0.0;
+#pragma unroll
+                for (int r = k + 1; r < 3; ++r) tail_sq += Aq[r][k] * Aq[r][k];
+                const double c0 = Aq[k][k];
+                double tau = 0.0, beta = c0, ess[3] = {0, 0, 0};
+                if (tail_sq > 2.2250738585072014e-308) {
+                    beta = sqrt(c0 * c0 + tail_sq);
+                    if (c0 >= 0) beta = -beta;
+#pragma unroll
+                    for (int r = k + 1; r < 3; ++r) ess[r] = Aq[r][k] / (c0 - beta);
+                    tau = (beta - c0) / beta;
+                }
+                Aq[k][k] = beta;
+                if (tau != 0.0) {
+                    if (k == 0) {
+                        double tmp = Aq[0][1];
+#pragma unroll
+                        for (int r = 1; r < 3; ++r) tmp += ess[r] * Aq[r][1];
+                        Aq[0][1] -= tau * tmp;
+#pragma unroll
+                        for (int r = 1; r < 3; ++r) Aq[r][1] -= tau * ess[r] * tmp;
+                    }
+                    double tmp = rhs[k];
+#pragma unroll
+                    for (int r = k + 1; r < 3; ++r) tmp += ess[r] * rhs[r];
+                    rhs[k] -= tau * tmp;
+#pragma unroll
+                    for (int r = k + 1; r < 3; ++r) rhs[r] -= tau * ess[r] * tmp;
+                }
+            }
+            const double y1 = rhs[1] / Aq[1][1];
+            const double y0 = (rhs[0] - Aq[0][1] * y1) / Aq[0][0];
+            if (p0 == 0) { s0 = y0; s1 = y1; } else { s1 = y0; s0 = y1; }
+            (void)p1;
+        }
+        const double x = -s0, y = -s1;
+        const double inv_norm = 1.0 / sqrt(x * x + y * y + z * z + 1.0);
+        double *E = S->Es + 9 * lane;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const double e = S->Nb[4 * k + 0] * x + S->Nb[4 * k + 1] * y + S->Nb[4 * k + 2] * z + S->Nb[4 * k + 3];
+            E[3 * (k % 3) + (k / 3)] = e * inv_norm; // k is the column-major index
+        }
+    }
+    __syncwarp();
+    return n;
+}
+
+// Four motion hypotheses of an essential matrix, filtered by cheirality on the sample (misc/essential.cc:103-169).
+// E: row-major; x1s/x2s: ns unit bearings each.  Returns a 4-bit mask of accepted candidates and writes all four
+// candidate poses to cand[4][7] (registers of the calling lane).
+PLB_DEV unsigned motions_from_E(const double *E9, const double *x1s, const double *x2s, int ns, double cand[4][7]) {
+    m3 E;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) E.a[k] = E9[k];
+    const d3 e0 = mcol(E, 0), e1 = mcol(E, 1), e2 = mcol(E, 2);
+    const d3 u12 = cross(e0, e1), u13 = cross(e0, e2), u23 = cross(e1, e2);
+    const double n12 = dot(u12, u12), n13 = dot(u13, u13), n23 = dot(u23, u23);
+    d3 c1, c2;
+    if (n12 > n13) {
+        if (n12 > n23) { c1 = unit(e0); c2 = u12 / sqrt(n12); }
+        else { c1 = unit(e1); c2 = u23 / sqrt(n23); }
+    } else {
+        if (n13 > n23) { c1 = unit(e0); c2 = u13 / sqrt(n13); }
+        else { c1 = unit(e1); c2 = u23 / sqrt(n23); }
+    }
+    const d3 c0 = -cross(c2, c1);
+    d3 v0 = mtvec(E, c1);
+    d3 v1 = mtvec(E, -c0);
+    v0 = unit(v0);
+    v1 = v1 - dot(v0, v1) * v0;
+    v1 = unit(v1);
+    m3 Vt;
+    set_row(Vt, 0, v0);
+    set_row(Vt, 1, v1);
+    set_row(Vt, 2, cross(v0, v1));
+    m3 UW;
+    set_col(UW, 0, c0);
+    set_col(UW, 1, c1);
+    set_col(UW, 2, c2);
+    double qa[4], qb[4];
+    rot_to_quat(mmul(UW, Vt), qa);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        UW(r, 0) = -UW(r, 0);
+        UW(r, 1) = -UW(r, 1);
+    }
+    rot_to_quat(mmul(UW, Vt), qb);
+    unsigned mask = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double *q = (c < 2) ? qa : qb;
+        // translation signs: +t, -t, then (after the second `pose.t = -pose.t`) -(-t) = +t ... follow the
+        // reference literally: cand0 = (qa, t), cand1 = (qa,-t), cand2 = (qb,-t), cand3 = (qb, t)
+        const double sgn = (c == 0 || c == 3) ? 1.0 : -1.0;
+        cand[c][0] = q[0]; cand[c][1] = q[1]; cand[c][2] = q[2]; cand[c][3] = q[3];
+        cand[c][4] = sgn * c2.x; cand[c][5] = sgn * c2.y; cand[c][6] = sgn * c2.z;
+        bool ok = true;
+        for (int i = 0; i < ns; ++i) {
+            const d3 a = mk(x1s[3 * i], x1s[3 * i + 1], x1s[3 * i + 2]);
+            const d3 b = mk(x2s[3 * i], x2s[3 * i + 1], x2s[3 * i + 2]);
+            if (!cheirality_ok(cand[c], cand[c] + 4, a, b, 0.0)) {
+                ok = false;
+                break;
+            }
+        }
+        if (ok) mask |= 1u << c;
+    }
+    return mask;
+}
+
+// Full relpose_5pt: poses (7 doubles each, up to 40) into `out` in the reference's order (E-major, then the four
+// candidates); returns the number of poses (uniform).   relpose_5pt.cc:397-409
+PLB_DEV int solve_5pt_poses(const double *x1s, const double *x2s, Scratch5 *S, const MonoTables *T, double *out,
+                            int lane) {
+    const int n = solve_5pt_E(x1s, x2s, S, T, lane);
+    double cand[4][7];
+    unsigned mask = 0;
+    if (lane < n) mask = motions_from_E(S->Es + 9 * lane, x1s, x2s, 5, cand);
+    const int mine = __popc(mask);
+    // exclusive prefix over lanes
+    int pre = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
+    int pos = pre - mine;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (mask & (1u << c)) {
+            double *o = out + 7 * pos;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) o[k] = cand[c][k];
+            ++pos;
+        }
+    }
+    __syncwarp();
+    return total;
+}
+
+// ================================ relpose_7pt ==============================================================
+struct Scratch7 {
+    double M[63];  // 9x7, col-major
+    double N[18];  // two basis vectors, N[9*j + k]
+};
+// F matrices (9 doubles COLUMN-major each, up to 3) into out; returns count (uniform).  relpose_7pt.cc:10-60
+PLB_DEV int solve_7pt(const double *x1s, const double *x2s, Scratch7 *S, double *out, int lane) {
+    for (int e = lane; e < 63; e += 32) {
+        const int i = e / 9, k = e % 9;
+        S->M[e] = x1s[3 * i + k / 3] * x2s[3 * i + k % 3];
+    }
+    __syncwarp();
+    warp_nullspace_9xC<7>(S->M, S->N, lane);
+    const double *n0 = S->N, *n1 = S->N + 9;
+    // mixed determinants: column j of the 3x3 (col-major 9-vector) taken from a, b, c respectively
+    auto detc = [](const double *a, const double *b, const double *c) -> double {
+        const double *c0 = a, *c1 = b + 3, *c2 = c + 6;
+        return c0[0] * (c1[1] * c2[2] - c1[2] * c2[1]) - c1[0] * (c0[1] * c2[2] - c0[2] * c2[1]) +
+               c2[0] * (c0[1] * c1[2] - c0[2] * c1[1]);
+    };
+    const double c3 = detc(n0, n0, n0);
+    const double c2 = detc(n1, n0, n0) + detc(n0, n1, n0) + detc(n0, n0, n1);
+    const double c1 = detc(n0, n1, n1) + detc(n1, n0, n1) + detc(n1, n1, n0);
+    const double c0 = detc(n1, n1, n1);
+    double roots[3];
+    int n_roots;
+    if (fabs(c3) < 1e-14) {
+        n_roots = quadratic_real(c2, c1, c0, roots);
+    } else {
+        const double inv_c3 = 1.0 / c3;
+        n_roots = cubic_real(c2 * inv_c3, c1 * inv_c3, c0 * inv_c3, roots);
+    }
+    if (lane < n_roots) {
+        double r = roots[0];
+        if (lane == 1) r = roots[1];
+        if (lane == 2) r = roots[2];
+        double f[9], n2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            f[k] = n0[k] * r + n1[k];
+            n2 += f[k] * f[k];
+        }
+        if (n2 > 0) {
+            const double nn = sqrt(n2);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) f[k] /= nn;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) out[9 * lane + k] = f[k];
+    }
+    __syncwarp();
+    return n_roots;
+}
+
+// robust/utils.cc:646-672 — note the reference stores the products in `float`
+PLB_DEV bool rfc_ok(const double *Fc /*column-major*/) {
+#define F_(r, c) Fc[3 * (c) + (r)]
+    float den, num;
+    den = F_(0, 0) * F_(0, 1) * F_(2, 0) * F_(2, 2) - F_(0, 0) * F_(0, 2) * F_(2, 0) * F_(2, 1) +
+          F_(0, 1) * F_(0, 1) * F_(2, 1) * F_(2, 2) - F_(0, 1) * F_(0, 2) * F_(2, 1) * F_(2, 1) +
+          F_(1, 0) * F_(1, 1) * F_(2, 0) * F_(2, 2) - F_(1, 0) * F_(1, 2) * F_(2, 0) * F_(2, 1) +
+          F_(1, 1) * F_(1, 1) * F_(2, 1) * F_(2, 2) - F_(1, 1) * F_(1, 2) * F_(2, 1) * F_(2, 1);
+    num = -F_(2, 2) * (F_(0, 1) * F_(0, 2) * F_(2, 2) - F_(0, 2) * F_(0, 2) * F_(2, 1) + F_(1, 1) * F_(1, 2) * F_(2, 2) -
+                       F_(1, 2) * F_(1, 2) * F_(2, 1));
+    if (num * den < 0) return false;
+    den = F_(0, 0) * F_(1, 0) * F_(0, 2) * F_(2, 2) - F_(0, 0) * F_(2, 0) * F_(0, 2) * F_(1, 2) +
+          F_(1, 0) * F_(1, 0) * F_(1, 2) * F_(2, 2) - F_(1, 0) * F_(2, 0) * F_(1, 2) * F_(1, 2) +
+          F_(0, 1) * F_(1, 1) * F_(0, 2) * F_(2, 2) - F_(0, 1) * F_(2, 1) * F_(0, 2) * F_(1, 2) +
+          F_(1, 1) * F_(1, 1) * F_(1, 2) * F_(2, 2) - F_(1, 1) * F_(2, 1) * F_(1, 2) * F_(1, 2);
+    num = -F_(2, 2) * (F_(1, 0) * F_(2, 0) * F_(2, 2) - F_(2, 0) * F_(2, 0) * F_(1, 2) + F_(1, 1) * F_(2, 1) * F_(2, 2) -
+                       F_(2, 1) * F_(2, 1) * F_(1, 2));
+    if (num * den < 0) return false;
+    return true;
+#undef F_
+}
+
+} // namespace plb

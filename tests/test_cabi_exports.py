@@ -1,0 +1,73 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/poselib_b200.h declares, and fails loudly
+(no CPU fallback) when no CUDA device is usable.  No compute calls need a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "poselib_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(plb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from poselib_b200 import cabi
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(cabi.lib(), s), f"{s} declared in the header but not exported"
+    assert sorted(cabi.EXPORTS) == syms
+
+
+def test_struct_layouts_match_header():
+    from poselib_b200 import cabi
+    assert C.sizeof(cabi.RansacOpt) == 56
+    assert C.sizeof(cabi.RansacStats) == 40
+    assert C.sizeof(cabi.BundleOpt) == 72
+    assert C.sizeof(cabi.Counters) == 64
+    assert C.sizeof(cabi.Camera) == 48
+    o = cabi.RansacOpt(1, 2, 9.0, 0.5, 77, True, True, 5)
+    cabi.lib().plb_ransac_opt_default(C.byref(o))
+    assert (o.max_iterations, o.min_iterations, o.dyn_num_trials_mult, o.success_prob, o.seed,
+            o.progressive_sampling, o.score_initial_model, o.max_prosac_iterations) == \
+        (100000, 1000, 3.0, 0.9999, 0, 0, 0, 100000)  # PoseLib/types.h:39-50 defaults
+    b = cabi.BundleOpt(1, "TRIVIAL", 7.0)
+    cabi.lib().plb_bundle_opt_default(C.byref(b))
+    assert (b.max_iterations, b.loss_type, b.loss_scale, b.gradient_tol, b.step_tol, b.relative_cost_tol,
+            b.initial_lambda, b.min_lambda, b.max_lambda) == (100, 3, 1.0, 1e-12, 1e-8, 1e-10, 1e-3, 1e-10, 1e10)
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    from poselib_b200 import cabi
+    st, cn = cabi.RansacStats(), cabi.Counters()
+    rc = cabi.lib().plb_ransac_relpose(None, None, C.c_size_t(10), None, C.c_double(1.0), None, None,
+                                       C.byref(st), C.byref(cn))
+    assert rc == cabi.PLB_ERR_ARG
+    assert cabi.lib().plb_set_mode(7) == cabi.PLB_ERR_ARG
+    # unsupported camera model -> NYI (reference throws "NYI", camera_models.cc:184-185)
+    x = np.zeros((8, 2))
+    cam = cabi.Camera(4, (500, 500, 0, 0))  # OPENCV
+    with pytest.raises(cabi.PoseLibB200Error) as e:
+        cabi.estimate("relpose", x, x, cabi.RansacOpt(), cabi.BundleOpt(), 1.0, cam, cam)
+    assert e.value.code == cabi.PLB_ERR_NYI
+
+
+def test_no_silent_cpu_fallback():
+    from poselib_b200 import cabi
+    if cabi.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    x = np.random.default_rng(0).normal(size=(50, 2))
+    with pytest.raises(cabi.PoseLibB200Error) as e:
+        cabi.ransac("relpose", x, x, cabi.RansacOpt(max_iterations=10, min_iterations=1), 1e-3)
+    assert e.value.code == cabi.PLB_ERR_CUDA
+    # too few / zero points return default stats without touching the device (ransac_impl.h:161-163)
+    r = cabi.ransac("relpose", np.zeros((0, 2)), np.zeros((0, 2)), cabi.RansacOpt(), 1e-3)
+    assert r["stats"]["iterations"] == 0 and r["stats"]["model_score"] > 1e300

@@ -1,0 +1,229 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs.  Bars: integer results (sample-driven trajectory: iterations, refinements, inlier counts,
+inlier masks) bit-exact; models within 1e-6 relative (north_star), solver outputs within 1e-9."""
+import numpy as np
+import pytest
+
+import plo_py as P
+from poselib_b200 import problem_generator as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    from poselib_b200 import cabi as c
+    if c.device_count() == 0:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box")
+    c.set_device(0)
+    return c
+
+
+def _noisy_samples(npts, count, seed, outliers=True):
+    """bearing samples as the estimators build them from noisy/outlier data (not exact minimal instances)."""
+    rng = np.random.default_rng(seed)
+    x1s, x2s = [], []
+    for i in range(count):
+        p = G.relpose_problem(64, 0.5 if outliers else 1.0, config_id=20, problem_idx=seed * 1000 + i)
+        idx = rng.choice(64, npts, replace=False)
+        a = np.c_[p["x1"][idx] / G.FOCAL, np.ones(npts)]
+        b = np.c_[p["x2"][idx] / G.FOCAL, np.ones(npts)]
+        x1s.append(a / np.linalg.norm(a, axis=1, keepdims=True))
+        x2s.append(b / np.linalg.norm(b, axis=1, keepdims=True))
+    return np.array(x1s), np.array(x2s)
+
+
+# ---------------------------------------------------------------------------------------------- solvers
+def test_p3p_matches_oracle(cabi):
+    xs, Xs = [], []
+    for i in range(400):
+        x, X, R, t = G.minimal_abspose(i)
+        xs.append(x)
+        Xs.append(X)
+    # plus samples drawn from noisy / outlier data
+    for i in range(100):
+        p = G.abspose_problem(50, 0.5, config_id=21, problem_idx=i)
+        a = np.c_[p["x"][:3] / G.FOCAL, np.ones(3)]
+        xs.append(a / np.linalg.norm(a, axis=1, keepdims=True))
+        Xs.append(p["X"][:3])
+    poses, n = cabi.p3p_batch(np.array(xs), np.array(Xs))
+    for i in range(len(xs)):
+        ref = P.p3p(xs[i], Xs[i])
+        assert n[i] == len(ref), i
+        assert np.allclose(poses[i, :n[i]], ref, rtol=1e-9, atol=1e-9), i
+
+
+def test_relpose_5pt_matches_oracle(cabi):
+    x1s, x2s = [], []
+    for i in range(300):
+        x1, x2, R, t = G.minimal_relpose(i, 5)
+        x1s.append(x1)
+        x2s.append(x2)
+    a, b = _noisy_samples(5, 300, 1)
+    x1s, x2s = np.concatenate([np.array(x1s), a]), np.concatenate([np.array(x2s), b])
+    Es, n = cabi.relpose_5pt_batch(x1s, x2s)
+    poses, npz = cabi.relpose_5pt_poses_batch(x1s, x2s)
+    exact = 0
+    for i in range(len(x1s)):
+        ref = P.relpose_5pt_E(x1s[i], x2s[i])
+        assert n[i] == len(ref), (i, n[i], len(ref))
+        assert np.allclose(Es[i, :n[i]], ref, rtol=1e-9, atol=1e-9), i
+        exact += np.array_equal(Es[i, :n[i]], ref)
+        refp = P.relpose_5pt(x1s[i], x2s[i])
+        assert npz[i] == len(refp), i
+        assert np.allclose(poses[i, :npz[i]], refp, rtol=1e-9, atol=1e-9), i
+    print("5pt bit-identical instances:", exact, "/", len(x1s))
+
+
+def test_relpose_7pt_matches_oracle(cabi):
+    x1s, x2s = [], []
+    for i in range(300):
+        x1, x2, R, t = G.minimal_relpose(i, 7)
+        x1s.append(x1)
+        x2s.append(x2)
+    a, b = _noisy_samples(7, 300, 2)
+    x1s, x2s = np.concatenate([np.array(x1s), a]), np.concatenate([np.array(x2s), b])
+    Fs, n = cabi.relpose_7pt_batch(x1s, x2s)
+    for i in range(len(x1s)):
+        ref = P.relpose_7pt(x1s[i], x2s[i])
+        assert n[i] == len(ref), i
+        assert np.allclose(Fs[i, :n[i]], ref, rtol=1e-8, atol=1e-9), i
+
+
+def test_homography_4pt_matches_oracle(cabi):
+    x1s, x2s = [], []
+    for i in range(300):
+        x1, x2, H = G.minimal_homography(i)
+        x1s.append(x1)
+        x2s.append(x2)
+    a, b = _noisy_samples(4, 300, 3)
+    x1s, x2s = np.concatenate([np.array(x1s), a]), np.concatenate([np.array(x2s), b])
+    Hs, n = cabi.homography_4pt_batch(x1s, x2s)
+    for i in range(len(x1s)):
+        nr, ref = P.homography_4pt(x1s[i], x2s[i])
+        assert n[i] == nr, i
+        if nr:
+            assert np.allclose(Hs[i], ref, rtol=1e-10, atol=1e-12), i
+
+
+# ---------------------------------------------------------------------------------------------- RANSAC
+def _same_trajectory(g, o, model_tol=1e-6):
+    for k in ("iterations", "refinements", "num_inliers"):
+        assert g["stats"][k] == o["stats"][k], (k, g["stats"], o["stats"])
+    assert np.isclose(g["stats"]["model_score"], o["stats"]["model_score"], rtol=1e-9), (g["stats"], o["stats"])
+    assert np.isclose(g["stats"]["inlier_ratio"], o["stats"]["inlier_ratio"], rtol=0, atol=1e-15)
+    assert np.array_equal(g["inliers"], o["inliers"]), int((g["inliers"] != o["inliers"]).sum())
+    gm, om = np.asarray(g["model"]), np.asarray(o["model"])
+    assert np.allclose(gm, om, rtol=model_tol, atol=model_tol * np.abs(om).max()), (gm, om)
+    assert g["counters"]["samples"] == o["counters"]["samples"]
+    assert g["counters"]["hypotheses"] == o["counters"]["hypotheses"]
+    assert g["counters"]["lo_calls"] == o["counters"]["lo_calls"]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("n,ratio,its", [(200, 0.5, 1000), (1500, 0.35, 3000)])
+def test_ransac_pnp_matches_oracle(cabi, n, ratio, its, seed):
+    p = G.abspose_problem(n, ratio, 1, seed)
+    x = p["x"] / G.FOCAL
+    kw = dict(max_iterations=its, min_iterations=min(its, 1000), seed=seed)
+    g = cabi.ransac("pnp", x, p["X"], cabi.RansacOpt(**kw), 12.0 / G.FOCAL)
+    o = P.ransac("pnp", x, p["X"], P.RansacOpt(**kw), 12.0 / G.FOCAL)
+    _same_trajectory(g, o)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("n,ratio", [(1000, 0.5), (10000, 0.3)])
+def test_ransac_relpose_matches_oracle(cabi, n, ratio, seed):
+    p = G.relpose_problem(n, ratio, 2, seed)
+    x1, x2 = p["x1"] / G.FOCAL, p["x2"] / G.FOCAL
+    kw = dict(max_iterations=100000, min_iterations=1000, seed=seed)
+    g = cabi.ransac("relpose", x1, x2, cabi.RansacOpt(**kw), 1.0 / G.FOCAL)
+    o = P.ransac("relpose", x1, x2, P.RansacOpt(**kw), 1.0 / G.FOCAL)
+    _same_trajectory(g, o)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+@pytest.mark.parametrize("prosac,rfc", [(False, False), (True, True)])
+def test_ransac_fundamental_matches_oracle(cabi, prosac, rfc, seed):
+    p = G.relpose_problem(2000, 0.3, 3, seed, prosac_sorted=prosac)
+    x1, x2 = p["x1"] / 500.0, p["x2"] / 500.0  # uncalibrated-style scaling, pp at origin for RFC
+    kw = dict(max_iterations=20000, min_iterations=1000, seed=seed, progressive_sampling=prosac,
+              max_prosac_iterations=5000)
+    g = cabi.ransac("fundamental", x1, x2, cabi.RansacOpt(**kw), 1.0 / 500.0, rfc=rfc)
+    o = P.ransac("fundamental", x1, x2, P.RansacOpt(**kw), 1.0 / 500.0, rfc=rfc)
+    _same_trajectory(g, o)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+@pytest.mark.parametrize("n,ratio", [(2000, 0.6), (20000, 0.6)])
+def test_ransac_homography_matches_oracle(cabi, n, ratio, seed):
+    p = G.homography_problem(n, ratio, 4, seed)
+    x1, x2 = p["x1"] / G.FOCAL, p["x2"] / G.FOCAL
+    kw = dict(max_iterations=100000, min_iterations=1000, seed=seed)
+    g = cabi.ransac("homography", x1, x2, cabi.RansacOpt(**kw), 1.0 / G.FOCAL)
+    o = P.ransac("homography", x1, x2, P.RansacOpt(**kw), 1.0 / G.FOCAL)
+    _same_trajectory(g, o)
+
+
+def test_score_initial_model_and_edge_sizes(cabi):
+    p = G.relpose_problem(800, 0.5, 2, 11)
+    x1, x2 = p["x1"] / G.FOCAL, p["x2"] / G.FOCAL
+    init = np.r_[p["q_gt"], p["t_gt"]]
+    kw = dict(max_iterations=2000, min_iterations=50, seed=5, score_initial_model=True)
+    g = cabi.ransac("relpose", x1, x2, cabi.RansacOpt(**kw), 1.0 / G.FOCAL, init=init)
+    o = P.ransac("relpose", x1, x2, P.RansacOpt(**kw), 1.0 / G.FOCAL, init=init)
+    _same_trajectory(g, o)
+    # fewer points than the sample size: default stats, identity model, mask of the identity model
+    g = cabi.ransac("relpose", x1[:4], x2[:4], cabi.RansacOpt(), 1.0 / G.FOCAL)
+    o = P.ransac("relpose", x1[:4], x2[:4], P.RansacOpt(), 1.0 / G.FOCAL)
+    assert g["stats"]["iterations"] == 0 and g["stats"]["model_score"] == o["stats"]["model_score"]
+    assert np.array_equal(g["inliers"], o["inliers"]) and np.array_equal(g["model"], o["model"])
+    # exactly the sample size; max_iterations smaller than min_iterations
+    kw = dict(max_iterations=7, min_iterations=1000, seed=1)
+    g = cabi.ransac("relpose", x1[:5], x2[:5], cabi.RansacOpt(**kw), 1.0 / G.FOCAL)
+    o = P.ransac("relpose", x1[:5], x2[:5], P.RansacOpt(**kw), 1.0 / G.FOCAL)
+    _same_trajectory(g, o)
+
+
+# ---------------------------------------------------------------------------------------------- estimate_*
+def test_estimate_entry_points_match_oracle(cabi):
+    cam = cabi.Camera("PINHOLE", (G.FOCAL, G.FOCAL, 0.0, 0.0))
+    camt = (G.FOCAL, G.FOCAL, 0.0, 0.0)
+    p = G.config_c1(3)
+    g = cabi.estimate("pnp", p["x"], p["X"], cabi.RansacOpt(**p["ransac"]), cabi.BundleOpt(), p["max_error"], cam)
+    o = P.estimate("pnp", p["x"], p["X"], P.RansacOpt(**p["ransac"]), P.BundleOpt(), p["max_error"], camt)
+    _same_trajectory(g, o)
+    p = G.relpose_problem(3000, 0.4, 2, 5)
+    kw = dict(max_iterations=20000, min_iterations=500, seed=2)
+    g = cabi.estimate("relpose", p["x1"], p["x2"], cabi.RansacOpt(**kw), cabi.BundleOpt(), 1.0, cam, cam)
+    o = P.estimate("relpose", p["x1"], p["x2"], P.RansacOpt(**kw), P.BundleOpt(), 1.0, camt, camt)
+    _same_trajectory(g, o)
+    p = G.relpose_problem(2000, 0.4, 3, 6, prosac_sorted=True)
+    kw = dict(max_iterations=20000, min_iterations=500, seed=2, progressive_sampling=True)
+    g = cabi.estimate("fundamental", p["x1"], p["x2"], cabi.RansacOpt(**kw), cabi.BundleOpt(), 1.0, rfc=True)
+    o = P.estimate("fundamental", p["x1"], p["x2"], P.RansacOpt(**kw), P.BundleOpt(), 1.0, rfc=True)
+    _same_trajectory(g, o)
+    p = G.homography_problem(3000, 0.6, 4, 7)
+    kw = dict(max_iterations=20000, min_iterations=500, seed=2)
+    g = cabi.estimate("homography", p["x1"], p["x2"], cabi.RansacOpt(**kw), cabi.BundleOpt(), 1.0)
+    o = P.estimate("homography", p["x1"], p["x2"], P.RansacOpt(**kw), P.BundleOpt(), 1.0)
+    _same_trajectory(g, o)
+
+
+def test_batch_api_matches_single_calls(cabi):
+    probs, singles = [], []
+    for i in range(6):
+        if i % 2 == 0:
+            p = G.abspose_problem(200, 0.5, 5, i)
+            a, b, kind, me = p["x"] / G.FOCAL, p["X"], "pnp", 12.0 / G.FOCAL
+            kw = dict(max_iterations=1000, min_iterations=1000, seed=i)
+        else:
+            p = G.relpose_problem(3000, 0.35, 5, i)
+            a, b, kind, me = p["x1"] / G.FOCAL, p["x2"] / G.FOCAL, "relpose", 1.0 / G.FOCAL
+            kw = dict(max_iterations=50000, min_iterations=1000, seed=i)
+        probs.append(dict(kind=kind, a=a, b=b, ransac=cabi.RansacOpt(**kw), max_error=me))
+        singles.append(P.ransac(kind, a, b, P.RansacOpt(**kw), me))
+    res = cabi.ransac_batch(probs, streams=3)
+    for g, o in zip(res, singles):
+        assert g["status"] == 0
+        _same_trajectory(g, o)
