@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on its headline config (relpose_5pt essential, 10 000 2D-2D corrs, 30 % inliers,
+max 100 000 iterations), one JSON line.
+
+A step = one pass of the LO-RANSAC hot path over a batch of `--pairs` independent synthetic image pairs of that
+config (own data seed each), per GPU.  Metric = RANSAC hypotheses/s (models passed to score_model) with
+scored-correspondences/s alongside.
+  value : whole job with the correspondences already resident in HBM (plb_resident_create handles)
+  e2e   : the same batch through the reference-facing C-ABI call with HOST buffers: the host->device copy of the
+          correspondences / sample tables and the device->host read of records, models and inlier masks are inside
+          the timed region (counted from the copies the engine makes)
+  --impl reference : the CPU restatement of the reference path (oracle/, the reference itself needs Eigen3, which
+          this image lacks) on the host cores, one problem per thread, same config/metric.
+Multi-GPU (torchrun): independent image pairs are sharded across ranks, no data-path collective; weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from poselib_b200 import problem_generator as G  # noqa: E402
+
+BYTES_PER_CORR_FP64 = 32  # the exact-mode kernel reads 4 fp64 per 2D-2D correspondence
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def make_batch(pairs, first_idx):
+    probs = []
+    for i in range(pairs):
+        p = G.config_c2(first_idx + i)
+        probs.append((np.ascontiguousarray(p["x1"] / G.FOCAL), np.ascontiguousarray(p["x2"] / G.FOCAL)))
+    return probs
+
+
+def totals(results):
+    hyp = sum(r["counters"]["hypotheses"] for r in results)
+    cor = sum(r["counters"]["scored_corrs"] for r in results)
+    smp = sum(r["counters"]["samples"] for r in results)
+    return hyp, cor, smp
+
+
+def run_reference(args, rank, world):
+    """CPU arm: oracle restatement, all host threads, one problem per thread (the reference itself is single-threaded)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import plo_py as P
+    threads = os.cpu_count() or 1
+    pairs = min(args.pairs, max(threads, 8))  # bounded sample of the same workload
+    batch = make_batch(pairs, 0)
+    opts = [P.RansacOpt(max_iterations=100000, min_iterations=1000, seed=0) for _ in range(pairs)]
+    me = [1.0 / G.FOCAL] * pairs
+    x1, x2 = [b[0] for b in batch], [b[1] for b in batch]
+    for _ in range(args.warmup):
+        P.ransac_relpose_batch_mt(x1[:threads], x2[:threads], opts[:threads], me[:threads], threads)
+    t_tot, hyp, cor, smp = 0.0, 0, 0, 0
+    for _ in range(args.steps):
+        sec, _, stats, cnts = P.ransac_relpose_batch_mt(x1, x2, opts, me, threads)
+        t_tot += sec
+        hyp += sum(c["hypotheses"] for c in cnts)
+        cor += sum(c["scored_corrs"] for c in cnts)
+        smp += sum(c["samples"] for c in cnts)
+    val = hyp / t_tot
+    line = {
+        "impl": "reference", "metric": "RANSAC hypotheses/sec (5pt E, 10k corrs)", "value": val, "unit": "hypotheses/s",
+        "scored_corrs_per_s": cor / t_tot, "samples_per_s": smp / t_tot, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{pairs} x relpose_5pt C2 (10000 corrs, 30% inliers, max 100000 its), one problem per host thread",
+                   "pairs_per_step": pairs},
+        "cpu_baseline": {"value": val, "unit": "hypotheses/s", "cores": threads, "kind": "port",
+                         "sample": f"{pairs} C2 problems per step x {args.steps} steps; restated PoseLib path (no Eigen), "
+                                   "g++ -O3 -ffp-contract=off"},
+        "e2e": {"value": val, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=64, help="independent C2 image pairs per GPU per step")
+    ap.add_argument("--streams", type=int, default=8, help="problems in flight per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    from poselib_b200 import cabi
+    if not torch.cuda.is_available() or cabi.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    cabi.set_device(local_rank)
+    cabi.set_mode(args.mode)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pairs = args.pairs
+    batch = make_batch(pairs, rank * pairs)  # every rank gets its own image pairs (weak scaling)
+    n = len(batch[0][0])
+    ropt = dict(max_iterations=100000, min_iterations=1000, seed=0)
+    host_probs = [dict(kind="relpose", a=a, b=b, ransac=cabi.RansacOpt(**ropt), max_error=1.0 / G.FOCAL) for a, b in batch]
+    handles = [cabi.resident_create("relpose", a, b) for a, b in batch]
+    res_probs = [dict(kind="relpose", resident=h, n=n, ransac=cabi.RansacOpt(**ropt), max_error=1.0 / G.FOCAL)
+                 for h in handles]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(probs, steps):
+        t_tot, agg, last = 0.0, None, None
+        for _ in range(steps):
+            flush.zero_()  # L2 flush between timed iterations (untimed)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            last = cabi.ransac_batch(probs, streams=args.streams)  # returns after its own stream syncs
+            torch.cuda.synchronize()
+            t_tot += time.perf_counter() - t0
+            c = {k: sum(r["counters"][k] for r in last) for k in last[0]["counters"]}
+            agg = c if agg is None else {k: agg[k] + c[k] for k in c}
+        return t_tot, agg, last
+
+    for _ in range(args.warmup):
+        cabi.ransac_batch(res_probs, streams=args.streams)
+        cabi.ransac_batch(host_probs, streams=args.streams)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_res, c_res, _ = timed(res_probs, args.steps)
+    barrier()
+    t_e2e, c_e2e, last = timed(host_probs, args.steps)
+    barrier()
+    sampler.stop_flag = True
+
+    def allmax(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if dist is None:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    T_res, T_e2e = allmax(t_res), allmax(t_e2e)
+    hyp, cor, smp = allsum(c_res["hypotheses"]), allsum(c_res["scored_corrs"]), allsum(c_res["samples"])
+    hyp_e, cor_e = allsum(c_e2e["hypotheses"]), allsum(c_e2e["scored_corrs"])
+    launches = allsum(c_res["gpu_launches"])
+    if rank == 0:
+        peak, peak_kind = load_peaks()
+        # roofline of the dominant kernel (k_hyp<relpose>: fused 5pt solve + Sampson/cheirality MSAC scoring):
+        # algorithmic bytes = models scored by the launches x N x 32 B (fp64 SoA) ; duration = CUDA events around
+        # every launch on the engine's stream (rank 0)
+        alg_bytes = c_res["models_evaluated"] * n * BYTES_PER_CORR_FP64
+        k_sec = c_res["gpu_seconds"]
+        ach = alg_bytes / k_sec / 1e9 if k_sec > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_k_hyp_relpose.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        line = {
+            "metric": "RANSAC hypotheses/sec (5pt E, 10k corrs)", "value": hyp / T_res, "unit": "hypotheses/s",
+            "scored_corrs_per_s": cor / T_res, "samples_per_s": smp / T_res,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T_res / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{pairs} x relpose_5pt C2 (10000 corrs, 30% inliers, max 100000 its) per GPU per step",
+                       "pairs_per_step_per_gpu": pairs, "streams": args.streams, "mode": args.mode,
+                       "l2": "flushed (256 MiB write) between timed steps", "timing": "host clock around synchronous "
+                       "C-ABI calls, cuda synchronize both sides, max over ranks; kernel time by CUDA events"},
+            "e2e": {"value": hyp_e / T_e2e, "unit": "hypotheses/s", "scored_corrs_per_s": cor_e / T_e2e,
+                    "ms_per_step": 1e3 * T_e2e / args.steps,
+                    "h2d_bytes_per_step": c_e2e["h2d_bytes"] // args.steps, "d2h_bytes_per_step": c_e2e["d2h_bytes"] // args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_hyp<relpose_5pt> (fused solve + score)", "achieved": ach,
+                         "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "algorithmic_bytes_per_step": alg_bytes / args.steps, "kernel_seconds_per_step": k_sec / args.steps,
+                         "kernel_share_of_step": k_sec / t_res if t_res > 0 else None,
+                         "note": "correspondences of one problem (320 KB fp64) are L2-resident: DRAM traffic << algorithmic bytes by design"},
+            "clocks": sampler.summary(),
+        }
+        # CPU baseline on this box's host cores: 1 thread (the reference's execution model), bounded sample
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import plo_py as P
+            k = min(8, pairs)
+            sec, _, _, cnts = P.ransac_relpose_batch_mt([b[0] for b in batch[:k]], [b[1] for b in batch[:k]],
+                                                         [P.RansacOpt(**ropt) for _ in range(k)], [1.0 / G.FOCAL] * k, 1)
+            line["cpu_baseline"] = {"value": sum(c["hypotheses"] for c in cnts) / sec, "unit": "hypotheses/s",
+                                    "scored_corrs_per_s": sum(c["scored_corrs"] for c in cnts) / sec, "cores": 1,
+                                    "kind": "port", "sample": f"first {k} problems of the step, 1 thread, restated "
+                                    "PoseLib path (no Eigen), g++ -O3 -ffp-contract=off", "seconds": sec,
+                                    "host_cpus": os.cpu_count()}
+        except Exception as e:  # the baseline is a reported number, never part of the product path
+            line["cpu_baseline"] = {"value": None, "unit": "hypotheses/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    for h in handles:
+        cabi.resident_free(h)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

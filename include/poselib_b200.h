@@ -81,6 +81,9 @@ typedef struct plb_counters {
     uint64_t gpu_launches;  /* kernels launched for this call */
     uint64_t samples_evaluated; /* incl. speculative samples past the serial break point */
     double gpu_seconds;     /* CUDA-event time of the hypothesis kernels */
+    uint64_t h2d_bytes;     /* bytes copied host -> device for this call */
+    uint64_t d2h_bytes;     /* bytes copied device -> host for this call */
+    uint64_t models_evaluated; /* models scored by the hypothesis kernels incl. speculative samples */
 } plb_counters;
 
 /* misc/camera_models.h:59-157 Camera, restricted to the models the path needs (others -> PLB_ERR_NYI) */
@@ -144,6 +147,18 @@ int plb_relpose_7pt_batch(size_t count, const double *x1 /*count*7*3*/, const do
 int plb_homography_4pt_batch(size_t count, const double *x1 /*count*4*3*/, const double *x2,
                              double *H_out /*count*9*/, int32_t *n_out, int check_cheirality);
 
+/* ---- PoseLib/robust/bundle.h: bundle_adjust (calibrated, :50-52), refine_relpose (:100-102), refine_fundamental
+ * (:133-135), refine_homography (:150-152) — the LM refiners the LO step and the final polish are built from.
+ * Uniform weights.  bundle_stats_out (may be NULL): {iterations, initial_cost, cost}. ------------------------- */
+int plb_bundle_adjust(const double *x_xy, const double *X_xyz, size_t n, double pose_inout[7],
+                      const plb_bundle_opt *opt, double bundle_stats_out[3]);
+int plb_refine_relpose(const double *x1_xy, const double *x2_xy, size_t n, double pose_inout[7],
+                       const plb_bundle_opt *opt, double bundle_stats_out[3]);
+int plb_refine_fundamental(const double *x1_xy, const double *x2_xy, size_t n, double F_inout[9],
+                           const plb_bundle_opt *opt, double bundle_stats_out[3]);
+int plb_refine_homography(const double *x1_xy, const double *x2_xy, size_t n, double H_inout[9],
+                          const plb_bundle_opt *opt, double bundle_stats_out[3]);
+
 /* ---- batch of independent problems (BASELINE config 5); sharded by the caller across GPUs ---------- */
 enum { PLB_KIND_PNP = 0, PLB_KIND_RELPOSE = 1, PLB_KIND_FUNDAMENTAL = 2, PLB_KIND_HOMOGRAPHY = 3 };
 typedef struct plb_problem {
@@ -159,10 +174,15 @@ typedef struct plb_problem {
     plb_ransac_stats stats;   /* out */
     plb_counters counters;    /* out */
     int32_t status;           /* out: PLB_OK / error */
-    int32_t reserved;
+    int32_t resident;         /* > 0: handle from plb_resident_create, a/b are ignored (points already in HBM) */
 } plb_problem;
 /* Runs ransac_{pnp,relpose,fundamental,homography} on every problem; `streams` problems are in flight at once. */
 int plb_ransac_batch(plb_problem *problems, size_t count, int streams);
+
+/* Correspondences kept resident in HBM across calls (measurement of the device-resident throughput, and callers
+ * that run several estimations on the same matches).  kind: PLB_KIND_*; returns a handle > 0 or an error < 0. */
+int plb_resident_create(int kind, const double *a, const double *b, size_t n);
+int plb_resident_free(int handle);
 
 #ifdef __cplusplus
 }

@@ -64,7 +64,8 @@ class BundleOpt(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("hypotheses", C.c_uint64), ("scored_corrs", C.c_uint64),
                 ("lo_calls", C.c_uint64), ("lo_seconds", C.c_double), ("gpu_launches", C.c_uint64),
-                ("samples_evaluated", C.c_uint64), ("gpu_seconds", C.c_double)]
+                ("samples_evaluated", C.c_uint64), ("gpu_seconds", C.c_double), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("models_evaluated", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -83,7 +84,7 @@ class Problem(C.Structure):
     _fields_ = [("kind", C.c_int32), ("real_focal_check", C.c_int32), ("n", C.c_uint64),
                 ("a", C.POINTER(C.c_double)), ("b", C.POINTER(C.c_double)), ("opt", RansacOpt),
                 ("max_error", C.c_double), ("model", C.c_double * 9), ("inliers", C.c_char_p),
-                ("stats", RansacStats), ("counters", Counters), ("status", C.c_int32), ("reserved", C.c_int32)]
+                ("stats", RansacStats), ("counters", Counters), ("status", C.c_int32), ("resident", C.c_int32)]
 
 
 EXPORTS = [
@@ -91,7 +92,9 @@ EXPORTS = [
     "plb_set_mode", "plb_ransac_pnp", "plb_ransac_relpose", "plb_ransac_fundamental", "plb_ransac_homography",
     "plb_estimate_absolute_pose", "plb_estimate_relative_pose", "plb_estimate_fundamental",
     "plb_estimate_homography", "plb_p3p_batch", "plb_relpose_5pt_batch", "plb_relpose_5pt_poses_batch",
-    "plb_relpose_7pt_batch", "plb_homography_4pt_batch", "plb_ransac_batch",
+    "plb_relpose_7pt_batch", "plb_homography_4pt_batch", "plb_ransac_batch", "plb_bundle_adjust",
+    "plb_refine_relpose", "plb_refine_fundamental", "plb_refine_homography", "plb_resident_create",
+    "plb_resident_free",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -197,6 +200,20 @@ def estimate(kind, a, b, ropt, bopt, max_error, cam1=None, cam2=None, init=None,
     return {"model": _model_out(kind, m), "inliers": mask[:n], "stats": st.as_dict(), "counters": cn.as_dict()}
 
 
+def refine(kind, model, a, b, bopt):
+    """bundle_adjust / refine_relpose / refine_fundamental / refine_homography (robust/bundle.h), uniform weights.
+    Returns (model, [iterations, initial_cost, cost])."""
+    n = len(a)
+    aa, ap = _d(a)
+    ba, bp = _d(b)
+    m = _init_model(kind, model)
+    bs = np.zeros(3)
+    fn = {"pnp": _lib.plb_bundle_adjust, "relpose": _lib.plb_refine_relpose,
+          "fundamental": _lib.plb_refine_fundamental, "homography": _lib.plb_refine_homography}[kind]
+    _check(fn(ap, bp, C.c_size_t(n), m.ctypes.data_as(_P), C.byref(bopt), bs.ctypes.data_as(_P)))
+    return _model_out(kind, m), bs
+
+
 # ---- solvers (batched; inputs [count, k, 3] unit bearings) -------------------------------------------
 def _solver(fn, a, b, per_out, extra=()):
     aa, ap = _d(a)
@@ -233,6 +250,20 @@ def homography_4pt_batch(x1, x2, check_cheirality=True):
     return out.reshape(-1, 3, 3).transpose(0, 2, 1), n
 
 
+def resident_create(kind, a, b):
+    """Uploads correspondences once and keeps them in HBM; returns a handle for ransac_batch(resident=...)."""
+    aa, ap = _d(a)
+    ba, bp = _d(b)
+    h = _lib.plb_resident_create(KIND[kind], ap, bp, C.c_size_t(len(aa)))
+    if h <= 0:
+        _check(h)
+    return h
+
+
+def resident_free(h):
+    _check(_lib.plb_resident_free(int(h)))
+
+
 # ---- batch of problems -------------------------------------------------------------------------------
 def ransac_batch(problems, streams=8):
     """problems: list of dict(kind, a, b, ransac=RansacOpt, max_error, rfc=False, init=None).
@@ -241,15 +272,21 @@ def ransac_batch(problems, streams=8):
     arr = (Problem * count)()
     keep = []
     for i, p in enumerate(problems):
-        aa, ap = _d(p["a"])
-        ba, bp = _d(p["b"])
-        mask = np.zeros(max(len(aa), 1), dtype=np.int8)
-        keep.append((aa, ba, mask))
         q = arr[i]
+        if p.get("resident"):
+            aa = ba = None
+            npts = int(p["n"])
+            q.resident = int(p["resident"])
+        else:
+            aa, ap = _d(p["a"])
+            ba, bp = _d(p["b"])
+            npts = len(aa)
+            q.a, q.b = ap, bp
+        mask = np.zeros(max(npts, 1), dtype=np.int8)
+        keep.append((aa, ba, mask))
         q.kind = KIND[p["kind"]]
         q.real_focal_check = int(p.get("rfc", False))
-        q.n = len(aa)
-        q.a, q.b = ap, bp
+        q.n = npts
         q.opt = p["ransac"]
         q.max_error = p["max_error"]
         m = _init_model(p["kind"], p.get("init"))

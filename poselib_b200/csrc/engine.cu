@@ -217,6 +217,15 @@ static Engine *pool_engine(size_t i) {
     return g_pool[i];
 }
 
+// correspondences resident in HBM (plb_resident_create)
+struct Resident {
+    DevBuf<double> soa64;
+    DevBuf<float> soa32;
+    int n = 0, n_pad = 0, kind = 0, device = 0;
+};
+static std::mutex g_res_mtx;
+static std::vector<Resident *> g_resident; // handle = index + 1
+
 // LO bundle options of the estimators (estimators/absolute_pose.cc:60-69 etc.): TRUNCATED(max_error), 25 iterations
 static LmParams lo_params(int kind, double max_error) {
     LmParams p;
@@ -265,7 +274,7 @@ struct FinalPolish { // the post-RANSAC refinement of PoseLib/robust.cc (estimat
 // One LO-RANSAC problem, points already calibrated / normalised.  `model` is 7 (pose) or 9 (column-major) doubles.
 static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, const plb_ransac_opt &opt,
                       double max_error, int rfc, double *model, char *inliers, plb_ransac_stats *stats_out,
-                      plb_counters *cnt_out, const FinalPolish &polish) {
+                      plb_counters *cnt_out, const FinalPolish &polish, const Resident *res = nullptr) {
     Engine &E = *engine();
     const int K = kind_sample_size(kind), MAXM = kind_max_models(kind), MSZ = kind_model_size(kind);
     plb_ransac_stats stats;
@@ -301,23 +310,35 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
     const int n_arr = 2 + b_dim;
 
     // ---- upload (pinned staging) + layout transform ---------------------------------------------------------
-    if ((rc = E.h_in_a.ensure(2 * (size_t)n)) || (rc = E.h_in_b.ensure((size_t)b_dim * n)) ||
-        (rc = E.in_a.ensure(2 * (size_t)n)) || (rc = E.in_b.ensure((size_t)b_dim * n)) ||
-        (rc = E.soa64.ensure((size_t)n_arr * n_pad)) || (rc = E.soa32.ensure((size_t)n_arr * n_pad)) ||
-        (rc = E.mask.ensure(n)) || (rc = E.h_mask.ensure(n)) || (rc = E.work.ensure(4)) ||
+    uint64_t h2d = 0, d2h = 0;
+    if ((rc = E.mask.ensure(n)) || (rc = E.h_mask.ensure(n)) || (rc = E.work.ensure(4)) ||
         (rc = E.model_dev.ensure(16)) || (rc = E.h_model.ensure(16)))
         return rc;
-    std::memcpy(E.h_in_a.p, a, sizeof(double) * 2 * n);
-    std::memcpy(E.h_in_b.p, b, sizeof(double) * b_dim * n);
-    PLB_CUDA(cudaMemcpyAsync(E.in_a.p, E.h_in_a.p, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
-    PLB_CUDA(cudaMemcpyAsync(E.in_b.p, E.h_in_b.p, sizeof(double) * b_dim * n, cudaMemcpyHostToDevice, st));
-    launch_transpose(E.in_a.p, E.in_b.p, n, b_dim, E.soa64.p, E.soa32.p, n_pad, st);
-    E.launches++;
+    const double *soa64 = nullptr;
+    const float *soa32 = nullptr;
+    if (res) {
+        soa64 = res->soa64.p;
+        soa32 = res->soa32.p;
+    } else {
+        if ((rc = E.h_in_a.ensure(2 * (size_t)n)) || (rc = E.h_in_b.ensure((size_t)b_dim * n)) ||
+            (rc = E.in_a.ensure(2 * (size_t)n)) || (rc = E.in_b.ensure((size_t)b_dim * n)) ||
+            (rc = E.soa64.ensure((size_t)n_arr * n_pad)) || (rc = E.soa32.ensure((size_t)n_arr * n_pad)))
+            return rc;
+        std::memcpy(E.h_in_a.p, a, sizeof(double) * 2 * n);
+        std::memcpy(E.h_in_b.p, b, sizeof(double) * b_dim * n);
+        PLB_CUDA(cudaMemcpyAsync(E.in_a.p, E.h_in_a.p, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+        PLB_CUDA(cudaMemcpyAsync(E.in_b.p, E.h_in_b.p, sizeof(double) * b_dim * n, cudaMemcpyHostToDevice, st));
+        h2d += sizeof(double) * (size_t)(2 + b_dim) * n;
+        launch_transpose(E.in_a.p, E.in_b.p, n, b_dim, E.soa64.p, E.soa32.p, n_pad, st);
+        E.launches++;
+        soa64 = E.soa64.p;
+        soa32 = E.soa32.p;
+    }
     ProblemDev P;
     std::memset(&P, 0, sizeof(P));
     for (int c = 0; c < n_arr; ++c) {
-        P.p[c] = E.soa64.p + (size_t)c * n_pad;
-        P.f[c] = E.soa32.p + (size_t)c * n_pad;
+        P.p[c] = soa64 + (size_t)c * n_pad;
+        P.f[c] = soa32 + (size_t)c * n_pad;
     }
     P.n = n;
     P.kind = kind;
@@ -432,6 +453,8 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
                 return rc;
             for (size_t s = 0; s < B; ++s) sampler.next(E.h_samples.p + s * K);
             PLB_CUDA(cudaMemcpyAsync(E.samples.p, E.h_samples.p, sizeof(uint32_t) * B * K, cudaMemcpyHostToDevice, st));
+            h2d += sizeof(uint32_t) * B * K;
+            d2h += sizeof(int) * B + (sizeof(uint32_t) + sizeof(double)) * B * MAXM;
             HypOut out;
             out.n_models = E.n_models.p;
             out.counts = E.counts.p;
@@ -451,6 +474,7 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
             cudaEventElapsedTime(&ms, E.ev0, E.ev1);
             gpu_ms_total += ms;
             cnt.samples_evaluated += B;
+            for (size_t s = 0; s < B; ++s) cnt.models_evaluated += E.h_n_models.p[s];
 
             // ---- pass 1: which models improve the best-minimal state?  (independent of LO results)
             imp_slot.clear();
@@ -496,6 +520,8 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
                 launch_lm(P, E.lm_in.p + 9 * (size_t)n_imp, n_trig, lo, nullptr, E.subset.p, E.lm_out.p, st);
                 E.launches++;
                 PLB_CUDA(cudaMemcpyAsync(E.h_lm_out.p, E.lm_out.p, sizeof(LmJobOut) * n_trig, cudaMemcpyDeviceToHost, st));
+                h2d += sizeof(int) * (n_imp + n_trig);
+                d2h += sizeof(double) * 9 * n_imp + sizeof(LmJobOut) * n_trig;
                 auto t0 = std::chrono::steady_clock::now();
                 PLB_CUDA(cudaStreamSynchronize(st));
                 lo_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -598,12 +624,64 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
     if (inliers) std::memcpy(inliers, E.h_mask.p, n);
     std::copy(best_model, best_model + MSZ, model);
 
+    d2h += n;
+    cnt.h2d_bytes = h2d;
+    cnt.d2h_bytes = d2h;
     cnt.scored_corrs = cnt.hypotheses * n_pts;
     cnt.lo_seconds = lo_wait;
     cnt.gpu_launches = E.launches - launches0;
     cnt.gpu_seconds = gpu_ms_total * 1e-3;
     if (stats_out) *stats_out = stats;
     if (cnt_out) *cnt_out = cnt;
+    return PLB_OK;
+}
+
+// One LM refinement over all n points (robust/bundle.cc:84-112,206-222,313-333,394-411)
+static int run_refine(int kind, const double *a, const double *b, size_t n_pts, double *model,
+                      const plb_bundle_opt &bopt, double *bstats) {
+    if (n_pts == 0) return PLB_OK;
+    Engine &E = *engine();
+    int rc = E.init();
+    if (rc != PLB_OK) return rc;
+    cudaStream_t st = E.stream;
+    const int n = (int)n_pts, n_pad = (n + 31) & ~31;
+    const int b_dim = (kind == KIND_PNP) ? 3 : 2, n_arr = 2 + b_dim, MSZ = kind_model_size(kind);
+    if ((rc = E.h_in_a.ensure(2 * (size_t)n)) || (rc = E.h_in_b.ensure((size_t)b_dim * n)) ||
+        (rc = E.in_a.ensure(2 * (size_t)n)) || (rc = E.in_b.ensure((size_t)b_dim * n)) ||
+        (rc = E.soa64.ensure((size_t)n_arr * n_pad)) || (rc = E.soa32.ensure((size_t)n_arr * n_pad)) ||
+        (rc = E.lm_in.ensure(9)) || (rc = E.h_lm_in.ensure(9)) || (rc = E.lm_out.ensure(1)) ||
+        (rc = E.h_lm_out.ensure(1)))
+        return rc;
+    std::memcpy(E.h_in_a.p, a, sizeof(double) * 2 * n);
+    std::memcpy(E.h_in_b.p, b, sizeof(double) * b_dim * n);
+    PLB_CUDA(cudaMemcpyAsync(E.in_a.p, E.h_in_a.p, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+    PLB_CUDA(cudaMemcpyAsync(E.in_b.p, E.h_in_b.p, sizeof(double) * b_dim * n, cudaMemcpyHostToDevice, st));
+    launch_transpose(E.in_a.p, E.in_b.p, n, b_dim, E.soa64.p, E.soa32.p, n_pad, st);
+    ProblemDev P;
+    std::memset(&P, 0, sizeof(P));
+    for (int c = 0; c < n_arr; ++c) {
+        P.p[c] = E.soa64.p + (size_t)c * n_pad;
+        P.f[c] = E.soa32.p + (size_t)c * n_pad;
+    }
+    P.n = n;
+    P.kind = kind;
+    P.sq_thr = 0.0;
+    LmParams bp = bundle_params(bopt);
+    bp.subset_mode = 0;
+    std::fill(E.h_lm_in.p, E.h_lm_in.p + 9, 0.0);
+    std::copy(model, model + MSZ, E.h_lm_in.p);
+    PLB_CUDA(cudaMemcpyAsync(E.lm_in.p, E.h_lm_in.p, sizeof(double) * 9, cudaMemcpyHostToDevice, st));
+    launch_lm(P, E.lm_in.p, 1, bp, nullptr, nullptr, E.lm_out.p, st);
+    E.launches += 2;
+    PLB_CUDA(cudaMemcpyAsync(E.h_lm_out.p, E.lm_out.p, sizeof(LmJobOut), cudaMemcpyDeviceToHost, st));
+    PLB_CUDA(cudaStreamSynchronize(st));
+    PLB_CUDA(cudaGetLastError());
+    std::copy(E.h_lm_out.p[0].model, E.h_lm_out.p[0].model + MSZ, model);
+    if (bstats) {
+        bstats[0] = E.h_lm_out.p[0].iterations;
+        bstats[1] = E.h_lm_out.p[0].initial_cost;
+        bstats[2] = E.h_lm_out.p[0].cost;
+    }
     return PLB_OK;
 }
 
@@ -952,6 +1030,32 @@ int plb_estimate_homography(const double *x1, const double *x2, size_t n, const 
     return PLB_OK;
 }
 
+// ---- robust/bundle.h refiners -------------------------------------------------------------------------------
+static int refine_entry(int kind, const double *a, const double *b, size_t n, double *model, const plb_bundle_opt *opt,
+                        double *bs) {
+    if (!opt || !model || (n > 0 && (!a || !b))) {
+        g_err = "null argument";
+        return PLB_ERR_ARG;
+    }
+    return run_refine(kind, a, b, n, model, *opt, bs);
+}
+int plb_bundle_adjust(const double *x, const double *X, size_t n, double pose[7], const plb_bundle_opt *opt,
+                      double bs[3]) {
+    return refine_entry(KIND_PNP, x, X, n, pose, opt, bs);
+}
+int plb_refine_relpose(const double *x1, const double *x2, size_t n, double pose[7], const plb_bundle_opt *opt,
+                       double bs[3]) {
+    return refine_entry(KIND_RELPOSE, x1, x2, n, pose, opt, bs);
+}
+int plb_refine_fundamental(const double *x1, const double *x2, size_t n, double F[9], const plb_bundle_opt *opt,
+                           double bs[3]) {
+    return refine_entry(KIND_FUND, x1, x2, n, F, opt, bs);
+}
+int plb_refine_homography(const double *x1, const double *x2, size_t n, double H[9], const plb_bundle_opt *opt,
+                          double bs[3]) {
+    return refine_entry(KIND_HOMOG, x1, x2, n, H, opt, bs);
+}
+
 // ---- solvers ------------------------------------------------------------------------------------------------
 static int solver_batch(int kind, int variant, size_t count, const double *a, size_t a_sz, const double *b,
                         size_t b_sz, double *out, size_t out_sz, int32_t *n_out, int flags) {
@@ -1020,6 +1124,20 @@ int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
             if (i >= count) break;
             plb_problem &p = problems[i];
             int rc;
+            if (p.resident > 0) {
+                const Resident *res = nullptr;
+                {
+                    std::lock_guard<std::mutex> lk(g_res_mtx);
+                    if ((size_t)p.resident <= g_resident.size()) res = g_resident[p.resident - 1];
+                }
+                if (!res || res->kind != p.kind) {
+                    g_err = "invalid resident handle";
+                    rc = PLB_ERR_ARG;
+                } else {
+                    rc = run_ransac(p.kind, nullptr, nullptr, (size_t)res->n, p.opt, p.max_error, p.real_focal_check,
+                                    p.model, p.inliers, &p.stats, &p.counters, FinalPolish(), res);
+                }
+            } else
             switch (p.kind) {
             case PLB_KIND_PNP:
                 rc = plb_ransac_pnp(p.a, p.b, p.n, &p.opt, p.max_error, p.model, p.inliers, &p.stats, &p.counters);
@@ -1052,6 +1170,50 @@ int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
     for (auto &t : th) t.join();
     if (first_err.load() != PLB_OK) g_err = err_msg;
     return first_err.load();
+}
+
+int plb_resident_create(int kind, const double *a, const double *b, size_t n_pts) {
+    if (kind < 0 || kind > 3 || !a || !b || n_pts == 0 || n_pts > (1u << 26)) {
+        g_err = "bad argument";
+        return PLB_ERR_ARG;
+    }
+    Engine &E = *engine();
+    int rc = E.init();
+    if (rc != PLB_OK) return rc;
+    const int n = (int)n_pts, n_pad = (n + 31) & ~31, b_dim = (kind == KIND_PNP) ? 3 : 2, n_arr = 2 + b_dim;
+    Resident *R = new Resident();
+    DevBuf<double> da, db;
+    if ((rc = R->soa64.ensure((size_t)n_arr * n_pad)) || (rc = R->soa32.ensure((size_t)n_arr * n_pad)) ||
+        (rc = da.ensure(2 * (size_t)n)) || (rc = db.ensure((size_t)b_dim * n))) {
+        delete R;
+        return rc;
+    }
+    PLB_CUDA(cudaMemcpyAsync(da.p, a, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, E.stream));
+    PLB_CUDA(cudaMemcpyAsync(db.p, b, sizeof(double) * b_dim * n, cudaMemcpyHostToDevice, E.stream));
+    launch_transpose(da.p, db.p, n, b_dim, R->soa64.p, R->soa32.p, n_pad, E.stream);
+    PLB_CUDA(cudaStreamSynchronize(E.stream));
+    R->n = n;
+    R->n_pad = n_pad;
+    R->kind = kind;
+    R->device = E.device;
+    std::lock_guard<std::mutex> lk(g_res_mtx);
+    for (size_t i = 0; i < g_resident.size(); ++i)
+        if (!g_resident[i]) {
+            g_resident[i] = R;
+            return (int)i + 1;
+        }
+    g_resident.push_back(R);
+    return (int)g_resident.size();
+}
+int plb_resident_free(int handle) {
+    std::lock_guard<std::mutex> lk(g_res_mtx);
+    if (handle <= 0 || (size_t)handle > g_resident.size() || !g_resident[handle - 1]) {
+        g_err = "invalid resident handle";
+        return PLB_ERR_ARG;
+    }
+    delete g_resident[handle - 1];
+    g_resident[handle - 1] = nullptr;
+    return PLB_OK;
 }
 
 } // extern "C"

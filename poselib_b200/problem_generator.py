@@ -62,21 +62,30 @@ def abspose_problem(n, inlier_ratio, config_id=1, problem_idx=0):
 def relpose_problem(n, inlier_ratio, config_id=2, problem_idx=0, prosac_sorted=False):
     """2D-2D correspondences in pixels for two PINHOLE f=1000 cameras; |t| = 1."""
     rng = _rng(config_id, problem_idx)
-    R, q = _random_rotation(rng)
-    t = rng.uniform(-1, 1, size=3)
-    t /= np.linalg.norm(t)
+    # Additions to the minimal generator (which checks nothing): the pose is redrawn until the two views overlap,
+    # and only points in front of and inside the field of view of camera 2 are kept.
+    while True:
+        R, q = _random_rotation(rng)
+        t = rng.uniform(-1, 1, size=3)
+        t /= np.linalg.norm(t)
+        x1, uv = _bearings(rng, 256)
+        X2 = (x1 * rng.uniform(0.1, 10.0, size=256)[:, None]) @ R.T + t
+        vis = (X2[:, 2] > 0.05) & (np.abs(X2[:, :2] / np.maximum(X2[:, 2:3], 1e-9)) <= FOV_SCALE).all(axis=1)
+        if vis.mean() >= 0.2:
+            break
     uv1 = np.zeros((n, 2))
     uv2 = np.zeros((n, 2))
     filled = 0
-    while filled < n:  # keep points in front of camera 2 (addition; the minimal generator does not check)
-        m = n - filled
+    while filled < n:
+        m = max(2 * (n - filled), 64)
         x1, uv = _bearings(rng, m)
         depth = rng.uniform(0.1, 10.0, size=m)
         X2 = (x1 * depth[:, None]) @ R.T + t
-        ok = X2[:, 2] > 0.05
-        k = int(ok.sum())
-        uv1[filled:filled + k] = uv[ok]
-        uv2[filled:filled + k] = X2[ok, :2] / X2[ok, 2:3]
+        h = X2[:, :2] / np.maximum(X2[:, 2:3], 1e-9)
+        ok = (X2[:, 2] > 0.05) & (np.abs(h) <= FOV_SCALE).all(axis=1)
+        k = min(int(ok.sum()), n - filled)
+        uv1[filled:filled + k] = uv[ok][:k]
+        uv2[filled:filled + k] = h[ok][:k]
         filled += k
     px1 = FOCAL * uv1 + rng.normal(0, NOISE_PX, size=(n, 2))
     px2 = FOCAL * uv2 + rng.normal(0, NOISE_PX, size=(n, 2))
