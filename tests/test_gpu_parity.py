@@ -114,6 +114,8 @@ def _same_trajectory(g, o, model_tol=1e-6, relpose=False):
     assert np.isclose(g["stats"]["inlier_ratio"], o["stats"]["inlier_ratio"], rtol=0, atol=1e-15)
     assert np.array_equal(g["inliers"], o["inliers"]), int((g["inliers"] != o["inliers"]).sum())
     gm, om = np.asarray(g["model"]), np.asarray(o["model"])
+    assert np.array_equal(np.isnan(gm), np.isnan(om))
+    gm, om = np.nan_to_num(gm), np.nan_to_num(om)  # degenerate inputs give NaN models on both sides
     if gm.ndim == 2:  # F / H are projective entities: defined up to sign (the SVD factorisation of the F refiner
         #               may legitimately return either sign, optim_utils.h:59-73)
         err = min(np.abs(gm - om).max(), np.abs(gm + om).max())
