@@ -155,6 +155,27 @@ template <typename T> struct PinBuf {
     }
 };
 
+// Pinned host memory mapped into the device address space: kernels write small result records straight to it.
+template <typename T> struct MapBuf {
+    T *p = nullptr;  // host pointer
+    T *d = nullptr;  // device alias
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return PLB_OK;
+        if (p) cudaFreeHost(p);
+        p = d = nullptr;
+        cap = 0;
+        const size_t want = std::max<size_t>(n, 64);
+        PLB_CUDA(cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocMapped | cudaHostAllocPortable));
+        PLB_CUDA(cudaHostGetDevicePointer((void **)&d, p, 0));
+        cap = want;
+        return PLB_OK;
+    }
+    ~MapBuf() {
+        if (p) cudaFreeHost(p);
+    }
+};
+
 __global__ void k_gather_models(const double *__restrict__ models, const int *__restrict__ slots, int n, int msz,
                                 double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,17 +189,20 @@ struct Engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ready = false;
     int device = -1;
-    DevBuf<double> in_a, in_b, soa64, px64, models, scores, lm_in, model_dev;
+    DevBuf<double> in_a, in_b, soa64, px64, models, lm_in, model_dev;
     DevBuf<float> soa32, fscores;
-    DevBuf<uint32_t> samples, counts, fcounts;
-    DevBuf<int> n_models, work, slots;
-    DevBuf<char> mask, subset;
-    DevBuf<LmJobOut> lm_out;
-    PinBuf<double> h_in_a, h_in_b, h_scores, h_lm_in, h_model;
-    PinBuf<uint32_t> h_samples, h_counts;
-    PinBuf<int> h_n_models, h_slots;
+    DevBuf<uint32_t> samples, fcounts;
+    DevBuf<int> work, slots, subset;
+    DevBuf<char> mask;
+    PinBuf<double> h_in_a, h_in_b, h_lm_in, h_model;
+    PinBuf<uint32_t> h_samples;
+    PinBuf<int> h_slots;
     PinBuf<char> h_mask;
-    PinBuf<LmJobOut> h_lm_out;
+    // result records written by the kernels directly into mapped pinned memory (no explicit D2H copies)
+    MapBuf<double> h_scores;
+    MapBuf<uint32_t> h_counts;
+    MapBuf<int> h_n_models, h_first_slot;
+    MapBuf<LmJobOut> h_lm_out;
     uint64_t launches = 0;
 
     int init() {
@@ -311,7 +335,7 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
 
     // ---- upload (pinned staging) + layout transform ---------------------------------------------------------
     uint64_t h2d = 0, d2h = 0;
-    if ((rc = E.mask.ensure(n)) || (rc = E.h_mask.ensure(n)) || (rc = E.work.ensure(4)) ||
+    if ((rc = E.mask.ensure(n)) || (rc = E.h_mask.ensure(n)) || (rc = E.work.ensure(8)) ||
         (rc = E.model_dev.ensure(16)) || (rc = E.h_model.ensure(16)))
         return rc;
     const double *soa64 = nullptr;
@@ -362,13 +386,13 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
     // Runs LM jobs on `njobs` models staged in E.h_lm_in (9 doubles each) and returns with E.h_lm_out filled.
     auto run_lm_host_models = [&](int njobs, const LmParams &prm, const char *mask_dev, const ProblemDev &PP) -> int {
         int r;
-        if ((r = E.lm_in.ensure(9 * (size_t)njobs)) || (r = E.lm_out.ensure(njobs)) || (r = E.h_lm_out.ensure(njobs)))
-            return r;
-        if (prm.subset_mode == 1 && (r = E.subset.ensure((size_t)njobs * n))) return r;
+        if ((r = E.lm_in.ensure(9 * (size_t)njobs)) || (r = E.h_lm_out.ensure(njobs))) return r;
+        if (prm.subset_mode != 0 && (r = E.subset.ensure((size_t)njobs * n_pad))) return r;
         PLB_CUDA(cudaMemcpyAsync(E.lm_in.p, E.h_lm_in.p, sizeof(double) * 9 * njobs, cudaMemcpyHostToDevice, st));
-        launch_lm(PP, E.lm_in.p, njobs, prm, mask_dev, E.subset.p, E.lm_out.p, st);
+        launch_lm(PP, E.lm_in.p, njobs, prm, mask_dev, E.subset.p, n_pad, E.h_lm_out.d, st);
         E.launches++;
-        PLB_CUDA(cudaMemcpyAsync(E.h_lm_out.p, E.lm_out.p, sizeof(LmJobOut) * njobs, cudaMemcpyDeviceToHost, st));
+        h2d += sizeof(double) * 9 * njobs;
+        d2h += sizeof(LmJobOut) * njobs;
         auto t0 = std::chrono::steady_clock::now();
         PLB_CUDA(cudaStreamSynchronize(st));
         lo_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -389,13 +413,13 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
         if (opt.score_initial_model) {
             std::copy(model, model + MSZ, E.h_model.p);
             PLB_CUDA(cudaMemcpyAsync(E.model_dev.p, E.h_model.p, sizeof(double) * MSZ, cudaMemcpyHostToDevice, st));
-            if ((rc = E.counts.ensure(64)) || (rc = E.scores.ensure(64)) || (rc = E.h_counts.ensure(64)) ||
-                (rc = E.h_scores.ensure(64)))
-                return rc;
-            launch_score_models(P, E.model_dev.p, 1, E.counts.p, E.scores.p, st);
+            if ((rc = E.h_counts.ensure(64)) || (rc = E.h_scores.ensure(64))) return rc;
+            {
+                const int one = 1;
+                PLB_CUDA(cudaMemcpyAsync(E.work.p + 2, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+            }
+            launch_score_models(P, E.model_dev.p, 1, E.work.p + 2, E.h_counts.d, E.h_scores.d, st);
             E.launches++;
-            PLB_CUDA(cudaMemcpyAsync(E.h_counts.p, E.counts.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            PLB_CUDA(cudaMemcpyAsync(E.h_scores.p, E.scores.p, sizeof(double), cudaMemcpyDeviceToHost, st));
             PLB_CUDA(cudaStreamSynchronize(st));
             const size_t ic = E.h_counts.p[0];
             const double sc = E.h_scores.p[0];
@@ -446,35 +470,38 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
 
             chunk = std::min(CHUNK_MAX, chunk * 2);
 
-            if ((rc = E.h_samples.ensure(B * K)) || (rc = E.samples.ensure(B * K)) || (rc = E.n_models.ensure(B)) ||
-                (rc = E.h_n_models.ensure(B)) || (rc = E.counts.ensure(B * MAXM)) || (rc = E.scores.ensure(B * MAXM)) ||
-                (rc = E.h_counts.ensure(B * MAXM)) || (rc = E.h_scores.ensure(B * MAXM)) ||
-                (rc = E.models.ensure(B * MAXM * MSZ)))
+            if ((rc = E.h_samples.ensure(B * K)) || (rc = E.samples.ensure(B * K)) || (rc = E.h_n_models.ensure(B)) ||
+                (rc = E.h_first_slot.ensure(B)) || (rc = E.h_counts.ensure(B * MAXM)) ||
+                (rc = E.h_scores.ensure(B * MAXM)) || (rc = E.models.ensure(B * MAXM * MSZ)))
                 return rc;
             for (size_t s = 0; s < B; ++s) sampler.next(E.h_samples.p + s * K);
             PLB_CUDA(cudaMemcpyAsync(E.samples.p, E.h_samples.p, sizeof(uint32_t) * B * K, cudaMemcpyHostToDevice, st));
             h2d += sizeof(uint32_t) * B * K;
-            d2h += sizeof(int) * B + (sizeof(uint32_t) + sizeof(double)) * B * MAXM;
+            d2h += 2 * sizeof(int) * B; // n_models + first_slot (records are added once the model count is known)
             HypOut out;
-            out.n_models = E.n_models.p;
-            out.counts = E.counts.p;
-            out.scores = E.scores.p;
+            out.n_models = E.h_n_models.d;
+            out.first_slot = E.h_first_slot.d;
+            out.model_count = E.work.p + 1;
+            out.counts = E.h_counts.d;
+            out.scores = E.h_scores.d;
             out.models = E.models.p;
             out.fscores = nullptr;
             out.fcounts = nullptr;
             PLB_CUDA(cudaEventRecord(E.ev0, st));
             launch_hypotheses(P, E.samples.p, (int)B, E.work.p, out, g_mode.load(), st);
             PLB_CUDA(cudaEventRecord(E.ev1, st));
-            E.launches++;
-            PLB_CUDA(cudaMemcpyAsync(E.h_n_models.p, E.n_models.p, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-            PLB_CUDA(cudaMemcpyAsync(E.h_counts.p, E.counts.p, sizeof(uint32_t) * B * MAXM, cudaMemcpyDeviceToHost, st));
-            PLB_CUDA(cudaMemcpyAsync(E.h_scores.p, E.scores.p, sizeof(double) * B * MAXM, cudaMemcpyDeviceToHost, st));
+            E.launches += 2; // k_solve + k_score
             PLB_CUDA(cudaStreamSynchronize(st));
             float ms = 0.f;
             cudaEventElapsedTime(&ms, E.ev0, E.ev1);
             gpu_ms_total += ms;
             cnt.samples_evaluated += B;
-            for (size_t s = 0; s < B; ++s) cnt.models_evaluated += E.h_n_models.p[s];
+            {
+                size_t nmod = 0;
+                for (size_t s = 0; s < B; ++s) nmod += E.h_n_models.p[s];
+                cnt.models_evaluated += nmod;
+                d2h += (sizeof(uint32_t) + sizeof(double)) * nmod;
+            }
 
             // ---- pass 1: which models improve the best-minimal state?  (independent of LO results)
             imp_slot.clear();
@@ -486,8 +513,9 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
                 for (size_t s = 0; s < B; ++s) {
                     const int nm = E.h_n_models.p[s];
                     int last = -1;
+                    const size_t first = (size_t)E.h_first_slot.p[s];
                     for (int m = 0; m < nm; ++m) {
-                        const size_t slot = s * MAXM + m;
+                        const size_t slot = first + m;
                         const size_t ic = E.h_counts.p[slot];
                         const double sc = E.h_scores.p[slot];
                         const bool more = ic > bc, better = sc < bs;
@@ -507,7 +535,7 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
                 // gather improving models, refine the trigger models (batched LO), fetch both
                 if ((rc = E.h_slots.ensure(n_imp + n_trig)) || (rc = E.slots.ensure(n_imp + n_trig)) ||
                     (rc = E.lm_in.ensure(9 * (size_t)(n_imp + n_trig))) || (rc = E.h_lm_in.ensure(9 * (size_t)(n_imp + n_trig))) ||
-                    (rc = E.lm_out.ensure(n_trig)) || (rc = E.h_lm_out.ensure(n_trig)))
+                    (rc = E.h_lm_out.ensure(n_trig)))
                     return rc;
                 for (int i = 0; i < n_imp; ++i) E.h_slots.p[i] = imp_slot[i];
                 for (int j = 0; j < n_trig; ++j) E.h_slots.p[n_imp + j] = imp_slot[trig[j]];
@@ -516,10 +544,9 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
                 k_gather_models<<<(tot + 127) / 128, 128, 0, st>>>(E.models.p, E.slots.p, n_imp + n_trig, MSZ, E.lm_in.p);
                 E.launches++;
                 PLB_CUDA(cudaMemcpyAsync(E.h_lm_in.p, E.lm_in.p, sizeof(double) * 9 * n_imp, cudaMemcpyDeviceToHost, st));
-                if (lo.subset_mode == 1 && (rc = E.subset.ensure((size_t)n_trig * n))) return rc;
-                launch_lm(P, E.lm_in.p + 9 * (size_t)n_imp, n_trig, lo, nullptr, E.subset.p, E.lm_out.p, st);
+                if (lo.subset_mode != 0 && (rc = E.subset.ensure((size_t)n_trig * n_pad))) return rc;
+                launch_lm(P, E.lm_in.p + 9 * (size_t)n_imp, n_trig, lo, nullptr, E.subset.p, n_pad, E.h_lm_out.d, st);
                 E.launches++;
-                PLB_CUDA(cudaMemcpyAsync(E.h_lm_out.p, E.lm_out.p, sizeof(LmJobOut) * n_trig, cudaMemcpyDeviceToHost, st));
                 h2d += sizeof(int) * (n_imp + n_trig);
                 d2h += sizeof(double) * 9 * n_imp + sizeof(LmJobOut) * n_trig;
                 auto t0 = std::chrono::steady_clock::now();
@@ -610,13 +637,12 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
             bp.use_camera = 1;
             for (int i = 0; i < 4; ++i) bp.cam[i] = polish.cam[i];
         }
-        if ((rc = E.lm_in.ensure(9)) || (rc = E.lm_out.ensure(1)) || (rc = E.h_lm_out.ensure(1))) return rc;
+        if ((rc = E.lm_in.ensure(9)) || (rc = E.h_lm_out.ensure(1)) || (rc = E.subset.ensure(n_pad))) return rc;
         std::fill(E.h_lm_in.p, E.h_lm_in.p + 9, 0.0);
         std::copy(best_model, best_model + MSZ, E.h_lm_in.p);
         PLB_CUDA(cudaMemcpyAsync(E.lm_in.p, E.h_lm_in.p, sizeof(double) * 9, cudaMemcpyHostToDevice, st));
-        launch_lm(PP, E.lm_in.p, 1, bp, E.mask.p, nullptr, E.lm_out.p, st);
+        launch_lm(PP, E.lm_in.p, 1, bp, E.mask.p, E.subset.p, n_pad, E.h_lm_out.d, st);
         E.launches++;
-        PLB_CUDA(cudaMemcpyAsync(E.h_lm_out.p, E.lm_out.p, sizeof(LmJobOut), cudaMemcpyDeviceToHost, st));
     }
     PLB_CUDA(cudaMemcpyAsync(E.h_mask.p, E.mask.p, n, cudaMemcpyDeviceToHost, st));
     PLB_CUDA(cudaStreamSynchronize(st));
@@ -649,8 +675,7 @@ static int run_refine(int kind, const double *a, const double *b, size_t n_pts, 
     if ((rc = E.h_in_a.ensure(2 * (size_t)n)) || (rc = E.h_in_b.ensure((size_t)b_dim * n)) ||
         (rc = E.in_a.ensure(2 * (size_t)n)) || (rc = E.in_b.ensure((size_t)b_dim * n)) ||
         (rc = E.soa64.ensure((size_t)n_arr * n_pad)) || (rc = E.soa32.ensure((size_t)n_arr * n_pad)) ||
-        (rc = E.lm_in.ensure(9)) || (rc = E.h_lm_in.ensure(9)) || (rc = E.lm_out.ensure(1)) ||
-        (rc = E.h_lm_out.ensure(1)))
+        (rc = E.lm_in.ensure(9)) || (rc = E.h_lm_in.ensure(9)) || (rc = E.h_lm_out.ensure(1)))
         return rc;
     std::memcpy(E.h_in_a.p, a, sizeof(double) * 2 * n);
     std::memcpy(E.h_in_b.p, b, sizeof(double) * b_dim * n);
@@ -671,9 +696,8 @@ static int run_refine(int kind, const double *a, const double *b, size_t n_pts, 
     std::fill(E.h_lm_in.p, E.h_lm_in.p + 9, 0.0);
     std::copy(model, model + MSZ, E.h_lm_in.p);
     PLB_CUDA(cudaMemcpyAsync(E.lm_in.p, E.h_lm_in.p, sizeof(double) * 9, cudaMemcpyHostToDevice, st));
-    launch_lm(P, E.lm_in.p, 1, bp, nullptr, nullptr, E.lm_out.p, st);
+    launch_lm(P, E.lm_in.p, 1, bp, nullptr, nullptr, n_pad, E.h_lm_out.d, st);
     E.launches += 2;
-    PLB_CUDA(cudaMemcpyAsync(E.h_lm_out.p, E.lm_out.p, sizeof(LmJobOut), cudaMemcpyDeviceToHost, st));
     PLB_CUDA(cudaStreamSynchronize(st));
     PLB_CUDA(cudaGetLastError());
     std::copy(E.h_lm_out.p[0].model, E.h_lm_out.p[0].model + MSZ, model);

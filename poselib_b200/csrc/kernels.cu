@@ -12,8 +12,12 @@
 // Compiled with -fmad=false (see device_math.cuh).  Reference citations are relative to /root/reference.
 #include "kernels.cuh"
 #include "solvers.cuh"
+#include <cooperative_groups.h>
+#include <cstring>
 
 namespace plb {
+
+PLB_DEV int min_i(int a, int b) { return a < b ? a : b; }
 
 // ============================================================================================================
 // layout transform
@@ -108,65 +112,87 @@ PLB_DEV double homography_r2(const double *H, double x1_0, double x1_1, double x
     return r0 * r0 + r1 * r1;
 }
 
-// Returns (count, score) of `model` over all correspondences; the result is identical on every lane.
-// The summation order (lane-strided partial sums, xor-butterfly) is fixed, so the same model always gets the same
-// score bits wherever it is scored (hypothesis kernel, LO kernel, explicit rescoring).
+// Scores `model` over all correspondences with the first SCORE_THREADS (=256) threads of the CTA; every thread of
+// the CTA must call it (it contains CTA barriers) and receives the same (count, score).
+// The summation order is fixed — thread-strided partial sums, xor-butterfly inside each warp, the 8 warp partials
+// added left to right — so the same model gets the same score bits wherever it is scored (hypothesis scoring,
+// LO rescoring, explicit rescoring): the equalities the serial loop relies on (ransac_impl.h:127,143) are preserved.
+constexpr int SCORE_THREADS = 256;
+constexpr int SCORE_WARPS = SCORE_THREADS / 32;
+struct ScoreRed {
+    double s[SCORE_WARPS];
+    uint32_t c[SCORE_WARPS];
+};
 template <int KIND>
-PLB_DEV void warp_score(const ProblemDev &P, const double *model, double sq_thr, int lane, uint32_t &count_out,
-                        double &score_out) {
-    ModelCtx<KIND> C;
-    C.init(model);
+PLB_DEV void cta_score(const ProblemDev &P, const double *model, double sq_thr, ScoreRed *red, uint32_t &count_out,
+                       double &score_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = P.n;
     uint32_t cnt = 0;
     double score = 0.0;
-    if (KIND == KIND_PNP) {
-        const double *__restrict__ xx = P.p[0], *__restrict__ xy = P.p[1];
-        const double *__restrict__ Xx = P.p[2], *__restrict__ Xy = P.p[3], *__restrict__ Xz = P.p[4];
-        const double *Pm = reinterpret_cast<const double *>(&C);
-        for (int k = lane; k < n; k += 32) {
-            const double X0 = Xx[k], X1 = Xy[k], X2 = Xz[k];
-            const double x0 = xx[k], x1 = xy[k];
-            const double z0 = Pm[0] * X0 + Pm[1] * X1 + Pm[2] * X2 + Pm[3];
-            const double z1 = Pm[4] * X0 + Pm[5] * X1 + Pm[6] * X2 + Pm[7];
-            const double z2 = Pm[8] * X0 + Pm[9] * X1 + Pm[10] * X2 + Pm[11];
-            if (z2 <= 0.0) continue;
-            const double inv_z2 = 1.0 / z2;
-            const double r_0 = z0 * inv_z2 - x0;
-            const double r_1 = z1 * inv_z2 - x1;
-            const double r_sq = r_0 * r_0 + r_1 * r_1;
-            if (r_sq < sq_thr) {
-                ++cnt;
-                score += r_sq;
+    if (tid < SCORE_THREADS) {
+        ModelCtx<KIND> C;
+        C.init(model);
+        if (KIND == KIND_PNP) {
+            const double *__restrict__ xx = P.p[0], *__restrict__ xy = P.p[1];
+            const double *__restrict__ Xx = P.p[2], *__restrict__ Xy = P.p[3], *__restrict__ Xz = P.p[4];
+            const double *Pm = reinterpret_cast<const double *>(&C);
+            for (int k = tid; k < n; k += SCORE_THREADS) {
+                const double X0 = Xx[k], X1 = Xy[k], X2 = Xz[k];
+                const double x0 = xx[k], x1 = xy[k];
+                const double z0 = Pm[0] * X0 + Pm[1] * X1 + Pm[2] * X2 + Pm[3];
+                const double z1 = Pm[4] * X0 + Pm[5] * X1 + Pm[6] * X2 + Pm[7];
+                const double z2 = Pm[8] * X0 + Pm[9] * X1 + Pm[10] * X2 + Pm[11];
+                if (z2 <= 0.0) continue;
+                const double inv_z2 = 1.0 / z2;
+                const double r_0 = z0 * inv_z2 - x0;
+                const double r_1 = z1 * inv_z2 - x1;
+                const double r_sq = r_0 * r_0 + r_1 * r_1;
+                if (r_sq < sq_thr) {
+                    ++cnt;
+                    score += r_sq;
+                }
+            }
+        } else {
+            const double *__restrict__ ax = P.p[0], *__restrict__ ay = P.p[1];
+            const double *__restrict__ bx = P.p[2], *__restrict__ by = P.p[3];
+            const double *M = reinterpret_cast<const double *>(&C); // first 9 doubles: E / F / H row-major
+            for (int k = tid; k < n; k += SCORE_THREADS) {
+                const double x1_0 = ax[k], x1_1 = ay[k], x2_0 = bx[k], x2_1 = by[k];
+                double r2;
+                if (KIND == KIND_HOMOG) r2 = homography_r2(M, x1_0, x1_1, x2_0, x2_1);
+                else r2 = sampson_r2(M, x1_0, x1_1, x2_0, x2_1);
+                bool inl = r2 < sq_thr;
+                if (KIND == KIND_RELPOSE) {
+                    if (inl) inl = cheirality_ok(M + 9, M + 13, bearing(x1_0, x1_1), bearing(x2_0, x2_1), 0.01);
+                }
+                if (inl) {
+                    ++cnt;
+                    score += r2;
+                } else {
+                    score += sq_thr;
+                }
             }
         }
         cnt = warp_sum_u(cnt);
         score = warp_sum(score);
-        score += (double)(n - (int)cnt) * sq_thr;
-    } else {
-        const double *__restrict__ ax = P.p[0], *__restrict__ ay = P.p[1];
-        const double *__restrict__ bx = P.p[2], *__restrict__ by = P.p[3];
-        const double *M = reinterpret_cast<const double *>(&C); // first 9 doubles: E / F / H row-major
-        for (int k = lane; k < n; k += 32) {
-            const double x1_0 = ax[k], x1_1 = ay[k], x2_0 = bx[k], x2_1 = by[k];
-            double r2;
-            if (KIND == KIND_HOMOG) r2 = homography_r2(M, x1_0, x1_1, x2_0, x2_1);
-            else r2 = sampson_r2(M, x1_0, x1_1, x2_0, x2_1);
-            bool inl = r2 < sq_thr;
-            if (KIND == KIND_RELPOSE) {
-                if (inl) inl = cheirality_ok(M + 9, M + 13, bearing(x1_0, x1_1), bearing(x2_0, x2_1), 0.01);
-            }
-            if (inl) {
-                ++cnt;
-                score += r2;
-            } else {
-                score += sq_thr;
-            }
+        if (lane == 0) {
+            red->c[warp] = cnt;
+            red->s[warp] = score;
         }
-        cnt = warp_sum_u(cnt);
-        score = warp_sum(score);
     }
-    count_out = cnt;
-    score_out = score;
+    __syncthreads();
+    uint32_t ct = 0;
+    double st = 0.0;
+#pragma unroll
+    for (int w = 0; w < SCORE_WARPS; ++w) {
+        ct += red->c[w];
+        st += red->s[w];
+    }
+    if (KIND == KIND_PNP) st += (double)(n - (int)ct) * sq_thr; // robust/utils.cc:62
+    __syncthreads();
+    count_out = ct;
+    score_out = st;
 }
 
 // ============================================================================================================
@@ -259,11 +285,12 @@ PLB_DEV int warp_generate_models(const ProblemDev &P, const uint32_t *sample, Hy
     }
 }
 
+// Solve kernel: persistent, one warp = one minimal sample.  Models are appended to a compact list (slot range
+// reserved with one atomicAdd per sample); n_models[s] / first_slot[s] let the host walk them in (sample, model) order.
 template <int KIND>
 __global__ void __launch_bounds__(HYP_WARPS * 32)
-    k_hyp(const ProblemDev P, const uint32_t *__restrict__ samples, int n_samples, int *work_counter, HypOut out) {
+    k_solve(const ProblemDev P, const uint32_t *__restrict__ samples, int n_samples, int *work_counter, HypOut out) {
     constexpr int K = (KIND == KIND_PNP) ? 3 : (KIND == KIND_RELPOSE) ? 5 : (KIND == KIND_FUND) ? 7 : 4;
-    constexpr int MAXM = (KIND == KIND_PNP) ? 4 : (KIND == KIND_RELPOSE) ? 40 : (KIND == KIND_FUND) ? 3 : 1;
     constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MonoTables *T = reinterpret_cast<MonoTables *>(smem_raw);
@@ -283,20 +310,38 @@ __global__ void __launch_bounds__(HYP_WARPS * 32)
 #pragma unroll
         for (int i = 0; i < K; ++i) sample[i] = samples[(size_t)s * K + i];
         const int nm = warp_generate_models<KIND>(P, sample, W, T, lane);
-        if (lane == 0) out.n_models[s] = nm;
-        const double *models = W->models;
-        for (int m = 0; m < nm; ++m) {
-            uint32_t cnt;
-            double score;
-            warp_score<KIND>(P, models + MSZ * m, P.sq_thr, lane, cnt, score);
-            const size_t slot = (size_t)s * MAXM + m;
-            if (lane == 0) {
-                out.counts[slot] = cnt;
-                out.scores[slot] = score;
-            }
-            if (lane < MSZ) out.models[slot * MSZ + lane] = models[MSZ * m + lane];
+        int base = 0;
+        if (lane == 0) {
+            base = nm ? atomicAdd(out.model_count, nm) : 0;
+            out.n_models[s] = nm;
+            out.first_slot[s] = base;
         }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const double *models = W->models;
+        for (int e = lane; e < nm * MSZ; e += 32) out.models[(size_t)base * MSZ + e] = models[e];
         __syncwarp();
+    }
+}
+
+// Score kernel: persistent grid of 256-thread CTAs, one CTA scores one model at a time over all correspondences.
+template <int KIND>
+__global__ void __launch_bounds__(SCORE_THREADS)
+    k_score(const ProblemDev P, const double *__restrict__ models, const int *__restrict__ model_count,
+            uint32_t *counts, double *scores) {
+    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    __shared__ ScoreRed red;
+    const int nmod = *model_count;
+    for (int m = blockIdx.x; m < nmod; m += gridDim.x) {
+        double mdl[MSZ];
+#pragma unroll
+        for (int k = 0; k < MSZ; ++k) mdl[k] = models[(size_t)m * MSZ + k];
+        uint32_t cnt;
+        double score;
+        cta_score<KIND>(P, mdl, P.sq_thr, &red, cnt, score);
+        if (threadIdx.x == 0) {
+            counts[m] = cnt;
+            scores[m] = score;
+        }
     }
 }
 
@@ -313,13 +358,22 @@ static int sm_count() {
     return g_sm_count;
 }
 
-template <int KIND> static int hyp_blocks_per_sm() {
+template <int KIND> static int solve_blocks_per_sm() {
     static int cached = -1;
     if (cached < 0) {
         const size_t smem = hyp_smem_bytes<KIND>();
-        cudaFuncSetAttribute(k_hyp<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_solve<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_hyp<KIND>, HYP_WARPS * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve<KIND>, HYP_WARPS * 32, smem);
+        cached = nb > 0 ? nb : 1;
+    }
+    return cached;
+}
+template <int KIND> static int score_blocks_per_sm() {
+    static int cached = -1;
+    if (cached < 0) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_score<KIND>, SCORE_THREADS, 0);
         cached = nb > 0 ? nb : 1;
     }
     return cached;
@@ -327,10 +381,10 @@ template <int KIND> static int hyp_blocks_per_sm() {
 int hyp_kernel_blocks(int kind) {
     int per = 1;
     switch (kind) {
-    case KIND_PNP: per = hyp_blocks_per_sm<KIND_PNP>(); break;
-    case KIND_RELPOSE: per = hyp_blocks_per_sm<KIND_RELPOSE>(); break;
-    case KIND_FUND: per = hyp_blocks_per_sm<KIND_FUND>(); break;
-    default: per = hyp_blocks_per_sm<KIND_HOMOG>(); break;
+    case KIND_PNP: per = solve_blocks_per_sm<KIND_PNP>(); break;
+    case KIND_RELPOSE: per = solve_blocks_per_sm<KIND_RELPOSE>(); break;
+    case KIND_FUND: per = solve_blocks_per_sm<KIND_FUND>(); break;
+    default: per = solve_blocks_per_sm<KIND_HOMOG>(); break;
     }
     return per * sm_count();
 }
@@ -338,18 +392,22 @@ int hyp_kernel_blocks(int kind) {
 template <int KIND>
 static void launch_hyp_t(const ProblemDev &P, const uint32_t *samples, int n_samples, int *work_counter,
                          const HypOut &out, cudaStream_t stream) {
-    // persistent grid: a multiple of the SM count (resident CTAs per SM from the occupancy API), never more CTAs
+    // persistent grids: a multiple of the SM count (resident CTAs per SM from the occupancy API), never more CTAs
     // than there is work for
-    int blocks = hyp_blocks_per_sm<KIND>() * sm_count();
+    int blocks = solve_blocks_per_sm<KIND>() * sm_count();
     const int need = (n_samples + HYP_WARPS - 1) / HYP_WARPS;
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
-    k_hyp<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(P, samples, n_samples, work_counter, out);
+    k_solve<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(P, samples, n_samples, work_counter, out);
+    int sblocks = score_blocks_per_sm<KIND>() * sm_count();
+    const int max_models = n_samples * kind_max_models(KIND);
+    if (sblocks > max_models) sblocks = max_models;
+    k_score<KIND><<<sblocks, SCORE_THREADS, 0, stream>>>(P, out.models, out.model_count, out.counts, out.scores);
 }
 void launch_hypotheses(const ProblemDev &P, const uint32_t *samples, int n_samples, int *work_counter,
                        const HypOut &out, int mode, cudaStream_t stream) {
     (void)mode;
-    cudaMemsetAsync(work_counter, 0, sizeof(int), stream);
+    cudaMemsetAsync(work_counter, 0, 2 * sizeof(int), stream); // [0] sample queue, [1] = out.model_count
     switch (P.kind) {
     case KIND_PNP: launch_hyp_t<KIND_PNP>(P, samples, n_samples, work_counter, out, stream); break;
     case KIND_RELPOSE: launch_hyp_t<KIND_RELPOSE>(P, samples, n_samples, work_counter, out, stream); break;
@@ -361,36 +419,16 @@ void launch_hypotheses(const ProblemDev &P, const uint32_t *samples, int n_sampl
 // ============================================================================================================
 // explicit model scoring
 // ============================================================================================================
-template <int KIND>
-__global__ void k_score_models(const ProblemDev P, const double *__restrict__ models, int n_models,
-                               uint32_t *counts, double *scores) {
-    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (int m = gw; m < n_models; m += nw) {
-        double mdl[MSZ];
-#pragma unroll
-        for (int k = 0; k < MSZ; ++k) mdl[k] = models[(size_t)m * MSZ + k];
-        uint32_t cnt;
-        double score;
-        warp_score<KIND>(P, mdl, P.sq_thr, lane, cnt, score);
-        if (lane == 0) {
-            counts[m] = cnt;
-            scores[m] = score;
-        }
-    }
-}
-void launch_score_models(const ProblemDev &P, const double *models, int n_models, uint32_t *counts, double *scores,
-                         cudaStream_t stream) {
+void launch_score_models(const ProblemDev &P, const double *models, int n_models, const int *n_models_dev,
+                         uint32_t *counts, double *scores, cudaStream_t stream) {
     if (n_models <= 0) return;
-    const int threads = 128;
-    int blocks = (n_models * 32 + threads - 1) / threads;
+    int blocks = n_models;
     if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
     switch (P.kind) {
-    case KIND_PNP: k_score_models<KIND_PNP><<<blocks, threads, 0, stream>>>(P, models, n_models, counts, scores); break;
-    case KIND_RELPOSE: k_score_models<KIND_RELPOSE><<<blocks, threads, 0, stream>>>(P, models, n_models, counts, scores); break;
-    case KIND_FUND: k_score_models<KIND_FUND><<<blocks, threads, 0, stream>>>(P, models, n_models, counts, scores); break;
-    default: k_score_models<KIND_HOMOG><<<blocks, threads, 0, stream>>>(P, models, n_models, counts, scores); break;
+    case KIND_PNP: k_score<KIND_PNP><<<blocks, SCORE_THREADS, 0, stream>>>(P, models, n_models_dev, counts, scores); break;
+    case KIND_RELPOSE: k_score<KIND_RELPOSE><<<blocks, SCORE_THREADS, 0, stream>>>(P, models, n_models_dev, counts, scores); break;
+    case KIND_FUND: k_score<KIND_FUND><<<blocks, SCORE_THREADS, 0, stream>>>(P, models, n_models_dev, counts, scores); break;
+    default: k_score<KIND_HOMOG><<<blocks, SCORE_THREADS, 0, stream>>>(P, models, n_models_dev, counts, scores); break;
     }
 }
 void launch_rescore_slots(const ProblemDev &, const HypOut &, const int *, int, cudaStream_t) {}
@@ -440,8 +478,10 @@ void launch_inlier_mask(const ProblemDev &P, const double *model, double sq_thr,
 // ============================================================================================================
 // Levenberg-Marquardt refit: one CTA per job
 // ============================================================================================================
-constexpr int LM_THREADS = 512;
+constexpr int LM_THREADS = 256;
 constexpr int LM_WARPS = LM_THREADS / 32;
+constexpr int LM_MAX_CLUSTER = 8;
+constexpr int LM_NV_MAX = 56;
 
 struct LossFn { // robust/robust_loss.h:41-67,125-136
     int type;
@@ -748,15 +788,20 @@ template <int NP> struct JacAcc {
 struct LmShared {
     double par[9], par_new[9];
     double ctx[80];
-    double tb[6];
-    double red[LM_WARPS][48];
-    double sums[48];
-    int flag;     // loop control broadcast
-    int use_new;  // evaluate par_new (residual pass) or par
+    double tb[6], tb_new[6];
+    double red[LM_WARPS][LM_NV_MAX];
+    double sums[2][LM_NV_MAX]; // CTA partial sums, double-buffered: read by the other CTAs of the cluster (DSMEM)
+    double tot[LM_NV_MAX];     // cluster totals (identical in every CTA)
+    ScoreRed sred;
+    int wcount[LM_WARPS];
+    int flag;
 };
 
-// block-wide deterministic sum of NV per-thread values -> S->sums[0..NV)
-template <int NV> PLB_DEV void block_sum(LmShared *S, const double *v) {
+// Cluster-wide deterministic sum of NV per-thread values -> S->tot[0..NV) in every CTA of the cluster.
+// Order: xor-butterfly inside a warp, warps left to right, CTAs in rank order.
+template <int NV> PLB_DEV void cluster_sum(LmShared *S, const double *v, int &buf, int csize) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -767,9 +812,19 @@ template <int NV> PLB_DEV void block_sum(LmShared *S, const double *v) {
     if (threadIdx.x < NV) {
         double s = 0.0;
         for (int w = 0; w < LM_WARPS; ++w) s += S->red[w][threadIdx.x];
-        S->sums[threadIdx.x] = s;
+        S->sums[buf][threadIdx.x] = s;
+    }
+    cluster.sync();
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+        for (int r = 0; r < csize; ++r) {
+            const double *remote = cluster.map_shared_rank(&S->sums[buf][0], r);
+            t += remote[threadIdx.x];
+        }
+        S->tot[threadIdx.x] = t;
     }
     __syncthreads();
+    buf ^= 1;
 }
 
 // thread 0 -> whole CTA broadcast of a small integer (two barriers: the slot can be reused right away)
@@ -781,72 +836,31 @@ PLB_DEV int block_bcast(LmShared *S, int v) {
     return r;
 }
 
-// residual pass: sum of robust losses + row count  (compute_residual of the four refiners)
+// One evaluation pass at the parameters whose context is in S->ctx: robust cost + row count (compute_residual of the
+// refiners) AND the normal equations JtJ (lower triangle, packed row-major), Jtr + count of non-zero-weight rows
+// (compute_jacobian), accumulated separately exactly as two passes of the reference would.
+// Output layout in S->tot: [0] loss sum, [1] residual rows, [2..2+NT) JtJ, [2+NT..2+NT+NP) Jtr, [2+NT+NP] jac rows.
 template <int KIND>
-PLB_DEV void lm_residual_pass(const ProblemDev &P, const LmParams &prm, const LossFn &L, const char *mask,
-                              LmShared *S) {
-    const double *ctx = S->ctx;
-    double acc[2] = {0.0, 0.0};
-    for (int k = threadIdx.x; k < P.n; k += LM_THREADS) {
-        if (mask && !mask[k]) continue;
-        if (KIND == KIND_PNP) {
-            const double X0 = P.p[2][k], X1 = P.p[3][k], X2 = P.p[4][k];
-            const double Z0 = ctx[0] * X0 + ctx[1] * X1 + ctx[2] * X2 + ctx[9];
-            const double Z1 = ctx[3] * X0 + ctx[4] * X1 + ctx[5] * X2 + ctx[10];
-            const double Z2 = ctx[6] * X0 + ctx[7] * X1 + ctx[8] * X2 + ctx[11];
-            if (Z2 < 0) continue;
-            double xp0, xp1;
-            if (prm.use_camera) {
-                xp0 = prm.cam[0] * Z0 / Z2 + prm.cam[2];
-                xp1 = prm.cam[1] * Z1 / Z2 + prm.cam[3];
-            } else {
-                xp0 = Z0 / Z2;
-                xp1 = Z1 / Z2;
-            }
-            const double r0 = xp0 - P.p[0][k], r1 = xp1 - P.p[1][k];
-            acc[0] += L.loss(r0 * r0 + r1 * r1);
-            acc[1] += 1.0;
-        } else if (KIND == KIND_HOMOG) {
-            const double a0 = P.p[0][k], a1 = P.p[1][k], b0 = P.p[2][k], b1 = P.p[3][k];
-            const double *H = ctx, *G = ctx + 9;
-            const double Hx0 = H[0] * a0 + H[1] * a1 + H[2];
-            const double Hx1 = H[3] * a0 + H[4] * a1 + H[5];
-            const double iw = 1.0 / (H[6] * a0 + H[7] * a1 + H[8]);
-            const double r0 = Hx0 * iw - b0, r1 = Hx1 * iw - b1;
-            acc[0] += L.loss(r0 * r0 + r1 * r1);
-            const double Gx0 = G[0] * b0 + G[1] * b1 + G[2];
-            const double Gx1 = G[3] * b0 + G[4] * b1 + G[5];
-            const double iv = 1.0 / (G[6] * b0 + G[7] * b1 + G[8]);
-            const double s0 = Gx0 * iv - a0, s1 = Gx1 * iv - a1;
-            acc[0] += L.loss(s0 * s0 + s1 * s1);
-            acc[1] += 2.0;
-        } else {
-            const double r = sampson_res(ctx, P.p[0][k], P.p[1][k], P.p[2][k], P.p[3][k]);
-            acc[0] += L.loss(r * r);
-            acc[1] += 1.0;
-        }
-    }
-    block_sum<2>(S, acc);
-}
-
-// Jacobian pass: JtJ (lower triangle, row-major packed), Jtr, count of rows with non-zero weight
-template <int KIND>
-PLB_DEV void lm_jacobian_pass(const ProblemDev &P, const LmParams &prm, const LossFn &L, const char *mask,
-                              LmShared *S) {
+PLB_DEV void lm_eval_pass(const ProblemDev &P, const LmParams &prm, const LossFn &L, const int *list, int lo, int na,
+                          LmShared *S, int &buf, int csize) {
     constexpr int NP = LmDims<KIND>::NP;
+    constexpr int NT = NP * (NP + 1) / 2;
     const double *ctx = S->ctx;
     JacAcc<NP> A;
     A.zero();
-    for (int k = threadIdx.x; k < P.n; k += LM_THREADS) {
-        if (mask && !mask[k]) continue;
+    double lsum = 0.0, rows = 0.0;
+    for (int i = threadIdx.x; i < na; i += LM_THREADS) {
+        const int k = list ? list[i] : lo + i;
         if (KIND == KIND_PNP) {
             const double X0 = P.p[2][k], X1 = P.p[3][k], X2 = P.p[4][k];
             const double Z0 = ctx[0] * X0 + ctx[1] * X1 + ctx[2] * X2 + ctx[9];
             const double Z1 = ctx[3] * X0 + ctx[4] * X1 + ctx[5] * X2 + ctx[10];
             const double Z2 = ctx[6] * X0 + ctx[7] * X1 + ctx[8] * X2 + ctx[11];
-            if (Z2 < 0) continue;
-            double zp0, zp1, Jp[2][3];
-            if (prm.use_camera) { // PinholeCameraModel::project_with_jac (camera_models.cc:672-685)
+            if (Z2 < 0) continue; // optim/absolute.h:57-58,93-94
+            double zp0, zp1, xr0, xr1, Jp[2][3];
+            if (prm.use_camera) { // PinholeCameraModel::project / project_with_jac (camera_models.cc:668-685)
+                xr0 = prm.cam[0] * Z0 / Z2 + prm.cam[2];
+                xr1 = prm.cam[1] * Z1 / Z2 + prm.cam[3];
                 const double inv_z = 1.0 / Z2;
                 const double px = prm.cam[0] * Z0 * inv_z, py = prm.cam[1] * Z1 * inv_z;
                 zp0 = px + prm.cam[2];
@@ -856,11 +870,19 @@ PLB_DEV void lm_jacobian_pass(const ProblemDev &P, const LmParams &prm, const Lo
             } else { // NullCameraModel (camera_models.cc:2708-2722)
                 zp0 = Z0 / Z2;
                 zp1 = Z1 / Z2;
+                xr0 = zp0;
+                xr1 = zp1;
                 const double z_inv = 1.0 / Z2;
                 Jp[0][0] = z_inv; Jp[0][1] = 0.0; Jp[0][2] = -zp0 * z_inv;
                 Jp[1][0] = 0.0; Jp[1][1] = z_inv; Jp[1][2] = -zp1 * z_inv;
             }
-            const double r0 = zp0 - P.p[0][k], r1 = zp1 - P.p[1][k];
+            const double x0 = P.p[0][k], x1 = P.p[1][k];
+            {
+                const double q0 = xr0 - x0, q1 = xr1 - x1;
+                lsum += L.loss(q0 * q0 + q1 * q1);
+                rows += 1.0;
+            }
+            const double r0 = zp0 - x0, r1 = zp1 - x1;
             double J[2][6];
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
@@ -876,11 +898,13 @@ PLB_DEV void lm_jacobian_pass(const ProblemDev &P, const LmParams &prm, const Lo
         } else if (KIND == KIND_HOMOG) {
             const double a0 = P.p[0][k], a1 = P.p[1][k], b0 = P.p[2][k], b1 = P.p[3][k];
             const double *H = ctx, *G = ctx + 9;
-            // forward transfer (optim/homography.h:107-123); parameters = H00,H10,H20,H01,H11,H21,H02,H12
+            // forward transfer (optim/homography.h:63-71,107-123); parameters = H00,H10,H20,H01,H11,H21,H02,H12
             const double Hx0 = H[0] * a0 + H[1] * a1 + H[2];
             const double Hx1 = H[3] * a0 + H[4] * a1 + H[5];
             const double iw = 1.0 / (H[6] * a0 + H[7] * a1 + H[8]);
             const double z0 = Hx0 * iw, z1 = Hx1 * iw;
+            const double r0 = z0 - b0, r1 = z1 - b1;
+            lsum += L.loss(r0 * r0 + r1 * r1);
             double J0[8] = {a0, 0.0, -a0 * z0, a1, 0.0, -a1 * z0, 1.0, 0.0};
             double J1[8] = {0.0, a0, -a0 * z1, 0.0, a1, -a1 * z1, 0.0, 1.0};
 #pragma unroll
@@ -888,13 +912,16 @@ PLB_DEV void lm_jacobian_pass(const ProblemDev &P, const LmParams &prm, const Lo
                 J0[m] = J0[m] * iw;
                 J1[m] = J1[m] * iw;
             }
-            A.add2(L, z0 - b0, z1 - b1, J0, J1);
-            // backward transfer through adj(H) (optim/homography.h:125-152):  y = pi(G x2),
+            A.add2(L, r0, r1, J0, J1);
+            // backward transfer through adj(H) (optim/homography.h:73-81,125-152):  y = pi(G x2),
             // dy_i/dH_k = ( (dG/dH_k x2)_i - y_i (dG/dH_k x2)_2 ) / (G x2)_2
             const double Gx0 = G[0] * b0 + G[1] * b1 + G[2];
             const double Gx1 = G[3] * b0 + G[4] * b1 + G[5];
             const double iv = 1.0 / (G[6] * b0 + G[7] * b1 + G[8]);
             const double y0 = Gx0 * iv, y1 = Gx1 * iv;
+            const double s0 = y0 - a0, s1 = y1 - a1;
+            lsum += L.loss(s0 * s0 + s1 * s1);
+            rows += 2.0;
             const double y0b1 = y0 * b1, y0b0 = y0 * b0, y1b1 = y1 * b1, y1b0 = y1 * b0;
             const double H00 = H[0], H01 = H[1], H02 = H[2], H10 = H[3], H11 = H[4], H12 = H[5], H20 = H[6],
                          H21 = H[7], H22 = H[8];
@@ -920,10 +947,16 @@ PLB_DEV void lm_jacobian_pass(const ProblemDev &P, const LmParams &prm, const Lo
                 K0[m] = K0[m] * iv;
                 K1[m] = K1[m] * iv;
             }
-            A.add2(L, y0 - a0, y1 - a1, K0, K1);
+            A.add2(L, s0, s1, K0, K1);
         } else {
+            const double a0 = P.p[0][k], a1 = P.p[1][k], b0 = P.p[2][k], b1 = P.p[3][k];
+            {
+                const double rr = sampson_res(ctx, a0, a1, b0, b1);
+                lsum += L.loss(rr * rr);
+                rows += 1.0;
+            }
             double r, dF[9], J[NP];
-            sampson_res_dF(ctx, P.p[0][k], P.p[1][k], P.p[2][k], P.p[3][k], r, dF);
+            sampson_res_dF(ctx, a0, a1, b0, b1, r, dF);
             const double *D = ctx + 9;
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
@@ -935,14 +968,16 @@ PLB_DEV void lm_jacobian_pass(const ProblemDev &P, const LmParams &prm, const Lo
             A.add1(L, r, J);
         }
     }
-    constexpr int NV = JacAcc<NP>::NT + NP + 1;
+    constexpr int NV = 2 + NT + NP + 1;
     double v[NV];
+    v[0] = lsum;
+    v[1] = rows;
 #pragma unroll
-    for (int i = 0; i < JacAcc<NP>::NT; ++i) v[i] = A.jtj[i];
+    for (int i = 0; i < NT; ++i) v[2 + i] = A.jtj[i];
 #pragma unroll
-    for (int i = 0; i < NP; ++i) v[JacAcc<NP>::NT + i] = A.jtr[i];
+    for (int i = 0; i < NP; ++i) v[2 + NT + i] = A.jtr[i];
     v[NV - 1] = A.cnt;
-    block_sum<NV>(S, v);
+    cluster_sum<NV>(S, v, buf, csize);
 }
 
 // lower Cholesky solve of (A) x = rhs, only the lower triangle of A read (jacobian_accumulator.h:145-154)
@@ -972,15 +1007,22 @@ template <int NP> PLB_DEV void llt_solve(const double *A, const double *rhs, dou
     }
 }
 
+// One thread-block CLUSTER per job (1..8 CTAs of 256 threads, DSMEM reductions); CTA r owns the correspondences
+// [r*chunk, (r+1)*chunk).  Every CTA runs the scalar LM logic (optim/lm_impl.h:56-140) redundantly on identical
+// cluster totals, so no broadcast between CTAs is needed.  The reference evaluates the residual of a trial step and,
+// if accepted, the Jacobian at the same parameters in a second pass; here both come from one pass.
 template <int KIND>
 __global__ void __launch_bounds__(LM_THREADS)
     k_lm(const ProblemDev P, const double *__restrict__ models_in, const LmParams prm, const char *mask_in,
-         char *subset_scratch, LmJobOut *outs) {
+         int *idx_scratch, int n_pad, LmJobOut *outs) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     constexpr int NP = LmDims<KIND>::NP;
     constexpr int NT = NP * (NP + 1) / 2;
     constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
     __shared__ LmShared S;
-    const int job = blockIdx.x;
+    const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+    const int job = blockIdx.x / csize;
     const double *min = models_in + (size_t)job * 9;
     LmJobOut *out = outs + job;
     LossFn L;
@@ -988,27 +1030,53 @@ __global__ void __launch_bounds__(LM_THREADS)
     L.thr = prm.loss_scale;
     L.sq_thr = prm.loss_scale * prm.loss_scale;
     L.inv_sq_thr = 1.0 / L.sq_thr;
+    int buf = 0;
 
-    const char *mask = (prm.subset_mode == 2) ? mask_in : nullptr;
+    // ---- this CTA's slice and its active-point list ------------------------------------------------------------
+    const int chunk = (((P.n + csize - 1) / csize) + 31) & ~31;
+    const int lo = min_i(crank * chunk, P.n), hi = min_i(lo + chunk, P.n);
+    int na = hi - lo;
+    const int *list = nullptr;
     bool untouched = false;
-    // ---- relpose LO subset: inliers of the start pose at 5*thr^2 (estimators/relative_pose.cc:62-86)
-    if (KIND == KIND_RELPOSE && prm.subset_mode == 1) {
-        char *mymask = subset_scratch + (size_t)job * P.n;
+    if (prm.subset_mode != 0) {
+        int *mylist = idx_scratch + (size_t)job * n_pad + lo;
         ModelCtx<KIND_RELPOSE> C;
-        C.init(min);
+        if (KIND == KIND_RELPOSE && prm.subset_mode == 1) C.init(min);
         const double *M = reinterpret_cast<const double *>(&C);
-        double c[1] = {0.0};
-        for (int k = threadIdx.x; k < P.n; k += LM_THREADS) {
-            const double a0 = P.p[0][k], a1 = P.p[1][k], b0 = P.p[2][k], b1 = P.p[3][k];
-            bool inl = sampson_r2(M, a0, a1, b0, b1) < prm.subset_sq_thr;
-            if (inl) inl = cheirality_ok(M + 9, M + 13, bearing(a0, a1), bearing(b0, b1), 0.01);
-            mymask[k] = inl ? 1 : 0;
-            c[0] += inl ? 1.0 : 0.0;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        int base = 0;
+        for (int t0 = lo; t0 < hi; t0 += LM_THREADS) {
+            const int k = t0 + threadIdx.x;
+            bool keep = false;
+            if (k < hi) {
+                if (prm.subset_mode == 2) {
+                    keep = mask_in[k] != 0;
+                } else if (KIND == KIND_RELPOSE) {
+                    // relpose LO subset: inliers of the start pose at 5*thr^2 (estimators/relative_pose.cc:62-86)
+                    const double a0 = P.p[0][k], a1 = P.p[1][k], b0 = P.p[2][k], b1 = P.p[3][k];
+                    keep = sampson_r2(M, a0, a1, b0, b1) < prm.subset_sq_thr;
+                    if (keep) keep = cheirality_ok(M + 9, M + 13, bearing(a0, a1), bearing(b0, b1), 0.01);
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) S.wcount[warp] = __popc(bal);
+            __syncthreads();
+            int off = base;
+            for (int w = 0; w < warp; ++w) off += S.wcount[w];
+            int tile = 0;
+            for (int w = 0; w < LM_WARPS; ++w) tile += S.wcount[w];
+            if (keep) mylist[off + __popc(bal & ((1u << lane) - 1u))] = k;
+            base += tile;
+            __syncthreads();
         }
-        block_sum<1>(&S, c);
-        untouched = !(S.sums[0] > 5.0);
-        mask = mymask;
+        na = base;
+        list = mylist;
         __syncthreads();
+        if (KIND == KIND_RELPOSE && prm.subset_mode == 1) {
+            double c[1] = {threadIdx.x == 0 ? (double)na : 0.0};
+            cluster_sum<1>(&S, c, buf, csize);
+            untouched = !(S.tot[0] > 5.0);
+        }
     }
 
     // ---- initial parameters
@@ -1017,15 +1085,15 @@ __global__ void __launch_bounds__(LM_THREADS)
             m3 F, U, V;
 #pragma unroll
             for (int k = 0; k < 9; ++k) F.a[3 * (k % 3) + k / 3] = min[k];
-            double s[3];
-            svd3_dev(F, U, s, V);
+            double sv[3];
+            svd3_dev(F, U, sv, V);
             if (det3(U) < 0)
                 for (int k = 0; k < 9; ++k) U.a[k] = -U.a[k];
             if (det3(V) < 0)
                 for (int k = 0; k < 9; ++k) V.a[k] = -V.a[k];
             rot_to_quat(U, S.par);
             rot_to_quat(V, S.par + 4);
-            S.par[8] = s[1] / s[0];
+            S.par[8] = sv[1] / sv[0];
         } else {
             for (int k = 0; k < MSZ; ++k) S.par[k] = min[k];
             for (int k = MSZ; k < 9; ++k) S.par[k] = 0.0;
@@ -1036,34 +1104,27 @@ __global__ void __launch_bounds__(LM_THREADS)
     int iterations = 0;
     double cost = 0.0, initial_cost = 0.0;
     if (!untouched) {
-        // thread-0 LM state (optim/lm_impl.h:56-140); rc mirrors NormalAccumulator::residual_count
+        // scalar LM state (thread 0 of every CTA); rc mirrors NormalAccumulator::residual_count
         double lambda = prm.initial_lambda, nu = 2.0, rc = 0.0;
         double JtJ[NP * NP], Jtr[NP], sol[NP];
         bool recompute_jac = true;
-        if (threadIdx.x == 0) lm_build_ctx<KIND>(S.par, S.ctx, S.tb, false);
+        if (threadIdx.x == 0) lm_build_ctx<KIND>(S.par, S.ctx, S.tb, true);
         __syncthreads();
-        lm_residual_pass<KIND>(P, prm, L, mask, &S);
+        lm_eval_pass<KIND>(P, prm, L, list, lo, na, &S, buf, csize);
         if (threadIdx.x == 0) {
-            rc = S.sums[1];
-            cost = S.sums[0] * (1.0 / fmax(1.0, rc));
+            cost = S.tot[0] * (1.0 / fmax(1.0, S.tot[1])); // acc.get_residual() after the residual pass
             initial_cost = cost;
+            int t = 0;
+            for (int i = 0; i < NP; ++i)
+                for (int j = 0; j <= i; ++j) JtJ[i * NP + j] = S.tot[2 + t++];
+            for (int i = 0; i < NP; ++i) Jtr[i] = S.tot[2 + NT + i];
+            rc = S.tot[2 + NT + NP]; // residual_count after the Jacobian pass
         }
         for (int it = 0; it < prm.max_iterations; ++it) {
             iterations = it;
-            const int do_jac = block_bcast(&S, recompute_jac ? 1 : 0);
-            if (do_jac) {
-                if (threadIdx.x == 0) lm_build_ctx<KIND>(S.par, S.ctx, S.tb, true);
-                __syncthreads();
-                lm_jacobian_pass<KIND>(P, prm, L, mask, &S);
-            }
             int stop = 0;
             if (threadIdx.x == 0) {
                 if (recompute_jac) {
-                    int t = 0;
-                    for (int i = 0; i < NP; ++i)
-                        for (int j = 0; j <= i; ++j) JtJ[i * NP + j] = S.sums[t++];
-                    for (int i = 0; i < NP; ++i) Jtr[i] = S.sums[NT + i];
-                    rc = S.sums[NT + NP];
                     double g = 0.0;
                     for (int i = 0; i < NP; ++i) g += Jtr[i] * Jtr[i];
                     const double grad_norm = (1.0 / fmax(1.0, rc)) * sqrt(g);
@@ -1083,20 +1144,19 @@ __global__ void __launch_bounds__(LM_THREADS)
                 }
                 if (!stop) {
                     lm_step<KIND>(S.par, sol, S.tb, S.par_new);
-                    double ctx_save_tb[6];
-                    for (int i = 0; i < 6; ++i) ctx_save_tb[i] = S.tb[i];
-                    lm_build_ctx<KIND>(S.par_new, S.ctx, ctx_save_tb, false);
+                    lm_build_ctx<KIND>(S.par_new, S.ctx, S.tb_new, true);
                 }
             }
             if (block_bcast(&S, stop)) break;
-            lm_residual_pass<KIND>(P, prm, L, mask, &S);
+            lm_eval_pass<KIND>(P, prm, L, list, lo, na, &S, buf, csize);
             int brk = 0;
             if (threadIdx.x == 0) {
-                rc = S.sums[1];
-                const double cost_new = S.sums[0] * (1.0 / fmax(1.0, rc));
+                rc = S.tot[1]; // residual_count after the residual pass of the trial point
+                const double cost_new = S.tot[0] * (1.0 / fmax(1.0, rc));
                 if (cost_new < cost) {
                     const double cost_decrease = cost - cost_new;
                     for (int k = 0; k < 9; ++k) S.par[k] = S.par_new[k];
+                    for (int k = 0; k < 6; ++k) S.tb[k] = S.tb_new[k];
                     cost = cost_new;
                     recompute_jac = true;
                     const double scale = 1.0 / fmax(1.0, rc);
@@ -1113,6 +1173,12 @@ __global__ void __launch_bounds__(LM_THREADS)
                     nu = 2.0;
                     lambda = fmax(prm.min_lambda, lambda);
                     if (cost > 0 && cost_decrease / cost < prm.relative_cost_tol) brk = 1;
+                    // the Jacobian pass the reference would run next at the accepted parameters
+                    int t = 0;
+                    for (int i = 0; i < NP; ++i)
+                        for (int j = 0; j <= i; ++j) JtJ[i * NP + j] = S.tot[2 + t++];
+                    for (int i = 0; i < NP; ++i) Jtr[i] = S.tot[2 + NT + i];
+                    if (!brk && it + 1 < prm.max_iterations) rc = S.tot[2 + NT + NP];
                 } else {
                     recompute_jac = false;
                     lambda *= nu;
@@ -1124,48 +1190,74 @@ __global__ void __launch_bounds__(LM_THREADS)
             if (block_bcast(&S, brk)) break;
         }
     }
-    // ---- output
+    // ---- output (CTA 0 of the cluster)
     __syncthreads();
     if (threadIdx.x == 0) {
         if (KIND == KIND_FUND) {
             if (untouched) {
-                for (int k = 0; k < 9; ++k) out->model[k] = min[k];
+                for (int k = 0; k < 9; ++k) S.par_new[k] = min[k];
             } else {
                 const m3 F = ff_to_F(S.par);
-                for (int k = 0; k < 9; ++k) out->model[k] = F.a[3 * (k % 3) + k / 3];
+                for (int k = 0; k < 9; ++k) S.par_new[k] = F.a[3 * (k % 3) + k / 3];
             }
         } else {
-            for (int k = 0; k < MSZ; ++k) out->model[k] = untouched ? min[k] : S.par[k];
-            for (int k = MSZ; k < 9; ++k) out->model[k] = 0.0;
+            for (int k = 0; k < MSZ; ++k) S.par_new[k] = untouched ? min[k] : S.par[k];
+            for (int k = MSZ; k < 9; ++k) S.par_new[k] = 0.0;
         }
-        out->iterations = iterations;
-        out->cost = cost;
-        out->initial_cost = initial_cost;
-        for (int k = 0; k < 9; ++k) S.par_new[k] = out->model[k];
+        if (crank == 0) {
+            for (int k = 0; k < 9; ++k) out->model[k] = S.par_new[k];
+            out->iterations = iterations;
+            out->cost = cost;
+            out->initial_cost = initial_cost;
+        }
     }
     __syncthreads();
-    if (prm.score_after && threadIdx.x < 32) {
+    if (prm.score_after && crank == 0) {
         uint32_t cnt;
         double score;
         double mdl[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) mdl[k] = S.par_new[k];
-        warp_score<KIND>(P, mdl, P.sq_thr, threadIdx.x, cnt, score);
+        cta_score<KIND>(P, mdl, P.sq_thr, &S.sred, cnt, score);
         if (threadIdx.x == 0) {
             out->count = cnt;
             out->score = score;
         }
     }
+    cluster.sync(); // no CTA may exit while a sibling can still read its shared memory
 }
 
+template <int KIND>
+static void launch_lm_t(const ProblemDev &P, const double *models_in, int n_jobs, const LmParams &prm,
+                        const char *mask, int *idx_scratch, int n_pad, LmJobOut *out, cudaStream_t stream) {
+    int csize = (P.n + 2047) / 2048; // >= ~8 correspondences per thread before a second CTA pays off
+    if (csize < 1) csize = 1;
+    if (csize > LM_MAX_CLUSTER) csize = LM_MAX_CLUSTER;
+    if (csize > 4 && csize < 8) csize = 4;
+    if (csize == 3) csize = 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(n_jobs * csize), 1, 1);
+    cfg.blockDim = dim3(LM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_lm<KIND>, P, models_in, prm, mask, idx_scratch, n_pad, out);
+}
 void launch_lm(const ProblemDev &P, const double *models_in, int n_jobs, const LmParams &prm, const char *mask,
-               char *subset_scratch, LmJobOut *out, cudaStream_t stream) {
+               int *idx_scratch, int n_pad, LmJobOut *out, cudaStream_t stream) {
     if (n_jobs <= 0) return;
     switch (P.kind) {
-    case KIND_PNP: k_lm<KIND_PNP><<<n_jobs, LM_THREADS, 0, stream>>>(P, models_in, prm, mask, subset_scratch, out); break;
-    case KIND_RELPOSE: k_lm<KIND_RELPOSE><<<n_jobs, LM_THREADS, 0, stream>>>(P, models_in, prm, mask, subset_scratch, out); break;
-    case KIND_FUND: k_lm<KIND_FUND><<<n_jobs, LM_THREADS, 0, stream>>>(P, models_in, prm, mask, subset_scratch, out); break;
-    default: k_lm<KIND_HOMOG><<<n_jobs, LM_THREADS, 0, stream>>>(P, models_in, prm, mask, subset_scratch, out); break;
+    case KIND_PNP: launch_lm_t<KIND_PNP>(P, models_in, n_jobs, prm, mask, idx_scratch, n_pad, out, stream); break;
+    case KIND_RELPOSE: launch_lm_t<KIND_RELPOSE>(P, models_in, n_jobs, prm, mask, idx_scratch, n_pad, out, stream); break;
+    case KIND_FUND: launch_lm_t<KIND_FUND>(P, models_in, n_jobs, prm, mask, idx_scratch, n_pad, out, stream); break;
+    default: launch_lm_t<KIND_HOMOG>(P, models_in, n_jobs, prm, mask, idx_scratch, n_pad, out, stream); break;
     }
 }
 

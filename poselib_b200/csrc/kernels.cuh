@@ -25,10 +25,13 @@ inline __host__ __device__ int kind_sample_size(int kind) { return kind == KIND_
 inline __host__ __device__ int kind_max_models(int kind) { return kind == KIND_PNP ? 4 : kind == KIND_RELPOSE ? 40 : kind == KIND_FUND ? 3 : 1; }
 inline __host__ __device__ int kind_model_size(int kind) { return (kind == KIND_PNP || kind == KIND_RELPOSE) ? 7 : 9; }
 
-// Per-round output of the hypothesis kernel, one fixed-size slot block per sample:
-//   n_models[s], counts[s*MAXM+m], scores[s*MAXM+m], models[(s*MAXM+m)*MSZ ...]
+// Per-round output of the hypothesis kernels.  Models are stored compactly: sample s owns slots
+// [first_slot[s], first_slot[s] + n_models[s]) of models / counts / scores; *model_count = total.
+// n_models, first_slot, counts and scores may point to pinned host memory (written straight over PCIe).
 struct HypOut {
     int *n_models;
+    int *first_slot;
+    int *model_count;
     uint32_t *counts;
     double *scores;
     double *models;
@@ -64,14 +67,15 @@ void launch_transpose(const double *in_a, const double *in_b, int n, int b_dim, 
 // Fused sample -> solve -> score kernel.  samples: n_samples * K indices.  mode 0 exact, 1 fast (fp32 screen only).
 void launch_hypotheses(const ProblemDev &P, const uint32_t *samples, int n_samples, int *work_counter,
                        const HypOut &out, int mode, cudaStream_t stream);
-// Exact fp64 scoring of an explicit list of models (model_size doubles each).
-void launch_score_models(const ProblemDev &P, const double *models, int n_models, uint32_t *counts, double *scores,
-                         cudaStream_t stream);
+// Exact fp64 scoring of an explicit list of models (model_size doubles each); *n_models_dev == n_models.
+void launch_score_models(const ProblemDev &P, const double *models, int n_models, const int *n_models_dev,
+                         uint32_t *counts, double *scores, cudaStream_t stream);
 // Exact rescoring of selected slots of a HypOut (fast mode confirmation): slots[i] = s*MAXM+m
 void launch_rescore_slots(const ProblemDev &P, const HypOut &out, const int *slots, int n_slots, cudaStream_t stream);
-// LM refinement: one CTA per job.  models_in: n_jobs * 9 doubles (model_size used).  mask (subset_mode 2): n bytes.
+// LM refinement: one thread-block cluster per job.  models_in: n_jobs * 9 doubles (model_size used).
+// mask (subset_mode 2): n bytes.  idx_scratch: n_jobs * n_pad ints (active-point lists, subset modes 1 and 2).
 void launch_lm(const ProblemDev &P, const double *models_in, int n_jobs, const LmParams &prm, const char *mask,
-               char *subset_scratch /* n_jobs * n bytes for subset_mode 1 */, LmJobOut *out, cudaStream_t stream);
+               int *idx_scratch, int n_pad, LmJobOut *out, cudaStream_t stream);
 // Final inlier mask of a model (robust/utils.cc:331-351,374-383,434-513)
 void launch_inlier_mask(const ProblemDev &P, const double *model, double sq_thr, char *mask, cudaStream_t stream);
 // Batched direct solver calls (solvers/*.h surface): one warp per instance.

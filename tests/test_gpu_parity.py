@@ -121,8 +121,8 @@ def _same_trajectory(g, o, model_tol=1e-6, relpose=False):
         err = min(np.abs(gm - om).max(), np.abs(gm + om).max())
     else:
         if relpose:  # |t| is a gauge freedom of a relative pose (the LM never renormalises it, relative.h:152-157)
-            gm = np.r_[gm[:4], gm[4:] / np.linalg.norm(gm[4:])]
-            om = np.r_[om[:4], om[4:] / np.linalg.norm(om[4:])]
+            gm = np.r_[gm[:4], gm[4:] / max(np.linalg.norm(gm[4:]), 1e-300)]
+            om = np.r_[om[:4], om[4:] / max(np.linalg.norm(om[4:]), 1e-300)]
         err = np.abs(gm - om).max()
     assert err <= model_tol * np.abs(om).max(), (err, gm, om)
     assert g["counters"]["samples"] == o["counters"]["samples"]
