@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(HYP_WARPS * 32)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     HypScratch<KIND> *W = Wall + warp;
     if (KIND == KIND_RELPOSE) {
-        if (threadIdx.x == 0) fill_tables(T);
+        fill_tables(T);
         __syncthreads();
     }
     for (;;) {
@@ -1274,7 +1274,7 @@ __global__ void __launch_bounds__(HYP_WARPS * 32)
     HypScratch<KIND> *W = reinterpret_cast<HypScratch<KIND> *>(smem_raw + 256) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (KIND == KIND_RELPOSE) {
-        if (threadIdx.x == 0) fill_tables(T);
+        fill_tables(T);
         __syncthreads();
     }
     const size_t gw = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((size_t)gridDim.x * blockDim.x) >> 5;

@@ -600,19 +600,21 @@ struct MonoTables {
     int8_t cub_n[20];
     int8_t cub_q[20][3], cub_l[20][3];
 };
-__device__ __forceinline__ void fill_tables(MonoTables *T) {
-    // executed by one thread
-    const int8_t qexp[10][3] = {{2, 0, 0}, {1, 1, 0}, {1, 0, 1}, {1, 0, 0}, {0, 2, 0},
-                                {0, 1, 1}, {0, 1, 0}, {0, 0, 2}, {0, 0, 1}, {0, 0, 0}};
-    const int8_t cexp[20][3] = {{3, 0, 0}, {0, 3, 0}, {2, 1, 0}, {1, 2, 0}, {2, 0, 1}, {2, 0, 0}, {0, 2, 1},
-                                {0, 2, 0}, {1, 1, 1}, {1, 1, 0}, {1, 0, 2}, {1, 0, 1}, {1, 0, 0}, {0, 1, 2},
-                                {0, 1, 1}, {0, 1, 0}, {0, 0, 3}, {0, 0, 2}, {0, 0, 1}, {0, 0, 0}};
-    const int8_t lexp[4][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
+// The tables are built once at compile time (host constexpr) into constant memory; each CTA copies them to shared
+// memory (lane-varying indices would serialise constant-cache reads).
+constexpr MonoTables make_mono_tables() {
+    MonoTables T{};
+    const int qexp[10][3] = {{2, 0, 0}, {1, 1, 0}, {1, 0, 1}, {1, 0, 0}, {0, 2, 0},
+                             {0, 1, 1}, {0, 1, 0}, {0, 0, 2}, {0, 0, 1}, {0, 0, 0}};
+    const int cexp[20][3] = {{3, 0, 0}, {0, 3, 0}, {2, 1, 0}, {1, 2, 0}, {2, 0, 1}, {2, 0, 0}, {0, 2, 1},
+                             {0, 2, 0}, {1, 1, 1}, {1, 1, 0}, {1, 0, 2}, {1, 0, 1}, {1, 0, 0}, {0, 1, 2},
+                             {0, 1, 1}, {0, 1, 0}, {0, 0, 3}, {0, 0, 2}, {0, 0, 1}, {0, 0, 0}};
+    const int lexp[4][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
     int qn = 0;
     for (int i = 0; i < 4; ++i)
         for (int j = i; j < 4; ++j) {
-            T->quad_i[qn] = (int8_t)i;
-            T->quad_j[qn] = (int8_t)j;
+            T.quad_i[qn] = (int8_t)i;
+            T.quad_j[qn] = (int8_t)j;
             ++qn;
         }
     for (int ci = 0; ci < 20; ++ci) {
@@ -621,12 +623,20 @@ __device__ __forceinline__ void fill_tables(MonoTables *T) {
             for (int l = 0; l < 4; ++l)
                 if (qexp[q][0] + lexp[l][0] == cexp[ci][0] && qexp[q][1] + lexp[l][1] == cexp[ci][1] &&
                     qexp[q][2] + lexp[l][2] == cexp[ci][2]) {
-                    T->cub_q[ci][n] = (int8_t)q;
-                    T->cub_l[ci][n] = (int8_t)l;
+                    T.cub_q[ci][n] = (int8_t)q;
+                    T.cub_l[ci][n] = (int8_t)l;
                     ++n;
                 }
-        T->cub_n[ci] = (int8_t)n;
+        T.cub_n[ci] = (int8_t)n;
     }
+    return T;
+}
+__constant__ MonoTables c_mono_tables = make_mono_tables();
+// cooperative copy constant -> shared (whole CTA), followed by a barrier at the call site
+__device__ __forceinline__ void fill_tables(MonoTables *T) {
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(&c_mono_tables);
+    unsigned char *dst = reinterpret_cast<unsigned char *>(T);
+    for (int i = threadIdx.x; i < (int)sizeof(MonoTables); i += blockDim.x) dst[i] = src[i];
 }
 
 // per-warp shared scratch of the 5-point solver (doubles)
