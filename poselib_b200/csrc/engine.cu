@@ -189,15 +189,23 @@ struct Engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ready = false;
     int device = -1;
-    DevBuf<double> in_a, in_b, soa64, px64, models, lm_in, model_dev;
-    DevBuf<float> soa32, fscores;
-    DevBuf<uint32_t> samples, fcounts;
-    DevBuf<int> work, slots, subset;
+    DevBuf<double> in, soa64, px64, models, lm_in;
+    DevBuf<float> soa32;
+    DevBuf<uint32_t> samples;
+    DevBuf<int> work, slots, subset, act, model_prob;
     DevBuf<char> mask;
-    PinBuf<double> h_in_a, h_in_b, h_lm_in, h_model;
+    DevBuf<ProblemDev> probs;
+    DevBuf<TransposeDesc> tdesc;
+    DevBuf<MaskDesc> mdesc;
+    DevBuf<LmJob> jobs;
+    PinBuf<double> h_in, h_lm_in;
     PinBuf<uint32_t> h_samples;
-    PinBuf<int> h_slots;
+    PinBuf<int> h_slots, h_act, h_work;
     PinBuf<char> h_mask;
+    PinBuf<ProblemDev> h_probs;
+    PinBuf<TransposeDesc> h_tdesc;
+    PinBuf<MaskDesc> h_mdesc;
+    PinBuf<LmJob> h_jobs;
     // result records written by the kernels directly into mapped pinned memory (no explicit D2H copies)
     MapBuf<double> h_scores;
     MapBuf<uint32_t> h_counts;
@@ -222,6 +230,10 @@ struct Engine {
         if (!stream) PLB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         if (!ev0) PLB_CUDA(cudaEventCreate(&ev0));
         if (!ev1) PLB_CUDA(cudaEventCreate(&ev1));
+        {
+            int r = h_work.ensure(8);
+            if (r) return r;
+        }
         device = dev;
         ready = true;
         return PLB_OK;
@@ -295,371 +307,646 @@ struct FinalPolish { // the post-RANSAC refinement of PoseLib/robust.cc (estimat
     double cam[4] = {1, 1, 0, 0};
 };
 
-// One LO-RANSAC problem, points already calibrated / normalised.  `model` is 7 (pose) or 9 (column-major) doubles.
-static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, const plb_ransac_opt &opt,
-                      double max_error, int rfc, double *model, char *inliers, plb_ransac_stats *stats_out,
-                      plb_counters *cnt_out, const FinalPolish &polish, const Resident *res = nullptr) {
+// One LO-RANSAC problem handed to the group engine (points already calibrated / normalised).
+struct Task {
+    int kind = 0;
+    const double *a = nullptr, *b = nullptr;
+    size_t n = 0;
+    plb_ransac_opt opt;
+    double max_error = 0;
+    int rfc = 0;
+    double *model = nullptr;   // in/out: 7 or 9 doubles
+    char *inliers = nullptr;
+    plb_ransac_stats *stats_out = nullptr;
+    plb_counters *cnt_out = nullptr;
+    FinalPolish polish;
+    const Resident *res = nullptr;
+};
+
+// per-problem serial state of the reference loop (ransac_impl.h:99-104,157-201)
+struct PState {
+    Task *t = nullptr;
+    int n = 0, n_pad = 0, pidx = 0;
+    bool enough = false, active = false, broke = false;
+    Sampler *sampler = nullptr;
+    size_t it = 0, chunk = 1024;
+    size_t best_minimal_inlier_count = 0;
+    double best_minimal_msac_score = std::numeric_limits<double>::max();
+    size_t dynamic_max_iter = 0;
+    double log_prob_missing_model = 0;
+    plb_ransac_stats stats;
+    plb_counters cnt;
+    double best_model[9];
+    // per round
+    size_t B = 0, g0 = 0;
+    std::vector<int> imp_slot, imp_sample, trig;
+    int imp_base = 0, trig_base = 0; // offsets into the round's gathered-model / LO-result arrays
+    long long mask_off = 0;
+    int polish_pidx = -1;
+    ~PState() { delete sampler; }
+};
+
+static void update_dynamic(PState &S, int K) { // ransac_impl.h:150-153
+    S.stats.inlier_ratio = static_cast<double>(S.stats.num_inliers) / static_cast<double>(S.t->n);
+    S.dynamic_max_iter = compute_dynamic_max_iter(S.stats.num_inliers, S.t->n, (size_t)K, S.log_prob_missing_model,
+                                                  S.t->opt.dyn_num_trials_mult, S.t->opt.min_iterations,
+                                                  S.t->opt.max_iterations);
+}
+
+// Runs a group of problems of the same kind in lock-step rounds: one solve launch, one score launch and (when some
+// model improved) one gather + one LM launch per round for the WHOLE group.
+static int run_group(int kind, std::vector<Task *> &tasks) {
     Engine &E = *engine();
     const int K = kind_sample_size(kind), MAXM = kind_max_models(kind), MSZ = kind_model_size(kind);
-    plb_ransac_stats stats;
-    stats.refinements = 0;
-    stats.iterations = 0;
-    stats.num_inliers = 0;
-    stats.inlier_ratio = 0;
-    stats.model_score = std::numeric_limits<double>::max();
-    plb_counters cnt;
-    std::memset(&cnt, 0, sizeof(cnt));
-    // ransac.cc:47-50 etc.: identity unless an initial model is scored
-    if (!opt.score_initial_model) {
-        std::fill(model, model + MSZ, 0.0);
-        if (MSZ == 7) model[0] = 1.0;
-        else model[0] = model[4] = model[8] = 1.0;
+    const int b_dim = (kind == KIND_PNP) ? 3 : 2, n_arr = 2 + b_dim;
+    const int NP = (int)tasks.size();
+    std::vector<PState> PS(NP);
+    bool any_points = false;
+    for (int i = 0; i < NP; ++i) {
+        Task &t = *tasks[i];
+        PState &S = PS[i];
+        S.t = &t;
+        std::memset(&S.cnt, 0, sizeof(S.cnt));
+        S.stats.refinements = S.stats.iterations = S.stats.num_inliers = 0;
+        S.stats.inlier_ratio = 0;
+        S.stats.model_score = std::numeric_limits<double>::max();
+        if (!t.opt.score_initial_model) { // ransac.cc:47-50 etc.: identity unless an initial model is scored
+            std::fill(t.model, t.model + MSZ, 0.0);
+            if (MSZ == 7) t.model[0] = 1.0;
+            else t.model[0] = t.model[4] = t.model[8] = 1.0;
+        }
+        std::fill(S.best_model, S.best_model + 9, 0.0);
+        std::copy(t.model, t.model + MSZ, S.best_model);
+        if (t.n > (size_t)(1u << 26)) {
+            g_err = "too many correspondences";
+            return PLB_ERR_ARG;
+        }
+        S.n = (int)t.n;
+        S.n_pad = (S.n + 31) & ~31;
+        S.enough = t.n >= (size_t)K; // ransac_impl.h:161-163
+        S.dynamic_max_iter = t.opt.max_iterations;
+        S.log_prob_missing_model = std::log(1.0 - t.opt.success_prob);
+        any_points |= (t.n > 0);
     }
-    if (n_pts > (size_t)std::numeric_limits<int>::max() / 64) {
-        g_err = "too many correspondences";
-        return PLB_ERR_ARG;
-    }
-    if (n_pts == 0) {
-        if (stats_out) *stats_out = stats;
-        if (cnt_out) *cnt_out = cnt;
+    auto finish = [&]() {
+        for (int i = 0; i < NP; ++i) {
+            PState &S = PS[i];
+            S.cnt.scored_corrs = S.cnt.hypotheses * S.t->n;
+            if (S.t->stats_out) *S.t->stats_out = S.stats;
+            if (S.t->cnt_out) *S.t->cnt_out = S.cnt;
+        }
+    };
+    if (!any_points) {
+        finish();
         return PLB_OK;
     }
     int rc = E.init();
     if (rc != PLB_OK) return rc;
-    const uint64_t launches0 = E.launches;
     cudaStream_t st = E.stream;
-    const int n = (int)n_pts;
-    const int n_pad = (n + 31) & ~31;
-    const int b_dim = (kind == KIND_PNP) ? 3 : 2;
-    const int n_arr = 2 + b_dim;
-
-    // ---- upload (pinned staging) + layout transform ---------------------------------------------------------
+    const uint64_t launches0 = E.launches;
     uint64_t h2d = 0, d2h = 0;
-    if ((rc = E.mask.ensure(n)) || (rc = E.h_mask.ensure(n)) || (rc = E.work.ensure(8)) ||
-        (rc = E.model_dev.ensure(16)) || (rc = E.h_model.ensure(16)))
-        return rc;
-    const double *soa64 = nullptr;
-    const float *soa32 = nullptr;
-    if (res) {
-        soa64 = res->soa64.p;
-        soa32 = res->soa32.p;
-    } else {
-        if ((rc = E.h_in_a.ensure(2 * (size_t)n)) || (rc = E.h_in_b.ensure((size_t)b_dim * n)) ||
-            (rc = E.in_a.ensure(2 * (size_t)n)) || (rc = E.in_b.ensure((size_t)b_dim * n)) ||
-            (rc = E.soa64.ensure((size_t)n_arr * n_pad)) || (rc = E.soa32.ensure((size_t)n_arr * n_pad)))
-            return rc;
-        std::memcpy(E.h_in_a.p, a, sizeof(double) * 2 * n);
-        std::memcpy(E.h_in_b.p, b, sizeof(double) * b_dim * n);
-        PLB_CUDA(cudaMemcpyAsync(E.in_a.p, E.h_in_a.p, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
-        PLB_CUDA(cudaMemcpyAsync(E.in_b.p, E.h_in_b.p, sizeof(double) * b_dim * n, cudaMemcpyHostToDevice, st));
-        h2d += sizeof(double) * (size_t)(2 + b_dim) * n;
-        launch_transpose(E.in_a.p, E.in_b.p, n, b_dim, E.soa64.p, E.soa32.p, n_pad, st);
-        E.launches++;
-        soa64 = E.soa64.p;
-        soa32 = E.soa32.p;
-    }
-    ProblemDev P;
-    std::memset(&P, 0, sizeof(P));
-    for (int c = 0; c < n_arr; ++c) {
-        P.p[c] = soa64 + (size_t)c * n_pad;
-        P.f[c] = soa32 + (size_t)c * n_pad;
-    }
-    P.n = n;
-    P.kind = kind;
-    P.sq_thr = max_error * max_error;
-    P.rfc = rfc;
-
-    const LmParams lo = lo_params(kind, max_error);
-    auto t_lo = std::chrono::steady_clock::now();
     double lo_wait = 0.0;
     float gpu_ms_total = 0.f;
-
-    // ---- serial state (ransac_impl.h:99-104,165-171) --------------------------------------------------------
-    size_t best_minimal_inlier_count = 0;
-    double best_minimal_msac_score = std::numeric_limits<double>::max();
-    size_t dynamic_max_iter = opt.max_iterations;
-    const double log_prob_missing_model = std::log(1.0 - opt.success_prob);
-    double best_model[9];
-    std::copy(model, model + MSZ, best_model);
-    const bool enough = n_pts >= (size_t)K; // ransac_impl.h:161-163
-
-    // Runs LM jobs on `njobs` models staged in E.h_lm_in (9 doubles each) and returns with E.h_lm_out filled.
-    auto run_lm_host_models = [&](int njobs, const LmParams &prm, const char *mask_dev, const ProblemDev &PP) -> int {
-        int r;
-        if ((r = E.lm_in.ensure(9 * (size_t)njobs)) || (r = E.h_lm_out.ensure(njobs))) return r;
-        if (prm.subset_mode != 0 && (r = E.subset.ensure((size_t)njobs * n_pad))) return r;
-        PLB_CUDA(cudaMemcpyAsync(E.lm_in.p, E.h_lm_in.p, sizeof(double) * 9 * njobs, cudaMemcpyHostToDevice, st));
-        launch_lm(PP, E.lm_in.p, njobs, prm, mask_dev, E.subset.p, n_pad, E.h_lm_out.d, st);
-        E.launches++;
-        h2d += sizeof(double) * 9 * njobs;
-        d2h += sizeof(LmJobOut) * njobs;
+    auto sync_timed = [&](double *acc) -> int {
         auto t0 = std::chrono::steady_clock::now();
         PLB_CUDA(cudaStreamSynchronize(st));
-        lo_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (acc) *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         return PLB_OK;
     };
 
-    // score_models() for ONE iteration given its records (ransac_impl.h:106-154).
-    //   cnts/scs: per-model records; mdl(i): pointer to model i; lo_result: LmJobOut of the refined last-improving model
-    auto update_dynamic = [&]() {
-        stats.inlier_ratio = static_cast<double>(stats.num_inliers) / static_cast<double>(n_pts);
-        dynamic_max_iter = compute_dynamic_max_iter(stats.num_inliers, n_pts, (size_t)K, log_prob_missing_model,
-                                                    opt.dyn_num_trials_mult, opt.min_iterations, opt.max_iterations);
-    };
-
-    if (enough) {
-        if ((rc = E.h_lm_in.ensure(9 * 64))) return rc;
-        // ---- initial model (ransac_impl.h:173-176) -----------------------------------------------------------
-        if (opt.score_initial_model) {
-            std::copy(model, model + MSZ, E.h_model.p);
-            PLB_CUDA(cudaMemcpyAsync(E.model_dev.p, E.h_model.p, sizeof(double) * MSZ, cudaMemcpyHostToDevice, st));
-            if ((rc = E.h_counts.ensure(64)) || (rc = E.h_scores.ensure(64))) return rc;
-            {
-                const int one = 1;
-                PLB_CUDA(cudaMemcpyAsync(E.work.p + 2, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    // ---- device layout of the group: SoA arrays of every non-resident problem, masks, ProblemDev table -----------
+    size_t in_doubles = 0, soa_elems = 0, mask_bytes = 0, px_elems = 0;
+    int max_n = 0, max_n_pad = 0, n_up = 0, n_polish_pnp = 0;
+    for (PState &S : PS) {
+        if (S.n == 0) continue;
+        if (!S.t->res) {
+            in_doubles += (size_t)n_arr * S.n;
+            soa_elems += (size_t)n_arr * S.n_pad;
+            ++n_up;
+        }
+        S.mask_off = (long long)mask_bytes;
+        mask_bytes += (size_t)S.n_pad;
+        max_n = std::max(max_n, S.n);
+        max_n_pad = std::max(max_n_pad, S.n_pad);
+        if (kind == KIND_PNP && S.t->polish.enabled && S.t->polish.px_scaled) {
+            px_elems += 2 * (size_t)S.n_pad;
+            ++n_polish_pnp;
+        }
+    }
+    const int n_probdev = NP + n_polish_pnp;
+    if ((rc = E.h_in.ensure(in_doubles + px_elems)) || (rc = E.in.ensure(in_doubles)) || (rc = E.soa64.ensure(soa_elems)) ||
+        (rc = E.soa32.ensure(soa_elems)) || (rc = E.px64.ensure(px_elems)) || (rc = E.mask.ensure(mask_bytes)) ||
+        (rc = E.h_mask.ensure(mask_bytes)) || (rc = E.work.ensure(8)) || (rc = E.probs.ensure(n_probdev)) ||
+        (rc = E.h_probs.ensure(n_probdev)) || (rc = E.tdesc.ensure(std::max(n_up, 1))) ||
+        (rc = E.h_tdesc.ensure(std::max(n_up, 1))))
+        return rc;
+    {
+        size_t in_off = 0, soa_off = 0, px_off = 0;
+        int iu = 0, ipol = 0;
+        for (int i = 0; i < NP; ++i) {
+            PState &S = PS[i];
+            S.pidx = i;
+            ProblemDev &P = E.h_probs.p[i];
+            std::memset(&P, 0, sizeof(P));
+            P.n = S.n;
+            P.kind = kind;
+            P.sq_thr = S.t->max_error * S.t->max_error;
+            P.rfc = S.t->rfc;
+            if (S.n == 0) continue;
+            if (S.t->res) {
+                for (int c = 0; c < n_arr; ++c) {
+                    P.p[c] = S.t->res->soa64.p + (size_t)c * S.n_pad;
+                    P.f[c] = S.t->res->soa32.p + (size_t)c * S.n_pad;
+                }
+            } else {
+                double *ha = E.h_in.p + in_off, *hb = ha + 2 * (size_t)S.n;
+                std::memcpy(ha, S.t->a, sizeof(double) * 2 * S.n);
+                std::memcpy(hb, S.t->b, sizeof(double) * (size_t)b_dim * S.n);
+                TransposeDesc &D = E.h_tdesc.p[iu++];
+                D.a = E.in.p + in_off;
+                D.b = D.a + 2 * (size_t)S.n;
+                D.s64 = E.soa64.p + soa_off;
+                D.s32 = E.soa32.p + soa_off;
+                D.n = S.n;
+                D.n_pad = S.n_pad;
+                D.b_dim = b_dim;
+                D.reserved = 0;
+                for (int c = 0; c < n_arr; ++c) {
+                    P.p[c] = D.s64 + (size_t)c * S.n_pad;
+                    P.f[c] = D.s32 + (size_t)c * S.n_pad;
+                }
+                in_off += (size_t)n_arr * S.n;
+                soa_off += (size_t)n_arr * S.n_pad;
             }
-            launch_score_models(P, E.model_dev.p, 1, E.work.p + 2, E.h_counts.d, E.h_scores.d, st);
-            E.launches++;
-            PLB_CUDA(cudaStreamSynchronize(st));
-            const size_t ic = E.h_counts.p[0];
-            const double sc = E.h_scores.p[0];
-            cnt.hypotheses++;
-            const bool more = ic > best_minimal_inlier_count, better = sc < best_minimal_msac_score;
-            if (more || better) {
-                if (more) best_minimal_inlier_count = ic;
-                if (better) best_minimal_msac_score = sc;
-                if (sc < stats.model_score) {
-                    stats.model_score = sc;
-                    stats.num_inliers = ic;
+            if (kind == KIND_PNP && S.t->polish.enabled && S.t->polish.px_scaled) {
+                // scaled pixels staged as SoA by the host (O(N) once); extra ProblemDev for the polish job
+                double *hp = E.h_in.p + in_doubles + px_off;
+                for (int k = 0; k < S.n; ++k) {
+                    hp[k] = S.t->polish.px_scaled[2 * k];
+                    hp[S.n_pad + k] = S.t->polish.px_scaled[2 * k + 1];
                 }
-                std::fill(E.h_lm_in.p, E.h_lm_in.p + 9, 0.0);
-                std::copy(model, model + MSZ, E.h_lm_in.p);
-                if ((rc = run_lm_host_models(1, lo, nullptr, P))) return rc;
-                stats.refinements++;
-                cnt.lo_calls++;
-                cnt.hypotheses++;
-                const LmJobOut &o = E.h_lm_out.p[0];
-                if (o.score < stats.model_score) {
-                    stats.model_score = o.score;
-                    stats.num_inliers = o.count;
-                    std::copy(o.model, o.model + MSZ, best_model);
-                }
-                update_dynamic();
+                for (int k = S.n; k < S.n_pad; ++k) hp[k] = hp[S.n_pad + k] = 0.0;
+                S.polish_pidx = NP + ipol;
+                ProblemDev &PP = E.h_probs.p[NP + ipol];
+                PP = P;
+                PP.p[0] = E.px64.p + px_off;
+                PP.p[1] = E.px64.p + px_off + S.n_pad;
+                px_off += 2 * (size_t)S.n_pad;
+                ++ipol;
             }
         }
+        if (in_doubles) {
+            PLB_CUDA(cudaMemcpyAsync(E.in.p, E.h_in.p, sizeof(double) * in_doubles, cudaMemcpyHostToDevice, st));
+            h2d += sizeof(double) * in_doubles;
+        }
+        if (px_elems) {
+            PLB_CUDA(cudaMemcpyAsync(E.px64.p, E.h_in.p + in_doubles, sizeof(double) * px_elems, cudaMemcpyHostToDevice, st));
+            h2d += sizeof(double) * px_elems;
+        }
+        PLB_CUDA(cudaMemcpyAsync(E.probs.p, E.h_probs.p, sizeof(ProblemDev) * n_probdev, cudaMemcpyHostToDevice, st));
+        if (n_up) {
+            PLB_CUDA(cudaMemcpyAsync(E.tdesc.p, E.h_tdesc.p, sizeof(TransposeDesc) * n_up, cudaMemcpyHostToDevice, st));
+            launch_transpose(E.tdesc.p, n_up, max_n_pad, st);
+            E.launches++;
+        }
+    }
 
-        // ---- main loop in rounds ---------------------------------------------------------------------------
-        Sampler sampler(n_pts, (size_t)K, opt);
-        size_t it = 0;
-        size_t chunk = 1024;
-        const size_t CHUNK_MAX = 16384;
-        bool broke = false;
-        std::vector<int> imp_slot;   // slots (s*MAXM+m) of improving models in this round
-        std::vector<int> imp_sample; // their sample index within the round
-        std::vector<int> trig;       // indices into imp_* that are the last improving model of their sample
-        while (!broke && it < opt.max_iterations) {
-            // break test at the top of iteration `it` (ransac_impl.h:182); the serial loop stops at the first
-            // it with it > min_it && it > dyn, i.e. at stop_at for the current dyn
-            if (it > opt.min_iterations && it > dynamic_max_iter) {
-                broke = true;
-                break;
-            }
-            const size_t stop_at = std::min<size_t>(opt.max_iterations, std::max(opt.min_iterations, dynamic_max_iter) + 1);
-            size_t B = std::min(chunk, CHUNK_MAX);
-            B = std::min(B, stop_at - it); // stop_at > it here
+    // LM launch helper: jobs[] + their input models already in E.h_lm_in[0 .. 9*njobs) (or on device, see gathered)
+    auto launch_lm_jobs = [&](int njobs, bool models_on_device, size_t dev_model_off) -> int {
+        int r;
+        if ((r = E.jobs.ensure(njobs)) || (r = E.h_lm_out.ensure(njobs)) || (r = E.lm_in.ensure(9 * (size_t)njobs + dev_model_off)))
+            return r;
+        PLB_CUDA(cudaMemcpyAsync(E.jobs.p, E.h_jobs.p, sizeof(LmJob) * njobs, cudaMemcpyHostToDevice, st));
+        h2d += sizeof(LmJob) * njobs;
+        if (!models_on_device) {
+            PLB_CUDA(cudaMemcpyAsync(E.lm_in.p + dev_model_off, E.h_lm_in.p, sizeof(double) * 9 * njobs, cudaMemcpyHostToDevice, st));
+            h2d += sizeof(double) * 9 * njobs;
+        }
+        launch_lm(kind, E.probs.p, E.jobs.p, E.lm_in.p + dev_model_off, njobs, max_n, E.mask.p, E.subset.p, E.h_lm_out.d, st);
+        E.launches++;
+        d2h += sizeof(LmJobOut) * njobs;
+        return PLB_OK;
+    };
+    auto make_lo_job = [&](LmJob &J, const PState &S, long long scratch_off) {
+        J.pidx = S.pidx;
+        J.reserved = 0;
+        J.mask_off = -1;
+        J.scratch_off = scratch_off;
+        J.prm = lo_params(kind, S.t->max_error);
+    };
 
-            chunk = std::min(CHUNK_MAX, chunk * 2);
-
-            if ((rc = E.h_samples.ensure(B * K)) || (rc = E.samples.ensure(B * K)) || (rc = E.h_n_models.ensure(B)) ||
-                (rc = E.h_first_slot.ensure(B)) || (rc = E.h_counts.ensure(B * MAXM)) ||
-                (rc = E.h_scores.ensure(B * MAXM)) || (rc = E.models.ensure(B * MAXM * MSZ)))
+    // ---- initial models (ransac_impl.h:173-176) ------------------------------------------------------------------
+    {
+        std::vector<int> who;
+        for (int i = 0; i < NP; ++i)
+            if (PS[i].enough && PS[i].t->opt.score_initial_model) who.push_back(i);
+        const int nw = (int)who.size();
+        if (nw) {
+            if ((rc = E.h_lm_in.ensure(9 * (size_t)nw)) || (rc = E.lm_in.ensure(9 * (size_t)nw)) || (rc = E.h_slots.ensure(nw)) ||
+                (rc = E.slots.ensure(nw)) || (rc = E.h_counts.ensure(nw)) || (rc = E.h_scores.ensure(nw)) ||
+                (rc = E.h_jobs.ensure(nw)) || (rc = E.subset.ensure((size_t)nw * max_n_pad)))
                 return rc;
-            for (size_t s = 0; s < B; ++s) sampler.next(E.h_samples.p + s * K);
-            PLB_CUDA(cudaMemcpyAsync(E.samples.p, E.h_samples.p, sizeof(uint32_t) * B * K, cudaMemcpyHostToDevice, st));
-            h2d += sizeof(uint32_t) * B * K;
-            d2h += 2 * sizeof(int) * B; // n_models + first_slot (records are added once the model count is known)
-            HypOut out;
-            out.n_models = E.h_n_models.d;
-            out.first_slot = E.h_first_slot.d;
-            out.model_count = E.work.p + 1;
-            out.counts = E.h_counts.d;
-            out.scores = E.h_scores.d;
-            out.models = E.models.p;
-            out.fscores = nullptr;
-            out.fcounts = nullptr;
-            PLB_CUDA(cudaEventRecord(E.ev0, st));
-            launch_hypotheses(P, E.samples.p, (int)B, E.work.p, out, g_mode.load(), st);
-            PLB_CUDA(cudaEventRecord(E.ev1, st));
-            E.launches += 2; // k_solve + k_score
-            PLB_CUDA(cudaStreamSynchronize(st));
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, E.ev0, E.ev1);
-            gpu_ms_total += ms;
-            cnt.samples_evaluated += B;
-            {
-                size_t nmod = 0;
-                for (size_t s = 0; s < B; ++s) nmod += E.h_n_models.p[s];
-                cnt.models_evaluated += nmod;
-                d2h += (sizeof(uint32_t) + sizeof(double)) * nmod;
+            // the 9-double staging rows double as the MSZ-strided model list expected by k_score
+            std::vector<double> packed((size_t)nw * MSZ);
+            for (int j = 0; j < nw; ++j) {
+                std::fill(E.h_lm_in.p + 9 * j, E.h_lm_in.p + 9 * j + 9, 0.0);
+                std::copy(PS[who[j]].t->model, PS[who[j]].t->model + MSZ, E.h_lm_in.p + 9 * j);
+                std::copy(PS[who[j]].t->model, PS[who[j]].t->model + MSZ, packed.data() + (size_t)j * MSZ);
+                E.h_slots.p[j] = who[j];
             }
-
-            // ---- pass 1: which models improve the best-minimal state?  (independent of LO results)
-            imp_slot.clear();
-            imp_sample.clear();
-            trig.clear();
-            {
-                size_t bc = best_minimal_inlier_count;
-                double bs = best_minimal_msac_score;
-                for (size_t s = 0; s < B; ++s) {
-                    const int nm = E.h_n_models.p[s];
-                    int last = -1;
-                    const size_t first = (size_t)E.h_first_slot.p[s];
-                    for (int m = 0; m < nm; ++m) {
-                        const size_t slot = first + m;
-                        const size_t ic = E.h_counts.p[slot];
-                        const double sc = E.h_scores.p[slot];
-                        const bool more = ic > bc, better = sc < bs;
-                        if (more || better) {
-                            if (more) bc = ic;
-                            if (better) bs = sc;
-                            imp_slot.push_back((int)slot);
-                            imp_sample.push_back((int)s);
-                            last = (int)imp_slot.size() - 1;
-                        }
+            if ((rc = E.models.ensure((size_t)nw * MSZ))) return rc;
+            PLB_CUDA(cudaMemcpyAsync(E.models.p, packed.data(), sizeof(double) * nw * MSZ, cudaMemcpyHostToDevice, st));
+            PLB_CUDA(cudaMemcpyAsync(E.slots.p, E.h_slots.p, sizeof(int) * nw, cudaMemcpyHostToDevice, st));
+            PLB_CUDA(cudaMemcpyAsync(E.work.p + 4, &nw, sizeof(int), cudaMemcpyHostToDevice, st));
+            launch_score_models(kind, E.probs.p, E.models.p, E.slots.p, nw, E.work.p + 4, E.h_counts.d, E.h_scores.d, st);
+            E.launches++;
+            if ((rc = sync_timed(nullptr))) return rc;
+            int nj = 0;
+            std::vector<int> jw;
+            for (int j = 0; j < nw; ++j) {
+                PState &S = PS[who[j]];
+                const size_t ic = E.h_counts.p[j];
+                const double sc = E.h_scores.p[j];
+                S.cnt.hypotheses++;
+                const bool more = ic > S.best_minimal_inlier_count, better = sc < S.best_minimal_msac_score;
+                if (more || better) {
+                    if (more) S.best_minimal_inlier_count = ic;
+                    if (better) S.best_minimal_msac_score = sc;
+                    if (sc < S.stats.model_score) {
+                        S.stats.model_score = sc;
+                        S.stats.num_inliers = ic;
                     }
-                    if (last >= 0) trig.push_back(last);
+                    make_lo_job(E.h_jobs.p[nj], S, (long long)nj * max_n_pad);
+                    if (nj != j) std::copy(E.h_lm_in.p + 9 * j, E.h_lm_in.p + 9 * j + 9, E.h_lm_in.p + 9 * nj);
+                    jw.push_back(who[j]);
+                    ++nj;
                 }
             }
-            const int n_imp = (int)imp_slot.size(), n_trig = (int)trig.size();
-            if (n_imp > 0) {
-                // gather improving models, refine the trigger models (batched LO), fetch both
-                if ((rc = E.h_slots.ensure(n_imp + n_trig)) || (rc = E.slots.ensure(n_imp + n_trig)) ||
-                    (rc = E.lm_in.ensure(9 * (size_t)(n_imp + n_trig))) || (rc = E.h_lm_in.ensure(9 * (size_t)(n_imp + n_trig))) ||
-                    (rc = E.h_lm_out.ensure(n_trig)))
-                    return rc;
-                for (int i = 0; i < n_imp; ++i) E.h_slots.p[i] = imp_slot[i];
-                for (int j = 0; j < n_trig; ++j) E.h_slots.p[n_imp + j] = imp_slot[trig[j]];
-                PLB_CUDA(cudaMemcpyAsync(E.slots.p, E.h_slots.p, sizeof(int) * (n_imp + n_trig), cudaMemcpyHostToDevice, st));
-                const int tot = 9 * (n_imp + n_trig);
-                k_gather_models<<<(tot + 127) / 128, 128, 0, st>>>(E.models.p, E.slots.p, n_imp + n_trig, MSZ, E.lm_in.p);
-                E.launches++;
-                PLB_CUDA(cudaMemcpyAsync(E.h_lm_in.p, E.lm_in.p, sizeof(double) * 9 * n_imp, cudaMemcpyDeviceToHost, st));
-                if (lo.subset_mode != 0 && (rc = E.subset.ensure((size_t)n_trig * n_pad))) return rc;
-                launch_lm(P, E.lm_in.p + 9 * (size_t)n_imp, n_trig, lo, nullptr, E.subset.p, n_pad, E.h_lm_out.d, st);
-                E.launches++;
-                h2d += sizeof(int) * (n_imp + n_trig);
-                d2h += sizeof(double) * 9 * n_imp + sizeof(LmJobOut) * n_trig;
-                auto t0 = std::chrono::steady_clock::now();
-                PLB_CUDA(cudaStreamSynchronize(st));
-                lo_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (nj) {
+                if ((rc = launch_lm_jobs(nj, false, 0))) return rc;
+                if ((rc = sync_timed(&lo_wait))) return rc;
+                for (int j = 0; j < nj; ++j) {
+                    PState &S = PS[jw[j]];
+                    const LmJobOut &o = E.h_lm_out.p[j];
+                    S.stats.refinements++;
+                    S.cnt.lo_calls++;
+                    S.cnt.hypotheses++;
+                    if (o.score < S.stats.model_score) {
+                        S.stats.model_score = o.score;
+                        S.stats.num_inliers = o.count;
+                        std::copy(o.model, o.model + MSZ, S.best_model);
+                    }
+                    update_dynamic(S, K);
+                }
             }
+        }
+    }
 
-            // ---- pass 2: replay the serial loop over this round ------------------------------------------------
-            int ip = 0, tp = 0; // cursors into imp_* / trig
-            for (size_t s = 0; s < B; ++s, ++it) {
-                if (it > opt.min_iterations && it > dynamic_max_iter) { // ransac_impl.h:182-184
-                    broke = true;
+    // ---- main loop in lock-step rounds ------------------------------------------------------------------------------
+    for (PState &S : PS) {
+        S.active = S.enough && S.t->opt.max_iterations > 0;
+        if (S.enough) S.sampler = new Sampler(S.t->n, (size_t)K, S.t->opt);
+    }
+    const size_t CHUNK_MAX = 16384, S_TOT_MAX = 262144;
+    int cap_factor = (kind == KIND_RELPOSE) ? 8 : MAXM;
+    std::vector<int> act;
+    for (;;) {
+        act.clear();
+        for (int i = 0; i < NP; ++i) {
+            PState &S = PS[i];
+            if (!S.active) continue;
+            // break test at the top of iteration `it` (ransac_impl.h:180-184)
+            if (S.it >= S.t->opt.max_iterations || (S.it > S.t->opt.min_iterations && S.it > S.dynamic_max_iter)) {
+                S.active = false;
+                continue;
+            }
+            act.push_back(i);
+        }
+        const int na = (int)act.size();
+        if (!na) break;
+        // round sizes: up to the iteration at which the serial loop would stop for the current dynamic_max_iter
+        size_t total = 0;
+        const size_t per_cap = std::max<size_t>(256, S_TOT_MAX / (size_t)na);
+        for (int a = 0; a < na; ++a) {
+            PState &S = PS[act[a]];
+            const size_t stop_at = std::min<size_t>(S.t->opt.max_iterations, std::max(S.t->opt.min_iterations, S.dynamic_max_iter) + 1);
+            size_t B = std::min(std::min(S.chunk, CHUNK_MAX), per_cap);
+            B = std::min(B, stop_at - S.it); // stop_at > it for an active problem
+            S.chunk = std::min(CHUNK_MAX, S.chunk * 2);
+            S.B = B;
+            S.g0 = total;
+            total += B;
+        }
+        const size_t cap_models = total * (size_t)cap_factor;
+        if ((rc = E.h_samples.ensure(total * K)) || (rc = E.samples.ensure(total * K)) || (rc = E.h_n_models.ensure(total)) ||
+            (rc = E.h_first_slot.ensure(total)) || (rc = E.h_counts.ensure(cap_models)) || (rc = E.h_scores.ensure(cap_models)) ||
+            (rc = E.models.ensure(cap_models * MSZ)) || (rc = E.model_prob.ensure(cap_models)) ||
+            (rc = E.h_act.ensure(2 * (size_t)na + 2)) || (rc = E.act.ensure(2 * (size_t)na + 2)))
+            return rc;
+        // sample tables on the host (robust/sampling.cc), problems in parallel when the round is large
+        {
+            auto gen = [&](int a0, int a1) {
+                for (int a = a0; a < a1; ++a) {
+                    PState &S = PS[act[a]];
+                    uint32_t *dst = E.h_samples.p + S.g0 * K;
+                    for (size_t s = 0; s < S.B; ++s) S.sampler->next(dst + s * K);
+                }
+            };
+            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            const int nt = (total >= 32768 && na > 1) ? (int)std::min<unsigned>({hw, 16u, (unsigned)na}) : 1;
+            if (nt <= 1) {
+                gen(0, na);
+            } else {
+                std::vector<std::thread> th;
+                for (int t = 0; t < nt; ++t) th.emplace_back(gen, (int)((long long)na * t / nt), (int)((long long)na * (t + 1) / nt));
+                for (auto &x : th) x.join();
+            }
+        }
+        for (int a = 0; a < na; ++a) {
+            E.h_act.p[a] = act[a];
+            E.h_act.p[na + a] = (int)PS[act[a]].g0;
+        }
+        E.h_act.p[2 * na] = (int)total;
+        PLB_CUDA(cudaMemcpyAsync(E.samples.p, E.h_samples.p, sizeof(uint32_t) * total * K, cudaMemcpyHostToDevice, st));
+        PLB_CUDA(cudaMemcpyAsync(E.act.p, E.h_act.p, sizeof(int) * (2 * na + 1), cudaMemcpyHostToDevice, st));
+        h2d += sizeof(uint32_t) * total * K + sizeof(int) * (2 * na + 1);
+        RoundDesc R;
+        R.probs = E.probs.p;
+        R.active = E.act.p;
+        R.g_off = E.act.p + na;
+        R.n_active = na;
+        R.samples = E.samples.p;
+        R.n_total = (int)total;
+        HypOut out;
+        out.n_models = E.h_n_models.d;
+        out.first_slot = E.h_first_slot.d;
+        out.model_count = E.work.p + 1;
+        out.cap_models = (int)std::min<size_t>(cap_models, (size_t)std::numeric_limits<int>::max());
+        out.overflow = E.work.p + 2;
+        out.counts = E.h_counts.d;
+        out.scores = E.h_scores.d;
+        out.models = E.models.p;
+        out.model_prob = E.model_prob.p;
+        PLB_CUDA(cudaEventRecord(E.ev0, st));
+        launch_hypotheses(kind, R, E.work.p, out, st);
+        PLB_CUDA(cudaEventRecord(E.ev1, st));
+        E.launches += 2; // k_solve + k_score
+        PLB_CUDA(cudaMemcpyAsync(E.h_work.p, E.work.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if ((rc = sync_timed(nullptr))) return rc;
+        if (E.h_work.p[2] != 0) { // model list overflow: redo the round with the worst-case capacity (no state was touched)
+            if (cap_factor >= MAXM) {
+                g_err = "internal error: model capacity exceeded";
+                return PLB_ERR_CUDA;
+            }
+            cap_factor = MAXM;
+            for (int a = 0; a < na; ++a) { // rewind the samplers by regenerating them up to `it`
+                PState &S = PS[act[a]];
+                delete S.sampler;
+                S.sampler = new Sampler(S.t->n, (size_t)K, S.t->opt);
+                std::vector<uint32_t> tmp(K);
+                for (size_t s = 0; s < S.it; ++s) S.sampler->next(tmp.data());
+                S.chunk = std::max<size_t>(1024, S.chunk / 2);
+            }
+            continue;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, E.ev0, E.ev1);
+        gpu_ms_total += ms;
+        d2h += 2 * sizeof(int) * total + (sizeof(uint32_t) + sizeof(double)) * (size_t)E.h_work.p[1];
+
+        // ---- pass 1: which models improve the best-minimal state?  (independent of LO results)
+        int n_imp_tot = 0, n_trig_tot = 0;
+        for (int a = 0; a < na; ++a) {
+            PState &S = PS[act[a]];
+            S.imp_slot.clear();
+            S.imp_sample.clear();
+            S.trig.clear();
+            size_t bc = S.best_minimal_inlier_count;
+            double bs = S.best_minimal_msac_score;
+            size_t nmod = 0;
+            for (size_t s = 0; s < S.B; ++s) {
+                const int nm = E.h_n_models.p[S.g0 + s];
+                nmod += nm;
+                const size_t first = (size_t)E.h_first_slot.p[S.g0 + s];
+                int last = -1;
+                for (int m = 0; m < nm; ++m) {
+                    const size_t slot = first + m;
+                    const size_t ic = E.h_counts.p[slot];
+                    const double sc = E.h_scores.p[slot];
+                    const bool more = ic > bc, better = sc < bs;
+                    if (more || better) {
+                        if (more) bc = ic;
+                        if (better) bs = sc;
+                        S.imp_slot.push_back((int)slot);
+                        S.imp_sample.push_back((int)s);
+                        last = (int)S.imp_slot.size() - 1;
+                    }
+                }
+                if (last >= 0) S.trig.push_back(last);
+            }
+            S.cnt.samples_evaluated += S.B;
+            S.cnt.models_evaluated += nmod;
+            S.imp_base = n_imp_tot;
+            S.trig_base = n_trig_tot;
+            n_imp_tot += (int)S.imp_slot.size();
+            n_trig_tot += (int)S.trig.size();
+        }
+        if (n_imp_tot > 0) {
+            // gather the improving models of every problem, refine the trigger models in one batched LM launch
+            const int ng = n_imp_tot + n_trig_tot;
+            if ((rc = E.h_slots.ensure(ng)) || (rc = E.slots.ensure(ng)) || (rc = E.lm_in.ensure(9 * (size_t)ng)) ||
+                (rc = E.h_lm_in.ensure(9 * (size_t)n_imp_tot)) || (rc = E.h_jobs.ensure(n_trig_tot)) ||
+                (rc = E.subset.ensure((size_t)n_trig_tot * max_n_pad)))
+                return rc;
+            for (int a = 0; a < na; ++a) {
+                PState &S = PS[act[a]];
+                for (size_t i = 0; i < S.imp_slot.size(); ++i) E.h_slots.p[S.imp_base + i] = S.imp_slot[i];
+                for (size_t j = 0; j < S.trig.size(); ++j) {
+                    E.h_slots.p[n_imp_tot + S.trig_base + j] = S.imp_slot[S.trig[j]];
+                    make_lo_job(E.h_jobs.p[S.trig_base + j], S, (long long)(S.trig_base + j) * max_n_pad);
+                }
+            }
+            PLB_CUDA(cudaMemcpyAsync(E.slots.p, E.h_slots.p, sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+            h2d += sizeof(int) * ng;
+            k_gather_models<<<(9 * ng + 127) / 128, 128, 0, st>>>(E.models.p, E.slots.p, ng, MSZ, E.lm_in.p);
+            E.launches++;
+            PLB_CUDA(cudaMemcpyAsync(E.h_lm_in.p, E.lm_in.p, sizeof(double) * 9 * n_imp_tot, cudaMemcpyDeviceToHost, st));
+            d2h += sizeof(double) * 9 * n_imp_tot;
+            if ((rc = launch_lm_jobs(n_trig_tot, true, 9 * (size_t)n_imp_tot))) return rc;
+            if ((rc = sync_timed(&lo_wait))) return rc;
+        }
+
+        // ---- pass 2: replay the serial loop over this round, problem by problem -----------------------------------
+        for (int a = 0; a < na; ++a) {
+            PState &S = PS[act[a]];
+            const plb_ransac_opt &opt = S.t->opt;
+            const int n_imp = (int)S.imp_slot.size();
+            int ip = 0, tp = 0;
+            for (size_t s = 0; s < S.B; ++s, ++S.it) {
+                if (S.it > opt.min_iterations && S.it > S.dynamic_max_iter) { // ransac_impl.h:182-184
+                    S.broke = true;
+                    S.active = false;
                     break;
                 }
-                const int nm = E.h_n_models.p[s];
-                cnt.samples++;
-                cnt.hypotheses += nm;
+                S.cnt.samples++;
+                S.cnt.hypotheses += E.h_n_models.p[S.g0 + s];
                 bool any = false;
-                while (ip < n_imp && imp_sample[ip] == (int)s) {
-                    const size_t slot = imp_slot[ip];
+                while (ip < n_imp && S.imp_sample[ip] == (int)s) {
+                    const size_t slot = S.imp_slot[ip];
                     const size_t ic = E.h_counts.p[slot];
                     const double sc = E.h_scores.p[slot];
                     // (more_inliers || better_score) holds by construction; state update as in :117-124
-                    if (ic > best_minimal_inlier_count) best_minimal_inlier_count = ic;
-                    if (sc < best_minimal_msac_score) best_minimal_msac_score = sc;
-                    if (sc < stats.model_score) { // :127-131
-                        stats.model_score = sc;
-                        std::copy(E.h_lm_in.p + 9 * ip, E.h_lm_in.p + 9 * ip + MSZ, best_model);
-                        stats.num_inliers = ic;
+                    if (ic > S.best_minimal_inlier_count) S.best_minimal_inlier_count = ic;
+                    if (sc < S.best_minimal_msac_score) S.best_minimal_msac_score = sc;
+                    if (sc < S.stats.model_score) { // :127-131
+                        S.stats.model_score = sc;
+                        const double *m = E.h_lm_in.p + 9 * (size_t)(S.imp_base + ip);
+                        std::copy(m, m + MSZ, S.best_model);
+                        S.stats.num_inliers = ic;
                     }
                     any = true;
                     ++ip;
                 }
                 if (any) { // :135-153
-                    const LmJobOut &o = E.h_lm_out.p[tp++];
-                    stats.refinements++;
-                    cnt.lo_calls++;
-                    cnt.hypotheses++;
-                    if (o.score < stats.model_score) {
-                        stats.model_score = o.score;
-                        stats.num_inliers = o.count;
-                        std::copy(o.model, o.model + MSZ, best_model);
+                    const LmJobOut &o = E.h_lm_out.p[S.trig_base + tp++];
+                    S.stats.refinements++;
+                    S.cnt.lo_calls++;
+                    S.cnt.hypotheses++;
+                    if (o.score < S.stats.model_score) {
+                        S.stats.model_score = o.score;
+                        S.stats.num_inliers = o.count;
+                        std::copy(o.model, o.model + MSZ, S.best_model);
                     }
-                    update_dynamic();
+                    update_dynamic(S, K);
                 }
             }
         }
-        stats.iterations = it;
+    }
+    for (PState &S : PS)
+        if (S.enough) S.stats.iterations = S.it;
 
-        // ---- final refinement (ransac_impl.h:190-198) ----------------------------------------------------------
-        std::fill(E.h_lm_in.p, E.h_lm_in.p + 9, 0.0);
-        std::copy(best_model, best_model + MSZ, E.h_lm_in.p);
-        if ((rc = run_lm_host_models(1, lo, nullptr, P))) return rc;
-        stats.refinements++;
-        cnt.lo_calls++;
-        cnt.hypotheses++;
-        {
-            const LmJobOut &o = E.h_lm_out.p[0];
-            if (o.score < stats.model_score) { // NB: model_score itself is not updated by the reference here
-                std::copy(o.model, o.model + MSZ, best_model);
-                stats.num_inliers = o.count;
+    // ---- final refinement of every problem (ransac_impl.h:190-198), one launch ---------------------------------------
+    {
+        std::vector<int> who;
+        for (int i = 0; i < NP; ++i)
+            if (PS[i].enough) who.push_back(i);
+        const int nw = (int)who.size();
+        if (nw) {
+            if ((rc = E.h_lm_in.ensure(9 * (size_t)nw)) || (rc = E.h_jobs.ensure(nw)) ||
+                (rc = E.subset.ensure((size_t)nw * max_n_pad)))
+                return rc;
+            for (int j = 0; j < nw; ++j) {
+                PState &S = PS[who[j]];
+                std::fill(E.h_lm_in.p + 9 * j, E.h_lm_in.p + 9 * j + 9, 0.0);
+                std::copy(S.best_model, S.best_model + MSZ, E.h_lm_in.p + 9 * j);
+                make_lo_job(E.h_jobs.p[j], S, (long long)j * max_n_pad);
+            }
+            if ((rc = launch_lm_jobs(nw, false, 0))) return rc;
+            if ((rc = sync_timed(&lo_wait))) return rc;
+            for (int j = 0; j < nw; ++j) {
+                PState &S = PS[who[j]];
+                const LmJobOut &o = E.h_lm_out.p[j];
+                S.stats.refinements++;
+                S.cnt.lo_calls++;
+                S.cnt.hypotheses++;
+                if (o.score < S.stats.model_score) { // NB: model_score itself is not updated by the reference here
+                    std::copy(o.model, o.model + MSZ, S.best_model);
+                    S.stats.num_inliers = o.count;
+                }
             }
         }
     }
-    (void)t_lo;
 
-    // ---- final inlier mask (ransac.cc:54,151,259,311) -----------------------------------------------------------
-    std::copy(best_model, best_model + MSZ, E.h_model.p);
-    PLB_CUDA(cudaMemcpyAsync(E.model_dev.p, E.h_model.p, sizeof(double) * MSZ, cudaMemcpyHostToDevice, st));
-    launch_inlier_mask(P, E.model_dev.p, P.sq_thr, E.mask.p, st);
-    E.launches++;
-    const bool do_polish = polish.enabled && stats.num_inliers > polish.min_inliers;
-    if (do_polish) {
-        // robust.cc:103-123,296-311,573-588,736-751: LM over the inliers with the user's BundleOptions
-        LmParams bp = bundle_params(polish.bundle);
-        ProblemDev PP = P;
-        if (kind == KIND_PNP && polish.px_scaled) {
-            if ((rc = E.px64.ensure(2 * (size_t)n_pad))) return rc;
-            // stage scaled pixels as SoA (host transposes: O(N) once)
-            if ((rc = E.h_in_a.ensure(2 * (size_t)n_pad))) return rc;
-            for (int k = 0; k < n; ++k) {
-                E.h_in_a.p[k] = polish.px_scaled[2 * k];
-                E.h_in_a.p[n_pad + k] = polish.px_scaled[2 * k + 1];
-            }
-            PLB_CUDA(cudaMemcpyAsync(E.px64.p, E.h_in_a.p, sizeof(double) * 2 * n_pad, cudaMemcpyHostToDevice, st));
-            PP.p[0] = E.px64.p;
-            PP.p[1] = E.px64.p + n_pad;
-            bp.use_camera = 1;
-            for (int i = 0; i < 4; ++i) bp.cam[i] = polish.cam[i];
+    // ---- final inlier masks (ransac.cc:54,151,259,311) + optional polish over the inliers (robust.cc) -----------------
+    {
+        std::vector<int> who;
+        for (int i = 0; i < NP; ++i)
+            if (PS[i].n > 0) who.push_back(i);
+        const int nw = (int)who.size();
+        if ((rc = E.h_mdesc.ensure(nw)) || (rc = E.mdesc.ensure(nw))) return rc;
+        for (int j = 0; j < nw; ++j) {
+            PState &S = PS[who[j]];
+            MaskDesc &D = E.h_mdesc.p[j];
+            D.pidx = S.pidx;
+            D.reserved = 0;
+            D.mask_off = S.mask_off;
+            std::copy(S.best_model, S.best_model + 9, D.model);
         }
-        if ((rc = E.lm_in.ensure(9)) || (rc = E.h_lm_out.ensure(1)) || (rc = E.subset.ensure(n_pad))) return rc;
-        std::fill(E.h_lm_in.p, E.h_lm_in.p + 9, 0.0);
-        std::copy(best_model, best_model + MSZ, E.h_lm_in.p);
-        PLB_CUDA(cudaMemcpyAsync(E.lm_in.p, E.h_lm_in.p, sizeof(double) * 9, cudaMemcpyHostToDevice, st));
-        launch_lm(PP, E.lm_in.p, 1, bp, E.mask.p, E.subset.p, n_pad, E.h_lm_out.d, st);
+        PLB_CUDA(cudaMemcpyAsync(E.mdesc.p, E.h_mdesc.p, sizeof(MaskDesc) * nw, cudaMemcpyHostToDevice, st));
+        h2d += sizeof(MaskDesc) * nw;
+        launch_inlier_masks(kind, E.probs.p, E.mdesc.p, nw, max_n, E.mask.p, st);
         E.launches++;
+        std::vector<int> pol;
+        for (int i = 0; i < NP; ++i)
+            if (PS[i].n > 0 && PS[i].t->polish.enabled && PS[i].stats.num_inliers > PS[i].t->polish.min_inliers) pol.push_back(i);
+        const int npol = (int)pol.size();
+        if (npol) {
+            // robust.cc:103-123,296-311,573-588,736-751: LM over the inliers with the user's BundleOptions
+            if ((rc = E.h_lm_in.ensure(9 * (size_t)npol)) || (rc = E.h_jobs.ensure(npol)) ||
+                (rc = E.subset.ensure((size_t)npol * max_n_pad)))
+                return rc;
+            for (int j = 0; j < npol; ++j) {
+                PState &S = PS[pol[j]];
+                std::fill(E.h_lm_in.p + 9 * j, E.h_lm_in.p + 9 * j + 9, 0.0);
+                std::copy(S.best_model, S.best_model + MSZ, E.h_lm_in.p + 9 * j);
+                LmJob &J = E.h_jobs.p[j];
+                J.pidx = S.pidx;
+                J.reserved = 0;
+                J.mask_off = S.mask_off;
+                J.scratch_off = (long long)j * max_n_pad;
+                J.prm = bundle_params(S.t->polish.bundle);
+                if (S.polish_pidx >= 0) {
+                    J.pidx = S.polish_pidx;
+                    J.prm.use_camera = 1;
+                    for (int c = 0; c < 4; ++c) J.prm.cam[c] = S.t->polish.cam[c];
+                }
+            }
+            if ((rc = launch_lm_jobs(npol, false, 0))) return rc;
+        }
+        PLB_CUDA(cudaMemcpyAsync(E.h_mask.p, E.mask.p, mask_bytes, cudaMemcpyDeviceToHost, st));
+        if ((rc = sync_timed(nullptr))) return rc;
+        for (int j = 0; j < npol; ++j) {
+            PState &S = PS[pol[j]];
+            std::copy(E.h_lm_out.p[j].model, E.h_lm_out.p[j].model + MSZ, S.best_model);
+        }
+        for (int i = 0; i < NP; ++i) {
+            PState &S = PS[i];
+            if (S.t->inliers && S.n > 0) std::memcpy(S.t->inliers, E.h_mask.p + S.mask_off, S.n);
+            std::copy(S.best_model, S.best_model + MSZ, S.t->model);
+            d2h += S.n;
+        }
     }
-    PLB_CUDA(cudaMemcpyAsync(E.h_mask.p, E.mask.p, n, cudaMemcpyDeviceToHost, st));
-    PLB_CUDA(cudaStreamSynchronize(st));
-    if (do_polish) std::copy(E.h_lm_out.p[0].model, E.h_lm_out.p[0].model + MSZ, best_model);
-    if (inliers) std::memcpy(inliers, E.h_mask.p, n);
-    std::copy(best_model, best_model + MSZ, model);
-
-    d2h += n;
-    cnt.h2d_bytes = h2d;
-    cnt.d2h_bytes = d2h;
-    cnt.scored_corrs = cnt.hypotheses * n_pts;
-    cnt.lo_seconds = lo_wait;
-    cnt.gpu_launches = E.launches - launches0;
-    cnt.gpu_seconds = gpu_ms_total * 1e-3;
-    if (stats_out) *stats_out = stats;
-    if (cnt_out) *cnt_out = cnt;
+    PLB_CUDA(cudaGetLastError());
+    // group-level counters are attributed to the first problem; per-problem ones are exact
+    PS[0].cnt.lo_seconds = lo_wait;
+    PS[0].cnt.gpu_launches = E.launches - launches0;
+    PS[0].cnt.gpu_seconds = gpu_ms_total * 1e-3;
+    PS[0].cnt.h2d_bytes = h2d;
+    PS[0].cnt.d2h_bytes = d2h;
+    finish();
     return PLB_OK;
+}
+
+// Single-problem convenience used by the plb_ransac_* / plb_estimate_* entry points.
+static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, const plb_ransac_opt &opt,
+                      double max_error, int rfc, double *model, char *inliers, plb_ransac_stats *stats_out,
+                      plb_counters *cnt_out, const FinalPolish &polish, const Resident *res = nullptr) {
+    Task t;
+    t.kind = kind;
+    t.a = a;
+    t.b = b;
+    t.n = n_pts;
+    t.opt = opt;
+    t.max_error = max_error;
+    t.rfc = rfc;
+    t.model = model;
+    t.inliers = inliers;
+    t.stats_out = stats_out;
+    t.cnt_out = cnt_out;
+    t.polish = polish;
+    t.res = res;
+    std::vector<Task *> v{&t};
+    return run_group(kind, v);
 }
 
 // One LM refinement over all n points (robust/bundle.cc:84-112,206-222,313-333,394-411)
@@ -672,17 +959,25 @@ static int run_refine(int kind, const double *a, const double *b, size_t n_pts, 
     cudaStream_t st = E.stream;
     const int n = (int)n_pts, n_pad = (n + 31) & ~31;
     const int b_dim = (kind == KIND_PNP) ? 3 : 2, n_arr = 2 + b_dim, MSZ = kind_model_size(kind);
-    if ((rc = E.h_in_a.ensure(2 * (size_t)n)) || (rc = E.h_in_b.ensure((size_t)b_dim * n)) ||
-        (rc = E.in_a.ensure(2 * (size_t)n)) || (rc = E.in_b.ensure((size_t)b_dim * n)) ||
+    if ((rc = E.h_in.ensure((size_t)n_arr * n)) || (rc = E.in.ensure((size_t)n_arr * n)) ||
         (rc = E.soa64.ensure((size_t)n_arr * n_pad)) || (rc = E.soa32.ensure((size_t)n_arr * n_pad)) ||
-        (rc = E.lm_in.ensure(9)) || (rc = E.h_lm_in.ensure(9)) || (rc = E.h_lm_out.ensure(1)))
+        (rc = E.lm_in.ensure(9)) || (rc = E.h_lm_in.ensure(9)) || (rc = E.h_lm_out.ensure(1)) ||
+        (rc = E.probs.ensure(1)) || (rc = E.h_probs.ensure(1)) || (rc = E.tdesc.ensure(1)) || (rc = E.h_tdesc.ensure(1)) ||
+        (rc = E.jobs.ensure(1)) || (rc = E.h_jobs.ensure(1)))
         return rc;
-    std::memcpy(E.h_in_a.p, a, sizeof(double) * 2 * n);
-    std::memcpy(E.h_in_b.p, b, sizeof(double) * b_dim * n);
-    PLB_CUDA(cudaMemcpyAsync(E.in_a.p, E.h_in_a.p, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
-    PLB_CUDA(cudaMemcpyAsync(E.in_b.p, E.h_in_b.p, sizeof(double) * b_dim * n, cudaMemcpyHostToDevice, st));
-    launch_transpose(E.in_a.p, E.in_b.p, n, b_dim, E.soa64.p, E.soa32.p, n_pad, st);
-    ProblemDev P;
+    std::memcpy(E.h_in.p, a, sizeof(double) * 2 * n);
+    std::memcpy(E.h_in.p + 2 * (size_t)n, b, sizeof(double) * b_dim * n);
+    PLB_CUDA(cudaMemcpyAsync(E.in.p, E.h_in.p, sizeof(double) * (size_t)n_arr * n, cudaMemcpyHostToDevice, st));
+    TransposeDesc &D = E.h_tdesc.p[0];
+    D.a = E.in.p;
+    D.b = E.in.p + 2 * (size_t)n;
+    D.s64 = E.soa64.p;
+    D.s32 = E.soa32.p;
+    D.n = n;
+    D.n_pad = n_pad;
+    D.b_dim = b_dim;
+    D.reserved = 0;
+    ProblemDev &P = E.h_probs.p[0];
     std::memset(&P, 0, sizeof(P));
     for (int c = 0; c < n_arr; ++c) {
         P.p[c] = E.soa64.p + (size_t)c * n_pad;
@@ -691,12 +986,21 @@ static int run_refine(int kind, const double *a, const double *b, size_t n_pts, 
     P.n = n;
     P.kind = kind;
     P.sq_thr = 0.0;
-    LmParams bp = bundle_params(bopt);
-    bp.subset_mode = 0;
+    LmJob &J = E.h_jobs.p[0];
+    J.pidx = 0;
+    J.reserved = 0;
+    J.mask_off = -1;
+    J.scratch_off = 0;
+    J.prm = bundle_params(bopt);
+    J.prm.subset_mode = 0;
     std::fill(E.h_lm_in.p, E.h_lm_in.p + 9, 0.0);
     std::copy(model, model + MSZ, E.h_lm_in.p);
+    PLB_CUDA(cudaMemcpyAsync(E.tdesc.p, E.h_tdesc.p, sizeof(TransposeDesc), cudaMemcpyHostToDevice, st));
+    PLB_CUDA(cudaMemcpyAsync(E.probs.p, E.h_probs.p, sizeof(ProblemDev), cudaMemcpyHostToDevice, st));
+    PLB_CUDA(cudaMemcpyAsync(E.jobs.p, E.h_jobs.p, sizeof(LmJob), cudaMemcpyHostToDevice, st));
     PLB_CUDA(cudaMemcpyAsync(E.lm_in.p, E.h_lm_in.p, sizeof(double) * 9, cudaMemcpyHostToDevice, st));
-    launch_lm(P, E.lm_in.p, 1, bp, nullptr, nullptr, n_pad, E.h_lm_out.d, st);
+    launch_transpose(E.tdesc.p, 1, n_pad, st);
+    launch_lm(kind, E.probs.p, E.jobs.p, E.lm_in.p, 1, n, nullptr, nullptr, E.h_lm_out.d, st);
     E.launches += 2;
     PLB_CUDA(cudaStreamSynchronize(st));
     PLB_CUDA(cudaGetLastError());
@@ -1134,7 +1438,59 @@ int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
         g_err = "no usable CUDA device";
         return PLB_ERR_CUDA;
     }
-    const int nthreads = std::max(1, std::min<int>(streams, (int)count));
+    // Problems of the same kind run in lock-step groups (one set of launches per round for the whole group);
+    // `streams` groups are in flight at once, each on its own stream, so the host replay of one group overlaps the
+    // kernels of the others.
+    std::vector<Task> tasks(count);
+    std::vector<std::vector<Task *>> groups;
+    const int nthreads_req = std::max(1, streams);
+    for (int kind = 0; kind < 4; ++kind) {
+        std::vector<Task *> of_kind;
+        for (size_t i = 0; i < count; ++i) {
+            plb_problem &p = problems[i];
+            if (p.kind != kind) continue;
+            Task &t = tasks[i];
+            t.kind = kind;
+            t.a = p.a;
+            t.b = p.b;
+            t.n = (size_t)p.n;
+            t.opt = p.opt;
+            t.max_error = p.max_error;
+            t.rfc = p.real_focal_check;
+            t.model = p.model;
+            t.inliers = p.inliers;
+            t.stats_out = &p.stats;
+            t.cnt_out = &p.counters;
+            p.status = PLB_OK;
+            if (p.resident > 0) {
+                const Resident *res = nullptr;
+                {
+                    std::lock_guard<std::mutex> lk(g_res_mtx);
+                    if ((size_t)p.resident <= g_resident.size()) res = g_resident[p.resident - 1];
+                }
+                if (!res || res->kind != kind) {
+                    g_err = "invalid resident handle";
+                    return PLB_ERR_ARG;
+                }
+                t.res = res;
+                t.n = (size_t)res->n;
+            } else if (t.n > 0 && (!p.a || !p.b)) {
+                g_err = "null argument";
+                return PLB_ERR_ARG;
+            }
+            of_kind.push_back(&t);
+        }
+        if (of_kind.empty()) continue;
+        const size_t gsz = std::min<size_t>(256, std::max<size_t>(1, (of_kind.size() + nthreads_req - 1) / nthreads_req));
+        for (size_t o = 0; o < of_kind.size(); o += gsz)
+            groups.emplace_back(of_kind.begin() + o, of_kind.begin() + std::min(of_kind.size(), o + gsz));
+    }
+    for (size_t i = 0; i < count; ++i)
+        if (problems[i].kind < 0 || problems[i].kind > 3) {
+            g_err = "unknown problem kind";
+            return PLB_ERR_ARG;
+        }
+    const int nthreads = std::max(1, std::min<int>(nthreads_req, (int)groups.size()));
     const int dev = g_device;
     std::atomic<size_t> next(0);
     std::atomic<int> first_err(PLB_OK);
@@ -1144,41 +1500,9 @@ int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
         g_device = dev;
         g_engine = pool_engine((size_t)dev * 1024 + tid);
         for (;;) {
-            const size_t i = next.fetch_add(1);
-            if (i >= count) break;
-            plb_problem &p = problems[i];
-            int rc;
-            if (p.resident > 0) {
-                const Resident *res = nullptr;
-                {
-                    std::lock_guard<std::mutex> lk(g_res_mtx);
-                    if ((size_t)p.resident <= g_resident.size()) res = g_resident[p.resident - 1];
-                }
-                if (!res || res->kind != p.kind) {
-                    g_err = "invalid resident handle";
-                    rc = PLB_ERR_ARG;
-                } else {
-                    rc = run_ransac(p.kind, nullptr, nullptr, (size_t)res->n, p.opt, p.max_error, p.real_focal_check,
-                                    p.model, p.inliers, &p.stats, &p.counters, FinalPolish(), res);
-                }
-            } else
-            switch (p.kind) {
-            case PLB_KIND_PNP:
-                rc = plb_ransac_pnp(p.a, p.b, p.n, &p.opt, p.max_error, p.model, p.inliers, &p.stats, &p.counters);
-                break;
-            case PLB_KIND_RELPOSE:
-                rc = plb_ransac_relpose(p.a, p.b, p.n, &p.opt, p.max_error, p.model, p.inliers, &p.stats, &p.counters);
-                break;
-            case PLB_KIND_FUNDAMENTAL:
-                rc = plb_ransac_fundamental(p.a, p.b, p.n, &p.opt, p.max_error, p.real_focal_check, p.model, p.inliers,
-                                            &p.stats, &p.counters);
-                break;
-            case PLB_KIND_HOMOGRAPHY:
-                rc = plb_ransac_homography(p.a, p.b, p.n, &p.opt, p.max_error, p.model, p.inliers, &p.stats, &p.counters);
-                break;
-            default: rc = PLB_ERR_ARG; g_err = "unknown problem kind";
-            }
-            p.status = rc;
+            const size_t gi = next.fetch_add(1);
+            if (gi >= groups.size()) break;
+            const int rc = run_group(groups[gi][0]->kind, groups[gi]);
             if (rc != PLB_OK) {
                 int exp = PLB_OK;
                 if (first_err.compare_exchange_strong(exp, rc)) {
@@ -1189,10 +1513,19 @@ int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
         }
         g_engine = nullptr; // the pooled engine outlives the thread
     };
-    std::vector<std::thread> th;
-    for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
-    for (auto &t : th) t.join();
-    if (first_err.load() != PLB_OK) g_err = err_msg;
+    if (nthreads == 1) {
+        Engine *saved = g_engine;
+        work(0);
+        g_engine = saved;
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
+        for (auto &t : th) t.join();
+    }
+    if (first_err.load() != PLB_OK) {
+        g_err = err_msg;
+        for (size_t i = 0; i < count; ++i) problems[i].status = first_err.load();
+    }
     return first_err.load();
 }
 
@@ -1214,7 +1547,21 @@ int plb_resident_create(int kind, const double *a, const double *b, size_t n_pts
     }
     PLB_CUDA(cudaMemcpyAsync(da.p, a, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, E.stream));
     PLB_CUDA(cudaMemcpyAsync(db.p, b, sizeof(double) * b_dim * n, cudaMemcpyHostToDevice, E.stream));
-    launch_transpose(da.p, db.p, n, b_dim, R->soa64.p, R->soa32.p, n_pad, E.stream);
+    if ((rc = E.tdesc.ensure(1)) || (rc = E.h_tdesc.ensure(1))) {
+        delete R;
+        return rc;
+    }
+    TransposeDesc &D = E.h_tdesc.p[0];
+    D.a = da.p;
+    D.b = db.p;
+    D.s64 = R->soa64.p;
+    D.s32 = R->soa32.p;
+    D.n = n;
+    D.n_pad = n_pad;
+    D.b_dim = b_dim;
+    D.reserved = 0;
+    PLB_CUDA(cudaMemcpyAsync(E.tdesc.p, E.h_tdesc.p, sizeof(TransposeDesc), cudaMemcpyHostToDevice, E.stream));
+    launch_transpose(E.tdesc.p, 1, n_pad, E.stream);
     PLB_CUDA(cudaStreamSynchronize(E.stream));
     R->n = n;
     R->n_pad = n_pad;

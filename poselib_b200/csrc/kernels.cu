@@ -22,27 +22,27 @@ PLB_DEV int min_i(int a, int b) { return a < b ? a : b; }
 // ============================================================================================================
 // layout transform
 // ============================================================================================================
-__global__ void k_transpose(const double *__restrict__ a, const double *__restrict__ b, int n, int b_dim,
-                            double *__restrict__ s64, float *__restrict__ s32, int n_pad) {
+__global__ void k_transpose(const TransposeDesc *__restrict__ descs) {
+    const TransposeDesc d = descs[blockIdx.y];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_pad) return;
-    const bool live = k < n;
-    const int idx = live ? k : (n - 1); // pad by repeating the last point (never read by the kernels)
-    const double a0 = a[2 * idx], a1 = a[2 * idx + 1];
-    s64[0 * (size_t)n_pad + k] = a0;
-    s64[1 * (size_t)n_pad + k] = a1;
-    s32[0 * (size_t)n_pad + k] = (float)a0;
-    s32[1 * (size_t)n_pad + k] = (float)a1;
-    for (int c = 0; c < b_dim; ++c) {
-        const double v = b[(size_t)b_dim * idx + c];
-        s64[(2 + c) * (size_t)n_pad + k] = v;
-        s32[(2 + c) * (size_t)n_pad + k] = (float)v;
+    if (k >= d.n_pad) return;
+    const int idx = (k < d.n) ? k : (d.n - 1); // pad by repeating the last point (never read by the kernels)
+    const double a0 = d.a[2 * (size_t)idx], a1 = d.a[2 * (size_t)idx + 1];
+    d.s64[0 * (size_t)d.n_pad + k] = a0;
+    d.s64[1 * (size_t)d.n_pad + k] = a1;
+    d.s32[0 * (size_t)d.n_pad + k] = (float)a0;
+    d.s32[1 * (size_t)d.n_pad + k] = (float)a1;
+    for (int c = 0; c < d.b_dim; ++c) {
+        const double v = d.b[(size_t)d.b_dim * idx + c];
+        d.s64[(2 + c) * (size_t)d.n_pad + k] = v;
+        d.s32[(2 + c) * (size_t)d.n_pad + k] = (float)v;
     }
 }
-void launch_transpose(const double *in_a, const double *in_b, int n, int b_dim, double *soa64, float *soa32,
-                      int n_pad, cudaStream_t stream) {
+void launch_transpose(const TransposeDesc *descs_dev, int n_desc, int max_n_pad, cudaStream_t stream) {
+    if (n_desc <= 0) return;
     const int threads = 256;
-    k_transpose<<<(n_pad + threads - 1) / threads, threads, 0, stream>>>(in_a, in_b, n, b_dim, soa64, soa32, n_pad);
+    dim3 grid((max_n_pad + threads - 1) / threads, n_desc, 1);
+    k_transpose<<<grid, threads, 0, stream>>>(descs_dev);
 }
 
 // ============================================================================================================
@@ -285,11 +285,11 @@ PLB_DEV int warp_generate_models(const ProblemDev &P, const uint32_t *sample, Hy
     }
 }
 
-// Solve kernel: persistent, one warp = one minimal sample.  Models are appended to a compact list (slot range
-// reserved with one atomicAdd per sample); n_models[s] / first_slot[s] let the host walk them in (sample, model) order.
+// Solve kernel: persistent, one warp = one minimal sample of one problem of the group.  Models are appended to a
+// compact list (slot range reserved with one atomicAdd per sample); n_models[g] / first_slot[g] let the host walk them
+// in (sample, model) order per problem.
 template <int KIND>
-__global__ void __launch_bounds__(HYP_WARPS * 32)
-    k_solve(const ProblemDev P, const uint32_t *__restrict__ samples, int n_samples, int *work_counter, HypOut out) {
+__global__ void __launch_bounds__(HYP_WARPS * 32, 3) k_solve(const RoundDesc R, int *work_counter, HypOut out) {
     constexpr int K = (KIND == KIND_PNP) ? 3 : (KIND == KIND_RELPOSE) ? 5 : (KIND == KIND_FUND) ? 7 : 4;
     constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -302,36 +302,57 @@ __global__ void __launch_bounds__(HYP_WARPS * 32)
         __syncthreads();
     }
     for (;;) {
-        int s = 0;
-        if (lane == 0) s = atomicAdd(work_counter, 1);
-        s = __shfl_sync(0xffffffffu, s, 0);
-        if (s >= n_samples) break;
+        int g = 0;
+        if (lane == 0) g = atomicAdd(work_counter, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= R.n_total) break;
+        // which problem does sample g belong to?  (upper bound over g_off[1..n_active])
+        int lo = 0, hi = R.n_active - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(R.g_off + mid + 1) <= g) lo = mid + 1;
+            else hi = mid;
+        }
+        const int pidx = __ldg(R.active + lo);
+        const ProblemDev &P = R.probs[pidx];
         uint32_t sample[K];
 #pragma unroll
-        for (int i = 0; i < K; ++i) sample[i] = samples[(size_t)s * K + i];
-        const int nm = warp_generate_models<KIND>(P, sample, W, T, lane);
+        for (int i = 0; i < K; ++i) sample[i] = R.samples[(size_t)g * K + i];
+        int nm = warp_generate_models<KIND>(P, sample, W, T, lane);
         int base = 0;
         if (lane == 0) {
-            base = nm ? atomicAdd(out.model_count, nm) : 0;
-            out.n_models[s] = nm;
-            out.first_slot[s] = base;
+            if (nm) {
+                base = atomicAdd(out.model_count, nm);
+                if (base + nm > out.cap_models) { // cannot happen with the engine's capacity rule; fail loudly
+                    atomicExch(out.overflow, 1);
+                    nm = 0;
+                }
+            }
+            out.n_models[g] = nm;
+            out.first_slot[g] = base;
         }
         base = __shfl_sync(0xffffffffu, base, 0);
+        nm = __shfl_sync(0xffffffffu, nm, 0);
         const double *models = W->models;
         for (int e = lane; e < nm * MSZ; e += 32) out.models[(size_t)base * MSZ + e] = models[e];
+        if (lane < nm) out.model_prob[base + lane] = pidx;
+        for (int m = 32 + lane; m < nm; m += 32) out.model_prob[base + m] = pidx;
         __syncwarp();
     }
 }
 
-// Score kernel: persistent grid of 256-thread CTAs, one CTA scores one model at a time over all correspondences.
+// Score kernel: persistent grid of 256-thread CTAs, one CTA scores one model at a time over all correspondences of
+// the model's problem.
 template <int KIND>
-__global__ void __launch_bounds__(SCORE_THREADS)
-    k_score(const ProblemDev P, const double *__restrict__ models, const int *__restrict__ model_count,
-            uint32_t *counts, double *scores) {
+__global__ void __launch_bounds__(SCORE_THREADS, 4)
+    k_score(const ProblemDev *__restrict__ probs, const double *__restrict__ models, const int *__restrict__ model_prob,
+            const int *__restrict__ model_count, int cap, uint32_t *counts, double *scores) {
     constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
     __shared__ ScoreRed red;
-    const int nmod = *model_count;
+    int nmod = *model_count;
+    if (nmod > cap) nmod = cap;
     for (int m = blockIdx.x; m < nmod; m += gridDim.x) {
+        const ProblemDev P = probs[model_prob[m]];
         double mdl[MSZ];
 #pragma unroll
         for (int k = 0; k < MSZ; ++k) mdl[k] = models[(size_t)m * MSZ + k];
@@ -378,70 +399,62 @@ template <int KIND> static int score_blocks_per_sm() {
     }
     return cached;
 }
-int hyp_kernel_blocks(int kind) {
-    int per = 1;
-    switch (kind) {
-    case KIND_PNP: per = solve_blocks_per_sm<KIND_PNP>(); break;
-    case KIND_RELPOSE: per = solve_blocks_per_sm<KIND_RELPOSE>(); break;
-    case KIND_FUND: per = solve_blocks_per_sm<KIND_FUND>(); break;
-    default: per = solve_blocks_per_sm<KIND_HOMOG>(); break;
-    }
-    return per * sm_count();
-}
+int device_sm_count() { return sm_count(); }
 
 template <int KIND>
-static void launch_hyp_t(const ProblemDev &P, const uint32_t *samples, int n_samples, int *work_counter,
-                         const HypOut &out, cudaStream_t stream) {
+static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, cudaStream_t stream) {
     // persistent grids: a multiple of the SM count (resident CTAs per SM from the occupancy API), never more CTAs
     // than there is work for
     int blocks = solve_blocks_per_sm<KIND>() * sm_count();
-    const int need = (n_samples + HYP_WARPS - 1) / HYP_WARPS;
+    const int need = (R.n_total + HYP_WARPS - 1) / HYP_WARPS;
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
-    k_solve<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(P, samples, n_samples, work_counter, out);
+    k_solve<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(R, work, out);
     int sblocks = score_blocks_per_sm<KIND>() * sm_count();
-    const int max_models = n_samples * kind_max_models(KIND);
-    if (sblocks > max_models) sblocks = max_models;
-    k_score<KIND><<<sblocks, SCORE_THREADS, 0, stream>>>(P, out.models, out.model_count, out.counts, out.scores);
+    if (sblocks > out.cap_models) sblocks = out.cap_models;
+    if (sblocks < 1) sblocks = 1;
+    k_score<KIND><<<sblocks, SCORE_THREADS, 0, stream>>>(R.probs, out.models, out.model_prob, out.model_count,
+                                                        out.cap_models, out.counts, out.scores);
 }
-void launch_hypotheses(const ProblemDev &P, const uint32_t *samples, int n_samples, int *work_counter,
-                       const HypOut &out, int mode, cudaStream_t stream) {
-    (void)mode;
-    cudaMemsetAsync(work_counter, 0, 2 * sizeof(int), stream); // [0] sample queue, [1] = out.model_count
-    switch (P.kind) {
-    case KIND_PNP: launch_hyp_t<KIND_PNP>(P, samples, n_samples, work_counter, out, stream); break;
-    case KIND_RELPOSE: launch_hyp_t<KIND_RELPOSE>(P, samples, n_samples, work_counter, out, stream); break;
-    case KIND_FUND: launch_hyp_t<KIND_FUND>(P, samples, n_samples, work_counter, out, stream); break;
-    default: launch_hyp_t<KIND_HOMOG>(P, samples, n_samples, work_counter, out, stream); break;
+void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, cudaStream_t stream) {
+    cudaMemsetAsync(work, 0, 3 * sizeof(int), stream); // [0] sample queue, [1] model count, [2] overflow flag
+    switch (kind) {
+    case KIND_PNP: launch_hyp_t<KIND_PNP>(R, work, out, stream); break;
+    case KIND_RELPOSE: launch_hyp_t<KIND_RELPOSE>(R, work, out, stream); break;
+    case KIND_FUND: launch_hyp_t<KIND_FUND>(R, work, out, stream); break;
+    default: launch_hyp_t<KIND_HOMOG>(R, work, out, stream); break;
     }
 }
 
 // ============================================================================================================
 // explicit model scoring
 // ============================================================================================================
-void launch_score_models(const ProblemDev &P, const double *models, int n_models, const int *n_models_dev,
-                         uint32_t *counts, double *scores, cudaStream_t stream) {
+void launch_score_models(int kind, const ProblemDev *probs, const double *models, const int *model_prob, int n_models,
+                         const int *n_models_dev, uint32_t *counts, double *scores, cudaStream_t stream) {
     if (n_models <= 0) return;
     int blocks = n_models;
     if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-    switch (P.kind) {
-    case KIND_PNP: k_score<KIND_PNP><<<blocks, SCORE_THREADS, 0, stream>>>(P, models, n_models_dev, counts, scores); break;
-    case KIND_RELPOSE: k_score<KIND_RELPOSE><<<blocks, SCORE_THREADS, 0, stream>>>(P, models, n_models_dev, counts, scores); break;
-    case KIND_FUND: k_score<KIND_FUND><<<blocks, SCORE_THREADS, 0, stream>>>(P, models, n_models_dev, counts, scores); break;
-    default: k_score<KIND_HOMOG><<<blocks, SCORE_THREADS, 0, stream>>>(P, models, n_models_dev, counts, scores); break;
+    switch (kind) {
+    case KIND_PNP: k_score<KIND_PNP><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, n_models_dev, n_models, counts, scores); break;
+    case KIND_RELPOSE: k_score<KIND_RELPOSE><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, n_models_dev, n_models, counts, scores); break;
+    case KIND_FUND: k_score<KIND_FUND><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, n_models_dev, n_models, counts, scores); break;
+    default: k_score<KIND_HOMOG><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, n_models_dev, n_models, counts, scores); break;
     }
 }
-void launch_rescore_slots(const ProblemDev &, const HypOut &, const int *, int, cudaStream_t) {}
 
 // ============================================================================================================
 // inlier masks
 // ============================================================================================================
 template <int KIND>
-__global__ void k_inlier_mask(const ProblemDev P, const double *__restrict__ model, double sq_thr, char *mask) {
+__global__ void k_inlier_mask(const ProblemDev *__restrict__ probs, const MaskDesc *__restrict__ descs, char *mask_base) {
     constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    const MaskDesc &D = descs[blockIdx.y];
+    const ProblemDev P = probs[D.pidx];
+    const double sq_thr = P.sq_thr;
+    char *mask = mask_base + D.mask_off;
     double mdl[MSZ];
 #pragma unroll
-    for (int k = 0; k < MSZ; ++k) mdl[k] = model[k];
+    for (int k = 0; k < MSZ; ++k) mdl[k] = D.model[k];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= P.n) return;
     if (KIND == KIND_PNP) {
@@ -465,13 +478,16 @@ __global__ void k_inlier_mask(const ProblemDev P, const double *__restrict__ mod
         mask[k] = inl ? 1 : 0;
     }
 }
-void launch_inlier_mask(const ProblemDev &P, const double *model, double sq_thr, char *mask, cudaStream_t stream) {
-    const int threads = 256, blocks = (P.n + threads - 1) / threads;
-    switch (P.kind) {
-    case KIND_PNP: k_inlier_mask<KIND_PNP><<<blocks, threads, 0, stream>>>(P, model, sq_thr, mask); break;
-    case KIND_RELPOSE: k_inlier_mask<KIND_RELPOSE><<<blocks, threads, 0, stream>>>(P, model, sq_thr, mask); break;
-    case KIND_FUND: k_inlier_mask<KIND_FUND><<<blocks, threads, 0, stream>>>(P, model, sq_thr, mask); break;
-    default: k_inlier_mask<KIND_HOMOG><<<blocks, threads, 0, stream>>>(P, model, sq_thr, mask); break;
+void launch_inlier_masks(int kind, const ProblemDev *probs, const MaskDesc *descs_dev, int n_desc, int max_n,
+                         char *mask_base, cudaStream_t stream) {
+    if (n_desc <= 0 || max_n <= 0) return;
+    const int threads = 256;
+    dim3 grid((max_n + threads - 1) / threads, n_desc, 1);
+    switch (kind) {
+    case KIND_PNP: k_inlier_mask<KIND_PNP><<<grid, threads, 0, stream>>>(probs, descs_dev, mask_base); break;
+    case KIND_RELPOSE: k_inlier_mask<KIND_RELPOSE><<<grid, threads, 0, stream>>>(probs, descs_dev, mask_base); break;
+    case KIND_FUND: k_inlier_mask<KIND_FUND><<<grid, threads, 0, stream>>>(probs, descs_dev, mask_base); break;
+    default: k_inlier_mask<KIND_HOMOG><<<grid, threads, 0, stream>>>(probs, descs_dev, mask_base); break;
     }
 }
 
@@ -1013,8 +1029,8 @@ template <int NP> PLB_DEV void llt_solve(const double *A, const double *rhs, dou
 // if accepted, the Jacobian at the same parameters in a second pass; here both come from one pass.
 template <int KIND>
 __global__ void __launch_bounds__(LM_THREADS)
-    k_lm(const ProblemDev P, const double *__restrict__ models_in, const LmParams prm, const char *mask_in,
-         int *idx_scratch, int n_pad, LmJobOut *outs) {
+    k_lm(const ProblemDev *__restrict__ probs, const LmJob *__restrict__ jobs, const double *__restrict__ models_in,
+         const char *mask_base, int *idx_scratch, LmJobOut *outs) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int NP = LmDims<KIND>::NP;
@@ -1023,6 +1039,10 @@ __global__ void __launch_bounds__(LM_THREADS)
     __shared__ LmShared S;
     const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
     const int job = blockIdx.x / csize;
+    const LmJob &J = jobs[job];
+    const ProblemDev P = probs[J.pidx];
+    const LmParams prm = J.prm;
+    const char *mask_in = (J.mask_off >= 0) ? mask_base + J.mask_off : nullptr;
     const double *min = models_in + (size_t)job * 9;
     LmJobOut *out = outs + job;
     LossFn L;
@@ -1039,7 +1059,7 @@ __global__ void __launch_bounds__(LM_THREADS)
     const int *list = nullptr;
     bool untouched = false;
     if (prm.subset_mode != 0) {
-        int *mylist = idx_scratch + (size_t)job * n_pad + lo;
+        int *mylist = idx_scratch + J.scratch_off + lo;
         ModelCtx<KIND_RELPOSE> C;
         if (KIND == KIND_RELPOSE && prm.subset_mode == 1) C.init(min);
         const double *M = reinterpret_cast<const double *>(&C);
@@ -1228,9 +1248,9 @@ __global__ void __launch_bounds__(LM_THREADS)
 }
 
 template <int KIND>
-static void launch_lm_t(const ProblemDev &P, const double *models_in, int n_jobs, const LmParams &prm,
-                        const char *mask, int *idx_scratch, int n_pad, LmJobOut *out, cudaStream_t stream) {
-    int csize = (P.n + 2047) / 2048; // >= ~8 correspondences per thread before a second CTA pays off
+static void launch_lm_t(const ProblemDev *probs, const LmJob *jobs, const double *models_in, int n_jobs, int max_n,
+                        const char *mask_base, int *idx_scratch, LmJobOut *out, cudaStream_t stream) {
+    int csize = (max_n + 2047) / 2048; // >= ~8 correspondences per thread before another CTA pays off
     if (csize < 1) csize = 1;
     if (csize > LM_MAX_CLUSTER) csize = LM_MAX_CLUSTER;
     if (csize > 4 && csize < 8) csize = 4;
@@ -1248,16 +1268,16 @@ static void launch_lm_t(const ProblemDev &P, const double *models_in, int n_jobs
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_lm<KIND>, P, models_in, prm, mask, idx_scratch, n_pad, out);
+    cudaLaunchKernelEx(&cfg, k_lm<KIND>, probs, jobs, models_in, mask_base, idx_scratch, out);
 }
-void launch_lm(const ProblemDev &P, const double *models_in, int n_jobs, const LmParams &prm, const char *mask,
-               int *idx_scratch, int n_pad, LmJobOut *out, cudaStream_t stream) {
+void launch_lm(int kind, const ProblemDev *probs, const LmJob *jobs_dev, const double *models_in, int n_jobs,
+               int max_n, const char *mask_base, int *idx_scratch, LmJobOut *out, cudaStream_t stream) {
     if (n_jobs <= 0) return;
-    switch (P.kind) {
-    case KIND_PNP: launch_lm_t<KIND_PNP>(P, models_in, n_jobs, prm, mask, idx_scratch, n_pad, out, stream); break;
-    case KIND_RELPOSE: launch_lm_t<KIND_RELPOSE>(P, models_in, n_jobs, prm, mask, idx_scratch, n_pad, out, stream); break;
-    case KIND_FUND: launch_lm_t<KIND_FUND>(P, models_in, n_jobs, prm, mask, idx_scratch, n_pad, out, stream); break;
-    default: launch_lm_t<KIND_HOMOG>(P, models_in, n_jobs, prm, mask, idx_scratch, n_pad, out, stream); break;
+    switch (kind) {
+    case KIND_PNP: launch_lm_t<KIND_PNP>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
+    case KIND_RELPOSE: launch_lm_t<KIND_RELPOSE>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
+    case KIND_FUND: launch_lm_t<KIND_FUND>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
+    default: launch_lm_t<KIND_HOMOG>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
     }
 }
 

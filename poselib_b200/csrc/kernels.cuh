@@ -25,18 +25,30 @@ inline __host__ __device__ int kind_sample_size(int kind) { return kind == KIND_
 inline __host__ __device__ int kind_max_models(int kind) { return kind == KIND_PNP ? 4 : kind == KIND_RELPOSE ? 40 : kind == KIND_FUND ? 3 : 1; }
 inline __host__ __device__ int kind_model_size(int kind) { return (kind == KIND_PNP || kind == KIND_RELPOSE) ? 7 : 9; }
 
-// Per-round output of the hypothesis kernels.  Models are stored compactly: sample s owns slots
-// [first_slot[s], first_slot[s] + n_models[s]) of models / counts / scores; *model_count = total.
-// n_models, first_slot, counts and scores may point to pinned host memory (written straight over PCIe).
+// One round of hypothesis generation over a GROUP of problems of the same kind.  Global sample index g in
+// [0, n_total) belongs to the active problem a with g_off[a] <= g < g_off[a+1]; its ProblemDev is probs[active[a]].
+struct RoundDesc {
+    const ProblemDev *probs;
+    const int *active;   // n_active problem indices
+    const int *g_off;    // n_active + 1 offsets into the concatenated sample table
+    int n_active;
+    const uint32_t *samples; // n_total * K indices
+    int n_total;
+};
+
+// Per-round output of the hypothesis kernels.  Models are stored compactly: sample g owns slots
+// [first_slot[g], first_slot[g] + n_models[g]) of models / model_prob / counts / scores; *model_count = total.
+// n_models, first_slot, counts and scores point to mapped pinned host memory (written straight over PCIe).
 struct HypOut {
     int *n_models;
     int *first_slot;
     int *model_count;
+    int cap_models;   // capacity of models[]; samples that do not fit set *overflow and report 0 models
+    int *overflow;
     uint32_t *counts;
     double *scores;
     double *models;
-    float *fscores;   // fast mode: fp32 screening score / count of every model
-    uint32_t *fcounts;
+    int *model_prob;  // problem index of every model slot
 };
 
 // LM (local optimisation / final polish) job description — mirrors BundleOptions (types.h:60-95)
@@ -52,6 +64,13 @@ struct LmParams {
     double cam[4];
     int score_after; // score the refined model with sq_thr of the problem (count, score)
 };
+struct LmJob {
+    int pidx;               // index into probs[]
+    int reserved;
+    long long mask_off;     // offset into the mask buffer (subset_mode 2), else -1
+    long long scratch_off;  // offset (ints) into idx_scratch for the active-point list (subset modes 1, 2)
+    LmParams prm;
+};
 struct LmJobOut {
     double model[9];
     double score;
@@ -59,28 +78,36 @@ struct LmJobOut {
     int iterations;
     double cost, initial_cost;
 };
+struct TransposeDesc {
+    const double *a, *b; // caller layout (device copies): 2n and b_dim*n doubles
+    double *s64;
+    float *s32;
+    int n, n_pad, b_dim, reserved;
+};
+struct MaskDesc {
+    int pidx;
+    int reserved;
+    long long mask_off;
+    double model[9];
+};
 
 // ---- launchers (all asynchronous on `stream`) --------------------------------------------------------------
-// AoS (caller layout) -> SoA fp64 + fp32.  in_a: 2n doubles; in_b: 2n (2D) or 3n (3D) doubles.
-void launch_transpose(const double *in_a, const double *in_b, int n, int b_dim, double *soa64, float *soa32,
-                      int n_pad, cudaStream_t stream);
-// Fused sample -> solve -> score kernel.  samples: n_samples * K indices.  mode 0 exact, 1 fast (fp32 screen only).
-void launch_hypotheses(const ProblemDev &P, const uint32_t *samples, int n_samples, int *work_counter,
-                       const HypOut &out, int mode, cudaStream_t stream);
-// Exact fp64 scoring of an explicit list of models (model_size doubles each); *n_models_dev == n_models.
-void launch_score_models(const ProblemDev &P, const double *models, int n_models, const int *n_models_dev,
-                         uint32_t *counts, double *scores, cudaStream_t stream);
-// Exact rescoring of selected slots of a HypOut (fast mode confirmation): slots[i] = s*MAXM+m
-void launch_rescore_slots(const ProblemDev &P, const HypOut &out, const int *slots, int n_slots, cudaStream_t stream);
-// LM refinement: one thread-block cluster per job.  models_in: n_jobs * 9 doubles (model_size used).
-// mask (subset_mode 2): n bytes.  idx_scratch: n_jobs * n_pad ints (active-point lists, subset modes 1 and 2).
-void launch_lm(const ProblemDev &P, const double *models_in, int n_jobs, const LmParams &prm, const char *mask,
-               int *idx_scratch, int n_pad, LmJobOut *out, cudaStream_t stream);
-// Final inlier mask of a model (robust/utils.cc:331-351,374-383,434-513)
-void launch_inlier_mask(const ProblemDev &P, const double *model, double sq_thr, char *mask, cudaStream_t stream);
+// AoS (caller layout) -> SoA fp64 + fp32 for n_desc problems (descriptors in device memory).
+void launch_transpose(const TransposeDesc *descs_dev, int n_desc, int max_n_pad, cudaStream_t stream);
+// Solve + score kernels of one round (kind = kind of every problem of the group).  work: 3 ints of device scratch.
+void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, cudaStream_t stream);
+// Exact fp64 scoring of an explicit list of models (9 doubles stride MSZ) with problem indices; *n_models_dev = count.
+void launch_score_models(int kind, const ProblemDev *probs, const double *models, const int *model_prob, int n_models,
+                         const int *n_models_dev, uint32_t *counts, double *scores, cudaStream_t stream);
+// LM refinement: one thread-block cluster per job.  models_in: n_jobs * 9 doubles.
+void launch_lm(int kind, const ProblemDev *probs, const LmJob *jobs_dev, const double *models_in, int n_jobs,
+               int max_n, const char *mask_base, int *idx_scratch, LmJobOut *out, cudaStream_t stream);
+// Final inlier masks (robust/utils.cc:331-351,374-383,434-513): one descriptor per mask, sq_thr from the problem.
+void launch_inlier_masks(int kind, const ProblemDev *probs, const MaskDesc *descs_dev, int n_desc, int max_n,
+                         char *mask_base, cudaStream_t stream);
 // Batched direct solver calls (solvers/*.h surface): one warp per instance.
 void launch_solver_batch(int kind, int variant, size_t count, const double *a, const double *b, double *out,
                          int *n_out, int flags, cudaStream_t stream);
-int hyp_kernel_blocks(int kind);
+int device_sm_count();
 
 } // namespace plb
