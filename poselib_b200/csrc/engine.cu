@@ -189,7 +189,8 @@ struct Engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ready = false;
     int device = -1;
-    DevBuf<double> in, soa64, px64, models, lm_in;
+    DevBuf<double> in, soa64, px64, models, lm_in, s5_blk, s5_cpoly, s5_roots;
+    DevBuf<int> s5_nroots;
     DevBuf<float> soa32;
     DevBuf<uint32_t> samples;
     DevBuf<int> work, slots, subset, act, model_prob;
@@ -215,7 +216,11 @@ struct Engine {
 
     int init() {
         int dev = g_device;
-        if (ready && device == dev) return PLB_OK;
+        if (ready && device == dev) {
+            // the current device is per host thread (worker threads start on device 0): always re-select ours
+            PLB_CUDA(cudaSetDevice(dev));
+            return PLB_OK;
+        }
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0) {
@@ -687,10 +692,21 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         out.scores = E.h_scores.d;
         out.models = E.models.p;
         out.model_prob = E.model_prob.p;
+        out.s5_blk = out.s5_cpoly = out.s5_roots = nullptr;
+        out.s5_nroots = nullptr;
+        if (kind == KIND_RELPOSE) { // phase buffers of the 3-kernel 5-point solver
+            if ((rc = E.s5_blk.ensure(total * 105)) || (rc = E.s5_cpoly.ensure(total * 11)) ||
+                (rc = E.s5_roots.ensure(total * 10)) || (rc = E.s5_nroots.ensure(total)))
+                return rc;
+            out.s5_blk = E.s5_blk.p;
+            out.s5_cpoly = E.s5_cpoly.p;
+            out.s5_roots = E.s5_roots.p;
+            out.s5_nroots = E.s5_nroots.p;
+        }
         PLB_CUDA(cudaEventRecord(E.ev0, st));
         launch_hypotheses(kind, R, E.work.p, out, st);
         PLB_CUDA(cudaEventRecord(E.ev1, st));
-        E.launches += 2; // k_solve + k_score
+        E.launches += (kind == KIND_RELPOSE) ? 4 : 2; // k_solve (or k5_prep + k5_roots + k5_back) + k_score
         PLB_CUDA(cudaMemcpyAsync(E.h_work.p, E.work.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
         if ((rc = sync_timed(nullptr))) return rc;
         if (E.h_work.p[2] != 0) { // model list overflow: redo the round with the worst-case capacity (no state was touched)

@@ -341,6 +341,130 @@ __global__ void __launch_bounds__(HYP_WARPS * 32, 3) k_solve(const RoundDesc R, 
     }
 }
 
+// ---- relpose_5pt as three phase kernels -------------------------------------------------------------------------
+// The fused warp-per-sample 5-point solver is 181 KB of SASS and runs its Sturm root isolation on one lane; 16 warps
+// per SM at different places of that code starve on instruction fetch (profiles/r01_v2_batch64_summary.md).  The
+// arithmetic is unchanged, only regrouped so that each kernel's code is small and every phase uses the lanes it can:
+//   k5_prep  : warp  = sample   gather, pivoted-QR nullspace, trace constraints, LU, determinant polynomial
+//   k5_roots : lane  = sample   Sturm bracketing + Ridders/Newton (scalar, data dependent)
+//   k5_back  : lane  = (sample, root)  back-substitution, motion decomposition, cheirality; 3 samples per warp
+constexpr int S5_BLK = 105;
+
+PLB_DEV int sample_problem_slot(const RoundDesc &R, int g) {
+    int lo = 0, hi = R.n_active - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(R.g_off + mid + 1) <= g) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+struct PrepScratch {
+    Scratch5 s5;
+    double xs[30];
+};
+__global__ void __launch_bounds__(HYP_WARPS * 32) k5_prep(const RoundDesc R, int *work_counter, HypOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MonoTables *T = reinterpret_cast<MonoTables *>(smem_raw);
+    PrepScratch *W = reinterpret_cast<PrepScratch *>(smem_raw + 256) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    fill_tables(T);
+    __syncthreads();
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(work_counter, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= R.n_total) break;
+        const ProblemDev &P = R.probs[__ldg(R.active + sample_problem_slot(R, g))];
+        if (lane < 10) { // bearings of the 5 sampled correspondences (estimators/relative_pose.cc:51-54)
+            const int i = lane % 5, side = lane / 5;
+            const uint32_t id = R.samples[(size_t)g * 5 + i];
+            const d3 v = bearing(P.p[2 * side][id], P.p[2 * side + 1][id]);
+            double *o = W->xs + 15 * side + 3 * i;
+            o[0] = v.x; o[1] = v.y; o[2] = v.z;
+        }
+        __syncwarp();
+        solve_5pt_poly(W->xs, W->xs + 15, &W->s5, T, lane);
+        double *blk = out.s5_blk + (size_t)g * S5_BLK;
+        for (int e = lane; e < 39; e += 32) blk[e] = W->s5.A[e];
+        for (int e = lane; e < 36; e += 32) blk[39 + e] = W->s5.Nb[e];
+        if (lane < 30) blk[75 + lane] = W->xs[lane];
+        if (lane < 11) out.s5_cpoly[(size_t)lane * R.n_total + g] = W->s5.cpoly[lane];
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128) k5_roots(int n_total, HypOut out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_total) return;
+    double c[11], roots[10];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) c[k] = out.s5_cpoly[(size_t)k * n_total + g];
+    SturmWork w;
+    const int n = sturm_bisect10(c, roots, &w);
+    out.s5_nroots[g] = n;
+    double *o = out.s5_roots + (size_t)g * 10;
+    for (int k = 0; k < n; ++k) o[k] = roots[k];
+}
+
+__global__ void __launch_bounds__(128) k5_back(const RoundDesc R, HypOut out) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int si = lane / 10, r = lane % 10;
+    const int g = 3 * gw + si;
+    const bool live = (si < 3) && (g < R.n_total);
+    int nr = 0;
+    if (live) nr = out.s5_nroots[g];
+    const bool valid = live && r < nr;
+    double cand[4][7];
+    unsigned mask = 0;
+    if (valid) {
+        const double *blk = out.s5_blk + (size_t)g * S5_BLK;
+        double E[9];
+        backsub_5pt(blk, blk + 39, out.s5_roots[(size_t)g * 10 + r], E);
+        mask = motions_from_E(E, blk + 75, blk + 90, 5, cand);
+    }
+    const int mine = __popc(mask);
+    // exclusive prefix inside the 10-lane segment of the sample (root-major, candidate-minor order of the reference)
+    int pre = 0, total = 0;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const int v = __shfl_sync(0xffffffffu, mine, (10 * si + j) & 31);
+        if (j < r) pre += v;
+        total += v;
+    }
+    int base = 0, pidx = 0;
+    if (live && r == 0) {
+        pidx = __ldg(R.active + sample_problem_slot(R, g));
+        if (total) {
+            base = atomicAdd(out.model_count, total);
+            if (base + total > out.cap_models) {
+                atomicExch(out.overflow, 1);
+                total = 0;
+            }
+        }
+        out.n_models[g] = total;
+        out.first_slot[g] = base;
+    }
+    base = __shfl_sync(0xffffffffu, base, (10 * si) & 31);
+    total = __shfl_sync(0xffffffffu, total, (10 * si) & 31);
+    pidx = __shfl_sync(0xffffffffu, pidx, (10 * si) & 31);
+    if (valid && total) {
+        int pos = base + pre;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (mask & (1u << c)) {
+                double *o = out.models + (size_t)pos * 7;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) o[k] = cand[c][k];
+                out.model_prob[pos] = pidx;
+                ++pos;
+            }
+        }
+    }
+}
+
 // Score kernel: persistent grid of 256-thread CTAs, one CTA scores one model at a time over all correspondences of
 // the model's problem.
 template <int KIND>
@@ -401,15 +525,38 @@ template <int KIND> static int score_blocks_per_sm() {
 }
 int device_sm_count() { return sm_count(); }
 
+static int prep_blocks_per_sm() {
+    static int cached = -1;
+    if (cached < 0) {
+        const size_t smem = 256 + sizeof(PrepScratch) * HYP_WARPS;
+        cudaFuncSetAttribute(k5_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k5_prep, HYP_WARPS * 32, smem);
+        cached = nb > 0 ? nb : 1;
+    }
+    return cached;
+}
+
 template <int KIND>
 static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, cudaStream_t stream) {
     // persistent grids: a multiple of the SM count (resident CTAs per SM from the occupancy API), never more CTAs
     // than there is work for
-    int blocks = solve_blocks_per_sm<KIND>() * sm_count();
-    const int need = (R.n_total + HYP_WARPS - 1) / HYP_WARPS;
-    if (blocks > need) blocks = need;
-    if (blocks < 1) blocks = 1;
-    k_solve<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(R, work, out);
+    if (KIND == KIND_RELPOSE && out.s5_blk != nullptr) {
+        int blocks = prep_blocks_per_sm() * sm_count();
+        const int need = (R.n_total + HYP_WARPS - 1) / HYP_WARPS;
+        if (blocks > need) blocks = need;
+        if (blocks < 1) blocks = 1;
+        k5_prep<<<blocks, HYP_WARPS * 32, 256 + sizeof(PrepScratch) * HYP_WARPS, stream>>>(R, work, out);
+        k5_roots<<<(R.n_total + 127) / 128, 128, 0, stream>>>(R.n_total, out);
+        const int warps = (R.n_total + 2) / 3;
+        k5_back<<<(warps * 32 + 127) / 128, 128, 0, stream>>>(R, out);
+    } else {
+        int blocks = solve_blocks_per_sm<KIND>() * sm_count();
+        const int need = (R.n_total + HYP_WARPS - 1) / HYP_WARPS;
+        if (blocks > need) blocks = need;
+        if (blocks < 1) blocks = 1;
+        k_solve<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(R, work, out);
+    }
     int sblocks = score_blocks_per_sm<KIND>() * sm_count();
     if (sblocks > out.cap_models) sblocks = out.cap_models;
     if (sblocks < 1) sblocks = 1;

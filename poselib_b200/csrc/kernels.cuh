@@ -49,6 +49,11 @@ struct HypOut {
     double *scores;
     double *models;
     int *model_prob;  // problem index of every model slot
+    // relpose_5pt phase buffers (device), sized for the round's n_total samples:
+    double *s5_blk;   // per sample 105 doubles: A (39) | Nb (36) | sample bearings x1s,x2s (30)
+    double *s5_cpoly; // 11 x n_total, coefficient-major (cpoly[c * n_total + g])
+    double *s5_roots; // per sample 10 doubles
+    int *s5_nroots;   // per sample
 };
 
 // LM (local optimisation / final polish) job description — mirrors BundleOptions (types.h:60-95)

@@ -663,7 +663,9 @@ PLB_DEV double lin_mul_coef(double acc, const double *a, const double *b, int i,
 
 // Essential matrices from 5 bearing pairs.  x1s/x2s: shared arrays of 5 unit bearings (3 doubles each).
 // On return S->Es holds nroots row-major E matrices (relpose_5pt.cc:159-395).  Returns nroots (uniform).
-PLB_DEV int solve_5pt_E(const double *x1s, const double *x2s, Scratch5 *S, const MonoTables *T, int lane) {
+// First half of the 5-point solver: nullspace basis S->Nb, polynomial matrix S->A (3x13) and the degree-10
+// determinant polynomial S->cpoly (ascending)   (relpose_5pt.cc:162-352).
+PLB_DEV void solve_5pt_poly(const double *x1s, const double *x2s, Scratch5 *S, const MonoTables *T, int lane) {
     // ---- 9x5 epipolar constraints (:163-166): entry 3a+b of column i = x1[i][a]*x2[i][b]
     for (int e = lane; e < 45; e += 32) {
         const int i = e / 9, k = e % 9;
@@ -849,14 +851,13 @@ PLB_DEV int solve_5pt_E(const double *x1s, const double *x2s, Scratch5 *S, const
         }
         __syncwarp();
     }
-    // ---- real roots by Sturm bracketing (:356): scalar work on lane 0
-    if (lane == 0) S->nroots = sturm_bisect10(S->cpoly, S->roots, &S->sturm);
-    __syncwarp();
-    const int n = S->nroots;
-    // ---- back-substitution, one lane per root (:359-392)
-    if (lane < n) {
-        const double *A = S->A;
-        const double z = S->roots[lane], z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
+}
+
+// Back-substitution for one root z of the determinant polynomial: E (row-major 9) from the polynomial matrix A (3x13)
+// and the nullspace basis Nb (relpose_5pt.cc:359-392).
+PLB_DEV void backsub_5pt(const double *A, const double *Nb, double z, double *E) {
+    {
+        const double z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
         double B[3][2], bb[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -924,13 +925,24 @@ PLB_DEV int solve_5pt_E(const double *x1s, const double *x2s, Scratch5 *S, const
         }
         const double x = -s0, y = -s1;
         const double inv_norm = 1.0 / sqrt(x * x + y * y + z * z + 1.0);
-        double *E = S->Es + 9 * lane;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            const double e = S->Nb[4 * k + 0] * x + S->Nb[4 * k + 1] * y + S->Nb[4 * k + 2] * z + S->Nb[4 * k + 3];
+            const double e = Nb[4 * k + 0] * x + Nb[4 * k + 1] * y + Nb[4 * k + 2] * z + Nb[4 * k + 3];
             E[3 * (k % 3) + (k / 3)] = e * inv_norm; // k is the column-major index
         }
     }
+}
+
+// Essential matrices from 5 bearing pairs.  x1s/x2s: shared arrays of 5 unit bearings (3 doubles each).
+// On return S->Es holds nroots row-major E matrices (relpose_5pt.cc:159-395).  Returns nroots (uniform).
+PLB_DEV int solve_5pt_E(const double *x1s, const double *x2s, Scratch5 *S, const MonoTables *T, int lane) {
+    solve_5pt_poly(x1s, x2s, S, T, lane);
+    // ---- real roots by Sturm bracketing (:356): scalar work on lane 0
+    if (lane == 0) S->nroots = sturm_bisect10(S->cpoly, S->roots, &S->sturm);
+    __syncwarp();
+    const int n = S->nroots;
+    // ---- back-substitution, one lane per root (:359-392)
+    if (lane < n) backsub_5pt(S->A, S->Nb, S->roots[lane], S->Es + 9 * lane);
     __syncwarp();
     return n;
 }
