@@ -193,7 +193,7 @@ struct Engine {
     DevBuf<int> s5_nroots;
     DevBuf<float> soa32;
     DevBuf<uint32_t> samples;
-    DevBuf<int> work, slots, subset, act, model_prob;
+    DevBuf<int> work, slots, subset, act, model_prob, prob_count;
     DevBuf<char> mask;
     DevBuf<ProblemDev> probs;
     DevBuf<TransposeDesc> tdesc;
@@ -646,7 +646,8 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         if ((rc = E.h_samples.ensure(total * K)) || (rc = E.samples.ensure(total * K)) || (rc = E.h_n_models.ensure(total)) ||
             (rc = E.h_first_slot.ensure(total)) || (rc = E.h_counts.ensure(cap_models)) || (rc = E.h_scores.ensure(cap_models)) ||
             (rc = E.models.ensure(cap_models * MSZ)) || (rc = E.model_prob.ensure(cap_models)) ||
-            (rc = E.h_act.ensure(2 * (size_t)na + 2)) || (rc = E.act.ensure(2 * (size_t)na + 2)))
+            (rc = E.h_act.ensure(4 * (size_t)na + 2)) || (rc = E.act.ensure(4 * (size_t)na + 2)) ||
+            (rc = E.prob_count.ensure(na)))
             return rc;
         // sample tables on the host (robust/sampling.cc), problems in parallel when the round is large
         {
@@ -667,14 +668,25 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 for (auto &x : th) x.join();
             }
         }
-        for (int a = 0; a < na; ++a) {
-            E.h_act.p[a] = act[a];
-            E.h_act.p[na + a] = (int)PS[act[a]].g0;
+        // h_act layout: active[na] | g_off[na+1] | seg_base[na] | seg_cap[na]
+        int max_seg_cap = 0;
+        {
+            size_t seg = 0;
+            for (int a = 0; a < na; ++a) {
+                const PState &S = PS[act[a]];
+                E.h_act.p[a] = act[a];
+                E.h_act.p[na + a] = (int)S.g0;
+                E.h_act.p[2 * na + 1 + a] = (int)seg;
+                const int cap = (int)(S.B * (size_t)cap_factor);
+                E.h_act.p[3 * na + 1 + a] = cap;
+                max_seg_cap = std::max(max_seg_cap, cap);
+                seg += (size_t)cap;
+            }
+            E.h_act.p[2 * na] = (int)total;
         }
-        E.h_act.p[2 * na] = (int)total;
         PLB_CUDA(cudaMemcpyAsync(E.samples.p, E.h_samples.p, sizeof(uint32_t) * total * K, cudaMemcpyHostToDevice, st));
-        PLB_CUDA(cudaMemcpyAsync(E.act.p, E.h_act.p, sizeof(int) * (2 * na + 1), cudaMemcpyHostToDevice, st));
-        h2d += sizeof(uint32_t) * total * K + sizeof(int) * (2 * na + 1);
+        PLB_CUDA(cudaMemcpyAsync(E.act.p, E.h_act.p, sizeof(int) * (4 * na + 1), cudaMemcpyHostToDevice, st));
+        h2d += sizeof(uint32_t) * total * K + sizeof(int) * (4 * na + 1);
         RoundDesc R;
         R.probs = E.probs.p;
         R.active = E.act.p;
@@ -685,8 +697,10 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         HypOut out;
         out.n_models = E.h_n_models.d;
         out.first_slot = E.h_first_slot.d;
-        out.model_count = E.work.p + 1;
-        out.cap_models = (int)std::min<size_t>(cap_models, (size_t)std::numeric_limits<int>::max());
+        out.seg_base = E.act.p + 2 * na + 1;
+        out.seg_cap = E.act.p + 3 * na + 1;
+        out.prob_count = E.prob_count.p;
+        out.max_seg_cap = max_seg_cap;
         out.overflow = E.work.p + 2;
         out.counts = E.h_counts.d;
         out.scores = E.h_scores.d;
@@ -728,7 +742,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, E.ev0, E.ev1);
         gpu_ms_total += ms;
-        d2h += 2 * sizeof(int) * total + (sizeof(uint32_t) + sizeof(double)) * (size_t)E.h_work.p[1];
+        d2h += 2 * sizeof(int) * total;
 
         // ---- pass 1: which models improve the best-minimal state?  (independent of LO results)
         int n_imp_tot = 0, n_trig_tot = 0;
@@ -762,6 +776,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             }
             S.cnt.samples_evaluated += S.B;
             S.cnt.models_evaluated += nmod;
+            d2h += (sizeof(uint32_t) + sizeof(double)) * nmod;
             S.imp_base = n_imp_tot;
             S.trig_base = n_trig_tot;
             n_imp_tot += (int)S.imp_slot.size();

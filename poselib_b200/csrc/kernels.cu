@@ -285,6 +285,16 @@ PLB_DEV int warp_generate_models(const ProblemDev &P, const uint32_t *sample, Hy
     }
 }
 
+PLB_DEV int sample_problem_slot(const RoundDesc &R, int g) {
+    int lo = 0, hi = R.n_active - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(R.g_off + mid + 1) <= g) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
 // Solve kernel: persistent, one warp = one minimal sample of one problem of the group.  Models are appended to a
 // compact list (slot range reserved with one atomicAdd per sample); n_models[g] / first_slot[g] let the host walk them
 // in (sample, model) order per problem.
@@ -306,14 +316,8 @@ __global__ void __launch_bounds__(HYP_WARPS * 32, 3) k_solve(const RoundDesc R, 
         if (lane == 0) g = atomicAdd(work_counter, 1);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= R.n_total) break;
-        // which problem does sample g belong to?  (upper bound over g_off[1..n_active])
-        int lo = 0, hi = R.n_active - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(R.g_off + mid + 1) <= g) lo = mid + 1;
-            else hi = mid;
-        }
-        const int pidx = __ldg(R.active + lo);
+        const int aslot = sample_problem_slot(R, g);
+        const int pidx = __ldg(R.active + aslot);
         const ProblemDev &P = R.probs[pidx];
         uint32_t sample[K];
 #pragma unroll
@@ -322,11 +326,12 @@ __global__ void __launch_bounds__(HYP_WARPS * 32, 3) k_solve(const RoundDesc R, 
         int base = 0;
         if (lane == 0) {
             if (nm) {
-                base = atomicAdd(out.model_count, nm);
-                if (base + nm > out.cap_models) { // cannot happen with the engine's capacity rule; fail loudly
-                    atomicExch(out.overflow, 1);
+                const int loc = atomicAdd(out.prob_count + aslot, nm);
+                if (loc + nm > __ldg(out.seg_cap + aslot)) { // cannot happen with the worst-case capacity; the engine
+                    atomicExch(out.overflow, 1);             // redoes the round with it when the optimistic one fails
                     nm = 0;
                 }
+                base = __ldg(out.seg_base + aslot) + loc;
             }
             out.n_models[g] = nm;
             out.first_slot[g] = base;
@@ -349,16 +354,6 @@ __global__ void __launch_bounds__(HYP_WARPS * 32, 3) k_solve(const RoundDesc R, 
 //   k5_roots : lane  = sample   Sturm bracketing + Ridders/Newton (scalar, data dependent)
 //   k5_back  : lane  = (sample, root)  back-substitution, motion decomposition, cheirality; 3 samples per warp
 constexpr int S5_BLK = 105;
-
-PLB_DEV int sample_problem_slot(const RoundDesc &R, int g) {
-    int lo = 0, hi = R.n_active - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(R.g_off + mid + 1) <= g) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
-}
 
 struct PrepScratch {
     Scratch5 s5;
@@ -436,13 +431,15 @@ __global__ void __launch_bounds__(128) k5_back(const RoundDesc R, HypOut out) {
     }
     int base = 0, pidx = 0;
     if (live && r == 0) {
-        pidx = __ldg(R.active + sample_problem_slot(R, g));
+        const int aslot = sample_problem_slot(R, g);
+        pidx = __ldg(R.active + aslot);
         if (total) {
-            base = atomicAdd(out.model_count, total);
-            if (base + total > out.cap_models) {
+            const int loc = atomicAdd(out.prob_count + aslot, total);
+            if (loc + total > __ldg(out.seg_cap + aslot)) {
                 atomicExch(out.overflow, 1);
                 total = 0;
             }
+            base = __ldg(out.seg_base + aslot) + loc;
         }
         out.n_models[g] = total;
         out.first_slot[g] = base;
@@ -486,6 +483,137 @@ __global__ void __launch_bounds__(SCORE_THREADS, 4)
         if (threadIdx.x == 0) {
             counts[m] = cnt;
             scores[m] = score;
+        }
+    }
+}
+
+// Tiled score kernel of the round path: CTA (x, a) scores tiles of SCORE_TM models of active problem a.  Every thread
+// loads a correspondence ONCE and evaluates all models of the tile against it (model constants are broadcast reads from
+// shared memory), which divides the L2 -> SM traffic of the one-CTA-per-model kernel by the tile size; the per-model
+// summation order is exactly that of cta_score, so both kernels produce the same bits for the same model.
+constexpr int SCORE_TM = 4;
+template <int KIND>
+__global__ void __launch_bounds__(SCORE_THREADS, 2)
+    k_score_tiled(const RoundDesc R, HypOut out) {
+    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    constexpr int CTX = (KIND == KIND_PNP) ? 12 : (KIND == KIND_RELPOSE) ? 16 : 9;
+    __shared__ double ctx[SCORE_TM][16];
+    __shared__ double red_s[SCORE_WARPS][SCORE_TM];
+    __shared__ uint32_t red_c[SCORE_WARPS][SCORE_TM];
+    const int a = blockIdx.y;
+    const int count = out.prob_count[a];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (blockIdx.x * SCORE_TM >= count) return;
+    const ProblemDev P = R.probs[R.active[a]];
+    const int n = P.n;
+    const double sq_thr = P.sq_thr;
+    const int seg = out.seg_base[a];
+    for (int m0 = blockIdx.x * SCORE_TM; m0 < count; m0 += gridDim.x * SCORE_TM) {
+        const int tm = (count - m0 < SCORE_TM) ? (count - m0) : SCORE_TM;
+        __syncthreads();
+        if (tid < tm) {
+            double mdl[MSZ];
+#pragma unroll
+            for (int k = 0; k < MSZ; ++k) mdl[k] = out.models[(size_t)(seg + m0 + tid) * MSZ + k];
+            ModelCtx<KIND> C;
+            C.init(mdl);
+            const double *cp = reinterpret_cast<const double *>(&C);
+#pragma unroll
+            for (int k = 0; k < CTX; ++k) ctx[tid][k] = cp[k];
+        }
+        __syncthreads();
+        uint32_t cnt[SCORE_TM];
+        double sc[SCORE_TM];
+#pragma unroll
+        for (int i = 0; i < SCORE_TM; ++i) {
+            cnt[i] = 0;
+            sc[i] = 0.0;
+        }
+        if (KIND == KIND_PNP) {
+            const double *__restrict__ xx = P.p[0], *__restrict__ xy = P.p[1];
+            const double *__restrict__ Xx = P.p[2], *__restrict__ Xy = P.p[3], *__restrict__ Xz = P.p[4];
+            for (int k = tid; k < n; k += SCORE_THREADS) {
+                const double X0 = Xx[k], X1 = Xy[k], X2 = Xz[k];
+                const double x0 = xx[k], x1 = xy[k];
+#pragma unroll
+                for (int i = 0; i < SCORE_TM; ++i) {
+                    if (i < tm) {
+                        const double *Pm = ctx[i];
+                        const double z0 = Pm[0] * X0 + Pm[1] * X1 + Pm[2] * X2 + Pm[3];
+                        const double z1 = Pm[4] * X0 + Pm[5] * X1 + Pm[6] * X2 + Pm[7];
+                        const double z2 = Pm[8] * X0 + Pm[9] * X1 + Pm[10] * X2 + Pm[11];
+                        if (z2 > 0.0) {
+                            const double inv_z2 = 1.0 / z2;
+                            const double r_0 = z0 * inv_z2 - x0;
+                            const double r_1 = z1 * inv_z2 - x1;
+                            const double r_sq = r_0 * r_0 + r_1 * r_1;
+                            if (r_sq < sq_thr) {
+                                ++cnt[i];
+                                sc[i] += r_sq;
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            const double *__restrict__ ax = P.p[0], *__restrict__ ay = P.p[1];
+            const double *__restrict__ bx = P.p[2], *__restrict__ by = P.p[3];
+            for (int k = tid; k < n; k += SCORE_THREADS) {
+                const double x1_0 = ax[k], x1_1 = ay[k], x2_0 = bx[k], x2_1 = by[k];
+                double r2v[SCORE_TM];
+                unsigned under = 0; // models whose residual is under the threshold at this correspondence
+#pragma unroll
+                for (int i = 0; i < SCORE_TM; ++i) {
+                    if (i < tm) {
+                        const double *M = ctx[i];
+                        if (KIND == KIND_HOMOG) r2v[i] = homography_r2(M, x1_0, x1_1, x2_0, x2_1);
+                        else r2v[i] = sampson_r2(M, x1_0, x1_1, x2_0, x2_1);
+                        if (r2v[i] < sq_thr) under |= 1u << i;
+                    }
+                }
+                if (KIND == KIND_RELPOSE && under) {
+                    // cheirality only for candidates under the threshold (robust/utils.cc:187-197); the normalised
+                    // bearings depend on the correspondence alone and are computed once
+                    const d3 b1 = bearing(x1_0, x1_1), b2 = bearing(x2_0, x2_1);
+#pragma unroll 1
+                    for (int i = 0; i < SCORE_TM; ++i)
+                        if ((under >> i) & 1u)
+                            if (!cheirality_ok(ctx[i] + 9, ctx[i] + 13, b1, b2, 0.01)) under &= ~(1u << i);
+                }
+#pragma unroll
+                for (int i = 0; i < SCORE_TM; ++i) {
+                    if (i < tm) {
+                        if ((under >> i) & 1u) {
+                            ++cnt[i];
+                            sc[i] += r2v[i];
+                        } else {
+                            sc[i] += sq_thr;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < SCORE_TM; ++i) {
+            const uint32_t c = warp_sum_u(cnt[i]);
+            const double v = warp_sum(sc[i]);
+            if (lane == 0) {
+                red_c[warp][i] = c;
+                red_s[warp][i] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < tm) {
+            uint32_t ct = 0;
+            double st = 0.0;
+#pragma unroll
+            for (int w = 0; w < SCORE_WARPS; ++w) {
+                ct += red_c[w][tid];
+                st += red_s[w][tid];
+            }
+            if (KIND == KIND_PNP) st += (double)(n - (int)ct) * sq_thr; // robust/utils.cc:62
+            out.counts[seg + m0 + tid] = ct;
+            out.scores[seg + m0 + tid] = st;
         }
     }
 }
@@ -557,14 +685,16 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, cudaS
         if (blocks < 1) blocks = 1;
         k_solve<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(R, work, out);
     }
-    int sblocks = score_blocks_per_sm<KIND>() * sm_count();
-    if (sblocks > out.cap_models) sblocks = out.cap_models;
-    if (sblocks < 1) sblocks = 1;
-    k_score<KIND><<<sblocks, SCORE_THREADS, 0, stream>>>(R.probs, out.models, out.model_prob, out.model_count,
-                                                        out.cap_models, out.counts, out.scores);
+    // tiled scoring: grid.y = active problem, grid.x CTAs stride over that problem's tiles of SCORE_TM models
+    int tiles = (out.max_seg_cap + SCORE_TM - 1) / SCORE_TM;
+    int gx = (4 * 8 * sm_count() + R.n_active - 1) / R.n_active; // ~4 waves of 8 CTAs per SM over the whole group
+    if (gx > tiles) gx = tiles;
+    if (gx < 1) gx = 1;
+    k_score_tiled<KIND><<<dim3(gx, R.n_active, 1), SCORE_THREADS, 0, stream>>>(R, out);
 }
 void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, cudaStream_t stream) {
-    cudaMemsetAsync(work, 0, 3 * sizeof(int), stream); // [0] sample queue, [1] model count, [2] overflow flag
+    cudaMemsetAsync(work, 0, 3 * sizeof(int), stream); // [0] sample queue, [2] overflow flag
+    cudaMemsetAsync(out.prob_count, 0, sizeof(int) * R.n_active, stream);
     switch (kind) {
     case KIND_PNP: launch_hyp_t<KIND_PNP>(R, work, out, stream); break;
     case KIND_RELPOSE: launch_hyp_t<KIND_RELPOSE>(R, work, out, stream); break;

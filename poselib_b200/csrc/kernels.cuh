@@ -36,15 +36,18 @@ struct RoundDesc {
     int n_total;
 };
 
-// Per-round output of the hypothesis kernels.  Models are stored compactly: sample g owns slots
-// [first_slot[g], first_slot[g] + n_models[g]) of models / model_prob / counts / scores; *model_count = total.
+// Per-round output of the hypothesis kernels.  Every active problem a owns the slot segment
+// [seg_base[a], seg_base[a] + seg_cap[a]) of models / model_prob / counts / scores and fills it from the front
+// (prob_count[a] models); sample g owns slots [first_slot[g], first_slot[g] + n_models[g]) inside its problem's segment.
 // n_models, first_slot, counts and scores point to mapped pinned host memory (written straight over PCIe).
 struct HypOut {
     int *n_models;
     int *first_slot;
-    int *model_count;
-    int cap_models;   // capacity of models[]; samples that do not fit set *overflow and report 0 models
-    int *overflow;
+    const int *seg_base; // n_active
+    const int *seg_cap;  // n_active
+    int *prob_count;     // n_active, zeroed before the round
+    int max_seg_cap;
+    int *overflow;       // set when a segment is full (the engine then redoes the round with worst-case capacity)
     uint32_t *counts;
     double *scores;
     double *models;
