@@ -84,6 +84,7 @@ typedef struct plb_counters {
     uint64_t h2d_bytes;     /* bytes copied host -> device for this call */
     uint64_t d2h_bytes;     /* bytes copied device -> host for this call */
     uint64_t models_evaluated; /* models scored by the hypothesis kernels incl. speculative samples */
+    uint64_t models_confirmed; /* fast mode: models rescored in fp64 after the fp32 screening pass */
 } plb_counters;
 
 /* misc/camera_models.h:59-157 Camera, restricted to the models the path needs (others -> PLB_ERR_NYI) */

@@ -211,6 +211,9 @@ struct Engine {
     MapBuf<double> h_scores;
     MapBuf<uint32_t> h_counts;
     MapBuf<int> h_n_models, h_first_slot;
+    MapBuf<uint32_t> h_fcounts; // fast mode: fp32 screening records
+    MapBuf<float> h_fscores;
+    std::vector<uint8_t> is_cand;
     MapBuf<LmJobOut> h_lm_out;
     uint64_t launches = 0;
 
@@ -613,6 +616,8 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         if (S.enough) S.sampler = new Sampler(S.t->n, (size_t)K, S.t->opt);
     }
     const size_t CHUNK_MAX = 16384, S_TOT_MAX = 262144;
+    const int mode = g_mode.load(); // 0 exact, 1 fast (fp32 screen + fp64 confirmation of candidates)
+    std::vector<int> cand_slots;
     int cap_factor = (kind == KIND_RELPOSE) ? 8 : MAXM;
     std::vector<int> act;
     for (;;) {
@@ -706,6 +711,14 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         out.scores = E.h_scores.d;
         out.models = E.models.p;
         out.model_prob = E.model_prob.p;
+        out.fcounts = nullptr;
+        out.fscores = nullptr;
+        if (mode == 1) {
+            if ((rc = E.h_fcounts.ensure(cap_models)) || (rc = E.h_fscores.ensure(cap_models))) return rc;
+            out.fcounts = E.h_fcounts.d;
+            out.fscores = E.h_fscores.d;
+            if (E.is_cand.size() < cap_models) E.is_cand.resize(cap_models, 0);
+        }
         out.s5_blk = out.s5_cpoly = out.s5_roots = nullptr;
         out.s5_nroots = nullptr;
         if (kind == KIND_RELPOSE) { // phase buffers of the 3-kernel 5-point solver
@@ -718,7 +731,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             out.s5_nroots = E.s5_nroots.p;
         }
         PLB_CUDA(cudaEventRecord(E.ev0, st));
-        launch_hypotheses(kind, R, E.work.p, out, st);
+        launch_hypotheses(kind, R, E.work.p, out, mode, max_n_pad, st);
         PLB_CUDA(cudaEventRecord(E.ev1, st));
         E.launches += (kind == KIND_RELPOSE) ? 4 : 2; // k_solve (or k5_prep + k5_roots + k5_back) + k_score
         PLB_CUDA(cudaMemcpyAsync(E.h_work.p, E.work.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -744,6 +757,55 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         gpu_ms_total += ms;
         d2h += 2 * sizeof(int) * total;
 
+        // ---- fast mode: pick, from the fp32 records, every model that COULD improve the best-minimal state and
+        //      rescore exactly those in fp64.  With count error <= dc and relative score error <= eps (generous
+        //      bounds for fp32 Sampson / reprojection arithmetic on normalised coordinates), a model that truly improves
+        //      the running (count, score) records always passes the test below, so skipping the others is exact.
+        if (mode == 1) {
+            cand_slots.clear();
+            const double eps = 1e-3;
+            for (int a = 0; a < na; ++a) {
+                PState &S = PS[act[a]];
+                double LB = (double)S.best_minimal_inlier_count; // lower bound of the true running max count
+                double UB = S.best_minimal_msac_score;           // upper bound of the true running min score
+                for (size_t s = 0; s < S.B; ++s) {
+                    const int nm = E.h_n_models.p[S.g0 + s];
+                    const size_t first = (size_t)E.h_first_slot.p[S.g0 + s];
+                    for (int m = 0; m < nm; ++m) {
+                        const size_t slot = first + m;
+                        const double c32 = (double)E.h_fcounts.p[slot], s32 = (double)E.h_fscores.p[slot];
+                        const double dc = 4.0 + 0.01 * c32;
+                        const bool finite = std::isfinite(s32);
+                        const bool cand = !finite || (c32 + dc > LB) || (s32 * (1.0 - eps) < UB);
+                        if (cand) {
+                            cand_slots.push_back((int)slot);
+                            E.is_cand[slot] = 1;
+                        }
+                        if (finite) {
+                            LB = std::max(LB, c32 - dc);
+                            UB = std::min(UB, s32 * (1.0 + eps));
+                        }
+                    }
+                }
+            }
+            const int nc = (int)cand_slots.size();
+            if (nc) {
+                if ((rc = E.h_slots.ensure(nc)) || (rc = E.slots.ensure(nc))) return rc;
+                std::copy(cand_slots.begin(), cand_slots.end(), E.h_slots.p);
+                PLB_CUDA(cudaMemcpyAsync(E.slots.p, E.h_slots.p, sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+                PLB_CUDA(cudaEventRecord(E.ev0, st));
+                launch_score_list(kind, E.probs.p, E.models.p, E.model_prob.p, E.slots.p, nc, E.h_counts.d, E.h_scores.d, st);
+                PLB_CUDA(cudaEventRecord(E.ev1, st));
+                E.launches++;
+                if ((rc = sync_timed(nullptr))) return rc;
+                float ms2 = 0.f;
+                cudaEventElapsedTime(&ms2, E.ev0, E.ev1);
+                gpu_ms_total += ms2;
+                h2d += sizeof(int) * nc;
+                PS[act[0]].cnt.models_confirmed += nc;
+            }
+        }
+
         // ---- pass 1: which models improve the best-minimal state?  (independent of LO results)
         int n_imp_tot = 0, n_trig_tot = 0;
         for (int a = 0; a < na; ++a) {
@@ -761,6 +823,10 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 int last = -1;
                 for (int m = 0; m < nm; ++m) {
                     const size_t slot = first + m;
+                    if (mode == 1) {
+                        if (!E.is_cand[slot]) continue; // cannot improve (screened out with margins)
+                        E.is_cand[slot] = 0;
+                    }
                     const size_t ic = E.h_counts.p[slot];
                     const double sc = E.h_scores.p[slot];
                     const bool more = ic > bc, better = sc < bs;

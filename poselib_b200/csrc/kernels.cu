@@ -14,6 +14,7 @@
 #include "solvers.cuh"
 #include <cooperative_groups.h>
 #include <cstring>
+#include <algorithm>
 
 namespace plb {
 
@@ -618,6 +619,242 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
     }
 }
 
+// ============================================================================================================
+// fp32 screening pass (fast mode)
+// ============================================================================================================
+// Scores EVERY model of the round in fp32 from the fp32 SoA copy of the correspondences (16 B / 2D-2D corr, 20 B /
+// 2D-3D corr).  The CTA stages its problem's arrays into shared memory with TMA bulk copies (cp.async.bulk, one
+// mbarrier) and then walks that problem's model tiles; every thread evaluates SCR_TM models per correspondence read
+// from shared memory.  The records (count32, score32) only decide which models COULD change the RANSAC state; those
+// candidates are rescored in fp64 (k_score_list) before the serial replay, so results are those of the exact mode.
+constexpr int SCR_THREADS = 256;
+constexpr int SCR_WARPS = SCR_THREADS / 32;
+constexpr int SCR_TM = 8;
+
+PLB_DEV uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+PLB_DEV void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PLB_DEV void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PLB_DEV void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+PLB_DEV void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(phase)
+                 : "memory");
+}
+
+PLB_DEV float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOut out, int use_smem) {
+    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    constexpr int CTX = (KIND == KIND_PNP) ? 12 : (KIND == KIND_RELPOSE) ? 16 : 9;
+    constexpr int NARR = (KIND == KIND_PNP) ? 5 : 4;
+    extern __shared__ __align__(128) unsigned char scr_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float ctx[SCR_TM][16];
+    __shared__ float red_s[SCR_WARPS][SCR_TM];
+    __shared__ uint32_t red_c[SCR_WARPS][SCR_TM];
+    const int a = blockIdx.y;
+    const int count = out.prob_count[a];
+    if (blockIdx.x * SCR_TM >= count) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ProblemDev P = R.probs[R.active[a]];
+    const int n = P.n, n_pad = (n + 31) & ~31;
+    const float thr = (float)P.sq_thr;
+    const int seg = out.seg_base[a];
+    const float *arr[NARR];
+    if (use_smem) {
+        float *pts = reinterpret_cast<float *>(scr_smem);
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)n_pad * 4u;
+            mbar_expect_tx(&bar, bytes * NARR);
+#pragma unroll
+            for (int c = 0; c < NARR; ++c) tma_bulk_g2s(pts + (size_t)c * n_pad, P.f[c], bytes, &bar);
+        }
+        mbar_wait(&bar, 0);
+#pragma unroll
+        for (int c = 0; c < NARR; ++c) arr[c] = pts + (size_t)c * n_pad;
+    } else {
+#pragma unroll
+        for (int c = 0; c < NARR; ++c) arr[c] = P.f[c];
+    }
+    for (int m0 = blockIdx.x * SCR_TM; m0 < count; m0 += gridDim.x * SCR_TM) {
+        const int tm = (count - m0 < SCR_TM) ? (count - m0) : SCR_TM;
+        __syncthreads();
+        if (tid < tm) {
+            double mdl[MSZ];
+#pragma unroll
+            for (int k = 0; k < MSZ; ++k) mdl[k] = out.models[(size_t)(seg + m0 + tid) * MSZ + k];
+            ModelCtx<KIND> C;
+            C.init(mdl);
+            const double *cp = reinterpret_cast<const double *>(&C);
+#pragma unroll
+            for (int k = 0; k < CTX; ++k) ctx[tid][k] = (float)cp[k];
+        }
+        __syncthreads();
+        uint32_t cnt[SCR_TM];
+        float sc[SCR_TM];
+#pragma unroll
+        for (int i = 0; i < SCR_TM; ++i) {
+            cnt[i] = 0;
+            sc[i] = 0.f;
+        }
+        for (int k = tid; k < n; k += SCR_THREADS) {
+            if (KIND == KIND_PNP) {
+                const float x0 = arr[0][k], x1 = arr[1][k], X0 = arr[2][k], X1 = arr[3][k], X2 = arr[4][k];
+#pragma unroll
+                for (int i = 0; i < SCR_TM; ++i) {
+                    if (i < tm) {
+                        const float *Pm = ctx[i];
+                        const float z0 = fmaf(Pm[0], X0, fmaf(Pm[1], X1, fmaf(Pm[2], X2, Pm[3])));
+                        const float z1 = fmaf(Pm[4], X0, fmaf(Pm[5], X1, fmaf(Pm[6], X2, Pm[7])));
+                        const float z2 = fmaf(Pm[8], X0, fmaf(Pm[9], X1, fmaf(Pm[10], X2, Pm[11])));
+                        if (z2 > 0.f) {
+                            const float iz = __fdividef(1.f, z2);
+                            const float r0 = fmaf(z0, iz, -x0), r1 = fmaf(z1, iz, -x1);
+                            const float r2 = fmaf(r0, r0, r1 * r1);
+                            if (r2 < thr) {
+                                ++cnt[i];
+                                sc[i] += r2;
+                            }
+                        }
+                    }
+                }
+            } else {
+                const float a0 = arr[0][k], a1 = arr[1][k], b0 = arr[2][k], b1 = arr[3][k];
+                float r2v[SCR_TM];
+                unsigned under = 0;
+#pragma unroll
+                for (int i = 0; i < SCR_TM; ++i) {
+                    if (i < tm) {
+                        const float *M = ctx[i];
+                        if (KIND == KIND_HOMOG) {
+                            const float h0 = fmaf(M[0], a0, fmaf(M[1], a1, M[2]));
+                            const float h1 = fmaf(M[3], a0, fmaf(M[4], a1, M[5]));
+                            const float iw = __fdividef(1.f, fmaf(M[6], a0, fmaf(M[7], a1, M[8])));
+                            const float r0 = fmaf(h0, iw, -b0), r1 = fmaf(h1, iw, -b1);
+                            r2v[i] = fmaf(r0, r0, r1 * r1);
+                        } else {
+                            const float e0 = fmaf(M[0], a0, fmaf(M[1], a1, M[2]));
+                            const float e1 = fmaf(M[3], a0, fmaf(M[4], a1, M[5]));
+                            const float e2 = fmaf(M[6], a0, fmaf(M[7], a1, M[8]));
+                            const float f0 = fmaf(M[0], b0, fmaf(M[3], b1, M[6]));
+                            const float f1 = fmaf(M[1], b0, fmaf(M[4], b1, M[7]));
+                            const float Cn = fmaf(b0, e0, fmaf(b1, e1, e2));
+                            const float den = fmaf(e0, e0, fmaf(e1, e1, fmaf(f0, f0, f1 * f1)));
+                            r2v[i] = __fdividef(Cn * Cn, den);
+                        }
+                        if (r2v[i] < thr) under |= 1u << i;
+                    }
+                }
+                if (KIND == KIND_RELPOSE && under) {
+                    // cheirality in fp32 for the candidates under the threshold (robust/utils.cc:187-197)
+                    const float in1 = rsqrtf(fmaf(a0, a0, fmaf(a1, a1, 1.f))), in2 = rsqrtf(fmaf(b0, b0, fmaf(b1, b1, 1.f)));
+                    const float u0 = a0 * in1, u1 = a1 * in1, u2 = in1, v0 = b0 * in2, v1 = b1 * in2, v2 = in2;
+#pragma unroll 1
+                    for (int i = 0; i < SCR_TM; ++i) {
+                        if (!((under >> i) & 1u)) continue;
+                        const float *q = ctx[i] + 9, *t = ctx[i] + 13;
+                        // rotate u by q (misc/quaternion.h:61-70)
+                        const float px1 = -u0 * q[1] - u1 * q[2] - u2 * q[3];
+                        const float px2 = u0 * q[0] - u1 * q[3] + u2 * q[2];
+                        const float px3 = u1 * q[0] + u0 * q[3] - u2 * q[1];
+                        const float px4 = u1 * q[1] - u0 * q[2] + u2 * q[0];
+                        const float w0 = px2 * q[0] - px1 * q[1] - px3 * q[3] + px4 * q[2];
+                        const float w1 = px3 * q[0] - px1 * q[2] + px2 * q[3] - px4 * q[1];
+                        const float w2 = px3 * q[1] - px2 * q[2] - px1 * q[3] + px4 * q[0];
+                        const float aa = -(w0 * v0 + w1 * v1 + w2 * v2);
+                        const float bb1 = -(w0 * t[0] + w1 * t[1] + w2 * t[2]);
+                        const float bb2 = v0 * t[0] + v1 * t[1] + v2 * t[2];
+                        const float l1 = bb1 - aa * bb2, l2 = -aa * bb1 + bb2;
+                        const float md = 0.01f * (1.f - aa * aa);
+                        if (!(l1 > md && l2 > md)) under &= ~(1u << i);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < SCR_TM; ++i) {
+                    if (i < tm) {
+                        if ((under >> i) & 1u) {
+                            ++cnt[i];
+                            sc[i] += r2v[i];
+                        } else {
+                            sc[i] += thr;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < SCR_TM; ++i) {
+            const uint32_t c = warp_sum_u(cnt[i]);
+            const float v = warp_sum_f(sc[i]);
+            if (lane == 0) {
+                red_c[warp][i] = c;
+                red_s[warp][i] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < tm) {
+            uint32_t ct = 0;
+            float st = 0.f;
+#pragma unroll
+            for (int w = 0; w < SCR_WARPS; ++w) {
+                ct += red_c[w][tid];
+                st += red_s[w][tid];
+            }
+            if (KIND == KIND_PNP) st += (float)(n - (int)ct) * thr;
+            out.fcounts[seg + m0 + tid] = ct;
+            out.fscores[seg + m0 + tid] = st;
+        }
+    }
+}
+
+// Exact fp64 rescoring of a list of model slots (fast mode confirmation): one CTA per listed slot.
+template <int KIND>
+__global__ void __launch_bounds__(SCORE_THREADS, 4)
+    k_score_list(const ProblemDev *__restrict__ probs, const double *__restrict__ models,
+                 const int *__restrict__ model_prob, const int *__restrict__ slots, int n_slots, uint32_t *counts,
+                 double *scores) {
+    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    __shared__ ScoreRed red;
+    for (int j = blockIdx.x; j < n_slots; j += gridDim.x) {
+        const int m = slots[j];
+        const ProblemDev P = probs[model_prob[m]];
+        double mdl[MSZ];
+#pragma unroll
+        for (int k = 0; k < MSZ; ++k) mdl[k] = models[(size_t)m * MSZ + k];
+        uint32_t cnt;
+        double score;
+        cta_score<KIND>(P, mdl, P.sq_thr, &red, cnt, score);
+        if (threadIdx.x == 0) {
+            counts[m] = cnt;
+            scores[m] = score;
+        }
+    }
+}
+
 template <int KIND> static size_t hyp_smem_bytes() { return 256 + sizeof(HypScratch<KIND>) * HYP_WARPS; }
 
 static int g_sm_count = 0;
@@ -666,7 +903,7 @@ static int prep_blocks_per_sm() {
 }
 
 template <int KIND>
-static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, cudaStream_t stream) {
+static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int mode, int max_n_pad, cudaStream_t stream) {
     // persistent grids: a multiple of the SM count (resident CTAs per SM from the occupancy API), never more CTAs
     // than there is work for
     if (KIND == KIND_RELPOSE && out.s5_blk != nullptr) {
@@ -685,21 +922,52 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, cudaS
         if (blocks < 1) blocks = 1;
         k_solve<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(R, work, out);
     }
-    // tiled scoring: grid.y = active problem, grid.x CTAs stride over that problem's tiles of SCORE_TM models
-    int tiles = (out.max_seg_cap + SCORE_TM - 1) / SCORE_TM;
-    int gx = (4 * 8 * sm_count() + R.n_active - 1) / R.n_active; // ~4 waves of 8 CTAs per SM over the whole group
-    if (gx > tiles) gx = tiles;
-    if (gx < 1) gx = 1;
-    k_score_tiled<KIND><<<dim3(gx, R.n_active, 1), SCORE_THREADS, 0, stream>>>(R, out);
+    if (mode == 0) {
+        // tiled exact scoring: grid.y = active problem, grid.x CTAs stride over that problem's tiles of SCORE_TM models
+        int tiles = (out.max_seg_cap + SCORE_TM - 1) / SCORE_TM;
+        int gx = (4 * 8 * sm_count() + R.n_active - 1) / R.n_active; // ~4 waves of 8 CTAs per SM over the whole group
+        if (gx > tiles) gx = tiles;
+        if (gx < 1) gx = 1;
+        k_score_tiled<KIND><<<dim3(gx, R.n_active, 1), SCORE_THREADS, 0, stream>>>(R, out);
+    } else {
+        // fp32 screening: one CTA holds one problem's fp32 arrays in shared memory (TMA) and strides over its tiles
+        constexpr int NARR = (KIND == KIND_PNP) ? 5 : 4;
+        const size_t bytes = (size_t)NARR * (size_t)max_n_pad * 4;
+        const int use_smem = bytes <= 200 * 1024 ? 1 : 0;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_screen<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_done = true;
+        }
+        int tiles = (out.max_seg_cap + SCR_TM - 1) / SCR_TM;
+        const int per_sm = use_smem ? std::max(1, (int)((220 * 1024) / (bytes + 2048))) : 4;
+        int gx = (2 * per_sm * sm_count() + R.n_active - 1) / R.n_active;
+        if (gx > tiles) gx = tiles;
+        if (gx < 1) gx = 1;
+        k_screen<KIND><<<dim3(gx, R.n_active, 1), SCR_THREADS, use_smem ? bytes : 0, stream>>>(R, out, use_smem);
+    }
 }
-void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, cudaStream_t stream) {
+void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, int mode, int max_n_pad,
+                       cudaStream_t stream) {
     cudaMemsetAsync(work, 0, 3 * sizeof(int), stream); // [0] sample queue, [2] overflow flag
     cudaMemsetAsync(out.prob_count, 0, sizeof(int) * R.n_active, stream);
     switch (kind) {
-    case KIND_PNP: launch_hyp_t<KIND_PNP>(R, work, out, stream); break;
-    case KIND_RELPOSE: launch_hyp_t<KIND_RELPOSE>(R, work, out, stream); break;
-    case KIND_FUND: launch_hyp_t<KIND_FUND>(R, work, out, stream); break;
-    default: launch_hyp_t<KIND_HOMOG>(R, work, out, stream); break;
+    case KIND_PNP: launch_hyp_t<KIND_PNP>(R, work, out, mode, max_n_pad, stream); break;
+    case KIND_RELPOSE: launch_hyp_t<KIND_RELPOSE>(R, work, out, mode, max_n_pad, stream); break;
+    case KIND_FUND: launch_hyp_t<KIND_FUND>(R, work, out, mode, max_n_pad, stream); break;
+    default: launch_hyp_t<KIND_HOMOG>(R, work, out, mode, max_n_pad, stream); break;
+    }
+}
+void launch_score_list(int kind, const ProblemDev *probs, const double *models, const int *model_prob, const int *slots,
+                       int n_slots, uint32_t *counts, double *scores, cudaStream_t stream) {
+    if (n_slots <= 0) return;
+    int blocks = n_slots;
+    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    switch (kind) {
+    case KIND_PNP: k_score_list<KIND_PNP><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
+    case KIND_RELPOSE: k_score_list<KIND_RELPOSE><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
+    case KIND_FUND: k_score_list<KIND_FUND><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
+    default: k_score_list<KIND_HOMOG><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
     }
 }
 

@@ -52,6 +52,8 @@ struct HypOut {
     double *scores;
     double *models;
     int *model_prob;  // problem index of every model slot
+    uint32_t *fcounts; // fast mode: fp32 screening records (mapped pinned host memory)
+    float *fscores;
     // relpose_5pt phase buffers (device), sized for the round's n_total samples:
     double *s5_blk;   // per sample 105 doubles: A (39) | Nb (36) | sample bearings x1s,x2s (30)
     double *s5_cpoly; // 11 x n_total, coefficient-major (cpoly[c * n_total + g])
@@ -103,7 +105,12 @@ struct MaskDesc {
 // AoS (caller layout) -> SoA fp64 + fp32 for n_desc problems (descriptors in device memory).
 void launch_transpose(const TransposeDesc *descs_dev, int n_desc, int max_n_pad, cudaStream_t stream);
 // Solve + score kernels of one round (kind = kind of every problem of the group).  work: 3 ints of device scratch.
-void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, cudaStream_t stream);
+// mode 0: exact fp64 scoring of every model; mode 1: fp32 screening of every model (exact rescoring of the candidates
+// is launched separately with launch_score_list once the host has selected them).
+void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, int mode, int max_n_pad,
+                       cudaStream_t stream);
+void launch_score_list(int kind, const ProblemDev *probs, const double *models, const int *model_prob, const int *slots,
+                       int n_slots, uint32_t *counts, double *scores, cudaStream_t stream);
 // Exact fp64 scoring of an explicit list of models (9 doubles stride MSZ) with problem indices; *n_models_dev = count.
 void launch_score_models(int kind, const ProblemDev *probs, const double *models, const int *model_prob, int n_models,
                          const int *n_models_dev, uint32_t *counts, double *scores, cudaStream_t stream);

@@ -293,3 +293,39 @@ def test_lm_refiners_match_oracle(cabi, kind, loss):
         else:
             err = np.abs(gm - om).max()
         assert err < 1e-6 * max(1.0, np.abs(om).max()), (kind, loss, idx, err, gs, os_[:3])
+
+
+# ---------------------------------------------------------------------------------------------- fast mode
+@pytest.mark.parametrize("kind", ["pnp", "relpose", "fundamental", "homography"])
+def test_fast_mode_gives_identical_results(cabi, kind):
+    """fp32 screening + fp64 confirmation of candidates must reproduce the exact mode bit for bit (same trajectory,
+    same models, same masks), and the oracle trajectory."""
+    for seed in range(3):
+        if kind == "pnp":
+            p = G.abspose_problem(800, 0.4, 41, seed)
+            a, b, me = p["x"] / G.FOCAL, p["X"], 12.0 / G.FOCAL
+            kw = dict(max_iterations=3000, min_iterations=500, seed=seed)
+        elif kind == "homography":
+            p = G.homography_problem(4000, 0.5, 44, seed)
+            a, b, me = p["x1"] / G.FOCAL, p["x2"] / G.FOCAL, 1.0 / G.FOCAL
+            kw = dict(max_iterations=5000, min_iterations=500, seed=seed)
+        else:
+            p = G.relpose_problem(6000 if kind == "relpose" else 3000, 0.3, 42, seed)
+            a, b, me = p["x1"] / G.FOCAL, p["x2"] / G.FOCAL, 1.0 / G.FOCAL
+            kw = dict(max_iterations=30000, min_iterations=500, seed=seed)
+        cabi.set_mode("exact")
+        e = cabi.ransac(kind, a, b, cabi.RansacOpt(**kw), me)
+        cabi.set_mode("fast")
+        try:
+            f = cabi.ransac(kind, a, b, cabi.RansacOpt(**kw), me)
+        finally:
+            cabi.set_mode("exact")
+        assert f["stats"] == e["stats"], (f["stats"], e["stats"])
+        assert np.array_equal(f["inliers"], e["inliers"])
+        assert np.array_equal(np.asarray(f["model"]), np.asarray(e["model"]))
+        assert f["counters"]["hypotheses"] == e["counters"]["hypotheses"]
+        assert 0 < f["counters"]["models_confirmed"] < max(64, f["counters"]["models_evaluated"] // 4), f["counters"]
+        o = P.ransac(kind, a, b, P.RansacOpt(**kw), me)
+        # (the F refiner is run here on un-normalised calibrated coordinates, where its SVD parametrisation is
+        #  ill-conditioned: trajectory and masks still agree exactly, the matrix itself to 1e-3)
+        _same_trajectory(f, o, model_tol=1e-3 if kind == "fundamental" else 1e-6, relpose=(kind == "relpose"))
