@@ -80,11 +80,12 @@ typedef struct plb_counters {
     double lo_seconds;      /* host wall time spent waiting on LO kernels */
     uint64_t gpu_launches;  /* kernels launched for this call */
     uint64_t samples_evaluated; /* incl. speculative samples past the serial break point */
-    double gpu_seconds;     /* CUDA-event time of the hypothesis kernels */
+    double gpu_seconds;     /* CUDA-event time of the hypothesis kernels (solve + score) */
     uint64_t h2d_bytes;     /* bytes copied host -> device for this call */
     uint64_t d2h_bytes;     /* bytes copied device -> host for this call */
     uint64_t models_evaluated; /* models scored by the hypothesis kernels incl. speculative samples */
     uint64_t models_confirmed; /* fast mode: models rescored in fp64 after the fp32 screening pass */
+    double gpu_seconds_score;  /* CUDA-event time of the scoring / screening kernels alone (part of gpu_seconds) */
 } plb_counters;
 
 /* misc/camera_models.h:59-157 Camera, restricted to the models the path needs (others -> PLB_ERR_NYI) */

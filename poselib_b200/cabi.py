@@ -65,7 +65,8 @@ class Counters(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("hypotheses", C.c_uint64), ("scored_corrs", C.c_uint64),
                 ("lo_calls", C.c_uint64), ("lo_seconds", C.c_double), ("gpu_launches", C.c_uint64),
                 ("samples_evaluated", C.c_uint64), ("gpu_seconds", C.c_double), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64), ("models_evaluated", C.c_uint64), ("models_confirmed", C.c_uint64)]
+                ("d2h_bytes", C.c_uint64), ("models_evaluated", C.c_uint64), ("models_confirmed", C.c_uint64),
+                ("gpu_seconds_score", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -186,7 +186,7 @@ __global__ void k_gather_models(const double *__restrict__ models, const int *__
 
 struct Engine {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     bool ready = false;
     int device = -1;
     DevBuf<double> in, soa64, px64, models, lm_in, s5_blk, s5_cpoly, s5_roots;
@@ -238,6 +238,7 @@ struct Engine {
         if (!stream) PLB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         if (!ev0) PLB_CUDA(cudaEventCreate(&ev0));
         if (!ev1) PLB_CUDA(cudaEventCreate(&ev1));
+        if (!ev2) PLB_CUDA(cudaEventCreate(&ev2));
         {
             int r = h_work.ensure(8);
             if (r) return r;
@@ -414,7 +415,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
     const uint64_t launches0 = E.launches;
     uint64_t h2d = 0, d2h = 0;
     double lo_wait = 0.0;
-    float gpu_ms_total = 0.f;
+    float gpu_ms_total = 0.f, gpu_ms_score = 0.f;
     auto sync_timed = [&](double *acc) -> int {
         auto t0 = std::chrono::steady_clock::now();
         PLB_CUDA(cudaStreamSynchronize(st));
@@ -731,7 +732,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             out.s5_nroots = E.s5_nroots.p;
         }
         PLB_CUDA(cudaEventRecord(E.ev0, st));
-        launch_hypotheses(kind, R, E.work.p, out, mode, max_n_pad, st);
+        launch_hypotheses(kind, R, E.work.p, out, mode, max_n_pad, st, E.ev2);
         PLB_CUDA(cudaEventRecord(E.ev1, st));
         E.launches += (kind == KIND_RELPOSE) ? 4 : 2; // k_solve (or k5_prep + k5_roots + k5_back) + k_score
         PLB_CUDA(cudaMemcpyAsync(E.h_work.p, E.work.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -752,9 +753,11 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             }
             continue;
         }
-        float ms = 0.f;
+        float ms = 0.f, ms_sc = 0.f;
         cudaEventElapsedTime(&ms, E.ev0, E.ev1);
+        cudaEventElapsedTime(&ms_sc, E.ev2, E.ev1);
         gpu_ms_total += ms;
+        gpu_ms_score += ms_sc;
         d2h += 2 * sizeof(int) * total;
 
         // ---- fast mode: pick, from the fp32 records, every model that COULD improve the best-minimal state and
@@ -801,6 +804,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 float ms2 = 0.f;
                 cudaEventElapsedTime(&ms2, E.ev0, E.ev1);
                 gpu_ms_total += ms2;
+                gpu_ms_score += ms2;
                 h2d += sizeof(int) * nc;
                 PS[act[0]].cnt.models_confirmed += nc;
             }
@@ -1018,6 +1022,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
     PS[0].cnt.lo_seconds = lo_wait;
     PS[0].cnt.gpu_launches = E.launches - launches0;
     PS[0].cnt.gpu_seconds = gpu_ms_total * 1e-3;
+    PS[0].cnt.gpu_seconds_score = gpu_ms_score * 1e-3;
     PS[0].cnt.h2d_bytes = h2d;
     PS[0].cnt.d2h_bytes = d2h;
     finish();

@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
 // mbarrier) and then walks that problem's model tiles; every thread evaluates SCR_TM models per correspondence read
 // from shared memory.  The records (count32, score32) only decide which models COULD change the RANSAC state; those
 // candidates are rescored in fp64 (k_score_list) before the serial replay, so results are those of the exact mode.
-constexpr int SCR_THREADS = 256;
+constexpr int SCR_THREADS = 512;
 constexpr int SCR_WARPS = SCR_THREADS / 32;
 constexpr int SCR_TM = 8;
 
@@ -662,6 +662,29 @@ PLB_DEV float warp_sum_f(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// fp32 cheirality of one correspondence for the screening pass (robust/utils.cc:187-197, misc/essential.cc:40-57);
+// deliberately not inlined: it runs only for the rare candidates under the threshold.
+__device__ __noinline__ bool cheirality32(const float *qt, float a0, float a1, float b0, float b1) {
+    const float in1 = rsqrtf(fmaf(a0, a0, fmaf(a1, a1, 1.f)));
+    const float in2 = rsqrtf(fmaf(b0, b0, fmaf(b1, b1, 1.f)));
+    const float u0 = a0 * in1, u1 = a1 * in1, u2 = in1;
+    const float v0 = b0 * in2, v1 = b1 * in2, v2 = in2;
+    const float *q = qt, *t = qt + 4;
+    const float px1 = -u0 * q[1] - u1 * q[2] - u2 * q[3];
+    const float px2 = u0 * q[0] - u1 * q[3] + u2 * q[2];
+    const float px3 = u1 * q[0] + u0 * q[3] - u2 * q[1];
+    const float px4 = u1 * q[1] - u0 * q[2] + u2 * q[0];
+    const float w0 = px2 * q[0] - px1 * q[1] - px3 * q[3] + px4 * q[2];
+    const float w1 = px3 * q[0] - px1 * q[2] + px2 * q[3] - px4 * q[1];
+    const float w2 = px3 * q[1] - px2 * q[2] - px1 * q[3] + px4 * q[0];
+    const float aa = -(w0 * v0 + w1 * v1 + w2 * v2);
+    const float bb1 = -(w0 * t[0] + w1 * t[1] + w2 * t[2]);
+    const float bb2 = v0 * t[0] + v1 * t[1] + v2 * t[2];
+    const float l1 = bb1 - aa * bb2, l2 = -aa * bb1 + bb2;
+    const float md = 0.01f * (1.f - aa * aa);
+    return (l1 > md) && (l2 > md);
 }
 
 template <int KIND>
@@ -721,8 +744,8 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
             cnt[i] = 0;
             sc[i] = 0.f;
         }
-        for (int k = tid; k < n; k += SCR_THREADS) {
-            if (KIND == KIND_PNP) {
+        for (int k = tid; KIND == KIND_PNP && k < n; k += SCR_THREADS) {
+            {
                 const float x0 = arr[0][k], x1 = arr[1][k], X0 = arr[2][k], X1 = arr[3][k], X2 = arr[4][k];
 #pragma unroll
                 for (int i = 0; i < SCR_TM; ++i) {
@@ -742,65 +765,59 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
                         }
                     }
                 }
-            } else {
-                const float a0 = arr[0][k], a1 = arr[1][k], b0 = arr[2][k], b1 = arr[3][k];
-                float r2v[SCR_TM];
-                unsigned under = 0;
+            }
+        }
+        if (KIND != KIND_PNP) {
+            // 2D-2D kinds: SCR_PB correspondences per thread per step, so that the 9 model constants fetched from
+            // shared memory (broadcast) are reused SCR_PB times
+            constexpr int SCR_PB = 4;
+            for (int k0 = tid; k0 < n; k0 += SCR_THREADS * SCR_PB) {
+                float a0[SCR_PB], a1[SCR_PB], b0[SCR_PB], b1[SCR_PB];
+                bool live[SCR_PB];
+#pragma unroll
+                for (int j = 0; j < SCR_PB; ++j) {
+                    const int k = k0 + j * SCR_THREADS;
+                    live[j] = k < n;
+                    const int kk = live[j] ? k : k0;
+                    a0[j] = arr[0][kk]; a1[j] = arr[1][kk]; b0[j] = arr[2][kk]; b1[j] = arr[3][kk];
+                }
 #pragma unroll
                 for (int i = 0; i < SCR_TM; ++i) {
                     if (i < tm) {
                         const float *M = ctx[i];
-                        if (KIND == KIND_HOMOG) {
-                            const float h0 = fmaf(M[0], a0, fmaf(M[1], a1, M[2]));
-                            const float h1 = fmaf(M[3], a0, fmaf(M[4], a1, M[5]));
-                            const float iw = __fdividef(1.f, fmaf(M[6], a0, fmaf(M[7], a1, M[8])));
-                            const float r0 = fmaf(h0, iw, -b0), r1 = fmaf(h1, iw, -b1);
-                            r2v[i] = fmaf(r0, r0, r1 * r1);
-                        } else {
-                            const float e0 = fmaf(M[0], a0, fmaf(M[1], a1, M[2]));
-                            const float e1 = fmaf(M[3], a0, fmaf(M[4], a1, M[5]));
-                            const float e2 = fmaf(M[6], a0, fmaf(M[7], a1, M[8]));
-                            const float f0 = fmaf(M[0], b0, fmaf(M[3], b1, M[6]));
-                            const float f1 = fmaf(M[1], b0, fmaf(M[4], b1, M[7]));
-                            const float Cn = fmaf(b0, e0, fmaf(b1, e1, e2));
-                            const float den = fmaf(e0, e0, fmaf(e1, e1, fmaf(f0, f0, f1 * f1)));
-                            r2v[i] = __fdividef(Cn * Cn, den);
-                        }
-                        if (r2v[i] < thr) under |= 1u << i;
-                    }
-                }
-                if (KIND == KIND_RELPOSE && under) {
-                    // cheirality in fp32 for the candidates under the threshold (robust/utils.cc:187-197)
-                    const float in1 = rsqrtf(fmaf(a0, a0, fmaf(a1, a1, 1.f))), in2 = rsqrtf(fmaf(b0, b0, fmaf(b1, b1, 1.f)));
-                    const float u0 = a0 * in1, u1 = a1 * in1, u2 = in1, v0 = b0 * in2, v1 = b1 * in2, v2 = in2;
-#pragma unroll 1
-                    for (int i = 0; i < SCR_TM; ++i) {
-                        if (!((under >> i) & 1u)) continue;
-                        const float *q = ctx[i] + 9, *t = ctx[i] + 13;
-                        // rotate u by q (misc/quaternion.h:61-70)
-                        const float px1 = -u0 * q[1] - u1 * q[2] - u2 * q[3];
-                        const float px2 = u0 * q[0] - u1 * q[3] + u2 * q[2];
-                        const float px3 = u1 * q[0] + u0 * q[3] - u2 * q[1];
-                        const float px4 = u1 * q[1] - u0 * q[2] + u2 * q[0];
-                        const float w0 = px2 * q[0] - px1 * q[1] - px3 * q[3] + px4 * q[2];
-                        const float w1 = px3 * q[0] - px1 * q[2] + px2 * q[3] - px4 * q[1];
-                        const float w2 = px3 * q[1] - px2 * q[2] - px1 * q[3] + px4 * q[0];
-                        const float aa = -(w0 * v0 + w1 * v1 + w2 * v2);
-                        const float bb1 = -(w0 * t[0] + w1 * t[1] + w2 * t[2]);
-                        const float bb2 = v0 * t[0] + v1 * t[1] + v2 * t[2];
-                        const float l1 = bb1 - aa * bb2, l2 = -aa * bb1 + bb2;
-                        const float md = 0.01f * (1.f - aa * aa);
-                        if (!(l1 > md && l2 > md)) under &= ~(1u << i);
-                    }
-                }
+                        const float m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5], m6 = M[6], m7 = M[7],
+                                    m8 = M[8];
 #pragma unroll
-                for (int i = 0; i < SCR_TM; ++i) {
-                    if (i < tm) {
-                        if ((under >> i) & 1u) {
-                            ++cnt[i];
-                            sc[i] += r2v[i];
-                        } else {
-                            sc[i] += thr;
+                        for (int j = 0; j < SCR_PB; ++j) {
+                            float r2;
+                            if (KIND == KIND_HOMOG) {
+                                const float h0 = fmaf(m0, a0[j], fmaf(m1, a1[j], m2));
+                                const float h1 = fmaf(m3, a0[j], fmaf(m4, a1[j], m5));
+                                const float iw = __fdividef(1.f, fmaf(m6, a0[j], fmaf(m7, a1[j], m8)));
+                                const float r0 = fmaf(h0, iw, -b0[j]), r1 = fmaf(h1, iw, -b1[j]);
+                                r2 = fmaf(r0, r0, r1 * r1);
+                            } else {
+                                const float e0 = fmaf(m0, a0[j], fmaf(m1, a1[j], m2));
+                                const float e1 = fmaf(m3, a0[j], fmaf(m4, a1[j], m5));
+                                const float e2 = fmaf(m6, a0[j], fmaf(m7, a1[j], m8));
+                                const float f0 = fmaf(m0, b0[j], fmaf(m3, b1[j], m6));
+                                const float f1 = fmaf(m1, b0[j], fmaf(m4, b1[j], m7));
+                                const float Cn = fmaf(b0[j], e0, fmaf(b1[j], e1, e2));
+                                const float den = fmaf(e0, e0, fmaf(e1, e1, fmaf(f0, f0, f1 * f1)));
+                                r2 = __fdividef(Cn * Cn, den);
+                            }
+                            bool inl = live[j] && (r2 < thr);
+                            if (KIND == KIND_RELPOSE && inl) {
+                                inl = cheirality32(M + 9, a0[j], a1[j], b0[j], b1[j]);
+                            }
+                            if (live[j]) {
+                                if (inl) {
+                                    ++cnt[i];
+                                    sc[i] += r2;
+                                } else {
+                                    sc[i] += thr;
+                                }
+                            }
                         }
                     }
                 }
@@ -903,7 +920,8 @@ static int prep_blocks_per_sm() {
 }
 
 template <int KIND>
-static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int mode, int max_n_pad, cudaStream_t stream) {
+static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int mode, int max_n_pad, cudaStream_t stream,
+                         cudaEvent_t ev_between) {
     // persistent grids: a multiple of the SM count (resident CTAs per SM from the occupancy API), never more CTAs
     // than there is work for
     if (KIND == KIND_RELPOSE && out.s5_blk != nullptr) {
@@ -922,6 +940,7 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
         if (blocks < 1) blocks = 1;
         k_solve<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(R, work, out);
     }
+    if (ev_between) cudaEventRecord(ev_between, stream); // solve | score boundary for the per-kernel timing
     if (mode == 0) {
         // tiled exact scoring: grid.y = active problem, grid.x CTAs stride over that problem's tiles of SCORE_TM models
         int tiles = (out.max_seg_cap + SCORE_TM - 1) / SCORE_TM;
@@ -948,14 +967,14 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
     }
 }
 void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, int mode, int max_n_pad,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, cudaEvent_t ev_between) {
     cudaMemsetAsync(work, 0, 3 * sizeof(int), stream); // [0] sample queue, [2] overflow flag
     cudaMemsetAsync(out.prob_count, 0, sizeof(int) * R.n_active, stream);
     switch (kind) {
-    case KIND_PNP: launch_hyp_t<KIND_PNP>(R, work, out, mode, max_n_pad, stream); break;
-    case KIND_RELPOSE: launch_hyp_t<KIND_RELPOSE>(R, work, out, mode, max_n_pad, stream); break;
-    case KIND_FUND: launch_hyp_t<KIND_FUND>(R, work, out, mode, max_n_pad, stream); break;
-    default: launch_hyp_t<KIND_HOMOG>(R, work, out, mode, max_n_pad, stream); break;
+    case KIND_PNP: launch_hyp_t<KIND_PNP>(R, work, out, mode, max_n_pad, stream, ev_between); break;
+    case KIND_RELPOSE: launch_hyp_t<KIND_RELPOSE>(R, work, out, mode, max_n_pad, stream, ev_between); break;
+    case KIND_FUND: launch_hyp_t<KIND_FUND>(R, work, out, mode, max_n_pad, stream, ev_between); break;
+    default: launch_hyp_t<KIND_HOMOG>(R, work, out, mode, max_n_pad, stream, ev_between); break;
     }
 }
 void launch_score_list(int kind, const ProblemDev *probs, const double *models, const int *model_prob, const int *slots,

@@ -108,7 +108,7 @@ void launch_transpose(const TransposeDesc *descs_dev, int n_desc, int max_n_pad,
 // mode 0: exact fp64 scoring of every model; mode 1: fp32 screening of every model (exact rescoring of the candidates
 // is launched separately with launch_score_list once the host has selected them).
 void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, int mode, int max_n_pad,
-                       cudaStream_t stream);
+                       cudaStream_t stream, cudaEvent_t ev_between = nullptr);
 void launch_score_list(int kind, const ProblemDev *probs, const double *models, const int *model_prob, const int *slots,
                        int n_slots, uint32_t *counts, double *scores, cudaStream_t stream);
 // Exact fp64 scoring of an explicit list of models (9 doubles stride MSZ) with problem indices; *n_models_dev = count.
