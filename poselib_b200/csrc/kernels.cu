@@ -768,59 +768,64 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
             }
         }
         if (KIND != KIND_PNP) {
-            // 2D-2D kinds: SCR_PB correspondences per thread per step, so that the 9 model constants fetched from
-            // shared memory (broadcast) are reused SCR_PB times
+            // 2D-2D kinds.  sc[i] accumulates sum over inliers of (r2 - thr); n*thr is added at the end, so the common
+            // (outlier) path is: two 2x3 products, the residual numerator/denominator, one multiply, one compare — the
+            // division only happens for correspondences under the threshold.  SCR_PB correspondences per thread per
+            // step reuse the 9 model constants fetched (broadcast) from shared memory.
             constexpr int SCR_PB = 4;
-            for (int k0 = tid; k0 < n; k0 += SCR_THREADS * SCR_PB) {
+            auto eval = [&](const float *M, float a0, float a1, float b0, float b1, uint32_t &c, float &sacc) {
+                const float m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5], m6 = M[6], m7 = M[7], m8 = M[8];
+                if (KIND == KIND_HOMOG) {
+                    const float h0 = fmaf(m0, a0, fmaf(m1, a1, m2));
+                    const float h1 = fmaf(m3, a0, fmaf(m4, a1, m5));
+                    const float w = fmaf(m6, a0, fmaf(m7, a1, m8));
+                    // |h/w - b|^2 < thr  <=>  |h - w b|^2 < thr w^2
+                    const float d0 = fmaf(-w, b0, h0), d1 = fmaf(-w, b1, h1);
+                    const float num = fmaf(d0, d0, d1 * d1), den = w * w;
+                    if (num < thr * den) {
+                        ++c;
+                        sacc += __fdividef(num, den) - thr;
+                    }
+                } else {
+                    const float e0 = fmaf(m0, a0, fmaf(m1, a1, m2));
+                    const float e1 = fmaf(m3, a0, fmaf(m4, a1, m5));
+                    const float e2 = fmaf(m6, a0, fmaf(m7, a1, m8));
+                    const float f0 = fmaf(m0, b0, fmaf(m3, b1, m6));
+                    const float f1 = fmaf(m1, b0, fmaf(m4, b1, m7));
+                    const float Cn = fmaf(b0, e0, fmaf(b1, e1, e2));
+                    const float den = fmaf(e0, e0, fmaf(e1, e1, fmaf(f0, f0, f1 * f1)));
+                    const float num = Cn * Cn;
+                    if (num < thr * den) {
+                        bool inl = true;
+                        if (KIND == KIND_RELPOSE) inl = cheirality32(M + 9, a0, a1, b0, b1);
+                        if (inl) {
+                            ++c;
+                            sacc += __fdividef(num, den) - thr;
+                        }
+                    }
+                }
+            };
+            int k0 = tid;
+            for (; k0 + (SCR_PB - 1) * SCR_THREADS < n; k0 += SCR_THREADS * SCR_PB) {
                 float a0[SCR_PB], a1[SCR_PB], b0[SCR_PB], b1[SCR_PB];
-                bool live[SCR_PB];
 #pragma unroll
                 for (int j = 0; j < SCR_PB; ++j) {
                     const int k = k0 + j * SCR_THREADS;
-                    live[j] = k < n;
-                    const int kk = live[j] ? k : k0;
-                    a0[j] = arr[0][kk]; a1[j] = arr[1][kk]; b0[j] = arr[2][kk]; b1[j] = arr[3][kk];
+                    a0[j] = arr[0][k]; a1[j] = arr[1][k]; b0[j] = arr[2][k]; b1[j] = arr[3][k];
                 }
 #pragma unroll
                 for (int i = 0; i < SCR_TM; ++i) {
                     if (i < tm) {
-                        const float *M = ctx[i];
-                        const float m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5], m6 = M[6], m7 = M[7],
-                                    m8 = M[8];
 #pragma unroll
-                        for (int j = 0; j < SCR_PB; ++j) {
-                            float r2;
-                            if (KIND == KIND_HOMOG) {
-                                const float h0 = fmaf(m0, a0[j], fmaf(m1, a1[j], m2));
-                                const float h1 = fmaf(m3, a0[j], fmaf(m4, a1[j], m5));
-                                const float iw = __fdividef(1.f, fmaf(m6, a0[j], fmaf(m7, a1[j], m8)));
-                                const float r0 = fmaf(h0, iw, -b0[j]), r1 = fmaf(h1, iw, -b1[j]);
-                                r2 = fmaf(r0, r0, r1 * r1);
-                            } else {
-                                const float e0 = fmaf(m0, a0[j], fmaf(m1, a1[j], m2));
-                                const float e1 = fmaf(m3, a0[j], fmaf(m4, a1[j], m5));
-                                const float e2 = fmaf(m6, a0[j], fmaf(m7, a1[j], m8));
-                                const float f0 = fmaf(m0, b0[j], fmaf(m3, b1[j], m6));
-                                const float f1 = fmaf(m1, b0[j], fmaf(m4, b1[j], m7));
-                                const float Cn = fmaf(b0[j], e0, fmaf(b1[j], e1, e2));
-                                const float den = fmaf(e0, e0, fmaf(e1, e1, fmaf(f0, f0, f1 * f1)));
-                                r2 = __fdividef(Cn * Cn, den);
-                            }
-                            bool inl = live[j] && (r2 < thr);
-                            if (KIND == KIND_RELPOSE && inl) {
-                                inl = cheirality32(M + 9, a0[j], a1[j], b0[j], b1[j]);
-                            }
-                            if (live[j]) {
-                                if (inl) {
-                                    ++cnt[i];
-                                    sc[i] += r2;
-                                } else {
-                                    sc[i] += thr;
-                                }
-                            }
-                        }
+                        for (int j = 0; j < SCR_PB; ++j) eval(ctx[i], a0[j], a1[j], b0[j], b1[j], cnt[i], sc[i]);
                     }
                 }
+            }
+            for (; k0 < n; k0 += SCR_THREADS) { // remainder
+                const float a0 = arr[0][k0], a1 = arr[1][k0], b0 = arr[2][k0], b1 = arr[3][k0];
+#pragma unroll
+                for (int i = 0; i < SCR_TM; ++i)
+                    if (i < tm) eval(ctx[i], a0, a1, b0, b1, cnt[i], sc[i]);
             }
         }
 #pragma unroll
@@ -842,6 +847,7 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
                 st += red_s[w][tid];
             }
             if (KIND == KIND_PNP) st += (float)(n - (int)ct) * thr;
+            else st += (float)n * thr; // the per-correspondence sums hold (r2 - thr) of the inliers only
             out.fcounts[seg + m0 + tid] = ct;
             out.fscores[seg + m0 + tid] = st;
         }
