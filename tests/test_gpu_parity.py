@@ -329,3 +329,57 @@ def test_fast_mode_gives_identical_results(cabi, kind):
         # (the F refiner is run here on un-normalised calibrated coordinates, where its SVD parametrisation is
         #  ill-conditioned: trajectory and masks still agree exactly, the matrix itself to 1e-3)
         _same_trajectory(f, o, model_tol=1e-3 if kind == "fundamental" else 1e-6, relpose=(kind == "relpose"))
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE configs, full size
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_baseline_configs_at_full_size(cabi, mode):
+    """BASELINE.json configs 1-4 at their full sizes through the estimate_* entry points (pixel coordinates + PINHOLE
+    cameras), both precision modes, against the oracle: same trajectory, bit-exact masks, models to 1e-6."""
+    cam = cabi.Camera("PINHOLE", (G.FOCAL, G.FOCAL, 0.0, 0.0))
+    camt = (G.FOCAL, G.FOCAL, 0.0, 0.0)
+    cabi.set_mode(mode)
+    try:
+        p = G.config_c1(0)
+        g = cabi.estimate("pnp", p["x"], p["X"], cabi.RansacOpt(**p["ransac"]), cabi.BundleOpt(), p["max_error"], cam)
+        o = P.estimate("pnp", p["x"], p["X"], P.RansacOpt(**p["ransac"]), P.BundleOpt(), p["max_error"], camt)
+        _same_trajectory(g, o)
+        p = G.config_c2(0)
+        g = cabi.estimate("relpose", p["x1"], p["x2"], cabi.RansacOpt(**p["ransac"]), cabi.BundleOpt(), p["max_error"], cam, cam)
+        o = P.estimate("relpose", p["x1"], p["x2"], P.RansacOpt(**p["ransac"]), P.BundleOpt(), p["max_error"], camt, camt)
+        _same_trajectory(g, o, relpose=True)
+        p = G.config_c3(0)
+        g = cabi.estimate("fundamental", p["x1"], p["x2"], cabi.RansacOpt(**p["ransac"]), cabi.BundleOpt(), p["max_error"], rfc=True)
+        o = P.estimate("fundamental", p["x1"], p["x2"], P.RansacOpt(**p["ransac"]), P.BundleOpt(), p["max_error"], rfc=True)
+        _same_trajectory(g, o)
+        p = G.config_c4(0)
+        g = cabi.estimate("homography", p["x1"], p["x2"], cabi.RansacOpt(**p["ransac"]), cabi.BundleOpt(), p["max_error"])
+        o = P.estimate("homography", p["x1"], p["x2"], P.RansacOpt(**p["ransac"]), P.BundleOpt(), p["max_error"])
+        _same_trajectory(g, o)
+    finally:
+        cabi.set_mode("exact")
+
+
+def test_mixed_batch_config5_style_fast_mode(cabi):
+    """BASELINE config 5 in miniature: alternating p3p / 5pt problems with their own seeds through plb_ransac_batch
+    (lock-step groups per kind), fast mode, several groups in flight."""
+    probs, refs = [], []
+    for i in range(16):
+        if i % 2 == 0:
+            p = G.abspose_problem(200, 0.5, 5, 100 + i)
+            a, b, kind, me = p["x"] / G.FOCAL, p["X"], "pnp", 12.0 / G.FOCAL
+            kw = dict(max_iterations=1000, min_iterations=1000, seed=i)
+        else:
+            p = G.relpose_problem(4000, 0.3, 5, 100 + i)
+            a, b, kind, me = p["x1"] / G.FOCAL, p["x2"] / G.FOCAL, "relpose", 1.0 / G.FOCAL
+            kw = dict(max_iterations=100000, min_iterations=1000, seed=i)
+        probs.append(dict(kind=kind, a=a, b=b, ransac=cabi.RansacOpt(**kw), max_error=me))
+        refs.append(P.ransac(kind, a, b, P.RansacOpt(**kw), me))
+    cabi.set_mode("fast")
+    try:
+        res = cabi.ransac_batch(probs, streams=3)
+    finally:
+        cabi.set_mode("exact")
+    for g, o, pr in zip(res, refs, probs):
+        assert g["status"] == 0
+        _same_trajectory(g, o, relpose=(pr["kind"] == "relpose"))
