@@ -128,7 +128,7 @@ template <typename T> struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        const size_t want = std::max<size_t>(n, 64);
+        const size_t want = std::max<size_t>(n + n / 4, 64); // slack: fewer device-synchronising reallocations
         PLB_CUDA(cudaMalloc(&p, want * sizeof(T)));
         cap = want;
         return PLB_OK;
@@ -145,7 +145,7 @@ template <typename T> struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
-        const size_t want = std::max<size_t>(n, 64);
+        const size_t want = std::max<size_t>(n + n / 4, 64);
         PLB_CUDA(cudaMallocHost(&p, want * sizeof(T)));
         cap = want;
         return PLB_OK;
@@ -165,7 +165,7 @@ template <typename T> struct MapBuf {
         if (p) cudaFreeHost(p);
         p = d = nullptr;
         cap = 0;
-        const size_t want = std::max<size_t>(n, 64);
+        const size_t want = std::max<size_t>(n + n / 4, 64);
         PLB_CUDA(cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocMapped | cudaHostAllocPortable));
         PLB_CUDA(cudaHostGetDevicePointer((void **)&d, p, 0));
         cap = want;
@@ -1594,16 +1594,16 @@ int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
         }
     const int nthreads = std::max(1, std::min<int>(nthreads_req, (int)groups.size()));
     const int dev = g_device;
-    std::atomic<size_t> next(0);
     std::atomic<int> first_err(PLB_OK);
     std::string err_msg;
     std::mutex mtx;
     auto work = [&](int tid) {
         g_device = dev;
         g_engine = pool_engine((size_t)dev * 1024 + tid);
-        for (;;) {
-            const size_t gi = next.fetch_add(1);
-            if (gi >= groups.size()) break;
+        // static group -> engine mapping: an engine sees the same group shapes on every call of a repeated workload,
+        // so its grow-only buffers stop reallocating (cudaMalloc / cudaFree synchronise the whole device) after the
+        // first call
+        for (size_t gi = (size_t)tid; gi < groups.size(); gi += (size_t)nthreads) {
             const int rc = run_group(groups[gi][0]->kind, groups[gi]);
             if (rc != PLB_OK) {
                 int exp = PLB_OK;
