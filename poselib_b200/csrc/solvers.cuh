@@ -475,31 +475,42 @@ PLB_DEV int sturm_signchanges(const double *svec, double x) {
     }
     return count;
 }
+// One step of the Sturm-sequence construction (sturm.h:56-79) with compile-time indices; the three work buffers rotate
+// roles (f1,f2,f3) -> (f2,f3,f1) from step to step exactly like the reference's pointer juggling, so after inlining
+// every array element lives in a register.
+template <int I> PLB_DEV void sturm_step(double (&f1)[11], double (&f2)[11], double (&f3)[11], double *svec) {
+    constexpr int N = 10;
+    const double q1 = f1[N - I] * f2[N - 1 - I];
+    const double q0 = f1[N - 1 - I] * f2[N - 1 - I] - f1[N - I] * f2[N - 2 - I];
+    f3[0] = f1[0] - q0 * f2[0];
+#pragma unroll
+    for (int j = 1; j < N - 1 - I; ++j) f3[j] = f1[j] - q1 * f2[j - 1] - q0 * f2[j];
+    const double c = -fabs(f3[N - 2 - I]);
+    const double ci = 1.0 / c;
+#pragma unroll
+    for (int j = 0; j < N - 1 - I; ++j) f3[j] = f3[j] * ci;
+    svec[3 * I] = q0;
+    svec[3 * I + 1] = q1;
+    svec[3 * I + 2] = c;
+    if constexpr (I + 1 < N - 1) {
+        sturm_step<I + 1>(f2, f3, f1, svec);
+    } else {
+        svec[3 * N - 3] = f2[0];
+        svec[3 * N - 2] = f2[1];
+        svec[3 * N - 1] = f3[0];
+    }
+}
 PLB_DEV void sturm_build_seq(const double *fvec, double *svec) {
     constexpr int N = 10;
-    double f[3 * N];
-    for (int i = 0; i < 2 * N + 1; ++i) f[i] = fvec[i];
-    int o1 = 0, o2 = N + 1, o3 = 2 * N + 1; // offsets of f1,f2,f3 inside f
-    for (int i = 0; i < N - 1; ++i) {
-        double *f1 = f + o1, *f2 = f + o2, *f3 = f + o3;
-        const double q1 = f1[N - i] * f2[N - 1 - i];
-        const double q0 = f1[N - 1 - i] * f2[N - 1 - i] - f1[N - i] * f2[N - 2 - i];
-        f3[0] = f1[0] - q0 * f2[0];
-        for (int j = 1; j < N - 1 - i; ++j) f3[j] = f1[j] - q1 * f2[j - 1] - q0 * f2[j];
-        const double c = -fabs(f3[N - 2 - i]);
-        const double ci = 1.0 / c;
-        for (int j = 0; j < N - 1 - i; ++j) f3[j] = f3[j] * ci;
-        const int t = o1;
-        o1 = o2;
-        o2 = o3;
-        o3 = t;
-        svec[3 * i] = q0;
-        svec[3 * i + 1] = q1;
-        svec[3 * i + 2] = c;
-    }
-    svec[3 * N - 3] = f[o1 + 0];
-    svec[3 * N - 2] = f[o1 + 1];
-    svec[3 * N - 1] = f[o2 + 0];
+    double f1[11], f2[11], f3[11];
+#pragma unroll
+    for (int i = 0; i < N + 1; ++i) f1[i] = fvec[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) f2[i] = fvec[N + 1 + i];
+    f2[N] = 0.0;
+#pragma unroll
+    for (int i = 0; i < N + 1; ++i) f3[i] = 0.0;
+    sturm_step<0>(f1, f2, f3, svec);
 }
 PLB_DEV void sturm_ridders_newton(const double *fvec, double a, double b, double *roots, int &n_roots, double tol) {
     double fa = sturm_polyval10(fvec, a);
@@ -539,12 +550,15 @@ PLB_DEV int sturm_bisect10(const double *coeffs, double *roots, SturmWork *w) {
     if (coeffs[N] == 0.0) return 0;
     double *fvec = w->fvec, *svec = w->svec;
     const double c_inv = 1.0 / coeffs[N];
+#pragma unroll
     for (int i = 0; i < N; ++i) fvec[i] = coeffs[i] * c_inv;
     fvec[N] = 1.0;
+#pragma unroll
     for (int i = 0; i < N - 1; ++i) fvec[N + 1 + i] = fvec[i + 1] * ((i + 1) / double(N));
     fvec[2 * N] = 1.0;
     sturm_build_seq(fvec, svec);
     double mx = 0;
+#pragma unroll
     for (int i = 0; i < N; ++i) mx = fmax(mx, fabs(fvec[i]));
     const double r0 = 1.0 + mx;
     const int s_lo = sturm_signchanges(svec, -r0), s_hi = sturm_signchanges(svec, r0);
