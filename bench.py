@@ -183,13 +183,19 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(probs, steps):
+    from poselib_b200 import sharding
+    my_idx = list(range(rank * pairs, (rank + 1) * pairs))
+
+    def timed(probs, steps, gather=False):
         t_tot, agg, last = 0.0, None, None
         for _ in range(steps):
             flush.zero_()  # L2 flush between timed iterations (untimed)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             last = cabi.ransac_batch(probs, streams=args.streams)  # returns after its own stream syncs
+            if gather and dist is not None:
+                # the only inter-GPU traffic of the path: fixed-size result records gathered over NCCL
+                sharding.gather_records(sharding.pack_results(list(zip(my_idx, last))), dist)
             torch.cuda.synchronize()
             t_tot += time.perf_counter() - t0
             c = {k: sum(r["counters"][k] for r in last) for k in last[0]["counters"]}
@@ -204,7 +210,7 @@ def main():
     barrier()
     t_res, c_res, _ = timed(res_probs, args.steps)
     barrier()
-    t_e2e, c_e2e, last = timed(host_probs, args.steps)
+    t_e2e, c_e2e, last = timed(host_probs, args.steps, gather=True)
     barrier()
     # roofline pass: the same workload with ONE lock-step group in flight, so that the CUDA-event duration of the scoring
     # kernel is not inflated by kernels of other groups sharing the GPU (still live, still on the engine's stream)
@@ -261,6 +267,7 @@ def main():
                        "l2": "flushed (256 MiB write) between timed steps", "timing": "host clock around synchronous "
                        "C-ABI calls, cuda synchronize both sides, max over ranks; kernel time by CUDA events"},
             "e2e": {"value": hyp_e / T_e2e, "unit": "hypotheses/s", "scored_corrs_per_s": cor_e / T_e2e,
+                    "includes": "host buffers in, results out" + ("; NCCL all_gather of the result records" if world > 1 else ""),
                     "ms_per_step": 1e3 * T_e2e / args.steps,
                     "h2d_bytes_per_step": c_e2e["h2d_bytes"] // args.steps, "d2h_bytes_per_step": c_e2e["d2h_bytes"] // args.steps},
             "gpu_launches": int(launches),

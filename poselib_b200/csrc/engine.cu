@@ -616,7 +616,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         S.active = S.enough && S.t->opt.max_iterations > 0;
         if (S.enough) S.sampler = new Sampler(S.t->n, (size_t)K, S.t->opt);
     }
-    const size_t CHUNK_MAX = 16384, S_TOT_MAX = 262144;
+    const size_t CHUNK_MAX = 16384, ROUND_MAX = 32768, S_TOT_MAX = 262144;
     const int mode = g_mode.load(); // 0 exact, 1 fast (fp32 screen + fp64 confirmation of candidates)
     std::vector<int> cand_slots;
     int cap_factor = (kind == KIND_RELPOSE) ? 8 : MAXM;
@@ -641,7 +641,12 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         for (int a = 0; a < na; ++a) {
             PState &S = PS[act[a]];
             const size_t stop_at = std::min<size_t>(S.t->opt.max_iterations, std::max(S.t->opt.min_iterations, S.dynamic_max_iter) + 1);
-            size_t B = std::min(std::min(S.chunk, CHUNK_MAX), per_cap);
+            // While no model with a usable inlier ratio exists (dyn == max_iterations) the round size doubles from
+            // 1024; once dynamic_max_iter has come down, later improvements only lower it a little, so the rest of the
+            // loop is evaluated in one go (what is past the final break point is discarded by the replay).
+            const bool settled = S.dynamic_max_iter < S.t->opt.max_iterations;
+            size_t B = settled ? std::min<size_t>(stop_at - S.it, ROUND_MAX) : std::min(S.chunk, CHUNK_MAX);
+            B = std::min(B, per_cap);
             B = std::min(B, stop_at - S.it); // stop_at > it for an active problem
             S.chunk = std::min(CHUNK_MAX, S.chunk * 2);
             S.B = B;

@@ -778,20 +778,20 @@ PLB_DEV void solve_5pt_poly(const double *x1s, const double *x2s, Scratch5 *S, c
                 if (lane > k && lane < 10) C[lane * 20 + k] /= pv;
                 __syncwarp();
             }
-            const int m = 9 - k;
-            for (int e = lane; e < m * m; e += 32) {
-                const int r = k + 1 + e / m, c = k + 1 + e % m;
-                C[r * 20 + c] -= C[r * 20 + k] * C[k * 20 + c];
+            // rank-1 update of the trailing block, one lane per column c > k.  Columns 10..19 are the right-hand sides:
+            // updating them here IS the forward substitution (same operands, same order per element) of the
+            // reference's permute / unit-lower solve, so only the back substitution is left afterwards.
+            {
+                const int c = k + 1 + lane;
+                if (c < 20) {
+                    const double ckc = C[k * 20 + c];
+                    for (int r = k + 1; r < 10; ++r) C[r * 20 + c] -= C[r * 20 + k] * ckc;
+                }
             }
             __syncwarp();
         }
         if (lane < 10) {
             const int c = 10 + lane;
-            for (int r = 1; r < 10; ++r) {
-                double s = C[r * 20 + c];
-                for (int k = 0; k < r; ++k) s -= C[r * 20 + k] * C[k * 20 + c];
-                C[r * 20 + c] = s;
-            }
             for (int r = 9; r >= 0; --r) {
                 double s = C[r * 20 + c];
                 for (int k = r + 1; k < 10; ++k) s -= C[r * 20 + k] * C[k * 20 + c];
