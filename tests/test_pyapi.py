@@ -1,0 +1,66 @@
+"""The `poselib`-compatible Python surface: option-dict handling on CPU, results on the GPU."""
+import numpy as np
+import pytest
+
+import plo_py as P
+from poselib_b200 import problem_generator as G
+
+
+def test_option_dicts_follow_the_pybind_helpers():
+    from poselib_b200 import cabi, pyapi
+    kw = pyapi._ransac({"max_iterations": 5, "seed": 7, "progressive_sampling": True, "score_initial_model": True,
+                        "success_prob": 0.5})
+    assert kw == {"max_iterations": 5, "seed": 7, "progressive_sampling": True, "success_prob": 0.5}  # helpers.h:39
+    b = pyapi._bundle({"loss_type": "cauchy", "loss_scale": 2, "max_iterations": 3})
+    assert b == {"loss_type": "CAUCHY", "loss_scale": 2.0, "max_iterations": 3}
+    with pytest.raises(cabi.PoseLibB200Error):
+        pyapi._bundle({"loss_type": "TRUNCATED_LE_ZACH"})
+    with pytest.raises(cabi.PoseLibB200Error):
+        pyapi._bundle({"damping": "MARQUARDT"})
+    with pytest.raises(cabi.PoseLibB200Error):
+        pyapi._camera({"model": "OPENCV", "params": [1, 1, 0, 0, 0, 0, 0, 0]})
+    c = pyapi._camera({"model": "SIMPLE_PINHOLE", "width": 640, "height": 480, "params": [500.0, 320.0, 240.0]})
+    assert (c.model_id, c.width, c.height, list(c.params)[:3]) == (0, 640, 480, [500.0, 320.0, 240.0])
+    with pytest.raises(cabi.PoseLibB200Error):
+        pyapi.estimate_relative_pose(np.zeros((8, 2)), np.zeros((8, 2)), None, None, {"tangent_sampson": True})
+
+
+@pytest.mark.gpu
+def test_pyapi_matches_oracle_through_the_poselib_call_surface():
+    from poselib_b200 import pyapi as poselib
+    cam = {"model": "PINHOLE", "width": 2000, "height": 2000, "params": [G.FOCAL, G.FOCAL, 0.0, 0.0]}
+    camt = (G.FOCAL, G.FOCAL, 0.0, 0.0)
+    p = G.relpose_problem(2000, 0.4, 2, 21)
+    opt = {"max_error": 1.0, "ransac": {"max_iterations": 20000, "min_iterations": 500, "seed": 3}}
+    pose, info = poselib.estimate_relative_pose(p["x1"], p["x2"], cam, cam, opt)
+    o = P.estimate("relpose", p["x1"], p["x2"], P.RansacOpt(max_iterations=20000, min_iterations=500, seed=3),
+                   P.BundleOpt(), 1.0, camt, camt)
+    assert info["iterations"] == o["stats"]["iterations"] and info["num_inliers"] == o["stats"]["num_inliers"]
+    assert info["inliers"] == [bool(v) for v in o["inliers"]]
+    assert np.allclose(pose.q, o["model"][:4], atol=1e-7)
+    assert np.allclose(pose.R @ pose.R.T, np.eye(3), atol=1e-12) and pose.Rt.shape == (3, 4)
+    # initial_pose switches score_initial_model on (relative_pose.cc:25-28)
+    pose2, info2 = poselib.estimate_relative_pose(p["x1"], p["x2"], cam, cam, opt, initial_pose=pose)
+    assert info2["num_inliers"] >= info["num_inliers"] - 5
+    q = G.config_c1(2)
+    img, info = poselib.estimate_absolute_pose(q["x"], q["X"], cam, {"max_error": 12.0, "ransac": q["ransac"]})
+    o = P.estimate("pnp", q["x"], q["X"], P.RansacOpt(**q["ransac"]), P.BundleOpt(), 12.0, camt)
+    assert info["num_inliers"] == o["stats"]["num_inliers"] and np.allclose(img.pose.t, o["model"][4:], atol=1e-6)
+    h = G.homography_problem(1500, 0.6, 4, 9)
+    H, info = poselib.estimate_homography(h["x1"], h["x2"], {"ransac": {"max_iterations": 5000, "seed": 1}})
+    o = P.estimate("homography", h["x1"], h["x2"], P.RansacOpt(max_iterations=5000, seed=1), P.BundleOpt(), 1.0)
+    assert info["num_inliers"] == o["stats"]["num_inliers"]
+    assert min(np.abs(H - o["model"]).max(), np.abs(H + o["model"]).max()) < 1e-6
+    F, info = poselib.estimate_fundamental(p["x1"], p["x2"], {"ransac": {"max_iterations": 5000, "seed": 1}})
+    o = P.estimate("fundamental", p["x1"], p["x2"], P.RansacOpt(max_iterations=5000, seed=1), P.BundleOpt(), 1.0)
+    assert info["num_inliers"] == o["stats"]["num_inliers"]
+    # solvers
+    x, X, R, t = G.minimal_abspose(1)
+    assert len(poselib.p3p(x, X)) == len(P.p3p(x, X))
+    x1, x2, R, t = G.minimal_relpose(1, 5)
+    assert len(poselib.relpose_5pt(x1, x2)) == len(P.relpose_5pt(x1, x2))
+    assert np.allclose(np.array(poselib.essential_matrix_5pt(x1, x2)), P.relpose_5pt_E(x1, x2), atol=1e-12)
+    x1, x2, R, t = G.minimal_relpose(1, 7)
+    assert np.allclose(np.array(poselib.relpose_7pt(x1, x2)), P.relpose_7pt(x1, x2), atol=1e-9)
+    x1, x2, Hgt = G.minimal_homography(1)
+    assert len(poselib.homography_4pt(x1, x2)) == 1
