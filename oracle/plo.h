@@ -98,6 +98,13 @@ int get_inliers(const Mat3 &F, const std::vector<Vec2> &x1, const std::vector<Ve
                 std::vector<char> *inliers);
 void get_homography_inliers(const Mat3 &H, const std::vector<Vec2> &x1, const std::vector<Vec2> &x2,
                             double sq_threshold, std::vector<char> *inliers);
+struct Mat32 { double m[3][2]; }; // Eigen::Matrix<double,3,2> (unprojection Jacobian d bearing / d pixel)
+double compute_tangent_sampson_msac_score(const CameraPose &pose, const std::vector<Vec3> &d1,
+                                          const std::vector<Vec3> &d2, const std::vector<Mat32> &M1,
+                                          const std::vector<Mat32> &M2, double sq_threshold, size_t *inlier_count);
+int get_tangent_sampson_inliers(const CameraPose &pose, const std::vector<Vec3> &d1, const std::vector<Vec3> &d2,
+                                const std::vector<Mat32> &M1, const std::vector<Mat32> &M2, double sq_threshold,
+                                std::vector<char> *inliers);
 double normalize_points(std::vector<Vec2> &x1, std::vector<Vec2> &x2, Mat3 &T1, Mat3 &T2, bool normalize_scale,
                         bool normalize_centroid, bool shared_scale);
 bool calculate_RFC(const Mat3 &F);
@@ -110,16 +117,28 @@ size_t compute_dynamic_max_iter(size_t num_inliers, size_t num_data, size_t samp
 RansacStats ransac_mock(size_t num_data, size_t sample_sz, size_t inlier_count, const RansacOptions &opt);
 
 // ---- robust/bundle.cc entry points (LM refiners) ---------------------------------------------
-struct SimpleCamera { // PINHOLE: fx,fy,cx,cy ; SIMPLE_PINHOLE: f,f,cx,cy ; NULL: 1,1,0,0
-    double fx = 1, fy = 1, cx = 0, cy = 0;
-    double focal() const { return 0.0 + fx / 2 + fy / 2; } // camera_models.cc:304-324 (mean of focal_idx)
+// misc/camera_models.h:39-157 restricted to the six models on the path (ids = CameraModelId)
+enum { CAM_NULL = -1, CAM_SIMPLE_PINHOLE = 0, CAM_PINHOLE = 1, CAM_SIMPLE_RADIAL = 2, CAM_RADIAL = 3, CAM_OPENCV = 4 };
+struct Camera {
+    int model_id = CAM_NULL;
+    double params[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int num_params() const;
+    double focal() const;
+    void rescale(double scale);
+    void project(const Vec3 &x, Vec2 *xp) const;
+    void project_with_jac(const Vec3 &x, Vec2 *xp, double jac[2][3]) const;
+    void unproject(const Vec2 &xp, Vec3 *x) const;
+    Vec2 unproject2(const Vec2 &xp) const;
+    void unproject_with_jac(const Vec2 &xp, Vec3 *x, double M[3][2]) const;
 };
 BundleStats bundle_adjust(const std::vector<Vec2> &x, const std::vector<Vec3> &X, CameraPose *pose,
                           const BundleOptions &opt);
-BundleStats bundle_adjust_camera(const std::vector<Vec2> &x, const std::vector<Vec3> &X, const SimpleCamera &cam,
+BundleStats bundle_adjust_camera(const std::vector<Vec2> &x, const std::vector<Vec3> &X, const Camera &cam,
                                  CameraPose *pose, const BundleOptions &opt);
 BundleStats refine_relpose(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, CameraPose *pose,
                            const BundleOptions &opt);
+BundleStats refine_relpose(const std::vector<Vec3> &d1, const std::vector<Vec3> &d2, const std::vector<Mat32> &M1,
+                           const std::vector<Mat32> &M2, CameraPose *pose, const BundleOptions &opt);
 BundleStats refine_fundamental(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, Mat3 *F,
                                const BundleOptions &opt);
 BundleStats refine_homography(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, Mat3 *H,
@@ -130,20 +149,24 @@ RansacStats ransac_pnp(const std::vector<Vec2> &x, const std::vector<Vec3> &X, c
                        double max_error, CameraPose *best, std::vector<char> *inliers, Counters *cnt = nullptr);
 RansacStats ransac_relpose(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, const RansacOptions &ropt,
                            double max_error, CameraPose *best, std::vector<char> *inliers, Counters *cnt = nullptr);
+struct Camera;
+RansacStats ransac_relpose(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, const Camera &camera1,
+                           const Camera &camera2, const RansacOptions &ropt, double max_error, CameraPose *best,
+                           std::vector<char> *inliers, Counters *cnt = nullptr);
 RansacStats ransac_fundamental(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, const RansacOptions &ropt,
                                double max_error, bool real_focal_check, Mat3 *best, std::vector<char> *inliers,
                                Counters *cnt = nullptr);
 RansacStats ransac_homography(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, const RansacOptions &ropt,
                               double max_error, Mat3 *best, std::vector<char> *inliers, Counters *cnt = nullptr);
 
-// ---- PoseLib/robust.cc entry points (PINHOLE-family cameras: focal + principal point only) -----
+// ---- PoseLib/robust.cc entry points ----------------------------------------------------------
 RansacStats estimate_absolute_pose(const std::vector<Vec2> &x, const std::vector<Vec3> &X, const RansacOptions &ropt,
-                                   const BundleOptions &bopt, double max_error, const SimpleCamera &cam,
+                                   const BundleOptions &bopt, double max_error, const Camera &cam,
                                    CameraPose *pose, std::vector<char> *inliers, Counters *cnt = nullptr);
-RansacStats estimate_relative_pose(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, const SimpleCamera &cam1,
-                                   const SimpleCamera &cam2, const RansacOptions &ropt, const BundleOptions &bopt,
+RansacStats estimate_relative_pose(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, const Camera &cam1,
+                                   const Camera &cam2, const RansacOptions &ropt, const BundleOptions &bopt,
                                    double max_error, CameraPose *pose, std::vector<char> *inliers,
-                                   Counters *cnt = nullptr);
+                                   Counters *cnt = nullptr, bool tangent_sampson = false);
 RansacStats estimate_fundamental(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, const RansacOptions &ropt,
                                  const BundleOptions &bopt, double max_error, bool real_focal_check, Mat3 *F,
                                  std::vector<char> *inliers, Counters *cnt = nullptr);

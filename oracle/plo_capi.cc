@@ -288,11 +288,103 @@ void plo_ransac_homography(const double *x1, const double *x2, uint64_t n, const
     mask_out(m, inliers);
     put(c, cnt);
 }
+// ---- camera models (cam9 = model id followed by 8 parameter slots) ----------------------------
+static Camera cam_in(const double *cam9) {
+    Camera c;
+    c.model_id = (int)cam9[0];
+    for (int i = 0; i < 8; ++i) c.params[i] = cam9[1 + i];
+    return c;
+}
+// out: n x (3 bearing + 6 M row-major 3x2)
+void plo_camera_unproject_with_jac(const double *cam9, const double *xp, uint64_t n, double *out) {
+    const Camera c = cam_in(cam9);
+    for (uint64_t k = 0; k < n; ++k) {
+        Vec2 p;
+        p[0] = xp[2 * k];
+        p[1] = xp[2 * k + 1];
+        Vec3 d;
+        double M[3][2];
+        c.unproject_with_jac(p, &d, M);
+        for (int i = 0; i < 3; ++i) out[9 * k + i] = d[i];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 2; ++j) out[9 * k + 3 + 2 * i + j] = M[i][j];
+    }
+}
+// out: n x 2 (Camera::unproject to 2D, camera_models.h:98-102)
+void plo_camera_unproject2(const double *cam9, const double *xp, uint64_t n, double *out) {
+    const Camera c = cam_in(cam9);
+    for (uint64_t k = 0; k < n; ++k) {
+        Vec2 p;
+        p[0] = xp[2 * k];
+        p[1] = xp[2 * k + 1];
+        const Vec2 r = c.unproject2(p);
+        out[2 * k] = r[0];
+        out[2 * k + 1] = r[1];
+    }
+}
+// out: n x (2 projection + 6 Jacobian row-major 2x3); proj_only: n x 2 from Camera::project
+void plo_camera_project_with_jac(const double *cam9, const double *X, uint64_t n, double *out, double *proj_only) {
+    const Camera c = cam_in(cam9);
+    for (uint64_t k = 0; k < n; ++k) {
+        const Vec3 x = mk3(X[3 * k], X[3 * k + 1], X[3 * k + 2]);
+        Vec2 xp;
+        double J[2][3];
+        c.project_with_jac(x, &xp, J);
+        out[8 * k] = xp[0];
+        out[8 * k + 1] = xp[1];
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 3; ++j) out[8 * k + 2 + 3 * i + j] = J[i][j];
+        c.project(x, &xp);
+        proj_only[2 * k] = xp[0];
+        proj_only[2 * k + 1] = xp[1];
+    }
+}
+double plo_camera_focal(const double *cam9) { return cam_in(cam9).focal(); }
+
+// ---- tangent Sampson path (d: n x 3 bearings, M: n x 6 row-major 3x2) -------------------------
+static std::vector<Mat32> m32(const double *M, uint64_t n) {
+    std::vector<Mat32> r(n);
+    for (uint64_t k = 0; k < n; ++k)
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 2; ++j) r[k].m[i][j] = M[6 * k + 2 * i + j];
+    return r;
+}
+double plo_score_tangent(const double *pose, const double *d1, const double *d2, const double *M1, const double *M2,
+                         uint64_t n, double sq_threshold, uint64_t *count, char *inliers) {
+    const CameraPose p = pose_in(pose);
+    size_t c = 0;
+    const double s = compute_tangent_sampson_msac_score(p, v3(d1, n), v3(d2, n), m32(M1, n), m32(M2, n), sq_threshold, &c);
+    *count = c;
+    if (inliers) {
+        std::vector<char> m;
+        get_tangent_sampson_inliers(p, v3(d1, n), v3(d2, n), m32(M1, n), m32(M2, n), sq_threshold, &m);
+        mask_out(m, inliers);
+    }
+    return s;
+}
+void plo_refine_relpose_tangent(const double *d1, const double *d2, const double *M1, const double *M2, uint64_t n,
+                                const plo_bundle_opt *bopt, double *pose, double *bstats7) {
+    CameraPose p = pose_in(pose);
+    const BundleStats st = refine_relpose(v3(d1, n), v3(d2, n), m32(M1, n), m32(M2, n), &p, cvt(bopt));
+    pose_out(p, pose);
+    put_bs(st, bstats7);
+}
+void plo_ransac_relpose_cameras(const double *x1, const double *x2, uint64_t n, const double *cam1_9,
+                                const double *cam2_9, const plo_ransac_opt *opt, double max_error, double *pose,
+                                char *inliers, plo_ransac_stats *stats, plo_counters *cnt) {
+    CameraPose p = pose_in(pose);
+    std::vector<char> m(n, 0);
+    Counters c;
+    put(ransac_relpose(v2(x1, n), v2(x2, n), cam_in(cam1_9), cam_in(cam2_9), cvt(opt), max_error, &p, &m, &c), stats);
+    pose_out(p, pose);
+    mask_out(m, inliers);
+    put(c, cnt);
+}
 // ---- estimate_* -------------------------------------------------------------------------------
 void plo_estimate_absolute_pose(const double *x, const double *X, uint64_t n, const plo_ransac_opt *ropt,
-                                const plo_bundle_opt *bopt, double max_error, const double *cam4, double *pose,
+                                const plo_bundle_opt *bopt, double max_error, const double *cam9, double *pose,
                                 char *inliers, plo_ransac_stats *stats, plo_counters *cnt) {
-    SimpleCamera cam{cam4[0], cam4[1], cam4[2], cam4[3]};
+    Camera cam = cam_in(cam9);
     CameraPose p = pose_in(pose);
     std::vector<char> m(n, 0);
     Counters c;
@@ -301,15 +393,17 @@ void plo_estimate_absolute_pose(const double *x, const double *X, uint64_t n, co
     mask_out(m, inliers);
     put(c, cnt);
 }
-void plo_estimate_relative_pose(const double *x1, const double *x2, uint64_t n, const double *cam1_4,
-                                const double *cam2_4, const plo_ransac_opt *ropt, const plo_bundle_opt *bopt,
-                                double max_error, double *pose, char *inliers, plo_ransac_stats *stats,
-                                plo_counters *cnt) {
-    SimpleCamera c1{cam1_4[0], cam1_4[1], cam1_4[2], cam1_4[3]}, c2{cam2_4[0], cam2_4[1], cam2_4[2], cam2_4[3]};
+void plo_estimate_relative_pose(const double *x1, const double *x2, uint64_t n, const double *cam1_9,
+                                const double *cam2_9, const plo_ransac_opt *ropt, const plo_bundle_opt *bopt,
+                                double max_error, int tangent_sampson, double *pose, char *inliers,
+                                plo_ransac_stats *stats, plo_counters *cnt) {
+    Camera c1 = cam_in(cam1_9), c2 = cam_in(cam2_9);
     CameraPose p = pose_in(pose);
     std::vector<char> m(n, 0);
     Counters c;
-    put(estimate_relative_pose(v2(x1, n), v2(x2, n), c1, c2, cvt(ropt), cvt(bopt), max_error, &p, &m, &c), stats);
+    put(estimate_relative_pose(v2(x1, n), v2(x2, n), c1, c2, cvt(ropt), cvt(bopt), max_error, &p, &m, &c,
+                               tangent_sampson != 0),
+        stats);
     pose_out(p, pose);
     mask_out(m, inliers);
     put(c, cnt);

@@ -1,26 +1,15 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.
-// The four robust.cc entry points for PINHOLE-family cameras (paths relative to /root/reference).
+// The four robust.cc entry points (paths relative to /root/reference/PoseLib).
 #include "plo.h"
 
 namespace plo {
 
-namespace {
-// camera_models.cc:668-711 (PINHOLE unproject): ((x-cx)/fx, (y-cy)/fy, 1) then hnormalized (camera_models.h:98-102)
-inline Vec2 unproject(const SimpleCamera &cam, const Vec2 &p) {
-    Vec2 r;
-    r[0] = (p[0] - cam.cx) / cam.fx;
-    r[1] = (p[1] - cam.cy) / cam.fy;
-    return r;
-}
-} // namespace
-
 // robust.cc:36-126 (branch without focal estimation)
 RansacStats estimate_absolute_pose(const std::vector<Vec2> &points2D, const std::vector<Vec3> &points3D,
                                    const RansacOptions &ropt, const BundleOptions &bopt, double max_error,
-                                   const SimpleCamera &cam, CameraPose *pose, std::vector<char> *inliers,
-                                   Counters *cnt) {
+                                   const Camera &cam, CameraPose *pose, std::vector<char> *inliers, Counters *cnt) {
     std::vector<Vec2> norm(points2D.size());
-    for (size_t k = 0; k < points2D.size(); ++k) norm[k] = unproject(cam, points2D[k]);
+    for (size_t k = 0; k < points2D.size(); ++k) norm[k] = cam.unproject2(points2D[k]);
     double scale = 1.0 / cam.focal();
     const double max_error_scaled = max_error * scale;
     RansacStats stats = ransac_pnp(norm, points3D, ropt, max_error_scaled, pose, inliers, cnt);
@@ -38,27 +27,55 @@ RansacStats estimate_absolute_pose(const std::vector<Vec2> &points2D, const std:
             x_in.push_back(p);
             X_in.push_back(points3D[k]);
         }
-        // camera.rescale(scale): focal and principal point multiplied by scale (camera_models.cc:432-454)
-        SimpleCamera rc = cam;
-        rc.fx *= scale; rc.fy *= scale; rc.cx *= scale; rc.cy *= scale;
+        Camera rc = cam;
+        rc.rescale(scale);
         bundle_adjust_camera(x_in, X_in, rc, pose, b);
     }
     return stats;
 }
 
-// robust.cc:242-314 (tangent_sampson == false branch)
-RansacStats estimate_relative_pose(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, const SimpleCamera &cam1,
-                                   const SimpleCamera &cam2, const RansacOptions &ropt, const BundleOptions &bopt,
-                                   double max_error, CameraPose *pose, std::vector<char> *inliers, Counters *cnt) {
+// robust.cc:242-314
+RansacStats estimate_relative_pose(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, const Camera &cam1,
+                                   const Camera &cam2, const RansacOptions &ropt, const BundleOptions &bopt,
+                                   double max_error, CameraPose *pose, std::vector<char> *inliers, Counters *cnt,
+                                   bool tangent_sampson) {
     const size_t n = x1.size();
     const double scale = 0.5 * (1.0 / cam1.focal() + 1.0 / cam2.focal());
     const double max_error_scaled = max_error * scale;
     BundleOptions b = bopt;
     b.loss_scale *= scale;
+    if (tangent_sampson) { // :255-284
+        std::vector<Vec2> s1(n), s2(n);
+        for (size_t k = 0; k < n; ++k) {
+            s1[k][0] = x1[k][0] * scale; s1[k][1] = x1[k][1] * scale;
+            s2[k][0] = x2[k][0] * scale; s2[k][1] = x2[k][1] * scale;
+        }
+        Camera c1 = cam1, c2 = cam2;
+        c1.rescale(scale);
+        c2.rescale(scale);
+        RansacStats stats = ransac_relpose(s1, s2, c1, c2, ropt, max_error_scaled, pose, inliers, cnt);
+        if (stats.num_inliers > 5) {
+            // refine_relpose(x1_inliers, x2_inliers, &pair, bundle) with fixed cameras (bundle.cc:237-247):
+            // unproject_with_jac of the inlier points, then the FixCameraRelativePoseRefiner
+            std::vector<Vec3> d1, d2;
+            std::vector<Mat32> M1, M2;
+            for (size_t k = 0; k < n; ++k) {
+                if (!(*inliers)[k]) continue;
+                Vec3 a, bb;
+                Mat32 ma, mb;
+                c1.unproject_with_jac(s1[k], &a, ma.m);
+                c2.unproject_with_jac(s2[k], &bb, mb.m);
+                d1.push_back(a); d2.push_back(bb);
+                M1.push_back(ma); M2.push_back(mb);
+            }
+            refine_relpose(d1, d2, M1, M2, pose, b);
+        }
+        return stats;
+    }
     std::vector<Vec2> c1(n), c2(n);
     for (size_t k = 0; k < n; ++k) {
-        c1[k] = unproject(cam1, x1[k]);
-        c2[k] = unproject(cam2, x2[k]);
+        c1[k] = cam1.unproject2(x1[k]);
+        c2[k] = cam2.unproject2(x2[k]);
     }
     RansacStats stats = ransac_relpose(c1, c2, ropt, max_error_scaled, pose, inliers, cnt);
     if (stats.num_inliers > 5) {

@@ -167,48 +167,30 @@ struct AbsolutePoseRefiner {
     int num_params = 6;
     const std::vector<Vec2> &x;
     const std::vector<Vec3> &X;
-    const SimpleCamera *cam;
-    AbsolutePoseRefiner(const std::vector<Vec2> &x_, const std::vector<Vec3> &X_, const SimpleCamera *c)
-        : x(x_), X(X_), cam(c) {}
-    double compute_residual(NormalAccumulator &acc, const CameraPose &pose) {
+    Camera cam; // fixed intrinsics (camera_refine_idx empty); the null camera when none is given
+    AbsolutePoseRefiner(const std::vector<Vec2> &x_, const std::vector<Vec3> &X_, const Camera *c)
+        : x(x_), X(X_), cam(c ? *c : Camera()) {}
+    double compute_residual(NormalAccumulator &acc, const CameraPose &pose) { // absolute.h:49-66
         const Mat3 R = pose.R();
         for (size_t i = 0; i < x.size(); ++i) {
             const Vec3 Z = R * X[i] + pose.t;
             if (Z[2] < 0) continue;
-            double xp0, xp1;
-            if (cam) {
-                xp0 = cam->fx * Z[0] / Z[2] + cam->cx;
-                xp1 = cam->fy * Z[1] / Z[2] + cam->cy;
-            } else {
-                xp0 = Z[0] / Z[2];
-                xp1 = Z[1] / Z[2];
-            }
-            acc.add_residual2(xp0 - x[i][0], xp1 - x[i][1]);
+            Vec2 xp;
+            cam.project(Z, &xp);
+            acc.add_residual2(xp[0] - x[i][0], xp[1] - x[i][1]);
         }
         return acc.get_residual();
     }
-    void compute_jacobian(NormalAccumulator &acc, const CameraPose &pose) {
+    void compute_jacobian(NormalAccumulator &acc, const CameraPose &pose) { // absolute.h:80-130
         const Mat3 R = pose.R();
         for (size_t i = 0; i < x.size(); ++i) {
             const Vec3 Xi = X[i];
             const Vec3 Z = R * Xi + pose.t;
             if (Z[2] < 0) continue;
-            double zp0, zp1, Jp[2][3];
-            if (cam) {
-                const double inv_z = 1.0 / Z[2];
-                const double px = cam->fx * Z[0] * inv_z, py = cam->fy * Z[1] * inv_z;
-                zp0 = px + cam->cx;
-                zp1 = py + cam->cy;
-                Jp[0][0] = cam->fx * inv_z; Jp[0][1] = 0.0; Jp[0][2] = -px * inv_z;
-                Jp[1][0] = 0.0; Jp[1][1] = cam->fy * inv_z; Jp[1][2] = -py * inv_z;
-            } else {
-                zp0 = Z[0] / Z[2];
-                zp1 = Z[1] / Z[2];
-                const double z_inv = 1.0 / Z[2];
-                Jp[0][0] = z_inv; Jp[0][1] = 0.0; Jp[0][2] = -zp0 * z_inv;
-                Jp[1][0] = 0.0; Jp[1][1] = z_inv; Jp[1][2] = -zp1 * z_inv;
-            }
-            const double r0 = zp0 - x[i][0], r1 = zp1 - x[i][1];
+            Vec2 zp;
+            double Jp[2][3];
+            cam.project_with_jac(Z, &zp, Jp);
+            const double r0 = zp[0] - x[i][0], r1 = zp[1] - x[i][1];
             double dZ[2][3]; // Jproj * R
             for (int a = 0; a < 2; ++a)
                 for (int c = 0; c < 3; ++c) dZ[a][c] = Jp[a][0] * R(0, c) + Jp[a][1] * R(1, c) + Jp[a][2] * R(2, c);
@@ -272,6 +254,54 @@ inline double sampson_resid(const Mat3 &E, const Vec2 &p1, const Vec2 &p2) {
     return C / std::sqrt(nJc_sq);
 }
 
+// relative.h:62-82
+inline void setup_tangent_basis(const Vec3 &t, double tb[3][2]) {
+    Vec3 b0;
+    const double ax = std::abs(t[0]), ay = std::abs(t[1]), az = std::abs(t[2]);
+    if (ax < ay) {
+        if (ax < az) b0 = normalized(cross(t, mk3(1, 0, 0)));
+        else b0 = normalized(cross(t, mk3(0, 0, 1)));
+    } else {
+        if (ay < az) b0 = normalized(cross(t, mk3(0, 1, 0)));
+        else b0 = normalized(cross(t, mk3(0, 0, 1)));
+    }
+    const Vec3 b1 = normalized(cross(b0, t));
+    for (int r = 0; r < 3; ++r) {
+        tb[r][0] = b0[r];
+        tb[r][1] = b1[r];
+    }
+}
+// dR (9x3), dt (9x2): derivatives of vec(E) (column-major)  (relative.h:39-60)
+inline void deriv_essential_wrt_pose(const Mat3 &E, const Mat3 &R, const double tb[3][2], double dR[9][3],
+                                     double dt[9][2]) {
+    const Vec3 e0 = col(E, 0), e1 = col(E, 1), e2 = col(E, 2);
+    for (int r = 0; r < 3; ++r) {
+        dR[r][0] = 0.0;        dR[r][1] = -e2[r];     dR[r][2] = e1[r];
+        dR[3 + r][0] = e2[r];  dR[3 + r][1] = 0.0;    dR[3 + r][2] = -e0[r];
+        dR[6 + r][0] = -e1[r]; dR[6 + r][1] = e0[r];  dR[6 + r][2] = 0.0;
+    }
+    const Vec3 tb0 = mk3(tb[0][0], tb[1][0], tb[2][0]), tb1 = mk3(tb[0][1], tb[1][1], tb[2][1]);
+    for (int c = 0; c < 3; ++c) {
+        const Vec3 v0 = cross(tb0, col(R, c)), v1 = cross(tb1, col(R, c));
+        for (int r = 0; r < 3; ++r) {
+            dt[3 * c + r][0] = v0[r];
+            dt[3 * c + r][1] = v1[r];
+        }
+    }
+}
+inline void pose_jac_from_dF(const double dF[9], const double dR[9][3], const double dt[9][2], double J[5]) {
+    for (int p = 0; p < 3; ++p) {
+        double s = 0;
+        for (int m = 0; m < 9; ++m) s += dF[m] * dR[m][p];
+        J[p] = s;
+    }
+    for (int p = 0; p < 2; ++p) {
+        double s = 0;
+        for (int m = 0; m < 9; ++m) s += dF[m] * dt[m][p];
+        J[3 + p] = s;
+    }
+}
+
 struct RelativePoseRefiner {
     int num_params = 5;
     const std::vector<Vec2> &x1, &x2;
@@ -283,56 +313,90 @@ struct RelativePoseRefiner {
         for (size_t k = 0; k < x1.size(); ++k) acc.add_residual1(sampson_resid(E, x1[k], x2[k]));
         return acc.get_residual();
     }
-    void setup_tangent_basis(const Vec3 &t) { // relative.h:62-82
-        Vec3 b0;
-        const double ax = std::abs(t[0]), ay = std::abs(t[1]), az = std::abs(t[2]);
-        if (ax < ay) {
-            if (ax < az) b0 = normalized(cross(t, mk3(1, 0, 0)));
-            else b0 = normalized(cross(t, mk3(0, 0, 1)));
-        } else {
-            if (ay < az) b0 = normalized(cross(t, mk3(0, 1, 0)));
-            else b0 = normalized(cross(t, mk3(0, 0, 1)));
-        }
-        const Vec3 b1 = normalized(cross(b0, t));
-        for (int r = 0; r < 3; ++r) {
-            tb[r][0] = b0[r];
-            tb[r][1] = b1[r];
-        }
-    }
     void compute_jacobian(NormalAccumulator &acc, const CameraPose &pose) {
         const Mat3 R = pose.R();
         Mat3 E;
         essential_from_motion(pose, &E);
-        setup_tangent_basis(pose.t);
-        // dR (9x3), dt (9x2): derivatives of vec(E) (column-major)  (relative.h:39-60)
+        setup_tangent_basis(pose.t, tb);
         double dR[9][3], dt[9][2];
-        const Vec3 e0 = col(E, 0), e1 = col(E, 1), e2 = col(E, 2);
-        for (int r = 0; r < 3; ++r) {
-            dR[r][0] = 0.0;        dR[r][1] = -e2[r];     dR[r][2] = e1[r];
-            dR[3 + r][0] = e2[r];  dR[3 + r][1] = 0.0;    dR[3 + r][2] = -e0[r];
-            dR[6 + r][0] = -e1[r]; dR[6 + r][1] = e0[r];  dR[6 + r][2] = 0.0;
-        }
-        const Vec3 tb0 = mk3(tb[0][0], tb[1][0], tb[2][0]), tb1 = mk3(tb[0][1], tb[1][1], tb[2][1]);
-        for (int c = 0; c < 3; ++c) {
-            const Vec3 v0 = cross(tb0, col(R, c)), v1 = cross(tb1, col(R, c));
-            for (int r = 0; r < 3; ++r) {
-                dt[3 * c + r][0] = v0[r];
-                dt[3 * c + r][1] = v1[r];
-            }
-        }
+        deriv_essential_wrt_pose(E, R, tb, dR, dt);
         for (size_t k = 0; k < x1.size(); ++k) {
             double r, dF[9], J[5];
             sampson_resid_and_dF(E, x1[k], x2[k], r, dF);
-            for (int p = 0; p < 3; ++p) {
-                double s = 0;
-                for (int m = 0; m < 9; ++m) s += dF[m] * dR[m][p];
-                J[p] = s;
-            }
-            for (int p = 0; p < 2; ++p) {
-                double s = 0;
-                for (int m = 0; m < 9; ++m) s += dF[m] * dt[m][p];
-                J[3 + p] = s;
-            }
+            pose_jac_from_dF(dF, dR, dt, J);
+            acc.add_jacobian1(r, J);
+        }
+    }
+    CameraPose step(const double *dp, const CameraPose &pose) const {
+        CameraPose p;
+        p.q = quat_step_post(pose.q, mk3(dp[0], dp[1], dp[2]));
+        for (int r = 0; r < 3; ++r) p.t[r] = pose.t[r] + (tb[r][0] * dp[3] + tb[r][1] * dp[4]);
+        return p;
+    }
+};
+
+// ---- optim/relative.h:167-262 FixCameraRelativePoseRefiner (tangent Sampson error, fixed intrinsics) --------
+// Eigen evaluates `M^T * E * d` left to right: the 2x3 product (M^T E) first, then times d.
+inline void tangent_terms(const Mat3 &E, const Vec3 &d1, const Vec3 &d2, const Mat32 &M1, const Mat32 &M2, double &C,
+                          double JC[4]) {
+    const Vec3 Ed1 = E * d1;
+    C = d2[0] * Ed1[0] + d2[1] * Ed1[1] + d2[2] * Ed1[2];
+    for (int i = 0; i < 2; ++i) {
+        double T1[3], T2[3]; // row i of M1^T E^T and of M2^T E
+        for (int j = 0; j < 3; ++j) {
+            T1[j] = M1.m[0][i] * E(j, 0) + M1.m[1][i] * E(j, 1) + M1.m[2][i] * E(j, 2);
+            T2[j] = M2.m[0][i] * E(0, j) + M2.m[1][i] * E(1, j) + M2.m[2][i] * E(2, j);
+        }
+        JC[i] = T1[0] * d2[0] + T1[1] * d2[1] + T1[2] * d2[2];
+        JC[2 + i] = T2[0] * d1[0] + T2[1] * d1[1] + T2[2] * d1[2];
+    }
+}
+struct FixCameraRelativePoseRefiner {
+    int num_params = 5;
+    const std::vector<Vec3> &d1, &d2;
+    const std::vector<Mat32> &M1, &M2;
+    double tb[3][2];
+    FixCameraRelativePoseRefiner(const std::vector<Vec3> &a, const std::vector<Vec3> &b, const std::vector<Mat32> &m1,
+                                 const std::vector<Mat32> &m2)
+        : d1(a), d2(b), M1(m1), M2(m2) {}
+    double compute_residual(NormalAccumulator &acc, const CameraPose &pose) { // relative.h:181-193
+        Mat3 E;
+        essential_from_motion(pose, &E);
+        for (size_t k = 0; k < d1.size(); ++k) {
+            double C, JC[4];
+            tangent_terms(E, d1[k], d2[k], M1[k], M2[k], C, JC);
+            const double nJc_sq = (JC[2] * JC[2] + JC[3] * JC[3]) + (JC[0] * JC[0] + JC[1] * JC[1]);
+            acc.add_residual1(C / std::sqrt(nJc_sq));
+        }
+        return acc.get_residual();
+    }
+    void compute_jacobian(NormalAccumulator &acc, const CameraPose &pose) { // relative.h:195-249
+        setup_tangent_basis(pose.t, tb);
+        const Mat3 R = pose.R();
+        Mat3 E;
+        essential_from_motion(pose, &E);
+        double dR[9][3], dt[9][2];
+        deriv_essential_wrt_pose(E, R, tb, dR, dt);
+        for (size_t k = 0; k < d1.size(); ++k) {
+            const Vec3 &a = d1[k], &b = d2[k];
+            const Mat32 &m1 = M1[k], &m2 = M2[k];
+            double C, JC[4];
+            tangent_terms(E, a, b, m1, m2, C, JC);
+            // Vector4d::norm(): packet-of-2 reduction order (SSE2 build)
+            const double nJ_C = std::sqrt((JC[0] * JC[0] + JC[2] * JC[2]) + (JC[1] * JC[1] + JC[3] * JC[3]));
+            const double inv_nJ_C = 1.0 / nJ_C;
+            const double r = C * inv_nJ_C;
+            double dF[9];
+            for (int c = 0; c < 3; ++c)
+                for (int rr = 0; rr < 3; ++rr) dF[3 * c + rr] = a[c] * b[rr];
+            const double s = C * inv_nJ_C * inv_nJ_C;
+            for (int c = 0; c < 3; ++c)
+                for (int rr = 0; rr < 3; ++rr)
+                    dF[3 * c + rr] -= s * (JC[0] * m1.m[c][0] * b[rr] + JC[1] * m1.m[c][1] * b[rr] +
+                                           JC[2] * m2.m[rr][0] * a[c] + JC[3] * m2.m[rr][1] * a[c]);
+            for (int m = 0; m < 9; ++m) dF[m] *= inv_nJ_C;
+            double J[5];
+            pose_jac_from_dF(dF, dR, dt, J);
             acc.add_jacobian1(r, J);
         }
     }
@@ -509,8 +573,8 @@ BundleStats bundle_adjust(const std::vector<Vec2> &x, const std::vector<Vec3> &X
     AbsolutePoseRefiner refiner(x, X, nullptr);
     return lm_impl(refiner, pose, opt);
 }
-// bundle.cc:95-112 with a fixed PINHOLE camera (no intrinsics refinement)
-BundleStats bundle_adjust_camera(const std::vector<Vec2> &x, const std::vector<Vec3> &X, const SimpleCamera &cam,
+// bundle.cc:95-112 with a fixed camera (no intrinsics refinement)
+BundleStats bundle_adjust_camera(const std::vector<Vec2> &x, const std::vector<Vec3> &X, const Camera &cam,
                                  CameraPose *pose, const BundleOptions &opt) {
     AbsolutePoseRefiner refiner(x, X, &cam);
     return lm_impl(refiner, pose, opt);
@@ -519,6 +583,12 @@ BundleStats bundle_adjust_camera(const std::vector<Vec2> &x, const std::vector<V
 BundleStats refine_relpose(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, CameraPose *pose,
                            const BundleOptions &opt) {
     RelativePoseRefiner refiner(x1, x2);
+    return lm_impl(refiner, pose, opt);
+}
+// bundle.cc:227-235,268-277 (pre-computed bearings and unprojection Jacobians, uniform weights)
+BundleStats refine_relpose(const std::vector<Vec3> &d1, const std::vector<Vec3> &d2, const std::vector<Mat32> &M1,
+                           const std::vector<Mat32> &M2, CameraPose *pose, const BundleOptions &opt) {
+    FixCameraRelativePoseRefiner refiner(d1, d2, M1, M2);
     return lm_impl(refiner, pose, opt);
 }
 // bundle.cc:313-333

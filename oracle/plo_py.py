@@ -269,14 +269,112 @@ def ransac(kind, a, b, ropt, max_error, init=None, rfc=False):
     return {"model": model, "inliers": mask, "stats": st.as_dict(), "counters": cn.as_dict()}
 
 
-def estimate(kind, a, b, ropt, bopt, max_error, cam1=(1, 1, 0, 0), cam2=(1, 1, 0, 0), init=None, rfc=False):
+CAMERA_IDS = {"NULL": -1, "SIMPLE_PINHOLE": 0, "PINHOLE": 1, "SIMPLE_RADIAL": 2, "RADIAL": 3, "OPENCV": 4}
+
+
+def _cam(spec):
+    """None -> NULL camera; ("MODEL", params); a bare 4-sequence means PINHOLE (fx, fy, cx, cy)."""
+    out = np.zeros(9, dtype=np.float64)
+    if spec is None:
+        out[0] = -1
+    elif isinstance(spec[0], str):
+        out[0] = CAMERA_IDS[spec[0].upper()]
+        out[1:1 + len(spec[1])] = spec[1]
+    else:
+        out[0] = 1
+        out[1:5] = spec
+    return out, out.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def camera_unproject_with_jac(cam, xp):
+    """-> (d (n,3), M (n,3,2)) of Camera::unproject_with_jac."""
+    c, cp = _cam(cam)
+    xa, xpp = _d(xp)
+    n = len(xp)
+    out = np.zeros((n, 9))
+    lib().plo_camera_unproject_with_jac(cp, xpp, C.c_uint64(n), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out[:, :3].copy(), out[:, 3:].reshape(n, 3, 2).copy()
+
+
+def camera_unproject2(cam, xp):
+    c, cp = _cam(cam)
+    xa, xpp = _d(xp)
+    n = len(xp)
+    out = np.zeros((n, 2))
+    lib().plo_camera_unproject2(cp, xpp, C.c_uint64(n), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
+
+
+def camera_project_with_jac(cam, X):
+    """-> (xp (n,2) from project_with_jac, J (n,2,3), xp (n,2) from project)."""
+    c, cp = _cam(cam)
+    Xa, Xp = _d(X)
+    n = len(X)
+    out = np.zeros((n, 8))
+    po = np.zeros((n, 2))
+    lib().plo_camera_project_with_jac(cp, Xp, C.c_uint64(n), out.ctypes.data_as(C.POINTER(C.c_double)),
+                                      po.ctypes.data_as(C.POINTER(C.c_double)))
+    return out[:, :2].copy(), out[:, 2:].reshape(n, 2, 3).copy(), po
+
+
+def camera_focal(cam):
+    c, cp = _cam(cam)
+    lib().plo_camera_focal.restype = C.c_double
+    return lib().plo_camera_focal(cp)
+
+
+def score_tangent(pose, d1, d2, M1, M2, sq_thr, want_inliers=False):
+    n = len(d1)
+    m = np.ascontiguousarray(pose, dtype=np.float64)
+    a, ap = _d(d1)
+    b, bp = _d(d2)
+    m1, m1p = _d(np.asarray(M1).reshape(n, 6))
+    m2, m2p = _d(np.asarray(M2).reshape(n, 6))
+    cnt = C.c_uint64(0)
+    mask, mkp = _mask(n)
+    lib().plo_score_tangent.restype = C.c_double
+    s = lib().plo_score_tangent(m.ctypes.data_as(C.POINTER(C.c_double)), ap, bp, m1p, m2p, C.c_uint64(n),
+                                C.c_double(sq_thr), C.byref(cnt), mkp if want_inliers else None)
+    return (s, cnt.value, mask) if want_inliers else (s, cnt.value)
+
+
+def refine_relpose_tangent(pose, d1, d2, M1, M2, bopt):
+    n = len(d1)
+    m = np.ascontiguousarray(pose, dtype=np.float64).copy()
+    a, ap = _d(d1)
+    b, bp = _d(d2)
+    m1, m1p = _d(np.asarray(M1).reshape(n, 6))
+    m2, m2p = _d(np.asarray(M2).reshape(n, 6))
+    bs = np.zeros(7)
+    lib().plo_refine_relpose_tangent(ap, bp, m1p, m2p, C.c_uint64(n), C.byref(bopt),
+                                     m.ctypes.data_as(C.POINTER(C.c_double)),
+                                     bs.ctypes.data_as(C.POINTER(C.c_double)))
+    return m, bs
+
+
+def ransac_relpose_cameras(x1, x2, cam1, cam2, ropt, max_error):
+    """ransac_relpose with cameras (tangent Sampson error, ransac.cc:155-168); points in (scaled) pixels."""
+    n = len(x1)
+    aa, ap = _d(x1)
+    ba, bp = _d(x2)
+    c1, c1p = _cam(cam1)
+    c2, c2p = _cam(cam2)
+    mask, mkp = _mask(n)
+    st, cn = RansacStats(), Counters()
+    m = np.array([1, 0, 0, 0, 0, 0, 0], dtype=np.float64)
+    lib().plo_ransac_relpose_cameras(ap, bp, C.c_uint64(n), c1p, c2p, C.byref(ropt), C.c_double(max_error),
+                                     m.ctypes.data_as(C.POINTER(C.c_double)), mkp, C.byref(st), C.byref(cn))
+    return {"model": m, "inliers": mask, "stats": st.as_dict(), "counters": cn.as_dict()}
+
+
+def estimate(kind, a, b, ropt, bopt, max_error, cam1=None, cam2=None, init=None, rfc=False, tangent_sampson=False):
     n = len(a)
     aa, ap = _d(a)
     ba, bp = _d(b)
     mask, mkp = _mask(n)
     st, cn = RansacStats(), Counters()
-    c1, c1p = _d(cam1)
-    c2, c2p = _d(cam2)
+    c1, c1p = _cam(cam1)
+    c2, c2p = _cam(cam2)
     if kind in ("pnp", "relpose"):
         m = np.array([1, 0, 0, 0, 0, 0, 0] if init is None else init, dtype=np.float64)
         mp = m.ctypes.data_as(C.POINTER(C.c_double))
@@ -285,7 +383,8 @@ def estimate(kind, a, b, ropt, bopt, max_error, cam1=(1, 1, 0, 0), cam2=(1, 1, 0
                                              C.c_double(max_error), c1p, mp, mkp, C.byref(st), C.byref(cn))
         else:
             lib().plo_estimate_relative_pose(ap, bp, C.c_uint64(n), c1p, c2p, C.byref(ropt), C.byref(bopt),
-                                             C.c_double(max_error), mp, mkp, C.byref(st), C.byref(cn))
+                                             C.c_double(max_error), int(tangent_sampson), mp, mkp, C.byref(st),
+                                             C.byref(cn))
         model = m
     else:
         m0 = np.eye(3) if init is None else np.asarray(init, dtype=np.float64)

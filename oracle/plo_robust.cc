@@ -140,6 +140,69 @@ double compute_sampson_msac_score(const CameraPose &pose, const std::vector<Vec2
     }
     return score;
 }
+namespace {
+// r2 of utils.cc:282-285 / :554-557; `M^T * E * d` is evaluated by Eigen as (M^T E) d
+inline double tangent_sampson_r2(const Mat3 &E, const Vec3 &d1, const Vec3 &d2, const Mat32 &M1, const Mat32 &M2) {
+    const Vec3 Ed1 = E * d1;
+    const double C = d2[0] * Ed1[0] + d2[1] * Ed1[1] + d2[2] * Ed1[2];
+    double a[2], b[2];
+    for (int i = 0; i < 2; ++i) {
+        double T1[3], T2[3];
+        for (int j = 0; j < 3; ++j) {
+            T2[j] = M2.m[0][i] * E(0, j) + M2.m[1][i] * E(1, j) + M2.m[2][i] * E(2, j);
+            T1[j] = M1.m[0][i] * E(j, 0) + M1.m[1][i] * E(j, 1) + M1.m[2][i] * E(j, 2);
+        }
+        a[i] = T2[0] * d1[0] + T2[1] * d1[1] + T2[2] * d1[2];
+        b[i] = T1[0] * d2[0] + T1[1] * d2[1] + T1[2] * d2[2];
+    }
+    const double denom2 = (a[0] * a[0] + a[1] * a[1]) + (b[0] * b[0] + b[1] * b[1]);
+    return C * C / denom2;
+}
+} // namespace
+// utils.cc:269-298
+double compute_tangent_sampson_msac_score(const CameraPose &pose, const std::vector<Vec3> &d1,
+                                          const std::vector<Vec3> &d2, const std::vector<Mat32> &M1,
+                                          const std::vector<Mat32> &M2, double sq_threshold, size_t *inlier_count) {
+    Mat3 E;
+    essential_from_motion(pose, &E);
+    *inlier_count = 0;
+    double score = 0;
+    for (size_t i = 0; i < d1.size(); ++i) {
+        const double r2 = tangent_sampson_r2(E, d1[i], d2[i], M1[i], M2[i]);
+        if (r2 < sq_threshold) {
+            const bool cheirality = check_cheirality(pose, d1[i], d2[i], 0.01);
+            if (cheirality) {
+                (*inlier_count)++;
+                score += r2;
+            } else {
+                score += sq_threshold;
+            }
+        } else {
+            score += sq_threshold;
+        }
+    }
+    return score;
+}
+// utils.cc:541-569
+int get_tangent_sampson_inliers(const CameraPose &pose, const std::vector<Vec3> &d1, const std::vector<Vec3> &d2,
+                                const std::vector<Mat32> &M1, const std::vector<Mat32> &M2, double sq_threshold,
+                                std::vector<char> *inliers) {
+    Mat3 E;
+    essential_from_motion(pose, &E);
+    inliers->resize(d1.size());
+    size_t inlier_count = 0;
+    for (size_t i = 0; i < d1.size(); ++i) {
+        const double r2 = tangent_sampson_r2(E, d1[i], d2[i], M1[i], M2[i]);
+        bool inlier = (r2 < sq_threshold);
+        if (inlier) {
+            const bool cheirality = check_cheirality(pose, d1[i], d2[i], 0.01);
+            if (cheirality) inlier_count++;
+            else inlier = false;
+        }
+        (*inliers)[i] = inlier;
+    }
+    return (int)inlier_count;
+}
 // utils.cc:204-239
 double compute_sampson_msac_score(const Mat3 &F, const std::vector<Vec2> &x1, const std::vector<Vec2> &x2,
                                   double sq_threshold, size_t *inlier_count) {
@@ -518,6 +581,50 @@ struct RelativePoseEstimator {
     std::vector<size_t> sample;
     Counters *cnt;
 };
+// estimators/relative_pose.h:71-106, relative_pose.cc:88-108
+struct CameraRelativePoseEstimator {
+    CameraRelativePoseEstimator(const RansacOptions &ropt, double max_err, const std::vector<Vec2> &a,
+                                const std::vector<Vec2> &b, const Camera &cam1, const Camera &cam2, Counters *c)
+        : sample_sz(5), num_data(a.size()), max_error(max_err), sampler(num_data, sample_sz, ropt), cnt(c) {
+        x1s.resize(sample_sz);
+        x2s.resize(sample_sz);
+        sample.resize(sample_sz);
+        d1.resize(num_data);
+        d2.resize(num_data);
+        M1.resize(num_data);
+        M2.resize(num_data);
+        for (size_t k = 0; k < num_data; ++k) { // Camera::unproject_with_jac vector wrapper (camera_models.cc:271-296)
+            cam1.unproject_with_jac(a[k], &d1[k], M1[k].m);
+            cam2.unproject_with_jac(b[k], &d2[k], M2[k].m);
+        }
+    }
+    void generate_models(std::vector<CameraPose> *models) {
+        models->clear();
+        sampler.generate_sample(&sample);
+        for (size_t k = 0; k < sample_sz; ++k) {
+            x1s[k] = d1[sample[k]];
+            x2s[k] = d2[sample[k]];
+        }
+        relpose_5pt(x1s, x2s, models);
+        if (cnt) cnt->samples++;
+    }
+    double score_model(const CameraPose &pose, size_t *inlier_count) const {
+        if (cnt) { cnt->hypotheses++; cnt->scored_corrs += num_data; }
+        return compute_tangent_sampson_msac_score(pose, d1, d2, M1, M2, max_error * max_error, inlier_count);
+    }
+    void refine_model(CameraPose *pose) const {
+        Timer tm;
+        refine_relpose(d1, d2, M1, M2, pose, lo_bundle_options(max_error));
+        if (cnt) { cnt->lo_calls++; cnt->lo_seconds += tm.sec(); }
+    }
+    size_t sample_sz, num_data;
+    double max_error;
+    RandomSampler sampler;
+    std::vector<Vec3> x1s, x2s, d1, d2;
+    std::vector<Mat32> M1, M2;
+    std::vector<size_t> sample;
+    Counters *cnt;
+};
 // estimators/relative_pose.{h,cc}:309-336 / :384-412
 struct FundamentalEstimator {
     FundamentalEstimator(const RansacOptions &ropt, double max_err, bool rfc, const std::vector<Vec2> &a,
@@ -623,6 +730,16 @@ RansacStats ransac_relpose(const std::vector<Vec2> &x1, const std::vector<Vec2> 
     RelativePoseEstimator est(ropt, max_error, x1, x2, cnt);
     RansacStats stats = ransac<RelativePoseEstimator, CameraPose>(est, ropt, best);
     get_inliers(*best, x1, x2, max_error * max_error, inliers);
+    return stats;
+}
+// ransac.cc:155-168 (points in the pixel units of the two cameras; tangent Sampson error)
+RansacStats ransac_relpose(const std::vector<Vec2> &x1, const std::vector<Vec2> &x2, const Camera &camera1,
+                           const Camera &camera2, const RansacOptions &ropt, double max_error, CameraPose *best,
+                           std::vector<char> *inliers, Counters *cnt) {
+    *best = CameraPose(); // :159-160 resets unconditionally
+    CameraRelativePoseEstimator est(ropt, max_error, x1, x2, camera1, camera2, cnt);
+    RansacStats stats = ransac<CameraRelativePoseEstimator, CameraPose>(est, ropt, best);
+    get_tangent_sampson_inliers(*best, est.d1, est.d2, est.M1, est.M2, max_error * max_error, inliers);
     return stats;
 }
 // ransac.cc:248-262
