@@ -88,12 +88,21 @@ typedef struct plb_counters {
     double gpu_seconds_score;  /* CUDA-event time of the scoring / screening kernels alone (part of gpu_seconds) */
 } plb_counters;
 
-/* misc/camera_models.h:59-157 Camera, restricted to the models the path needs (others -> PLB_ERR_NYI) */
-enum { PLB_CAMERA_NULL = -1, PLB_CAMERA_SIMPLE_PINHOLE = 0, PLB_CAMERA_PINHOLE = 1 };
+/* misc/camera_models.h:39-157 Camera, restricted to the six models on the path (others -> PLB_ERR_NYI, like the
+ * reference's "NYI" throw, camera_models.cc:184-185).  Ids are the reference's CameraModelId values. */
+enum {
+    PLB_CAMERA_NULL = -1,
+    PLB_CAMERA_SIMPLE_PINHOLE = 0, /* f, cx, cy */
+    PLB_CAMERA_PINHOLE = 1,        /* fx, fy, cx, cy */
+    PLB_CAMERA_SIMPLE_RADIAL = 2,  /* f, cx, cy, k */
+    PLB_CAMERA_RADIAL = 3,         /* f, cx, cy, k1, k2 */
+    PLB_CAMERA_OPENCV = 4          /* fx, fy, cx, cy, k1, k2, p1, p2 */
+};
 typedef struct plb_camera {
     int32_t model_id;
     int32_t width, height;
-    double params[4]; /* SIMPLE_PINHOLE: f,cx,cy ; PINHOLE: fx,fy,cx,cy ; NULL: none */
+    int32_t reserved;
+    double params[8];
 } plb_camera;
 
 void plb_ransac_opt_default(plb_ransac_opt *o);
@@ -117,16 +126,25 @@ int plb_ransac_fundamental(const double *x1_xy, const double *x2_xy, size_t n, c
 int plb_ransac_homography(const double *x1_xy, const double *x2_xy, size_t n, const plb_ransac_opt *opt,
                           double max_error, double H_inout[9], char *inliers, plb_ransac_stats *stats,
                           plb_counters *counters);
+/* robust/ransac.h:65-67, ransac.cc:155-168: relative pose with camera models, scored with the tangent Sampson error
+ * on the unprojected bearings (CameraRelativePoseEstimator); x1/x2 and max_error in the pixel units of the cameras.
+ * The start pose is reset to identity (ransac.cc:159-160). */
+int plb_ransac_relpose_cameras(const double *x1_px, const double *x2_px, size_t n, const plb_camera *camera1,
+                               const plb_camera *camera2, const plb_ransac_opt *opt, double max_error,
+                               double pose_out[7], char *inliers, plb_ransac_stats *stats, plb_counters *counters);
 
-/* ---- PoseLib/robust.h:45-46,68-70,112-113,133-134 (pixel coordinates + cameras) ------------------- */
+/* ---- PoseLib/robust.h:45-46,68-70,112-113,133-134 (pixel coordinates + cameras) -------------------
+ * The camera pre-step (Camera::unproject / unproject_with_jac of every point, robust.cc:40-43,255-266,287-292) runs
+ * on the device.  tangent_sampson = RelativePoseOptions::tangent_sampson (types.h:140). */
 int plb_estimate_absolute_pose(const double *points2D, const double *points3D, size_t n,
                                const plb_ransac_opt *ransac, const plb_bundle_opt *bundle, double max_error,
                                const plb_camera *camera, double pose_inout[7], char *inliers,
                                plb_ransac_stats *stats, plb_counters *counters);
 int plb_estimate_relative_pose(const double *x1, const double *x2, size_t n, const plb_camera *camera1,
                                const plb_camera *camera2, const plb_ransac_opt *ransac,
-                               const plb_bundle_opt *bundle, double max_error, double pose_inout[7], char *inliers,
-                               plb_ransac_stats *stats, plb_counters *counters);
+                               const plb_bundle_opt *bundle, double max_error, int tangent_sampson,
+                               double pose_inout[7], char *inliers, plb_ransac_stats *stats,
+                               plb_counters *counters);
 int plb_estimate_fundamental(const double *x1, const double *x2, size_t n, const plb_ransac_opt *ransac,
                              const plb_bundle_opt *bundle, double max_error, int real_focal_check,
                              double F_inout[9], char *inliers, plb_ransac_stats *stats, plb_counters *counters);
@@ -156,6 +174,10 @@ int plb_bundle_adjust(const double *x_xy, const double *X_xyz, size_t n, double 
                       const plb_bundle_opt *opt, double bundle_stats_out[3]);
 int plb_refine_relpose(const double *x1_xy, const double *x2_xy, size_t n, double pose_inout[7],
                        const plb_bundle_opt *opt, double bundle_stats_out[3]);
+/* bundle.h refine_relpose(x1, x2, ImagePair*, opt) with fixed intrinsics (bundle.cc:237-247): tangent Sampson refiner */
+int plb_refine_relpose_cameras(const double *x1_px, const double *x2_px, size_t n, const plb_camera *camera1,
+                               const plb_camera *camera2, double pose_inout[7], const plb_bundle_opt *opt,
+                               double bundle_stats_out[3]);
 int plb_refine_fundamental(const double *x1_xy, const double *x2_xy, size_t n, double F_inout[9],
                            const plb_bundle_opt *opt, double bundle_stats_out[3]);
 int plb_refine_homography(const double *x1_xy, const double *x2_xy, size_t n, double H_inout[9],

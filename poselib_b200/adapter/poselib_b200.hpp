@@ -76,13 +76,14 @@ template <typename RansacStats> inline RansacStats from_c(const plb_ransac_stats
     r.model_score = s.model_score;
     return r;
 }
-// misc/camera_models.h:59-157 -> plb_camera (pinhole family only; others raise NYI inside the library)
+// misc/camera_models.h:59-157 -> plb_camera (six models on the path; others raise NYI inside the library)
 template <typename Camera> inline plb_camera camera_to_c(const Camera &cam) {
     plb_camera c;
     c.model_id = cam.model_id;
     c.width = cam.width;
     c.height = cam.height;
-    for (int i = 0; i < 4; ++i) c.params[i] = (i < (int)cam.params.size()) ? cam.params[i] : 0.0;
+    c.reserved = 0;
+    for (int i = 0; i < 8; ++i) c.params[i] = (i < (int)cam.params.size()) ? cam.params[i] : 0.0;
     if (cam.params.empty()) c.model_id = PLB_CAMERA_NULL; // "empty camera assumed to be identity" camera_models.cc:305-307
     return c;
 }
@@ -125,6 +126,21 @@ RansacStats ransac_relpose(const std::vector<P2> &x1, const std::vector<P2> &x2,
     best_inliers->resize(x1.size());
     detail::check(plb_ransac_relpose(detail::raw(x1), detail::raw(x2), x1.size(), &ro, opt.max_error, m,
                                      best_inliers->data(), &st, nullptr));
+    detail::pose_from(m, best_model);
+    return detail::from_c<RansacStats>(st);
+}
+// ransac_relpose(x1, x2, camera1, camera2, RelativePoseOptions, CameraPose*, inliers*)   robust/ransac.h:65-67
+template <typename RansacStats, typename P2, typename Camera, typename Opt, typename Pose>
+RansacStats ransac_relpose(const std::vector<P2> &x1, const std::vector<P2> &x2, const Camera &camera1,
+                           const Camera &camera2, const Opt &opt, Pose *best_model, std::vector<char> *best_inliers) {
+    static_assert(sizeof(P2) == 2 * sizeof(double), "dense point layout required");
+    double m[7];
+    plb_ransac_opt ro = detail::to_c(opt.ransac);
+    plb_camera c1 = detail::camera_to_c(camera1), c2 = detail::camera_to_c(camera2);
+    plb_ransac_stats st;
+    best_inliers->resize(x1.size());
+    detail::check(plb_ransac_relpose_cameras(detail::raw(x1), detail::raw(x2), x1.size(), &c1, &c2, &ro, opt.max_error,
+                                             m, best_inliers->data(), &st, nullptr));
     detail::pose_from(m, best_model);
     return detail::from_c<RansacStats>(st);
 }
@@ -175,7 +191,6 @@ RansacStats estimate_absolute_pose(const std::vector<P2> &points2D, const std::v
 template <typename RansacStats, typename P2, typename Camera, typename Opt, typename Pose>
 RansacStats estimate_relative_pose(const std::vector<P2> &x1, const std::vector<P2> &x2, const Camera &camera1,
                                    const Camera &camera2, const Opt &opt, Pose *pose, std::vector<char> *inliers) {
-    if (opt.tangent_sampson) throw std::runtime_error("poselib_b200: NYI (tangent Sampson is row N1 of SURVEY.md §8f)");
     double m[7];
     detail::pose_to(*pose, m);
     plb_ransac_opt ro = detail::to_c(opt.ransac);
@@ -184,7 +199,8 @@ RansacStats estimate_relative_pose(const std::vector<P2> &x1, const std::vector<
     plb_ransac_stats st;
     inliers->resize(x1.size());
     detail::check(plb_estimate_relative_pose(detail::raw(x1), detail::raw(x2), x1.size(), &c1, &c2, &ro, &bo,
-                                             opt.max_error, m, inliers->data(), &st, nullptr));
+                                             opt.max_error, opt.tangent_sampson ? 1 : 0, m, inliers->data(), &st,
+                                             nullptr));
     detail::pose_from(m, pose);
     return detail::from_c<RansacStats>(st);
 }

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libposelib_b200.so")
 PLB_OK, PLB_ERR_CUDA, PLB_ERR_ARG, PLB_ERR_NYI = 0, -1, -2, -3
 KIND = {"pnp": 0, "relpose": 1, "fundamental": 2, "homography": 3}
 LOSS = {"TRIVIAL": 0, "TRUNCATED": 1, "HUBER": 2, "CAUCHY": 3}
-CAMERA = {"NULL": -1, "SIMPLE_PINHOLE": 0, "PINHOLE": 1}
+CAMERA = {"NULL": -1, "SIMPLE_PINHOLE": 0, "PINHOLE": 1, "SIMPLE_RADIAL": 2, "RADIAL": 3, "OPENCV": 4}
 
 
 class PoseLibB200Error(RuntimeError):
@@ -73,12 +73,13 @@ class Counters(C.Structure):
 
 
 class Camera(C.Structure):
-    _fields_ = [("model_id", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("params", C.c_double * 4)]
+    _fields_ = [("model_id", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("reserved", C.c_int32),
+                ("params", C.c_double * 8)]
 
     def __init__(self, model="PINHOLE", params=(1.0, 1.0, 0.0, 0.0), width=0, height=0):
         mid = CAMERA[model] if isinstance(model, str) else int(model)
-        p = list(params) + [0.0] * (4 - len(params))
-        super().__init__(mid, width, height, (C.c_double * 4)(*p))
+        p = list(params)[:8] + [0.0] * (8 - len(params))
+        super().__init__(mid, width, height, 0, (C.c_double * 8)(*p))
 
 
 class Problem(C.Structure):
@@ -90,11 +91,12 @@ class Problem(C.Structure):
 
 EXPORTS = [
     "plb_ransac_opt_default", "plb_bundle_opt_default", "plb_last_error", "plb_device_count", "plb_set_device",
-    "plb_set_mode", "plb_ransac_pnp", "plb_ransac_relpose", "plb_ransac_fundamental", "plb_ransac_homography",
+    "plb_set_mode", "plb_ransac_pnp", "plb_ransac_relpose", "plb_ransac_relpose_cameras", "plb_ransac_fundamental",
+    "plb_ransac_homography",
     "plb_estimate_absolute_pose", "plb_estimate_relative_pose", "plb_estimate_fundamental",
     "plb_estimate_homography", "plb_p3p_batch", "plb_relpose_5pt_batch", "plb_relpose_5pt_poses_batch",
     "plb_relpose_7pt_batch", "plb_homography_4pt_batch", "plb_ransac_batch", "plb_bundle_adjust",
-    "plb_refine_relpose", "plb_refine_fundamental", "plb_refine_homography", "plb_resident_create",
+    "plb_refine_relpose", "plb_refine_relpose_cameras", "plb_refine_fundamental", "plb_refine_homography", "plb_resident_create",
     "plb_resident_free",
 ]
 
@@ -173,7 +175,33 @@ def ransac(kind, a, b, ropt, max_error, init=None, rfc=False):
     return {"model": _model_out(kind, m), "inliers": mask[:n], "stats": st.as_dict(), "counters": cn.as_dict()}
 
 
-def estimate(kind, a, b, ropt, bopt, max_error, cam1=None, cam2=None, init=None, rfc=False):
+def ransac_relpose_cameras(x1, x2, cam1, cam2, ropt, max_error):
+    """ransac_relpose with camera models (tangent Sampson error, ransac.cc:155-168); points in pixels."""
+    n = len(x1)
+    aa, ap = _d(x1)
+    ba, bp = _d(x2)
+    mask = np.zeros(max(n, 1), dtype=np.int8)
+    st, cn = RansacStats(), Counters()
+    m = _init_model("relpose", None)
+    _check(_lib.plb_ransac_relpose_cameras(ap, bp, C.c_size_t(n), C.byref(cam1), C.byref(cam2), C.byref(ropt),
+                                           C.c_double(max_error), m.ctypes.data_as(_P),
+                                           mask.ctypes.data_as(C.c_char_p), C.byref(st), C.byref(cn)))
+    return {"model": _model_out("relpose", m), "inliers": mask[:n], "stats": st.as_dict(), "counters": cn.as_dict()}
+
+
+def refine_relpose_cameras(pose, x1, x2, cam1, cam2, bopt):
+    """refine_relpose(x1, x2, ImagePair*, opt) with fixed intrinsics (bundle.cc:237-247)."""
+    n = len(x1)
+    aa, ap = _d(x1)
+    ba, bp = _d(x2)
+    m = _init_model("relpose", pose)
+    bs = np.zeros(3)
+    _check(_lib.plb_refine_relpose_cameras(ap, bp, C.c_size_t(n), C.byref(cam1), C.byref(cam2),
+                                           m.ctypes.data_as(_P), C.byref(bopt), bs.ctypes.data_as(_P)))
+    return _model_out("relpose", m), bs
+
+
+def estimate(kind, a, b, ropt, bopt, max_error, cam1=None, cam2=None, init=None, rfc=False, tangent_sampson=False):
     """estimate_absolute_pose / estimate_relative_pose / estimate_fundamental / estimate_homography (robust.h)."""
     n = len(a)
     aa, ap = _d(a)
@@ -190,7 +218,8 @@ def estimate(kind, a, b, ropt, bopt, max_error, cam1=None, cam2=None, init=None,
                                              C.c_double(max_error), C.byref(c1), mp, mk, C.byref(st), C.byref(cn))
     elif kind == "relpose":
         rc = _lib.plb_estimate_relative_pose(ap, bp, C.c_size_t(n), C.byref(c1), C.byref(c2), C.byref(ropt),
-                                             C.byref(bopt), C.c_double(max_error), mp, mk, C.byref(st), C.byref(cn))
+                                             C.byref(bopt), C.c_double(max_error), int(tangent_sampson), mp, mk,
+                                             C.byref(st), C.byref(cn))
     elif kind == "fundamental":
         rc = _lib.plb_estimate_fundamental(ap, bp, C.c_size_t(n), C.byref(ropt), C.byref(bopt),
                                            C.c_double(max_error), int(rfc), mp, mk, C.byref(st), C.byref(cn))

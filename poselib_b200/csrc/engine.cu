@@ -287,6 +287,7 @@ static LmParams lo_params(int kind, double max_error) {
     p.subset_mode = (kind == KIND_RELPOSE) ? 1 : 0;
     p.subset_sq_thr = 5 * (max_error * max_error); // estimators/relative_pose.cc:70
     p.use_camera = 0;
+    p.cam.model = CAMM_NULL;
     p.score_after = 1;
     return p;
 }
@@ -303,6 +304,7 @@ static LmParams bundle_params(const plb_bundle_opt &b) {
     p.min_lambda = b.min_lambda;
     p.max_lambda = b.max_lambda;
     p.subset_mode = 2;
+    p.cam.model = CAMM_NULL;
     p.score_after = 0;
     return p;
 }
@@ -311,9 +313,9 @@ struct FinalPolish { // the post-RANSAC refinement of PoseLib/robust.cc (estimat
     bool enabled = false;
     plb_bundle_opt bundle;
     size_t min_inliers = 0; // run iff stats.num_inliers > min_inliers
-    // pnp only: refine in pixel*scale coordinates with the rescaled pinhole camera (robust.cc:103-123)
+    // pnp only: refine in pixel*scale coordinates with the rescaled camera (robust.cc:103-123)
     const double *px_scaled = nullptr; // 2n doubles (AoS) or null
-    double cam[4] = {1, 1, 0, 0};
+    CamDev cam{CAMM_NULL, 0, {0, 0, 0, 0, 0, 0, 0, 0}};
 };
 
 // One LO-RANSAC problem handed to the group engine (points already calibrated / normalised).
@@ -330,6 +332,10 @@ struct Task {
     plb_counters *cnt_out = nullptr;
     FinalPolish polish;
     const Resident *res = nullptr;
+    // camera pre-step fused into the layout kernel (TransposeDesc modes): 0 none, 1 unproject to 2D, 2 tangent Sampson
+    int pre_mode = 0;
+    double pre_scale = 1.0;
+    CamDev cam_a{CAMM_NULL, 0, {0, 0, 0, 0, 0, 0, 0, 0}}, cam_b{CAMM_NULL, 0, {0, 0, 0, 0, 0, 0, 0, 0}};
 };
 
 // per-problem serial state of the reference loop (ransac_impl.h:99-104,157-201)
@@ -367,7 +373,8 @@ static void update_dynamic(PState &S, int K) { // ransac_impl.h:150-153
 static int run_group(int kind, std::vector<Task *> &tasks) {
     Engine &E = *engine();
     const int K = kind_sample_size(kind), MAXM = kind_max_models(kind), MSZ = kind_model_size(kind);
-    const int b_dim = (kind == KIND_PNP) ? 3 : 2, n_arr = 2 + b_dim;
+    // in_arr: doubles per correspondence in the caller layout; n_arr: SoA arrays resident per correspondence
+    const int b_dim = (kind == KIND_PNP) ? 3 : 2, in_arr = 2 + b_dim, n_arr = (kind == KIND_RELPOSE_TS) ? TS_ARRAYS : in_arr;
     const int NP = (int)tasks.size();
     std::vector<PState> PS(NP);
     bool any_points = false;
@@ -429,7 +436,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
     for (PState &S : PS) {
         if (S.n == 0) continue;
         if (!S.t->res) {
-            in_doubles += (size_t)n_arr * S.n;
+            in_doubles += (size_t)in_arr * S.n;
             soa_elems += (size_t)n_arr * S.n_pad;
             ++n_up;
         }
@@ -461,6 +468,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             P.kind = kind;
             P.sq_thr = S.t->max_error * S.t->max_error;
             P.rfc = S.t->rfc;
+            P.n_pad = S.n_pad;
             if (S.n == 0) continue;
             if (S.t->res) {
                 for (int c = 0; c < n_arr; ++c) {
@@ -479,12 +487,19 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 D.n = S.n;
                 D.n_pad = S.n_pad;
                 D.b_dim = b_dim;
-                D.reserved = 0;
-                for (int c = 0; c < n_arr; ++c) {
-                    P.p[c] = D.s64 + (size_t)c * S.n_pad;
-                    P.f[c] = D.s32 + (size_t)c * S.n_pad;
+                D.mode = (kind == KIND_RELPOSE_TS) ? 2 : S.t->pre_mode;
+                D.scale = S.t->pre_scale;
+                D.cam_a = S.t->cam_a;
+                D.cam_b = S.t->cam_b;
+                if (kind == KIND_RELPOSE_TS) {
+                    P.ts = D.s64;
+                } else {
+                    for (int c = 0; c < n_arr; ++c) {
+                        P.p[c] = D.s64 + (size_t)c * S.n_pad;
+                        P.f[c] = D.s32 + (size_t)c * S.n_pad;
+                    }
                 }
-                in_off += (size_t)n_arr * S.n;
+                in_off += (size_t)in_arr * S.n;
                 soa_off += (size_t)n_arr * S.n_pad;
             }
             if (kind == KIND_PNP && S.t->polish.enabled && S.t->polish.px_scaled) {
@@ -617,9 +632,10 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         if (S.enough) S.sampler = new Sampler(S.t->n, (size_t)K, S.t->opt);
     }
     const size_t CHUNK_MAX = 16384, ROUND_MAX = 32768, S_TOT_MAX = 262144;
-    const int mode = g_mode.load(); // 0 exact, 1 fast (fp32 screen + fp64 confirmation of candidates)
+    // 0 exact, 1 fast (fp32 screen + fp64 confirmation of candidates); the tangent-Sampson kind has no fp32 copy
+    const int mode = (kind == KIND_RELPOSE_TS) ? 0 : g_mode.load();
     std::vector<int> cand_slots;
-    int cap_factor = (kind == KIND_RELPOSE) ? 8 : MAXM;
+    int cap_factor = kind_is_relpose(kind) ? 8 : MAXM;
     std::vector<int> act;
     for (;;) {
         act.clear();
@@ -727,7 +743,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         }
         out.s5_blk = out.s5_cpoly = out.s5_roots = nullptr;
         out.s5_nroots = nullptr;
-        if (kind == KIND_RELPOSE) { // phase buffers of the 3-kernel 5-point solver
+        if (kind_is_relpose(kind)) { // phase buffers of the 3-kernel 5-point solver
             if ((rc = E.s5_blk.ensure(total * 105)) || (rc = E.s5_cpoly.ensure(total * 11)) ||
                 (rc = E.s5_roots.ensure(total * 10)) || (rc = E.s5_nroots.ensure(total)))
                 return rc;
@@ -739,7 +755,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         PLB_CUDA(cudaEventRecord(E.ev0, st));
         launch_hypotheses(kind, R, E.work.p, out, mode, max_n_pad, st, E.ev2);
         PLB_CUDA(cudaEventRecord(E.ev1, st));
-        E.launches += (kind == KIND_RELPOSE) ? 4 : 2; // k_solve (or k5_prep + k5_roots + k5_back) + k_score
+        E.launches += kind_is_relpose(kind) ? 4 : 2; // k_solve (or k5_prep + k5_roots + k5_back) + k_score
         PLB_CUDA(cudaMemcpyAsync(E.h_work.p, E.work.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
         if ((rc = sync_timed(nullptr))) return rc;
         if (E.h_work.p[2] != 0) { // model list overflow: redo the round with the worst-case capacity (no state was touched)
@@ -1004,7 +1020,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 if (S.polish_pidx >= 0) {
                     J.pidx = S.polish_pidx;
                     J.prm.use_camera = 1;
-                    for (int c = 0; c < 4; ++c) J.prm.cam[c] = S.t->polish.cam[c];
+                    J.prm.cam = S.t->polish.cam;
                 }
             }
             if ((rc = launch_lm_jobs(npol, false, 0))) return rc;
@@ -1037,8 +1053,14 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
 // Single-problem convenience used by the plb_ransac_* / plb_estimate_* entry points.
 static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, const plb_ransac_opt &opt,
                       double max_error, int rfc, double *model, char *inliers, plb_ransac_stats *stats_out,
-                      plb_counters *cnt_out, const FinalPolish &polish, const Resident *res = nullptr) {
+                      plb_counters *cnt_out, const FinalPolish &polish, const Resident *res = nullptr,
+                      int pre_mode = 0, const CamDev *cam_a = nullptr, const CamDev *cam_b = nullptr,
+                      double pre_scale = 1.0) {
     Task t;
+    t.pre_mode = pre_mode;
+    t.pre_scale = pre_scale;
+    if (cam_a) t.cam_a = *cam_a;
+    if (cam_b) t.cam_b = *cam_b;
     t.kind = kind;
     t.a = a;
     t.b = b;
@@ -1058,15 +1080,17 @@ static int run_ransac(int kind, const double *a, const double *b, size_t n_pts, 
 
 // One LM refinement over all n points (robust/bundle.cc:84-112,206-222,313-333,394-411)
 static int run_refine(int kind, const double *a, const double *b, size_t n_pts, double *model,
-                      const plb_bundle_opt &bopt, double *bstats) {
+                      const plb_bundle_opt &bopt, double *bstats, const CamDev *cam_a = nullptr,
+                      const CamDev *cam_b = nullptr) {
     if (n_pts == 0) return PLB_OK;
     Engine &E = *engine();
     int rc = E.init();
     if (rc != PLB_OK) return rc;
     cudaStream_t st = E.stream;
     const int n = (int)n_pts, n_pad = (n + 31) & ~31;
-    const int b_dim = (kind == KIND_PNP) ? 3 : 2, n_arr = 2 + b_dim, MSZ = kind_model_size(kind);
-    if ((rc = E.h_in.ensure((size_t)n_arr * n)) || (rc = E.in.ensure((size_t)n_arr * n)) ||
+    const int b_dim = (kind == KIND_PNP) ? 3 : 2, in_arr = 2 + b_dim, MSZ = kind_model_size(kind);
+    const int n_arr = (kind == KIND_RELPOSE_TS) ? TS_ARRAYS : in_arr;
+    if ((rc = E.h_in.ensure((size_t)in_arr * n)) || (rc = E.in.ensure((size_t)in_arr * n)) ||
         (rc = E.soa64.ensure((size_t)n_arr * n_pad)) || (rc = E.soa32.ensure((size_t)n_arr * n_pad)) ||
         (rc = E.lm_in.ensure(9)) || (rc = E.h_lm_in.ensure(9)) || (rc = E.h_lm_out.ensure(1)) ||
         (rc = E.probs.ensure(1)) || (rc = E.h_probs.ensure(1)) || (rc = E.tdesc.ensure(1)) || (rc = E.h_tdesc.ensure(1)) ||
@@ -1074,7 +1098,7 @@ static int run_refine(int kind, const double *a, const double *b, size_t n_pts, 
         return rc;
     std::memcpy(E.h_in.p, a, sizeof(double) * 2 * n);
     std::memcpy(E.h_in.p + 2 * (size_t)n, b, sizeof(double) * b_dim * n);
-    PLB_CUDA(cudaMemcpyAsync(E.in.p, E.h_in.p, sizeof(double) * (size_t)n_arr * n, cudaMemcpyHostToDevice, st));
+    PLB_CUDA(cudaMemcpyAsync(E.in.p, E.h_in.p, sizeof(double) * (size_t)in_arr * n, cudaMemcpyHostToDevice, st));
     TransposeDesc &D = E.h_tdesc.p[0];
     D.a = E.in.p;
     D.b = E.in.p + 2 * (size_t)n;
@@ -1083,13 +1107,22 @@ static int run_refine(int kind, const double *a, const double *b, size_t n_pts, 
     D.n = n;
     D.n_pad = n_pad;
     D.b_dim = b_dim;
-    D.reserved = 0;
+    D.mode = (kind == KIND_RELPOSE_TS) ? 2 : 0;
+    D.scale = 1.0;
+    D.cam_a.model = D.cam_b.model = CAMM_NULL;
+    if (cam_a) D.cam_a = *cam_a;
+    if (cam_b) D.cam_b = *cam_b;
     ProblemDev &P = E.h_probs.p[0];
     std::memset(&P, 0, sizeof(P));
-    for (int c = 0; c < n_arr; ++c) {
-        P.p[c] = E.soa64.p + (size_t)c * n_pad;
-        P.f[c] = E.soa32.p + (size_t)c * n_pad;
+    if (kind == KIND_RELPOSE_TS) {
+        P.ts = E.soa64.p;
+    } else {
+        for (int c = 0; c < n_arr; ++c) {
+            P.p[c] = E.soa64.p + (size_t)c * n_pad;
+            P.f[c] = E.soa32.p + (size_t)c * n_pad;
+        }
     }
+    P.n_pad = n_pad;
     P.n = n;
     P.kind = kind;
     P.sq_thr = 0.0;
@@ -1212,23 +1245,38 @@ static double normalize_points(std::vector<double> &x1, std::vector<double> &x2,
     return scale;
 }
 
-// Camera::unproject + hnormalized for the pinhole family (misc/camera_models.cc:176-188,668-761; .h:98-102)
-static int camera_params(const plb_camera *c, double out[4]) {
-    if (!c) {
-        out[0] = out[1] = 1; out[2] = out[3] = 0;
-        return PLB_OK;
-    }
+// plb_camera -> CamDev; models outside the six on the path are rejected like Camera::unproject's "NYI"
+// (misc/camera_models.cc:176-188)
+static int camera_dev(const plb_camera *c, CamDev *out) {
+    out->model = CAMM_NULL;
+    out->reserved = 0;
+    for (int i = 0; i < 8; ++i) out->p[i] = 0.0;
+    if (!c || c->model_id == PLB_CAMERA_NULL) return PLB_OK;
+    int np = 0;
     switch (c->model_id) {
-    case PLB_CAMERA_NULL: out[0] = out[1] = 1; out[2] = out[3] = 0; return PLB_OK;
-    case PLB_CAMERA_SIMPLE_PINHOLE: out[0] = out[1] = c->params[0]; out[2] = c->params[1]; out[3] = c->params[2]; return PLB_OK;
-    case PLB_CAMERA_PINHOLE: out[0] = c->params[0]; out[1] = c->params[1]; out[2] = c->params[2]; out[3] = c->params[3]; return PLB_OK;
+    case PLB_CAMERA_SIMPLE_PINHOLE: np = 3; break;
+    case PLB_CAMERA_PINHOLE: np = 4; break;
+    case PLB_CAMERA_SIMPLE_RADIAL: np = 4; break;
+    case PLB_CAMERA_RADIAL: np = 5; break;
+    case PLB_CAMERA_OPENCV: np = 8; break;
     default: g_err = "NYI: camera model not supported by the B200 path (undistort on the host first)"; return PLB_ERR_NYI;
     }
+    out->model = c->model_id;
+    for (int i = 0; i < np; ++i) out->p[i] = c->params[i];
+    return PLB_OK;
 }
-static double camera_focal(const plb_camera *c, const double cp[4]) { // Camera::focal() camera_models.cc:304-324
-    if (!c || c->model_id == PLB_CAMERA_NULL) return 1.0;
-    if (c->model_id == PLB_CAMERA_SIMPLE_PINHOLE) return 0.0 + cp[0] / 1;
-    return 0.0 + cp[0] / 2 + cp[1] / 2;
+static double camera_focal(const CamDev &c) { // Camera::focal() camera_models.cc:304-324
+    switch (c.model) {
+    case CAMM_NULL: return 1.0;
+    case CAMM_PINHOLE:
+    case CAMM_OPENCV: return 0.0 + c.p[0] / 2 + c.p[1] / 2;
+    default: return 0.0 + c.p[0] / 1;
+    }
+}
+static void camera_rescale(CamDev &c, double scale) { // Camera::rescale camera_models.cc:432-454
+    if (c.model == CAMM_NULL) return;
+    const int k = (c.model == CAMM_PINHOLE || c.model == CAMM_OPENCV) ? 4 : 3; // focal_idx then principal_point_idx
+    for (int i = 0; i < k; ++i) c.p[i] *= scale;
 }
 
 } // namespace plb
@@ -1303,6 +1351,19 @@ int plb_ransac_relpose(const double *x1, const double *x2, size_t n, const plb_r
     if (int r = check_ptrs(x1, x2, opt, pose, n)) return r;
     return run_ransac(KIND_RELPOSE, x1, x2, n, *opt, max_error, 0, pose, inliers, stats, counters, FinalPolish());
 }
+// robust/ransac.cc:155-168: points in the pixel units of the two cameras, tangent Sampson error
+int plb_ransac_relpose_cameras(const double *x1, const double *x2, size_t n, const plb_camera *camera1,
+                               const plb_camera *camera2, const plb_ransac_opt *opt, double max_error, double pose[7],
+                               char *inliers, plb_ransac_stats *stats, plb_counters *counters) {
+    if (int r = check_ptrs(x1, x2, opt, pose, n)) return r;
+    CamDev c1, c2;
+    if (int r = camera_dev(camera1, &c1)) return r;
+    if (int r = camera_dev(camera2, &c2)) return r;
+    pose[0] = 1.0; // :159-160
+    for (int i = 1; i < 7; ++i) pose[i] = 0.0;
+    return run_ransac(KIND_RELPOSE_TS, x1, x2, n, *opt, max_error, 0, pose, inliers, stats, counters, FinalPolish(),
+                      nullptr, 2, &c1, &c2, 1.0);
+}
 int plb_ransac_fundamental(const double *x1, const double *x2, size_t n, const plb_ransac_opt *opt, double max_error,
                            int real_focal_check, double F[9], char *inliers, plb_ransac_stats *stats,
                            plb_counters *counters) {
@@ -1316,7 +1377,8 @@ int plb_ransac_homography(const double *x1, const double *x2, size_t n, const pl
     return run_ransac(KIND_HOMOG, x1, x2, n, *opt, max_error, 0, H, inliers, stats, counters, FinalPolish());
 }
 
-// PoseLib/robust.cc:36-126 (no focal estimation)
+// PoseLib/robust.cc:36-126 (no focal estimation).  The camera pre-step (Camera::unproject of every 2D point) runs
+// on the device, fused into the layout kernel.
 int plb_estimate_absolute_pose(const double *points2D, const double *points3D, size_t n, const plb_ransac_opt *ransac,
                                const plb_bundle_opt *bundle, double max_error, const plb_camera *camera,
                                double pose[7], char *inliers, plb_ransac_stats *stats, plb_counters *counters) {
@@ -1325,58 +1387,56 @@ int plb_estimate_absolute_pose(const double *points2D, const double *points3D, s
         g_err = "null bundle options";
         return PLB_ERR_ARG;
     }
-    double cp[4];
-    if (int r = camera_params(camera, cp)) return r;
-    std::vector<double> norm(2 * n), px(2 * n);
-    for (size_t k = 0; k < n; ++k) {
-        norm[2 * k] = (points2D[2 * k] - cp[2]) / cp[0];
-        norm[2 * k + 1] = (points2D[2 * k + 1] - cp[3]) / cp[1];
-    }
-    const double scale = 1.0 / camera_focal(camera, cp);
+    CamDev cam;
+    if (int r = camera_dev(camera, &cam)) return r;
+    const double scale = 1.0 / camera_focal(cam);
     FinalPolish fp;
     fp.enabled = true;
     fp.bundle = *bundle;
     fp.bundle.loss_scale = bundle->loss_scale * scale;
     fp.min_inliers = 3;
-    for (size_t k = 0; k < 2 * n; ++k) px[k] = points2D[k] * scale;
-    fp.px_scaled = px.data();
-    for (int i = 0; i < 4; ++i) fp.cam[i] = cp[i] * scale; // Camera::rescale (camera_models.cc:432-454)
-    if (camera == nullptr || camera->model_id == PLB_CAMERA_NULL) {
-        fp.cam[0] = fp.cam[1] = 1.0; // empty params: rescale is a no-op and the null projection is used
-        fp.cam[2] = fp.cam[3] = 0.0;
-        fp.px_scaled = nullptr;
+    std::vector<double> px;
+    if (cam.model != CAMM_NULL) { // the polish runs on pixels*scale with the rescaled camera (robust.cc:103-123)
+        px.resize(2 * n);
+        for (size_t k = 0; k < 2 * n; ++k) px[k] = points2D[k] * scale;
+        fp.px_scaled = px.data();
+        fp.cam = cam;
+        camera_rescale(fp.cam, scale);
     }
-    return run_ransac(KIND_PNP, norm.data(), points3D, n, *ransac, max_error * scale, 0, pose, inliers, stats,
-                      counters, fp);
+    return run_ransac(KIND_PNP, points2D, points3D, n, *ransac, max_error * scale, 0, pose, inliers, stats, counters, fp,
+                      nullptr, cam.model != CAMM_NULL ? 1 : 0, &cam, nullptr);
 }
-// PoseLib/robust.cc:242-314 (tangent_sampson == false)
+// PoseLib/robust.cc:242-314: tangent_sampson == 0 unprojects both images to calibrated 2D points and runs the Sampson
+// estimator; tangent_sampson != 0 keeps the (scaled) pixels and runs the tangent-Sampson estimator with the cameras.
 int plb_estimate_relative_pose(const double *x1, const double *x2, size_t n, const plb_camera *camera1,
                                const plb_camera *camera2, const plb_ransac_opt *ransac, const plb_bundle_opt *bundle,
-                               double max_error, double pose[7], char *inliers, plb_ransac_stats *stats,
-                               plb_counters *counters) {
+                               double max_error, int tangent_sampson, double pose[7], char *inliers,
+                               plb_ransac_stats *stats, plb_counters *counters) {
     if (int r = check_ptrs(x1, x2, ransac, pose, n)) return r;
     if (!bundle) {
         g_err = "null bundle options";
         return PLB_ERR_ARG;
     }
-    double c1[4], c2[4];
-    if (int r = camera_params(camera1, c1)) return r;
-    if (int r = camera_params(camera2, c2)) return r;
-    const double scale = 0.5 * (1.0 / camera_focal(camera1, c1) + 1.0 / camera_focal(camera2, c2));
-    std::vector<double> a(2 * n), b(2 * n);
-    for (size_t k = 0; k < n; ++k) {
-        a[2 * k] = (x1[2 * k] - c1[2]) / c1[0];
-        a[2 * k + 1] = (x1[2 * k + 1] - c1[3]) / c1[1];
-        b[2 * k] = (x2[2 * k] - c2[2]) / c2[0];
-        b[2 * k + 1] = (x2[2 * k + 1] - c2[3]) / c2[1];
-    }
+    CamDev c1, c2;
+    if (int r = camera_dev(camera1, &c1)) return r;
+    if (int r = camera_dev(camera2, &c2)) return r;
+    const double scale = 0.5 * (1.0 / camera_focal(c1) + 1.0 / camera_focal(c2));
     FinalPolish fp;
     fp.enabled = true;
     fp.bundle = *bundle;
     fp.bundle.loss_scale = bundle->loss_scale * scale;
     fp.min_inliers = 5;
-    return run_ransac(KIND_RELPOSE, a.data(), b.data(), n, *ransac, max_error * scale, 0, pose, inliers, stats,
-                      counters, fp);
+    if (tangent_sampson) {
+        camera_rescale(c1, scale);
+        camera_rescale(c2, scale);
+        pose[0] = 1.0; // ransac.cc:159-160: the start pose is reset even when score_initial_model is set
+        for (int i = 1; i < 7; ++i) pose[i] = 0.0;
+        return run_ransac(KIND_RELPOSE_TS, x1, x2, n, *ransac, max_error * scale, 0, pose, inliers, stats, counters, fp,
+                          nullptr, 2, &c1, &c2, scale);
+    }
+    const int pre = (c1.model != CAMM_NULL || c2.model != CAMM_NULL) ? 1 : 0;
+    return run_ransac(KIND_RELPOSE, x1, x2, n, *ransac, max_error * scale, 0, pose, inliers, stats, counters, fp,
+                      nullptr, pre, &c1, &c2);
 }
 // PoseLib/robust.cc:544-594
 int plb_estimate_fundamental(const double *x1, const double *x2, size_t n, const plb_ransac_opt *ransac,
@@ -1481,6 +1541,18 @@ int plb_bundle_adjust(const double *x, const double *X, size_t n, double pose[7]
 int plb_refine_relpose(const double *x1, const double *x2, size_t n, double pose[7], const plb_bundle_opt *opt,
                        double bs[3]) {
     return refine_entry(KIND_RELPOSE, x1, x2, n, pose, opt, bs);
+}
+// robust/bundle.cc:237-266 with fixed intrinsics: unproject_with_jac of both images, then the tangent-Sampson refiner
+int plb_refine_relpose_cameras(const double *x1, const double *x2, size_t n, const plb_camera *camera1,
+                               const plb_camera *camera2, double pose[7], const plb_bundle_opt *opt, double bs[3]) {
+    if (!opt || !pose || (n > 0 && (!x1 || !x2))) {
+        g_err = "null argument";
+        return PLB_ERR_ARG;
+    }
+    CamDev c1, c2;
+    if (int r = camera_dev(camera1, &c1)) return r;
+    if (int r = camera_dev(camera2, &c2)) return r;
+    return run_refine(KIND_RELPOSE_TS, x1, x2, n, pose, *opt, bs, &c1, &c2);
 }
 int plb_refine_fundamental(const double *x1, const double *x2, size_t n, double F[9], const plb_bundle_opt *opt,
                            double bs[3]) {
@@ -1666,7 +1738,8 @@ int plb_resident_create(int kind, const double *a, const double *b, size_t n_pts
     D.n = n;
     D.n_pad = n_pad;
     D.b_dim = b_dim;
-    D.reserved = 0;
+    D.mode = 0;
+    D.scale = 1.0;
     PLB_CUDA(cudaMemcpyAsync(E.tdesc.p, E.h_tdesc.p, sizeof(TransposeDesc), cudaMemcpyHostToDevice, E.stream));
     launch_transpose(E.tdesc.p, 1, n_pad, E.stream);
     PLB_CUDA(cudaStreamSynchronize(E.stream));

@@ -24,11 +24,41 @@ PLB_DEV int min_i(int a, int b) { return a < b ? a : b; }
 // layout transform
 // ============================================================================================================
 __global__ void k_transpose(const TransposeDesc *__restrict__ descs) {
-    const TransposeDesc d = descs[blockIdx.y];
+    const TransposeDesc &d = descs[blockIdx.y];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= d.n_pad) return;
     const int idx = (k < d.n) ? k : (d.n - 1); // pad by repeating the last point (never read by the kernels)
-    const double a0 = d.a[2 * (size_t)idx], a1 = d.a[2 * (size_t)idx + 1];
+    double a0 = d.a[2 * (size_t)idx], a1 = d.a[2 * (size_t)idx + 1];
+    if (d.mode == 2) {
+        // tangent-Sampson pre-step: scaled pixels -> unit bearing + unprojection Jacobian of both images
+        double v[9];
+        cam_unproject_with_jac(d.cam_a, a0 * d.scale, a1 * d.scale, v, v + 3);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) d.s64[(size_t)j * d.n_pad + k] = v[j];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) d.s64[(size_t)(6 + j) * d.n_pad + k] = v[3 + j];
+        const double b0 = d.b[2 * (size_t)idx], b1 = d.b[2 * (size_t)idx + 1];
+        cam_unproject_with_jac(d.cam_b, b0 * d.scale, b1 * d.scale, v, v + 3);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) d.s64[(size_t)(3 + j) * d.n_pad + k] = v[j];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) d.s64[(size_t)(12 + j) * d.n_pad + k] = v[3 + j];
+        return;
+    }
+    if (d.mode == 1) cam_unproject2(d.cam_a, a0, a1, a0, a1);
+    if (d.mode == 1 && d.b_dim == 2) {
+        double b0, b1;
+        cam_unproject2(d.cam_b, d.b[2 * (size_t)idx], d.b[2 * (size_t)idx + 1], b0, b1);
+        d.s64[0 * (size_t)d.n_pad + k] = a0;
+        d.s64[1 * (size_t)d.n_pad + k] = a1;
+        d.s64[2 * (size_t)d.n_pad + k] = b0;
+        d.s64[3 * (size_t)d.n_pad + k] = b1;
+        d.s32[0 * (size_t)d.n_pad + k] = (float)a0;
+        d.s32[1 * (size_t)d.n_pad + k] = (float)a1;
+        d.s32[2 * (size_t)d.n_pad + k] = (float)b0;
+        d.s32[3 * (size_t)d.n_pad + k] = (float)b1;
+        return;
+    }
     d.s64[0 * (size_t)d.n_pad + k] = a0;
     d.s64[1 * (size_t)d.n_pad + k] = a1;
     d.s32[0 * (size_t)d.n_pad + k] = (float)a0;
@@ -76,6 +106,8 @@ template <> struct ModelCtx<KIND_RELPOSE> {
         for (int i = 0; i < 9; ++i) E[i] = Em.a[i];
     }
 };
+// tangent Sampson error + cheirality (robust/utils.cc:269-298): same model constants as KIND_RELPOSE
+template <> struct ModelCtx<KIND_RELPOSE_TS> : ModelCtx<KIND_RELPOSE> {};
 // Sampson error (robust/utils.cc:204-239); model is column-major
 template <> struct ModelCtx<KIND_FUND> {
     double E[9];
@@ -103,6 +135,37 @@ PLB_DEV double sampson_r2(const double *E, double x1_0, double x1_1, double x2_0
     const double Cx = Ex1_0 * Ex1_0 + Ex1_1 * Ex1_1;
     const double Cy = Ex2_0 * Ex2_0 + Ex2_1 * Ex2_1;
     return C * C / (Cx + Cy);
+}
+// Epipolar constraint C = d2^T E d1 and its image-space gradient J_C = [M1^T E^T d2 ; M2^T E d1] for unit bearings
+// d1,d2 with unprojection Jacobians M1,M2 (3x2 row-major).  Eigen evaluates `M^T * E * d` left to right, i.e. the 2x3
+// product first (robust/utils.cc:282-284, optim/relative.h:184-187,210-213); the association is kept.
+PLB_DEV void tangent_terms(const double *E, const double *d1, const double *d2, const double *M1, const double *M2,
+                           double &C, double *JC) {
+    const double Ed0 = E[0] * d1[0] + E[1] * d1[1] + E[2] * d1[2];
+    const double Ed1 = E[3] * d1[0] + E[4] * d1[1] + E[5] * d1[2];
+    const double Ed2 = E[6] * d1[0] + E[7] * d1[1] + E[8] * d1[2];
+    C = d2[0] * Ed0 + d2[1] * Ed1 + d2[2] * Ed2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        double T1[3], T2[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            T1[j] = M1[i] * E[3 * j] + M1[2 + i] * E[3 * j + 1] + M1[4 + i] * E[3 * j + 2];
+            T2[j] = M2[i] * E[j] + M2[2 + i] * E[3 + j] + M2[4 + i] * E[6 + j];
+        }
+        JC[i] = T1[0] * d2[0] + T1[1] * d2[1] + T1[2] * d2[2];
+        JC[2 + i] = T2[0] * d1[0] + T2[1] * d1[1] + T2[2] * d1[2];
+    }
+}
+PLB_DEV double tangent_r2(const double *E, const double *v) { // v: the 18 values of one correspondence
+    double C, JC[4];
+    tangent_terms(E, v, v + 3, v + 6, v + 12, C, JC);
+    const double denom2 = (JC[2] * JC[2] + JC[3] * JC[3]) + (JC[0] * JC[0] + JC[1] * JC[1]);
+    return C * C / denom2;
+}
+PLB_DEV void load_ts(const ProblemDev &P, int k, double *v) {
+#pragma unroll
+    for (int j = 0; j < TS_ARRAYS; ++j) v[j] = P.ts[(size_t)j * P.n_pad + k];
 }
 PLB_DEV double homography_r2(const double *H, double x1_0, double x1_1, double x2_0, double x2_1) {
     const double Hx1_0 = H[0] * x1_0 + H[1] * x1_1 + H[2];
@@ -152,6 +215,21 @@ PLB_DEV void cta_score(const ProblemDev &P, const double *model, double sq_thr, 
                 if (r_sq < sq_thr) {
                     ++cnt;
                     score += r_sq;
+                }
+            }
+        } else if (KIND == KIND_RELPOSE_TS) {
+            const double *M = reinterpret_cast<const double *>(&C);
+            for (int k = tid; k < n; k += SCORE_THREADS) {
+                double v[TS_ARRAYS];
+                load_ts(P, k, v);
+                const double r2 = tangent_r2(M, v);
+                bool inl = r2 < sq_thr;
+                if (inl) inl = cheirality_ok(M + 9, M + 13, mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), 0.01);
+                if (inl) {
+                    ++cnt;
+                    score += r2;
+                } else {
+                    score += sq_thr;
                 }
             }
         } else {
@@ -302,7 +380,7 @@ PLB_DEV int sample_problem_slot(const RoundDesc &R, int g) {
 template <int KIND>
 __global__ void __launch_bounds__(HYP_WARPS * 32, 3) k_solve(const RoundDesc R, int *work_counter, HypOut out) {
     constexpr int K = (KIND == KIND_PNP) ? 3 : (KIND == KIND_RELPOSE) ? 5 : (KIND == KIND_FUND) ? 7 : 4;
-    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    constexpr int MSZ = kind_model_size(KIND);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MonoTables *T = reinterpret_cast<MonoTables *>(smem_raw);
     HypScratch<KIND> *Wall = reinterpret_cast<HypScratch<KIND> *>(smem_raw + 256);
@@ -373,10 +451,16 @@ __global__ void __launch_bounds__(HYP_WARPS * 32) k5_prep(const RoundDesc R, int
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= R.n_total) break;
         const ProblemDev &P = R.probs[__ldg(R.active + sample_problem_slot(R, g))];
-        if (lane < 10) { // bearings of the 5 sampled correspondences (estimators/relative_pose.cc:51-54)
+        if (lane < 10) { // bearings of the 5 sampled correspondences (estimators/relative_pose.cc:51-54,90-94)
             const int i = lane % 5, side = lane / 5;
             const uint32_t id = R.samples[(size_t)g * 5 + i];
-            const d3 v = bearing(P.p[2 * side][id], P.p[2 * side + 1][id]);
+            d3 v;
+            if (P.kind == KIND_RELPOSE_TS) {
+                const double *t = P.ts + (size_t)(3 * side) * P.n_pad + id;
+                v = mk(t[0], t[P.n_pad], t[2 * (size_t)P.n_pad]);
+            } else {
+                v = bearing(P.p[2 * side][id], P.p[2 * side + 1][id]);
+            }
             double *o = W->xs + 15 * side + 3 * i;
             o[0] = v.x; o[1] = v.y; o[2] = v.z;
         }
@@ -469,7 +553,7 @@ template <int KIND>
 __global__ void __launch_bounds__(SCORE_THREADS, 4)
     k_score(const ProblemDev *__restrict__ probs, const double *__restrict__ models, const int *__restrict__ model_prob,
             const int *__restrict__ model_count, int cap, uint32_t *counts, double *scores) {
-    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    constexpr int MSZ = kind_model_size(KIND);
     __shared__ ScoreRed red;
     int nmod = *model_count;
     if (nmod > cap) nmod = cap;
@@ -496,8 +580,8 @@ constexpr int SCORE_TM = 4;
 template <int KIND>
 __global__ void __launch_bounds__(SCORE_THREADS, 2)
     k_score_tiled(const RoundDesc R, HypOut out) {
-    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
-    constexpr int CTX = (KIND == KIND_PNP) ? 12 : (KIND == KIND_RELPOSE) ? 16 : 9;
+    constexpr int MSZ = kind_model_size(KIND);
+    constexpr int CTX = (KIND == KIND_PNP) ? 12 : kind_is_relpose(KIND) ? 16 : 9;
     __shared__ double ctx[SCORE_TM][16];
     __shared__ double red_s[SCORE_WARPS][SCORE_TM];
     __shared__ uint32_t red_c[SCORE_WARPS][SCORE_TM];
@@ -552,6 +636,26 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
                                 ++cnt[i];
                                 sc[i] += r_sq;
                             }
+                        }
+                    }
+                }
+            }
+        } else if (KIND == KIND_RELPOSE_TS) {
+            for (int k = tid; k < n; k += SCORE_THREADS) {
+                double v[TS_ARRAYS];
+                load_ts(P, k, v);
+#pragma unroll
+                for (int i = 0; i < SCORE_TM; ++i) {
+                    if (i < tm) {
+                        const double r2 = tangent_r2(ctx[i], v);
+                        bool inl = r2 < sq_thr;
+                        if (inl)
+                            inl = cheirality_ok(ctx[i] + 9, ctx[i] + 13, mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), 0.01);
+                        if (inl) {
+                            ++cnt[i];
+                            sc[i] += r2;
+                        } else {
+                            sc[i] += sq_thr;
                         }
                     }
                 }
@@ -689,8 +793,8 @@ __device__ __noinline__ bool cheirality32(const float *qt, float a0, float a1, f
 
 template <int KIND>
 __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOut out, int use_smem) {
-    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
-    constexpr int CTX = (KIND == KIND_PNP) ? 12 : (KIND == KIND_RELPOSE) ? 16 : 9;
+    constexpr int MSZ = kind_model_size(KIND);
+    constexpr int CTX = (KIND == KIND_PNP) ? 12 : kind_is_relpose(KIND) ? 16 : 9;
     constexpr int NARR = (KIND == KIND_PNP) ? 5 : 4;
     extern __shared__ __align__(128) unsigned char scr_smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -860,7 +964,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 4)
     k_score_list(const ProblemDev *__restrict__ probs, const double *__restrict__ models,
                  const int *__restrict__ model_prob, const int *__restrict__ slots, int n_slots, uint32_t *counts,
                  double *scores) {
-    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    constexpr int MSZ = kind_model_size(KIND);
     __shared__ ScoreRed red;
     for (int j = blockIdx.x; j < n_slots; j += gridDim.x) {
         const int m = slots[j];
@@ -930,7 +1034,8 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
                          cudaEvent_t ev_between) {
     // persistent grids: a multiple of the SM count (resident CTAs per SM from the occupancy API), never more CTAs
     // than there is work for
-    if (KIND == KIND_RELPOSE && out.s5_blk != nullptr) {
+    if constexpr (KIND == KIND_RELPOSE_TS) mode = 0; // no fp32 screening copy of the 18-array layout: exact scoring
+    if (kind_is_relpose(KIND) && (KIND == KIND_RELPOSE_TS || out.s5_blk != nullptr)) {
         int blocks = prep_blocks_per_sm() * sm_count();
         const int need = (R.n_total + HYP_WARPS - 1) / HYP_WARPS;
         if (blocks > need) blocks = need;
@@ -939,7 +1044,7 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
         k5_roots<<<(R.n_total + 127) / 128, 128, 0, stream>>>(R.n_total, out);
         const int warps = (R.n_total + 2) / 3;
         k5_back<<<(warps * 32 + 127) / 128, 128, 0, stream>>>(R, out);
-    } else {
+    } else if constexpr (KIND != KIND_RELPOSE_TS) {
         int blocks = solve_blocks_per_sm<KIND>() * sm_count();
         const int need = (R.n_total + HYP_WARPS - 1) / HYP_WARPS;
         if (blocks > need) blocks = need;
@@ -954,7 +1059,7 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
         if (gx > tiles) gx = tiles;
         if (gx < 1) gx = 1;
         k_score_tiled<KIND><<<dim3(gx, R.n_active, 1), SCORE_THREADS, 0, stream>>>(R, out);
-    } else {
+    } else if constexpr (KIND != KIND_RELPOSE_TS) {
         // fp32 screening: one CTA holds one problem's fp32 arrays in shared memory (TMA) and strides over its tiles
         constexpr int NARR = (KIND == KIND_PNP) ? 5 : 4;
         const size_t bytes = (size_t)NARR * (size_t)max_n_pad * 4;
@@ -980,6 +1085,7 @@ void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &ou
     case KIND_PNP: launch_hyp_t<KIND_PNP>(R, work, out, mode, max_n_pad, stream, ev_between); break;
     case KIND_RELPOSE: launch_hyp_t<KIND_RELPOSE>(R, work, out, mode, max_n_pad, stream, ev_between); break;
     case KIND_FUND: launch_hyp_t<KIND_FUND>(R, work, out, mode, max_n_pad, stream, ev_between); break;
+    case KIND_RELPOSE_TS: launch_hyp_t<KIND_RELPOSE_TS>(R, work, out, mode, max_n_pad, stream, ev_between); break;
     default: launch_hyp_t<KIND_HOMOG>(R, work, out, mode, max_n_pad, stream, ev_between); break;
     }
 }
@@ -992,6 +1098,7 @@ void launch_score_list(int kind, const ProblemDev *probs, const double *models, 
     case KIND_PNP: k_score_list<KIND_PNP><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
     case KIND_RELPOSE: k_score_list<KIND_RELPOSE><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
     case KIND_FUND: k_score_list<KIND_FUND><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
+    case KIND_RELPOSE_TS: k_score_list<KIND_RELPOSE_TS><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
     default: k_score_list<KIND_HOMOG><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
     }
 }
@@ -1008,6 +1115,7 @@ void launch_score_models(int kind, const ProblemDev *probs, const double *models
     case KIND_PNP: k_score<KIND_PNP><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, n_models_dev, n_models, counts, scores); break;
     case KIND_RELPOSE: k_score<KIND_RELPOSE><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, n_models_dev, n_models, counts, scores); break;
     case KIND_FUND: k_score<KIND_FUND><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, n_models_dev, n_models, counts, scores); break;
+    case KIND_RELPOSE_TS: k_score<KIND_RELPOSE_TS><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, n_models_dev, n_models, counts, scores); break;
     default: k_score<KIND_HOMOG><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, n_models_dev, n_models, counts, scores); break;
     }
 }
@@ -1017,7 +1125,7 @@ void launch_score_models(int kind, const ProblemDev *probs, const double *models
 // ============================================================================================================
 template <int KIND>
 __global__ void k_inlier_mask(const ProblemDev *__restrict__ probs, const MaskDesc *__restrict__ descs, char *mask_base) {
-    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    constexpr int MSZ = kind_model_size(KIND);
     const MaskDesc &D = descs[blockIdx.y];
     const ProblemDev P = probs[D.pidx];
     const double sq_thr = P.sq_thr;
@@ -1034,6 +1142,15 @@ __global__ void k_inlier_mask(const ProblemDev *__restrict__ probs, const MaskDe
         const double d0 = Z.x / Z.z - P.p[0][k], d1 = Z.y / Z.z - P.p[1][k];
         const double r2 = d0 * d0 + d1 * d1;
         mask[k] = (r2 < sq_thr && Z.z > 0.0) ? 1 : 0;
+    } else if (KIND == KIND_RELPOSE_TS) { // robust/utils.cc:541-569
+        ModelCtx<KIND> C;
+        C.init(mdl);
+        const double *M = reinterpret_cast<const double *>(&C);
+        double v[TS_ARRAYS];
+        load_ts(P, k, v);
+        bool inl = tangent_r2(M, v) < sq_thr;
+        if (inl) inl = cheirality_ok(M + 9, M + 13, mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), 0.01);
+        mask[k] = inl ? 1 : 0;
     } else {
         ModelCtx<KIND> C;
         C.init(mdl);
@@ -1057,6 +1174,7 @@ void launch_inlier_masks(int kind, const ProblemDev *probs, const MaskDesc *desc
     case KIND_PNP: k_inlier_mask<KIND_PNP><<<grid, threads, 0, stream>>>(probs, descs_dev, mask_base); break;
     case KIND_RELPOSE: k_inlier_mask<KIND_RELPOSE><<<grid, threads, 0, stream>>>(probs, descs_dev, mask_base); break;
     case KIND_FUND: k_inlier_mask<KIND_FUND><<<grid, threads, 0, stream>>>(probs, descs_dev, mask_base); break;
+    case KIND_RELPOSE_TS: k_inlier_mask<KIND_RELPOSE_TS><<<grid, threads, 0, stream>>>(probs, descs_dev, mask_base); break;
     default: k_inlier_mask<KIND_HOMOG><<<grid, threads, 0, stream>>>(probs, descs_dev, mask_base); break;
     }
 }
@@ -1099,6 +1217,7 @@ struct LossFn { // robust/robust_loss.h:41-67,125-136
 template <int KIND> struct LmDims;
 template <> struct LmDims<KIND_PNP> { static constexpr int NP = 6, CTX = 12; };
 template <> struct LmDims<KIND_RELPOSE> { static constexpr int NP = 5, CTX = 9 + 45; };
+template <> struct LmDims<KIND_RELPOSE_TS> { static constexpr int NP = 5, CTX = 9 + 45; };
 template <> struct LmDims<KIND_FUND> { static constexpr int NP = 7, CTX = 9 + 63; };
 template <> struct LmDims<KIND_HOMOG> { static constexpr int NP = 8, CTX = 18; };
 
@@ -1182,7 +1301,7 @@ template <int KIND> PLB_DEV void lm_build_ctx(const double *par, double *ctx, do
 #pragma unroll
         for (int k = 0; k < 9; ++k) ctx[k] = R.a[k];
         ctx[9] = par[4]; ctx[10] = par[5]; ctx[11] = par[6];
-    } else if (KIND == KIND_RELPOSE) {
+    } else if (kind_is_relpose(KIND)) {
         const m3 E = essential_from_pose(par, par + 4);
 #pragma unroll
         for (int k = 0; k < 9; ++k) ctx[k] = E.a[k];
@@ -1271,7 +1390,7 @@ template <int KIND> PLB_DEV void lm_step(const double *par, const double *dp, co
         quat_mul(par, e, out);
         const d3 rt = quat_rotate(par, mk(dp[3], dp[4], dp[5]));
         out[4] = par[4] + rt.x; out[5] = par[5] + rt.y; out[6] = par[6] + rt.z;
-    } else if (KIND == KIND_RELPOSE) {
+    } else if (kind_is_relpose(KIND)) {
         double e[4];
         quat_exp(mk(dp[0], dp[1], dp[2]), e);
         quat_mul(par, e, out);
@@ -1444,15 +1563,9 @@ PLB_DEV void lm_eval_pass(const ProblemDev &P, const LmParams &prm, const LossFn
             const double Z2 = ctx[6] * X0 + ctx[7] * X1 + ctx[8] * X2 + ctx[11];
             if (Z2 < 0) continue; // optim/absolute.h:57-58,93-94
             double zp0, zp1, xr0, xr1, Jp[2][3];
-            if (prm.use_camera) { // PinholeCameraModel::project / project_with_jac (camera_models.cc:668-685)
-                xr0 = prm.cam[0] * Z0 / Z2 + prm.cam[2];
-                xr1 = prm.cam[1] * Z1 / Z2 + prm.cam[3];
-                const double inv_z = 1.0 / Z2;
-                const double px = prm.cam[0] * Z0 * inv_z, py = prm.cam[1] * Z1 * inv_z;
-                zp0 = px + prm.cam[2];
-                zp1 = py + prm.cam[3];
-                Jp[0][0] = prm.cam[0] * inv_z; Jp[0][1] = 0.0; Jp[0][2] = -px * inv_z;
-                Jp[1][0] = 0.0; Jp[1][1] = prm.cam[1] * inv_z; Jp[1][2] = -py * inv_z;
+            if (prm.use_camera) { // <Model>::project for the residual, ::project_with_jac for the Jacobian pass
+                cam_project(prm.cam, Z0, Z1, Z2, xr0, xr1); // (optim/absolute.h:59-61,97-104)
+                cam_project_with_jac(prm.cam, Z0, Z1, Z2, zp0, zp1, &Jp[0][0]);
             } else { // NullCameraModel (camera_models.cc:2708-2722)
                 zp0 = Z0 / Z2;
                 zp1 = Z1 / Z2;
@@ -1534,6 +1647,42 @@ PLB_DEV void lm_eval_pass(const ProblemDev &P, const LmParams &prm, const LossFn
                 K1[m] = K1[m] * iv;
             }
             A.add2(L, s0, s1, K0, K1);
+        } else if (KIND == KIND_RELPOSE_TS) {
+            // FixCameraRelativePoseRefiner (optim/relative.h:181-249)
+            double v[TS_ARRAYS];
+            load_ts(P, k, v);
+            double C, JC[4];
+            tangent_terms(ctx, v, v + 3, v + 6, v + 12, C, JC);
+            {
+                const double nJc_sq = (JC[2] * JC[2] + JC[3] * JC[3]) + (JC[0] * JC[0] + JC[1] * JC[1]);
+                const double rr = C / sqrt(nJc_sq);
+                lsum += L.loss(rr * rr);
+                rows += 1.0;
+            }
+            const double nJ_C = sqrt((JC[0] * JC[0] + JC[2] * JC[2]) + (JC[1] * JC[1] + JC[3] * JC[3]));
+            const double inv = 1.0 / nJ_C;
+            const double r = C * inv;
+            const double s = C * inv * inv;
+            const double *d1 = v, *d2 = v + 3, *M1 = v + 6, *M2 = v + 12;
+            double dF[9], J[NP];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr) {
+                    double e = d1[c] * d2[rr];
+                    e -= s * (JC[0] * M1[2 * c] * d2[rr] + JC[1] * M1[2 * c + 1] * d2[rr] + JC[2] * M2[2 * rr] * d1[c] +
+                              JC[3] * M2[2 * rr + 1] * d1[c]);
+                    dF[3 * c + rr] = e * inv;
+                }
+            const double *D = ctx + 9;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                double t = 0.0;
+#pragma unroll
+                for (int m = 0; m < 9; ++m) t += dF[m] * D[NP * m + p];
+                J[p] = t;
+            }
+            A.add1(L, r, J);
         } else {
             const double a0 = P.p[0][k], a1 = P.p[1][k], b0 = P.p[2][k], b1 = P.p[3][k];
             {
@@ -1605,7 +1754,7 @@ __global__ void __launch_bounds__(LM_THREADS)
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int NP = LmDims<KIND>::NP;
     constexpr int NT = NP * (NP + 1) / 2;
-    constexpr int MSZ = (KIND == KIND_PNP || KIND == KIND_RELPOSE) ? 7 : 9;
+    constexpr int MSZ = kind_model_size(KIND);
     __shared__ LmShared S;
     const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
     const int job = blockIdx.x / csize;
@@ -1847,6 +1996,7 @@ void launch_lm(int kind, const ProblemDev *probs, const LmJob *jobs_dev, const d
     case KIND_PNP: launch_lm_t<KIND_PNP>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
     case KIND_RELPOSE: launch_lm_t<KIND_RELPOSE>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
     case KIND_FUND: launch_lm_t<KIND_FUND>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
+    case KIND_RELPOSE_TS: launch_lm_t<KIND_RELPOSE_TS>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
     default: launch_lm_t<KIND_HOMOG>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
     }
 }

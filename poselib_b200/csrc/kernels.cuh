@@ -1,15 +1,19 @@
 // poselib_b200 — device-side data layout + host-callable launchers (implemented in kernels.cu).
 #pragma once
+#include "camera.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace plb {
 
-enum Kind { KIND_PNP = 0, KIND_RELPOSE = 1, KIND_FUND = 2, KIND_HOMOG = 3 };
+// KIND_RELPOSE_TS: relative pose scored / refined with the tangent Sampson error on unit bearings d1,d2 and the
+// unprojection Jacobians M1,M2 of arbitrary camera models (CameraRelativePoseEstimator, ransac.cc:155-168).
+enum Kind { KIND_PNP = 0, KIND_RELPOSE = 1, KIND_FUND = 2, KIND_HOMOG = 3, KIND_RELPOSE_TS = 4 };
 
 // Correspondences of ONE problem, resident in HBM as structure-of-arrays fp64 (exactly the caller's doubles):
 //   2D-2D kinds : p[0]=x1.x p[1]=x1.y p[2]=x2.x p[3]=x2.y                      (32 B / correspondence)
 //   PnP         : p[0]=x.x  p[1]=x.y  p[2]=X.x  p[3]=X.y  p[4]=X.z             (40 B / correspondence)
+//   RELPOSE_TS  : ts + j*n_pad, j = 0..2 d1 | 3..5 d2 | 6..11 M1 (3x2 row-major) | 12..17 M2  (144 B / correspondence)
 // Lanes read consecutive k -> every warp load is one fully coalesced 256 B request per array.
 // f[] is the fp32 copy of the same arrays used by the screening pass (16 B / 20 B per correspondence).
 struct ProblemDev {
@@ -19,11 +23,15 @@ struct ProblemDev {
     int kind;
     double sq_thr;  // max_error^2 in the units of the points
     int rfc;        // real focal check (fundamental)
+    int n_pad;      // array stride of ts
+    const double *ts;
 };
 
-inline __host__ __device__ int kind_sample_size(int kind) { return kind == KIND_PNP ? 3 : kind == KIND_RELPOSE ? 5 : kind == KIND_FUND ? 7 : 4; }
-inline __host__ __device__ int kind_max_models(int kind) { return kind == KIND_PNP ? 4 : kind == KIND_RELPOSE ? 40 : kind == KIND_FUND ? 3 : 1; }
-inline __host__ __device__ int kind_model_size(int kind) { return (kind == KIND_PNP || kind == KIND_RELPOSE) ? 7 : 9; }
+constexpr __host__ __device__ bool kind_is_relpose(int kind) { return kind == KIND_RELPOSE || kind == KIND_RELPOSE_TS; }
+constexpr __host__ __device__ int kind_sample_size(int kind) { return kind == KIND_PNP ? 3 : kind_is_relpose(kind) ? 5 : kind == KIND_FUND ? 7 : 4; }
+constexpr __host__ __device__ int kind_max_models(int kind) { return kind == KIND_PNP ? 4 : kind_is_relpose(kind) ? 40 : kind == KIND_FUND ? 3 : 1; }
+constexpr __host__ __device__ int kind_model_size(int kind) { return (kind == KIND_PNP || kind_is_relpose(kind)) ? 7 : 9; }
+constexpr int TS_ARRAYS = 18;
 
 // One round of hypothesis generation over a GROUP of problems of the same kind.  Global sample index g in
 // [0, n_total) belongs to the active problem a with g_off[a] <= g < g_off[a+1]; its ProblemDev is probs[active[a]].
@@ -70,8 +78,8 @@ struct LmParams {
     int subset_mode; // 0: all points; 1: relpose LO subset (Sampson+cheirality inliers at subset_sq_thr of the start pose,
                      //    return untouched if <= 5, estimators/relative_pose.cc:70-76); 2: use given mask
     double subset_sq_thr;
-    int use_camera;  // pnp final polish: project with pinhole (fx,fy,cx,cy) instead of the null camera
-    double cam[4];
+    int use_camera;  // pnp final polish: project with `cam` (rescaled intrinsics) instead of the null camera
+    CamDev cam;
     int score_after; // score the refined model with sq_thr of the problem (count, score)
 };
 struct LmJob {
@@ -88,11 +96,18 @@ struct LmJobOut {
     int iterations;
     double cost, initial_cost;
 };
+// Pre-step of one problem: caller layout (AoS doubles, device copies) -> resident SoA arrays.
+//   mode 0: plain transposition (points already calibrated / normalised)
+//   mode 1: Camera::unproject to 2D of a (cam_a) and, for 2D-2D kinds, of b (cam_b)   (robust.cc:40-43,287-292)
+//   mode 2: a*scale, b*scale -> unproject_with_jac -> the 18 RELPOSE_TS arrays (robust.cc:255-266,
+//           estimators/relative_pose.h:80-81); s32 unused
 struct TransposeDesc {
-    const double *a, *b; // caller layout (device copies): 2n and b_dim*n doubles
+    const double *a, *b; // 2n and b_dim*n doubles
     double *s64;
     float *s32;
-    int n, n_pad, b_dim, reserved;
+    int n, n_pad, b_dim, mode;
+    double scale;
+    CamDev cam_a, cam_b;
 };
 struct MaskDesc {
     int pidx;
@@ -102,7 +117,7 @@ struct MaskDesc {
 };
 
 // ---- launchers (all asynchronous on `stream`) --------------------------------------------------------------
-// AoS (caller layout) -> SoA fp64 + fp32 for n_desc problems (descriptors in device memory).
+// AoS (caller layout) -> SoA fp64 + fp32 for n_desc problems (descriptors in device memory), camera pre-step fused.
 void launch_transpose(const TransposeDesc *descs_dev, int n_desc, int max_n_pad, cudaStream_t stream);
 // Solve + score kernels of one round (kind = kind of every problem of the group).  work: 3 ints of device scratch.
 // mode 0: exact fp64 scoring of every model; mode 1: fp32 screening of every model (exact rescoring of the candidates

@@ -16,7 +16,7 @@ from . import cabi
 __all__ = ["CameraPose", "Image", "estimate_absolute_pose", "estimate_relative_pose", "estimate_fundamental",
            "estimate_homography", "p3p", "relpose_5pt", "essential_matrix_5pt", "relpose_7pt", "homography_4pt"]
 
-_CAMERA_IDS = {"SIMPLE_PINHOLE": 0, "PINHOLE": 1, "NULL": -1}
+_CAMERA_IDS = dict(cabi.CAMERA)
 
 
 class CameraPose:
@@ -133,8 +133,6 @@ def estimate_absolute_pose(points2D, points3D, camera, opt=None, initial_pose=No
 def estimate_relative_pose(points2D_1, points2D_2, camera1, camera2, opt=None, initial_pose=None):
     """relative_pose.cc:15-52,405-421.  Returns (CameraPose, info)."""
     opt = opt or {}
-    if _truthy(opt.get("tangent_sampson", False)):
-        raise cabi.PoseLibB200Error(cabi.PLB_ERR_NYI, "NYI: tangent_sampson (SURVEY §8f N1)")
     rkw = _ransac(opt.get("ransac", {}))
     init = None
     if initial_pose is not None:
@@ -142,7 +140,8 @@ def estimate_relative_pose(points2D_1, points2D_2, camera1, camera2, opt=None, i
         rkw["score_initial_model"] = True
     r = cabi.estimate("relpose", _pts(points2D_1, 2), _pts(points2D_2, 2), cabi.RansacOpt(**rkw),
                       cabi.BundleOpt(**_bundle(opt.get("bundle", {}))), float(opt.get("max_error", 1.0)),
-                      _camera(camera1), _camera(camera2), init=init)
+                      _camera(camera1), _camera(camera2), init=init,
+                      tangent_sampson=_truthy(opt.get("tangent_sampson", False)))
     return CameraPose(r["model"][:4], r["model"][4:]), _info(r)
 
 

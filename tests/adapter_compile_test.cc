@@ -108,6 +108,13 @@ int main(int argc, char **argv) {
         st = poselib_b200::estimate_absolute_pose<RansacStats>(x1, X, ao, &img, &inl);
         st = poselib_b200::ransac_pnp<RansacStats>(x1, X, ao, &pose, &inl);
         st = poselib_b200::ransac_relpose<RansacStats>(x1, x2, ro, &pose, &inl);
+        Camera rad; // SIMPLE_RADIAL through the tangent-Sampson path
+        rad.model_id = 2;
+        rad.params = {1.0, 0.0, 0.0, -0.05};
+        st = poselib_b200::ransac_relpose<RansacStats>(x1, x2, rad, rad, ro, &pose, &inl);
+        ro.tangent_sampson = true;
+        st = poselib_b200::estimate_relative_pose<RansacStats>(x1, x2, rad, rad, ro, &pose, &inl);
+        ro.tangent_sampson = false;
         st = poselib_b200::ransac_fundamental<RansacStats>(x1, x2, ro, &F, &inl);
         st = poselib_b200::ransac_homography<RansacStats>(x1, x2, ho, &H, &inl);
         std::vector<Vector3d> b1(7), b2(7);

@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(cabi.RansacStats) == 40
     assert C.sizeof(cabi.BundleOpt) == 72
     assert C.sizeof(cabi.Counters) == 104
-    assert C.sizeof(cabi.Camera) == 48
+    assert C.sizeof(cabi.Camera) == 80
     o = cabi.RansacOpt(1, 2, 9.0, 0.5, 77, True, True, 5)
     cabi.lib().plb_ransac_opt_default(C.byref(o))
     assert (o.max_iterations, o.min_iterations, o.dyn_num_trials_mult, o.success_prob, o.seed,
@@ -54,7 +54,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert cabi.lib().plb_set_mode(7) == cabi.PLB_ERR_ARG
     # unsupported camera model -> NYI (reference throws "NYI", camera_models.cc:184-185)
     x = np.zeros((8, 2))
-    cam = cabi.Camera(4, (500, 500, 0, 0))  # OPENCV
+    cam = cabi.Camera(5, (500, 500, 0, 0))  # OPENCV_FISHEYE: not one of the six models on the path
     with pytest.raises(cabi.PoseLibB200Error) as e:
         cabi.estimate("relpose", x, x, cabi.RansacOpt(), cabi.BundleOpt(), 1.0, cam, cam)
     assert e.value.code == cabi.PLB_ERR_NYI

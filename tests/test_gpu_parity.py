@@ -383,3 +383,107 @@ def test_mixed_batch_config5_style_fast_mode(cabi):
     for g, o, pr in zip(res, refs, probs):
         assert g["status"] == 0
         _same_trajectory(g, o, relpose=(pr["kind"] == "relpose"))
+
+
+# ---------------------------------------------------------------------------------------------- cameras (rows N3 / N1)
+DISTORTION_CAMERAS = [  # tests/example_cameras.h:31-38 of the reference, principal point moved to the image centre
+    ("SIMPLE_RADIAL", [1100.0, 30.0, -20.0, -0.0397695]),
+    ("RADIAL", [1050.0, -15.0, 25.0, -0.04012, 0.00123]),
+    ("OPENCV", [1020.0, 990.0, 12.0, -8.0, 0.0141865, -0.0465301, 0.0005, -0.0003]),
+    ("OPENCV", [868.993378, 866.063001, 5.9, -4.0, -0.399431, 0.188924, 0.000153, 0.000571]),
+    ("SIMPLE_PINHOLE", [950.0, 3.0, 4.0]),
+]
+
+
+def _distort(cam, x_px):
+    """pixel observations of the synthetic pinhole camera (f = G.FOCAL, pp = 0) re-imaged by `cam`."""
+    X = np.c_[np.asarray(x_px) / G.FOCAL, np.ones(len(x_px))]
+    return P.camera_project_with_jac(cam, X)[2]
+
+
+@pytest.mark.parametrize("model,params", DISTORTION_CAMERAS)
+def test_estimate_relative_pose_camera_prestep_on_device(cabi, model, params):
+    """robust.cc:287-292: Camera::unproject of every point happens in the layout kernel; the calibrated points must be
+    the oracle's doubles, so trajectory and masks are bit-exact."""
+    p = G.relpose_problem(2500, 0.45, 31, 2)
+    camo = (model, params)
+    camg = cabi.Camera(model, params)
+    x1, x2 = _distort(camo, p["x1"]), _distort(camo, p["x2"])
+    kw = dict(max_iterations=20000, min_iterations=300, seed=4)
+    for mode in (0, 1):
+        cabi.set_mode(mode)
+        g = cabi.estimate("relpose", x1, x2, cabi.RansacOpt(**kw), cabi.BundleOpt(), 1.5, camg, camg)
+        cabi.set_mode(0)
+        o = P.estimate("relpose", x1, x2, P.RansacOpt(**kw), P.BundleOpt(), 1.5, camo, camo)
+        assert o["stats"]["num_inliers"] > 800
+        _same_trajectory(g, o, relpose=True)
+    # two different cameras
+    cam2o = DISTORTION_CAMERAS[1]
+    x2b = _distort(cam2o, p["x2"])
+    g = cabi.estimate("relpose", x1, x2b, cabi.RansacOpt(**kw), cabi.BundleOpt(), 1.5, camg, cabi.Camera(*cam2o))
+    o = P.estimate("relpose", x1, x2b, P.RansacOpt(**kw), P.BundleOpt(), 1.5, camo, cam2o)
+    _same_trajectory(g, o, relpose=True)
+
+
+@pytest.mark.parametrize("model,params", DISTORTION_CAMERAS)
+def test_estimate_absolute_pose_distortion_cameras(cabi, model, params):
+    """robust.cc:36-126 with a distorted camera: device unprojection + the final bundle adjustment through the
+    camera's project_with_jac (optim/absolute.h:80-130)."""
+    p = G.abspose_problem(1500, 0.5, 32, 4)
+    camo = (model, params)
+    x = _distort(camo, p["x"])
+    kw = dict(max_iterations=5000, min_iterations=300, seed=1)
+    g = cabi.estimate("pnp", x, p["X"], cabi.RansacOpt(**kw), cabi.BundleOpt(), 4.0, cabi.Camera(model, params))
+    o = P.estimate("pnp", x, p["X"], P.RansacOpt(**kw), P.BundleOpt(), 4.0, camo)
+    assert o["stats"]["num_inliers"] > 600
+    _same_trajectory(g, o)
+
+
+@pytest.mark.parametrize("model,params", DISTORTION_CAMERAS[:4])
+def test_tangent_sampson_ransac_matches_oracle(cabi, model, params):
+    """ransac.cc:155-168 (CameraRelativePoseEstimator): bearings + unprojection Jacobians computed on the device, 5-point
+    solver on the bearings, tangent-Sampson MSAC scoring, LO over all points: same trajectory, bit-exact mask."""
+    p = G.relpose_problem(2000, 0.4, 33, 1)
+    camo = (model, params)
+    camg = cabi.Camera(model, params)
+    x1, x2 = _distort(camo, p["x1"]), _distort(camo, p["x2"])
+    kw = dict(max_iterations=20000, min_iterations=300, seed=6)
+    g = cabi.ransac_relpose_cameras(x1, x2, camg, camg, cabi.RansacOpt(**kw), 1.5)
+    o = P.ransac_relpose_cameras(x1, x2, camo, camo, P.RansacOpt(**kw), 1.5)
+    assert o["stats"]["num_inliers"] > 600
+    _same_trajectory(g, o, relpose=True)
+    for mode in (0, 1):  # the precision mode does not apply to this kind; results stay the same
+        cabi.set_mode(mode)
+        g = cabi.estimate("relpose", x1, x2, cabi.RansacOpt(**kw), cabi.BundleOpt(), 1.5, camg, camg, tangent_sampson=True)
+        cabi.set_mode(0)
+        o = P.estimate("relpose", x1, x2, P.RansacOpt(**kw), P.BundleOpt(), 1.5, camo, camo, tangent_sampson=True)
+        _same_trajectory(g, o, relpose=True)
+
+
+def test_tangent_sampson_edge_sizes_and_prosac(cabi):
+    camo = DISTORTION_CAMERAS[0]
+    camg = cabi.Camera(*camo)
+    p = G.relpose_problem(400, 0.5, 34, 3, prosac_sorted=True)
+    x1, x2 = _distort(camo, p["x1"]), _distort(camo, p["x2"])
+    for n in (0, 4, 5, 6, 33, 400):
+        kw = dict(max_iterations=300, min_iterations=50, seed=n, progressive_sampling=(n == 400))
+        g = cabi.ransac_relpose_cameras(x1[:n], x2[:n], camg, camg, cabi.RansacOpt(**kw), 2.0)
+        o = P.ransac_relpose_cameras(x1[:n], x2[:n], camo, camo, P.RansacOpt(**kw), 2.0)
+        _same_trajectory(g, o, relpose=True)
+
+
+@pytest.mark.parametrize("loss", ["TRIVIAL", "TRUNCATED", "HUBER", "CAUCHY"])
+def test_refine_relpose_cameras_matches_oracle(cabi, loss):
+    camo = DISTORTION_CAMERAS[1]
+    camg = cabi.Camera(*camo)
+    p = G.relpose_problem(600, 1.0, 35, 2)
+    x1, x2 = _distort(camo, p["x1"]), _distort(camo, p["x2"])
+    start = np.r_[p["q_gt"], p["t_gt"]] + np.random.default_rng(3).normal(0, 0.003, 7)
+    start[:4] /= np.linalg.norm(start[:4])
+    d1, M1 = P.camera_unproject_with_jac(camo, x1)
+    d2, M2 = P.camera_unproject_with_jac(camo, x2)
+    gm, gs = cabi.refine_relpose_cameras(start, x1, x2, camg, camg, cabi.BundleOpt(loss_type=loss, loss_scale=2.0))
+    om, os_ = P.refine_relpose_tangent(start, d1, d2, M1, M2, P.BundleOpt(loss_type=loss, loss_scale=2.0))
+    assert gs[0] == os_[0], (gs, os_)
+    assert np.allclose(gs[1:3], os_[1:3], rtol=1e-9, atol=1e-12)
+    assert np.allclose(gm, om, rtol=1e-6, atol=1e-8)

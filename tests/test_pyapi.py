@@ -18,7 +18,7 @@ def test_option_dicts_follow_the_pybind_helpers():
     with pytest.raises(cabi.PoseLibB200Error):
         pyapi._bundle({"damping": "MARQUARDT"})
     with pytest.raises(cabi.PoseLibB200Error):
-        pyapi._camera({"model": "OPENCV", "params": [1, 1, 0, 0, 0, 0, 0, 0]})
+        pyapi._camera({"model": "OPENCV_FISHEYE", "params": [1, 1, 0, 0, 0, 0, 0, 0]})
     c = pyapi._camera({"model": "SIMPLE_PINHOLE", "width": 640, "height": 480, "params": [500.0, 320.0, 240.0]})
     assert (c.model_id, c.width, c.height, list(c.params)[:3]) == (0, 640, 480, [500.0, 320.0, 240.0])
     with pytest.raises(cabi.PoseLibB200Error):
