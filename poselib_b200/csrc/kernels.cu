@@ -434,25 +434,28 @@ __global__ void __launch_bounds__(HYP_WARPS * 32, 3) k_solve(const RoundDesc R, 
 //   k5_back  : lane  = (sample, root)  back-substitution, motion decomposition, cheirality; 3 samples per warp
 constexpr int S5_BLK = 105;
 
-struct PrepScratch {
-    Scratch5 s5;
-    double xs[30];
-};
+constexpr int PREP_SAMPLES_PER_WARP = 4;
+constexpr size_t PREP_SMEM = 256 + sizeof(double) * P5_STRIDE * PREP_SAMPLES_PER_WARP * HYP_WARPS;
 __global__ void __launch_bounds__(HYP_WARPS * 32) k5_prep(const RoundDesc R, int *work_counter, HypOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MonoTables *T = reinterpret_cast<MonoTables *>(smem_raw);
-    PrepScratch *W = reinterpret_cast<PrepScratch *>(smem_raw + 256) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sl = lane & 7, grp = lane >> 3;
+    double *W = reinterpret_cast<double *>(smem_raw + 256) +
+                (size_t)((threadIdx.x >> 5) * PREP_SAMPLES_PER_WARP + grp) * P5_STRIDE;
     fill_tables(T);
     __syncthreads();
     for (;;) {
-        int g = 0;
-        if (lane == 0) g = atomicAdd(work_counter, 1);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        if (g >= R.n_total) break;
+        int g0 = 0;
+        if (lane == 0) g0 = atomicAdd(work_counter, PREP_SAMPLES_PER_WARP);
+        g0 = __shfl_sync(0xffffffffu, g0, 0);
+        if (g0 >= R.n_total) break;
+        int g = g0 + grp;
+        const bool live = g < R.n_total;
+        if (!live) g = R.n_total - 1; // idle groups redo the last sample (uniform control flow), nothing is stored
         const ProblemDev &P = R.probs[__ldg(R.active + sample_problem_slot(R, g))];
-        if (lane < 10) { // bearings of the 5 sampled correspondences (estimators/relative_pose.cc:51-54,90-94)
-            const int i = lane % 5, side = lane / 5;
+        // bearings of the 5 sampled correspondences (estimators/relative_pose.cc:51-54,90-94)
+        for (int idx = sl; idx < 10; idx += 8) {
+            const int i = idx % 5, side = idx / 5;
             const uint32_t id = R.samples[(size_t)g * 5 + i];
             d3 v;
             if (P.kind == KIND_RELPOSE_TS) {
@@ -461,16 +464,18 @@ __global__ void __launch_bounds__(HYP_WARPS * 32) k5_prep(const RoundDesc R, int
             } else {
                 v = bearing(P.p[2 * side][id], P.p[2 * side + 1][id]);
             }
-            double *o = W->xs + 15 * side + 3 * i;
+            double *o = W + P5_XS + 15 * side + 3 * i;
             o[0] = v.x; o[1] = v.y; o[2] = v.z;
         }
         __syncwarp();
-        solve_5pt_poly(W->xs, W->xs + 15, &W->s5, T, lane);
-        double *blk = out.s5_blk + (size_t)g * S5_BLK;
-        for (int e = lane; e < 39; e += 32) blk[e] = W->s5.A[e];
-        for (int e = lane; e < 36; e += 32) blk[39 + e] = W->s5.Nb[e];
-        if (lane < 30) blk[75 + lane] = W->xs[lane];
-        if (lane < 11) out.s5_cpoly[(size_t)lane * R.n_total + g] = W->s5.cpoly[lane];
+        solve_5pt_poly_grp8(W, T, sl);
+        if (live) {
+            double *blk = out.s5_blk + (size_t)g * S5_BLK;
+            for (int e = sl; e < 39; e += 8) blk[e] = W[P5_A + e];
+            for (int e = sl; e < 36; e += 8) blk[39 + e] = W[P5_NB + e];
+            for (int e = sl; e < 30; e += 8) blk[75 + e] = W[P5_XS + e];
+            for (int k = sl; k < 11; k += 8) out.s5_cpoly[(size_t)k * R.n_total + g] = W[P5_CPOLY + k];
+        }
         __syncwarp();
     }
 }
@@ -1020,7 +1025,7 @@ int device_sm_count() { return sm_count(); }
 static int prep_blocks_per_sm() {
     static int cached = -1;
     if (cached < 0) {
-        const size_t smem = 256 + sizeof(PrepScratch) * HYP_WARPS;
+        const size_t smem = PREP_SMEM;
         cudaFuncSetAttribute(k5_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k5_prep, HYP_WARPS * 32, smem);
@@ -1037,10 +1042,11 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
     if constexpr (KIND == KIND_RELPOSE_TS) mode = 0; // no fp32 screening copy of the 18-array layout: exact scoring
     if (kind_is_relpose(KIND) && (KIND == KIND_RELPOSE_TS || out.s5_blk != nullptr)) {
         int blocks = prep_blocks_per_sm() * sm_count();
-        const int need = (R.n_total + HYP_WARPS - 1) / HYP_WARPS;
+        const int per_cta = HYP_WARPS * PREP_SAMPLES_PER_WARP;
+        const int need = (R.n_total + per_cta - 1) / per_cta;
         if (blocks > need) blocks = need;
         if (blocks < 1) blocks = 1;
-        k5_prep<<<blocks, HYP_WARPS * 32, 256 + sizeof(PrepScratch) * HYP_WARPS, stream>>>(R, work, out);
+        k5_prep<<<blocks, HYP_WARPS * 32, PREP_SMEM, stream>>>(R, work, out);
         k5_roots<<<(R.n_total + 127) / 128, 128, 0, stream>>>(R.n_total, out);
         const int warps = (R.n_total + 2) / 3;
         k5_back<<<(warps * 32 + 127) / 128, 128, 0, stream>>>(R, out);

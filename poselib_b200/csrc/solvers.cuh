@@ -867,6 +867,324 @@ PLB_DEV void solve_5pt_poly(const double *x1s, const double *x2s, Scratch5 *S, c
     }
 }
 
+// ---- the same first half, FOUR samples per warp (k5_prep) ------------------------------------------------------------
+// Most steps of solve_5pt_poly have 4..20-way parallelism, so a whole warp per sample leaves most lanes idle (7.7 k
+// warp-instructions per sample, profiles/r01_v4_summary.md).  Here lanes [8s, 8s+8) own sample s: the serial steps
+// (pivoted QR, LU pivots, back substitution) advance four samples per instruction, and the table-driven steps map a
+// lane to a MONOMIAL (its factor tables live in registers) instead of to a matrix entry.  Every element is computed
+// by the same sequence of operations as in solve_5pt_poly / the reference, so the outputs are bit-identical.
+// Control flow is uniform across the warp (every __syncwarp is reached by all lanes; sample-dependent cases are
+// predicated), which is what allows four independent samples to share the barriers.
+// Per-sample shared scratch W (doubles):  C[200] coefficient matrix (first 36: nullspace tmp) | Q[90] quadratic blocks
+// (before: M[45]; after: A[39] @0, minors[24] @40, cpoly[11] @64) | Nb[36] | xs[30]
+// stride 360 = 8 (mod 16) doubles: the two groups of a half-warp sit 16 banks apart (conflict-free 64-bit accesses)
+constexpr int P5_C = 0, P5_Q = 200, P5_NB = 290, P5_XS = 326, P5_STRIDE = 360;
+constexpr int P5_A = P5_Q, P5_MIN = P5_Q + 40, P5_CPOLY = P5_Q + 64;
+
+// warp_nullspace_9xC for a group of 8 lanes (sl = lane & 7)
+template <int COLS> PLB_DEV void grp8_nullspace_9xC(double *a, double *qn, int sl) {
+    constexpr int ROWS = 9;
+    static_assert(COLS <= 8, "one lane per column");
+    double tau_k[COLS];
+    int rt_k[COLS];
+    const double precision = 2.220446049250313e-16 * double(COLS);
+    double biggest = 0.0;
+    bool stopped = false;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) {
+        const int nr = ROWS - k, cnt = nr * (COLS - k);
+        double best = -1.0;
+        int bord = 0x7fffffff;
+        for (int e = sl; e < cnt; e += 8) {
+            const int c = k + e / nr, r = k + e % nr;
+            const double v = fabs(a[c * ROWS + r]);
+            if (v > best) {
+                best = v;
+                bord = e;
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oo = __shfl_xor_sync(0xffffffffu, bord, o);
+            if (ob > best || (ob == best && oo < bord)) {
+                best = ob;
+                bord = oo;
+            }
+        }
+        if (k == 0) biggest = best;
+        if (!stopped && fabs(best) <= fabs(biggest) * precision) stopped = true;
+        int cb = k, rb = k;
+        if (!stopped) {
+            cb = k + bord / nr;
+            rb = k + bord % nr;
+        }
+        rt_k[k] = rb;
+        if (rb != k && sl >= k && sl < COLS) {
+            const double t = a[sl * ROWS + k];
+            a[sl * ROWS + k] = a[sl * ROWS + rb];
+            a[sl * ROWS + rb] = t;
+        }
+        __syncwarp();
+        if (cb != k) {
+            for (int r = sl; r < ROWS; r += 8) {
+                const double t = a[k * ROWS + r];
+                a[k * ROWS + r] = a[cb * ROWS + r];
+                a[cb * ROWS + r] = t;
+            }
+        }
+        __syncwarp();
+        double tail_sq = 0.0;
+        for (int r = k + 1; r < ROWS; ++r) tail_sq += a[k * ROWS + r] * a[k * ROWS + r];
+        const double c0 = a[k * ROWS + k];
+        double tau = 0.0;
+        __syncwarp();
+        if (!stopped) {
+            double beta;
+            if (tail_sq <= 2.2250738585072014e-308) {
+                beta = c0;
+                for (int r = sl; r < ROWS; r += 8)
+                    if (r > k) a[k * ROWS + r] = 0.0;
+            } else {
+                beta = sqrt(c0 * c0 + tail_sq);
+                if (c0 >= 0) beta = -beta;
+                for (int r = sl; r < ROWS; r += 8)
+                    if (r > k) a[k * ROWS + r] = a[k * ROWS + r] / (c0 - beta);
+                tau = (beta - c0) / beta;
+            }
+            if (sl == k) a[k * ROWS + k] = beta;
+        }
+        tau_k[k] = tau;
+        __syncwarp();
+        if (tau != 0.0 && sl > k && sl < COLS) {
+            double *col = a + sl * ROWS;
+            const double *v = a + k * ROWS;
+            double tmp = 0.0;
+            for (int r = k + 1; r < ROWS; ++r) tmp += v[r] * col[r];
+            tmp += col[k];
+            col[k] -= tau * tmp;
+            for (int r = k + 1; r < ROWS; ++r) col[r] -= tau * v[r] * tmp;
+        }
+        __syncwarp();
+    }
+    if (sl < ROWS - COLS) {
+        double q[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) q[r] = (r == COLS + sl) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = COLS - 1; k >= 0; --k) {
+            const double tau = tau_k[k];
+            const double *v = a + k * ROWS;
+            if (tau != 0.0) {
+                double tmp = 0.0;
+#pragma unroll
+                for (int r = k + 1; r < ROWS; ++r) tmp += v[r] * q[r];
+                tmp += q[k];
+                q[k] -= tau * tmp;
+#pragma unroll
+                for (int r = k + 1; r < ROWS; ++r) q[r] -= tau * v[r] * tmp;
+            }
+            const int rt = rt_k[k];
+            if (rt != k) {
+                const double qk = q[k];
+                double qr = 0.0;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r)
+                    if (r == rt) qr = q[r];
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r)
+                    if (r == rt) q[r] = qk;
+                q[k] = qr;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) qn[sl * ROWS + r] = q[r];
+    }
+    __syncwarp();
+}
+
+// W: this sample's scratch (xs filled, see layout above); on return Nb, A (P5_A), cpoly (P5_CPOLY) are valid.
+PLB_DEV void solve_5pt_poly_grp8(double *W, const MonoTables *T, int sl) {
+    double *C = W + P5_C, *Q = W + P5_Q, *Nb = W + P5_NB;
+    const double *x1s = W + P5_XS, *x2s = W + P5_XS + 15;
+    // ---- 9x5 epipolar constraints (relpose_5pt.cc:163-166), M aliases Q
+    double *M = Q;
+    for (int e = sl; e < 45; e += 8) {
+        const int i = e / 9, k = e % 9;
+        M[e] = x1s[3 * i + k / 3] * x2s[3 * i + k % 3];
+    }
+    __syncwarp();
+    grp8_nullspace_9xC<5>(M, C /*tmp: 36 doubles*/, sl);
+    for (int e = sl; e < 36; e += 8) {
+        const int r = e / 9, k = e % 9;
+        Nb[4 * k + r] = C[9 * r + k];
+    }
+    __syncwarp();
+#define PLB_EE(i, j) (Nb + 4 * (3 * (j) + (i)))
+    // ---- quadratic building blocks (:113-123,129-144): lane <-> quadratic monomial m, blocks unrolled
+#pragma unroll 1
+    for (int m = sl; m < 10; m += 8) {
+        const int qi = T->quad_i[m], qj = T->quad_j[m];
+#pragma unroll
+        for (int blk = 0; blk < 9; ++blk) {
+            double v = 0.0;
+            if (blk < 6) {
+                const int i = (blk < 3) ? 0 : (blk < 5 ? 1 : 2);
+                const int j = (blk < 3) ? blk : (blk < 5 ? blk - 2 : 2);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v = lin_mul_coef(v, PLB_EE(i, k), PLB_EE(j, k), qi, qj, 1.0);
+            } else {
+                const int t = blk - 6;
+                const int c1 = (t == 0) ? 1 : (t == 1 ? 2 : 0);
+                const int c2 = (t == 0) ? 2 : (t == 1 ? 0 : 1);
+                v = lin_mul_coef(v, PLB_EE(0, c1), PLB_EE(1, c2), qi, qj, 1.0);
+                v = lin_mul_coef(v, PLB_EE(0, c2), PLB_EE(1, c1), qi, qj, -1.0);
+            }
+            Q[10 * blk + m] = v;
+        }
+        // trace subtraction (:139-144) touches only this lane's monomial
+        const double t = 0.5 * (Q[m] + Q[30 + m] + Q[50 + m]);
+        Q[m] -= t;
+        Q[30 + m] -= t;
+        Q[50 + m] -= t;
+    }
+    __syncwarp();
+    // ---- 10 x 20 coefficient matrix (:146-154 rows 0..8, :113-125 row 9): lane <-> cubic monomial ci
+#pragma unroll 1
+    for (int ci = sl; ci < 20; ci += 8) {
+        const int np = T->cub_n[ci];
+        const int q0 = T->cub_q[ci][0], q1 = T->cub_q[ci][1], q2 = T->cub_q[ci][2];
+        const int l0 = T->cub_l[ci][0], l1 = T->cub_l[ci][1], l2 = T->cub_l[ci][2];
+#pragma unroll
+        for (int row = 0; row < 10; ++row) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double *Qb, *Lk;
+                if (row < 9) {
+                    const int i = row / 3, j = row % 3;
+                    const int lo = i < k ? i : k, hi = i < k ? k : i;
+                    const int blk = (lo == 0) ? hi : (lo == 1 ? 2 + hi : 5);
+                    Qb = Q + 10 * blk;
+                    Lk = PLB_EE(k, j);
+                } else {
+                    Qb = Q + 10 * (6 + k);
+                    Lk = PLB_EE(2, k);
+                }
+                v += Qb[q0] * Lk[l0];
+                if (np > 1) v += Qb[q1] * Lk[l1];
+                if (np > 2) v += Qb[q2] * Lk[l2];
+            }
+            C[row * 20 + ci] = v;
+        }
+    }
+    __syncwarp();
+#undef PLB_EE
+    // ---- [A | B] -> A^{-1} B by partial-pivot LU with the forward substitution fused (:173)
+    for (int k = 0; k < 10; ++k) {
+        int p = k;
+        double best = fabs(C[k * 20 + k]);
+        for (int r = k + 1; r < 10; ++r) {
+            const double v = fabs(C[r * 20 + k]);
+            if (v > best) {
+                best = v;
+                p = r;
+            }
+        }
+        __syncwarp();
+        if (best != 0.0 && p != k) {
+            for (int c = sl; c < 20; c += 8) {
+                const double t = C[k * 20 + c];
+                C[k * 20 + c] = C[p * 20 + c];
+                C[p * 20 + c] = t;
+            }
+        }
+        __syncwarp();
+        const double pv = C[k * 20 + k];
+        __syncwarp();
+        if (best != 0.0) {
+            for (int r = sl; r < 10; r += 8)
+                if (r > k) C[r * 20 + k] /= pv;
+        }
+        __syncwarp();
+        for (int c = k + 1 + sl; c < 20; c += 8) {
+            const double ckc = C[k * 20 + c];
+            for (int r = k + 1; r < 10; ++r) C[r * 20 + c] -= C[r * 20 + k] * ckc;
+        }
+        __syncwarp();
+    }
+    for (int c = 10 + sl; c < 20; c += 8) {
+        for (int r = 9; r >= 0; --r) {
+            double s = C[r * 20 + c];
+            for (int k = r + 1; k < 10; ++k) s -= C[r * 20 + k] * C[k * 20 + c];
+            C[r * 20 + c] = s / C[r * 20 + r];
+        }
+    }
+    __syncwarp();
+    // ---- 3 x 13 polynomial matrix (:176-189); A aliases the dead quadratic blocks
+    double *A = W + P5_A;
+    for (int e = sl; e < 39; e += 8) {
+        const int i = e / 13, c = e % 13;
+        const double *top = C + (4 + 2 * i) * 20 + 10, *bot = C + (5 + 2 * i) * 20 + 10;
+        const int g0 = (c < 4) ? 0 : (c < 8 ? 4 : 8), src0 = (c < 4) ? 0 : (c < 8 ? 3 : 6);
+        const int w = (c < 8) ? 3 : 4, o = c - g0;
+        double v = 0.0;
+        if (o >= 1) v = top[src0 + o - 1];
+        if (o < w) v -= bot[src0 + o];
+        A[e] = v;
+    }
+    __syncwarp();
+    // ---- det(A(z)) as a degree-10 polynomial, ascending coefficients (:191-352)
+    {
+        auto P = [&](int i, int j, int k) -> double {
+            return (j == 0) ? A[13 * i + 3 - k] : (j == 1 ? A[13 * i + 7 - k] : A[13 * i + 12 - k]);
+        };
+        double *minors = W + P5_MIN;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { // minor t, coefficient k = sl
+            const int k = sl;
+            const int ja = (t == 0) ? 1 : 0, jb = (t == 2) ? 1 : 2;
+            const int da = 3, db = (jb == 2) ? 4 : 3;
+            double v = 0.0;
+            if (k <= da + db) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int i = 0; i <= da; ++i) {
+                    const int j = k - i;
+                    if (j >= 0 && j <= db) s1 += P(1, ja, i) * P(2, jb, j);
+                }
+                for (int i = 0; i <= db; ++i) {
+                    const int j = k - i;
+                    if (j >= 0 && j <= da) s2 += P(1, jb, i) * P(2, ja, j);
+                }
+                v = s1 - s2;
+            }
+            minors[8 * t + k] = v;
+        }
+        __syncwarp();
+        for (int k = sl; k < 11; k += 8) {
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            for (int i = 0; i <= 3; ++i) {
+                const int j = k - i;
+                if (j >= 0 && j <= 7) t0 += P(0, 0, i) * minors[j];
+            }
+            for (int i = 0; i <= 3; ++i) {
+                const int j = k - i;
+                if (j >= 0 && j <= 7) t1 += P(0, 1, i) * minors[8 + j];
+            }
+            for (int i = 0; i <= 4; ++i) {
+                const int j = k - i;
+                if (j >= 0 && j <= 6) t2 += P(0, 2, i) * minors[16 + j];
+            }
+            double c = 0.0;
+            c += t0;
+            c -= t1;
+            c += t2;
+            W[P5_CPOLY + k] = c;
+        }
+        __syncwarp();
+    }
+}
+
 // Back-substitution for one root z of the determinant polynomial: E (row-major 9) from the polynomial matrix A (3x13)
 // and the nullspace basis Nb (relpose_5pt.cc:359-392).
 PLB_DEV void backsub_5pt(const double *A, const double *Nb, double z, double *E) {
