@@ -480,17 +480,20 @@ __global__ void __launch_bounds__(HYP_WARPS * 32) k5_prep(const RoundDesc R, int
     }
 }
 
-__global__ void __launch_bounds__(128) k5_roots(int n_total, HypOut out) {
+constexpr int ROOTS_THREADS = 64;
+__global__ void __launch_bounds__(ROOTS_THREADS) k5_roots(int n_total, HypOut out) {
+    __shared__ RootsShared S[ROOTS_THREADS / 32];
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_total) return;
+    const bool has = g < n_total;
     double c[11], roots[10];
 #pragma unroll
-    for (int k = 0; k < 11; ++k) c[k] = out.s5_cpoly[(size_t)k * n_total + g];
-    SturmWork w;
-    const int n = sturm_bisect10(c, roots, &w);
-    out.s5_nroots[g] = n;
-    double *o = out.s5_roots + (size_t)g * 10;
-    for (int k = 0; k < n; ++k) o[k] = roots[k];
+    for (int k = 0; k < 11; ++k) c[k] = has ? out.s5_cpoly[(size_t)k * n_total + g] : 0.0;
+    const int n = sturm_bisect10_warp(c, has, roots, &S[threadIdx.x >> 5], threadIdx.x & 31);
+    if (has) {
+        out.s5_nroots[g] = n;
+        double *o = out.s5_roots + (size_t)g * 10;
+        for (int k = 0; k < n; ++k) o[k] = roots[k];
+    }
 }
 
 __global__ void __launch_bounds__(128) k5_back(const RoundDesc R, HypOut out) {
@@ -1047,7 +1050,7 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
         if (blocks > need) blocks = need;
         if (blocks < 1) blocks = 1;
         k5_prep<<<blocks, HYP_WARPS * 32, PREP_SMEM, stream>>>(R, work, out);
-        k5_roots<<<(R.n_total + 127) / 128, 128, 0, stream>>>(R.n_total, out);
+        k5_roots<<<(R.n_total + ROOTS_THREADS - 1) / ROOTS_THREADS, ROOTS_THREADS, 0, stream>>>(R.n_total, out);
         const int warps = (R.n_total + 2) / 3;
         k5_back<<<(warps * 32 + 127) / 128, 128, 0, stream>>>(R, out);
     } else if constexpr (KIND != KIND_RELPOSE_TS) {

@@ -603,6 +603,172 @@ PLB_DEV int sturm_bisect10(const double *coeffs, double *roots, SturmWork *w) {
     return n_roots;
 }
 
+// ---- warp-cooperative variant used by k5_roots: lane = sample, 32 samples per warp ------------------------------------
+// sturm_bisect10 run by 32 lanes on 32 different polynomials diverges badly (3.8 active lanes per instruction,
+// profiles/r01_v5_summary.md): every lane is at a different point of the interval walk or inside a Ridders/Newton
+// refinement.  The same computation is regrouped into phases that keep the warp converged:
+//   A  Sturm sequence of every lane's polynomial (uniform);
+//   B  interval walk: cheap transitions (pop / split bookkeeping / emit) advance until the lane needs ONE
+//      sturm_signchanges evaluation, which all lanes then execute together; isolated intervals are only RECORDED,
+//      in the order the serial routine would refine them;
+//   C  the recorded intervals of the whole warp are dealt out to the lanes evenly (prefix sum + binary search) and
+//      refined by sturm_ridders_newton with the owner's polynomial read from shared memory;
+//   D  every lane compacts its results in recording order, applying the n_roots < 10 guards of the serial routine.
+// Functions, operands and per-polynomial operation order are those of sturm_bisect10: results are bit-identical.
+constexpr int RT_MAXB = 16; // recorded intervals per polynomial; more (never seen) falls back to the serial routine
+struct RootsShared {        // per warp
+    double fvec[21][32];
+    double a[RT_MAXB][32]; // interval start; overwritten by the refined root
+    double b[RT_MAXB][32]; // interval end;   overwritten by 1.0 / 0.0 = root valid / not
+    int prefix[33];
+};
+// c: 11 ascending coefficients (registers); returns the number of roots written to roots[0..n)
+PLB_DEV int sturm_bisect10_warp(const double *c, bool has_poly, double *roots, RootsShared *S, int lane) {
+    constexpr int N = 10;
+    const double tol = 1e-10;
+    double fvec[21], svec[30];
+    bool done = !has_poly || c[N] == 0.0;
+    {
+        const double c_inv = done ? 1.0 : 1.0 / c[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) fvec[i] = (has_poly ? c[i] : 0.0) * c_inv;
+        fvec[N] = 1.0;
+#pragma unroll
+        for (int i = 0; i < N - 1; ++i) fvec[N + 1 + i] = fvec[i + 1] * ((i + 1) / double(N));
+        fvec[2 * N] = 1.0;
+#pragma unroll
+        for (int i = 0; i < 21; ++i) S->fvec[i][lane] = fvec[i];
+    }
+    sturm_build_seq(fvec, svec);
+    double mx = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) mx = fmax(mx, fabs(fvec[i]));
+    const double r0 = 1.0 + mx;
+    const int s_lo = sturm_signchanges(svec, -r0), s_hi = sturm_signchanges(svec, r0);
+    if (s_lo - s_hi == 0) done = true;
+    // ---- phase B
+    double st_a[12], st_b[12];
+    int st_sa[12], st_sb[12], st_depth[12];
+    int sp = 0, nb = 0;
+    unsigned degenerate = 0; // bit j: recorded interval j is a terminal-width one whose upper end is the root
+    bool overflow = false;
+    if (!done) {
+        st_a[0] = -r0; st_b[0] = r0; st_sa[0] = s_lo; st_sb[0] = s_hi; st_depth[0] = 0;
+        sp = 1;
+    }
+    double a = 0, b = 0;
+    int sa = 0, sb = 0, depth = 0;
+    bool walking = false;
+    for (;;) {
+        bool need = false;
+        double cm = 0.0;
+        while (!done && !need) {
+            if (!walking) {
+                if (sp == 0) {
+                    done = true;
+                    break;
+                }
+                --sp;
+                a = st_a[sp]; b = st_b[sp]; sa = st_sa[sp]; sb = st_sb[sp]; depth = st_depth[sp];
+                walking = true;
+            }
+            if (depth > 300) {
+                walking = false;
+            } else if (b - a < tol) {
+                if (nb < RT_MAXB) {
+                    S->a[nb][lane] = a;
+                    S->b[nb][lane] = b;
+                    degenerate |= 1u << nb;
+                    ++nb;
+                } else {
+                    overflow = true;
+                }
+                walking = false;
+            } else {
+                const int n_rts = sa - sb;
+                if (n_rts > 1) {
+                    cm = (a + b) * 0.5;
+                    need = true;
+                } else {
+                    if (n_rts == 1) {
+                        if (nb < RT_MAXB) {
+                            S->a[nb][lane] = a;
+                            S->b[nb][lane] = b;
+                            ++nb;
+                        } else {
+                            overflow = true;
+                        }
+                    }
+                    walking = false;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, need)) break;
+        int sc = 0;
+        if (need) sc = sturm_signchanges(svec, cm);
+        if (need) {
+            if (sp < 12 && ((sc - sb) >= 1 || (b - cm) < tol)) {
+                st_a[sp] = cm; st_b[sp] = b; st_sa[sp] = sc; st_sb[sp] = sb; st_depth[sp] = depth + 1;
+                ++sp;
+            }
+            b = cm;
+            sb = sc;
+            ++depth;
+        }
+    }
+    // ---- phase C: deal the recorded intervals of the warp out to the lanes
+    int incl = nb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    S->prefix[lane + 1] = incl;
+    if (lane == 0) S->prefix[0] = 0;
+    __syncwarp();
+    const int total = S->prefix[32];
+    for (int t = lane; t < ((total + 31) & ~31); t += 32) {
+        const bool live = t < total;
+        int owner = 0, j = 0;
+        if (live) {
+            int lo = 0, hi = 31; // largest owner with prefix[owner] <= t
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (S->prefix[mid] <= t) lo = mid;
+                else hi = mid - 1;
+            }
+            owner = lo;
+            j = t - S->prefix[owner];
+        }
+        const unsigned deg_owner = __shfl_sync(0xffffffffu, degenerate, owner);
+        if (live) {
+            const double ia = S->a[j][owner], ib = S->b[j][owner];
+            double root = ib;
+            int got = 1;
+            if (!((deg_owner >> j) & 1u)) {
+                double f[21];
+#pragma unroll
+                for (int i = 0; i < 21; ++i) f[i] = S->fvec[i][owner];
+                got = 0;
+                sturm_ridders_newton(f, ia, ib, &root, got, tol);
+            }
+            S->a[j][owner] = root;
+            S->b[j][owner] = got ? 1.0 : 0.0;
+        }
+    }
+    __syncwarp();
+    // ---- phase D
+    int n_roots = 0;
+    for (int j = 0; j < nb; ++j)
+        if (n_roots < 10 && S->b[j][lane] != 0.0) roots[n_roots++] = S->a[j][lane];
+    __syncwarp();
+    if (overflow) { // never observed; keeps the routine total
+        SturmWork w;
+        n_roots = sturm_bisect10(c, roots, &w);
+    }
+    return n_roots;
+}
+
 // ================================ relpose_5pt (Nister) =====================================================
 // Monomial tables, filled once per CTA into shared memory (see fill_tables):
 //   quad_idx[i][j]      : index of lin_i*lin_j in [x^2,xy,xz,x,y^2,yz,y,z^2,z,1]       (relpose_5pt.cc:11-12)
