@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -430,6 +431,19 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         return PLB_OK;
     };
 
+    // host-side phase timer (PLB_PROFILE=1 prints one line per group to stderr)
+    static const bool prof_on = std::getenv("PLB_PROFILE") != nullptr;
+    enum { PH_SETUP, PH_SAMPLE, PH_LAUNCH, PH_WAIT_HYP, PH_SELECT, PH_WAIT_CONF, PH_PASS1, PH_WAIT_LM, PH_PASS2, PH_FINAL, PH_N };
+    double ph[PH_N] = {0};
+    auto ph_t = std::chrono::steady_clock::now();
+    auto mark = [&](int which) {
+        if (!prof_on) return;
+        const auto now = std::chrono::steady_clock::now();
+        ph[which] += std::chrono::duration<double>(now - ph_t).count();
+        ph_t = now;
+    };
+    int n_rounds = 0;
+
     // ---- device layout of the group: SoA arrays of every non-resident problem, masks, ProblemDev table -----------
     size_t in_doubles = 0, soa_elems = 0, mask_bytes = 0, px_elems = 0;
     int max_n = 0, max_n_pad = 0, n_up = 0, n_polish_pnp = 0;
@@ -626,6 +640,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         }
     }
 
+    mark(PH_SETUP);
     // ---- main loop in lock-step rounds ------------------------------------------------------------------------------
     for (PState &S : PS) {
         S.active = S.enough && S.t->opt.max_iterations > 0;
@@ -695,6 +710,8 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 for (auto &x : th) x.join();
             }
         }
+        mark(PH_SAMPLE);
+        ++n_rounds;
         // h_act layout: active[na] | g_off[na+1] | seg_base[na] | seg_cap[na]
         int max_seg_cap = 0;
         {
@@ -757,7 +774,9 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         PLB_CUDA(cudaEventRecord(E.ev1, st));
         E.launches += kind_is_relpose(kind) ? 4 : 2; // k_solve (or k5_prep + k5_roots + k5_back) + k_score
         PLB_CUDA(cudaMemcpyAsync(E.h_work.p, E.work.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        mark(PH_LAUNCH);
         if ((rc = sync_timed(nullptr))) return rc;
+        mark(PH_WAIT_HYP);
         if (E.h_work.p[2] != 0) { // model list overflow: redo the round with the worst-case capacity (no state was touched)
             if (cap_factor >= MAXM) {
                 g_err = "internal error: model capacity exceeded";
@@ -813,6 +832,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 }
             }
             const int nc = (int)cand_slots.size();
+            mark(PH_SELECT);
             if (nc) {
                 if ((rc = E.h_slots.ensure(nc)) || (rc = E.slots.ensure(nc))) return rc;
                 std::copy(cand_slots.begin(), cand_slots.end(), E.h_slots.p);
@@ -829,6 +849,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 h2d += sizeof(int) * nc;
                 PS[act[0]].cnt.models_confirmed += nc;
             }
+            mark(PH_WAIT_CONF);
         }
 
         // ---- pass 1: which models improve the best-minimal state?  (independent of LO results)
@@ -873,6 +894,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             n_imp_tot += (int)S.imp_slot.size();
             n_trig_tot += (int)S.trig.size();
         }
+        mark(PH_PASS1);
         if (n_imp_tot > 0) {
             // gather the improving models of every problem, refine the trigger models in one batched LM launch
             const int ng = n_imp_tot + n_trig_tot;
@@ -897,6 +919,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             if ((rc = launch_lm_jobs(n_trig_tot, true, 9 * (size_t)n_imp_tot))) return rc;
             if ((rc = sync_timed(&lo_wait))) return rc;
         }
+        mark(PH_WAIT_LM);
 
         // ---- pass 2: replay the serial loop over this round, problem by problem -----------------------------------
         for (int a = 0; a < na; ++a) {
@@ -943,6 +966,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 }
             }
         }
+        mark(PH_PASS2);
     }
     for (PState &S : PS)
         if (S.enough) S.stats.iterations = S.it;
@@ -1039,6 +1063,16 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         }
     }
     PLB_CUDA(cudaGetLastError());
+    mark(PH_FINAL);
+    if (prof_on) {
+        double tot = 0;
+        for (int i = 0; i < PH_N; ++i) tot += ph[i];
+        std::fprintf(stderr,
+                     "[plb profile] kind %d problems %d rounds %d total %.2f ms | setup %.2f sample %.2f launch %.2f wait_hyp %.2f "
+                     "select %.2f wait_conf %.2f pass1 %.2f wait_lm %.2f pass2 %.2f final %.2f\n",
+                     kind, NP, n_rounds, 1e3 * tot, 1e3 * ph[0], 1e3 * ph[1], 1e3 * ph[2], 1e3 * ph[3], 1e3 * ph[4], 1e3 * ph[5],
+                     1e3 * ph[6], 1e3 * ph[7], 1e3 * ph[8], 1e3 * ph[9]);
+    }
     // group-level counters are attributed to the first problem; per-problem ones are exact
     PS[0].cnt.lo_seconds = lo_wait;
     PS[0].cnt.gpu_launches = E.launches - launches0;

@@ -809,33 +809,122 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
     __shared__ float ctx[SCR_TM][16];
     __shared__ float red_s[SCR_WARPS][SCR_TM];
     __shared__ uint32_t red_c[SCR_WARPS][SCR_TM];
-    const int a = blockIdx.y;
-    const int count = out.prob_count[a];
-    if (blockIdx.x * SCR_TM >= count) return;
+    // ---- static, cost-balanced partition of the round's (problem, tile) list over the CTAs of the grid ------------
+    // cost of a tile = correspondences of its problem; CTA c owns the tiles whose start cost lies in
+    // [W c / G, W (c+1) / G).  The grid is ONE wave (resident CTAs x SMs), so there is no tail wave; a CTA touches a
+    // contiguous range of problems (usually one or two) and re-stages the shared-memory arrays when it moves on.
+    __shared__ long long s_warp[SCR_WARPS];
+    __shared__ long long s_pre[SCR_THREADS];
+    __shared__ int s_first, s_last;
+    __shared__ long long s_first_pre, s_total, s_clo, s_chi, s_Sa;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int na = R.n_active;
+    auto tiles_of = [&](int a) -> int { return (out.prob_count[a] + SCR_TM - 1) / SCR_TM; };
+    auto n_of = [&](int a) -> int { return R.probs[R.active[a]].n; };
+    const int per = (na + SCR_THREADS - 1) / SCR_THREADS;
+    const int own_lo = min_i(tid * per, na), own_hi = min_i(own_lo + per, na);
+    {
+        long long loc = 0;
+        for (int a = own_lo; a < own_hi; ++a) loc += (long long)tiles_of(a) * n_of(a);
+        long long inc = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        if (tid == 0) {
+            s_first = 0x7fffffff;
+            s_last = -1;
+        }
+        __syncthreads();
+        long long base = 0;
+        for (int w = 0; w < warp; ++w) base += s_warp[w];
+        s_pre[tid] = base + inc - loc;
+        if (tid == SCR_THREADS - 1) s_total = base + inc;
+        __syncthreads();
+    }
+    const long long total_cost = s_total;
+    if (total_cost == 0) return;
+    if (tid == 0) { // kept in shared memory: long-lived 64-bit values would otherwise spill around the hot loop
+        s_clo = total_cost * (long long)blockIdx.x / (long long)gridDim.x;
+        s_chi = total_cost * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
+    }
+    __syncthreads();
+    auto tile_range = [&](long long S, int tiles, int nn, int &t0, int &t1) {
+        // tiles t with c_lo <= S + t*nn < c_hi
+        const long long c_lo = s_clo, c_hi = s_chi;
+        long long a0 = (c_lo > S) ? (c_lo - S + nn - 1) / nn : 0;
+        long long a1 = (c_hi > S) ? (c_hi - S + nn - 1) / nn : 0;
+        if (a1 > tiles) a1 = tiles;
+        t0 = (int)a0;
+        t1 = (int)a1;
+    };
+    {
+        long long S = s_pre[tid];
+        for (int a = own_lo; a < own_hi; ++a) {
+            const int tl = tiles_of(a), nn = n_of(a);
+            if (tl > 0 && nn > 0) {
+                int t0, t1;
+                tile_range(S, tl, nn, t0, t1);
+                if (t0 < t1) {
+                    atomicMin(&s_first, a);
+                    atomicMax(&s_last, a);
+                }
+            }
+            S += (long long)tl * nn;
+        }
+        __syncthreads();
+        if (tid == 0 && s_last >= 0) {
+            const int owner = s_first / per;
+            long long Sf = s_pre[owner];
+            for (int a = owner * per; a < s_first; ++a) Sf += (long long)tiles_of(a) * n_of(a);
+            s_first_pre = Sf;
+        }
+        __syncthreads();
+    }
+    if (s_last < 0) return;
+    if (tid == 0) {
+        s_Sa = s_first_pre;
+        if (use_smem) mbar_init(&bar, 1);
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    for (int a = s_first; a <= s_last; ++a) {
+    const int count = out.prob_count[a];
     const ProblemDev P = R.probs[R.active[a]];
     const int n = P.n, n_pad = (n + 31) & ~31;
+    int t_begin = 0, t_end = 0;
+    {
+        const int tl = (count + SCR_TM - 1) / SCR_TM;
+        const long long S_a = s_Sa;
+        if (tl > 0 && n > 0) tile_range(S_a, tl, n, t_begin, t_end);
+        __syncthreads();
+        if (tid == 0) s_Sa = S_a + (long long)tl * n;
+        __syncthreads();
+    }
+    if (t_begin >= t_end) continue;
     const float thr = (float)P.sq_thr;
     const int seg = out.seg_base[a];
     const float *arr[NARR];
     if (use_smem) {
         float *pts = reinterpret_cast<float *>(scr_smem);
-        if (tid == 0) mbar_init(&bar, 1);
-        __syncthreads();
+        __syncthreads(); // every thread is done with the previous problem's arrays
         if (tid == 0) {
             const uint32_t bytes = (uint32_t)n_pad * 4u;
             mbar_expect_tx(&bar, bytes * NARR);
 #pragma unroll
             for (int c = 0; c < NARR; ++c) tma_bulk_g2s(pts + (size_t)c * n_pad, P.f[c], bytes, &bar);
         }
-        mbar_wait(&bar, 0);
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
 #pragma unroll
         for (int c = 0; c < NARR; ++c) arr[c] = pts + (size_t)c * n_pad;
     } else {
 #pragma unroll
         for (int c = 0; c < NARR; ++c) arr[c] = P.f[c];
     }
-    for (int m0 = blockIdx.x * SCR_TM; m0 < count; m0 += gridDim.x * SCR_TM) {
+    for (int m0 = t_begin * SCR_TM; m0 < t_end * SCR_TM; m0 += SCR_TM) {
         const int tm = (count - m0 < SCR_TM) ? (count - m0) : SCR_TM;
         __syncthreads();
         if (tid < tm) {
@@ -964,6 +1053,7 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
             out.fscores[seg + m0 + tid] = st;
         }
     }
+    } // problems of this CTA
 }
 
 // Exact fp64 rescoring of a list of model slots (fast mode confirmation): one CTA per listed slot.
@@ -1078,12 +1168,16 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
             cudaFuncSetAttribute(k_screen<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_done = true;
         }
-        int tiles = (out.max_seg_cap + SCR_TM - 1) / SCR_TM;
-        const int per_sm = use_smem ? std::max(1, (int)((220 * 1024) / (bytes + 2048))) : 4;
-        int gx = (2 * per_sm * sm_count() + R.n_active - 1) / R.n_active;
-        if (gx > tiles) gx = tiles;
+        // one wave: resident CTAs per SM (occupancy API for this shared-memory size) x SMs; the kernel partitions the
+        // (problem, tile) list over the CTAs by cost itself
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_screen<KIND>, SCR_THREADS, use_smem ? bytes : 0);
+        if (per_sm < 1) per_sm = 1;
+        long long tiles = ((long long)out.max_seg_cap + SCR_TM - 1) / SCR_TM * (long long)R.n_active;
+        int gx = per_sm * sm_count();
+        if ((long long)gx > tiles) gx = (int)tiles;
         if (gx < 1) gx = 1;
-        k_screen<KIND><<<dim3(gx, R.n_active, 1), SCR_THREADS, use_smem ? bytes : 0, stream>>>(R, out, use_smem);
+        k_screen<KIND><<<gx, SCR_THREADS, use_smem ? bytes : 0, stream>>>(R, out, use_smem);
     }
 }
 void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, int mode, int max_n_pad,
