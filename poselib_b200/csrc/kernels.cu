@@ -969,12 +969,16 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
             }
         }
         if (KIND != KIND_PNP) {
-            // 2D-2D kinds.  sc[i] accumulates sum over inliers of (r2 - thr); n*thr is added at the end, so the common
-            // (outlier) path is: two 2x3 products, the residual numerator/denominator, one multiply, one compare — the
-            // division only happens for correspondences under the threshold.  SCR_PB correspondences per thread per
-            // step reuse the 9 model constants fetched (broadcast) from shared memory.
+            // 2D-2D kinds.  sc[i] accumulates sum over inliers of (r2 - thr); n*thr is added at the end.
+            // The streaming pass is branch-free: two 2x3 products, the residual numerator / denominator, one multiply,
+            // one compare, and a predicated OR that records "correspondence q of this lane is under the threshold for
+            // model i" in a per-lane bit mask.  SCR_PB correspondences per thread per step reuse the 9 model
+            // constants fetched (broadcast) from shared memory.  The rare under-threshold cases (cheirality test,
+            // division, accumulation) are handled afterwards in a compacted loop in which every lane pops one of ITS
+            // recorded cases per iteration — handled inline they cost a divergent ~60-instruction detour for the
+            // whole warp whenever one lane of 32 hits (35 % of all issued instructions, profiles/r01_v6_summary.md).
             constexpr int SCR_PB = 4;
-            auto eval = [&](const float *M, float a0, float a1, float b0, float b1, uint32_t &c, float &sacc) {
+            auto numden = [&](const float *M, float a0, float a1, float b0, float b1, float &num, float &den) {
                 const float m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5], m6 = M[6], m7 = M[7], m8 = M[8];
                 if (KIND == KIND_HOMOG) {
                     const float h0 = fmaf(m0, a0, fmaf(m1, a1, m2));
@@ -982,11 +986,8 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
                     const float w = fmaf(m6, a0, fmaf(m7, a1, m8));
                     // |h/w - b|^2 < thr  <=>  |h - w b|^2 < thr w^2
                     const float d0 = fmaf(-w, b0, h0), d1 = fmaf(-w, b1, h1);
-                    const float num = fmaf(d0, d0, d1 * d1), den = w * w;
-                    if (num < thr * den) {
-                        ++c;
-                        sacc += __fdividef(num, den) - thr;
-                    }
+                    num = fmaf(d0, d0, d1 * d1);
+                    den = w * w;
                 } else {
                     const float e0 = fmaf(m0, a0, fmaf(m1, a1, m2));
                     const float e1 = fmaf(m3, a0, fmaf(m4, a1, m5));
@@ -994,39 +995,82 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
                     const float f0 = fmaf(m0, b0, fmaf(m3, b1, m6));
                     const float f1 = fmaf(m1, b0, fmaf(m4, b1, m7));
                     const float Cn = fmaf(b0, e0, fmaf(b1, e1, e2));
-                    const float den = fmaf(e0, e0, fmaf(e1, e1, fmaf(f0, f0, f1 * f1)));
-                    const float num = Cn * Cn;
-                    if (num < thr * den) {
-                        bool inl = true;
-                        if (KIND == KIND_RELPOSE) inl = cheirality32(M + 9, a0, a1, b0, b1);
-                        if (inl) {
-                            ++c;
-                            sacc += __fdividef(num, den) - thr;
+                    den = fmaf(e0, e0, fmaf(e1, e1, fmaf(f0, f0, f1 * f1)));
+                    num = Cn * Cn;
+                }
+            };
+            for (int base = 0; base < n; base += 32 * SCR_THREADS) {
+                const int lim = min_i(n, base + 32 * SCR_THREADS);
+                uint32_t hit[SCR_TM];
+#pragma unroll
+                for (int i = 0; i < SCR_TM; ++i) hit[i] = 0u;
+                int k0 = base + tid;
+                uint32_t qbit = 1u;
+                for (; k0 + (SCR_PB - 1) * SCR_THREADS < lim; k0 += SCR_THREADS * SCR_PB, qbit <<= SCR_PB) {
+                    float a0[SCR_PB], a1[SCR_PB], b0[SCR_PB], b1[SCR_PB];
+#pragma unroll
+                    for (int j = 0; j < SCR_PB; ++j) {
+                        const int k = k0 + j * SCR_THREADS;
+                        a0[j] = arr[0][k]; a1[j] = arr[1][k]; b0[j] = arr[2][k]; b1[j] = arr[3][k];
+                    }
+#pragma unroll
+                    for (int i = 0; i < SCR_TM; ++i) {
+                        if (i < tm) {
+#pragma unroll
+                            for (int j = 0; j < SCR_PB; ++j) {
+                                float num, den;
+                                numden(ctx[i], a0[j], a1[j], b0[j], b1[j], num, den);
+                                if (num < thr * den) hit[i] |= qbit << j;
+                            }
                         }
                     }
                 }
-            };
-            int k0 = tid;
-            for (; k0 + (SCR_PB - 1) * SCR_THREADS < n; k0 += SCR_THREADS * SCR_PB) {
-                float a0[SCR_PB], a1[SCR_PB], b0[SCR_PB], b1[SCR_PB];
+                for (; k0 < lim; k0 += SCR_THREADS, qbit <<= 1) { // remainder
+                    const float a0 = arr[0][k0], a1 = arr[1][k0], b0 = arr[2][k0], b1 = arr[3][k0];
 #pragma unroll
-                for (int j = 0; j < SCR_PB; ++j) {
-                    const int k = k0 + j * SCR_THREADS;
-                    a0[j] = arr[0][k]; a1[j] = arr[1][k]; b0[j] = arr[2][k]; b1[j] = arr[3][k];
-                }
-#pragma unroll
-                for (int i = 0; i < SCR_TM; ++i) {
-                    if (i < tm) {
-#pragma unroll
-                        for (int j = 0; j < SCR_PB; ++j) eval(ctx[i], a0[j], a1[j], b0[j], b1[j], cnt[i], sc[i]);
+                    for (int i = 0; i < SCR_TM; ++i) {
+                        if (i < tm) {
+                            float num, den;
+                            numden(ctx[i], a0, a1, b0, b1, num, den);
+                            if (num < thr * den) hit[i] |= qbit;
+                        }
                     }
                 }
-            }
-            for (; k0 < n; k0 += SCR_THREADS) { // remainder
-                const float a0 = arr[0][k0], a1 = arr[1][k0], b0 = arr[2][k0], b1 = arr[3][k0];
+                // compacted handling of the recorded cases
+                for (;;) {
+                    int mi = -1;
+                    uint32_t hm = 0u;
 #pragma unroll
-                for (int i = 0; i < SCR_TM; ++i)
-                    if (i < tm) eval(ctx[i], a0, a1, b0, b1, cnt[i], sc[i]);
+                    for (int i = 0; i < SCR_TM; ++i)
+                        if (mi < 0 && hit[i] != 0u) {
+                            mi = i;
+                            hm = hit[i];
+                        }
+                    if (!__any_sync(0xffffffffu, mi >= 0)) break;
+                    if (mi >= 0) {
+                        const int q = __ffs((int)hm) - 1;
+                        const uint32_t cleared = hm & (hm - 1u);
+#pragma unroll
+                        for (int i = 0; i < SCR_TM; ++i)
+                            if (i == mi) hit[i] = cleared;
+                        const int k = base + tid + q * SCR_THREADS;
+                        const float a0 = arr[0][k], a1 = arr[1][k], b0 = arr[2][k], b1 = arr[3][k];
+                        const float *M = ctx[mi];
+                        float num, den;
+                        numden(M, a0, a1, b0, b1, num, den);
+                        bool inl = true;
+                        if (KIND == KIND_RELPOSE) inl = cheirality32(M + 9, a0, a1, b0, b1);
+                        if (inl) {
+                            const float v = __fdividef(num, den) - thr;
+#pragma unroll
+                            for (int i = 0; i < SCR_TM; ++i)
+                                if (i == mi) {
+                                    ++cnt[i];
+                                    sc[i] += v;
+                                }
+                        }
+                    }
+                }
             }
         }
 #pragma unroll
