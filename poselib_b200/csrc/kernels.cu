@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 #include "solvers.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 
@@ -2116,11 +2117,19 @@ __global__ void __launch_bounds__(LM_THREADS)
 template <int KIND>
 static void launch_lm_t(const ProblemDev *probs, const LmJob *jobs, const double *models_in, int n_jobs, int max_n,
                         const char *mask_base, int *idx_scratch, LmJobOut *out, cudaStream_t stream) {
-    int csize = (max_n + 2047) / 2048; // >= ~8 correspondences per thread before another CTA pays off
+    static const int per_cta = [] { // correspondences per CTA before another CTA of the cluster pays off
+        const char *e = std::getenv("PLB_LM_PER_CTA");
+        const int v = e ? std::atoi(e) : 0;
+        return v > 0 ? v : 2048;
+    }();
+    int csize = (max_n + per_cta - 1) / per_cta;
     if (csize < 1) csize = 1;
     if (csize > LM_MAX_CLUSTER) csize = LM_MAX_CLUSTER;
     if (csize > 4 && csize < 8) csize = 4;
     if (csize == 3) csize = 2;
+    // k_lm needs the whole register file of an SM per CTA: with many jobs in one launch (batch groups) wide clusters
+    // only take SMs away from the co-running hypothesis kernels, so the cluster shrinks as the job count grows
+    while (csize > 1 && n_jobs * csize > sm_count() / 2) csize /= 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(n_jobs * csize), 1, 1);
