@@ -497,62 +497,110 @@ __global__ void __launch_bounds__(ROOTS_THREADS) k5_roots(int n_total, HypOut ou
     }
 }
 
+// A warp owns 32 consecutive samples.  Their real roots (0..10 each, ~2.6 on average) are dealt out to the lanes in
+// passes of up to 32 roots made of WHOLE samples, so that the per-sample model count / segment reservation stays a
+// warp-local segmented sum; a fixed lane = (sample, root slot) mapping keeps only ~8 of 32 lanes busy.
 __global__ void __launch_bounds__(128) k5_back(const RoundDesc R, HypOut out) {
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int si = lane / 10, r = lane % 10;
-    const int g = 3 * gw + si;
-    const bool live = (si < 3) && (g < R.n_total);
-    int nr = 0;
-    if (live) nr = out.s5_nroots[g];
-    const bool valid = live && r < nr;
-    double cand[4][7];
-    unsigned mask = 0;
-    if (valid) {
-        const double *blk = out.s5_blk + (size_t)g * S5_BLK;
-        double E[9];
-        backsub_5pt(blk, blk + 39, out.s5_roots[(size_t)g * 10 + r], E);
-        mask = motions_from_E(E, blk + 75, blk + 90, 5, cand);
-    }
-    const int mine = __popc(mask);
-    // exclusive prefix inside the 10-lane segment of the sample (root-major, candidate-minor order of the reference)
-    int pre = 0, total = 0;
-#pragma unroll
-    for (int j = 0; j < 10; ++j) {
-        const int v = __shfl_sync(0xffffffffu, mine, (10 * si + j) & 31);
-        if (j < r) pre += v;
-        total += v;
-    }
-    int base = 0, pidx = 0;
-    if (live && r == 0) {
-        const int aslot = sample_problem_slot(R, g);
-        pidx = __ldg(R.active + aslot);
-        if (total) {
-            const int loc = atomicAdd(out.prob_count + aslot, total);
-            if (loc + total > __ldg(out.seg_cap + aslot)) {
-                atomicExch(out.overflow, 1);
-                total = 0;
-            }
-            base = __ldg(out.seg_base + aslot) + loc;
+    __shared__ int s_incl[4][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    if (g0 >= R.n_total) return; // whole warp
+    int *P = s_incl[w];
+    {
+        const int gs = g0 + lane;
+        const bool has = gs < R.n_total;
+        const int nr = has ? out.s5_nroots[gs] : 0;
+        if (has && nr == 0) { // no essential matrix, no model
+            out.n_models[gs] = 0;
+            out.first_slot[gs] = 0;
         }
-        out.n_models[g] = total;
-        out.first_slot[g] = base;
+        int incl = nr;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        P[lane + 1] = incl;
+        if (lane == 0) P[0] = 0;
     }
-    base = __shfl_sync(0xffffffffu, base, (10 * si) & 31);
-    total = __shfl_sync(0xffffffffu, total, (10 * si) & 31);
-    pidx = __shfl_sync(0xffffffffu, pidx, (10 * si) & 31);
-    if (valid && total) {
-        int pos = base + pre;
+    __syncwarp();
+    const int T = P[32];
+    const int my_incl = P[lane + 1];
+    int b0 = 0;
+    while (b0 < 32) {
+        const int base_roots = P[b0];
+        if (base_roots == T) break;
+        // samples [b0, e) = the longest run whose roots fit into the 32 lanes (a sample has <= 10 roots, so e > b0)
+        const unsigned fm = __ballot_sync(0xffffffffu, lane >= b0 && (my_incl - base_roots) <= 32);
+        const int e = b0 + __popc(fm);
+        const int cnt = P[e] - base_roots;
+        const bool valid = lane < cnt;
+        int s = b0, r = 0, nrs = 0;
+        if (valid) {
+            const int t = base_roots + lane;
+            int lo = b0, hi = e - 1; // largest s with P[s] <= t
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (P[mid] <= t) lo = mid;
+                else hi = mid - 1;
+            }
+            s = lo;
+            r = t - P[s];
+            nrs = P[s + 1] - P[s];
+        }
+        const int g = g0 + s;
+        double cand[4][7];
+        unsigned mask = 0;
+        if (valid) {
+            const double *blk = out.s5_blk + (size_t)g * S5_BLK;
+            double E[9];
+            backsub_5pt(blk, blk + 39, out.s5_roots[(size_t)g * 10 + r], E);
+            mask = motions_from_E(E, blk + 75, blk + 90, 5, cand);
+        }
+        const int mine = __popc(mask);
+        // exclusive prefix / total inside the sample's lane segment (root-major, candidate-minor order of the reference)
+        const int start = lane - r;
+        int pre = 0, total = 0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (mask & (1u << c)) {
-                double *o = out.models + (size_t)pos * 7;
-#pragma unroll
-                for (int k = 0; k < 7; ++k) o[k] = cand[c][k];
-                out.model_prob[pos] = pidx;
-                ++pos;
+        for (int j = 0; j < 10; ++j) {
+            const int v = __shfl_sync(0xffffffffu, mine, (start + j) & 31);
+            if (j < nrs) {
+                if (j < r) pre += v;
+                total += v;
             }
         }
+        int base = 0, pidx = 0;
+        if (valid && r == 0) {
+            const int aslot = sample_problem_slot(R, g);
+            pidx = __ldg(R.active + aslot);
+            if (total) {
+                const int loc = atomicAdd(out.prob_count + aslot, total);
+                if (loc + total > __ldg(out.seg_cap + aslot)) {
+                    atomicExch(out.overflow, 1);
+                    total = 0;
+                }
+                base = __ldg(out.seg_base + aslot) + loc;
+            }
+            out.n_models[g] = total;
+            out.first_slot[g] = base;
+        }
+        base = __shfl_sync(0xffffffffu, base, start & 31);
+        total = __shfl_sync(0xffffffffu, total, start & 31);
+        pidx = __shfl_sync(0xffffffffu, pidx, start & 31);
+        if (valid && total) {
+            int pos = base + pre;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (mask & (1u << c)) {
+                    double *o = out.models + (size_t)pos * 7;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) o[k] = cand[c][k];
+                    out.model_prob[pos] = pidx;
+                    ++pos;
+                }
+            }
+        }
+        b0 = e;
     }
 }
 
@@ -1186,7 +1234,7 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
         if (blocks < 1) blocks = 1;
         k5_prep<<<blocks, HYP_WARPS * 32, PREP_SMEM, stream>>>(R, work, out);
         k5_roots<<<(R.n_total + ROOTS_THREADS - 1) / ROOTS_THREADS, ROOTS_THREADS, 0, stream>>>(R.n_total, out);
-        const int warps = (R.n_total + 2) / 3;
+        const int warps = (R.n_total + 31) / 32;
         k5_back<<<(warps * 32 + 127) / 128, 128, 0, stream>>>(R, out);
     } else if constexpr (KIND != KIND_RELPOSE_TS) {
         int blocks = solve_blocks_per_sm<KIND>() * sm_count();
