@@ -1187,10 +1187,27 @@ PLB_DEV void solve_5pt_poly_grp8(double *W, const MonoTables *T, int sl) {
     }
     __syncwarp();
 #define PLB_EE(i, j) (Nb + 4 * (3 * (j) + (i)))
-    // ---- quadratic building blocks (:113-123,129-144): lane <-> quadratic monomial m, blocks unrolled
+    // ---- quadratic building blocks (:113-123,129-144): lane <-> quadratic monomial m.  The 2 x 9 nullspace
+    // coefficients the monomial needs are read into registers once (the kernel is bound by shared-memory wavefronts).
 #pragma unroll 1
     for (int m = sl; m < 10; m += 8) {
         const int qi = T->quad_i[m], qj = T->quad_j[m];
+        const bool same = qi == qj;
+        double ei[3][3], ej[3][3]; // [row i][col j] of E: coefficient of basis qi / qj
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                ei[i][j] = PLB_EE(i, j)[qi];
+                ej[i][j] = PLB_EE(i, j)[qj];
+            }
+        // acc + sgn * (a*b) in the accumulation order of lin_mul_coef
+        auto lmc = [&](double acc, int ia, int ja, int ib, int jb, double sgn) -> double {
+            acc = acc + sgn * (ei[ia][ja] * ej[ib][jb]);
+            if (!same) acc = acc + sgn * (ej[ia][ja] * ei[ib][jb]);
+            return acc;
+        };
+        double qv[9];
 #pragma unroll
         for (int blk = 0; blk < 9; ++blk) {
             double v = 0.0;
@@ -1198,50 +1215,81 @@ PLB_DEV void solve_5pt_poly_grp8(double *W, const MonoTables *T, int sl) {
                 const int i = (blk < 3) ? 0 : (blk < 5 ? 1 : 2);
                 const int j = (blk < 3) ? blk : (blk < 5 ? blk - 2 : 2);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) v = lin_mul_coef(v, PLB_EE(i, k), PLB_EE(j, k), qi, qj, 1.0);
+                for (int k = 0; k < 3; ++k) v = lmc(v, i, k, j, k, 1.0);
             } else {
                 const int t = blk - 6;
                 const int c1 = (t == 0) ? 1 : (t == 1 ? 2 : 0);
                 const int c2 = (t == 0) ? 2 : (t == 1 ? 0 : 1);
-                v = lin_mul_coef(v, PLB_EE(0, c1), PLB_EE(1, c2), qi, qj, 1.0);
-                v = lin_mul_coef(v, PLB_EE(0, c2), PLB_EE(1, c1), qi, qj, -1.0);
+                v = lmc(v, 0, c1, 1, c2, 1.0);
+                v = lmc(v, 0, c2, 1, c1, -1.0);
             }
-            Q[10 * blk + m] = v;
+            qv[blk] = v;
         }
         // trace subtraction (:139-144) touches only this lane's monomial
-        const double t = 0.5 * (Q[m] + Q[30 + m] + Q[50 + m]);
-        Q[m] -= t;
-        Q[30 + m] -= t;
-        Q[50 + m] -= t;
+        const double t = 0.5 * (qv[0] + qv[3] + qv[5]);
+        qv[0] -= t;
+        qv[3] -= t;
+        qv[5] -= t;
+#pragma unroll
+        for (int blk = 0; blk < 9; ++blk) Q[10 * blk + m] = qv[blk];
     }
     __syncwarp();
-    // ---- 10 x 20 coefficient matrix (:146-154 rows 0..8, :113-125 row 9): lane <-> cubic monomial ci
+    // ---- 10 x 20 coefficient matrix (:146-154 rows 0..8, :113-125 row 9): lane <-> cubic monomial ci; the linear
+    // factors (27 values) are read once per monomial, the quadratic ones once per row group
 #pragma unroll 1
     for (int ci = sl; ci < 20; ci += 8) {
         const int np = T->cub_n[ci];
         const int q0 = T->cub_q[ci][0], q1 = T->cub_q[ci][1], q2 = T->cub_q[ci][2];
         const int l0 = T->cub_l[ci][0], l1 = T->cub_l[ci][1], l2 = T->cub_l[ci][2];
+        double L0[3][3], L1[3][3], L2[3][3]; // [k][j]: PLB_EE(k, j)[l_p]
 #pragma unroll
-        for (int row = 0; row < 10; ++row) {
-            double v = 0.0;
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double *Lk = PLB_EE(k, j);
+                L0[k][j] = Lk[l0];
+                L1[k][j] = Lk[l1];
+                L2[k][j] = Lk[l2];
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { // i = 3: the determinant row
+            double Q0[3], Q1[3], Q2[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const double *Qb, *Lk;
-                if (row < 9) {
-                    const int i = row / 3, j = row % 3;
+                int blk;
+                if (i < 3) {
                     const int lo = i < k ? i : k, hi = i < k ? k : i;
-                    const int blk = (lo == 0) ? hi : (lo == 1 ? 2 + hi : 5);
-                    Qb = Q + 10 * blk;
-                    Lk = PLB_EE(k, j);
+                    blk = (lo == 0) ? hi : (lo == 1 ? 2 + hi : 5);
                 } else {
-                    Qb = Q + 10 * (6 + k);
-                    Lk = PLB_EE(2, k);
+                    blk = 6 + k;
                 }
-                v += Qb[q0] * Lk[l0];
-                if (np > 1) v += Qb[q1] * Lk[l1];
-                if (np > 2) v += Qb[q2] * Lk[l2];
+                const double *Qb = Q + 10 * blk;
+                Q0[k] = Qb[q0];
+                Q1[k] = Qb[q1];
+                Q2[k] = Qb[q2];
             }
-            C[row * 20 + ci] = v;
+            if (i < 3) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        v += Q0[k] * L0[k][j];
+                        if (np > 1) v += Q1[k] * L1[k][j];
+                        if (np > 2) v += Q2[k] * L2[k][j];
+                    }
+                    C[(3 * i + j) * 20 + ci] = v;
+                }
+            } else {
+                double v = 0.0;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) { // quad[6 + t] * PLB_EE(2, t)
+                    v += Q0[t] * L0[2][t];
+                    if (np > 1) v += Q1[t] * L1[2][t];
+                    if (np > 2) v += Q2[t] * L2[2][t];
+                }
+                C[9 * 20 + ci] = v;
+            }
         }
     }
     __syncwarp();
