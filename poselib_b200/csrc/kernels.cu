@@ -1025,7 +1025,7 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
             // constants fetched (broadcast) from shared memory.  The rare under-threshold cases (cheirality test,
             // division, accumulation) are handled afterwards in a compacted loop in which every lane pops one of ITS
             // recorded cases per iteration — handled inline they cost a divergent ~60-instruction detour for the
-            // whole warp whenever one lane of 32 hits (35 % of all issued instructions, profiles/r01_v6_summary.md).
+            // whole warp whenever one lane of 32 hits (35 % of all issued instructions, profiles/r01_v7_summary.md).
             constexpr int SCR_PB = 4;
             auto numden = [&](const float *M, float a0, float a1, float b0, float b1, float &num, float &den) {
                 const float m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5], m6 = M[6], m7 = M[7], m8 = M[8];

@@ -605,7 +605,7 @@ PLB_DEV int sturm_bisect10(const double *coeffs, double *roots, SturmWork *w) {
 
 // ---- warp-cooperative variant used by k5_roots: lane = sample, 32 samples per warp ------------------------------------
 // sturm_bisect10 run by 32 lanes on 32 different polynomials diverges badly (3.8 active lanes per instruction,
-// profiles/r01_v5_summary.md): every lane is at a different point of the interval walk or inside a Ridders/Newton
+// profiles/r01_v7_summary.md): every lane is at a different point of the interval walk or inside a Ridders/Newton
 // refinement.  The same computation is regrouped into phases that keep the warp converged:
 //   A  Sturm sequence of every lane's polynomial (uniform);
 //   B  interval walk: cheap transitions (pop / split bookkeeping / emit) advance until the lane needs ONE
