@@ -156,6 +156,9 @@ def main():
         return
 
     import torch
+    # ranks of one node share the host cores: tell the engine its share (helper threads for the sample tables)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    os.environ.setdefault("PLB_HOST_THREADS", str(max(1, usable_cores() // max(1, local_world))))
     from poselib_b200 import cabi
     if not torch.cuda.is_available() or cabi.device_count() == 0:
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")

@@ -13,6 +13,8 @@
 #include "../../include/poselib_b200.h"
 #include "kernels.cuh"
 
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -254,6 +256,29 @@ static Engine *engine() {
     if (!g_engine) g_engine = new Engine(); // lives as long as the process (buffers are reused across calls)
     return g_engine;
 }
+// host cores this process may use: affinity mask, capped by the cgroup CPU quota (containers / shared hosts)
+static int usable_cpus() {
+    static const int cached = [] {
+        int n = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+        if (FILE *f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+            char q[64];
+            long long period = 0;
+            if (std::fscanf(f, "%63s %lld", q, &period) == 2 && std::strcmp(q, "max") != 0 && period > 0) {
+                const long long quota = std::atoll(q);
+                if (quota > 0) n = std::min<long long>(n, std::max<long long>(1, (quota + period - 1) / period));
+            }
+            std::fclose(f);
+        }
+        if (const char *e = std::getenv("PLB_HOST_THREADS")) n = std::max(1, std::atoi(e));
+        return std::max(1, n);
+    }();
+    return cached;
+}
+// number of threads a run_group call may use for its sample tables (1 inside batch workers that share the cores)
+static thread_local int t_sampler_threads = 0;
+
 // engines of the batch worker threads, reused across plb_ransac_batch calls
 static std::mutex g_pool_mtx;
 static std::vector<Engine *> g_pool;
@@ -373,6 +398,7 @@ static void update_dynamic(PState &S, int K) { // ransac_impl.h:150-153
 // model improved) one gather + one LM launch per round for the WHOLE group.
 static int run_group(int kind, std::vector<Task *> &tasks) {
     Engine &E = *engine();
+    if (t_sampler_threads == 0) t_sampler_threads = usable_cpus();
     const int K = kind_sample_size(kind), MAXM = kind_max_models(kind), MSZ = kind_model_size(kind);
     // in_arr: doubles per correspondence in the caller layout; n_arr: SoA arrays resident per correspondence
     const int b_dim = (kind == KIND_PNP) ? 3 : 2, in_arr = 2 + b_dim, n_arr = (kind == KIND_RELPOSE_TS) ? TS_ARRAYS : in_arr;
@@ -700,7 +726,9 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                     for (size_t s = 0; s < S.B; ++s) S.sampler->next(dst + s * K);
                 }
             };
-            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            // helper threads for the sample tables: only what this group's share of the usable host cores allows
+            // (batch workers already run one thread per group; several ranks may share the host)
+            const unsigned hw = (unsigned)std::max(1, t_sampler_threads);
             const int nt = (total >= 32768 && na > 1) ? (int)std::min<unsigned>({hw, 16u, (unsigned)na}) : 1;
             if (nt <= 1) {
                 gen(0, na);
@@ -1709,6 +1737,7 @@ int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
     std::string err_msg;
     std::mutex mtx;
     auto work = [&](int tid) {
+        t_sampler_threads = std::max(1, usable_cpus() / nthreads);
         g_device = dev;
         g_engine = pool_engine((size_t)dev * 1024 + tid);
         // static group -> engine mapping: an engine sees the same group shapes on every call of a repeated workload,
