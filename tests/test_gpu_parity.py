@@ -385,6 +385,35 @@ def test_mixed_batch_config5_style_fast_mode(cabi):
         _same_trajectory(g, o, relpose=(pr["kind"] == "relpose"))
 
 
+@pytest.mark.parametrize("kind", ["relpose", "fundamental", "homography"])
+@pytest.mark.parametrize("big", [False, True])
+def test_heterogeneous_group_sizes_both_modes(cabi, kind, big):
+    """One lock-step group of problems with very different numbers of correspondences (5 .. 12 000, and up to 20 000
+    with `big`, which moves the screening kernel off its shared-memory path): the cost-balanced one-wave partition of
+    the screening kernel crosses problem boundaries inside a CTA, the packed solver kernels mix samples of different
+    problems in one warp.  Every problem must still follow the oracle's trajectory, in both precision modes."""
+    sizes = [5, 9, 40, 333, 1000, 2500, 7001, 12000] + ([20000] if big else [])
+    probs, refs = [], []
+    for i, n in enumerate(sizes):
+        if kind == "homography":
+            p = G.homography_problem(n, 0.5, 41, i)
+        else:
+            p = G.relpose_problem(n, 0.4, 41, i)
+        a, b = p["x1"] / G.FOCAL, p["x2"] / G.FOCAL
+        kw = dict(max_iterations=3000, min_iterations=200, seed=10 + i)
+        probs.append(dict(kind=kind, a=a, b=b, ransac=cabi.RansacOpt(**kw), max_error=1.5 / G.FOCAL))
+        refs.append(P.ransac(kind, a, b, P.RansacOpt(**kw), 1.5 / G.FOCAL))
+    for mode in ("exact", "fast"):
+        cabi.set_mode(mode)
+        try:
+            res = cabi.ransac_batch(probs, streams=1)
+        finally:
+            cabi.set_mode("exact")
+        for g, o in zip(res, refs):
+            assert g["status"] == 0
+            _same_trajectory(g, o, relpose=(kind == "relpose"), model_tol=1e-6 if kind != "fundamental" else 1e-3)
+
+
 # ---------------------------------------------------------------------------------------------- cameras (rows N3 / N1)
 DISTORTION_CAMERAS = [  # tests/example_cameras.h:31-38 of the reference, principal point moved to the image centre
     ("SIMPLE_RADIAL", [1100.0, 30.0, -20.0, -0.0397695]),
