@@ -229,8 +229,6 @@ PLB_DEV void cta_score(const ProblemDev &P, const double *model, double sq_thr, 
                 if (inl) {
                     ++cnt;
                     score += r2;
-                } else {
-                    score += sq_thr;
                 }
             }
         } else {
@@ -249,8 +247,6 @@ PLB_DEV void cta_score(const ProblemDev &P, const double *model, double sq_thr, 
                 if (inl) {
                     ++cnt;
                     score += r2;
-                } else {
-                    score += sq_thr;
                 }
             }
         }
@@ -269,7 +265,11 @@ PLB_DEV void cta_score(const ProblemDev &P, const double *model, double sq_thr, 
         ct += red->c[w];
         st += red->s[w];
     }
-    if (KIND == KIND_PNP) st += (double)(n - (int)ct) * sq_thr; // robust/utils.cc:62
+    // Outliers contribute (n - count) * thr in ONE product for every kind (the reference does so for reprojection
+    // scores, robust/utils.cc:62, and adds thr per outlier for the others).  Position-independent on purpose: models
+    // supported only by their own minimal sample all score (n - K) thr to the last bit, as in the CPU's sequential
+    // sum where the K negligible residuals are absorbed — so such ties are not "better scores" (ransac_impl.h:116).
+    st += (double)(n - (int)ct) * sq_thr;
     __syncthreads();
     count_out = ct;
     score_out = st;
@@ -711,8 +711,6 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
                         if (inl) {
                             ++cnt[i];
                             sc[i] += r2;
-                        } else {
-                            sc[i] += sq_thr;
                         }
                     }
                 }
@@ -748,8 +746,6 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
                         if ((under >> i) & 1u) {
                             ++cnt[i];
                             sc[i] += r2v[i];
-                        } else {
-                            sc[i] += sq_thr;
                         }
                     }
                 }
@@ -773,7 +769,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
                 ct += red_c[w][tid];
                 st += red_s[w][tid];
             }
-            if (KIND == KIND_PNP) st += (double)(n - (int)ct) * sq_thr; // robust/utils.cc:62
+            st += (double)(n - (int)ct) * sq_thr; // see cta_score
             out.counts[seg + m0 + tid] = ct;
             out.scores[seg + m0 + tid] = st;
         }
