@@ -114,6 +114,14 @@ int plb_set_device(int device);      /* device used by subsequent calls from thi
  * every hypothesis + fp64 confirmation of every candidate that could change the RANSAC state; same results) */
 int plb_set_mode(int mode);
 
+/* ---- host-side pieces of the loop; no device needed (exercised by the CPU test-suite) ---------------------
+ * plb_host_sample_table: the first `iters` minimal samples (k indices each) RandomSampler(n, k, opt) draws
+ * (robust/sampling.cc:37-61,85-136, incl. PROSAC and the int sign-extension of random_int before `% n`).
+ * plb_host_dynamic_max_iter: compute_dynamic_max_iter (robust/ransac_impl.h:51-76). */
+int plb_host_sample_table(uint64_t n, uint32_t k, const plb_ransac_opt *opt, uint64_t iters, uint32_t *out);
+uint64_t plb_host_dynamic_max_iter(uint64_t num_inliers, uint64_t num_data, uint32_t sample_sz, double success_prob,
+                                   double dyn_num_trials_mult, uint64_t min_iterations, uint64_t max_iterations);
+
 /* ---- robust/ransac.h:39-40,60-61,85-87,99-101 (points already calibrated / normalised) ---------- */
 int plb_ransac_pnp(const double *x_xy, const double *X_xyz, size_t n, const plb_ransac_opt *opt, double max_error,
                    double pose_inout[7], char *inliers, plb_ransac_stats *stats, plb_counters *counters);

@@ -91,7 +91,7 @@ class Problem(C.Structure):
 
 EXPORTS = [
     "plb_ransac_opt_default", "plb_bundle_opt_default", "plb_last_error", "plb_device_count", "plb_set_device",
-    "plb_set_mode", "plb_ransac_pnp", "plb_ransac_relpose", "plb_ransac_relpose_cameras", "plb_ransac_fundamental",
+    "plb_set_mode", "plb_host_sample_table", "plb_host_dynamic_max_iter", "plb_ransac_pnp", "plb_ransac_relpose", "plb_ransac_relpose_cameras", "plb_ransac_fundamental",
     "plb_ransac_homography",
     "plb_estimate_absolute_pose", "plb_estimate_relative_pose", "plb_estimate_fundamental",
     "plb_estimate_homography", "plb_p3p_batch", "plb_relpose_5pt_batch", "plb_relpose_5pt_poses_batch",
@@ -128,6 +128,21 @@ def set_device(i):
 
 def set_mode(mode):
     _check(_lib.plb_set_mode({"exact": 0, "fast": 1}.get(mode, mode)))
+
+
+def host_sample_table(n, k, ropt, iters):
+    """First `iters` minimal samples of RandomSampler(n, k, opt) as the engine's host sampler draws them (no device)."""
+    out = np.zeros((iters, k), dtype=np.uint32)
+    _check(_lib.plb_host_sample_table(C.c_uint64(n), C.c_uint32(k), C.byref(ropt), C.c_uint64(iters),
+                                      out.ctypes.data_as(C.POINTER(C.c_uint32))))
+    return out
+
+
+def host_dynamic_max_iter(num_inliers, num_data, sample_sz, success_prob, mult, min_it, max_it):
+    _lib.plb_host_dynamic_max_iter.restype = C.c_uint64
+    return _lib.plb_host_dynamic_max_iter(C.c_uint64(num_inliers), C.c_uint64(num_data), C.c_uint32(sample_sz),
+                                          C.c_double(success_prob), C.c_double(mult), C.c_uint64(min_it),
+                                          C.c_uint64(max_it))
 
 
 def _d(a):

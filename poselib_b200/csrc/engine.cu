@@ -1386,6 +1386,24 @@ int plb_set_device(int device) {
     g_device = device;
     return PLB_OK;
 }
+// ---- host-side pieces of the loop, callable without a device (used by the CPU test-suite) --------------------------
+// robust/sampling.cc:37-61,85-136: the first `iters` samples (k indices each) of RandomSampler(n, k, opt)
+int plb_host_sample_table(uint64_t n, uint32_t k, const plb_ransac_opt *opt, uint64_t iters, uint32_t *out) {
+    if (!opt || !out || k == 0 || k > 16 || n < k) {
+        g_err = "bad argument";
+        return PLB_ERR_ARG;
+    }
+    Sampler smp((size_t)n, (size_t)k, *opt);
+    for (uint64_t i = 0; i < iters; ++i) smp.next(out + i * k);
+    return PLB_OK;
+}
+// robust/ransac_impl.h:51-76 (compute_dynamic_max_iter with log_prob_missing_model = log(1 - success_prob))
+uint64_t plb_host_dynamic_max_iter(uint64_t num_inliers, uint64_t num_data, uint32_t sample_sz, double success_prob,
+                                   double dyn_num_trials_mult, uint64_t min_iterations, uint64_t max_iterations) {
+    return (uint64_t)compute_dynamic_max_iter((size_t)num_inliers, (size_t)num_data, (size_t)sample_sz,
+                                              std::log(1.0 - success_prob), dyn_num_trials_mult, (size_t)min_iterations,
+                                              (size_t)max_iterations);
+}
 int plb_set_mode(int mode) {
     if (mode != 0 && mode != 1) {
         g_err = "mode must be 0 (exact) or 1 (fast)";

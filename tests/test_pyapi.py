@@ -21,8 +21,8 @@ def test_option_dicts_follow_the_pybind_helpers():
         pyapi._camera({"model": "OPENCV_FISHEYE", "params": [1, 1, 0, 0, 0, 0, 0, 0]})
     c = pyapi._camera({"model": "SIMPLE_PINHOLE", "width": 640, "height": 480, "params": [500.0, 320.0, 240.0]})
     assert (c.model_id, c.width, c.height, list(c.params)[:3]) == (0, 640, 480, [500.0, 320.0, 240.0])
-    with pytest.raises(cabi.PoseLibB200Error):
-        pyapi.estimate_relative_pose(np.zeros((8, 2)), np.zeros((8, 2)), None, None, {"tangent_sampson": True})
+    c = pyapi._camera({"model": "OPENCV", "params": [900.0, 901.0, 3.0, 4.0, 0.1, -0.2, 1e-3, 2e-3]})
+    assert c.model_id == 4 and list(c.params) == [900.0, 901.0, 3.0, 4.0, 0.1, -0.2, 1e-3, 2e-3]
 
 
 @pytest.mark.gpu
@@ -54,6 +54,20 @@ def test_pyapi_matches_oracle_through_the_poselib_call_surface():
     F, info = poselib.estimate_fundamental(p["x1"], p["x2"], {"ransac": {"max_iterations": 5000, "seed": 1}})
     o = P.estimate("fundamental", p["x1"], p["x2"], P.RansacOpt(max_iterations=5000, seed=1), P.BundleOpt(), 1.0)
     assert info["num_inliers"] == o["stats"]["num_inliers"]
+    # distorted cameras + RelativePoseOptions.tangent_sampson through the dict interface (relative_pose.cc:15-52)
+    camd = {"model": "RADIAL", "width": 2000, "height": 2000, "params": [1050.0, -15.0, 25.0, -0.04012, 0.00123]}
+    camo = ("RADIAL", camd["params"])
+    X1 = np.c_[p["x1"] / G.FOCAL, np.ones(len(p["x1"]))]
+    X2 = np.c_[p["x2"] / G.FOCAL, np.ones(len(p["x2"]))]
+    d1, d2 = P.camera_project_with_jac(camo, X1)[2], P.camera_project_with_jac(camo, X2)[2]
+    for ts in (False, True):
+        optd = {"max_error": 1.5, "tangent_sampson": ts, "ransac": {"max_iterations": 20000, "min_iterations": 500, "seed": 3}}
+        pose, info = poselib.estimate_relative_pose(d1, d2, camd, camd, optd)
+        o = P.estimate("relpose", d1, d2, P.RansacOpt(max_iterations=20000, min_iterations=500, seed=3), P.BundleOpt(),
+                       1.5, camo, camo, tangent_sampson=ts)
+        assert info["iterations"] == o["stats"]["iterations"] and info["num_inliers"] == o["stats"]["num_inliers"]
+        assert info["inliers"] == [bool(v) for v in o["inliers"]]
+        assert np.allclose(pose.q, o["model"][:4], atol=1e-7)
     # solvers
     x, X, R, t = G.minimal_abspose(1)
     assert len(poselib.p3p(x, X)) == len(P.p3p(x, X))
