@@ -84,6 +84,16 @@ def usable_cores():
     return n
 
 
+def cpu_model():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def make_batch(pairs, first_idx):
     probs = []
     for i in range(pairs):
@@ -128,7 +138,7 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{pairs} x relpose_5pt C2 (10000 corrs, 30% inliers, max 100000 its), one problem per host thread",
                    "pairs_per_step": pairs},
-        "cpu_baseline": {"value": val, "unit": "hypotheses/s", "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "hypotheses/s", "cores": threads, "host_cpus": os.cpu_count(), "cpu_model": cpu_model(), "kind": "port",
                          "sample": f"{pairs} C2 problems per step x {args.steps} steps; restated PoseLib path (no Eigen), "
                                    "g++ -O3 -ffp-contract=off"},
         "e2e": {"value": val, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -298,7 +308,7 @@ def main():
                                     "scored_corrs_per_s": sum(c["scored_corrs"] for c in cnts) / sec, "cores": 1,
                                     "kind": "port", "sample": f"first {k} problems of the step, 1 thread, restated "
                                     "PoseLib path (no Eigen), g++ -O3 -ffp-contract=off", "seconds": sec,
-                                    "host_cpus": os.cpu_count(), "usable_cores": usable_cores()}
+                                    "host_cpus": os.cpu_count(), "usable_cores": usable_cores(), "cpu_model": cpu_model()}
         except Exception as e:  # the baseline is a reported number, never part of the product path
             line["cpu_baseline"] = {"value": None, "unit": "hypotheses/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line))

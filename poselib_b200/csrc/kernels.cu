@@ -1171,20 +1171,29 @@ __global__ void __launch_bounds__(SCORE_THREADS, 4)
 
 template <int KIND> static size_t hyp_smem_bytes() { return 256 + sizeof(HypScratch<KIND>) * HYP_WARPS; }
 
-static int g_sm_count = 0;
+// Occupancy figures and opt-in attributes are per device: the caches below are indexed by the current device so that a
+// process driving several GPUs (plb_set_device from different threads) configures each of them.
+constexpr int MAX_DEVICES = 64;
+static int cur_dev() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
+}
 static int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
+    static int cached[MAX_DEVICES] = {0};
+    const int dev = cur_dev();
+    if (cached[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 148;
     }
-    return g_sm_count;
+    return cached[dev];
 }
 
 template <int KIND> static int solve_blocks_per_sm() {
-    static int cached = -1;
-    if (cached < 0) {
+    static int cached_dev[MAX_DEVICES] = {0};
+    int &cached = cached_dev[cur_dev()];
+    if (cached <= 0) {
         const size_t smem = hyp_smem_bytes<KIND>();
         cudaFuncSetAttribute(k_solve<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int nb = 0;
@@ -1194,8 +1203,9 @@ template <int KIND> static int solve_blocks_per_sm() {
     return cached;
 }
 template <int KIND> static int score_blocks_per_sm() {
-    static int cached = -1;
-    if (cached < 0) {
+    static int cached_dev[MAX_DEVICES] = {0};
+    int &cached = cached_dev[cur_dev()];
+    if (cached <= 0) {
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_score<KIND>, SCORE_THREADS, 0);
         cached = nb > 0 ? nb : 1;
@@ -1205,8 +1215,9 @@ template <int KIND> static int score_blocks_per_sm() {
 int device_sm_count() { return sm_count(); }
 
 static int prep_blocks_per_sm() {
-    static int cached = -1;
-    if (cached < 0) {
+    static int cached_dev[MAX_DEVICES] = {0};
+    int &cached = cached_dev[cur_dev()];
+    if (cached <= 0) {
         const size_t smem = PREP_SMEM;
         cudaFuncSetAttribute(k5_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int nb = 0;
@@ -1252,7 +1263,8 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
         constexpr int NARR = (KIND == KIND_PNP) ? 5 : 4;
         const size_t bytes = (size_t)NARR * (size_t)max_n_pad * 4;
         const int use_smem = bytes <= 200 * 1024 ? 1 : 0;
-        static bool attr_done = false;
+        static bool attr_done_dev[MAX_DEVICES] = {false};
+        bool &attr_done = attr_done_dev[cur_dev()];
         if (!attr_done) {
             cudaFuncSetAttribute(k_screen<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_done = true;
