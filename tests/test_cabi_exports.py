@@ -60,6 +60,27 @@ def test_argument_errors_do_not_need_a_gpu():
     assert e.value.code == cabi.PLB_ERR_NYI
 
 
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    from poselib_b200 import cabi
+    x = np.zeros((8, 2))
+    bad = cabi.Camera(7, (1, 1, 0, 0))  # FOV: not on the path
+    good = cabi.Camera("RADIAL", (1000.0, 0.0, 0.0, -0.04, 0.001))
+    for fn in (lambda: cabi.ransac_relpose_cameras(x, x, bad, good, cabi.RansacOpt(), 1.0),
+               lambda: cabi.ransac_relpose_cameras(x, x, good, bad, cabi.RansacOpt(), 1.0),
+               lambda: cabi.refine_relpose_cameras(np.r_[1.0, np.zeros(6)], x, x, bad, good, cabi.BundleOpt()),
+               lambda: cabi.estimate("relpose", x, x, cabi.RansacOpt(), cabi.BundleOpt(), 1.0, good, bad, tangent_sampson=True),
+               lambda: cabi.estimate("pnp", x, np.zeros((8, 3)), cabi.RansacOpt(), cabi.BundleOpt(), 1.0, bad)):
+        with pytest.raises(cabi.PoseLibB200Error) as e:
+            fn()
+        assert e.value.code == cabi.PLB_ERR_NYI
+    st, cn = cabi.RansacStats(), cabi.Counters()
+    rc = cabi.lib().plb_ransac_relpose_cameras(None, None, C.c_size_t(10), C.byref(good), C.byref(good), None,
+                                               C.c_double(1.0), None, None, C.byref(st), C.byref(cn))
+    assert rc == cabi.PLB_ERR_ARG
+    assert cabi.lib().plb_host_sample_table(C.c_uint64(3), C.c_uint32(5), C.byref(cabi.RansacOpt()), C.c_uint64(1),
+                                            None) == cabi.PLB_ERR_ARG
+
+
 def test_no_silent_cpu_fallback():
     from poselib_b200 import cabi
     if cabi.device_count() > 0:
