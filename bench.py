@@ -320,7 +320,10 @@ def main():
                          "measured": f"{roof_steps} extra steps of the same workload with one lock-step group in flight "
                                      "(kernel durations by CUDA events on the engine's stream, no co-running kernels)",
                          "note": "correspondences are SMEM/L2-resident and reused across thousands of models: DRAM "
-                                 "traffic << algorithmic bytes by design (SURVEY H7); frac is the SURVEY §8d figure"},
+                                 "traffic << algorithmic bytes by design (SURVEY H7); frac is the SURVEY §8d figure and "
+                                 "can exceed 1 for the fp32 screening kernel: its operand stream is served from shared "
+                                 "memory after one TMA stage per CTA, the binding resource is fp32 issue (60 % of the "
+                                 "slots, profiles/r01_v7_summary.md)"},
             "clocks": sampler.summary(),
         }
         # CPU baseline on this box's host cores: 1 thread (the reference's execution model), bounded sample
