@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// PARITY PARTLY PINNED: sampler, loop control flow, iteration arithmetic, univariate solvers and Sturm root isolation against the reference's own code (oracle/_ref, oracle/ref/ref_capi.cc); the Eigen-dependent arithmetic is UNPINNED.
 // extern "C" surface of the CPU oracle for ctypes (tests/, __graft_entry__.smoke(), bench.py cpu legs).
 // 3x3 matrices cross this boundary as 9 doubles COLUMN-MAJOR (Eigen::Matrix3d layout); poses as q(wxyz)+t.
 #include "plo.h"
@@ -165,6 +166,11 @@ int plo_homography_4pt(const double *x1, const double *x2, double *H_out, int ch
     return n;
 }
 int plo_bisect_sturm10(const double *c11, double *roots) { return bisect_sturm10(c11, roots); }
+int plo_solve_quadratic_real(double a, double b, double c, double *roots) { return solve_quadratic_real(a, b, c, roots); }
+int plo_solve_cubic_single_real(double c2, double c1, double c0, double *root) {
+    return solve_cubic_single_real(c2, c1, c0, *root) ? 1 : 0;
+}
+int plo_solve_cubic_real(double c2, double c1, double c0, double *roots) { return solve_cubic_real(c2, c1, c0, roots); }
 int plo_calculate_RFC(const double *F9) { return calculate_RFC(mat_in(F9)) ? 1 : 0; }
 // ---- scorers / masks --------------------------------------------------------------------------
 double plo_score_pnp(const double *pose, const double *x, const double *X, uint64_t n, double sq_thr, uint64_t *cnt) {

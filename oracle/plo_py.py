@@ -1,8 +1,10 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes binding of oracle/_build/libplo.so.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu legs may import this module.  The product
-package (poselib_b200/) never does.  PARITY UNPINNED: the oracle is a restatement of
-PoseLib's CPU path without Eigen, not a build of PoseLib.
+package (poselib_b200/) never does.  PARITY PARTLY PINNED: the oracle is a restatement of PoseLib's CPU
+path without Eigen, not a build of PoseLib; the Eigen-free parts of the reference (sampler, loop templates, univariate
+solvers, Sturm) are built into oracle/_ref and pin the corresponding oracle functions bit for bit (tests/test_ref_pins.py),
+the Eigen-dependent arithmetic is unpinned.
 """
 import ctypes as C
 import os
@@ -419,3 +421,99 @@ def ransac_relpose_batch_mt(x1_list, x2_list, ropts, max_errors, threads):
         me.ctypes.data_as(C.POINTER(C.c_double)), int(threads), poses.ctypes.data_as(C.POINTER(C.c_double)),
         stats, cnts)
     return sec, poses, [s.as_dict() for s in stats], [c.as_dict() for c in cnts]
+
+
+# ---- oracle/_ref: the reference's own sampler and loop templates (built by `make -C oracle ref`) --------------------
+_REF_PATH = os.path.join(_HERE, "_ref", "libplref.so")
+_ref = None
+
+
+def ref_available(build_if_possible=True):
+    """True when oracle/_ref/libplref.so exists (it is built here, where /root/reference is mounted, and travels with
+    the tree; on a box without the reference sources it can only be used if already built)."""
+    if not os.path.exists(_REF_PATH) and build_if_possible and os.path.isdir("/root/reference/PoseLib"):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    return os.path.exists(_REF_PATH)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not ref_available():
+            raise RuntimeError("oracle/_ref/libplref.so is not built (needs /root/reference)")
+        _ref = C.CDLL(_REF_PATH)
+        _ref.plref_all_inlier_sample_probability.restype = C.c_double
+        _ref.plref_compute_dynamic_max_iter.restype = C.c_uint64
+    return _ref
+
+
+def ref_random_ints(seed, n):
+    out = np.zeros(n, dtype=np.int32)
+    ref_lib().plref_random_ints(C.c_uint64(seed), C.c_uint64(n), out.ctypes.data_as(C.POINTER(C.c_int32)))
+    return out
+
+
+def ref_sample_table(N, K, opt, iters):
+    out = np.zeros((iters, K), dtype=np.uint32)
+    ref_lib().plref_sample_table(C.c_uint64(N), C.c_uint64(K), C.byref(opt), C.c_uint64(iters),
+                                 out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return out
+
+
+def ref_all_inlier_sample_probability(ni, nd, k):
+    return ref_lib().plref_all_inlier_sample_probability(C.c_uint64(ni), C.c_uint64(nd), C.c_uint64(k))
+
+
+def ref_compute_dynamic_max_iter(ni, nd, k, logp, mult, mn, mx):
+    return ref_lib().plref_compute_dynamic_max_iter(C.c_uint64(ni), C.c_uint64(nd), C.c_uint64(k), C.c_double(logp),
+                                                    C.c_double(mult), C.c_uint64(mn), C.c_uint64(mx))
+
+
+def _univariate(libobj, prefix, name, coeffs, nroots):
+    out = np.zeros(nroots)
+    n = getattr(libobj, prefix + name)(*[C.c_double(v) for v in coeffs], out.ctypes.data_as(C.POINTER(C.c_double)))
+    return n, out
+
+
+def solve_quadratic_real(a, b, c, ref=False):
+    return _univariate(ref_lib() if ref else lib(), "plref_" if ref else "plo_", "solve_quadratic_real", (a, b, c), 2)
+
+
+def solve_cubic_single_real(c2, c1, c0, ref=False):
+    return _univariate(ref_lib() if ref else lib(), "plref_" if ref else "plo_", "solve_cubic_single_real", (c2, c1, c0), 1)
+
+
+def solve_cubic_real(c2, c1, c0, ref=False):
+    return _univariate(ref_lib() if ref else lib(), "plref_" if ref else "plo_", "solve_cubic_real", (c2, c1, c0), 3)
+
+
+def ref_bisect_sturm10(c):
+    ca, cp = _d(c)
+    roots = np.zeros(10)
+    n = ref_lib().plref_bisect_sturm10(cp, roots.ctypes.data_as(C.POINTER(C.c_double)))
+    return roots[:n].copy()
+
+
+def ref_ransac_mock(nd, k, inl, opt):
+    st = RansacStats()
+    ref_lib().plref_ransac_mock(C.c_uint64(nd), C.c_uint64(k), C.c_uint64(inl), C.byref(opt), C.byref(st))
+    return st
+
+
+def ref_ransac(kind, a, b, ropt, max_error, init=None, rfc=False):
+    """The REFERENCE's ransac<> / score_models<> (robust/ransac_impl.h) driving the oracle's estimators."""
+    n = len(a)
+    aa, ap = _d(a)
+    ba, bp = _d(b)
+    mask, mkp = _mask(n)
+    st = RansacStats()
+    if kind in ("pnp", "relpose"):
+        m = np.array([1, 0, 0, 0, 0, 0, 0] if init is None else init, dtype=np.float64)
+    else:
+        m0 = np.eye(3) if init is None else np.asarray(init, dtype=np.float64)
+        m = np.ascontiguousarray(m0.T.reshape(-1)).copy()
+    ref_lib().plref_ransac({"pnp": 0, "relpose": 1, "fundamental": 2, "homography": 3}[kind], ap, bp, C.c_uint64(n),
+                           C.byref(ropt), C.c_double(max_error), int(rfc), m.ctypes.data_as(C.POINTER(C.c_double)), mkp,
+                           C.byref(st))
+    model = m if kind in ("pnp", "relpose") else m.reshape(3, 3).T.copy()
+    return {"model": model, "inliers": mask, "stats": st.as_dict()}

@@ -1,7 +1,7 @@
 """Regenerates tests/golden/oracle_regression.json.
 
-These are REGRESSION fixtures of this repository's CPU oracle (oracle/), not outputs of the reference: PoseLib cannot
-be built in this image (no Eigen), so there is nothing reference-generated to commit ("parity unpinned").
+These are REGRESSION fixtures of this repository's CPU oracle (oracle/), not outputs of the reference: PoseLib as a whole
+cannot be built in this image (no Eigen); only its Eigen-free parts are (oracle/_ref).
 They pin the oracle's behaviour between rounds: any change of its arithmetic or control flow shows up on the CPU, and
 the GPU parity tests compare the CUDA path with the very same expectations.
 
