@@ -517,3 +517,18 @@ def ref_ransac(kind, a, b, ropt, max_error, init=None, rfc=False):
                            C.byref(st))
     model = m if kind in ("pnp", "relpose") else m.reshape(3, 3).T.copy()
     return {"model": model, "inliers": mask, "stats": st.as_dict()}
+
+
+def p3p_root2real(b, c, ref=False):
+    r = np.zeros(2)
+    L = ref_lib() if ref else lib()
+    ok = getattr(L, ("plref_" if ref else "plo_") + "p3p_root2real")(C.c_double(b), C.c_double(c), r.ctypes.data_as(C.POINTER(C.c_double)))
+    return ok, r
+
+
+def p3p_refine_lambda(l, a12, a13, a23, b12, b13, b23, ref=False):
+    out = np.ascontiguousarray(l, dtype=np.float64).copy()
+    L = ref_lib() if ref else lib()
+    getattr(L, ("plref_" if ref else "plo_") + "p3p_refine_lambda")(out.ctypes.data_as(C.POINTER(C.c_double)),
+                                                                    *[C.c_double(v) for v in (a12, a13, a23, b12, b13, b23)])
+    return out

@@ -771,3 +771,12 @@ int homography_4pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, Mat
 }
 
 } // namespace plo
+
+// test hooks for the two scalar helpers of p3p (anonymous namespace above), compared with the reference's
+// p3p_common.h through oracle/_ref (tests/test_ref_pins.py)
+extern "C" {
+int plo_p3p_root2real(double b, double c, double *r) { return plo::root2real(b, c, r[0], r[1]) ? 1 : 0; }
+void plo_p3p_refine_lambda(double *l, double a12, double a13, double a23, double b12, double b13, double b23) {
+    plo::refine_lambda(l[0], l[1], l[2], a12, a13, a23, b12, b13, b23);
+}
+}

@@ -6,6 +6,7 @@
 //                                             ransac<> (header-only templates, instantiated here)
 //   * PoseLib/misc/univariate.cc            — solve_quadratic_real, solve_cubic_single_real, solve_cubic_real
 //   * PoseLib/misc/sturm.h                  — bisect_sturm<10> (Sturm sequence, root isolation, Ridders + Newton)
+//   * PoseLib/solvers/p3p_common.h          — root2real, refine_lambda (the scalar helpers of p3p)
 // The templates are instantiated (a) with the MockEstimator of the reference's tests/ransac_test.cc:12-28 and (b) with
 // this repository's oracle estimators (solver / scorer / refiner restatements of oracle/plo_robust.cc), so that the
 // REFERENCE's loop drives them: comparing the outcome with the oracle's own loop pins the control flow of
@@ -15,6 +16,7 @@
 #include "PoseLib/misc/univariate.h"
 #include "PoseLib/robust/ransac_impl.h"
 #include "PoseLib/robust/sampling.h"
+#include "PoseLib/solvers/p3p_common.h"
 
 #include "../plo_robust.cc" // unity include: the oracle estimators live in an anonymous namespace
 
@@ -131,6 +133,10 @@ int plref_solve_cubic_single_real(double c2, double c1, double c0, double *root)
 }
 int plref_solve_cubic_real(double c2, double c1, double c0, double *roots) {
     return poselib::univariate::solve_cubic_real(c2, c1, c0, roots);
+}
+int plref_p3p_root2real(double b, double c, double *r) { return poselib::root2real(b, c, r[0], r[1]) ? 1 : 0; }
+void plref_p3p_refine_lambda(double *l, double a12, double a13, double a23, double b12, double b13, double b23) {
+    poselib::refine_lambda(l[0], l[1], l[2], a12, a13, a23, b12, b13, b23);
 }
 int plref_bisect_sturm10(const double *coeffs11, double *roots10) {
     return poselib::sturm::bisect_sturm<10>(coeffs11, roots10);

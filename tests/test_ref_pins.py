@@ -140,3 +140,27 @@ def test_reference_sturm_root_isolation_pins_the_oracle_bitwise():
         assert np.array_equal(r, o, equal_nan=True), (c, r, o)
         exact += 1
     assert exact == len(polys)
+
+
+def test_reference_p3p_scalar_helpers_pin_the_oracle_bitwise():
+    """solvers/p3p_common.h root2real / refine_lambda (the scalar part of Ding's P3P) compiled from the reference."""
+    rng = np.random.default_rng(4)
+    for i in range(3000):
+        b, c = rng.normal(0, 3, 2)
+        if i % 5 == 0:
+            c = b * b / 4 + rng.choice([0.0, 1e-13, -1e-13, 5e-13])   # around the THRESHOLD branches
+        okr, rr = P.p3p_root2real(b, c, ref=True)
+        oko, ro = P.p3p_root2real(b, c)
+        assert okr == oko and np.array_equal(rr, ro, equal_nan=True), (b, c)
+    for _ in range(2000):
+        # a consistent instance: three unit bearings, true depths perturbed as the solver's initial estimate would be
+        x = rng.normal(size=(3, 3))
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        lam = rng.uniform(0.5, 5.0, 3)
+        X = x * lam[:, None]
+        a12, a13, a23 = (np.sum((X[0] - X[1]) ** 2), np.sum((X[0] - X[2]) ** 2), np.sum((X[1] - X[2]) ** 2))
+        b12, b13, b23 = x[0] @ x[1], x[0] @ x[2], x[1] @ x[2]
+        l0 = lam * (1 + rng.normal(0, 1e-3, 3))
+        rr = P.p3p_refine_lambda(l0, a12, a13, a23, b12, b13, b23, ref=True)
+        ro = P.p3p_refine_lambda(l0, a12, a13, a23, b12, b13, b23)
+        assert np.array_equal(rr, ro, equal_nan=True)
