@@ -441,7 +441,11 @@ def ref_lib():
     if _ref is None:
         if not ref_available():
             raise RuntimeError("oracle/_ref/libplref.so is not built (needs /root/reference)")
-        _ref = C.CDLL(_REF_PATH)
+        # lazy binding: the reference's utils.cc is compiled whole, its Eigen-dependent functions reference symbols the
+        # Eigen stand-in only declares; they are never called
+        _ref = C.CDLL(_REF_PATH, mode=os.RTLD_LAZY)
+        _ref.plref_score_fundamental.restype = C.c_double
+        _ref.plref_score_homography.restype = C.c_double
         _ref.plref_all_inlier_sample_probability.restype = C.c_double
         _ref.plref_compute_dynamic_max_iter.restype = C.c_uint64
     return _ref
@@ -532,3 +536,28 @@ def p3p_refine_lambda(l, a12, a13, a23, b12, b13, b23, ref=False):
     getattr(L, ("plref_" if ref else "plo_") + "p3p_refine_lambda")(out.ctypes.data_as(C.POINTER(C.c_double)),
                                                                     *[C.c_double(v) for v in (a12, a13, a23, b12, b13, b23)])
     return out
+
+
+def ref_score(kind, M, x1, x2, sq_thr, want_inliers=False):
+    """compute_sampson_msac_score(F) / compute_homography_msac_score (+ get_inliers / get_homography_inliers) of the
+    reference's robust/utils.cc (oracle/_ref).  kind: "fundamental" | "homography"."""
+    n = len(x1)
+    m, mp = _cm(M)
+    a, ap = _d(x1)
+    b, bp = _d(x2)
+    cnt = C.c_uint64(0)
+    fn = ref_lib().plref_score_fundamental if kind == "fundamental" else ref_lib().plref_score_homography
+    s = fn(mp, ap, bp, C.c_uint64(n), C.c_double(sq_thr), C.byref(cnt))
+    if not want_inliers:
+        return s, cnt.value
+    mask, mkp = _mask(n)
+    if kind == "fundamental":
+        ref_lib().plref_inliers_fundamental(mp, ap, bp, C.c_uint64(n), C.c_double(sq_thr), mkp)
+    else:
+        ref_lib().plref_inliers_homography(mp, ap, bp, C.c_uint64(n), C.c_double(sq_thr), mkp)
+    return s, cnt.value, mask
+
+
+def ref_calculate_RFC(F):
+    m, mp = _cm(F)
+    return bool(ref_lib().plref_calculate_RFC(mp))

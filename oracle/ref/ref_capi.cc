@@ -7,6 +7,12 @@
 //   * PoseLib/misc/univariate.cc            — solve_quadratic_real, solve_cubic_single_real, solve_cubic_real
 //   * PoseLib/misc/sturm.h                  — bisect_sturm<10> (Sturm sequence, root isolation, Ridders + Newton)
 //   * PoseLib/solvers/p3p_common.h          — root2real, refine_lambda (the scalar helpers of p3p)
+//   * PoseLib/robust/utils.cc               — the five functions of that file that only read matrix / point ELEMENTS
+//                                             and do scalar arithmetic: compute_sampson_msac_score(F), get_inliers(F),
+//                                             compute_homography_msac_score, get_homography_inliers, calculate_RFC.
+//                                             (The rest of utils.cc compiles against the Eigen stand-in but references
+//                                             undefined Eigen symbols and is never called; the library is therefore
+//                                             loaded with lazy binding.)
 // The templates are instantiated (a) with the MockEstimator of the reference's tests/ransac_test.cc:12-28 and (b) with
 // this repository's oracle estimators (solver / scorer / refiner restatements of oracle/plo_robust.cc), so that the
 // REFERENCE's loop drives them: comparing the outcome with the oracle's own loop pins the control flow of
@@ -16,6 +22,7 @@
 #include "PoseLib/misc/univariate.h"
 #include "PoseLib/robust/ransac_impl.h"
 #include "PoseLib/robust/sampling.h"
+#include "PoseLib/robust/utils.h"
 #include "PoseLib/solvers/p3p_common.h"
 
 #include "../plo_robust.cc" // unity include: the oracle estimators live in an anonymous namespace
@@ -134,6 +141,48 @@ int plref_solve_cubic_single_real(double c2, double c1, double c0, double *root)
 int plref_solve_cubic_real(double c2, double c1, double c0, double *roots) {
     return poselib::univariate::solve_cubic_real(c2, c1, c0, roots);
 }
+// robust/utils.cc: element-access-only scorers / masks / RFC of the reference.  F, H column-major 9 doubles.
+static Eigen::Matrix3d mat_in(const double *m9) {
+    Eigen::Matrix3d M;
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) M(r, c) = m9[3 * c + r];
+    return M;
+}
+static std::vector<poselib::Point2D> pts_in(const double *p, uint64_t n) {
+    std::vector<poselib::Point2D> v(n);
+    for (uint64_t k = 0; k < n; ++k) {
+        v[k](0) = p[2 * k];
+        v[k](1) = p[2 * k + 1];
+    }
+    return v;
+}
+double plref_score_fundamental(const double *F9, const double *x1, const double *x2, uint64_t n, double sq_thr,
+                               uint64_t *count) {
+    size_t c = 0;
+    const double s = poselib::compute_sampson_msac_score(mat_in(F9), pts_in(x1, n), pts_in(x2, n), sq_thr, &c);
+    *count = c;
+    return s;
+}
+double plref_score_homography(const double *H9, const double *x1, const double *x2, uint64_t n, double sq_thr,
+                              uint64_t *count) {
+    size_t c = 0;
+    const double s = poselib::compute_homography_msac_score(mat_in(H9), pts_in(x1, n), pts_in(x2, n), sq_thr, &c);
+    *count = c;
+    return s;
+}
+int plref_inliers_fundamental(const double *F9, const double *x1, const double *x2, uint64_t n, double sq_thr, char *mask) {
+    std::vector<char> m;
+    const int c = poselib::get_inliers(mat_in(F9), pts_in(x1, n), pts_in(x2, n), sq_thr, &m);
+    std::memcpy(mask, m.data(), n);
+    return c;
+}
+void plref_inliers_homography(const double *H9, const double *x1, const double *x2, uint64_t n, double sq_thr, char *mask) {
+    std::vector<char> m;
+    poselib::get_homography_inliers(mat_in(H9), pts_in(x1, n), pts_in(x2, n), sq_thr, &m);
+    std::memcpy(mask, m.data(), n);
+}
+int plref_calculate_RFC(const double *F9) { return poselib::calculate_RFC(mat_in(F9)) ? 1 : 0; }
+
 int plref_p3p_root2real(double b, double c, double *r) { return poselib::root2real(b, c, r[0], r[1]) ? 1 : 0; }
 void plref_p3p_refine_lambda(double *l, double a12, double a13, double a23, double b12, double b13, double b23) {
     poselib::refine_lambda(l[0], l[1], l[2], a12, a13, a23, b12, b13, b23);

@@ -164,3 +164,48 @@ def test_reference_p3p_scalar_helpers_pin_the_oracle_bitwise():
         rr = P.p3p_refine_lambda(l0, a12, a13, a23, b12, b13, b23, ref=True)
         ro = P.p3p_refine_lambda(l0, a12, a13, a23, b12, b13, b23)
         assert np.array_equal(rr, ro, equal_nan=True)
+
+
+@pytest.mark.parametrize("kind", ["fundamental", "homography"])
+def test_reference_scorers_and_masks_pin_the_oracle_bitwise(kind):
+    """robust/utils.cc compiled from the reference: compute_sampson_msac_score(F) / get_inliers(F) and
+    compute_homography_msac_score / get_homography_inliers are element-access + scalar code, so they run as the
+    reference wrote them.  Score bits, inlier counts and masks of the oracle must be identical — for good models,
+    perturbed models, random and degenerate (rank-deficient, zero) models, on normalised and pixel-scale coordinates."""
+    rng = np.random.default_rng(5)
+    for idx in range(6):
+        n = [50, 333, 1000, 2500, 5000, 8][idx]
+        p = G.homography_problem(n, 0.5, 81, idx) if kind == "homography" else G.relpose_problem(n, 0.4, 81, idx)
+        for scale, thr in ((1.0 / G.FOCAL, 1.5 / G.FOCAL), (1.0, 2.0)):
+            x1, x2 = p["x1"] * scale, p["x2"] * scale
+            if kind == "homography":
+                gt = p["H_gt"]  # exact for the normalised coordinates, merely "some model" for the pixel-scale ones
+            else:
+                t = p["t_gt"]
+                gt = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]) @ p["R_gt"]
+            models = [gt, gt + rng.normal(0, 1e-3, (3, 3)), rng.normal(size=(3, 3)), np.zeros((3, 3)),
+                      np.outer(rng.normal(size=3), rng.normal(size=3)), np.eye(3)]
+            for M in models:
+                sr, cr, mr = P.ref_score(kind, M, x1, x2, thr * thr, want_inliers=True)
+                so, co = P.score(kind, M, x1, x2, thr * thr)
+                mo = P.inliers(kind, M, x1, x2, thr * thr)
+                assert cr == co
+                assert (sr == so) or (np.isnan(sr) and np.isnan(so)), (sr, so)
+                assert np.array_equal(mr, mo)
+
+
+def test_reference_real_focal_check_pins_the_oracle():
+    rng = np.random.default_rng(6)
+    agree = 0
+    for i in range(3000):
+        if i % 3 == 0:
+            p = G.relpose_problem(8, 1.0, 82, i)
+            t = p["t_gt"]
+            f1, f2 = rng.uniform(0.5, 3.0, 2)
+            E = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]) @ p["R_gt"]
+            F = np.diag([1 / f2, 1 / f2, 1.0]) @ E @ np.diag([1 / f1, 1 / f1, 1.0]) + rng.normal(0, 1e-4, (3, 3)) * (i % 2)
+        else:
+            F = rng.normal(size=(3, 3))
+        assert P.ref_calculate_RFC(F) == bool(P.calculate_RFC(F))
+        agree += 1
+    assert agree == 3000
