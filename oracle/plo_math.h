@@ -3,10 +3,10 @@
 //
 // PARITY PARTLY PINNED.  The reference (PoseLib @ a69263d) as a whole cannot be compiled here (Eigen3 absent) and its
 // tests hold no golden vectors for the solver/scorer arithmetic.  What DOES compile without Eigen
-// arithmetic — robust/sampling.cc, the loop templates of robust/ransac_impl.h, misc/univariate.cc and the Sturm
-// templates of misc/sturm.h — is built from the reference sources into oracle/_ref (oracle/ref/ref_capi.cc) and pins
-// the oracle's sampler, loop control flow, iteration arithmetic, cubic/quadratic solvers and Sturm root isolation bit
-// for bit (tests/test_ref_pins.py).  Everything that needs Eigen arithmetic stays UNPINNED.  This file
+// arithmetic — robust/sampling.cc, the loop templates of robust/ransac_impl.h, misc/univariate.cc, the Sturm templates of
+// misc/sturm.h, the scalar helpers of solvers/p3p_common.h and the element-access-only functions of robust/utils.cc — is built from the reference sources into oracle/_ref (oracle/ref/ref_capi.cc) and pins
+// the oracle's sampler, loop control flow, iteration arithmetic, cubic/quadratic/p3p scalar solvers, Sturm root isolation,
+// F / H scorers, masks and the real-focal check bit for bit (tests/test_ref_pins.py).  Everything that needs Eigen arithmetic stays UNPINNED.  This file
 // restates, as plain sequential loops, the small Eigen routines whose arithmetic shapes PoseLib's
 // results.  Eigen's source is not available here; semantics are recalled from
 // Eigen 3.4 and summation order is canonical left-to-right.
