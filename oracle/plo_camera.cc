@@ -1,5 +1,5 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
-// PARITY PARTLY PINNED: sampler, loop control flow, iteration arithmetic, univariate / p3p scalar solvers, Sturm root isolation, F / H scorers, masks and the real-focal check against the reference's own code (oracle/_ref, oracle/ref/ref_capi.cc); the Eigen-dependent arithmetic is UNPINNED.
+// PARITY PARTLY PINNED: sampler, loop control flow, iteration arithmetic, univariate / p3p scalar solvers, Sturm root isolation, F / H scorers, masks, the real-focal check and the scalar camera code against the reference's own code (oracle/_ref, oracle/ref/ref_capi.cc); the Eigen-dependent arithmetic is UNPINNED.
 // Camera models on the path of estimate_absolute_pose / estimate_relative_pose
 // (misc/camera_models.{h,cc}, paths relative to /root/reference/PoseLib):
 // NULL, SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, RADIAL, OPENCV.
@@ -331,3 +331,27 @@ void Camera::unproject_with_jac(const Vec2 &xp, Vec3 *x, double M[3][2]) const {
 }
 
 } // namespace plo
+
+// test hooks for the scalar helpers above (anonymous namespace), compared with the reference's camera_models.cc
+// through oracle/_ref (tests/test_ref_pins.py)
+extern "C" {
+double plo_undistort_poly(double k1, double k2, int two, double rd) {
+    return two ? plo::undistort_poly2(k1, k2, rd) : plo::undistort_poly1(k1, rd);
+}
+void plo_opencv_distortion(const double *d4, const double *x2, double *out2, double *jac4) {
+    if (jac4) {
+        double J[2][2];
+        plo::opencv_distortion_jac(d4[0], d4[1], d4[2], d4[3], x2, out2, J);
+        jac4[0] = J[0][0]; jac4[1] = J[0][1]; jac4[2] = J[1][0]; jac4[3] = J[1][1];
+    } else {
+        plo::opencv_distortion(d4[0], d4[1], d4[2], d4[3], x2, out2);
+    }
+}
+void plo_camera_rescale(int model_id, double *params8, double scale) {
+    plo::Camera c;
+    c.model_id = model_id;
+    for (int i = 0; i < 8; ++i) c.params[i] = params8[i];
+    c.rescale(scale);
+    for (int i = 0; i < 8; ++i) params8[i] = c.params[i];
+}
+}

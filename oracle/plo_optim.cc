@@ -1,5 +1,5 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
-// PARITY PARTLY PINNED: sampler, loop control flow, iteration arithmetic, univariate / p3p scalar solvers, Sturm root isolation, F / H scorers, masks and the real-focal check against the reference's own code (oracle/_ref, oracle/ref/ref_capi.cc); the Eigen-dependent arithmetic is UNPINNED.
+// PARITY PARTLY PINNED: sampler, loop control flow, iteration arithmetic, univariate / p3p scalar solvers, Sturm root isolation, F / H scorers, masks, the real-focal check and the scalar camera code against the reference's own code (oracle/_ref, oracle/ref/ref_capi.cc); the Eigen-dependent arithmetic is UNPINNED.
 // Levenberg-Marquardt + normal-equation accumulator + robust losses + the four refiners used by
 // LO and by the post-RANSAC polish, restated from PoseLib (paths relative to /root/reference).
 #include "plo.h"

@@ -561,3 +561,53 @@ def ref_score(kind, M, x1, x2, sq_thr, want_inliers=False):
 def ref_calculate_RFC(F):
     m, mp = _cm(F)
     return bool(ref_lib().plref_calculate_RFC(mp))
+
+
+def undistort_poly(k1, k2, two, rd, ref=False):
+    L = ref_lib() if ref else lib()
+    fn = getattr(L, ("plref_" if ref else "plo_") + "undistort_poly")
+    fn.restype = C.c_double
+    return fn(C.c_double(k1), C.c_double(k2), int(two), C.c_double(rd))
+
+
+def opencv_distortion(d4, x2, with_jac=False, ref=False):
+    L = ref_lib() if ref else lib()
+    d, dp = _d(d4)
+    x, xp = _d(x2)
+    out, jac = np.zeros(2), np.zeros(4)
+    getattr(L, ("plref_" if ref else "plo_") + "opencv_distortion")(dp, xp, out.ctypes.data_as(C.POINTER(C.c_double)),
+                                                                    jac.ctypes.data_as(C.POINTER(C.c_double)) if with_jac else None)
+    return (out, jac.reshape(2, 2)) if with_jac else out
+
+
+def ref_camera_project(cam, X, with_jac=False):
+    """Camera::project (models 0, 1, 2, 4) / Camera::project_with_jac (models 0, 1) of the reference (oracle/_ref)."""
+    mid, params = CAMERA_IDS[cam[0].upper()], np.ascontiguousarray(cam[1], dtype=np.float64)
+    Xa, Xp = _d(X)
+    n = len(X)
+    pp = params.ctypes.data_as(C.POINTER(C.c_double))
+    if with_jac:
+        out = np.zeros((n, 8))
+        ref_lib().plref_camera_project_with_jac(mid, pp, len(params), Xp, C.c_uint64(n), out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out[:, :2].copy(), out[:, 2:].reshape(n, 2, 3).copy()
+    out = np.zeros((n, 2))
+    ref_lib().plref_camera_project(mid, pp, len(params), Xp, C.c_uint64(n), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
+
+
+def ref_camera_focal(cam):
+    params = np.ascontiguousarray(cam[1], dtype=np.float64)
+    ref_lib().plref_camera_focal.restype = C.c_double
+    return ref_lib().plref_camera_focal(CAMERA_IDS[cam[0].upper()], params.ctypes.data_as(C.POINTER(C.c_double)), len(params))
+
+
+def camera_rescale(cam, scale, ref=False):
+    mid = CAMERA_IDS[cam[0].upper()]
+    if ref:
+        params = np.ascontiguousarray(cam[1], dtype=np.float64).copy()
+        ref_lib().plref_camera_rescale(mid, params.ctypes.data_as(C.POINTER(C.c_double)), len(params), C.c_double(scale))
+        return params
+    p8 = np.zeros(8)
+    p8[:len(cam[1])] = cam[1]
+    lib().plo_camera_rescale(mid, p8.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(scale))
+    return p8[:len(cam[1])]

@@ -13,6 +13,10 @@
 //                                             (The rest of utils.cc compiles against the Eigen stand-in but references
 //                                             undefined Eigen symbols and is never called; the library is therefore
 //                                             loaded with lazy binding.)
+//   * PoseLib/misc/camera_models.cc         — likewise the scalar parts: undistort_poly1/2 (Newton undistortion),
+//                                             compute_opencv_distortion(_jac), Camera::focal / rescale, and through
+//                                             Camera::project / project_with_jac the PINHOLE, SIMPLE_PINHOLE,
+//                                             SIMPLE_RADIAL and OPENCV projections that only touch elements
 // The templates are instantiated (a) with the MockEstimator of the reference's tests/ransac_test.cc:12-28 and (b) with
 // this repository's oracle estimators (solver / scorer / refiner restatements of oracle/plo_robust.cc), so that the
 // REFERENCE's loop drives them: comparing the outcome with the oracle's own loop pins the control flow of
@@ -141,6 +145,76 @@ int plref_solve_cubic_single_real(double c2, double c1, double c0, double *root)
 int plref_solve_cubic_real(double c2, double c1, double c0, double *roots) {
     return poselib::univariate::solve_cubic_real(c2, c1, c0, roots);
 }
+// misc/camera_models.cc: scalar functions defined there at namespace scope (not declared in a header)
+extern "C++" {
+namespace poselib {
+double undistort_poly1(double k1, double rd);
+double undistort_poly2(double k1, double k2, double rd);
+void compute_opencv_distortion(double k1, double k2, double p1, double p2, const Eigen::Vector2d &x, Eigen::Vector2d &xp);
+void compute_opencv_distortion_jac(double k1, double k2, double p1, double p2, const Eigen::Vector2d &x, Eigen::Vector2d &xp,
+                                   Eigen::Matrix2d &jac, Eigen::Matrix<double, 2, 4> *jacp);
+} // namespace poselib
+} // extern "C++"
+static poselib::Camera cam_ref(int model_id, const double *params, int np) {
+    poselib::Camera c;
+    c.model_id = model_id;
+    c.params.assign(params, params + np);
+    return c;
+}
+double plref_undistort_poly(double k1, double k2, int two, double rd) {
+    return two ? poselib::undistort_poly2(k1, k2, rd) : poselib::undistort_poly1(k1, rd);
+}
+// d4 = k1,k2,p1,p2; out2 = distorted point; jac4 (may be null) = row-major 2x2
+void plref_opencv_distortion(const double *d4, const double *x2, double *out2, double *jac4) {
+    Eigen::Vector2d x, xp;
+    x(0) = x2[0];
+    x(1) = x2[1];
+    if (jac4) {
+        Eigen::Matrix2d J;
+        poselib::compute_opencv_distortion_jac(d4[0], d4[1], d4[2], d4[3], x, xp, J, nullptr);
+        jac4[0] = J(0, 0); jac4[1] = J(0, 1); jac4[2] = J(1, 0); jac4[3] = J(1, 1);
+    } else {
+        poselib::compute_opencv_distortion(d4[0], d4[1], d4[2], d4[3], x, xp);
+    }
+    out2[0] = xp(0);
+    out2[1] = xp(1);
+}
+// Camera::project for the models whose projection only touches elements (ids 0 SIMPLE_PINHOLE, 1 PINHOLE,
+// 2 SIMPLE_RADIAL, 4 OPENCV); out: n x 2
+void plref_camera_project(int model_id, const double *params, int np, const double *X, uint64_t n, double *out) {
+    const poselib::Camera c = cam_ref(model_id, params, np);
+    for (uint64_t k = 0; k < n; ++k) {
+        Eigen::Vector3d x;
+        x(0) = X[3 * k]; x(1) = X[3 * k + 1]; x(2) = X[3 * k + 2];
+        Eigen::Vector2d xp;
+        c.project(x, &xp);
+        out[2 * k] = xp(0);
+        out[2 * k + 1] = xp(1);
+    }
+}
+// Camera::project_with_jac (point Jacobian, no parameter Jacobian) for the pinhole family (ids 0, 1);
+// out: n x (2 + 6 row-major 2x3)
+void plref_camera_project_with_jac(int model_id, const double *params, int np, const double *X, uint64_t n, double *out) {
+    const poselib::Camera c = cam_ref(model_id, params, np);
+    for (uint64_t k = 0; k < n; ++k) {
+        Eigen::Vector3d x;
+        x(0) = X[3 * k]; x(1) = X[3 * k + 1]; x(2) = X[3 * k + 2];
+        Eigen::Vector2d xp;
+        Eigen::Matrix<double, 2, 3> J;
+        c.project_with_jac(x, &xp, &J);
+        out[8 * k] = xp(0);
+        out[8 * k + 1] = xp(1);
+        for (int r = 0; r < 2; ++r)
+            for (int q = 0; q < 3; ++q) out[8 * k + 2 + 3 * r + q] = J(r, q);
+    }
+}
+double plref_camera_focal(int model_id, const double *params, int np) { return cam_ref(model_id, params, np).focal(); }
+void plref_camera_rescale(int model_id, double *params, int np, double scale) {
+    poselib::Camera c = cam_ref(model_id, params, np);
+    c.rescale(scale);
+    for (int i = 0; i < np; ++i) params[i] = c.params[i];
+}
+
 // robust/utils.cc: element-access-only scorers / masks / RFC of the reference.  F, H column-major 9 doubles.
 static Eigen::Matrix3d mat_in(const double *m9) {
     Eigen::Matrix3d M;

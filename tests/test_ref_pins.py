@@ -209,3 +209,36 @@ def test_reference_real_focal_check_pins_the_oracle():
         assert P.ref_calculate_RFC(F) == bool(P.calculate_RFC(F))
         agree += 1
     assert agree == 3000
+
+
+REF_CAMERAS = [  # tests/example_cameras.h of the reference (the models whose projection is element-access code)
+    ("SIMPLE_RADIAL", [2425.85, 932.383, 628.265, -0.0397695]),
+    ("PINHOLE", [3425.62, 3426.29, 3118.41, 2069.07]),
+    ("SIMPLE_PINHOLE", [3425.62, 3118.41, 2069.07]),
+    ("OPENCV", [2575.94, 2608.29, 1599.26, 1257.13, 0.141865, -0.465301, 0, 0]),
+    ("OPENCV", [868.993378, 866.063001, 525.942323, 420.042529, -0.399431, 0.188924, 0.000153, 0.000571]),
+]
+
+
+def test_reference_camera_scalar_code_pins_the_oracle_bitwise():
+    """misc/camera_models.cc compiled from the reference: Newton undistortion (undistort_poly1/2), the OpenCV distortion
+    and its Jacobian, Camera::focal / rescale, and the projections (+ pinhole projection Jacobians) that are pure
+    element-access code."""
+    rng = np.random.default_rng(8)
+    for _ in range(3000):
+        k1, k2, rd = rng.normal(0, 0.2), rng.normal(0, 0.05), abs(rng.normal(0, 0.6))
+        for two in (0, 1):
+            assert P.undistort_poly(k1, k2, two, rd, ref=True) == P.undistort_poly(k1, k2, two, rd)
+        d4, x2 = rng.normal(0, [0.3, 0.2, 1e-3, 1e-3]), rng.normal(0, 0.5, 2)
+        assert np.array_equal(P.opencv_distortion(d4, x2, ref=True), P.opencv_distortion(d4, x2))
+        (xr, jr), (xo, jo) = P.opencv_distortion(d4, x2, True, ref=True), P.opencv_distortion(d4, x2, True)
+        assert np.array_equal(xr, xo) and np.array_equal(jr, jo)
+    X = np.c_[rng.uniform(-0.6, 0.6, (500, 2)), np.ones(500)] * rng.uniform(0.5, 9.0, (500, 1))
+    for cam in REF_CAMERAS:
+        assert P.ref_camera_focal(cam) == P.camera_focal(cam)
+        assert np.array_equal(P.camera_rescale(cam, 1.0 / 1234.5, ref=True), P.camera_rescale(cam, 1.0 / 1234.5))
+        xp_jac, J, xp = P.camera_project_with_jac(cam, X)
+        assert np.array_equal(P.ref_camera_project(cam, X), xp)
+        if cam[0] in ("PINHOLE", "SIMPLE_PINHOLE"):
+            rxp, rJ = P.ref_camera_project(cam, X, with_jac=True)
+            assert np.array_equal(rxp, xp_jac) and np.array_equal(rJ, J)
