@@ -1,5 +1,5 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
-// PARITY PARTLY PINNED: sampler, loop control flow, iteration arithmetic, univariate / p3p scalar solvers, Sturm root isolation, F / H scorers, masks, the real-focal check and the scalar camera code against the reference's own code (oracle/_ref, oracle/ref/ref_capi.cc); the Eigen-dependent arithmetic is UNPINNED.
+// PARITY PARTLY PINNED: sampler, loop control flow, iteration arithmetic, univariate / p3p scalar solvers, Sturm root isolation, F / H scorers, masks, the real-focal check and the scalar camera code against the reference's own code (oracle/_ref, oracle/ref/ref_capi.cc); the transcription of PoseLib's logic for the WHOLE path (solvers, scorers, refiners, estimators, estimate_*) against the reference's own sources run on mini-Eigen (oracle/_ref/libplref2.so, oracle/ref/ref2_capi.cc, tests/test_ref_sources.py); Eigen's own arithmetic (reduction order, decompositions) is UNPINNED.
 // extern "C" surface of the CPU oracle for ctypes (tests/, __graft_entry__.smoke(), bench.py cpu legs).
 // 3x3 matrices cross this boundary as 9 doubles COLUMN-MAJOR (Eigen::Matrix3d layout); poses as q(wxyz)+t.
 #include "plo.h"

@@ -6,7 +6,10 @@
 // arithmetic — robust/sampling.cc, the loop templates of robust/ransac_impl.h, misc/univariate.cc, the Sturm templates of
 // misc/sturm.h, the scalar helpers of solvers/p3p_common.h and the element-access-only functions of robust/utils.cc — is built from the reference sources into oracle/_ref (oracle/ref/ref_capi.cc) and pins
 // the oracle's sampler, loop control flow, iteration arithmetic, cubic/quadratic/p3p scalar solvers, Sturm root isolation,
-// F / H scorers, masks and the real-focal check bit for bit (tests/test_ref_pins.py).  Everything that needs Eigen arithmetic stays UNPINNED.  This file
+// F / H scorers, masks and the real-focal check bit for bit (tests/test_ref_pins.py).  The reference's own sources for the
+// whole path, compiled unmodified on top of mini-Eigen (oracle/ref/mini: Eigen's interface implemented with THIS
+// file's routines), pin the oracle's transcription of PoseLib's logic end to end (oracle/_ref/libplref2.so,
+// tests/test_ref_sources.py).  Whether the routines below equal real Eigen's bit for bit stays UNPINNED.  This file
 // restates, as plain sequential loops, the small Eigen routines whose arithmetic shapes PoseLib's
 // results.  Eigen's source is not available here; semantics are recalled from
 // Eigen 3.4 and summation order is canonical left-to-right.
@@ -122,8 +125,8 @@ inline Mat3 quat_to_rotmat(const Vec4 &q) {
     R(2, 0) = txz - twy;       R(2, 1) = tyz + twx;       R(2, 2) = 1 - (txx + tyy);
     return R;
 }
-// Eigen::Quaterniond(R) then q.normalize()  (quaternion.h:45-51; SURVEY Appendix C)
-inline Vec4 rotmat_to_quat(const Mat3 &R) {
+// Eigen::Quaterniond(R), not yet normalised (w,x,y,z)  (quaternion.h:45-48)
+inline Vec4 rotmat_to_quat_raw(const Mat3 &R) {
     double q[4]; // x,y,z at [0..2], w at [3]
     double t = R(0, 0) + R(1, 1) + R(2, 2);
     if (t > 0) {
@@ -147,6 +150,11 @@ inline Vec4 rotmat_to_quat(const Mat3 &R) {
     }
     Vec4 out;
     out[0] = q[3]; out[1] = q[0]; out[2] = q[1]; out[3] = q[2];
+    return out;
+}
+// Eigen::Quaterniond(R) then q.normalize()  (quaternion.h:45-51; SURVEY Appendix C)
+inline Vec4 rotmat_to_quat(const Mat3 &R) {
+    Vec4 out = rotmat_to_quat_raw(R);
     double n2 = out[0] * out[0] + out[1] * out[1] + out[2] * out[2] + out[3] * out[3];
     if (n2 > 0) {
         double n = std::sqrt(n2);

@@ -4,7 +4,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu legs may import this mod
 package (poselib_b200/) never does.  PARITY PARTLY PINNED: the oracle is a restatement of PoseLib's CPU
 path without Eigen, not a build of PoseLib; the Eigen-free parts of the reference (sampler, loop templates, univariate
 solvers, Sturm) are built into oracle/_ref and pin the corresponding oracle functions bit for bit (tests/test_ref_pins.py),
-the Eigen-dependent arithmetic is unpinned.
+the reference's own sources for the whole path run on mini-Eigen (oracle/_ref/libplref2.so, tests/test_ref_sources.py)
+and pin the transcription of PoseLib's logic end to end; Eigen's own arithmetic (reduction order, decompositions) is
+unpinned.
 """
 import ctypes as C
 import os
@@ -72,8 +74,14 @@ def build(force=False):
 _lib = None
 
 
+_DOUBLE_RETURNS = ("plo_score_pnp", "plo_score_relpose", "plo_score_fundamental", "plo_score_homography",
+                   "plo_score_tangent", "plo_camera_focal")
+
+
 def lib():
     global _lib
+    if _use_ref2:
+        return _Ref2Proxy()
     if _lib is None:
         build()
         _lib = C.CDLL(_LIB_PATH)
@@ -611,3 +619,51 @@ def camera_rescale(cam, scale, ref=False):
     p8[:len(cam[1])] = cam[1]
     lib().plo_camera_rescale(mid, p8.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(scale))
     return p8[:len(cam[1])]
+
+
+# ---- oracle/_ref/libplref2.so: the reference's own sources for the whole path on mini-Eigen ------------------------
+# (oracle/ref/ref2_capi.cc).  Its entry points mirror the oracle's (plr2_* for plo_*), so every wrapper of this module
+# can be pointed at it:   with P.reference_sources(): P.estimate(...)
+_REF2_PATH = os.path.join(_HERE, "_ref", "libplref2.so")
+_ref2 = None
+_use_ref2 = False
+
+
+def ref2_available(build_if_possible=True):
+    if not os.path.exists(_REF2_PATH) and build_if_possible and os.path.isdir("/root/reference/PoseLib"):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref2"])
+    return os.path.exists(_REF2_PATH)
+
+
+def ref2_lib():
+    global _ref2
+    if _ref2 is None:
+        if not ref2_available():
+            raise RuntimeError("oracle/_ref/libplref2.so is not built (needs /root/reference)")
+        # lazy binding: the estimators reference out-of-scope solvers (p4pf, gp3p, ...) that are not compiled in
+        _ref2 = C.CDLL(_REF2_PATH, mode=os.RTLD_LAZY)
+        for n in _DOUBLE_RETURNS:
+            getattr(_ref2, "plr2_" + n[4:]).restype = C.c_double
+    return _ref2
+
+
+class _Ref2Proxy:
+    def __getattr__(self, name):
+        if not name.startswith("plo_"):
+            raise AttributeError(name)
+        return getattr(ref2_lib(), "plr2_" + name[4:])
+
+
+class reference_sources:
+    """Context manager: the wrappers of this module call the reference's sources (libplref2.so) instead of the oracle."""
+
+    def __enter__(self):
+        global _use_ref2
+        self._prev = _use_ref2
+        _use_ref2 = True
+        return self
+
+    def __exit__(self, *exc):
+        global _use_ref2
+        _use_ref2 = self._prev
+        return False
