@@ -10,7 +10,8 @@ scored-correspondences/s alongside.
           correspondences / sample tables and the device->host read of records, models and inlier masks are inside
           the timed region (counted from the copies the engine makes)
   --impl reference : the CPU restatement of the reference path (oracle/, the reference itself needs Eigen3, which
-          this image lacks) on the host cores, one problem per thread, same config/metric.
+          this image lacks) on the host cores, one problem per thread, same config/metric; the reference's own sources
+          built on mini-Eigen (oracle/_ref/libplref2.so) are timed beside it as `reference_sources` (informational).
 Multi-GPU (torchrun): independent image pairs are sharded across ranks, no data-path collective; weak scaling.
 """
 import argparse
@@ -131,6 +132,7 @@ def run_reference(args, rank, world):
         cor += sum(c["scored_corrs"] for c in cnts)
         smp += sum(c["samples"] for c in cnts)
     val = hyp / t_tot
+    ref_src = reference_sources_leg(P, x1, x2, opts, me, threads, stats, cnts)
     line = {
         "impl": "reference", "metric": "RANSAC hypotheses/sec (5pt E, 10k corrs)", "value": val, "unit": "hypotheses/s",
         "scored_corrs_per_s": cor / t_tot, "samples_per_s": smp / t_tot, "n_gpus": args.gpus, "steps": args.steps,
@@ -143,7 +145,30 @@ def run_reference(args, rank, world):
                                    "g++ -O3 -ffp-contract=off"},
         "e2e": {"value": val, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if ref_src:
+        line["reference_sources"] = ref_src
     print(json.dumps(line))
+
+
+def reference_sources_leg(P, x1, x2, opts, me, threads, stats, cnts):
+    """Informational: the reference's OWN sources (oracle/_ref/libplref2.so: robust/ransac.cc, estimators, solvers,
+    scorers, bundle, compiled unmodified on mini-Eigen) on the same problems, one problem per thread.  That build pays for
+    mini-Eigen's heap temporaries and bounds checks, so it is slower than the reference with real Eigen would be; the
+    arm's `value` therefore stays the faster oracle port and this number is reported beside it, not instead of it."""
+    if not P.ref2_available(build_if_possible=False):
+        return None
+    from concurrent.futures import ThreadPoolExecutor
+    with P.reference_sources():
+        P.ransac("relpose", x1[0], x2[0], opts[0], me[0])  # load + warm
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=threads) as ex:  # ctypes releases the GIL inside the call
+            out = list(ex.map(lambda i: P.ransac("relpose", x1[i], x2[i], opts[i], me[i])["stats"], range(len(x1))))
+        sec = time.perf_counter() - t0
+    same = sum(int(o["iterations"] == s["iterations"] and o["num_inliers"] == s["num_inliers"]) for o, s in zip(out, stats))
+    hyp = sum(c["hypotheses"] for c in cnts)  # same trajectory => same hypotheses; counted by the oracle run
+    return {"value": hyp / sec, "unit": "hypotheses/s", "cores": threads, "kind": "reference",
+            "problems": len(x1), "same_trajectory_as_port": f"{same}/{len(x1)}",
+            "note": "PoseLib sources unmodified on mini-Eigen (no Eigen3 in this image); slower than a real-Eigen build"}
 
 
 def main():

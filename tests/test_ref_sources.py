@@ -231,3 +231,29 @@ def test_distorted_cameras_and_tangent_sampson_path():
         xd = P.camera_project_with_jac(c, np.c_[q["x"] / G.FOCAL, np.ones(len(q["x"]))])[2]
         a, b = both(lambda: P.estimate("pnp", xd, q["X"], P.RansacOpt(**q["ransac"]), P.BundleOpt(), 12.0, c))
         assert same(a, b) and a["stats"]["num_inliers"] >= 90
+
+
+# ---- edge sizes -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["relpose", "fundamental", "homography", "pnp"])
+def test_edge_sizes_agree_in_all_discrete_outputs(kind):
+    """Fewer points than the sample size, exactly the sample size, all inliers, all outliers, max < min iterations:
+    the reference's sources and the oracle take the same path (iterations, refinements, inlier count, mask)."""
+    for n in (2, 3, 4, 5, 6, 7, 8, 9, 12, 30):
+        for ratio in (1.0, 0.5, 0.0):
+            if kind == "pnp":
+                q = G.abspose_problem(max(n, 10), ratio, 1, n)
+                a1, a2, thr, kw = q["x"][:n], q["X"][:n], 12.0, dict(cam1=CAMT)
+            elif kind == "homography":
+                h = G.homography_problem(max(n, 10), ratio, 4, n)
+                a1, a2, thr, kw = h["x1"][:n], h["x2"][:n], 1.0, {}
+            else:
+                p = G.relpose_problem(max(n, 10), ratio, 2, n)
+                a1, a2, thr = p["x1"][:n], p["x2"][:n], 1.0
+                kw = dict(cam1=CAMT, cam2=CAMT) if kind == "relpose" else {}
+            for ro in (P.RansacOpt(max_iterations=200, min_iterations=20, seed=n),
+                       P.RansacOpt(max_iterations=10, min_iterations=50, seed=n)):
+                a, b = both(lambda: P.estimate(kind, a1, a2, ro, P.BundleOpt(), thr, **kw))
+                sa, sb = a["stats"], b["stats"]
+                assert (sa["iterations"], sa["refinements"], sa["num_inliers"]) == \
+                       (sb["iterations"], sb["refinements"], sb["num_inliers"]), (kind, n, ratio)
+                assert np.array_equal(a["inliers"], b["inliers"]), (kind, n, ratio)
