@@ -1,0 +1,121 @@
+"""Case table shared by tests/golden/make_reference_golden.py (which runs the REFERENCE'S OWN SOURCES on it), the CPU test
+(oracle vs the committed fixtures) and the GPU test (CUDA path vs the committed fixtures).  Every case repeats, input for
+input and option for option, a case of tests/test_gpu_parity.py."""
+import numpy as np
+
+from poselib_b200 import problem_generator as G
+
+CAMT = (G.FOCAL, G.FOCAL, 0.0, 0.0)
+
+
+def _pnp(n, ratio, its, seed):
+    p = G.abspose_problem(n, ratio, 1, seed)
+    return dict(api="ransac", kind="pnp", a=p["x"] / G.FOCAL, b=p["X"], me=12.0 / G.FOCAL,
+                kw=dict(max_iterations=its, min_iterations=min(its, 1000), seed=seed))
+
+
+def _relpose(n, ratio, seed):
+    p = G.relpose_problem(n, ratio, 2, seed)
+    return dict(api="ransac", kind="relpose", a=p["x1"] / G.FOCAL, b=p["x2"] / G.FOCAL, me=1.0 / G.FOCAL,
+                kw=dict(max_iterations=100000, min_iterations=1000, seed=seed))
+
+
+def _fundamental(prosac, rfc, seed):
+    p = G.relpose_problem(2000, 0.3, 3, seed, prosac_sorted=prosac)
+    return dict(api="ransac", kind="fundamental", a=p["x1"] / 500.0, b=p["x2"] / 500.0, me=1.0 / 500.0, rfc=rfc,
+                kw=dict(max_iterations=20000, min_iterations=1000, seed=seed, progressive_sampling=prosac,
+                        max_prosac_iterations=5000))
+
+
+def _homography(n, ratio, seed):
+    p = G.homography_problem(n, ratio, 4, seed)
+    return dict(api="ransac", kind="homography", a=p["x1"] / G.FOCAL, b=p["x2"] / G.FOCAL, me=1.0 / G.FOCAL,
+                kw=dict(max_iterations=100000, min_iterations=1000, seed=seed))
+
+
+def _initial_model():
+    p = G.relpose_problem(800, 0.5, 2, 11)
+    return dict(api="ransac", kind="relpose", a=p["x1"] / G.FOCAL, b=p["x2"] / G.FOCAL, me=1.0 / G.FOCAL,
+                init=np.r_[p["q_gt"], p["t_gt"]],
+                kw=dict(max_iterations=2000, min_iterations=50, seed=5, score_initial_model=True))
+
+
+def _est_pnp():
+    p = G.config_c1(3)
+    return dict(api="estimate", kind="pnp", a=p["x"], b=p["X"], me=p["max_error"], cams=1, kw=dict(p["ransac"]))
+
+
+def _est_relpose():
+    p = G.relpose_problem(3000, 0.4, 2, 5)
+    return dict(api="estimate", kind="relpose", a=p["x1"], b=p["x2"], me=1.0, cams=2,
+                kw=dict(max_iterations=20000, min_iterations=500, seed=2))
+
+
+def _est_fundamental():
+    p = G.relpose_problem(2000, 0.4, 3, 6, prosac_sorted=True)
+    return dict(api="estimate", kind="fundamental", a=p["x1"], b=p["x2"], me=1.0, cams=0, rfc=True,
+                kw=dict(max_iterations=20000, min_iterations=500, seed=2, progressive_sampling=True))
+
+
+def _est_homography():
+    p = G.homography_problem(3000, 0.6, 4, 7)
+    return dict(api="estimate", kind="homography", a=p["x1"], b=p["x2"], me=1.0, cams=0,
+                kw=dict(max_iterations=20000, min_iterations=500, seed=2))
+
+
+CASES = {}
+for _s in (0, 1, 2):
+    CASES[f"ransac_pnp_200_s{_s}"] = lambda s=_s: _pnp(200, 0.5, 1000, s)
+    CASES[f"ransac_pnp_1500_s{_s}"] = lambda s=_s: _pnp(1500, 0.35, 3000, s)
+    CASES[f"ransac_relpose_1000_s{_s}"] = lambda s=_s: _relpose(1000, 0.5, s)
+    CASES[f"ransac_relpose_10000_s{_s}"] = lambda s=_s: _relpose(10000, 0.3, s)
+for _s in (0, 1):
+    CASES[f"ransac_fundamental_s{_s}"] = lambda s=_s: _fundamental(False, False, s)
+    CASES[f"ransac_fundamental_prosac_rfc_s{_s}"] = lambda s=_s: _fundamental(True, True, s)
+    CASES[f"ransac_homography_2000_s{_s}"] = lambda s=_s: _homography(2000, 0.6, s)
+    CASES[f"ransac_homography_20000_s{_s}"] = lambda s=_s: _homography(20000, 0.6, s)
+CASES["ransac_relpose_initial_model"] = _initial_model
+CASES["estimate_pnp_c1"] = _est_pnp
+CASES["estimate_relpose_3000"] = _est_relpose
+CASES["estimate_fundamental_prosac_rfc"] = _est_fundamental
+CASES["estimate_homography_3000"] = _est_homography
+
+
+def run(api, case):
+    """api: oracle/plo_py (also inside `with plo_py.reference_sources()`) or poselib_b200.cabi — same call surface."""
+    ro = api.RansacOpt(**case["kw"])
+    extra = {}
+    if "rfc" in case:
+        extra["rfc"] = case["rfc"]
+    if "init" in case:
+        extra["init"] = case["init"]
+    if case["api"] == "ransac":
+        return api.ransac(case["kind"], case["a"], case["b"], ro, case["me"], **extra)
+    cam = api.Camera("PINHOLE", CAMT) if hasattr(api, "Camera") else CAMT
+    cams = [cam] * case["cams"]
+    return api.estimate(case["kind"], case["a"], case["b"], ro, api.BundleOpt(), case["me"], *cams, **extra)
+
+
+def pack_mask(m):
+    return np.packbits(np.asarray(m, dtype=np.uint8) != 0).tobytes().hex()
+
+
+def check(result, gold, kind, model_tol, score_rtol):
+    """Discrete outputs exact; score and model within the stated tolerances (F / H up to sign, |t| of a relative pose
+    up to its gauge — the same normalisations as tests/test_gpu_parity.py::_same_trajectory)."""
+    for k in ("iterations", "refinements", "num_inliers"):
+        assert result["stats"][k] == gold[k], (k, result["stats"][k], gold[k])
+    assert pack_mask(result["inliers"]) == gold["inliers"]
+    gs = float.fromhex(gold["model_score"])
+    assert abs(result["stats"]["model_score"] - gs) <= score_rtol * abs(gs), (result["stats"]["model_score"], gs)
+    gm = np.array([float.fromhex(v) for v in gold["model"]]).reshape(np.asarray(result["model"]).shape)
+    rm = np.asarray(result["model"], dtype=np.float64)
+    if rm.ndim == 2:
+        err = min(np.abs(rm - gm).max(), np.abs(rm + gm).max())
+    else:
+        if kind == "relpose":
+            rm = np.r_[rm[:4], rm[4:] / max(np.linalg.norm(rm[4:]), 1e-300)]
+            gm = np.r_[gm[:4], gm[4:] / max(np.linalg.norm(gm[4:]), 1e-300)]
+        err = np.abs(rm - gm).max()
+    assert err <= model_tol * np.abs(gm).max(), (err, rm, gm)
+    return err / np.abs(gm).max()

@@ -1,0 +1,28 @@
+"""GPU half of tests/test_golden_reference.py: the CUDA path, called through the C-ABI, reproduces the committed fixtures
+that PoseLib's OWN SOURCES produced (tests/golden/reference_sources.json; generator and provenance:
+tests/golden/make_reference_golden.py) — iterations, refinements, inlier counts and inlier masks exactly, the
+MSAC score to 2e-9 and the model to 2e-6 relative (north_star's 1e-6 against the oracle plus the oracle's own, measured,
+distance to the fixtures: <= 1e-10).  Every case repeats a case of tests/test_gpu_parity.py input for input.
+(The file name sorts last so that `pytest -x` reaches the oracle-parity tests first.)"""
+import json
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import reference_cases as RC  # noqa: E402
+
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_sources.json")))["cases"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(RC.CASES))
+def test_cuda_path_reproduces_the_reference_sources_fixtures(name):
+    from poselib_b200 import cabi
+    if cabi.device_count() == 0:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box")
+    cabi.set_device(0)
+    case, gold = RC.CASES[name](), GOLD[name]
+    RC.check(RC.run(cabi, case), gold, case["kind"], model_tol=2e-6, score_rtol=2e-9)
