@@ -624,43 +624,51 @@ def camera_rescale(cam, scale, ref=False):
 # ---- oracle/_ref/libplref2.so: the reference's own sources for the whole path on mini-Eigen ------------------------
 # (oracle/ref/ref2_capi.cc).  Its entry points mirror the oracle's (plr2_* for plo_*), so every wrapper of this module
 # can be pointed at it:   with P.reference_sources(): P.estimate(...)
-_REF2_PATH = os.path.join(_HERE, "_ref", "libplref2.so")
-_ref2 = None
-_use_ref2 = False
+# libplref2_alt.so is the same build with mini-Eigen's reductions in packet / tree order (sensitivity study).
+_REF2_PATHS = {"std": os.path.join(_HERE, "_ref", "libplref2.so"), "alt": os.path.join(_HERE, "_ref", "libplref2_alt.so")}
+_REF2_TARGETS = {"std": "ref2", "alt": "ref2alt"}
+_ref2 = {}
+_use_ref2 = None
 
 
-def ref2_available(build_if_possible=True):
-    if not os.path.exists(_REF2_PATH) and build_if_possible and os.path.isdir("/root/reference/PoseLib"):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "ref2"])
-    return os.path.exists(_REF2_PATH)
+def ref2_available(build_if_possible=True, variant="std"):
+    path = _REF2_PATHS[variant]
+    if not os.path.exists(path) and build_if_possible and os.path.isdir("/root/reference/PoseLib"):
+        with open(os.devnull, "w") as quiet:
+            subprocess.check_call(["make", "-C", _HERE, "-s", _REF2_TARGETS[variant]], stdout=quiet, stderr=quiet)
+    return os.path.exists(path)
 
 
-def ref2_lib():
-    global _ref2
-    if _ref2 is None:
-        if not ref2_available():
-            raise RuntimeError("oracle/_ref/libplref2.so is not built (needs /root/reference)")
+def ref2_lib(variant="std"):
+    if variant not in _ref2:
+        if not ref2_available(variant=variant):
+            raise RuntimeError(f"oracle/_ref/{os.path.basename(_REF2_PATHS[variant])} is not built (needs /root/reference)")
         # lazy binding: the estimators reference out-of-scope solvers (p4pf, gp3p, ...) that are not compiled in
-        _ref2 = C.CDLL(_REF2_PATH, mode=os.RTLD_LAZY)
+        lib2 = C.CDLL(_REF2_PATHS[variant], mode=os.RTLD_LAZY)
         for n in _DOUBLE_RETURNS:
-            getattr(_ref2, "plr2_" + n[4:]).restype = C.c_double
-    return _ref2
+            getattr(lib2, "plr2_" + n[4:]).restype = C.c_double
+        _ref2[variant] = lib2
+    return _ref2[variant]
 
 
 class _Ref2Proxy:
     def __getattr__(self, name):
         if not name.startswith("plo_"):
             raise AttributeError(name)
-        return getattr(ref2_lib(), "plr2_" + name[4:])
+        return getattr(ref2_lib(_use_ref2), "plr2_" + name[4:])
 
 
 class reference_sources:
-    """Context manager: the wrappers of this module call the reference's sources (libplref2.so) instead of the oracle."""
+    """Context manager: the wrappers of this module call the reference's sources (libplref2.so; alt=True: the build with
+    packet / tree shaped reductions) instead of the oracle."""
+
+    def __init__(self, alt=False):
+        self._variant = "alt" if alt else "std"
 
     def __enter__(self):
         global _use_ref2
         self._prev = _use_ref2
-        _use_ref2 = True
+        _use_ref2 = self._variant
         return self
 
     def __exit__(self, *exc):
