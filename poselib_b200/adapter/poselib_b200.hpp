@@ -237,6 +237,67 @@ RansacStats estimate_homography(const std::vector<P2> &x1, const std::vector<P2>
     return detail::from_c<RansacStats>(st);
 }
 
+// ---- robust/bundle.h: the LM refiners (uniform weights; the reference's optional per-residual weights are NYI) -----
+// BundleStats carries iterations, initial_cost and cost; lambda / step_norm / grad_norm stay at their defaults.
+namespace detail {
+template <typename BundleStats> inline BundleStats bundle_from_c(const double s[3]) {
+    BundleStats b = BundleStats();
+    b.iterations = static_cast<size_t>(s[0]);
+    b.initial_cost = s[1];
+    b.cost = s[2];
+    return b;
+}
+inline void no_weights(const std::vector<double> &weights) {
+    if (!weights.empty()) throw std::runtime_error("poselib_b200: NYI (per-residual weights in the LM refiners)");
+}
+} // namespace detail
+// bundle_adjust(x, X, CameraPose*, BundleOptions, weights)   robust/bundle.h:41-43
+template <typename BundleStats, typename P2, typename P3, typename Pose, typename BOpt>
+BundleStats bundle_adjust(const std::vector<P2> &x, const std::vector<P3> &X, Pose *pose, const BOpt &opt,
+                          const std::vector<double> &weights = std::vector<double>()) {
+    detail::no_weights(weights);
+    double m[7], st[3];
+    detail::pose_to(*pose, m);
+    plb_bundle_opt bo = detail::bundle_to_c(opt);
+    detail::check(plb_bundle_adjust(detail::raw(x), detail::raw(X), x.size(), m, &bo, st));
+    detail::pose_from(m, pose);
+    return detail::bundle_from_c<BundleStats>(st);
+}
+// refine_relpose(x1, x2, CameraPose*, BundleOptions, weights)   robust/bundle.h:84-86
+template <typename BundleStats, typename P2, typename Pose, typename BOpt>
+BundleStats refine_relpose(const std::vector<P2> &x1, const std::vector<P2> &x2, Pose *pose, const BOpt &opt,
+                           const std::vector<double> &weights = std::vector<double>()) {
+    detail::no_weights(weights);
+    double m[7], st[3];
+    detail::pose_to(*pose, m);
+    plb_bundle_opt bo = detail::bundle_to_c(opt);
+    detail::check(plb_refine_relpose(detail::raw(x1), detail::raw(x2), x1.size(), m, &bo, st));
+    detail::pose_from(m, pose);
+    return detail::bundle_from_c<BundleStats>(st);
+}
+// refine_fundamental(x1, x2, Matrix3d*, BundleOptions, weights)   robust/bundle.h:132-134
+template <typename BundleStats, typename P2, typename Mat3, typename BOpt>
+BundleStats refine_fundamental(const std::vector<P2> &x1, const std::vector<P2> &x2, Mat3 *F, const BOpt &opt,
+                               const std::vector<double> &weights = std::vector<double>()) {
+    static_assert(sizeof(Mat3) == 9 * sizeof(double), "column-major 3x3 of doubles required");
+    detail::no_weights(weights);
+    double st[3];
+    plb_bundle_opt bo = detail::bundle_to_c(opt);
+    detail::check(plb_refine_fundamental(detail::raw(x1), detail::raw(x2), x1.size(), reinterpret_cast<double *>(F), &bo, st));
+    return detail::bundle_from_c<BundleStats>(st);
+}
+// refine_homography(x1, x2, Matrix3d*, BundleOptions, weights)   robust/bundle.h:148-150
+template <typename BundleStats, typename P2, typename Mat3, typename BOpt>
+BundleStats refine_homography(const std::vector<P2> &x1, const std::vector<P2> &x2, Mat3 *H, const BOpt &opt,
+                              const std::vector<double> &weights = std::vector<double>()) {
+    static_assert(sizeof(Mat3) == 9 * sizeof(double), "column-major 3x3 of doubles required");
+    detail::no_weights(weights);
+    double st[3];
+    plb_bundle_opt bo = detail::bundle_to_c(opt);
+    detail::check(plb_refine_homography(detail::raw(x1), detail::raw(x2), x1.size(), reinterpret_cast<double *>(H), &bo, st));
+    return detail::bundle_from_c<BundleStats>(st);
+}
+
 // ---- solvers/*.h (one instance; unit bearing vectors).  Return value = number of solutions, like the reference.
 template <typename V3, typename Pose> int p3p(const std::vector<V3> &x, const std::vector<V3> &X, std::vector<Pose> *output) {
     if (output == nullptr) return 0; // p3p.cc:41-43
