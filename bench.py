@@ -132,7 +132,10 @@ def run_reference(args, rank, world):
         cor += sum(c["scored_corrs"] for c in cnts)
         smp += sum(c["samples"] for c in cnts)
     val = hyp / t_tot
-    ref_src = reference_sources_leg(P, x1, x2, opts, me, threads, stats, cnts)
+    try:
+        ref_src = reference_sources_leg(P, x1, x2, opts, me, threads, stats, cnts)
+    except Exception as e:  # informational leg only: never let it take the arm's line down
+        ref_src = {"unavailable": f"{type(e).__name__}: {e}"}
     line = {
         "impl": "reference", "metric": "RANSAC hypotheses/sec (5pt E, 10k corrs)", "value": val, "unit": "hypotheses/s",
         "scored_corrs_per_s": cor / t_tot, "samples_per_s": smp / t_tot, "n_gpus": args.gpus, "steps": args.steps,

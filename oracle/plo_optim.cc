@@ -119,7 +119,7 @@ BundleStats lm_impl(Problem &problem, Model *parameters, const BundleOptions &op
     stats.lambda = opt.initial_lambda;
     stats.nu = 2.0;
     bool recompute_jac = true;
-    double sol[8];
+    double sol[8] = {0};
     for (stats.iterations = 0; stats.iterations < opt.max_iterations; ++stats.iterations) {
         if (recompute_jac) {
             acc.reset_jacobian();
