@@ -479,6 +479,52 @@ struct MonoTables {
 };
 const MonoTables MT;
 
+// ---- optional "reference operation order" (test hook, off by default) ------------------------------------------
+// By default the 5- and 7-point solvers restate the reference's GENERATED polynomial expansions structurally (the code
+// below), which is algebraically identical but adds the terms up in a different order.  tests/test_ref_sources.py
+// switches this mode on to prove that the order is the ONLY difference to the reference's sources:
+//   * o1 / o1p / o1m / o2 / o2p (relpose_5pt.cc:13-99): every output monomial is the sum of its products in ascending
+//     index of the first factor, formed FIRST and then assigned / added / subtracted (a rule, implemented below);
+//   * the cubic of relpose_7pt.cc:22-37: terms in lexicographic order of (entry, basis) triples (a rule, below);
+//   * the degree-10 determinant of relpose_5pt.cc:191-352: the term order of that computer-algebra output follows no
+//     simple rule; the test parses it from the reference's source file at run time and injects it
+//     (plo_set_reference_order) — nothing of it is stored in this repository.  The injected table is checked against the
+//     mathematically complete term set before it is accepted.
+struct DetTerm { int sign, r[3], c[3]; };
+struct RefOrder {
+    bool enabled = false;
+    std::vector<DetTerm> det[11];
+};
+RefOrder g_ref_order;
+
+struct OrderedTables { // products contributing to each output monomial, ascending in the first factor's index
+    std::vector<std::pair<int, int>> quad[10], cub[20];
+    OrderedTables() {
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) quad[MT.quad[i][j]].push_back({i, j});
+        for (int q = 0; q < 10; ++q)
+            for (int l = 0; l < 4; ++l) cub[MT.cub[q][l]].push_back({q, l});
+    }
+};
+const OrderedTables OT;
+// mode: 0 assign, +1 add, -1 subtract the per-monomial sum
+inline void lin_mul_ref(const double a[4], const double b[4], double c[10], int mode) {
+    for (int m = 0; m < 10; ++m) {
+        const auto &t = OT.quad[m];
+        double s = a[t[0].first] * b[t[0].second];
+        for (size_t k = 1; k < t.size(); ++k) s = s + a[t[k].first] * b[t[k].second];
+        c[m] = mode == 0 ? s : (mode > 0 ? c[m] + s : c[m] - s);
+    }
+}
+inline void quad_mul_ref(const double a[10], const double b[4], double c[20], int mode) {
+    for (int m = 0; m < 20; ++m) {
+        const auto &t = OT.cub[m];
+        double s = a[t[0].first] * b[t[0].second];
+        for (size_t k = 1; k < t.size(); ++k) s = s + a[t[k].first] * b[t[k].second];
+        c[m] = mode == 0 ? s : c[m] + s;
+    }
+}
+
 // c (+)= sgn * a*b for linear a,b -> quadratic c      (o1/o1p/o1m, relpose_5pt.cc:13-48)
 inline void lin_mul_acc(const double a[4], const double b[4], double c[10], double sgn) {
     for (int i = 0; i < 4; ++i)
@@ -491,7 +537,45 @@ inline void quad_mul_acc(const double a[10], const double b[4], double c[20]) {
 }
 
 // relpose_5pt.cc:101-157.  Nb[k][r] = coefficient of basis matrix r (x,y,z,1) in entry k (col-major) of E.
+void compute_trace_constraints_ref_order(const double Nb[9][4], double coeffs[10][20]) {
+    auto EE = [&](int i, int j) -> const double * { return Nb[3 * j + i]; };
+    double d[10];
+    double *row = coeffs[9]; // determinant constraint (:113-125)
+    lin_mul_ref(EE(0, 1), EE(1, 2), d, 0);
+    lin_mul_ref(EE(0, 2), EE(1, 1), d, -1);
+    quad_mul_ref(d, EE(2, 0), row, 0);
+    lin_mul_ref(EE(0, 2), EE(1, 0), d, 0);
+    lin_mul_ref(EE(0, 0), EE(1, 2), d, -1);
+    quad_mul_ref(d, EE(2, 1), row, 1);
+    lin_mul_ref(EE(0, 0), EE(1, 1), d, 0);
+    lin_mul_ref(EE(0, 1), EE(1, 0), d, -1);
+    quad_mul_ref(d, EE(2, 2), row, 1);
+    double EET[3][3][10]; // (:129-136)
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j) {
+            lin_mul_ref(EE(i, 0), EE(j, 0), EET[i][j], 0);
+            lin_mul_ref(EE(i, 1), EE(j, 1), EET[i][j], 1);
+            lin_mul_ref(EE(i, 2), EE(j, 2), EET[i][j], 1);
+        }
+    for (int m = 0; m < 10; ++m) { // (:139-144)
+        const double t = 0.5 * (EET[0][0][m] + EET[1][1][m] + EET[2][2][m]);
+        EET[0][0][m] -= t;
+        EET[1][1][m] -= t;
+        EET[2][2][m] -= t;
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < i; ++j) std::copy(EET[j][i], EET[j][i] + 10, EET[i][j]);
+    int cnt = 0; // (:146-154)
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double *r = coeffs[cnt++];
+            quad_mul_ref(EET[i][0], EE(0, j), r, 0);
+            quad_mul_ref(EET[i][1], EE(1, j), r, 1);
+            quad_mul_ref(EET[i][2], EE(2, j), r, 1);
+        }
+}
 void compute_trace_constraints(const double Nb[9][4], double coeffs[10][20]) {
+    if (g_ref_order.enabled) return compute_trace_constraints_ref_order(Nb, coeffs);
     auto EE = [&](int i, int j) -> const double * { return Nb[3 * j + i]; };
     // determinant constraint -> row 9 (:113-125): cofactor expansion along the last row of E
     {
@@ -593,7 +677,19 @@ int relpose_5pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::v
         for (int k = 0; k <= 4; ++k) p[i][2][k] = A[i][12 - k];
     }
     double c[11];
-    {
+    if (g_ref_order.enabled) { // injected term order of the reference's expansion (see RefOrder above)
+        for (int k = 0; k <= 10; ++k) {
+            double acc = 0.0;
+            bool first = true;
+            for (const DetTerm &t : g_ref_order.det[k]) {
+                const double v = A[t.r[0]][t.c[0]] * A[t.r[1]][t.c[1]] * A[t.r[2]][t.c[2]];
+                if (first) acc = t.sign > 0 ? v : -v;
+                else acc = t.sign > 0 ? acc + v : acc - v;
+                first = false;
+            }
+            c[k] = acc;
+        }
+    } else {
         double m1[8], m2[8], minor[8], term[11];
         for (int k = 0; k <= 10; ++k) c[k] = 0.0;
         // + p00 * (p11*p22 - p12*p21)
@@ -672,10 +768,42 @@ int relpose_7pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::v
         return col0[0] * (col1[1] * col2[2] - col1[2] * col2[1]) - col1[0] * (col0[1] * col2[2] - col0[2] * col2[1]) +
                col2[0] * (col0[1] * col1[2] - col0[2] * col1[1]);
     };
-    const double c3 = det_cols(n0, n0, n0);
-    const double c2 = det_cols(n1, n0, n0) + det_cols(n0, n1, n0) + det_cols(n0, n0, n1);
-    const double c1 = det_cols(n0, n1, n1) + det_cols(n1, n0, n1) + det_cols(n1, n1, n0);
-    const double c0 = det_cols(n1, n1, n1);
+    double c3 = det_cols(n0, n0, n0);
+    double c2 = det_cols(n1, n0, n0) + det_cols(n0, n1, n0) + det_cols(n0, n0, n1);
+    double c1 = det_cols(n0, n1, n1) + det_cols(n1, n0, n1) + det_cols(n1, n1, n0);
+    double c0 = det_cols(n1, n1, n1);
+    if (g_ref_order.enabled) {
+        // relpose_7pt.cc:22-37 as a rule: the six Leibniz products of det(x F0 + F1) over column-major entries
+        // (0,4,8)+ (0,5,7)- (1,3,8)- (1,5,6)+ (2,3,7)+ (2,4,6)-, each expanded over the basis choice (0 = F0, 1 = F1) of its
+        // three factors; the coefficient of x^(3-p) collects the expansions with p factors from F1, ordered
+        // lexicographically by (entry, basis, entry, basis, entry, basis), products and sums left to right.
+        static const int T[6][4] = {{0, 4, 8, +1}, {0, 5, 7, -1}, {1, 3, 8, -1}, {1, 5, 6, +1}, {2, 3, 7, +1}, {2, 4, 6, -1}};
+        struct Tm { int key[6]; int sign; };
+        double cc[4];
+        for (int pcount = 0; pcount <= 3; ++pcount) {
+            std::vector<Tm> terms;
+            for (int t = 0; t < 6; ++t)
+                for (int mask = 0; mask < 8; ++mask) {
+                    const int b0 = (mask >> 2) & 1, b1 = (mask >> 1) & 1, b2 = mask & 1;
+                    if (b0 + b1 + b2 != pcount) continue;
+                    terms.push_back({{T[t][0], b0, T[t][1], b1, T[t][2], b2}, T[t][3]});
+                }
+            std::sort(terms.begin(), terms.end(), [](const Tm &a, const Tm &b) {
+                return std::lexicographical_compare(a.key, a.key + 6, b.key, b.key + 6);
+            });
+            double acc = 0.0;
+            bool first = true;
+            for (const Tm &t : terms) {
+                auto N = [&](int e, int b) { return b ? n1[e] : n0[e]; };
+                const double v = N(t.key[0], t.key[1]) * N(t.key[2], t.key[3]) * N(t.key[4], t.key[5]);
+                if (first) acc = t.sign > 0 ? v : -v;
+                else acc = t.sign > 0 ? acc + v : acc - v;
+                first = false;
+            }
+            cc[pcount] = acc;
+        }
+        c3 = cc[0]; c2 = cc[1]; c1 = cc[2]; c0 = cc[3];
+    }
     double roots[3];
     int n_roots;
     if (std::abs(c3) < 1e-14) { // :42-44
@@ -775,6 +903,53 @@ int homography_4pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, Mat
 // test hooks for the two scalar helpers of p3p (anonymous namespace above), compared with the reference's
 // p3p_common.h through oracle/_ref (tests/test_ref_pins.py)
 extern "C" {
+// Test hook (tests/test_ref_sources.py): switch the 5- / 7-point solvers to the reference's operation order.  `terms`
+// holds n rows {k, sign, r0, c0, r1, c1, r2, c2}: coefficient c[k] of the 5-point determinant polynomial is the running
+// sum, in row order, of sign * A(r0,c0) * A(r1,c1) * A(r2,c2) (relpose_5pt.cc:191-352, parsed by the test from the
+// reference's source at run time).  The table is accepted only if, for every k, it is exactly the complete term set of
+// det [p_i0 p_i1 p_i2] (as a signed multiset).  Returns 0 on success; enable = 0 restores the default order.
+int plo_set_reference_order(int enable, const int32_t *terms, int n) {
+    plo::g_ref_order.enabled = false;
+    for (int k = 0; k <= 10; ++k) plo::g_ref_order.det[k].clear();
+    if (!enable) return 0;
+    auto deg = [](int c) { return c < 4 ? 3 - c : (c < 8 ? 7 - c : 12 - c); };
+    auto blk = [](int c) { return c < 4 ? 0 : (c < 8 ? 1 : 2); };
+    std::vector<std::array<int, 7>> got[11], want[11]; // canonical: (c of row 0, c of row 1, c of row 2), sign
+    for (int t = 0; t < n; ++t) {
+        const int32_t *q = terms + 8 * t;
+        const int k = q[0], sign = q[1];
+        if (k < 0 || k > 10 || (sign != 1 && sign != -1)) return 1;
+        plo::DetTerm d;
+        d.sign = sign;
+        int col_of_row[3] = {-1, -1, -1};
+        for (int f = 0; f < 3; ++f) {
+            d.r[f] = q[2 + 2 * f];
+            d.c[f] = q[3 + 2 * f];
+            if (d.r[f] < 0 || d.r[f] > 2 || d.c[f] < 0 || d.c[f] > 12 || col_of_row[d.r[f]] >= 0) return 2;
+            col_of_row[d.r[f]] = d.c[f];
+        }
+        if (deg(d.c[0]) + deg(d.c[1]) + deg(d.c[2]) != k) return 3;
+        got[k].push_back({col_of_row[0], col_of_row[1], col_of_row[2], sign, 0, 0, 0});
+        plo::g_ref_order.det[k].push_back(d);
+    }
+    static const int perm[6][4] = {{0, 1, 2, +1}, {0, 2, 1, -1}, {1, 0, 2, -1}, {1, 2, 0, +1}, {2, 0, 1, +1}, {2, 1, 0, -1}};
+    for (int pi = 0; pi < 6; ++pi) // row i takes its entry from column block perm[pi][i]
+        for (int c0 = 0; c0 < 13; ++c0)
+            for (int c1 = 0; c1 < 13; ++c1)
+                for (int c2 = 0; c2 < 13; ++c2)
+                    if (blk(c0) == perm[pi][0] && blk(c1) == perm[pi][1] && blk(c2) == perm[pi][2])
+                        want[deg(c0) + deg(c1) + deg(c2)].push_back({c0, c1, c2, perm[pi][3], 0, 0, 0});
+    for (int k = 0; k <= 10; ++k) {
+        std::sort(got[k].begin(), got[k].end());
+        std::sort(want[k].begin(), want[k].end());
+        if (got[k] != want[k]) {
+            for (int j = 0; j <= 10; ++j) plo::g_ref_order.det[j].clear();
+            return 4;
+        }
+    }
+    plo::g_ref_order.enabled = true;
+    return 0;
+}
 int plo_p3p_root2real(double b, double c, double *r) { return plo::root2real(b, c, r[0], r[1]) ? 1 : 0; }
 void plo_p3p_refine_lambda(double *l, double a12, double a13, double a23, double b12, double b13, double b23) {
     plo::refine_lambda(l[0], l[1], l[2], a12, a13, a23, b12, b13, b23);

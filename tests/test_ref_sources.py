@@ -19,6 +19,9 @@ Result of the comparison (asserted below):
     solution count, solutions equal up to the conditioning of the minimal problem (median 1e-15, worst 1e-7 over
     the sample).  End to end, ransac_relpose / ransac_fundamental / estimate_* return the same iteration count,
     refinement count, inlier count and inlier mask; the model agrees to 1e-9 and the MSAC score to 1e-12 relative.
+    Switched to the reference's operation order (test hook plo_set_reference_order; the 480-term determinant order is
+    parsed from the reference's source at run time, nothing of it is stored here) the oracle is BIT-IDENTICAL to the
+    reference's sources on the whole path, degenerate inputs included (last four tests of this file).
   * FixCameraRelativePoseRefiner (tangent Sampson): the oracle models Vector4d::norm() with the SSE2 packet order
     (a0²+a2²)+(a1²+a3²) in that one place; mini-Eigen sums left to right.  Agreement 1e-9.
 """
@@ -289,3 +292,121 @@ def test_outcome_does_not_depend_on_eigens_summation_order():
             d = min(d, np.abs(am + bm).max())
         worst_model.append(d / np.abs(am).max())
     assert max(worst_model) < 1e-5 and np.median(worst_model) < 1e-12 and sorted(worst_model)[-2] < 1e-9
+
+
+# ---- the operation order of the generated expansions is the ONLY difference ---------------------------------------
+REF_5PT = "/root/reference/PoseLib/solvers/relpose_5pt.cc"
+
+
+def _parse_reference_det_terms():
+    """The term order of the degree-10 determinant expansion (relpose_5pt.cc:191-352), read from the reference's source at
+    run time: rows (k, sign, r0, c0, r1, c1, r2, c2).  Nothing of it is stored in this repository."""
+    import re
+    src = open(REF_5PT).read()
+    i = src.index("double c[11];")
+    j = src.index("bisect_sturm", i)
+    rows = []
+    for m in re.finditer(r"c\[(\d+)\]\s*=\s*(.*?);", src[i:j], re.S):
+        k, expr = int(m.group(1)), re.sub(r"\s+", " ", m.group(2))
+        for sg, t in re.findall(r"([+-]?)\s*(A\(\d+, \d+\) \* A\(\d+, \d+\) \* A\(\d+, \d+\))", expr):
+            f = [int(v) for ab in re.findall(r"A\((\d+), (\d+)\)", t) for v in ab]
+            rows.append([k, -1 if sg == "-" else 1] + f)
+    return rows
+
+
+@pytest.fixture
+def reference_order():
+    import os
+    if not os.path.exists(REF_5PT):
+        pytest.skip("needs the reference's source file to read the term order from")
+    P.set_reference_order(True, _parse_reference_det_terms())
+    try:
+        yield
+    finally:
+        P.set_reference_order(False)
+
+
+def test_incomplete_order_tables_are_rejected():
+    import os
+    if not os.path.exists(REF_5PT):
+        pytest.skip("needs the reference's source file")
+    rows = _parse_reference_det_terms()
+    assert len(rows) == 480
+    try:
+        with pytest.raises(ValueError):
+            P.set_reference_order(True, rows[:-1])  # one term missing
+        bad = [r[:] for r in rows]
+        bad[7][1] = -bad[7][1]  # one sign flipped
+        with pytest.raises(ValueError):
+            P.set_reference_order(True, bad)
+    finally:
+        P.set_reference_order(False)
+
+
+def test_with_the_reference_operation_order_the_solvers_are_bit_identical(reference_order):
+    """relpose_5pt (trace constraints by rule, determinant expansion in the injected order) and relpose_7pt (cubic by
+    rule) — the two places where the oracle's default order differs — equal the reference's sources bit for bit."""
+    for s in range(300):
+        x1, x2, _, _ = G.minimal_relpose(s, 5)
+        a, b = both(lambda: P.relpose_5pt_E(x1, x2))
+        assert a.shape == b.shape and np.array_equal(a, b), s
+        a, b = both(lambda: P.relpose_5pt(x1, x2))
+        assert a.shape == b.shape and np.array_equal(a, b), s
+        x1, x2, _, _ = G.minimal_relpose(s, 7)
+        a, b = both(lambda: P.relpose_7pt(x1, x2))
+        assert a.shape == b.shape and np.array_equal(a, b), s
+
+
+def test_with_the_reference_operation_order_the_whole_path_is_bit_identical(reference_order):
+    """estimate_* for all four kinds on 240 random problems — sizes 8..800, inlier ratios 0.1..1, all four losses, PROSAC
+    on/off, and DEGENERATE data (identical views + noise, duplicated points, pure zoom, planar 3D points, collinear image
+    points) where the default order's last-bit differences decide ties: stats, masks, scores and models all identical."""
+    rng = np.random.default_rng(123)
+    for it in range(240):
+        kind = ["relpose", "fundamental", "homography", "pnp"][it % 4]
+        n = int(rng.choice([8, 15, 40, 100, 300, 800]))
+        ratio = float(rng.choice([0.1, 0.3, 0.6, 0.9, 1.0]))
+        mode = int(rng.integers(0, 5))
+        if kind == "pnp":
+            p = G.abspose_problem(n, ratio, 1, it)
+            a1, a2, thr, kw = p["x"].copy(), p["X"].copy(), float(rng.choice([2.0, 12.0])), dict(cam1=CAMT)
+            if mode == 1:
+                a2[:, 2] = a2[:, 2].mean()
+            if mode == 2:
+                a1[:n // 2], a2[:n // 2] = a1[0], a2[0]
+        elif kind == "homography":
+            p = G.homography_problem(n, ratio, 4, it)
+            a1, a2, thr, kw = p["x1"].copy(), p["x2"].copy(), float(rng.choice([0.5, 3.0])), {}
+            if mode == 2:
+                a1[:n // 2], a2[:n // 2] = a1[0], a2[0]
+            if mode == 3:
+                a1[:, 1] = a1[:, 0] * 0.5 + 3
+        else:
+            p = G.relpose_problem(n, ratio, 2, it)
+            a1, a2, thr = p["x1"].copy(), p["x2"].copy(), float(rng.choice([0.5, 3.0]))
+            kw = dict(cam1=CAMT, cam2=CAMT) if kind == "relpose" else {}
+            if mode == 1:
+                a2 = a1 + rng.normal(0, 0.3, a1.shape)
+            if mode == 2:
+                a1[:n // 2], a2[:n // 2] = a1[0], a2[0]
+            if mode == 3:
+                a2 = a1 * 1.1
+        ro = P.RansacOpt(max_iterations=int(rng.choice([50, 500, 3000])), min_iterations=int(rng.choice([10, 100])),
+                         seed=int(rng.integers(0, 1 << 30)), progressive_sampling=bool(rng.integers(0, 2)))
+        bo = P.BundleOpt(loss_type=str(rng.choice(["TRIVIAL", "TRUNCATED", "HUBER", "CAUCHY"])))
+        a, b = both(lambda: P.estimate(kind, a1, a2, ro, bo, thr, **kw))
+        assert a["stats"] == b["stats"], (it, kind, n, ratio, mode, a["stats"], b["stats"])
+        assert np.array_equal(a["inliers"], b["inliers"]), (it, kind)
+        assert np.array_equal(a["model"], b["model"], equal_nan=True), (it, kind)
+
+
+def test_with_the_reference_operation_order_the_fixture_cases_are_bit_identical(reference_order):
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import reference_cases as RC
+    for name in sorted(RC.CASES):
+        case = RC.CASES[name]()
+        a, b = both(lambda: RC.run(P, case))
+        assert a["stats"] == b["stats"] and np.array_equal(a["inliers"], b["inliers"]), name
+        assert np.array_equal(a["model"], b["model"]), name
