@@ -7,6 +7,8 @@
 #include <vector>
 
 namespace plo {
+// test hook state (plo_set_reference_order, plo_solvers.cc): true while the reference's operation order is switched on
+bool reference_order_enabled();
 
 // ---- PoseLib/types.h:39-58 -------------------------------------------------------------------
 struct RansacOptions {

@@ -383,8 +383,11 @@ struct FixCameraRelativePoseRefiner {
             const Mat32 &m1 = M1[k], &m2 = M2[k];
             double C, JC[4];
             tangent_terms(E, a, b, m1, m2, C, JC);
-            // Vector4d::norm(): packet-of-2 reduction order (SSE2 build)
-            const double nJ_C = std::sqrt((JC[0] * JC[0] + JC[2] * JC[2]) + (JC[1] * JC[1] + JC[3] * JC[3]));
+            // Vector4d::norm(): packet-of-2 reduction order (SSE2 build) — the one place where this restatement leaves
+            // its own left-to-right convention; the reference-order test hook uses the convention
+            const double nJ_C = reference_order_enabled()
+                                    ? std::sqrt(((JC[0] * JC[0] + JC[1] * JC[1]) + JC[2] * JC[2]) + JC[3] * JC[3])
+                                    : std::sqrt((JC[0] * JC[0] + JC[2] * JC[2]) + (JC[1] * JC[1] + JC[3] * JC[3]));
             const double inv_nJ_C = 1.0 / nJ_C;
             const double r = C * inv_nJ_C;
             double dF[9];

@@ -900,6 +900,10 @@ int homography_4pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, Mat
 
 } // namespace plo
 
+namespace plo {
+bool reference_order_enabled() { return g_ref_order.enabled; }
+} // namespace plo
+
 // test hooks for the two scalar helpers of p3p (anonymous namespace above), compared with the reference's
 // p3p_common.h through oracle/_ref (tests/test_ref_pins.py)
 extern "C" {

@@ -410,3 +410,26 @@ def test_with_the_reference_operation_order_the_fixture_cases_are_bit_identical(
         a, b = both(lambda: RC.run(P, case))
         assert a["stats"] == b["stats"] and np.array_equal(a["inliers"], b["inliers"]), name
         assert np.array_equal(a["model"], b["model"]), name
+
+
+def test_with_the_reference_operation_order_the_tangent_sampson_path_is_bit_identical(reference_order):
+    """Distorted cameras: ransac_relpose(cameras), the tangent-Sampson refiner (Vector4d::norm() left to right, the oracle's
+    own convention, instead of the packet order it models by default in that one place) and estimate_relative_pose with
+    and without tangent_sampson."""
+    for cam, seed in ((CAMERAS[3], 5), (CAMERAS[4], 6), (CAMERAS[2], 7)):
+        p = G.relpose_problem(1200, 0.5, 2, seed)
+        X1 = np.c_[p["x1"] / G.FOCAL, np.ones(len(p["x1"]))]
+        X2 = np.c_[p["x2"] / G.FOCAL, np.ones(len(p["x2"]))]
+        d1, d2 = P.camera_project_with_jac(cam, X1)[2], P.camera_project_with_jac(cam, X2)[2]
+        ro = P.RansacOpt(max_iterations=1000, min_iterations=100, seed=seed)
+        a, b = both(lambda: P.ransac_relpose_cameras(d1, d2, cam, cam, ro, 1.5))
+        assert same(a, b)
+        u1, M1 = P.camera_unproject_with_jac(cam, d1)
+        u2, M2 = P.camera_unproject_with_jac(cam, d2)
+        pert = a["model"].copy()
+        pert[4:] += 0.01
+        for loss in ("TRIVIAL", "TRUNCATED", "HUBER", "CAUCHY"):
+            bo = P.BundleOpt(loss_type=loss, loss_scale=1.0)
+            assert same(*both(lambda: P.refine_relpose_tangent(pert, u1, u2, M1, M2, bo))), loss
+        for ts in (False, True):
+            assert same(*both(lambda: P.estimate("relpose", d1, d2, ro, P.BundleOpt(), 1.5, cam, cam, tangent_sampson=ts)))
