@@ -99,6 +99,30 @@ def _bundle(d):
     return kw
 
 
+def RansacOptions(opt=None):
+    """poselib.RansacOptions(opt={}) (pybind/bindings/types.cc:14-20,168): the defaults of PoseLib/types.h:39-50 with the
+    given keys overwritten, as a dict with the keys of write_to_dict (helpers.h:175-183)."""
+    out = {"max_iterations": 100000, "min_iterations": 1000, "dyn_num_trials_mult": 3.0, "success_prob": 0.9999,
+           "seed": 0, "progressive_sampling": False, "max_prosac_iterations": 100000}
+    out.update(_ransac(opt or {}))
+    return out
+
+
+def BundleOptions(opt=None):
+    """poselib.BundleOptions(opt={}) (types.cc:22-28,169): defaults of PoseLib/types.h:60-95, keys of helpers.h:185-235.
+    Values the B200 path does not implement (FIXED_FACTOR, MARQUARDT, TRUNCATED_CAUCHY / TRUNCATED_LE_ZACH) raise NYI."""
+    opt = dict(opt or {})
+    out = {"max_iterations": 100, "loss_scale": 1.0, "loss_type": "CAUCHY", "gradient_tol": 1e-12, "step_tol": 1e-8,
+           "relative_cost_tol": 1e-10, "initial_lambda": 1e-3, "min_lambda": 1e-10, "max_lambda": 1e10,
+           "lambda_factor": 10.0, "verbose": False, "lambda_update": "NIELSEN", "damping": "LEVENBERG"}
+    out.update(_bundle(opt))
+    if "lambda_factor" in opt:
+        out["lambda_factor"] = float(opt["lambda_factor"])
+    if "verbose" in opt:
+        out["verbose"] = _truthy(opt["verbose"])
+    return out
+
+
 def _info(r):
     """write_to_dict(RansacStats) + inliers as a list of bool (helpers.h:237-253,266-272)."""
     out = dict(r["stats"])

@@ -25,6 +25,28 @@ def test_option_dicts_follow_the_pybind_helpers():
     assert c.model_id == 4 and list(c.params) == [900.0, 901.0, 3.0, 4.0, 0.1, -0.2, 1e-3, 2e-3]
 
 
+def test_option_factories_return_the_pybind_defaults():
+    from poselib_b200 import cabi, pyapi
+    r = pyapi.RansacOptions()
+    assert r == {"max_iterations": 100000, "min_iterations": 1000, "dyn_num_trials_mult": 3.0, "success_prob": 0.9999,
+                 "seed": 0, "progressive_sampling": False, "max_prosac_iterations": 100000}  # types.h:39-50
+    assert pyapi.RansacOptions({"seed": 9, "progressive_sampling": True})["seed"] == 9
+    b = pyapi.BundleOptions({"loss_type": "huber", "loss_scale": 0.5})
+    assert (b["loss_type"], b["loss_scale"], b["max_iterations"], b["lambda_update"], b["damping"]) == ("HUBER", 0.5, 100, "NIELSEN", "LEVENBERG")
+    assert sorted(b) == sorted(["max_iterations", "loss_scale", "loss_type", "gradient_tol", "step_tol", "relative_cost_tol",
+                                "initial_lambda", "min_lambda", "max_lambda", "lambda_factor", "verbose", "lambda_update",
+                                "damping"])  # helpers.h:185-235
+    with pytest.raises(cabi.PoseLibB200Error):
+        pyapi.BundleOptions({"damping": "MARQUARDT"})
+    # the defaults are the ones the C-ABI structs carry
+    ro, bo = cabi.RansacOpt(), cabi.BundleOpt()
+    for k in ("max_iterations", "min_iterations", "dyn_num_trials_mult", "success_prob", "seed", "max_prosac_iterations"):
+        assert getattr(ro, k) == r[k], k
+    for k in ("max_iterations", "loss_scale", "gradient_tol", "step_tol", "relative_cost_tol", "initial_lambda", "min_lambda",
+              "max_lambda"):
+        assert getattr(bo, k) == pyapi.BundleOptions()[k], k
+
+
 @pytest.mark.gpu
 def test_pyapi_matches_oracle_through_the_poselib_call_surface():
     from poselib_b200 import pyapi as poselib
