@@ -83,6 +83,9 @@ int relpose_5pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::v
 int relpose_5pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::vector<CameraPose> *out);
 int relpose_7pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::vector<Mat3> *F);
 int homography_4pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, Mat3 *H, bool check_cheirality = true);
+// solvers/relpose_8pt.cc:52-95: non-minimal essential matrix from n >= 8 bearing pairs
+void essential_matrix_8pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, Mat3 *E);
+int relpose_8pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::vector<CameraPose> *output);
 
 // ---- robust/utils.cc -------------------------------------------------------------------------
 double compute_msac_score(const CameraPose &pose, const std::vector<Vec2> &x, const std::vector<Vec3> &X,

@@ -165,6 +165,17 @@ int plo_homography_4pt(const double *x1, const double *x2, double *H_out, int ch
     mat_out(H, H_out);
     return n;
 }
+void plo_essential_matrix_8pt(const double *x1, const double *x2, uint64_t n, double *E_out) {
+    Mat3 E;
+    essential_matrix_8pt(v3(x1, n), v3(x2, n), &E);
+    mat_out(E, E_out);
+}
+int plo_relpose_8pt(const double *x1, const double *x2, uint64_t n, double *poses_out) {
+    std::vector<CameraPose> out;
+    const int c = relpose_8pt(v3(x1, n), v3(x2, n), &out);
+    for (size_t k = 0; k < out.size(); ++k) pose_out(out[k], poses_out + 7 * k);
+    return c;
+}
 int plo_bisect_sturm10(const double *c11, double *roots) { return bisect_sturm10(c11, roots); }
 int plo_solve_quadratic_real(double a, double b, double c, double *roots) { return solve_quadratic_real(a, b, c, roots); }
 int plo_solve_cubic_single_real(double c2, double c1, double c0, double *root) {

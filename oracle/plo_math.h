@@ -302,6 +302,107 @@ template <int ROWS, int COLS> inline void full_piv_householder_q(double *a, doub
     }
 }
 
+// householderQr().householderQ() for a ROWS x COLS matrix (ROWS >= COLS, column-major a[c*ROWS+r], destroyed): the same
+// reflectors as above without any pivoting (Eigen's HouseholderQR, unblocked for these sizes).  Q is ROWS x ROWS,
+// column-major.  relpose_8pt.cc:65 takes its last column as the nullspace of the 8 x 9 epipolar system.
+template <int ROWS, int COLS> inline void householder_q(double *a, double *Q) {
+    constexpr int size = (ROWS < COLS) ? ROWS : COLS;
+    double hcoeffs[size];
+    auto A = [&](int r, int c) -> double & { return a[c * ROWS + r]; };
+    for (int k = 0; k < size; ++k) {
+        double tail_sq = 0.0;
+        for (int r = k + 1; r < ROWS; ++r) tail_sq += A(r, k) * A(r, k);
+        const double c0 = A(k, k);
+        double tau, beta;
+        if (tail_sq <= std::numeric_limits<double>::min()) {
+            tau = 0.0;
+            beta = c0;
+            for (int r = k + 1; r < ROWS; ++r) A(r, k) = 0.0;
+        } else {
+            beta = std::sqrt(c0 * c0 + tail_sq);
+            if (c0 >= 0) beta = -beta;
+            for (int r = k + 1; r < ROWS; ++r) A(r, k) = A(r, k) / (c0 - beta);
+            tau = (beta - c0) / beta;
+        }
+        hcoeffs[k] = tau;
+        A(k, k) = beta;
+        if (tau != 0.0) {
+            for (int c = k + 1; c < COLS; ++c) {
+                double tmp = 0.0;
+                for (int r = k + 1; r < ROWS; ++r) tmp += A(r, k) * A(r, c);
+                tmp += A(k, c);
+                A(k, c) -= tau * tmp;
+                for (int r = k + 1; r < ROWS; ++r) A(r, c) -= tau * A(r, k) * tmp;
+            }
+        }
+    }
+    for (int c = 0; c < ROWS; ++c)
+        for (int r = 0; r < ROWS; ++r) Q[c * ROWS + r] = (r == c) ? 1.0 : 0.0;
+    auto QQ = [&](int r, int c) -> double & { return Q[c * ROWS + r]; };
+    for (int k = size - 1; k >= 0; --k) {
+        const double tau = hcoeffs[k];
+        if (tau == 0.0) continue;
+        for (int c = k; c < ROWS; ++c) {
+            double tmp = 0.0;
+            for (int r = k + 1; r < ROWS; ++r) tmp += A(r, k) * QQ(r, c);
+            tmp += QQ(k, c);
+            QQ(k, c) -= tau * tmp;
+            for (int r = k + 1; r < ROWS; ++r) QQ(r, c) -= tau * A(r, k) * tmp;
+        }
+    }
+}
+
+// SelfAdjointEigenSolver<Matrix<double,N,N>>: eigenvalues ascending, eigenvectors as columns (column-major V[c*N+r]).
+// Eigen tridiagonalises and runs implicit QL; this restatement is a cyclic Jacobi iteration — same eigenpairs up to the
+// sign of each vector and to roundoff (an iterative method cannot be restated bit for bit; tolerance parity only).
+// Only the lower triangle of the row-major input is read.
+template <int N> inline void sym_eigen_jacobi(const double *Ain, double *evals, double *V) {
+    double A[N][N];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) A[i][j] = (j <= i) ? Ain[i * N + j] : Ain[j * N + i];
+    for (int c = 0; c < N; ++c)
+        for (int r = 0; r < N; ++r) V[c * N + r] = (r == c) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < N; ++i) {
+            diag += A[i][i] * A[i][i];
+            for (int j = i + 1; j < N; ++j) off += A[i][j] * A[i][j];
+        }
+        if (off <= 1e-32 * diag || off == 0.0) break;
+        for (int p = 0; p < N - 1; ++p)
+            for (int q = p + 1; q < N; ++q) {
+                if (A[p][q] == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = ((theta >= 0) ? 1.0 : -1.0) / (std::abs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < N; ++k) { // A <- A J
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - sn * akq;
+                    A[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < N; ++k) { // A <- J^T A
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - sn * aqk;
+                    A[q][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < N; ++k) {
+                    const double vkp = V[p * N + k], vkq = V[q * N + k];
+                    V[p * N + k] = c * vkp - sn * vkq;
+                    V[q * N + k] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    int idx[N];
+    for (int i = 0; i < N; ++i) idx[i] = i;
+    std::sort(idx, idx + N, [&](int a, int b) { return A[a][a] < A[b][b]; });
+    double Vs[N * N];
+    for (int c = 0; c < N; ++c) {
+        evals[c] = A[idx[c]][idx[c]];
+        for (int r = 0; r < N; ++r) Vs[c * N + r] = V[idx[c] * N + r];
+    }
+    std::memcpy(V, Vs, sizeof(Vs));
+}
+
 // partialPivLu().solve(B): A is n x n row-major (a[r*lda+c]); B is n x nrhs row-major, overwritten by X.
 inline void partial_piv_lu_solve(int n, double *a, int lda, double *b, int ldb, int nrhs) {
     int piv[32];

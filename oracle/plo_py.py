@@ -166,6 +166,23 @@ def relpose_7pt(x1, x2):
     return out[:n].reshape(n, 3, 3).transpose(0, 2, 1)
 
 
+def essential_matrix_8pt(x1, x2):
+    """solvers/relpose_8pt.cc essential_matrix_8pt: n >= 8 unit bearing pairs -> E[r,c]."""
+    a, ap = _d(x1)
+    b, bp = _d(x2)
+    out = np.zeros(9)
+    lib().plo_essential_matrix_8pt(ap, bp, C.c_uint64(len(a)), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out.reshape(3, 3).T.copy()
+
+
+def relpose_8pt(x1, x2):
+    a, ap = _d(x1)
+    b, bp = _d(x2)
+    out = np.zeros((4, 7))
+    n = lib().plo_relpose_8pt(ap, bp, C.c_uint64(len(a)), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out[:n]
+
+
 def homography_4pt(x1, x2, check_cheirality=True):
     a, ap = _d(x1)
     b, bp = _d(x2)

@@ -830,6 +830,61 @@ int relpose_7pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::v
     return n_roots;
 }
 
+// ============================ solvers/relpose_8pt.cc ==========================================
+// relpose_8pt.cc:52-83.  Row i of the n x 9 system is [x2.x * x1^T, x2.y * x1^T, x2.z * x1^T] (:41-49), i.e. the
+// ROW-major entries of E.  Exactly 8 points: last column of the Householder Q of the transposed system (:63-67);
+// more: eigenvector of the smallest eigenvalue of A^T A (:68-72, an iterative solver in Eigen -> tolerance parity).
+// Then the closest essential matrix in Frobenius norm: singular values (a, b, c) -> ((a+b)/2, (a+b)/2, 0) (:74-81).
+void essential_matrix_8pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, Mat3 *essential_matrix) {
+    const size_t n = x1.size();
+    double e[9];
+    auto row = [&](size_t i, double r[9]) {
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) r[3 * a + b] = x2[i][a] * x1[i][b];
+    };
+    if (n == 8) {
+        double At[9 * 8], Q[81]; // transposed system, 9 x 8 column-major: column i = row i of A
+        for (size_t i = 0; i < 8; ++i) row(i, At + 9 * i);
+        householder_q<9, 8>(At, Q);
+        for (int k = 0; k < 9; ++k) e[k] = Q[8 * 9 + k];
+    } else {
+        double G[81]; // A^T A, row-major; entry (p,q) summed over the correspondences in order
+        std::vector<double> rows(9 * n);
+        for (size_t i = 0; i < n; ++i) row(i, rows.data() + 9 * i);
+        for (int p = 0; p < 9; ++p)
+            for (int q = 0; q < 9; ++q) {
+                double s = 0.0;
+                for (size_t i = 0; i < n; ++i) s = (i == 0) ? rows[9 * i + p] * rows[9 * i + q] : s + rows[9 * i + p] * rows[9 * i + q];
+                G[p * 9 + q] = s;
+            }
+        double evals[9], V[81];
+        sym_eigen_jacobi<9>(G, evals, V);
+        for (int k = 0; k < 9; ++k) e[k] = V[k]; // first column = smallest eigenvalue
+    }
+    Mat3 E;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) E(a, b) = e[3 * a + b]; // Map<const RowMajor 3x3>
+    Mat3 U, V;
+    double d[3];
+    svd3(E, U, d, V);
+    const double m = (d[0] + d[1]) / 2.;
+    Mat3 UD; // U * diag(m, m, 0)
+    for (int r = 0; r < 3; ++r) {
+        UD(r, 0) = U(r, 0) * m;
+        UD(r, 1) = U(r, 1) * m;
+        UD(r, 2) = U(r, 2) * 0.0;
+    }
+    *essential_matrix = UD * transpose(V);
+}
+// relpose_8pt.cc:85-94
+int relpose_8pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::vector<CameraPose> *output) {
+    Mat3 E;
+    essential_matrix_8pt(x1, x2, &E);
+    output->clear();
+    motion_from_essential(E, x1, x2, output);
+    return (int)output->size();
+}
+
 // ============================ solvers/homography_4pt.cc =======================================
 // homography_4pt.cc:36-128 (SKS/ACA closed form, Cai et al. PAMI'25)
 int homography_4pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, Mat3 *H, bool check_cheir) {

@@ -6,7 +6,7 @@
 //   PoseLib/robust/estimators/*.cc             the estimators (sampling, minimal solver calls, scoring, LO refits)
 //   PoseLib/robust/bundle.cc, optim/*.h        the LM refiners, Jacobian accumulators, robust losses
 //   PoseLib/robust/utils.cc                    all scorers and inlier masks
-//   PoseLib/solvers/{p3p,relpose_5pt,relpose_7pt,homography_4pt}.cc, misc/{essential,univariate,camera_models}.cc
+//   PoseLib/solvers/{p3p,relpose_5pt,relpose_7pt,homography_4pt,relpose_8pt}.cc, misc/{essential,univariate,camera_models}.cc
 // WHAT A MATCH PROVES: mini-Eigen implements every Eigen operation with the oracle's restatement of it
 // (oracle/plo_math.h), so `reference sources + mini-Eigen == oracle` checks that the oracle transcribes PoseLib's
 // LOGIC faithfully — every formula, branch, loop, call order and sign convention of the files above — but NOT that the
@@ -23,6 +23,7 @@
 #include "PoseLib/solvers/p3p.h"
 #include "PoseLib/solvers/relpose_5pt.h"
 #include "PoseLib/solvers/relpose_7pt.h"
+#include "PoseLib/solvers/relpose_8pt.h"
 
 #include <cstring>
 
@@ -167,6 +168,17 @@ int plr2_homography_4pt(const double *x1, const double *x2, double *H_out, int c
     const int n = homography_4pt(v3(x1, 4), v3(x2, 4), &H, check_cheirality != 0);
     mat_out(H, H_out);
     return n;
+}
+void plr2_essential_matrix_8pt(const double *x1, const double *x2, uint64_t n, double *E_out) {
+    Eigen::Matrix3d E;
+    essential_matrix_8pt(v3(x1, n), v3(x2, n), &E);
+    mat_out(E, E_out);
+}
+int plr2_relpose_8pt(const double *x1, const double *x2, uint64_t n, double *poses_out) {
+    CameraPoseVector out;
+    const int c = relpose_8pt(v3(x1, n), v3(x2, n), &out);
+    for (size_t k = 0; k < out.size(); ++k) pose_out(out[k], poses_out + 7 * k);
+    return c;
 }
 int plr2_calculate_RFC(const double *F9) { return calculate_RFC(mat_in(F9)) ? 1 : 0; }
 
