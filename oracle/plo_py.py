@@ -695,17 +695,20 @@ class reference_sources:
 
 
 def set_reference_order(enable, det_terms=None):
-    """Test hook: switch the oracle's 5- / 7-point solvers to the reference's operation order.  det_terms: rows
-    (k, sign, r0, c0, r1, c1, r2, c2) of the 5-point determinant expansion in the reference's order (parsed from the
-    reference's source by the caller; nothing of it is stored here).  Raises if the table is not the complete term set."""
+    """Test hook: switch the oracle's 5- / 7-point solvers (and the tangent refiner's norm) to the reference's operation
+    order.  det_terms: rows (k, sign, r0, c0, r1, c1, r2, c2) of the 5-point determinant expansion in the reference's order
+    (parsed from the reference's source by the caller; nothing of it is stored here).  Raises if the table is not the
+    complete term set.  Always addresses the oracle library, also inside `with reference_sources()`."""
+    global _use_ref2
+    saved, _use_ref2 = _use_ref2, None
+    try:
+        oracle = lib()
+    finally:
+        _use_ref2 = saved
     if not enable:
-        C.CDLL(_LIB_PATH).plo_set_reference_order(0, None, 0) if _lib is None else _lib.plo_set_reference_order(0, None, 0)
+        oracle.plo_set_reference_order(0, None, 0)
         return
-    build()
     t = np.ascontiguousarray(det_terms, dtype=np.int32).reshape(-1, 8)
-    real = lib() if not _use_ref2 else None
-    if real is None:
-        raise RuntimeError("set_reference_order configures the oracle, not the reference sources")
-    rc = real.plo_set_reference_order(1, t.ctypes.data_as(C.POINTER(C.c_int32)), len(t))
+    rc = oracle.plo_set_reference_order(1, t.ctypes.data_as(C.POINTER(C.c_int32)), len(t))
     if rc != 0:
         raise ValueError(f"reference-order table rejected (code {rc})")
