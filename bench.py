@@ -132,6 +132,14 @@ def run_reference(args, rank, world):
         cor += sum(c["scored_corrs"] for c in cnts)
         smp += sum(c["samples"] for c in cnts)
     val = hyp / t_tot
+    try:  # the -march=native build of the same port beside the reference-flags build (built on this box)
+        nsec, _, nstats, ncnts = P.ransac_relpose_batch_mt(x1, x2, opts, me, threads, native=True)
+        same = sum(int(a["iterations"] == b["iterations"] and a["num_inliers"] == b["num_inliers"]) for a, b in zip(nstats, stats))
+        native = {"value": sum(c["hypotheses"] for c in ncnts) / nsec, "unit": "hypotheses/s", "cores": threads,
+                  "kind": "port", "flags": "g++ -O3 -march=native -ffp-contract=off",
+                  "same_trajectory_as_reference_flags_build": f"{same}/{len(x1)}"}
+    except Exception as e:
+        native = {"unavailable": f"{type(e).__name__}: {e}"}
     try:
         ref_src = reference_sources_leg(P, x1, x2, opts, me, threads, stats, cnts)
     except Exception as e:  # informational leg only: never let it take the arm's line down
@@ -148,6 +156,7 @@ def run_reference(args, rank, world):
                                    "g++ -O3 -ffp-contract=off"},
         "e2e": {"value": val, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    line["cpu_baseline_native"] = native
     if ref_src:
         line["reference_sources"] = ref_src
     print(json.dumps(line))

@@ -427,7 +427,21 @@ def estimate(kind, a, b, ropt, bopt, max_error, cam1=None, cam2=None, init=None,
     return {"model": model, "inliers": mask, "stats": st.as_dict(), "counters": cn.as_dict()}
 
 
-def ransac_relpose_batch_mt(x1_list, x2_list, ropts, max_errors, threads):
+_native = None
+
+
+def native_lib():
+    """The same oracle built with -march=native for the CPU it is built on (`make -C oracle native`, SURVEY §8d asks for
+    this variant beside the reference-flags build); -ffp-contract=off is kept, so results are identical, only faster."""
+    global _native
+    if _native is None:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "native"])
+        _native = C.CDLL(os.path.join(_HERE, "_build", "libplo_native.so"))
+        _native.plo_ransac_relpose_batch_mt.restype = C.c_double
+    return _native
+
+
+def ransac_relpose_batch_mt(x1_list, x2_list, ropts, max_errors, threads, native=False):
     """Many relpose problems, one problem per thread at a time.  Returns (seconds, poses, stats, counters)."""
     count = len(x1_list)
     off = np.zeros(count + 1, dtype=np.uint64)
@@ -440,7 +454,7 @@ def ransac_relpose_batch_mt(x1_list, x2_list, ropts, max_errors, threads):
     poses[:, 0] = 1
     stats = (RansacStats * count)()
     cnts = (Counters * count)()
-    sec = lib().plo_ransac_relpose_batch_mt(
+    sec = (native_lib() if native else lib()).plo_ransac_relpose_batch_mt(
         x1.ctypes.data_as(C.POINTER(C.c_double)), x2.ctypes.data_as(C.POINTER(C.c_double)),
         off.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint64(count), opts,
         me.ctypes.data_as(C.POINTER(C.c_double)), int(threads), poses.ctypes.data_as(C.POINTER(C.c_double)),

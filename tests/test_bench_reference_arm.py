@@ -18,6 +18,9 @@ def test_reference_arm_prints_the_contract_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "C2" in cb["sample"]
     assert "workload" in line["config"]
+    nat = line["cpu_baseline_native"]  # the -march=native build beside the reference-flags build
+    assert nat["kind"] == "port" and nat["value"] > 0 and "-march=native" in nat["flags"]
+    assert nat["same_trajectory_as_reference_flags_build"] == f"{line['config']['pairs_per_step']}/{line['config']['pairs_per_step']}"
     rs = line.get("reference_sources")
     if rs is not None:  # present when oracle/_ref/libplref2.so exists: the reference's own sources take the same path
         n = rs["problems"]
