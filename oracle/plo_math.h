@@ -491,8 +491,8 @@ inline void col_piv_qr_solve_3x2(const double B[3][2], const double b[3], double
 
 // selfadjointView<Lower>().llt().solve(rhs): only the lower triangle of A (n x n row-major) is read.
 // Returns false if a pivot is not positive (Eigen would carry NaNs on; we do too but flag it).
-inline bool llt_solve_lower(int n, const double *A, const double *rhs, double *x) {
-    double L[8 * 8];
+inline bool llt_solve_lower(int n, const double *A, const double *rhs, double *x) { // n <= 32
+    double L[32 * 32];
     bool ok = true;
     for (int j = 0; j < n; ++j) {
         double d = A[j * n + j];
@@ -506,7 +506,7 @@ inline bool llt_solve_lower(int n, const double *A, const double *rhs, double *x
             L[i * n + j] = s / ljj;
         }
     }
-    double y[8];
+    double y[32];
     for (int i = 0; i < n; ++i) {
         double s = rhs[i];
         for (int k = 0; k < i; ++k) s -= L[i * n + k] * y[k];
