@@ -92,3 +92,22 @@ def test_no_silent_cpu_fallback():
     # too few / zero points return default stats without touching the device (ransac_impl.h:161-163)
     r = cabi.ransac("relpose", np.zeros((0, 2)), np.zeros((0, 2)), cabi.RansacOpt(), 1e-3)
     assert r["stats"]["iterations"] == 0 and r["stats"]["model_score"] > 1e300
+
+
+def test_product_tree_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under poselib_b200/ or include/ may include, import, link or name it,
+    and the built library depends on the CUDA runtime and the C/C++ runtimes only."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"oracle|plo_py|plo_[a-z]+\.(cc|h)|libplo|plr2_|plref")
+    for base in ("poselib_b200", "include"):
+        for d, _, files in os.walk(os.path.join(root, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc", "Makefile")):
+                    text = open(os.path.join(d, f), errors="ignore").read()
+                    assert not pat.search(text), os.path.join(d, f)
+    lib = os.path.join(root, "poselib_b200", "libposelib_b200.so")
+    needed = subprocess.run(["readelf", "-d", lib], capture_output=True, text=True).stdout
+    libs = re.findall(r"\(NEEDED\)\s+Shared library: \[(.+?)\]", needed)
+    assert libs and all(re.match(r"(lib(cudart|stdc\+\+|m|gcc_s|c|pthread|dl|rt)\.so|ld-linux)", n) for n in libs), libs
