@@ -40,8 +40,17 @@ def main():
             "model": [float(v).hex() for v in np.asarray(r["model"], dtype=np.float64).reshape(-1)],
         }
         print(name, r["stats"]["iterations"], r["stats"]["num_inliers"])
+    out["refine"] = {}
+    for kind, loss in RC.REFINE_CELLS:
+        cell = []
+        for m0, a, b, kw in RC.refine_cases(kind, loss):
+            with P.reference_sources():
+                m, bs = P.refine(kind, m0, a, b, P.BundleOpt(**kw))
+            cell.append({"iterations": int(bs[0]), "initial_cost": float(bs[1]).hex(), "cost": float(bs[2]).hex(),
+                         "model": [float(v).hex() for v in np.asarray(m, dtype=np.float64).reshape(-1)]})
+        out["refine"][f"{kind}/{loss}"] = cell
     json.dump(out, open(os.path.join(HERE, "reference_sources.json"), "w"), indent=1)
-    print("wrote", len(out["cases"]), "cases")
+    print("wrote", len(out["cases"]), "cases and", 3 * len(out["refine"]), "refinements")
 
 
 if __name__ == "__main__":

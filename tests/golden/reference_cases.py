@@ -81,6 +81,57 @@ CASES["estimate_fundamental_prosac_rfc"] = _est_fundamental
 CASES["estimate_homography_3000"] = _est_homography
 
 
+# ---- LM refiners: the 48 cases of tests/test_gpu_parity.py::test_lm_refiners_match_oracle, input for input ---------------
+def _perturbed(kind, p, rng):
+    if kind == "pnp":
+        q = p["q_gt"] + rng.normal(0, 0.01, 4)
+        return np.r_[q / np.linalg.norm(q), p["t_gt"] + rng.normal(0, 0.02, 3)]
+    if kind == "relpose":
+        q = p["q_gt"] + rng.normal(0, 0.01, 4)
+        t = p["t_gt"] + rng.normal(0, 0.02, 3)
+        return np.r_[q / np.linalg.norm(q), t / np.linalg.norm(t)]
+    if kind == "fundamental":
+        t = p["t_gt"]
+        E = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]) @ p["R_gt"]
+        E = E + rng.normal(0, 0.01, (3, 3))
+        return E / np.linalg.norm(E)
+    H = p["H_gt"] / np.linalg.norm(p["H_gt"])
+    return H + rng.normal(0, 0.002, (3, 3))
+
+
+def refine_cases(kind, loss):
+    """The three problems of one (kind, loss) cell: (model0, a, b, BundleOpt kwargs)."""
+    rng = np.random.default_rng(7)
+    out = []
+    for idx in range(3):
+        if kind == "pnp":
+            p = G.abspose_problem(500, 0.7, 31, idx)
+            a, b, scale = p["x"] / G.FOCAL, p["X"], 12.0 / G.FOCAL
+        elif kind == "homography":
+            p = G.homography_problem(600, 0.7, 34, idx)
+            a, b, scale = p["x1"] / G.FOCAL, p["x2"] / G.FOCAL, 2.0 / G.FOCAL
+        else:
+            p = G.relpose_problem(600, 0.7, 32, idx)
+            a, b, scale = p["x1"] / G.FOCAL, p["x2"] / G.FOCAL, 2.0 / G.FOCAL
+        out.append((_perturbed(kind, p, rng), a, b, dict(max_iterations=25, loss_type=loss, loss_scale=scale)))
+    return out
+
+
+REFINE_CELLS = [(k, l) for k in ("pnp", "relpose", "fundamental", "homography") for l in ("TRUNCATED", "CAUCHY", "HUBER", "TRIVIAL")]
+
+
+def check_refine(model, bstats, gold, model_tol, cost0_rtol, cost_rtol):
+    """bstats = [iterations, initial_cost, cost, ...]; F / H up to sign (same comparison as the GPU parity test)."""
+    gm = np.array([float.fromhex(v) for v in gold["model"]]).reshape(np.asarray(model).shape)
+    c0, c1 = float.fromhex(gold["initial_cost"]), float.fromhex(gold["cost"])
+    assert abs(bstats[1] - c0) <= cost0_rtol * abs(c0), (bstats[1], c0)
+    assert abs(bstats[2] - c1) <= cost_rtol * abs(c1), (bstats[2], c1)
+    m = np.asarray(model, dtype=np.float64)
+    err = min(np.abs(m - gm).max(), np.abs(m + gm).max()) if m.ndim == 2 else np.abs(m - gm).max()
+    assert err <= model_tol * max(1.0, np.abs(gm).max()), (err, m, gm)
+    return err
+
+
 def run(api, case):
     """api: oracle/plo_py (also inside `with plo_py.reference_sources()`) or poselib_b200.cabi — same call surface."""
     ro = api.RansacOpt(**case["kw"])

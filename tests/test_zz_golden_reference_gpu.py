@@ -26,3 +26,22 @@ def test_cuda_path_reproduces_the_reference_sources_fixtures(name):
     cabi.set_device(0)
     case, gold = RC.CASES[name](), GOLD[name]
     RC.check(RC.run(cabi, case), gold, case["kind"], model_tol=2e-6, score_rtol=2e-9)
+
+
+REFINE = json.load(open(os.path.join(HERE, "golden", "reference_sources.json")))["refine"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,loss", RC.REFINE_CELLS)
+def test_cuda_refiners_reproduce_the_reference_sources_refinements(kind, loss):
+    """plb_bundle_adjust / plb_refine_* against the refinements the reference's sources produced — the cases and the
+    tolerances of tests/test_gpu_parity.py::test_lm_refiners_match_oracle (initial cost 1e-10, final cost 1e-7, model 1e-6;
+    the oracle reproduces these fixtures bit for bit on the CPU)."""
+    from poselib_b200 import cabi
+    if cabi.device_count() == 0:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box")
+    cabi.set_device(0)
+    for (m0, a, b, kw), gold in zip(RC.refine_cases(kind, loss), REFINE[f"{kind}/{loss}"]):
+        m, bs = cabi.refine(kind, m0, a, b, cabi.BundleOpt(**kw))
+        RC.check_refine(m, bs, gold, model_tol=1e-6, cost0_rtol=1e-10, cost_rtol=1e-7)
+
