@@ -63,7 +63,58 @@ def _est_homography():
                 kw=dict(max_iterations=20000, min_iterations=500, seed=2))
 
 
+# ---- cameras with distortion / tangent Sampson (rows N3 / N1): the cases of test_estimate_relative_pose_camera_prestep_on_device,
+# test_estimate_absolute_pose_distortion_cameras and test_tangent_sampson_ransac_matches_oracle, input for input -------------
+DISTORTION_CAMERAS = [  # tests/example_cameras.h:31-38 of the reference, principal point moved to the image centre
+    ("SIMPLE_RADIAL", [1100.0, 30.0, -20.0, -0.0397695]),
+    ("RADIAL", [1050.0, -15.0, 25.0, -0.04012, 0.00123]),
+    ("OPENCV", [1020.0, 990.0, 12.0, -8.0, 0.0141865, -0.0465301, 0.0005, -0.0003]),
+    ("OPENCV", [868.993378, 866.063001, 5.9, -4.0, -0.399431, 0.188924, 0.000153, 0.000571]),
+    ("SIMPLE_PINHOLE", [950.0, 3.0, 4.0]),
+]
+
+
+def _distort(cam, x_px):
+    """pixel observations of the synthetic pinhole camera (f = G.FOCAL, pp = 0) re-imaged by `cam` (oracle projection,
+    pinned bit for bit to the reference's camera code)."""
+    import plo_py
+    X = np.c_[np.asarray(x_px) / G.FOCAL, np.ones(len(x_px))]
+    return plo_py.camera_project_with_jac(cam, X)[2]
+
+
+def _cam_relpose(i, second=None):
+    p = G.relpose_problem(2500, 0.45, 31, 2)
+    c1 = DISTORTION_CAMERAS[i]
+    c2 = DISTORTION_CAMERAS[second] if second is not None else c1
+    return dict(api="estimate", kind="relpose", a=_distort(c1, p["x1"]), b=_distort(c2, p["x2"]), me=1.5,
+                cam_specs=[c1, c2], kw=dict(max_iterations=20000, min_iterations=300, seed=4))
+
+
+def _cam_pnp(i):
+    p = G.abspose_problem(1500, 0.5, 32, 4)
+    c = DISTORTION_CAMERAS[i]
+    return dict(api="estimate", kind="pnp", a=_distort(c, p["x"]), b=p["X"], me=4.0, cam_specs=[c],
+                kw=dict(max_iterations=5000, min_iterations=300, seed=1))
+
+
+def _tangent(i, api):
+    p = G.relpose_problem(2000, 0.4, 33, 1)
+    c = DISTORTION_CAMERAS[i]
+    d = dict(api=api, kind="relpose", a=_distort(c, p["x1"]), b=_distort(c, p["x2"]), me=1.5, cam_specs=[c, c],
+             kw=dict(max_iterations=20000, min_iterations=300, seed=6))
+    if api == "estimate":
+        d["tangent_sampson"] = True
+    return d
+
+
 CASES = {}
+for _i in range(5):
+    CASES[f"estimate_relpose_camera{_i}"] = lambda i=_i: _cam_relpose(i)
+    CASES[f"estimate_pnp_camera{_i}"] = lambda i=_i: _cam_pnp(i)
+CASES["estimate_relpose_camera0_and_1"] = lambda: _cam_relpose(0, 1)
+for _i in range(4):
+    CASES[f"ransac_relpose_cameras{_i}"] = lambda i=_i: _tangent(i, "ransac_relpose_cameras")
+    CASES[f"estimate_relpose_tangent_camera{_i}"] = lambda i=_i: _tangent(i, "estimate")
 for _s in (0, 1, 2):
     CASES[f"ransac_pnp_200_s{_s}"] = lambda s=_s: _pnp(200, 0.5, 1000, s)
     CASES[f"ransac_pnp_1500_s{_s}"] = lambda s=_s: _pnp(1500, 0.35, 3000, s)
@@ -142,6 +193,13 @@ def run(api, case):
         extra["init"] = case["init"]
     if case["api"] == "ransac":
         return api.ransac(case["kind"], case["a"], case["b"], ro, case["me"], **extra)
+    if "cam_specs" in case:  # (model name, params): the oracle wrappers take the tuple, the C-ABI binding a Camera struct
+        cams = [api.Camera(*c) if hasattr(api, "Camera") else c for c in case["cam_specs"]]
+        if case["api"] == "ransac_relpose_cameras":
+            return api.ransac_relpose_cameras(case["a"], case["b"], cams[0], cams[1], ro, case["me"])
+        if case.get("tangent_sampson"):
+            extra["tangent_sampson"] = True
+        return api.estimate(case["kind"], case["a"], case["b"], ro, api.BundleOpt(), case["me"], *cams, **extra)
     cam = api.Camera("PINHOLE", CAMT) if hasattr(api, "Camera") else CAMT
     cams = [cam] * case["cams"]
     return api.estimate(case["kind"], case["a"], case["b"], ro, api.BundleOpt(), case["me"], *cams, **extra)
