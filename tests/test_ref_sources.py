@@ -18,7 +18,8 @@ Result of the comparison (asserted below):
     7-point cubic) instead of copying ~200 lines of generated expressions, so the operation ORDER differs: same
     solution count, solutions equal up to the conditioning of the minimal problem (median 1e-15, worst 1e-7 over
     the sample).  End to end, ransac_relpose / ransac_fundamental / estimate_* return the same iteration count,
-    refinement count, inlier count and inlier mask; the model agrees to 1e-9 and the MSAC score to 1e-12 relative.
+    refinement count, inlier count and inlier mask; the model agrees to 1e-9 (relative poses up to the |t| gauge) and the
+    MSAC score to 1e-12 relative.
     Switched to the reference's operation order (test hook plo_set_reference_order; the 480-term determinant order is
     parsed from the reference's source at run time, nothing of it is stored here) the oracle is BIT-IDENTICAL to the
     reference's sources on the whole path, degenerate inputs included (last four tests of this file).
@@ -155,9 +156,15 @@ def _close_runs(a, b, sign_free=False, tol=1e-9):
     assert (sa["iterations"], sa["refinements"], sa["num_inliers"]) == (sb["iterations"], sb["refinements"], sb["num_inliers"])
     assert np.array_equal(a["inliers"], b["inliers"])
     assert abs(sa["model_score"] - sb["model_score"]) <= 1e-12 * abs(sa["model_score"])
-    d = maxdiff(a["model"], b["model"])
+    am, bm = np.asarray(a["model"], dtype=float), np.asarray(b["model"], dtype=float)
+    if am.ndim == 1 and not sign_free:
+        # 7-vectors here are relative poses: |t| is a gauge freedom the refiner never renormalises (relative.h:152-157), and
+        # it is the one quantity that drifts (up to 1e-5) between two last-bit-different runs; compare the direction
+        am = np.r_[am[:4], am[4:] / max(np.linalg.norm(am[4:]), 1e-300)]
+        bm = np.r_[bm[:4], bm[4:] / max(np.linalg.norm(bm[4:]), 1e-300)]
+    d = maxdiff(am, bm)
     if sign_free:
-        d = min(d, maxdiff(a["model"], -np.asarray(b["model"])))
+        d = min(d, maxdiff(am, -bm))
     assert d < tol
 
 
@@ -192,11 +199,9 @@ def test_initial_model_and_prosac_on_relpose():
     p = G.relpose_problem(1500, 0.4, 2, 9, prosac_sorted=True)
     ro = P.RansacOpt(max_iterations=3000, min_iterations=100, seed=4, progressive_sampling=True)
     a, b = both(lambda: P.estimate("relpose", p["x1"], p["x2"], ro, P.BundleOpt(), 1.0, CAMT, CAMT))
-    # same iterations / inliers / mask and the same cost to 1e-12, but this problem has a flat direction: LM started from
-    # minimal models that differ in the last bits stops (step_tol 1e-8) up to 3e-6 apart in t
-    _close_runs(a, b, tol=1e-5)
+    _close_runs(a, b)
     ro2 = P.RansacOpt(max_iterations=500, min_iterations=50, seed=4, score_initial_model=True)
-    _close_runs(*both(lambda: P.estimate("relpose", p["x1"], p["x2"], ro2, P.BundleOpt(), 1.0, CAMT, CAMT, init=a["model"])), tol=1e-5)
+    _close_runs(*both(lambda: P.estimate("relpose", p["x1"], p["x2"], ro2, P.BundleOpt(), 1.0, CAMT, CAMT, init=a["model"])))
 
 
 def test_headline_configuration_c2_agrees():
@@ -270,7 +275,8 @@ def test_outcome_does_not_depend_on_eigens_summation_order():
     SSE2 build (2-wide packets combined as a tree: (x0+x2)+(x1+x3); tree-shaped inner sums in coefficient-based products:
     x0+(x1+x2)) — `make -C oracle ref2alt`.  On every fixture case (tests/golden/reference_cases.py: all RANSAC and
     estimate_* cases of the GPU parity suite) both orders give the same iterations, refinements, inlier counts and inlier
-    masks; the MSAC scores agree to 1e-13 and the models to 1e-9, except where LM stops in a flat direction (2e-6)."""
+    masks; the MSAC scores agree to 1e-13 and the models to 1e-9 (relative poses compared up to the |t| gauge, which
+    is the one quantity that drifts, by up to 1e-5)."""
     import os
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
@@ -286,12 +292,15 @@ def test_outcome_does_not_depend_on_eigens_summation_order():
         assert (sa["iterations"], sa["refinements"], sa["num_inliers"]) == (sb["iterations"], sb["refinements"], sb["num_inliers"]), name
         assert np.array_equal(a["inliers"], b["inliers"]), name
         assert abs(sa["model_score"] - sb["model_score"]) <= 1e-13 * abs(sa["model_score"]), name
-        am, bm = np.asarray(a["model"]), np.asarray(b["model"])
+        am, bm = np.asarray(a["model"], dtype=float), np.asarray(b["model"], dtype=float)
+        if case["kind"] == "relpose":  # |t| is a gauge freedom (see _close_runs): it drifts by up to 1e-5, the direction does not
+            am = np.r_[am[:4], am[4:] / np.linalg.norm(am[4:])]
+            bm = np.r_[bm[:4], bm[4:] / np.linalg.norm(bm[4:])]
         d = np.abs(am - bm).max()
         if am.ndim == 2:
             d = min(d, np.abs(am + bm).max())
         worst_model.append(d / np.abs(am).max())
-    assert max(worst_model) < 1e-5 and np.median(worst_model) < 1e-12 and sorted(worst_model)[-2] < 1e-9
+    assert max(worst_model) < 1e-9 and np.median(worst_model) < 1e-12
 
 
 # ---- the operation order of the generated expansions is the ONLY difference ---------------------------------------
