@@ -49,6 +49,15 @@ def main():
             cell.append({"iterations": int(bs[0]), "initial_cost": float(bs[1]).hex(), "cost": float(bs[2]).hex(),
                          "model": [float(v).hex() for v in np.asarray(m, dtype=np.float64).reshape(-1)]})
         out["refine"][f"{kind}/{loss}"] = cell
+    out["solvers"] = {}
+    for name in RC.SOLVERS:
+        a, b = RC.solver_instances(name)
+        sols = []
+        for i in range(len(a)):
+            with P.reference_sources():
+                r = RC.solve_one(P, name, a[i], b[i])
+            sols.append([float(v).hex() for v in r.reshape(-1)])
+        out["solvers"][name] = sols
     json.dump(out, open(os.path.join(HERE, "reference_sources.json"), "w"), indent=1)
     print("wrote", len(out["cases"]), "cases and", 3 * len(out["refine"]), "refinements")
 

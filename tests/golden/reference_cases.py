@@ -183,6 +183,61 @@ def check_refine(model, bstats, gold, model_tol, cost0_rtol, cost_rtol):
     return err
 
 
+# ---- minimal solvers: subsets of the instances of test_p3p / test_relpose_7pt / test_homography_4pt_matches_oracle --------
+def _noisy_samples(npts, count, seed, outliers=True):
+    """bearing samples as the estimators build them from noisy / outlier data (same generator as tests/test_gpu_parity.py)."""
+    rng = np.random.default_rng(seed)
+    x1s, x2s = [], []
+    for i in range(count):
+        p = G.relpose_problem(64, 0.5 if outliers else 1.0, config_id=20, problem_idx=seed * 1000 + i)
+        idx = rng.choice(64, npts, replace=False)
+        a = np.c_[p["x1"][idx] / G.FOCAL, np.ones(npts)]
+        b = np.c_[p["x2"][idx] / G.FOCAL, np.ones(npts)]
+        x1s.append(a / np.linalg.norm(a, axis=1, keepdims=True))
+        x2s.append(b / np.linalg.norm(b, axis=1, keepdims=True))
+    return np.array(x1s), np.array(x2s)
+
+
+def solver_instances(name, n_min=40, n_noisy=12):
+    """(a, b) arrays [count, k, 3]: the first n_min minimal instances and the first n_noisy noisy samples of the GPU test."""
+    if name == "p3p":
+        xs, Xs = [], []
+        for i in range(n_min):
+            x, X, _, _ = G.minimal_abspose(i)
+            xs.append(x)
+            Xs.append(X)
+        for i in range(n_noisy):
+            p = G.abspose_problem(50, 0.5, config_id=21, problem_idx=i)
+            a = np.c_[p["x"][:3] / G.FOCAL, np.ones(3)]
+            xs.append(a / np.linalg.norm(a, axis=1, keepdims=True))
+            Xs.append(p["X"][:3])
+        return np.array(xs), np.array(Xs)
+    k, seed = {"relpose_7pt": (7, 2), "homography_4pt": (4, 3)}[name]
+    x1s, x2s = [], []
+    for i in range(n_min):
+        if name == "relpose_7pt":
+            x1, x2, _, _ = G.minimal_relpose(i, 7)
+        else:
+            x1, x2, _ = G.minimal_homography(i)
+        x1s.append(x1)
+        x2s.append(x2)
+    a, b = _noisy_samples(k, 300, seed)  # the GPU test draws 300; the stream must be consumed identically
+    return np.concatenate([np.array(x1s), a[:n_noisy]]), np.concatenate([np.array(x2s), b[:n_noisy]])
+
+
+SOLVERS = ("p3p", "relpose_7pt", "homography_4pt")
+
+
+def solve_one(api, name, a, b):
+    """One instance through the oracle-style wrapper; -> array of solutions (k, 7) / (k, 3, 3)."""
+    if name == "p3p":
+        return np.asarray(api.p3p(a, b))
+    if name == "relpose_7pt":
+        return np.asarray(api.relpose_7pt(a, b))
+    n, H = api.homography_4pt(a, b)
+    return np.asarray(H)[None] if n else np.zeros((0, 3, 3))
+
+
 def run(api, case):
     """api: oracle/plo_py (also inside `with plo_py.reference_sources()`) or poselib_b200.cabi — same call surface."""
     ro = api.RansacOpt(**case["kw"])
