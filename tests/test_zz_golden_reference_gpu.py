@@ -75,3 +75,17 @@ def test_cuda_solvers_reproduce_the_reference_sources_solver_outputs(name):
         elif n[i]:
             assert np.allclose(out[i], g[0], rtol=1e-10, atol=1e-12, equal_nan=True), i
 
+
+@pytest.mark.gpu
+def test_poselib_client_runs_on_the_b200_backend():
+    """tests/dropin_client_test.cc — a client written against PoseLib's own headers only, whose checks pass on PoseLib's own
+    CPU implementation (tests/test_dropin_reference_headers.py) — linked with poselib_b200/adapter/poselib_dropin.cc and
+    libposelib_b200.so instead: every estimate_*, ransac_relpose, refine_relpose and relpose_5pt call goes through PoseLib's
+    declared signatures into the CUDA path.  The binary is built in the CPU container (it needs the reference's headers)."""
+    import subprocess
+    exe = os.path.join(HERE, "_dropin_client")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_dropin_client was not built (needs /root/reference; run the CPU test-suite or build() first)")
+    out = subprocess.run([exe, "run"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "dropin run ok" in out.stdout, out.stdout + out.stderr
+
