@@ -117,7 +117,7 @@ int plb_set_mode(int mode);
 /* ---- host-side pieces of the loop; no device needed (exercised by the CPU test-suite) ---------------------
  * plb_host_sample_table: the first `iters` minimal samples (k indices each) RandomSampler(n, k, opt) draws
  * (robust/sampling.cc:37-61,85-136, incl. PROSAC and the int sign-extension of random_int before `% n`).
- * plb_host_dynamic_max_iter: compute_dynamic_max_iter (robust/ransac_impl.h:51-76). */
+ * plb_host_dynamic_max_iter: compute_dynamic_max_iter (robust/ransac_impl.h:58-74). */
 int plb_host_sample_table(uint64_t n, uint32_t k, const plb_ransac_opt *opt, uint64_t iters, uint32_t *out);
 uint64_t plb_host_dynamic_max_iter(uint64_t num_inliers, uint64_t num_data, uint32_t sample_sz, double success_prob,
                                    double dyn_num_trials_mult, uint64_t min_iterations, uint64_t max_iterations);
@@ -134,7 +134,7 @@ int plb_ransac_fundamental(const double *x1_xy, const double *x2_xy, size_t n, c
 int plb_ransac_homography(const double *x1_xy, const double *x2_xy, size_t n, const plb_ransac_opt *opt,
                           double max_error, double H_inout[9], char *inliers, plb_ransac_stats *stats,
                           plb_counters *counters);
-/* robust/ransac.h:65-67, ransac.cc:155-168: relative pose with camera models, scored with the tangent Sampson error
+/* robust/ransac.h:62-64, ransac.cc:155-168: relative pose with camera models, scored with the tangent Sampson error
  * on the unprojected bearings (CameraRelativePoseEstimator); x1/x2 and max_error in the pixel units of the cameras.
  * The start pose is reset to identity (ransac.cc:159-160). */
 int plb_ransac_relpose_cameras(const double *x1_px, const double *x2_px, size_t n, const plb_camera *camera1,
@@ -175,8 +175,8 @@ int plb_relpose_7pt_batch(size_t count, const double *x1 /*count*7*3*/, const do
 int plb_homography_4pt_batch(size_t count, const double *x1 /*count*4*3*/, const double *x2,
                              double *H_out /*count*9*/, int32_t *n_out, int check_cheirality);
 
-/* ---- PoseLib/robust/bundle.h: bundle_adjust (calibrated, :50-52), refine_relpose (:100-102), refine_fundamental
- * (:133-135), refine_homography (:150-152) — the LM refiners the LO step and the final polish are built from.
+/* ---- PoseLib/robust/bundle.h: bundle_adjust (calibrated, :41-43), refine_relpose (:84-86), refine_fundamental
+ * (:132-134), refine_homography (:148-150) — the LM refiners the LO step and the final polish are built from.
  * Uniform weights.  bundle_stats_out (may be NULL): {iterations, initial_cost, cost}. ------------------------- */
 int plb_bundle_adjust(const double *x_xy, const double *X_xyz, size_t n, double pose_inout[7],
                       const plb_bundle_opt *opt, double bundle_stats_out[3]);

@@ -129,7 +129,7 @@ RansacStats ransac_relpose(const std::vector<P2> &x1, const std::vector<P2> &x2,
     detail::pose_from(m, best_model);
     return detail::from_c<RansacStats>(st);
 }
-// ransac_relpose(x1, x2, camera1, camera2, RelativePoseOptions, CameraPose*, inliers*)   robust/ransac.h:65-67
+// ransac_relpose(x1, x2, camera1, camera2, RelativePoseOptions, CameraPose*, inliers*)   robust/ransac.h:62-64
 template <typename RansacStats, typename P2, typename Camera, typename Opt, typename Pose>
 RansacStats ransac_relpose(const std::vector<P2> &x1, const std::vector<P2> &x2, const Camera &camera1,
                            const Camera &camera2, const Opt &opt, Pose *best_model, std::vector<char> *best_inliers) {
