@@ -119,6 +119,11 @@ int plb_set_mode(int mode);
  * (robust/sampling.cc:37-61,85-136, incl. PROSAC and the int sign-extension of random_int before `% n`).
  * plb_host_dynamic_max_iter: compute_dynamic_max_iter (robust/ransac_impl.h:58-74). */
 int plb_host_sample_table(uint64_t n, uint32_t k, const plb_ransac_opt *opt, uint64_t iters, uint32_t *out);
+/* The table the DEVICE sampler of the engine draws (k_sample): `count` samplers with seeds opt->seed + j, `round`
+ * samples per launch with the state carried across launches like the engine's rounds.  out: count * iters * k.
+ * Test surface: pins the device sampler to plb_host_sample_table (itself pinned to robust/sampling.cc). */
+int plb_device_sample_table(uint64_t n, uint32_t k, const plb_ransac_opt *opt, uint64_t iters, uint64_t round,
+                            uint32_t count, uint32_t *out);
 uint64_t plb_host_dynamic_max_iter(uint64_t num_inliers, uint64_t num_data, uint32_t sample_sz, double success_prob,
                                    double dyn_num_trials_mult, uint64_t min_iterations, uint64_t max_iterations);
 

@@ -91,7 +91,7 @@ class Problem(C.Structure):
 
 EXPORTS = [
     "plb_ransac_opt_default", "plb_bundle_opt_default", "plb_last_error", "plb_device_count", "plb_set_device",
-    "plb_set_mode", "plb_host_sample_table", "plb_host_dynamic_max_iter", "plb_ransac_pnp", "plb_ransac_relpose", "plb_ransac_relpose_cameras", "plb_ransac_fundamental",
+    "plb_set_mode", "plb_host_sample_table", "plb_device_sample_table", "plb_host_dynamic_max_iter", "plb_ransac_pnp", "plb_ransac_relpose", "plb_ransac_relpose_cameras", "plb_ransac_fundamental",
     "plb_ransac_homography",
     "plb_estimate_absolute_pose", "plb_estimate_relative_pose", "plb_estimate_fundamental",
     "plb_estimate_homography", "plb_p3p_batch", "plb_relpose_5pt_batch", "plb_relpose_5pt_poses_batch",
@@ -135,6 +135,16 @@ def host_sample_table(n, k, ropt, iters):
     out = np.zeros((iters, k), dtype=np.uint32)
     _check(_lib.plb_host_sample_table(C.c_uint64(n), C.c_uint32(k), C.byref(ropt), C.c_uint64(iters),
                                       out.ctypes.data_as(C.POINTER(C.c_uint32))))
+    return out
+
+
+def device_sample_table(n, k, ropt, iters, round_size=4096, count=1):
+    """The same table drawn by the engine's DEVICE sampler (k_sample): `count` samplers with seeds seed+j, `round_size`
+    samples per launch (state carried across launches).  Returns (count, iters, k)."""
+    out = np.zeros((count, iters, k), dtype=np.uint32)
+    _check(_lib.plb_device_sample_table(C.c_uint64(n), C.c_uint32(k), C.byref(ropt), C.c_uint64(iters),
+                                        C.c_uint64(round_size), C.c_uint32(count),
+                                        out.ctypes.data_as(C.POINTER(C.c_uint32))))
     return out
 
 

@@ -189,7 +189,7 @@ __global__ void k_gather_models(const double *__restrict__ models, const int *__
 
 struct Engine {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     bool ready = false;
     int device = -1;
     DevBuf<double> in, soa64, px64, models, lm_in, s5_blk, s5_cpoly, s5_roots;
@@ -197,26 +197,39 @@ struct Engine {
     DevBuf<float> soa32;
     DevBuf<uint32_t> samples;
     DevBuf<int> work, slots, subset, act, model_prob, prob_count;
+    // round state that stays on the device: sampler states, per-sample / per-model records, candidate lists
+    DevBuf<SamplerDev> smp;
+    DevBuf<uint64_t> growth;
+    DevBuf<RoundProb> rp;
+    DevBuf<int> n_models, first_slot, prefix, cand_slot, cand_sample, n_cand, n_models_tot;
+    DevBuf<uint32_t> counts, fcounts, fborder;
+    DevBuf<double> scores;
+    DevBuf<float> fscores, ferr;
+    DevBuf<LmJob> lo_tmpl;
+    DevBuf<LoJobSrc> job_src;
+    PinBuf<SamplerDev> h_smp;
+    PinBuf<uint64_t> h_growth;
+    PinBuf<RoundProb> h_rp;
+    PinBuf<LmJob> h_lo_tmpl;
+    PinBuf<int> h_hypfix;
     DevBuf<char> mask;
     DevBuf<ProblemDev> probs;
     DevBuf<TransposeDesc> tdesc;
     DevBuf<MaskDesc> mdesc;
     DevBuf<LmJob> jobs;
     PinBuf<double> h_in, h_lm_in;
-    PinBuf<uint32_t> h_samples;
     PinBuf<int> h_slots, h_act, h_work;
     PinBuf<char> h_mask;
     PinBuf<ProblemDev> h_probs;
     PinBuf<TransposeDesc> h_tdesc;
     PinBuf<MaskDesc> h_mdesc;
     PinBuf<LmJob> h_jobs;
-    // result records written by the kernels directly into mapped pinned memory (no explicit D2H copies)
+    // result records written by the kernels directly into mapped pinned memory (no explicit D2H copies): per round and
+    // problem one header, the models that improved the best-minimal state and the LO results
     MapBuf<double> h_scores;
     MapBuf<uint32_t> h_counts;
-    MapBuf<int> h_n_models, h_first_slot;
-    MapBuf<uint32_t> h_fcounts; // fast mode: fp32 screening records
-    MapBuf<float> h_fscores;
-    std::vector<uint8_t> is_cand;
+    MapBuf<SelHeader> h_hdr;
+    MapBuf<ImpRec> h_imp;
     MapBuf<LmJobOut> h_lm_out;
     uint64_t launches = 0;
 
@@ -242,6 +255,7 @@ struct Engine {
         if (!ev0) PLB_CUDA(cudaEventCreate(&ev0));
         if (!ev1) PLB_CUDA(cudaEventCreate(&ev1));
         if (!ev2) PLB_CUDA(cudaEventCreate(&ev2));
+        if (!ev3) PLB_CUDA(cudaEventCreate(&ev3));
         {
             int r = h_work.ensure(8);
             if (r) return r;
@@ -276,8 +290,6 @@ static int usable_cpus() {
     }();
     return cached;
 }
-// number of threads a run_group call may use for its sample tables (1 inside batch workers that share the cores)
-static thread_local int t_sampler_threads = 0;
 
 // engines of the batch worker threads, reused across plb_ransac_batch calls
 static std::mutex g_pool_mtx;
@@ -369,7 +381,7 @@ struct PState {
     Task *t = nullptr;
     int n = 0, n_pad = 0, pidx = 0;
     bool enough = false, active = false, broke = false;
-    Sampler *sampler = nullptr;
+    bool hyp_pending = false; // hypotheses of the last (broken) round still to be added from Engine::h_hypfix
     size_t it = 0, chunk = 1024;
     size_t best_minimal_inlier_count = 0;
     double best_minimal_msac_score = std::numeric_limits<double>::max();
@@ -380,11 +392,8 @@ struct PState {
     double best_model[9];
     // per round
     size_t B = 0, g0 = 0;
-    std::vector<int> imp_slot, imp_sample, trig;
-    int imp_base = 0, trig_base = 0; // offsets into the round's gathered-model / LO-result arrays
     long long mask_off = 0;
     int polish_pidx = -1;
-    ~PState() { delete sampler; }
 };
 
 static void update_dynamic(PState &S, int K) { // ransac_impl.h:150-153
@@ -398,7 +407,6 @@ static void update_dynamic(PState &S, int K) { // ransac_impl.h:150-153
 // model improved) one gather + one LM launch per round for the WHOLE group.
 static int run_group(int kind, std::vector<Task *> &tasks) {
     Engine &E = *engine();
-    if (t_sampler_threads == 0) t_sampler_threads = usable_cpus();
     const int K = kind_sample_size(kind), MAXM = kind_max_models(kind), MSZ = kind_model_size(kind);
     // in_arr: doubles per correspondence in the caller layout; n_arr: SoA arrays resident per correspondence
     const int b_dim = (kind == KIND_PNP) ? 3 : 2, in_arr = 2 + b_dim, n_arr = (kind == KIND_RELPOSE_TS) ? TS_ARRAYS : in_arr;
@@ -434,6 +442,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
     auto finish = [&]() {
         for (int i = 0; i < NP; ++i) {
             PState &S = PS[i];
+            if (S.hyp_pending) S.cnt.hypotheses += (uint64_t)E.h_hypfix.p[S.pidx];
             S.cnt.scored_corrs = S.cnt.hypotheses * S.t->n;
             if (S.t->stats_out) *S.t->stats_out = S.stats;
             if (S.t->cnt_out) *S.t->cnt_out = S.cnt;
@@ -449,7 +458,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
     const uint64_t launches0 = E.launches;
     uint64_t h2d = 0, d2h = 0;
     double lo_wait = 0.0;
-    float gpu_ms_total = 0.f, gpu_ms_score = 0.f;
+    float gpu_ms_total = 0.f, gpu_ms_score = 0.f, gpu_ms_confirm = 0.f;
     auto sync_timed = [&](double *acc) -> int {
         auto t0 = std::chrono::steady_clock::now();
         PLB_CUDA(cudaStreamSynchronize(st));
@@ -586,7 +595,8 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             PLB_CUDA(cudaMemcpyAsync(E.lm_in.p + dev_model_off, E.h_lm_in.p, sizeof(double) * 9 * njobs, cudaMemcpyHostToDevice, st));
             h2d += sizeof(double) * 9 * njobs;
         }
-        launch_lm(kind, E.probs.p, E.jobs.p, E.lm_in.p + dev_model_off, njobs, max_n, E.mask.p, E.subset.p, E.h_lm_out.d, st);
+        launch_lm(kind, E.probs.p, E.jobs.p, E.lm_in.p + dev_model_off, njobs, max_n, E.mask.p, E.subset.p, max_n_pad,
+                  E.h_lm_out.d, st);
         E.launches++;
         d2h += sizeof(LmJobOut) * njobs;
         return PLB_OK;
@@ -668,16 +678,64 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
 
     mark(PH_SETUP);
     // ---- main loop in lock-step rounds ------------------------------------------------------------------------------
-    for (PState &S : PS) {
-        S.active = S.enough && S.t->opt.max_iterations > 0;
-        if (S.enough) S.sampler = new Sampler(S.t->n, (size_t)K, S.t->opt);
+    // Every round is ONE chain of launches with ONE host synchronisation at its end:
+    //   k_sample -> solve kernels -> scoring (fp64 of every model, or fp32 screening) -> k_select -> [k_confirm] ->
+    //   k_pass1 -> k_lm over the LO triggers it listed.
+    // The sampler state, the per-model records and the candidate lists never leave the device; the host receives, per
+    // problem, one header, the few models that improved the best-minimal state and the LO results, and replays
+    // score_models() (ransac_impl.h:106-154) over those.
+    for (PState &S : PS) S.active = S.enough && S.t->opt.max_iterations > 0;
+    {
+        // device sampler states (robust/sampling.h:49-83) + PROSAC growth tables (sampling.cc:105-136)
+        size_t growth_total = 0;
+        for (PState &S : PS)
+            if (S.active && S.t->opt.progressive_sampling) growth_total += std::max<size_t>(S.t->n, (size_t)K);
+        if ((rc = E.h_smp.ensure(NP)) || (rc = E.smp.ensure(2 * (size_t)NP)) || (rc = E.h_growth.ensure(growth_total)) ||
+            (rc = E.growth.ensure(growth_total)) || (rc = E.h_lo_tmpl.ensure(NP)) || (rc = E.lo_tmpl.ensure(NP)) ||
+            (rc = E.h_hypfix.ensure(NP)))
+            return rc;
+        size_t goff = 0;
+        for (int i = 0; i < NP; ++i) {
+            PState &S = PS[i];
+            SamplerDev &D = E.h_smp.p[i];
+            std::memset(&D, 0, sizeof(D));
+            make_lo_job(E.h_lo_tmpl.p[i], S, 0);
+            if (!S.active) continue;
+            D.state = S.t->opt.seed;
+            D.n = (uint32_t)S.t->n;
+            D.k = (uint32_t)K;
+            D.max_prosac = S.t->opt.max_prosac_iterations;
+            if (S.t->opt.progressive_sampling) {
+                Sampler smp(S.t->n, (size_t)K, S.t->opt); // host: the O(N) growth table only
+                uint64_t *g = E.h_growth.p + goff;
+                bool strict = true;
+                for (size_t j = 0; j < smp.growth.size(); ++j) {
+                    g[j] = (uint64_t)smp.growth[j];
+                    if (j >= (size_t)K && !(smp.growth[j] > smp.growth[j - 1])) strict = false;
+                }
+                D.growth = E.growth.p + goff;
+                D.sample_k = 1;
+                D.subset_sz = (uint32_t)K;
+                D.flags = 1u | (strict ? 2u : 0u);
+                goff += smp.growth.size();
+            }
+        }
+        PLB_CUDA(cudaMemcpyAsync(E.smp.p, E.h_smp.p, sizeof(SamplerDev) * NP, cudaMemcpyHostToDevice, st));
+        PLB_CUDA(cudaMemcpyAsync(E.lo_tmpl.p, E.h_lo_tmpl.p, sizeof(LmJob) * NP, cudaMemcpyHostToDevice, st));
+        h2d += (sizeof(SamplerDev) + sizeof(LmJob)) * NP;
+        if (growth_total) {
+            PLB_CUDA(cudaMemcpyAsync(E.growth.p, E.h_growth.p, sizeof(uint64_t) * growth_total, cudaMemcpyHostToDevice, st));
+            h2d += sizeof(uint64_t) * growth_total;
+        }
     }
+    int smp_cur = 0; // sampler states of the current round: E.smp[smp_cur * NP ..]; the advanced ones land in the other half
     const size_t CHUNK_MAX = 16384, ROUND_MAX = 32768, S_TOT_MAX = 262144;
     // 0 exact, 1 fast (fp32 screen + fp64 confirmation of candidates); the tangent-Sampson kind has no fp32 copy
     const int mode = (kind == KIND_RELPOSE_TS) ? 0 : g_mode.load();
-    std::vector<int> cand_slots;
     int cap_factor = kind_is_relpose(kind) ? 8 : MAXM;
+    bool big_caps = false;
     std::vector<int> act;
+    std::vector<uint8_t> first_round(NP, 1);
     for (;;) {
         act.clear();
         for (int i = 0; i < NP; ++i) {
@@ -695,6 +753,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         // round sizes: up to the iteration at which the serial loop would stop for the current dynamic_max_iter
         size_t total = 0;
         const size_t per_cap = std::max<size_t>(256, S_TOT_MAX / (size_t)na);
+        int est_jobs = 0;
         for (int a = 0; a < na; ++a) {
             PState &S = PS[act[a]];
             const size_t stop_at = std::min<size_t>(S.t->opt.max_iterations, std::max(S.t->opt.min_iterations, S.dynamic_max_iter) + 1);
@@ -705,40 +764,26 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             size_t B = settled ? std::min<size_t>(stop_at - S.it, ROUND_MAX) : std::min(S.chunk, CHUNK_MAX);
             B = std::min(B, per_cap);
             B = std::min(B, stop_at - S.it); // stop_at > it for an active problem
-            S.chunk = std::min(CHUNK_MAX, S.chunk * 2);
             S.B = B;
             S.g0 = total;
             total += B;
+            est_jobs += first_round[act[a]] ? 12 : 2; // LO triggers: a record chain at first, then the odd improvement
         }
         const size_t cap_models = total * (size_t)cap_factor;
-        if ((rc = E.h_samples.ensure(total * K)) || (rc = E.samples.ensure(total * K)) || (rc = E.h_n_models.ensure(total)) ||
-            (rc = E.h_first_slot.ensure(total)) || (rc = E.h_counts.ensure(cap_models)) || (rc = E.h_scores.ensure(cap_models)) ||
+        // capacity of the host-visible records of the round; exceeded -> the round is redone with the worst case
+        const size_t job_cap = big_caps ? total : std::min(total, std::max<size_t>(1024, total / 8));
+        const size_t imp_cap = big_caps ? cap_models : std::min(cap_models, 2 * job_cap);
+        const int lm_clusters = lm_round_max_clusters(kind, est_jobs, max_n);
+        if ((rc = E.samples.ensure(total * K)) || (rc = E.n_models.ensure(total)) || (rc = E.first_slot.ensure(total)) ||
+            (rc = E.prefix.ensure(total)) || (rc = E.counts.ensure(cap_models)) || (rc = E.scores.ensure(cap_models)) ||
             (rc = E.models.ensure(cap_models * MSZ)) || (rc = E.model_prob.ensure(cap_models)) ||
+            (rc = E.cand_slot.ensure(cap_models)) || (rc = E.cand_sample.ensure(cap_models)) ||
             (rc = E.h_act.ensure(4 * (size_t)na + 2)) || (rc = E.act.ensure(4 * (size_t)na + 2)) ||
-            (rc = E.prob_count.ensure(na)))
+            (rc = E.h_rp.ensure(na)) || (rc = E.rp.ensure(na)) || (rc = E.n_cand.ensure(na)) ||
+            (rc = E.n_models_tot.ensure(na)) || (rc = E.prob_count.ensure(na)) || (rc = E.h_hdr.ensure(na)) ||
+            (rc = E.h_imp.ensure(imp_cap)) || (rc = E.job_src.ensure(job_cap)) || (rc = E.h_lm_out.ensure(job_cap)) ||
+            (rc = E.subset.ensure((size_t)lm_clusters * max_n_pad)))
             return rc;
-        // sample tables on the host (robust/sampling.cc), problems in parallel when the round is large
-        {
-            auto gen = [&](int a0, int a1) {
-                for (int a = a0; a < a1; ++a) {
-                    PState &S = PS[act[a]];
-                    uint32_t *dst = E.h_samples.p + S.g0 * K;
-                    for (size_t s = 0; s < S.B; ++s) S.sampler->next(dst + s * K);
-                }
-            };
-            // helper threads for the sample tables: only what this group's share of the usable host cores allows
-            // (batch workers already run one thread per group; several ranks may share the host)
-            const unsigned hw = (unsigned)std::max(1, t_sampler_threads);
-            const int nt = (total >= 32768 && na > 1) ? (int)std::min<unsigned>({hw, 16u, (unsigned)na}) : 1;
-            if (nt <= 1) {
-                gen(0, na);
-            } else {
-                std::vector<std::thread> th;
-                for (int t = 0; t < nt; ++t) th.emplace_back(gen, (int)((long long)na * t / nt), (int)((long long)na * (t + 1) / nt));
-                for (auto &x : th) x.join();
-            }
-        }
-        mark(PH_SAMPLE);
         ++n_rounds;
         // h_act layout: active[na] | g_off[na+1] | seg_base[na] | seg_cap[na]
         int max_seg_cap = 0;
@@ -752,13 +797,26 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 const int cap = (int)(S.B * (size_t)cap_factor);
                 E.h_act.p[3 * na + 1 + a] = cap;
                 max_seg_cap = std::max(max_seg_cap, cap);
+                RoundProb &Q = E.h_rp.p[a];
+                Q.pidx = act[a];
+                Q.g0 = (int)S.g0;
+                Q.B = (int)S.B;
+                Q.seg_base = (int)seg;
+                Q.seg_cap = cap;
+                Q.reserved = 0;
+                Q.lb0 = (double)S.best_minimal_inlier_count;
+                Q.ub0 = S.best_minimal_msac_score;
                 seg += (size_t)cap;
             }
             E.h_act.p[2 * na] = (int)total;
         }
-        PLB_CUDA(cudaMemcpyAsync(E.samples.p, E.h_samples.p, sizeof(uint32_t) * total * K, cudaMemcpyHostToDevice, st));
         PLB_CUDA(cudaMemcpyAsync(E.act.p, E.h_act.p, sizeof(int) * (4 * na + 1), cudaMemcpyHostToDevice, st));
-        h2d += sizeof(uint32_t) * total * K + sizeof(int) * (4 * na + 1);
+        PLB_CUDA(cudaMemcpyAsync(E.rp.p, E.h_rp.p, sizeof(RoundProb) * na, cudaMemcpyHostToDevice, st));
+        h2d += sizeof(int) * (4 * na + 1) + sizeof(RoundProb) * na;
+        PLB_CUDA(cudaMemsetAsync(E.work.p, 0, CTL_WORDS * sizeof(int), st));
+        launch_sample(E.rp.p, na, E.smp.p + (size_t)smp_cur * NP, E.smp.p + (size_t)(smp_cur ^ 1) * NP, E.samples.p, st);
+        E.launches++;
+        mark(PH_SAMPLE);
         RoundDesc R;
         R.probs = E.probs.p;
         R.active = E.act.p;
@@ -767,24 +825,29 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         R.samples = E.samples.p;
         R.n_total = (int)total;
         HypOut out;
-        out.n_models = E.h_n_models.d;
-        out.first_slot = E.h_first_slot.d;
+        out.n_models = E.n_models.p;
+        out.first_slot = E.first_slot.p;
         out.seg_base = E.act.p + 2 * na + 1;
         out.seg_cap = E.act.p + 3 * na + 1;
         out.prob_count = E.prob_count.p;
         out.max_seg_cap = max_seg_cap;
-        out.overflow = E.work.p + 2;
-        out.counts = E.h_counts.d;
-        out.scores = E.h_scores.d;
+        out.overflow = E.work.p + CTL_OVERFLOW;
+        out.counts = E.counts.p;
+        out.scores = E.scores.p;
         out.models = E.models.p;
         out.model_prob = E.model_prob.p;
         out.fcounts = nullptr;
         out.fscores = nullptr;
+        out.fborder = nullptr;
+        out.ferr = nullptr;
         if (mode == 1) {
-            if ((rc = E.h_fcounts.ensure(cap_models)) || (rc = E.h_fscores.ensure(cap_models))) return rc;
-            out.fcounts = E.h_fcounts.d;
-            out.fscores = E.h_fscores.d;
-            if (E.is_cand.size() < cap_models) E.is_cand.resize(cap_models, 0);
+            if ((rc = E.fcounts.ensure(cap_models)) || (rc = E.fscores.ensure(cap_models)) ||
+                (rc = E.fborder.ensure(cap_models)) || (rc = E.ferr.ensure(cap_models)))
+                return rc;
+            out.fcounts = E.fcounts.p;
+            out.fscores = E.fscores.p;
+            out.fborder = E.fborder.p;
+            out.ferr = E.ferr.p;
         }
         out.s5_blk = out.s5_cpoly = out.s5_roots = nullptr;
         out.s5_nroots = nullptr;
@@ -800,198 +863,154 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         PLB_CUDA(cudaEventRecord(E.ev0, st));
         launch_hypotheses(kind, R, E.work.p, out, mode, max_n_pad, st, E.ev2);
         PLB_CUDA(cudaEventRecord(E.ev1, st));
-        E.launches += kind_is_relpose(kind) ? 4 : 2; // k_solve (or k5_prep + k5_roots + k5_back) + k_score
-        PLB_CUDA(cudaMemcpyAsync(E.h_work.p, E.work.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        E.launches += kind_is_relpose(kind) ? 4 : 2; // k_solve (or k5_prep + k5_roots + k5_back) + scoring
+        SelectArgs SA;
+        SA.rp = E.rp.p;
+        SA.na = na;
+        SA.mode = mode;
+        SA.n_models = E.n_models.p;
+        SA.first_slot = E.first_slot.p;
+        SA.fcounts = out.fcounts;
+        SA.fscores = out.fscores;
+        SA.fborder = out.fborder;
+        SA.ferr = out.ferr;
+        SA.counts = E.counts.p;
+        SA.scores = E.scores.p;
+        SA.prefix = E.prefix.p;
+        SA.cand_slot = E.cand_slot.p;
+        SA.cand_sample = E.cand_sample.p;
+        SA.n_cand = E.n_cand.p;
+        SA.n_models_tot = E.n_models_tot.p;
+        launch_select(SA, st);
+        E.launches++;
+        if (mode == 1) {
+            launch_confirm(kind, E.probs.p, SA, E.models.p, st);
+            E.launches++;
+        }
+        PLB_CUDA(cudaEventRecord(E.ev3, st));
+        Pass1Args PA;
+        PA.rp = E.rp.p;
+        PA.na = na;
+        PA.cand_slot = E.cand_slot.p;
+        PA.cand_sample = E.cand_sample.p;
+        PA.n_cand = E.n_cand.p;
+        PA.n_models_tot = E.n_models_tot.p;
+        PA.counts = E.counts.p;
+        PA.scores = E.scores.p;
+        PA.models = E.models.p;
+        PA.msz = MSZ;
+        PA.ctl = E.work.p;
+        PA.imp_cap = (int)imp_cap;
+        PA.job_cap = (int)job_cap;
+        PA.hdr = E.h_hdr.d;
+        PA.imp = E.h_imp.d;
+        PA.job_src = E.job_src.p;
+        launch_pass1(PA, st);
+        launch_lm_round(kind, E.probs.p, E.lo_tmpl.p, E.job_src.p, E.models.p, E.work.p + CTL_JOB_TOTAL, (int)job_cap,
+                        est_jobs, max_n, E.subset.p, max_n_pad, E.h_lm_out.d, st);
+        E.launches += 2;
+        PLB_CUDA(cudaMemcpyAsync(E.h_work.p, E.work.p, CTL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
         mark(PH_LAUNCH);
         if ((rc = sync_timed(nullptr))) return rc;
         mark(PH_WAIT_HYP);
-        if (E.h_work.p[2] != 0) { // model list overflow: redo the round with the worst-case capacity (no state was touched)
-            if (cap_factor >= MAXM) {
+        d2h += CTL_WORDS * sizeof(int);
+        if (E.h_work.p[CTL_OVERFLOW] != 0) { // model list overflow: redo the round with the worst-case capacity
+            if (cap_factor >= MAXM) {        // (nothing was committed: the sampler states of this round are still current)
                 g_err = "internal error: model capacity exceeded";
                 return PLB_ERR_CUDA;
             }
             cap_factor = MAXM;
-            for (int a = 0; a < na; ++a) { // rewind the samplers by regenerating them up to `it`
-                PState &S = PS[act[a]];
-                delete S.sampler;
-                S.sampler = new Sampler(S.t->n, (size_t)K, S.t->opt);
-                std::vector<uint32_t> tmp(K);
-                for (size_t s = 0; s < S.it; ++s) S.sampler->next(tmp.data());
-                S.chunk = std::max<size_t>(1024, S.chunk / 2);
-            }
             continue;
         }
-        float ms = 0.f, ms_sc = 0.f;
+        if (E.h_work.p[CTL_FLAGS] != 0) { // more improving models / LO triggers than the record buffers hold
+            if (big_caps) {
+                g_err = "internal error: record capacity exceeded";
+                return PLB_ERR_CUDA;
+            }
+            big_caps = true;
+            continue;
+        }
+        smp_cur ^= 1;
+        float ms = 0.f, ms_sc = 0.f, ms_cf = 0.f;
         cudaEventElapsedTime(&ms, E.ev0, E.ev1);
         cudaEventElapsedTime(&ms_sc, E.ev2, E.ev1);
-        gpu_ms_total += ms;
+        cudaEventElapsedTime(&ms_cf, E.ev1, E.ev3);
+        gpu_ms_total += ms + ms_cf;
         gpu_ms_score += ms_sc;
-        d2h += 2 * sizeof(int) * total;
+        gpu_ms_confirm += ms_cf;
 
-        // ---- fast mode: pick, from the fp32 records, every model that COULD improve the best-minimal state and
-        //      rescore exactly those in fp64.  With count error <= dc and relative score error <= eps (generous
-        //      bounds for fp32 Sampson / reprojection arithmetic on normalised coordinates), a model that truly improves
-        //      the running (count, score) records always passes the test below, so skipping the others is exact.
-        if (mode == 1) {
-            cand_slots.clear();
-            const double eps = 1e-3;
-            for (int a = 0; a < na; ++a) {
-                PState &S = PS[act[a]];
-                double LB = (double)S.best_minimal_inlier_count; // lower bound of the true running max count
-                double UB = S.best_minimal_msac_score;           // upper bound of the true running min score
-                for (size_t s = 0; s < S.B; ++s) {
-                    const int nm = E.h_n_models.p[S.g0 + s];
-                    const size_t first = (size_t)E.h_first_slot.p[S.g0 + s];
-                    for (int m = 0; m < nm; ++m) {
-                        const size_t slot = first + m;
-                        const double c32 = (double)E.h_fcounts.p[slot], s32 = (double)E.h_fscores.p[slot];
-                        const double dc = 4.0 + 0.01 * c32;
-                        const bool finite = std::isfinite(s32);
-                        const bool cand = !finite || (c32 + dc > LB) || (s32 * (1.0 - eps) < UB);
-                        if (cand) {
-                            cand_slots.push_back((int)slot);
-                            E.is_cand[slot] = 1;
-                        }
-                        if (finite) {
-                            LB = std::max(LB, c32 - dc);
-                            UB = std::min(UB, s32 * (1.0 + eps));
-                        }
-                    }
-                }
-            }
-            const int nc = (int)cand_slots.size();
-            mark(PH_SELECT);
-            if (nc) {
-                if ((rc = E.h_slots.ensure(nc)) || (rc = E.slots.ensure(nc))) return rc;
-                std::copy(cand_slots.begin(), cand_slots.end(), E.h_slots.p);
-                PLB_CUDA(cudaMemcpyAsync(E.slots.p, E.h_slots.p, sizeof(int) * nc, cudaMemcpyHostToDevice, st));
-                PLB_CUDA(cudaEventRecord(E.ev0, st));
-                launch_score_list(kind, E.probs.p, E.models.p, E.model_prob.p, E.slots.p, nc, E.h_counts.d, E.h_scores.d, st);
-                PLB_CUDA(cudaEventRecord(E.ev1, st));
-                E.launches++;
-                if ((rc = sync_timed(nullptr))) return rc;
-                float ms2 = 0.f;
-                cudaEventElapsedTime(&ms2, E.ev0, E.ev1);
-                gpu_ms_total += ms2;
-                gpu_ms_score += ms2;
-                h2d += sizeof(int) * nc;
-                PS[act[0]].cnt.models_confirmed += nc;
-            }
-            mark(PH_WAIT_CONF);
-        }
-
-        // ---- pass 1: which models improve the best-minimal state?  (independent of LO results)
-        int n_imp_tot = 0, n_trig_tot = 0;
+        // ---- replay of the serial loop over this round, problem by problem (ransac_impl.h:106-154,180-188) --------
+        // Only samples with an improving model change the state; between two of them the break test
+        // `it > min_iterations && it > dynamic_max_iter` (:182) first holds at max(min_iterations, dyn) + 1.
         for (int a = 0; a < na; ++a) {
             PState &S = PS[act[a]];
-            S.imp_slot.clear();
-            S.imp_sample.clear();
-            S.trig.clear();
-            size_t bc = S.best_minimal_inlier_count;
-            double bs = S.best_minimal_msac_score;
-            size_t nmod = 0;
-            for (size_t s = 0; s < S.B; ++s) {
-                const int nm = E.h_n_models.p[S.g0 + s];
-                nmod += nm;
-                const size_t first = (size_t)E.h_first_slot.p[S.g0 + s];
-                int last = -1;
-                for (int m = 0; m < nm; ++m) {
-                    const size_t slot = first + m;
-                    if (mode == 1) {
-                        if (!E.is_cand[slot]) continue; // cannot improve (screened out with margins)
-                        E.is_cand[slot] = 0;
-                    }
-                    const size_t ic = E.h_counts.p[slot];
-                    const double sc = E.h_scores.p[slot];
-                    const bool more = ic > bc, better = sc < bs;
-                    if (more || better) {
-                        if (more) bc = ic;
-                        if (better) bs = sc;
-                        S.imp_slot.push_back((int)slot);
-                        S.imp_sample.push_back((int)s);
-                        last = (int)S.imp_slot.size() - 1;
-                    }
-                }
-                if (last >= 0) S.trig.push_back(last);
-            }
-            S.cnt.samples_evaluated += S.B;
-            S.cnt.models_evaluated += nmod;
-            d2h += (sizeof(uint32_t) + sizeof(double)) * nmod;
-            S.imp_base = n_imp_tot;
-            S.trig_base = n_trig_tot;
-            n_imp_tot += (int)S.imp_slot.size();
-            n_trig_tot += (int)S.trig.size();
-        }
-        mark(PH_PASS1);
-        if (n_imp_tot > 0) {
-            // gather the improving models of every problem, refine the trigger models in one batched LM launch
-            const int ng = n_imp_tot + n_trig_tot;
-            if ((rc = E.h_slots.ensure(ng)) || (rc = E.slots.ensure(ng)) || (rc = E.lm_in.ensure(9 * (size_t)ng)) ||
-                (rc = E.h_lm_in.ensure(9 * (size_t)n_imp_tot)) || (rc = E.h_jobs.ensure(n_trig_tot)) ||
-                (rc = E.subset.ensure((size_t)n_trig_tot * max_n_pad)))
-                return rc;
-            for (int a = 0; a < na; ++a) {
-                PState &S = PS[act[a]];
-                for (size_t i = 0; i < S.imp_slot.size(); ++i) E.h_slots.p[S.imp_base + i] = S.imp_slot[i];
-                for (size_t j = 0; j < S.trig.size(); ++j) {
-                    E.h_slots.p[n_imp_tot + S.trig_base + j] = S.imp_slot[S.trig[j]];
-                    make_lo_job(E.h_jobs.p[S.trig_base + j], S, (long long)(S.trig_base + j) * max_n_pad);
-                }
-            }
-            PLB_CUDA(cudaMemcpyAsync(E.slots.p, E.h_slots.p, sizeof(int) * ng, cudaMemcpyHostToDevice, st));
-            h2d += sizeof(int) * ng;
-            k_gather_models<<<(9 * ng + 127) / 128, 128, 0, st>>>(E.models.p, E.slots.p, ng, MSZ, E.lm_in.p);
-            E.launches++;
-            PLB_CUDA(cudaMemcpyAsync(E.h_lm_in.p, E.lm_in.p, sizeof(double) * 9 * n_imp_tot, cudaMemcpyDeviceToHost, st));
-            d2h += sizeof(double) * 9 * n_imp_tot;
-            if ((rc = launch_lm_jobs(n_trig_tot, true, 9 * (size_t)n_imp_tot))) return rc;
-            if ((rc = sync_timed(&lo_wait))) return rc;
-        }
-        mark(PH_WAIT_LM);
-
-        // ---- pass 2: replay the serial loop over this round, problem by problem -----------------------------------
-        for (int a = 0; a < na; ++a) {
-            PState &S = PS[act[a]];
+            first_round[act[a]] = 0;
             const plb_ransac_opt &opt = S.t->opt;
-            const int n_imp = (int)S.imp_slot.size();
+            const SelHeader &H = E.h_hdr.p[a];
+            const ImpRec *imp = E.h_imp.p + H.imp_base;
+            const LmJobOut *lo = E.h_lm_out.p + H.trig_base;
+            d2h += sizeof(SelHeader) + sizeof(ImpRec) * (size_t)H.n_imp + sizeof(LmJobOut) * (size_t)H.n_trig;
+            S.cnt.samples_evaluated += S.B;
+            S.cnt.models_evaluated += (uint64_t)H.n_models;
+            S.cnt.models_confirmed += (mode == 1) ? (uint64_t)H.n_cand : 0;
+            S.chunk = std::min(CHUNK_MAX, S.chunk * 2);
+            const size_t it0 = S.it, it_end = S.it + S.B;
             int ip = 0, tp = 0;
-            for (size_t s = 0; s < S.B; ++s, ++S.it) {
-                if (S.it > opt.min_iterations && S.it > S.dynamic_max_iter) { // ransac_impl.h:182-184
-                    S.broke = true;
-                    S.active = false;
+            size_t cur = it0;
+            bool broke = false;
+            for (;;) {
+                const size_t next_trig = (ip < H.n_imp) ? it0 + (size_t)imp[ip].sample : it_end;
+                const size_t brk = std::max(cur, std::max<size_t>(opt.min_iterations, S.dynamic_max_iter) + 1);
+                if (brk <= next_trig && brk < it_end) { // the loop leaves at the top of iteration `brk`
+                    cur = brk;
+                    broke = true;
                     break;
                 }
-                S.cnt.samples++;
-                S.cnt.hypotheses += E.h_n_models.p[S.g0 + s];
-                bool any = false;
-                while (ip < n_imp && S.imp_sample[ip] == (int)s) {
-                    const size_t slot = S.imp_slot[ip];
-                    const size_t ic = E.h_counts.p[slot];
-                    const double sc = E.h_scores.p[slot];
-                    // (more_inliers || better_score) holds by construction; state update as in :117-124
+                if (next_trig >= it_end) {
+                    cur = it_end;
+                    break;
+                }
+                // iteration next_trig: its improving models in order (ransac_impl.h:113-133), then LO (:135-153)
+                const int smp = imp[ip].sample;
+                while (ip < H.n_imp && imp[ip].sample == smp) {
+                    const size_t ic = imp[ip].count;
+                    const double sc = imp[ip].score;
                     if (ic > S.best_minimal_inlier_count) S.best_minimal_inlier_count = ic;
                     if (sc < S.best_minimal_msac_score) S.best_minimal_msac_score = sc;
                     if (sc < S.stats.model_score) { // :127-131
                         S.stats.model_score = sc;
-                        const double *m = E.h_lm_in.p + 9 * (size_t)(S.imp_base + ip);
-                        std::copy(m, m + MSZ, S.best_model);
+                        std::copy(imp[ip].model, imp[ip].model + MSZ, S.best_model);
                         S.stats.num_inliers = ic;
                     }
-                    any = true;
                     ++ip;
                 }
-                if (any) { // :135-153
-                    const LmJobOut &o = E.h_lm_out.p[S.trig_base + tp++];
-                    S.stats.refinements++;
-                    S.cnt.lo_calls++;
-                    S.cnt.hypotheses++;
-                    if (o.score < S.stats.model_score) {
-                        S.stats.model_score = o.score;
-                        S.stats.num_inliers = o.count;
-                        std::copy(o.model, o.model + MSZ, S.best_model);
-                    }
-                    update_dynamic(S, K);
+                const LmJobOut &o = lo[tp++];
+                S.stats.refinements++;
+                S.cnt.lo_calls++;
+                S.cnt.hypotheses++;
+                if (o.score < S.stats.model_score) {
+                    S.stats.model_score = o.score;
+                    S.stats.num_inliers = o.count;
+                    std::copy(o.model, o.model + MSZ, S.best_model);
                 }
+                update_dynamic(S, K);
+                cur = next_trig + 1;
+            }
+            S.cnt.samples += cur - it0;
+            S.it = cur;
+            if (broke) {
+                S.broke = true;
+                S.active = false;
+                // hypotheses of the samples before the break: one prefix-sum word, fetched behind the round (read at
+                // the end of the call; stream order keeps it ahead of the next round's kernels)
+                if (cur > it0) {
+                    PLB_CUDA(cudaMemcpyAsync(E.h_hypfix.p + S.pidx, E.prefix.p + S.g0 + (cur - it0 - 1), sizeof(int),
+                                             cudaMemcpyDeviceToHost, st));
+                    S.hyp_pending = true;
+                    d2h += sizeof(int);
+                }
+            } else {
+                S.cnt.hypotheses += (uint64_t)H.n_models;
             }
         }
         mark(PH_PASS2);
@@ -1202,7 +1221,7 @@ static int run_refine(int kind, const double *a, const double *b, size_t n_pts, 
     PLB_CUDA(cudaMemcpyAsync(E.jobs.p, E.h_jobs.p, sizeof(LmJob), cudaMemcpyHostToDevice, st));
     PLB_CUDA(cudaMemcpyAsync(E.lm_in.p, E.h_lm_in.p, sizeof(double) * 9, cudaMemcpyHostToDevice, st));
     launch_transpose(E.tdesc.p, 1, n_pad, st);
-    launch_lm(kind, E.probs.p, E.jobs.p, E.lm_in.p, 1, n, nullptr, nullptr, E.h_lm_out.d, st);
+    launch_lm(kind, E.probs.p, E.jobs.p, E.lm_in.p, 1, n, nullptr, nullptr, 0, E.h_lm_out.d, st);
     E.launches += 2;
     PLB_CUDA(cudaStreamSynchronize(st));
     PLB_CUDA(cudaGetLastError());
@@ -1403,6 +1422,71 @@ uint64_t plb_host_dynamic_max_iter(uint64_t num_inliers, uint64_t num_data, uint
     return (uint64_t)compute_dynamic_max_iter((size_t)num_inliers, (size_t)num_data, (size_t)sample_sz,
                                               std::log(1.0 - success_prob), dyn_num_trials_mult, (size_t)min_iterations,
                                               (size_t)max_iterations);
+}
+// The same table drawn by the device sampler (k_sample), `round` samples per launch so that the sampler state is carried
+// from launch to launch as in the engine's rounds; `count` independent samplers with seeds opt->seed + j are drawn in the
+// same launches (one warp each).  out: count * iters * k indices.
+int plb_device_sample_table(uint64_t n, uint32_t k, const plb_ransac_opt *opt, uint64_t iters, uint64_t round,
+                            uint32_t count, uint32_t *out) {
+    if (!opt || !out || k < 3 || k > 7 || n < k || count == 0 || round == 0 || n > (1u << 26) ||
+        iters * (uint64_t)count > (1ull << 28)) {
+        g_err = "bad argument";
+        return PLB_ERR_ARG;
+    }
+    Engine &E = *engine();
+    int rc = E.init();
+    if (rc != PLB_OK) return rc;
+    cudaStream_t st = E.stream;
+    const int NP = (int)count;
+    Sampler host(n, k, *opt);
+    const size_t gsz = opt->progressive_sampling ? host.growth.size() : 0;
+    if ((rc = E.h_smp.ensure(NP)) || (rc = E.smp.ensure(2 * (size_t)NP)) || (rc = E.h_growth.ensure(gsz)) ||
+        (rc = E.growth.ensure(gsz)) || (rc = E.h_rp.ensure(NP)) || (rc = E.rp.ensure(NP)) ||
+        (rc = E.samples.ensure((size_t)NP * round * k)))
+        return rc;
+    bool strict = true;
+    for (size_t j = 0; j < gsz; ++j) {
+        E.h_growth.p[j] = (uint64_t)host.growth[j];
+        if (j >= k && !(host.growth[j] > host.growth[j - 1])) strict = false;
+    }
+    if (const char *e = std::getenv("PLB_PROSAC_SEQUENTIAL")) strict = strict && std::atoi(e) == 0; // test hook
+    for (int i = 0; i < NP; ++i) {
+        SamplerDev &D = E.h_smp.p[i];
+        std::memset(&D, 0, sizeof(D));
+        D.state = opt->seed + (uint64_t)i;
+        D.n = (uint32_t)n;
+        D.k = k;
+        D.max_prosac = opt->max_prosac_iterations;
+        if (opt->progressive_sampling) {
+            D.growth = E.growth.p;
+            D.sample_k = 1;
+            D.subset_sz = k;
+            D.flags = 1u | (strict ? 2u : 0u);
+        }
+    }
+    PLB_CUDA(cudaMemcpyAsync(E.smp.p, E.h_smp.p, sizeof(SamplerDev) * NP, cudaMemcpyHostToDevice, st));
+    if (gsz) PLB_CUDA(cudaMemcpyAsync(E.growth.p, E.h_growth.p, sizeof(uint64_t) * gsz, cudaMemcpyHostToDevice, st));
+    int cur = 0;
+    for (uint64_t done = 0; done < iters; done += round) {
+        const uint64_t B = std::min<uint64_t>(round, iters - done);
+        for (int i = 0; i < NP; ++i) {
+            RoundProb &Q = E.h_rp.p[i];
+            std::memset(&Q, 0, sizeof(Q));
+            Q.pidx = i;
+            Q.g0 = (int)(i * B);
+            Q.B = (int)B;
+        }
+        PLB_CUDA(cudaMemcpyAsync(E.rp.p, E.h_rp.p, sizeof(RoundProb) * NP, cudaMemcpyHostToDevice, st));
+        launch_sample(E.rp.p, NP, E.smp.p + (size_t)cur * NP, E.smp.p + (size_t)(cur ^ 1) * NP, E.samples.p, st);
+        E.launches++;
+        for (int i = 0; i < NP; ++i)
+            PLB_CUDA(cudaMemcpyAsync(out + ((size_t)i * iters + done) * k, E.samples.p + (size_t)i * B * k,
+                                     sizeof(uint32_t) * B * k, cudaMemcpyDeviceToHost, st));
+        PLB_CUDA(cudaStreamSynchronize(st));
+        cur ^= 1;
+    }
+    PLB_CUDA(cudaGetLastError());
+    return PLB_OK;
 }
 int plb_set_mode(int mode) {
     if (mode != 0 && mode != 1) {
@@ -1755,7 +1839,6 @@ int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
     std::string err_msg;
     std::mutex mtx;
     auto work = [&](int tid) {
-        t_sampler_threads = std::max(1, usable_cpus() / nthreads);
         g_device = dev;
         g_engine = pool_engine((size_t)dev * 1024 + tid);
         // static group -> engine mapping: an engine sees the same group shapes on every call of a repeated workload,

@@ -1140,6 +1140,8 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
             else st += (float)n * thr; // the per-correspondence sums hold (r2 - thr) of the inliers only
             out.fcounts[seg + m0 + tid] = ct;
             out.fscores[seg + m0 + tid] = st;
+            out.fborder[seg + m0 + tid] = 5u + ct / 100u;
+            out.ferr[seg + m0 + tid] = 1e-3f * st;
         }
     }
     } // problems of this CTA
@@ -1165,6 +1167,33 @@ __global__ void __launch_bounds__(SCORE_THREADS, 4)
         if (threadIdx.x == 0) {
             counts[m] = cnt;
             scores[m] = score;
+        }
+    }
+}
+
+// fast mode confirmation driven by the device-side candidate lists of k_select: CTA (x, a) rescores the candidates
+// x, x + gridDim.x, ... of active problem a in fp64 (same cta_score routine, hence the same bits, as everywhere else).
+template <int KIND>
+__global__ void __launch_bounds__(SCORE_THREADS, 4)
+    k_confirm(const ProblemDev *__restrict__ probs, const SelectArgs A, const double *__restrict__ models) {
+    constexpr int MSZ = kind_model_size(KIND);
+    __shared__ ScoreRed red;
+    const int a = blockIdx.y;
+    const int nc = A.n_cand[a];
+    if ((int)blockIdx.x >= nc) return;
+    const RoundProb R = A.rp[a];
+    const ProblemDev P = probs[R.pidx];
+    for (int j = blockIdx.x; j < nc; j += gridDim.x) {
+        const int m = A.cand_slot[R.seg_base + j];
+        double mdl[MSZ];
+#pragma unroll
+        for (int k = 0; k < MSZ; ++k) mdl[k] = models[(size_t)m * MSZ + k];
+        uint32_t cnt;
+        double score;
+        cta_score<KIND>(P, mdl, P.sq_thr, &red, cnt, score);
+        if (threadIdx.x == 0) {
+            A.counts[m] = cnt;
+            A.scores[m] = score;
         }
     }
 }
@@ -1304,6 +1333,21 @@ void launch_score_list(int kind, const ProblemDev *probs, const double *models, 
     case KIND_FUND: k_score_list<KIND_FUND><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
     case KIND_RELPOSE_TS: k_score_list<KIND_RELPOSE_TS><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
     default: k_score_list<KIND_HOMOG><<<blocks, SCORE_THREADS, 0, stream>>>(probs, models, model_prob, slots, n_slots, counts, scores); break;
+    }
+}
+
+void launch_confirm(int kind, const ProblemDev *probs, const SelectArgs &A, const double *models, cudaStream_t stream) {
+    if (A.na <= 0) return;
+    int gx = (8 * sm_count() + A.na - 1) / A.na;
+    if (gx > 64) gx = 64;
+    if (gx < 1) gx = 1;
+    const dim3 grid((unsigned)gx, (unsigned)A.na, 1);
+    switch (kind) {
+    case KIND_PNP: k_confirm<KIND_PNP><<<grid, SCORE_THREADS, 0, stream>>>(probs, A, models); break;
+    case KIND_RELPOSE: k_confirm<KIND_RELPOSE><<<grid, SCORE_THREADS, 0, stream>>>(probs, A, models); break;
+    case KIND_FUND: k_confirm<KIND_FUND><<<grid, SCORE_THREADS, 0, stream>>>(probs, A, models); break;
+    case KIND_RELPOSE_TS: k_confirm<KIND_RELPOSE_TS><<<grid, SCORE_THREADS, 0, stream>>>(probs, A, models); break;
+    default: k_confirm<KIND_HOMOG><<<grid, SCORE_THREADS, 0, stream>>>(probs, A, models); break;
     }
 }
 
@@ -1952,8 +1996,9 @@ template <int NP> PLB_DEV void llt_solve(const double *A, const double *rhs, dou
 // if accepted, the Jacobian at the same parameters in a second pass; here both come from one pass.
 template <int KIND>
 __global__ void __launch_bounds__(LM_THREADS)
-    k_lm(const ProblemDev *__restrict__ probs, const LmJob *__restrict__ jobs, const double *__restrict__ models_in,
-         const char *mask_base, int *idx_scratch, LmJobOut *outs) {
+    k_lm(const ProblemDev *__restrict__ probs, const LmJob *__restrict__ jobs, const LoJobSrc *__restrict__ job_src,
+         const double *__restrict__ models_in, const int *__restrict__ n_jobs_dev, int n_jobs, const char *mask_base,
+         int *idx_scratch, int scratch_stride, LmJobOut *outs) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int NP = LmDims<KIND>::NP;
@@ -1961,19 +2006,28 @@ __global__ void __launch_bounds__(LM_THREADS)
     constexpr int MSZ = kind_model_size(KIND);
     __shared__ LmShared S;
     const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
-    const int job = blockIdx.x / csize;
-    const LmJob &J = jobs[job];
+    // The grid is a set of clusters that walk the job list: explicit jobs (jobs[j], model j of models_in, stride 9) or
+    // the LO jobs k_pass1 listed on the device (template jobs[job_src[j].pidx], model slot job_src[j].slot of the
+    // round's model list, stride MSZ; the count is read from device memory and clamped to n_jobs).
+    const int n_clusters = (int)gridDim.x / csize, cluster_id = (int)blockIdx.x / csize;
+    int nj = n_jobs;
+    if (n_jobs_dev) {
+        const int v = *n_jobs_dev;
+        if (v < nj) nj = v;
+    }
+    int buf = 0;
+    for (int job = cluster_id; job < nj; job += n_clusters) {
+    const LmJob &J = job_src ? jobs[job_src[job].pidx] : jobs[job];
     const ProblemDev P = probs[J.pidx];
     const LmParams prm = J.prm;
     const char *mask_in = (J.mask_off >= 0) ? mask_base + J.mask_off : nullptr;
-    const double *min = models_in + (size_t)job * 9;
+    const double *min = job_src ? models_in + (size_t)job_src[job].slot * MSZ : models_in + (size_t)job * 9;
     LmJobOut *out = outs + job;
     LossFn L;
     L.type = prm.loss_type;
     L.thr = prm.loss_scale;
     L.sq_thr = prm.loss_scale * prm.loss_scale;
     L.inv_sq_thr = 1.0 / L.sq_thr;
-    int buf = 0;
 
     // ---- this CTA's slice and its active-point list ------------------------------------------------------------
     const int chunk = (((P.n + csize - 1) / csize) + 31) & ~31;
@@ -1982,7 +2036,7 @@ __global__ void __launch_bounds__(LM_THREADS)
     const int *list = nullptr;
     bool untouched = false;
     if (prm.subset_mode != 0) {
-        int *mylist = idx_scratch + J.scratch_off + lo;
+        int *mylist = idx_scratch + (size_t)cluster_id * (size_t)scratch_stride + lo;
         ModelCtx<KIND_RELPOSE> C;
         if (KIND == KIND_RELPOSE && prm.subset_mode == 1) C.init(min);
         const double *M = reinterpret_cast<const double *>(&C);
@@ -2167,12 +2221,11 @@ __global__ void __launch_bounds__(LM_THREADS)
             out->score = score;
         }
     }
-    cluster.sync(); // no CTA may exit while a sibling can still read its shared memory
+    cluster.sync(); // no CTA may exit (or start the next job) while a sibling can still read its shared memory
+    } // jobs of this cluster
 }
 
-template <int KIND>
-static void launch_lm_t(const ProblemDev *probs, const LmJob *jobs, const double *models_in, int n_jobs, int max_n,
-                        const char *mask_base, int *idx_scratch, LmJobOut *out, cudaStream_t stream) {
+static int lm_cluster_size(int n_jobs, int max_n) {
     static const int per_cta = [] { // correspondences per CTA before another CTA of the cluster pays off
         const char *e = std::getenv("PLB_LM_PER_CTA");
         const int v = e ? std::atoi(e) : 0;
@@ -2186,9 +2239,15 @@ static void launch_lm_t(const ProblemDev *probs, const LmJob *jobs, const double
     // k_lm needs the whole register file of an SM per CTA: with many jobs in one launch (batch groups) wide clusters
     // only take SMs away from the co-running hypothesis kernels, so the cluster shrinks as the job count grows
     while (csize > 1 && n_jobs * csize > sm_count() / 2) csize /= 2;
+    return csize;
+}
+template <int KIND>
+static void launch_lm_t(const ProblemDev *probs, const LmJob *jobs, const LoJobSrc *job_src, const double *models_in,
+                        const int *n_jobs_dev, int n_jobs, int n_clusters, int csize, const char *mask_base,
+                        int *idx_scratch, int scratch_stride, LmJobOut *out, cudaStream_t stream) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(n_jobs * csize), 1, 1);
+    cfg.gridDim = dim3((unsigned)(n_clusters * csize), 1, 1);
     cfg.blockDim = dim3(LM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
@@ -2199,18 +2258,44 @@ static void launch_lm_t(const ProblemDev *probs, const LmJob *jobs, const double
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_lm<KIND>, probs, jobs, models_in, mask_base, idx_scratch, out);
+    cudaLaunchKernelEx(&cfg, k_lm<KIND>, probs, jobs, job_src, models_in, n_jobs_dev, n_jobs, mask_base, idx_scratch,
+                       scratch_stride, out);
+}
+static void launch_lm_any(int kind, const ProblemDev *probs, const LmJob *jobs, const LoJobSrc *job_src,
+                          const double *models_in, const int *n_jobs_dev, int n_jobs, int n_clusters, int csize,
+                          const char *mask_base, int *idx_scratch, int scratch_stride, LmJobOut *out, cudaStream_t stream) {
+    switch (kind) {
+    case KIND_PNP: launch_lm_t<KIND_PNP>(probs, jobs, job_src, models_in, n_jobs_dev, n_jobs, n_clusters, csize, mask_base, idx_scratch, scratch_stride, out, stream); break;
+    case KIND_RELPOSE: launch_lm_t<KIND_RELPOSE>(probs, jobs, job_src, models_in, n_jobs_dev, n_jobs, n_clusters, csize, mask_base, idx_scratch, scratch_stride, out, stream); break;
+    case KIND_FUND: launch_lm_t<KIND_FUND>(probs, jobs, job_src, models_in, n_jobs_dev, n_jobs, n_clusters, csize, mask_base, idx_scratch, scratch_stride, out, stream); break;
+    case KIND_RELPOSE_TS: launch_lm_t<KIND_RELPOSE_TS>(probs, jobs, job_src, models_in, n_jobs_dev, n_jobs, n_clusters, csize, mask_base, idx_scratch, scratch_stride, out, stream); break;
+    default: launch_lm_t<KIND_HOMOG>(probs, jobs, job_src, models_in, n_jobs_dev, n_jobs, n_clusters, csize, mask_base, idx_scratch, scratch_stride, out, stream); break;
+    }
 }
 void launch_lm(int kind, const ProblemDev *probs, const LmJob *jobs_dev, const double *models_in, int n_jobs,
-               int max_n, const char *mask_base, int *idx_scratch, LmJobOut *out, cudaStream_t stream) {
+               int max_n, const char *mask_base, int *idx_scratch, int scratch_stride, LmJobOut *out, cudaStream_t stream) {
     if (n_jobs <= 0) return;
-    switch (kind) {
-    case KIND_PNP: launch_lm_t<KIND_PNP>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
-    case KIND_RELPOSE: launch_lm_t<KIND_RELPOSE>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
-    case KIND_FUND: launch_lm_t<KIND_FUND>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
-    case KIND_RELPOSE_TS: launch_lm_t<KIND_RELPOSE_TS>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
-    default: launch_lm_t<KIND_HOMOG>(probs, jobs_dev, models_in, n_jobs, max_n, mask_base, idx_scratch, out, stream); break;
-    }
+    const int csize = lm_cluster_size(n_jobs, max_n);
+    launch_lm_any(kind, probs, jobs_dev, nullptr, models_in, nullptr, n_jobs, n_jobs, csize, mask_base, idx_scratch,
+                  scratch_stride, out, stream);
+}
+// Clusters of a round's LO launch: at most one wave (a k_lm CTA owns an SM), at most the estimated number of jobs.
+int lm_round_max_clusters(int kind, int est_jobs, int max_n) {
+    (void)kind;
+    if (est_jobs < 1) est_jobs = 1;
+    const int csize = lm_cluster_size(est_jobs, max_n);
+    int nc = sm_count() / csize;
+    if (nc > est_jobs) nc = est_jobs;
+    return nc < 1 ? 1 : nc;
+}
+void launch_lm_round(int kind, const ProblemDev *probs, const LmJob *tmpl, const LoJobSrc *job_src,
+                     const double *models, const int *n_jobs_dev, int job_cap, int est_jobs, int max_n,
+                     int *idx_scratch, int scratch_stride, LmJobOut *out, cudaStream_t stream) {
+    if (est_jobs < 1) est_jobs = 1;
+    const int csize = lm_cluster_size(est_jobs, max_n);
+    const int nc = lm_round_max_clusters(kind, est_jobs, max_n);
+    launch_lm_any(kind, probs, tmpl, job_src, models, n_jobs_dev, job_cap, nc, csize, nullptr, idx_scratch, scratch_stride,
+                  out, stream);
 }
 
 // ============================================================================================================

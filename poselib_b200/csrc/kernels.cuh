@@ -47,7 +47,7 @@ struct RoundDesc {
 // Per-round output of the hypothesis kernels.  Every active problem a owns the slot segment
 // [seg_base[a], seg_base[a] + seg_cap[a]) of models / model_prob / counts / scores and fills it from the front
 // (prob_count[a] models); sample g owns slots [first_slot[g], first_slot[g] + n_models[g]) inside its problem's segment.
-// n_models, first_slot, counts and scores point to mapped pinned host memory (written straight over PCIe).
+// Everything stays in HBM: the ordered scans of k_select / k_pass1 reduce it to the few records the host replays.
 struct HypOut {
     int *n_models;
     int *first_slot;
@@ -60,13 +60,94 @@ struct HypOut {
     double *scores;
     double *models;
     int *model_prob;  // problem index of every model slot
-    uint32_t *fcounts; // fast mode: fp32 screening records (mapped pinned host memory)
+    uint32_t *fcounts; // fast mode: fp32 screening records
     float *fscores;
+    uint32_t *fborder; // fast mode: correspondences whose fp32 inlier decision is within the error bound of the test
+    float *ferr;       // fast mode: bound of |score32 - score64|
     // relpose_5pt phase buffers (device), sized for the round's n_total samples:
     double *s5_blk;   // per sample 105 doubles: A (39) | Nb (36) | sample bearings x1s,x2s (30)
     double *s5_cpoly; // 11 x n_total, coefficient-major (cpoly[c * n_total + g])
     double *s5_roots; // per sample 10 doubles
     int *s5_nroots;   // per sample
+};
+
+// ---- device-side control of a round (sampling, candidate selection, best-minimal reduction) -----------------------
+// RandomSampler state of one problem (robust/sampling.h:49-83), kept in HBM across the rounds of a group.
+struct SamplerDev {
+    uint64_t state;        // splitmix64 state (sampling.h:73)
+    uint64_t sample_k;     // PROSAC: samples drawn so far + 1 (sampling.cc:91)
+    uint64_t max_prosac;   // RansacOptions::max_prosac_iterations
+    const uint64_t *growth; // PROSAC growth function, n entries (sampling.cc:105-136), or null
+    uint32_t subset_sz;    // PROSAC: current subset size
+    uint32_t n, k;         // num_data, sample size
+    uint32_t flags;        // bit 0: PROSAC, bit 1: growth[] strictly increasing from k-1 on (closed-form subset size)
+};
+// One active problem of a round.
+struct RoundProb {
+    int pidx;     // index into probs[] / sampler states / LO job templates
+    int g0, B;    // its samples are g0 .. g0+B-1 of the round's sample table
+    int seg_base, seg_cap; // its segment of the model list
+    int reserved;
+    double lb0;   // best_minimal_inlier_count at the start of the round (ransac_impl.h:99-104)
+    double ub0;   // best_minimal_msac_score at the start of the round
+};
+// Per active problem, written by k_pass1 into mapped pinned host memory: what the host needs to replay score_models().
+struct SelHeader {
+    int n_models;  // models generated by the round's samples (incl. samples past the serial break point)
+    int n_cand;    // fast mode: models the fp32 records could not rule out (rescored in fp64)
+    int n_imp;     // models that improve the best-minimal state, in (sample, model) order
+    int imp_base;  // first ImpRec of this problem
+    int n_trig;    // samples with at least one improving model = LO jobs of this problem
+    int trig_base; // first LmJobOut of this problem
+};
+struct ImpRec {
+    int sample;      // sample index inside the round (0-based)
+    uint32_t count;  // exact inlier count
+    double score;    // exact MSAC score
+    double model[9];
+};
+struct LoJobSrc {
+    int pidx;  // LO job template (per problem)
+    int slot;  // model slot in the round's model list
+};
+// round control words in device memory (ints)
+enum { CTL_QUEUE = 0, CTL_OVERFLOW = 2, CTL_NW = 4, CTL_IMP_TOTAL = 5, CTL_JOB_TOTAL = 6, CTL_FLAGS = 7, CTL_WORDS = 8 };
+enum { FLAG_IMP_OVERFLOW = 1, FLAG_JOB_OVERFLOW = 2 };
+
+struct SelectArgs {
+    const RoundProb *rp;
+    int na;
+    int mode;                // 0: exact records (counts/scores) for every model; 1: fp32 screening records
+    const int *n_models;     // per sample
+    const int *first_slot;   // per sample
+    const uint32_t *fcounts; // fast mode, per model slot: fp32 inlier count
+    const float *fscores;    //   fp32 MSAC score
+    const uint32_t *fborder; //   number of correspondences whose fp32 inlier decision is not certain
+    const float *ferr;       //   bound of |score32 - score64|
+    uint32_t *counts;        // exact records per model slot (mode 0: input; mode 1: filled by k_confirm for candidates)
+    double *scores;
+    int *prefix;             // out, per sample: inclusive prefix sum of n_models inside its problem
+    int *cand_slot;          // out, per problem segment: candidate slots in (sample, model) order
+    int *cand_sample;        // out, same layout: their sample index inside the round
+    int *n_cand;             // out, per active problem
+    int *n_models_tot;       // out, per active problem
+};
+struct Pass1Args {
+    const RoundProb *rp;
+    int na;
+    int *cand_slot;          // in/out: compacted in place to the improving models
+    int *cand_sample;
+    const int *n_cand;
+    const int *n_models_tot;
+    const uint32_t *counts;
+    const double *scores;
+    const double *models;
+    int msz;
+    int *ctl;
+    int imp_cap, job_cap;
+    SelHeader *hdr;          // mapped pinned host memory
+    ImpRec *imp;             // mapped pinned host memory
+    LoJobSrc *job_src;       // device
 };
 
 // LM (local optimisation / final polish) job description — mirrors BundleOptions (types.h:60-95)
@@ -131,7 +212,24 @@ void launch_score_models(int kind, const ProblemDev *probs, const double *models
                          const int *n_models_dev, uint32_t *counts, double *scores, cudaStream_t stream);
 // LM refinement: one thread-block cluster per job.  models_in: n_jobs * 9 doubles.
 void launch_lm(int kind, const ProblemDev *probs, const LmJob *jobs_dev, const double *models_in, int n_jobs,
-               int max_n, const char *mask_base, int *idx_scratch, LmJobOut *out, cudaStream_t stream);
+               int max_n, const char *mask_base, int *idx_scratch, int scratch_stride, LmJobOut *out, cudaStream_t stream);
+// LO jobs of a round, listed on the device by k_pass1: job j refines model slot job_src[j].slot of the round's model
+// list (stride MSZ) with the template tmpl[job_src[j].pidx]; *n_jobs_dev jobs.  A persistent grid of clusters walks the
+// list; est_jobs (host estimate) only sizes the clusters / the grid.
+void launch_lm_round(int kind, const ProblemDev *probs, const LmJob *tmpl, const LoJobSrc *job_src,
+                     const double *models, const int *n_jobs_dev, int job_cap, int est_jobs, int max_n,
+                     int *idx_scratch, int scratch_stride, LmJobOut *out, cudaStream_t stream);
+int lm_round_max_clusters(int kind, int est_jobs, int max_n);
+// Device-side sampling of a round: one warp per active problem draws its B samples into samples[(g0+s)*K ..] from
+// st_in[pidx] and leaves the advanced state in st_out[pidx] (robust/sampling.cc:46-61,85-103).
+void launch_sample(const RoundProb *rp, int na, const SamplerDev *st_in, SamplerDev *st_out, uint32_t *samples,
+                   cudaStream_t stream);
+// Ordered scan over the round's models per problem: which models could improve the best-minimal state.
+void launch_select(const SelectArgs &A, cudaStream_t stream);
+// fast mode: exact fp64 rescoring of the candidates k_select listed.
+void launch_confirm(int kind, const ProblemDev *probs, const SelectArgs &A, const double *models, cudaStream_t stream);
+// Exact pass over the candidates: improving models, LO triggers, records for the host replay.
+void launch_pass1(const Pass1Args &A, cudaStream_t stream);
 // Final inlier masks (robust/utils.cc:331-351,374-383,434-513): one descriptor per mask, sq_thr from the problem.
 void launch_inlier_masks(int kind, const ProblemDev *probs, const MaskDesc *descs_dev, int n_desc, int max_n,
                          char *mask_base, cudaStream_t stream);
