@@ -110,8 +110,10 @@ void plb_bundle_opt_default(plb_bundle_opt *o);
 const char *plb_last_error(void);
 int plb_device_count(void);          /* CUDA devices visible; 0 if none / driver missing */
 int plb_set_device(int device);      /* device used by subsequent calls from this thread */
-/* precision mode: 0 = exact (fp64 scoring of every hypothesis), 1 = fast (fp32 SMEM-resident screening of
- * every hypothesis + fp64 confirmation of every candidate that could change the RANSAC state; same results) */
+/* precision mode of the calling thread (batch workers inherit it): 1 = fast, the DEFAULT (fp32 SMEM-resident screening
+ * of every hypothesis with a rigorous error interval per model + fp64 confirmation of every model whose interval could
+ * change the RANSAC state; results identical to mode 0), 0 = exact (fp64 scoring of every hypothesis).  The environment
+ * variable PLB_MODE=0 changes the default. */
 int plb_set_mode(int mode);
 
 /* ---- host-side pieces of the loop; no device needed (exercised by the CPU test-suite) ---------------------
@@ -213,8 +215,14 @@ typedef struct plb_problem {
     int32_t status;           /* out: PLB_OK / error */
     int32_t resident;         /* > 0: handle from plb_resident_create, a/b are ignored (points already in HBM) */
 } plb_problem;
-/* Runs ransac_{pnp,relpose,fundamental,homography} on every problem; `streams` problems are in flight at once. */
+/* Runs ransac_{pnp,relpose,fundamental,homography} on every problem on the calling thread's device; `streams` lock-step
+ * groups of problems are in flight at once. */
 int plb_ransac_batch(plb_problem *problems, size_t count, int streams);
+/* The same over the first n_gpus CUDA devices of the process (0 = all of them), in one call from one host thread:
+ * problems are partitioned by size x expected iterations, every device runs streams_per_gpu groups at once, results
+ * (stats, models, inlier masks) are written straight into the caller's array.  No collective: image pairs are
+ * independent (robust/ransac.cc:144-148).  Resident inputs stay on the device that holds them. */
+int plb_ransac_batch_multi(plb_problem *problems, size_t count, int n_gpus, int streams_per_gpu);
 
 /* Correspondences kept resident in HBM across calls (measurement of the device-resident throughput, and callers
  * that run several estimations on the same matches).  kind: PLB_KIND_*; returns a handle > 0 or an error < 0. */

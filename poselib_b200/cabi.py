@@ -95,7 +95,7 @@ EXPORTS = [
     "plb_ransac_homography",
     "plb_estimate_absolute_pose", "plb_estimate_relative_pose", "plb_estimate_fundamental",
     "plb_estimate_homography", "plb_p3p_batch", "plb_relpose_5pt_batch", "plb_relpose_5pt_poses_batch",
-    "plb_relpose_7pt_batch", "plb_homography_4pt_batch", "plb_ransac_batch", "plb_bundle_adjust",
+    "plb_relpose_7pt_batch", "plb_homography_4pt_batch", "plb_ransac_batch", "plb_ransac_batch_multi", "plb_bundle_adjust",
     "plb_refine_relpose", "plb_refine_relpose_cameras", "plb_refine_fundamental", "plb_refine_homography", "plb_resident_create",
     "plb_resident_free",
 ]
@@ -320,9 +320,10 @@ def resident_free(h):
 
 
 # ---- batch of problems -------------------------------------------------------------------------------
-def ransac_batch(problems, streams=8):
+def ransac_batch(problems, streams=8, n_gpus=None):
     """problems: list of dict(kind, a, b, ransac=RansacOpt, max_error, rfc=False, init=None).
-    Returns list of dict(model, inliers, stats, counters)."""
+    n_gpus=None: plb_ransac_batch on the current device; an int: plb_ransac_batch_multi over that many devices of this
+    process (0 = all).  Returns list of dict(model, inliers, stats, counters)."""
     count = len(problems)
     arr = (Problem * count)()
     keep = []
@@ -348,7 +349,10 @@ def ransac_batch(problems, streams=8):
         for k in range(len(m)):
             q.model[k] = m[k]
         q.inliers = C.cast(mask.ctypes.data_as(C.POINTER(C.c_char)), C.c_char_p)
-    _check(_lib.plb_ransac_batch(arr, C.c_size_t(count), int(streams)))
+    if n_gpus is None:
+        _check(_lib.plb_ransac_batch(arr, C.c_size_t(count), int(streams)))
+    else:
+        _check(_lib.plb_ransac_batch_multi(arr, C.c_size_t(count), int(n_gpus), int(streams)))
     out = []
     for i, p in enumerate(problems):
         q = arr[i]

@@ -18,6 +18,10 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <map>
+#include <memory>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -32,7 +36,17 @@ namespace plb {
 
 static thread_local std::string g_err;
 static thread_local int g_device = 0;
-static std::atomic<int> g_mode{0};
+// precision mode of the calling thread (plb_set_mode): 1 = fast (fp32 screening with rigorous error intervals + fp64
+// confirmation; same results as 0 = exact, fp64 scoring of every model).  Batch workers inherit the caller's mode.
+static int default_mode() {
+    static const int m = [] {
+        const char *e = std::getenv("PLB_MODE");
+        return (e && std::atoi(e) == 0) ? 0 : 1;
+    }();
+    return m;
+}
+static thread_local int g_mode = -1; // -1: not set by this thread -> default_mode()
+static int current_mode() { return g_mode < 0 ? default_mode() : g_mode; }
 
 #define PLB_CUDA(expr)                                                                                              \
     do {                                                                                                            \
@@ -194,7 +208,7 @@ struct Engine {
     int device = -1;
     DevBuf<double> in, soa64, px64, models, lm_in, s5_blk, s5_cpoly, s5_roots;
     DevBuf<int> s5_nroots;
-    DevBuf<float> soa32;
+    DevBuf<float> soa32, cmax;
     DevBuf<uint32_t> samples;
     DevBuf<int> work, slots, subset, act, model_prob, prob_count;
     // round state that stays on the device: sampler states, per-sample / per-model records, candidate lists
@@ -213,13 +227,14 @@ struct Engine {
     PinBuf<LmJob> h_lo_tmpl;
     PinBuf<int> h_hypfix;
     DevBuf<char> mask;
+    DevBuf<uint32_t> mask_bits;
+    PinBuf<uint32_t> h_mask_bits;
     DevBuf<ProblemDev> probs;
     DevBuf<TransposeDesc> tdesc;
     DevBuf<MaskDesc> mdesc;
     DevBuf<LmJob> jobs;
     PinBuf<double> h_in, h_lm_in;
     PinBuf<int> h_slots, h_act, h_work;
-    PinBuf<char> h_mask;
     PinBuf<ProblemDev> h_probs;
     PinBuf<TransposeDesc> h_tdesc;
     PinBuf<MaskDesc> h_mdesc;
@@ -265,10 +280,70 @@ struct Engine {
         return PLB_OK;
     }
 };
-static thread_local Engine *g_engine = nullptr;
+// One engine (stream, events, grow-only buffers) per host thread AND device: a thread that switches devices with
+// plb_set_device gets a separate engine for each, so streams and buffers never cross devices.  Engines live as long as
+// the process (buffers are reused across calls).
+static thread_local std::map<int, Engine *> *g_engines = nullptr;
 static Engine *engine() {
-    if (!g_engine) g_engine = new Engine(); // lives as long as the process (buffers are reused across calls)
-    return g_engine;
+    if (!g_engines) g_engines = new std::map<int, Engine *>();
+    Engine *&e = (*g_engines)[g_device];
+    if (!e) e = new Engine();
+    return e;
+}
+
+// Persistent worker threads of the batch entry points (created on first use, grown on demand).  Worker w of a dispatch
+// always runs job w, so a repeated workload meets the same engine with the same group shapes (no reallocation after the
+// first call).  Dispatches are serialised: concurrent callers of plb_ransac_batch queue up instead of sharing engines.
+class WorkerPool {
+  public:
+    void run(int n, const std::function<void(int)> &fn) {
+        std::lock_guard<std::mutex> dispatch(dispatch_mtx_);
+        if (n <= 0) return;
+        {
+            std::unique_lock<std::mutex> lk(mtx_);
+            while ((int)threads_.size() < n) {
+                const int id = (int)threads_.size();
+                threads_.emplace_back([this, id] { loop(id); });
+            }
+            fn_ = &fn;
+            n_ = n;
+            pending_ = n;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> lk(mtx_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)> *fn = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mtx_);
+                cv_.wait(lk, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (id < n_) fn = fn_;
+            }
+            if (fn) {
+                (*fn)(id);
+                std::unique_lock<std::mutex> lk(mtx_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::mutex dispatch_mtx_, mtx_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> threads_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int n_ = 0, pending_ = 0;
+    uint64_t epoch_ = 0;
+};
+static WorkerPool &worker_pool() {
+    static WorkerPool *p = new WorkerPool(); // never destroyed: its threads outlive static destruction
+    return *p;
 }
 // host cores this process may use: affinity mask, capped by the cgroup CPU quota (containers / shared hosts)
 static int usable_cpus() {
@@ -291,23 +366,14 @@ static int usable_cpus() {
     return cached;
 }
 
-// engines of the batch worker threads, reused across plb_ransac_batch calls
-static std::mutex g_pool_mtx;
-static std::vector<Engine *> g_pool;
-static Engine *pool_engine(size_t i) {
-    std::lock_guard<std::mutex> lk(g_pool_mtx);
-    while (g_pool.size() <= i) g_pool.push_back(new Engine());
-    return g_pool[i];
-}
-
 // correspondences resident in HBM (plb_resident_create)
 struct Resident {
     DevBuf<double> soa64;
-    DevBuf<float> soa32;
+    DevBuf<float> soa32, cmax;
     int n = 0, n_pad = 0, kind = 0, device = 0;
 };
 static std::mutex g_res_mtx;
-static std::vector<Resident *> g_resident; // handle = index + 1
+static std::vector<std::shared_ptr<Resident>> g_resident; // handle = index + 1; calls in flight hold a reference
 
 // LO bundle options of the estimators (estimators/absolute_pose.cc:60-69 etc.): TRUNCATED(max_error), 25 iterations
 static LmParams lo_params(int kind, double max_error) {
@@ -500,8 +566,9 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
     }
     const int n_probdev = NP + n_polish_pnp;
     if ((rc = E.h_in.ensure(in_doubles + px_elems)) || (rc = E.in.ensure(in_doubles)) || (rc = E.soa64.ensure(soa_elems)) ||
-        (rc = E.soa32.ensure(soa_elems)) || (rc = E.px64.ensure(px_elems)) || (rc = E.mask.ensure(mask_bytes)) ||
-        (rc = E.h_mask.ensure(mask_bytes)) || (rc = E.work.ensure(8)) || (rc = E.probs.ensure(n_probdev)) ||
+        (rc = E.soa32.ensure(soa_elems)) || (rc = E.cmax.ensure(5 * (size_t)NP)) || (rc = E.px64.ensure(px_elems)) || (rc = E.mask.ensure(mask_bytes)) ||
+        (rc = E.mask_bits.ensure(mask_bytes / 32 + 1)) || (rc = E.h_mask_bits.ensure(mask_bytes / 32 + 1)) ||
+        (rc = E.work.ensure(8)) || (rc = E.probs.ensure(n_probdev)) ||
         (rc = E.h_probs.ensure(n_probdev)) || (rc = E.tdesc.ensure(std::max(n_up, 1))) ||
         (rc = E.h_tdesc.ensure(std::max(n_up, 1))))
         return rc;
@@ -519,11 +586,13 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             P.rfc = S.t->rfc;
             P.n_pad = S.n_pad;
             if (S.n == 0) continue;
+            P.cmax = E.cmax.p + 5 * (size_t)i;
             if (S.t->res) {
                 for (int c = 0; c < n_arr; ++c) {
                     P.p[c] = S.t->res->soa64.p + (size_t)c * S.n_pad;
                     P.f[c] = S.t->res->soa32.p + (size_t)c * S.n_pad;
                 }
+                P.cmax = S.t->res->cmax.p;
             } else {
                 double *ha = E.h_in.p + in_off, *hb = ha + 2 * (size_t)S.n;
                 std::memcpy(ha, S.t->a, sizeof(double) * 2 * S.n);
@@ -533,6 +602,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 D.b = D.a + 2 * (size_t)S.n;
                 D.s64 = E.soa64.p + soa_off;
                 D.s32 = E.soa32.p + soa_off;
+                D.cmax = E.cmax.p + 5 * (size_t)i;
                 D.n = S.n;
                 D.n_pad = S.n_pad;
                 D.b_dim = b_dim;
@@ -578,6 +648,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         }
         PLB_CUDA(cudaMemcpyAsync(E.probs.p, E.h_probs.p, sizeof(ProblemDev) * n_probdev, cudaMemcpyHostToDevice, st));
         if (n_up) {
+            PLB_CUDA(cudaMemsetAsync(E.cmax.p, 0, sizeof(float) * 5 * (size_t)NP, st));
             PLB_CUDA(cudaMemcpyAsync(E.tdesc.p, E.h_tdesc.p, sizeof(TransposeDesc) * n_up, cudaMemcpyHostToDevice, st));
             launch_transpose(E.tdesc.p, n_up, max_n_pad, st);
             E.launches++;
@@ -731,7 +802,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
     int smp_cur = 0; // sampler states of the current round: E.smp[smp_cur * NP ..]; the advanced ones land in the other half
     const size_t CHUNK_MAX = 16384, ROUND_MAX = 32768, S_TOT_MAX = 262144;
     // 0 exact, 1 fast (fp32 screen + fp64 confirmation of candidates); the tangent-Sampson kind has no fp32 copy
-    const int mode = (kind == KIND_RELPOSE_TS) ? 0 : g_mode.load();
+    const int mode = (kind == KIND_RELPOSE_TS) ? 0 : current_mode();
     int cap_factor = kind_is_relpose(kind) ? 8 : MAXM;
     bool big_caps = false;
     std::vector<int> act;
@@ -1096,7 +1167,10 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             }
             if ((rc = launch_lm_jobs(npol, false, 0))) return rc;
         }
-        PLB_CUDA(cudaMemcpyAsync(E.h_mask.p, E.mask.p, mask_bytes, cudaMemcpyDeviceToHost, st));
+        // the masks cross PCIe as bits (1/8 of the bytes) and are expanded into the caller's char[n] below
+        launch_pack_mask(E.mask.p, E.mask_bits.p, mask_bytes, st);
+        E.launches++;
+        PLB_CUDA(cudaMemcpyAsync(E.h_mask_bits.p, E.mask_bits.p, sizeof(uint32_t) * (mask_bytes / 32), cudaMemcpyDeviceToHost, st));
         if ((rc = sync_timed(nullptr))) return rc;
         for (int j = 0; j < npol; ++j) {
             PState &S = PS[pol[j]];
@@ -1104,9 +1178,13 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         }
         for (int i = 0; i < NP; ++i) {
             PState &S = PS[i];
-            if (S.t->inliers && S.n > 0) std::memcpy(S.t->inliers, E.h_mask.p + S.mask_off, S.n);
+            if (S.t->inliers && S.n > 0) {
+                const uint32_t *w = E.h_mask_bits.p + (S.mask_off >> 5); // mask_off is a multiple of 32
+                char *dst = S.t->inliers;
+                for (int k = 0; k < S.n; ++k) dst[k] = (char)((w[k >> 5] >> (k & 31)) & 1u);
+            }
             std::copy(S.best_model, S.best_model + MSZ, S.t->model);
-            d2h += S.n;
+            d2h += (size_t)S.n_pad / 8;
         }
     }
     PLB_CUDA(cudaGetLastError());
@@ -1185,6 +1263,7 @@ static int run_refine(int kind, const double *a, const double *b, size_t n_pts, 
     D.b = E.in.p + 2 * (size_t)n;
     D.s64 = E.soa64.p;
     D.s32 = E.soa32.p;
+    D.cmax = nullptr;
     D.n = n;
     D.n_pad = n_pad;
     D.b_dim = b_dim;
@@ -1493,7 +1572,7 @@ int plb_set_mode(int mode) {
         g_err = "mode must be 0 (exact) or 1 (fast)";
         return PLB_ERR_ARG;
     }
-    g_mode.store(mode);
+    g_mode = mode;
     return PLB_OK;
 }
 
@@ -1770,8 +1849,17 @@ int plb_homography_4pt_batch(size_t count, const double *x1, const double *x2, d
     return solver_batch(KIND_HOMOG, 0, count, x1, 12, x2, 12, H_out, 9, n_out, check_cheirality);
 }
 
-// ---- batch of problems: `streams` host threads, each with its own engine/stream ------------------------------
-int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
+// ---- batch of problems: `streams` lock-step groups in flight per device, each on its own engine / stream ----------
+// Problems of the same kind run in lock-step groups (one chain of launches per round for the whole group); the groups of
+// a device are spread over `streams` persistent worker threads.  devices[0..n_dev): the CUDA devices to use; problems
+// are assigned to devices by longest-processing-time-first on (correspondences x expected iterations), problems whose
+// correspondences are resident stay on the device that holds them.
+static double problem_cost(const plb_problem &p, size_t n) {
+    static const double its[4] = {4.0 * 1000, 0.5 * 14000, 2.0 * 30000, 1.0 * 1000}; // models x iterations, typical
+    const double cap = (double)std::max<uint64_t>(p.opt.max_iterations, 1) * 4.0;
+    return (double)std::max<size_t>(n, 1) * std::min(its[p.kind], cap);
+}
+static int batch_impl(plb_problem *problems, size_t count, const int *devices, int n_dev, int streams) {
     if (count == 0) return PLB_OK;
     if (!problems) {
         g_err = "null argument";
@@ -1781,71 +1869,117 @@ int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
         g_err = "no usable CUDA device";
         return PLB_ERR_CUDA;
     }
-    // Problems of the same kind run in lock-step groups (one set of launches per round for the whole group);
-    // `streams` groups are in flight at once, each on its own stream, so the host replay of one group overlaps the
-    // kernels of the others.
-    std::vector<Task> tasks(count);
-    std::vector<std::vector<Task *>> groups;
-    const int nthreads_req = std::max(1, streams);
-    for (int kind = 0; kind < 4; ++kind) {
-        std::vector<Task *> of_kind;
-        for (size_t i = 0; i < count; ++i) {
-            plb_problem &p = problems[i];
-            if (p.kind != kind) continue;
-            Task &t = tasks[i];
-            t.kind = kind;
-            t.a = p.a;
-            t.b = p.b;
-            t.n = (size_t)p.n;
-            t.opt = p.opt;
-            t.max_error = p.max_error;
-            t.rfc = p.real_focal_check;
-            t.model = p.model;
-            t.inliers = p.inliers;
-            t.stats_out = &p.stats;
-            t.cnt_out = &p.counters;
-            p.status = PLB_OK;
-            if (p.resident > 0) {
-                const Resident *res = nullptr;
-                {
-                    std::lock_guard<std::mutex> lk(g_res_mtx);
-                    if ((size_t)p.resident <= g_resident.size()) res = g_resident[p.resident - 1];
-                }
-                if (!res || res->kind != kind) {
-                    g_err = "invalid resident handle";
-                    return PLB_ERR_ARG;
-                }
-                t.res = res;
-                t.n = (size_t)res->n;
-            } else if (t.n > 0 && (!p.a || !p.b)) {
-                g_err = "null argument";
-                return PLB_ERR_ARG;
-            }
-            of_kind.push_back(&t);
-        }
-        if (of_kind.empty()) continue;
-        const size_t gsz = std::min<size_t>(256, std::max<size_t>(1, (of_kind.size() + nthreads_req - 1) / nthreads_req));
-        for (size_t o = 0; o < of_kind.size(); o += gsz)
-            groups.emplace_back(of_kind.begin() + o, of_kind.begin() + std::min(of_kind.size(), o + gsz));
-    }
-    for (size_t i = 0; i < count; ++i)
+    for (size_t i = 0; i < count; ++i) {
+        problems[i].status = PLB_OK;
         if (problems[i].kind < 0 || problems[i].kind > 3) {
             g_err = "unknown problem kind";
+            for (size_t j = 0; j < count; ++j) problems[j].status = PLB_ERR_ARG;
             return PLB_ERR_ARG;
         }
-    const int nthreads = std::max(1, std::min<int>(nthreads_req, (int)groups.size()));
-    const int dev = g_device;
+    }
+    std::vector<Task> tasks(count);
+    std::vector<int> dev_of(count, -1);
+    std::vector<std::shared_ptr<Resident>> held; // resident inputs stay alive for the duration of the call
+    auto fail_all = [&](int rc, const char *msg) {
+        g_err = msg;
+        for (size_t j = 0; j < count; ++j) problems[j].status = rc;
+        return rc;
+    };
+    for (size_t i = 0; i < count; ++i) {
+        plb_problem &p = problems[i];
+        Task &t = tasks[i];
+        t.kind = p.kind;
+        t.a = p.a;
+        t.b = p.b;
+        t.n = (size_t)p.n;
+        t.opt = p.opt;
+        t.max_error = p.max_error;
+        t.rfc = p.real_focal_check;
+        t.model = p.model;
+        t.inliers = p.inliers;
+        t.stats_out = &p.stats;
+        t.cnt_out = &p.counters;
+        if (p.resident > 0) {
+            std::shared_ptr<Resident> res;
+            {
+                std::lock_guard<std::mutex> lk(g_res_mtx);
+                if ((size_t)p.resident <= g_resident.size()) res = g_resident[p.resident - 1];
+            }
+            if (!res || res->kind != p.kind) return fail_all(PLB_ERR_ARG, "invalid resident handle");
+            bool ok = false;
+            for (int d = 0; d < n_dev; ++d) ok |= (devices[d] == res->device);
+            if (!ok) return fail_all(PLB_ERR_ARG, "resident correspondences live on a device this call does not use");
+            t.res = res.get();
+            t.n = (size_t)res->n;
+            dev_of[i] = res->device;
+            held.push_back(std::move(res));
+        } else if (t.n > 0 && (!p.a || !p.b)) {
+            return fail_all(PLB_ERR_ARG, "null argument");
+        }
+    }
+    // device assignment: LPT over the problems that are free to move
+    {
+        std::vector<double> load(n_dev, 0.0);
+        std::vector<size_t> order;
+        for (size_t i = 0; i < count; ++i) {
+            if (dev_of[i] >= 0) {
+                for (int d = 0; d < n_dev; ++d)
+                    if (devices[d] == dev_of[i]) load[d] += problem_cost(problems[i], tasks[i].n);
+            } else {
+                order.push_back(i);
+            }
+        }
+        if (n_dev == 1) {
+            for (size_t i : order) dev_of[i] = devices[0];
+        } else {
+            std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+                return problem_cost(problems[x], tasks[x].n) > problem_cost(problems[y], tasks[y].n);
+            });
+            for (size_t i : order) {
+                int best = 0;
+                for (int d = 1; d < n_dev; ++d)
+                    if (load[d] < load[best]) best = d;
+                dev_of[i] = devices[best];
+                load[best] += problem_cost(problems[i], tasks[i].n);
+            }
+        }
+    }
+    // groups per device
+    const int nthreads_req = std::max(1, streams);
+    struct Job {
+        int device;
+        std::vector<std::vector<Task *>> groups;
+    };
+    std::vector<Job> jobs; // one per (device, worker)
+    for (int d = 0; d < n_dev; ++d) {
+        std::vector<std::vector<Task *>> groups;
+        for (int kind = 0; kind < 4; ++kind) {
+            std::vector<Task *> of_kind;
+            for (size_t i = 0; i < count; ++i)
+                if (problems[i].kind == kind && dev_of[i] == devices[d]) of_kind.push_back(&tasks[i]);
+            if (of_kind.empty()) continue;
+            const size_t gsz = std::min<size_t>(256, std::max<size_t>(1, (of_kind.size() + nthreads_req - 1) / nthreads_req));
+            for (size_t o = 0; o < of_kind.size(); o += gsz)
+                groups.emplace_back(of_kind.begin() + o, of_kind.begin() + std::min(of_kind.size(), o + gsz));
+        }
+        const int nthreads = std::max(1, std::min<int>(nthreads_req, (int)groups.size()));
+        for (int t = 0; t < nthreads; ++t) {
+            Job j;
+            j.device = devices[d];
+            for (size_t gi = (size_t)t; gi < groups.size(); gi += (size_t)nthreads) j.groups.push_back(groups[gi]);
+            if (!j.groups.empty()) jobs.push_back(std::move(j));
+        }
+    }
     std::atomic<int> first_err(PLB_OK);
     std::string err_msg;
     std::mutex mtx;
-    auto work = [&](int tid) {
-        g_device = dev;
-        g_engine = pool_engine((size_t)dev * 1024 + tid);
-        // static group -> engine mapping: an engine sees the same group shapes on every call of a repeated workload,
-        // so its grow-only buffers stop reallocating (cudaMalloc / cudaFree synchronise the whole device) after the
-        // first call
-        for (size_t gi = (size_t)tid; gi < groups.size(); gi += (size_t)nthreads) {
-            const int rc = run_group(groups[gi][0]->kind, groups[gi]);
+    const int mode = current_mode();
+    auto work = [&](int w) {
+        const int saved_dev = g_device, saved_mode = g_mode;
+        g_device = jobs[w].device;
+        g_mode = mode;
+        for (auto &grp : jobs[w].groups) {
+            const int rc = run_group(grp[0]->kind, grp);
             if (rc != PLB_OK) {
                 int exp = PLB_OK;
                 if (first_err.compare_exchange_strong(exp, rc)) {
@@ -1854,22 +1988,38 @@ int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
                 }
             }
         }
-        g_engine = nullptr; // the pooled engine outlives the thread
+        g_device = saved_dev;
+        g_mode = saved_mode;
     };
-    if (nthreads == 1) {
-        Engine *saved = g_engine;
-        work(0);
-        g_engine = saved;
-    } else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
-        for (auto &t : th) t.join();
-    }
+    if (jobs.size() == 1) work(0); // the caller's own thread and engine
+    else worker_pool().run((int)jobs.size(), work);
     if (first_err.load() != PLB_OK) {
         g_err = err_msg;
         for (size_t i = 0; i < count; ++i) problems[i].status = first_err.load();
     }
     return first_err.load();
+}
+int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
+    const int dev = g_device;
+    return batch_impl(problems, count, &dev, 1, streams);
+}
+// The same over the first n_gpus CUDA devices of this process (0 = all): in-process multi-GPU, no collective — image
+// pairs are independent (robust/ransac.cc:144-148 builds one estimator per call).  Results (stats, models, inlier
+// masks) land in the caller's plb_problem array exactly as with plb_ransac_batch.
+int plb_ransac_batch_multi(plb_problem *problems, size_t count, int n_gpus, int streams_per_gpu) {
+    const int have = plb_device_count();
+    if (have == 0) {
+        g_err = "no usable CUDA device";
+        return PLB_ERR_CUDA;
+    }
+    if (n_gpus < 0 || n_gpus > have) {
+        g_err = "n_gpus out of range";
+        return PLB_ERR_ARG;
+    }
+    if (n_gpus == 0) n_gpus = have;
+    std::vector<int> devs(n_gpus);
+    for (int d = 0; d < n_gpus; ++d) devs[d] = d;
+    return batch_impl(problems, count, devs.data(), n_gpus, streams_per_gpu);
 }
 
 int plb_resident_create(int kind, const double *a, const double *b, size_t n_pts) {
@@ -1881,29 +2031,27 @@ int plb_resident_create(int kind, const double *a, const double *b, size_t n_pts
     int rc = E.init();
     if (rc != PLB_OK) return rc;
     const int n = (int)n_pts, n_pad = (n + 31) & ~31, b_dim = (kind == KIND_PNP) ? 3 : 2, n_arr = 2 + b_dim;
-    Resident *R = new Resident();
+    std::shared_ptr<Resident> R = std::make_shared<Resident>(); // freed on every early return below
     DevBuf<double> da, db;
     if ((rc = R->soa64.ensure((size_t)n_arr * n_pad)) || (rc = R->soa32.ensure((size_t)n_arr * n_pad)) ||
-        (rc = da.ensure(2 * (size_t)n)) || (rc = db.ensure((size_t)b_dim * n))) {
-        delete R;
+        (rc = R->cmax.ensure(8)) || (rc = da.ensure(2 * (size_t)n)) || (rc = db.ensure((size_t)b_dim * n)) ||
+        (rc = E.tdesc.ensure(1)) || (rc = E.h_tdesc.ensure(1)))
         return rc;
-    }
     PLB_CUDA(cudaMemcpyAsync(da.p, a, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, E.stream));
     PLB_CUDA(cudaMemcpyAsync(db.p, b, sizeof(double) * b_dim * n, cudaMemcpyHostToDevice, E.stream));
-    if ((rc = E.tdesc.ensure(1)) || (rc = E.h_tdesc.ensure(1))) {
-        delete R;
-        return rc;
-    }
     TransposeDesc &D = E.h_tdesc.p[0];
+    std::memset(&D, 0, sizeof(D));
     D.a = da.p;
     D.b = db.p;
     D.s64 = R->soa64.p;
     D.s32 = R->soa32.p;
+    D.cmax = R->cmax.p;
     D.n = n;
     D.n_pad = n_pad;
     D.b_dim = b_dim;
     D.mode = 0;
     D.scale = 1.0;
+    PLB_CUDA(cudaMemsetAsync(R->cmax.p, 0, sizeof(float) * 8, E.stream));
     PLB_CUDA(cudaMemcpyAsync(E.tdesc.p, E.h_tdesc.p, sizeof(TransposeDesc), cudaMemcpyHostToDevice, E.stream));
     launch_transpose(E.tdesc.p, 1, n_pad, E.stream);
     PLB_CUDA(cudaStreamSynchronize(E.stream));
@@ -1921,13 +2069,16 @@ int plb_resident_create(int kind, const double *a, const double *b, size_t n_pts
     return (int)g_resident.size();
 }
 int plb_resident_free(int handle) {
-    std::lock_guard<std::mutex> lk(g_res_mtx);
-    if (handle <= 0 || (size_t)handle > g_resident.size() || !g_resident[handle - 1]) {
-        g_err = "invalid resident handle";
-        return PLB_ERR_ARG;
+    std::shared_ptr<Resident> gone; // destroyed (cudaFree) outside the lock; a batch call in flight keeps its own reference
+    {
+        std::lock_guard<std::mutex> lk(g_res_mtx);
+        if (handle <= 0 || (size_t)handle > g_resident.size() || !g_resident[handle - 1]) {
+            g_err = "invalid resident handle";
+            return PLB_ERR_ARG;
+        }
+        gone = std::move(g_resident[handle - 1]);
+        g_resident[handle - 1] = nullptr;
     }
-    delete g_resident[handle - 1];
-    g_resident[handle - 1] = nullptr;
     return PLB_OK;
 }
 

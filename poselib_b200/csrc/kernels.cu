@@ -12,6 +12,7 @@
 // Compiled with -fmad=false (see device_math.cuh).  Reference citations are relative to /root/reference.
 #include "kernels.cuh"
 #include "solvers.cuh"
+#include "screen_math.cuh"
 #include <cooperative_groups.h>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +25,16 @@ PLB_DEV int min_i(int a, int b) { return a < b ? a : b; }
 // ============================================================================================================
 // layout transform
 // ============================================================================================================
+// Per-problem maximum |coordinate| of every SoA array (of the fp64 values, rounded up to float): the error bounds of the
+// fp32 screening pass are built on them (screen_math.cuh).  All 32 lanes of a warp call it (n_pad is a multiple of 32).
+// NaN coordinates order above every finite value as unsigned bit patterns, so they poison the maximum (and with it the
+// bounds: every model of such a problem is rescored exactly).
+PLB_DEV void coord_max(float *cmax, int c, double v) {
+    if (!cmax) return;
+    const unsigned bits = __float_as_uint(scr::f_up(fabs(v)));
+    const unsigned m = __reduce_max_sync(0xffffffffu, bits);
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned *>(cmax) + c, m);
+}
 __global__ void k_transpose(const TransposeDesc *__restrict__ descs) {
     const TransposeDesc &d = descs[blockIdx.y];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,16 +69,23 @@ __global__ void k_transpose(const TransposeDesc *__restrict__ descs) {
         d.s32[1 * (size_t)d.n_pad + k] = (float)a1;
         d.s32[2 * (size_t)d.n_pad + k] = (float)b0;
         d.s32[3 * (size_t)d.n_pad + k] = (float)b1;
+        coord_max(d.cmax, 0, a0);
+        coord_max(d.cmax, 1, a1);
+        coord_max(d.cmax, 2, b0);
+        coord_max(d.cmax, 3, b1);
         return;
     }
     d.s64[0 * (size_t)d.n_pad + k] = a0;
     d.s64[1 * (size_t)d.n_pad + k] = a1;
     d.s32[0 * (size_t)d.n_pad + k] = (float)a0;
     d.s32[1 * (size_t)d.n_pad + k] = (float)a1;
+    coord_max(d.cmax, 0, a0);
+    coord_max(d.cmax, 1, a1);
     for (int c = 0; c < d.b_dim; ++c) {
         const double v = d.b[(size_t)d.b_dim * idx + c];
         d.s64[(2 + c) * (size_t)d.n_pad + k] = v;
         d.s32[(2 + c) * (size_t)d.n_pad + k] = (float)v;
+        coord_max(d.cmax, 2 + c, v);
     }
 }
 void launch_transpose(const TransposeDesc *descs_dev, int n_desc, int max_n_pad, cudaStream_t stream) {
@@ -815,45 +833,38 @@ PLB_DEV void mbar_wait(uint64_t *bar, uint32_t phase) {
                  : "memory");
 }
 
+// Model constants are re-read from shared memory for every (model, step) on purpose: left to itself the compiler hoists
+// the loop-invariant loads of all SCR_TM models out of the streaming loop and spills them.
+PLB_DEV void lds_v4(const float *p, float *o) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(smem_u32(p)));
+}
+PLB_DEV float2 lds_f2(const float2 *p) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem_u32(p)));
+    return v;
+}
 PLB_DEV float warp_sum_f(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-// fp32 cheirality of one correspondence for the screening pass (robust/utils.cc:187-197, misc/essential.cc:40-57);
-// deliberately not inlined: it runs only for the rare candidates under the threshold.
-__device__ __noinline__ bool cheirality32(const float *qt, float a0, float a1, float b0, float b1) {
-    const float in1 = rsqrtf(fmaf(a0, a0, fmaf(a1, a1, 1.f)));
-    const float in2 = rsqrtf(fmaf(b0, b0, fmaf(b1, b1, 1.f)));
-    const float u0 = a0 * in1, u1 = a1 * in1, u2 = in1;
-    const float v0 = b0 * in2, v1 = b1 * in2, v2 = in2;
-    const float *q = qt, *t = qt + 4;
-    const float px1 = -u0 * q[1] - u1 * q[2] - u2 * q[3];
-    const float px2 = u0 * q[0] - u1 * q[3] + u2 * q[2];
-    const float px3 = u1 * q[0] + u0 * q[3] - u2 * q[1];
-    const float px4 = u1 * q[1] - u0 * q[2] + u2 * q[0];
-    const float w0 = px2 * q[0] - px1 * q[1] - px3 * q[3] + px4 * q[2];
-    const float w1 = px3 * q[0] - px1 * q[2] + px2 * q[3] - px4 * q[1];
-    const float w2 = px3 * q[1] - px2 * q[2] - px1 * q[3] + px4 * q[0];
-    const float aa = -(w0 * v0 + w1 * v1 + w2 * v2);
-    const float bb1 = -(w0 * t[0] + w1 * t[1] + w2 * t[2]);
-    const float bb2 = v0 * t[0] + v1 * t[1] + v2 * t[2];
-    const float l1 = bb1 - aa * bb2, l2 = -aa * bb1 + bb2;
-    const float md = 0.01f * (1.f - aa * aa);
-    return (l1 > md) && (l2 > md);
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOut out, int use_smem) {
+template <int KIND, bool PACKED>
+__global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const RoundDesc R, HypOut out, int use_smem) {
     constexpr int MSZ = kind_model_size(KIND);
     constexpr int CTX = (KIND == KIND_PNP) ? 12 : kind_is_relpose(KIND) ? 16 : 9;
     constexpr int NARR = (KIND == KIND_PNP) ? 5 : 4;
     extern __shared__ __align__(128) unsigned char scr_smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ float ctx[SCR_TM][16];
+    __shared__ __align__(16) float ctx[SCR_TM][scr::CTX_FLOATS];
     __shared__ float red_s[SCR_WARPS][SCR_TM];
+    __shared__ float red_e[SCR_WARPS][SCR_TM];
     __shared__ uint32_t red_c[SCR_WARPS][SCR_TM];
+    __shared__ uint32_t s_border[SCR_TM];
+    // packed-fp32 streaming loop (Sampson kinds): the 9 model constants and the two constants of the streaming test,
+    // duplicated (m, m) so that one 64-bit broadcast load feeds both halves of an FFMA2
+    constexpr bool PK = PACKED && (KIND == KIND_RELPOSE || KIND == KIND_FUND);
+    __shared__ __align__(16) float2 ctx2[PK ? SCR_TM : 1][12];
     // ---- static, cost-balanced partition of the round's (problem, tile) list over the CTAs of the grid ------------
     // cost of a tile = correspondences of its problem; CTA c owns the tiles whose start cost lies in
     // [W c / G, W (c+1) / G).  The grid is ONE wave (resident CTAs x SMs), so there is no tail wave; a CTA touches a
@@ -972,6 +983,7 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
     for (int m0 = t_begin * SCR_TM; m0 < t_end * SCR_TM; m0 += SCR_TM) {
         const int tm = (count - m0 < SCR_TM) ? (count - m0) : SCR_TM;
         __syncthreads();
+        if (tid < SCR_TM) s_border[tid] = 0u;
         if (tid < tm) {
             double mdl[MSZ];
 #pragma unroll
@@ -981,105 +993,141 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
             const double *cp = reinterpret_cast<const double *>(&C);
 #pragma unroll
             for (int k = 0; k < CTX; ++k) ctx[tid][k] = (float)cp[k];
+            // per-model constants of the error bounds (screen_math.cuh), from the fp64 model and the problem's maxima
+            float cm[5];
+#pragma unroll
+            for (int c = 0; c < NARR; ++c) cm[c] = P.cmax[c];
+            if (KIND == KIND_PNP) scr::transfer_setup<3>(cp, cm + 2, cm, P.sq_thr, ctx[tid]);
+            else if (KIND == KIND_HOMOG) scr::transfer_setup<2>(cp, cm, cm + 2, P.sq_thr, ctx[tid]);
+            else scr::sampson_setup(cp, cm, P.sq_thr, ctx[tid]);
+            if (KIND == KIND_RELPOSE) scr::cheirality_setup(cp + 9, cp + 13, ctx[tid]);
+            if (PK) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) ctx2[tid][k] = make_float2(ctx[tid][k], ctx[tid][k]);
+                ctx2[tid][9] = make_float2(ctx[tid][scr::S_THR_X], ctx[tid][scr::S_THR_X]);
+                ctx2[tid][10] = make_float2(ctx[tid][scr::S_BETA_X], ctx[tid][scr::S_BETA_X]);
+            }
         }
         __syncthreads();
         uint32_t cnt[SCR_TM];
-        float sc[SCR_TM];
+        float sc[SCR_TM], er[SCR_TM];
 #pragma unroll
         for (int i = 0; i < SCR_TM; ++i) {
             cnt[i] = 0;
             sc[i] = 0.f;
+            er[i] = 0.f;
         }
-        for (int k = tid; KIND == KIND_PNP && k < n; k += SCR_THREADS) {
-            {
-                const float x0 = arr[0][k], x1 = arr[1][k], X0 = arr[2][k], X1 = arr[3][k], X2 = arr[4][k];
-#pragma unroll
-                for (int i = 0; i < SCR_TM; ++i) {
-                    if (i < tm) {
-                        const float *Pm = ctx[i];
-                        const float z0 = fmaf(Pm[0], X0, fmaf(Pm[1], X1, fmaf(Pm[2], X2, Pm[3])));
-                        const float z1 = fmaf(Pm[4], X0, fmaf(Pm[5], X1, fmaf(Pm[6], X2, Pm[7])));
-                        const float z2 = fmaf(Pm[8], X0, fmaf(Pm[9], X1, fmaf(Pm[10], X2, Pm[11])));
-                        if (z2 > 0.f) {
-                            const float iz = __fdividef(1.f, z2);
-                            const float r0 = fmaf(z0, iz, -x0), r1 = fmaf(z1, iz, -x1);
-                            const float r2 = fmaf(r0, r0, r1 * r1);
-                            if (r2 < thr) {
-                                ++cnt[i];
-                                sc[i] += r2;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        if (KIND != KIND_PNP) {
-            // 2D-2D kinds.  sc[i] accumulates sum over inliers of (r2 - thr); n*thr is added at the end.
-            // The streaming pass is branch-free: two 2x3 products, the residual numerator / denominator, one multiply,
-            // one compare, and a predicated OR that records "correspondence q of this lane is under the threshold for
-            // model i" in a per-lane bit mask.  SCR_PB correspondences per thread per step reuse the 9 model
-            // constants fetched (broadcast) from shared memory.  The rare under-threshold cases (cheirality test,
-            // division, accumulation) are handled afterwards in a compacted loop in which every lane pops one of ITS
-            // recorded cases per iteration — handled inline they cost a divergent ~60-instruction detour for the
-            // whole warp whenever one lane of 32 hits (35 % of all issued instructions, profiles/r01_v7_summary.md).
+        {
+            // sc[i] accumulates sum over inliers of (r2 - thr); n*thr is added at the end.
+            // The streaming pass is branch-free: the residual terms, one test "could this correspondence be an inlier
+            // of model i in fp64" (the plain fp32 test widened by the rigorous error bound, screen_math.cuh) and a
+            // predicated OR that records the correspondence in a per-lane bit mask.  SCR_PB correspondences per thread
+            // per step reuse the model constants fetched (broadcast) from shared memory.  The recorded cases (plain
+            // decision, is it provably the fp64 decision, cheirality, division, accumulation of score and error bound)
+            // are handled afterwards in a compacted loop in which every lane pops one of ITS recorded cases per
+            // iteration — handled inline they cost a divergent detour for the whole warp whenever one lane of 32 hits.
             constexpr int SCR_PB = 4;
-            auto numden = [&](const float *M, float a0, float a1, float b0, float b1, float &num, float &den) {
-                const float m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5], m6 = M[6], m7 = M[7], m8 = M[8];
-                if (KIND == KIND_HOMOG) {
-                    const float h0 = fmaf(m0, a0, fmaf(m1, a1, m2));
-                    const float h1 = fmaf(m3, a0, fmaf(m4, a1, m5));
-                    const float w = fmaf(m6, a0, fmaf(m7, a1, m8));
-                    // |h/w - b|^2 < thr  <=>  |h - w b|^2 < thr w^2
-                    const float d0 = fmaf(-w, b0, h0), d1 = fmaf(-w, b1, h1);
-                    num = fmaf(d0, d0, d1 * d1);
-                    den = w * w;
-                } else {
-                    const float e0 = fmaf(m0, a0, fmaf(m1, a1, m2));
-                    const float e1 = fmaf(m3, a0, fmaf(m4, a1, m5));
-                    const float e2 = fmaf(m6, a0, fmaf(m7, a1, m8));
-                    const float f0 = fmaf(m0, b0, fmaf(m3, b1, m6));
-                    const float f1 = fmaf(m1, b0, fmaf(m4, b1, m7));
-                    const float Cn = fmaf(b0, e0, fmaf(b1, e1, e2));
-                    den = fmaf(e0, e0, fmaf(e1, e1, fmaf(f0, f0, f1 * f1)));
-                    num = Cn * Cn;
-                }
+            auto maybe = [&](const float *M, const float *p) -> bool {
+                if (KIND == KIND_PNP) return scr::transfer_maybe<true>(M, scr::pnp_terms(M, p[0], p[1], p[2], p[3], p[4]));
+                if (KIND == KIND_HOMOG) return scr::transfer_maybe<false>(M, scr::homography_terms(M, p[0], p[1], p[2], p[3]));
+                return scr::sampson_maybe(M, p[0], p[1], p[2], p[3]);
             };
             for (int base = 0; base < n; base += 32 * SCR_THREADS) {
                 const int lim = min_i(n, base + 32 * SCR_THREADS);
                 uint32_t hit[SCR_TM];
 #pragma unroll
                 for (int i = 0; i < SCR_TM; ++i) hit[i] = 0u;
+                if constexpr (PK) {
+                    // Blackwell packed fp32 (FFMA2): lane-adjacent correspondences (2p, 2p+1) ride in the two halves of
+                    // 64-bit registers; every instruction of the residual evaluates both.  Bit 2j+h of a hit mask is
+                    // correspondence base + 2 (tid + j SCR_THREADS) + h.  The test is scr::sampson_maybe_x.
+                    auto pair_hits = [&](const float2 *M2, float2 a0, float2 a1, float2 b0, float2 b1, uint32_t bx, uint32_t by) -> uint32_t {
+                        const float2 e0 = __ffma2_rn(M2[0], a0, __ffma2_rn(M2[1], a1, M2[2]));
+                        const float2 e1 = __ffma2_rn(M2[3], a0, __ffma2_rn(M2[4], a1, M2[5]));
+                        const float2 e2 = __ffma2_rn(M2[6], a0, __ffma2_rn(M2[7], a1, M2[8]));
+                        const float2 f0 = __ffma2_rn(M2[0], b0, __ffma2_rn(M2[3], b1, M2[6]));
+                        const float2 f1 = __ffma2_rn(M2[1], b0, __ffma2_rn(M2[4], b1, M2[7]));
+                        const float2 Cn = __ffma2_rn(b0, e0, __ffma2_rn(b1, e1, e2));
+                        const float2 D = __ffma2_rn(e0, e0, __ffma2_rn(e1, e1, __ffma2_rn(f0, f0, __fmul2_rn(f1, f1))));
+                        const float2 q = __fmul2_rn(Cn, Cn);
+                        const float2 rhs = __ffma2_rn(M2[9], D, M2[10]);
+                        return (q.x <= rhs.x ? bx : 0u) | (q.y <= rhs.y ? by : 0u);
+                    };
+                    int p0 = tid; // pair index inside the chunk
+                    uint32_t sh = 0;
+                    const int npairs = (lim - base + 1) >> 1;
+                    for (; p0 + SCR_THREADS < npairs; p0 += 2 * SCR_THREADS, sh += 4) {
+                        float2 pa[2][4];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int k = base + 2 * (p0 + j * SCR_THREADS);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) pa[j][c] = *reinterpret_cast<const float2 *>(arr[c] + k);
+                        }
+                        const uint32_t q0 = 1u << sh, q1 = 2u << sh, q2 = 4u << sh, q3 = 8u << sh;
+#pragma unroll
+                        for (int i = 0; i < SCR_TM; ++i) {
+                            if (i < tm) {
+                                float2 M2[11];
+#pragma unroll
+                                for (int k = 0; k < 11; ++k) M2[k] = lds_f2(&ctx2[i][k]);
+                                hit[i] |= pair_hits(M2, pa[0][0], pa[0][1], pa[0][2], pa[0][3], q0, q1);
+                                hit[i] |= pair_hits(M2, pa[1][0], pa[1][1], pa[1][2], pa[1][3], q2, q3);
+                            }
+                        }
+                    }
+                    for (; p0 < npairs; p0 += SCR_THREADS, sh += 2) { // remainder
+                        const int k = base + 2 * p0;
+                        float2 pa[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) pa[c] = *reinterpret_cast<const float2 *>(arr[c] + k);
+                        const uint32_t q0 = 1u << sh, q1 = 2u << sh;
+#pragma unroll
+                        for (int i = 0; i < SCR_TM; ++i) {
+                            if (i < tm) {
+                                float2 M2[11];
+#pragma unroll
+                                for (int k = 0; k < 11; ++k) M2[k] = lds_f2(&ctx2[i][k]);
+                                hit[i] |= pair_hits(M2, pa[0], pa[1], pa[2], pa[3], q0, q1);
+                            }
+                        }
+                    }
+                } else {
                 int k0 = base + tid;
                 uint32_t qbit = 1u;
                 for (; k0 + (SCR_PB - 1) * SCR_THREADS < lim; k0 += SCR_THREADS * SCR_PB, qbit <<= SCR_PB) {
-                    float a0[SCR_PB], a1[SCR_PB], b0[SCR_PB], b1[SCR_PB];
+                    float p[SCR_PB][NARR];
 #pragma unroll
                     for (int j = 0; j < SCR_PB; ++j) {
                         const int k = k0 + j * SCR_THREADS;
-                        a0[j] = arr[0][k]; a1[j] = arr[1][k]; b0[j] = arr[2][k]; b1[j] = arr[3][k];
+#pragma unroll
+                        for (int c = 0; c < NARR; ++c) p[j][c] = arr[c][k];
                     }
 #pragma unroll
                     for (int i = 0; i < SCR_TM; ++i) {
                         if (i < tm) {
+                            float Mr[20]; // [0..11] model, [16..19] constants of the streaming test
+                            lds_v4(ctx[i], Mr);
+                            lds_v4(ctx[i] + 4, Mr + 4);
+                            lds_v4(ctx[i] + 8, Mr + 8);
+                            lds_v4(ctx[i] + 16, Mr + 16);
 #pragma unroll
-                            for (int j = 0; j < SCR_PB; ++j) {
-                                float num, den;
-                                numden(ctx[i], a0[j], a1[j], b0[j], b1[j], num, den);
-                                if (num < thr * den) hit[i] |= qbit << j;
-                            }
+                            for (int j = 0; j < SCR_PB; ++j)
+                                if (maybe(Mr, p[j])) hit[i] |= qbit << j;
                         }
                     }
                 }
                 for (; k0 < lim; k0 += SCR_THREADS, qbit <<= 1) { // remainder
-                    const float a0 = arr[0][k0], a1 = arr[1][k0], b0 = arr[2][k0], b1 = arr[3][k0];
+                    float p[NARR];
+#pragma unroll
+                    for (int c = 0; c < NARR; ++c) p[c] = arr[c][k0];
 #pragma unroll
                     for (int i = 0; i < SCR_TM; ++i) {
                         if (i < tm) {
-                            float num, den;
-                            numden(ctx[i], a0, a1, b0, b1, num, den);
-                            if (num < thr * den) hit[i] |= qbit;
+                            if (maybe(ctx[i], p)) hit[i] |= qbit;
                         }
                     }
+                }
                 }
                 // compacted handling of the recorded cases
                 for (;;) {
@@ -1098,20 +1146,42 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
 #pragma unroll
                         for (int i = 0; i < SCR_TM; ++i)
                             if (i == mi) hit[i] = cleared;
-                        const int k = base + tid + q * SCR_THREADS;
-                        const float a0 = arr[0][k], a1 = arr[1][k], b0 = arr[2][k], b1 = arr[3][k];
+                        const int k = PK ? base + 2 * (tid + (q >> 1) * SCR_THREADS) + (q & 1) : base + tid + q * SCR_THREADS;
+                        float p[NARR];
+#pragma unroll
+                        for (int c = 0; c < NARR; ++c) p[c] = arr[c][k];
                         const float *M = ctx[mi];
-                        float num, den;
-                        numden(M, a0, a1, b0, b1, num, den);
-                        bool inl = true;
-                        if (KIND == KIND_RELPOSE) inl = cheirality32(M + 9, a0, a1, b0, b1);
-                        if (inl) {
-                            const float v = __fdividef(num, den) - thr;
+                        bool plain = false, border = false;
+                        float v = 0.f, e = 0.f;
+                        if (PK && k >= n) { // second half of the last pair of an odd-sized problem: padding, not data
+                        } else if (KIND == KIND_PNP) {
+                            scr::transfer_point<true>(M, scr::pnp_terms(M, p[0], p[1], p[2], p[3], p[4]), plain, border, v, e);
+                        } else if (KIND == KIND_HOMOG) {
+                            scr::transfer_point<false>(M, scr::homography_terms(M, p[0], p[1], p[2], p[3]), plain, border, v, e);
+                        } else {
+                            scr::sampson_point(M, p[0], p[1], p[2], p[3], plain, border, v, e);
+                            if (KIND == KIND_RELPOSE && (plain || border)) {
+                                bool ok, cb;
+                                scr::cheirality_point(M + 9, M[scr::S_EH], p[0], p[1], p[2], p[3], ok, cb);
+                                if (cb) { // the cheirality decision itself is uncertain: +-1 inlier, up to thr of score
+                                    border = true;
+                                    e += thr;
+                                } else if (!ok) {
+                                    border = false; // certainly behind a camera: not an inlier whatever the residual
+                                }
+                                plain = plain && ok;
+                            }
+                        }
+                        if (border) atomicAdd(&s_border[mi], 1u);
+                        if (plain || border) {
 #pragma unroll
                             for (int i = 0; i < SCR_TM; ++i)
                                 if (i == mi) {
-                                    ++cnt[i];
-                                    sc[i] += v;
+                                    if (plain) {
+                                        ++cnt[i];
+                                        sc[i] += v;
+                                    }
+                                    er[i] += e;
                                 }
                         }
                     }
@@ -1122,26 +1192,32 @@ __global__ void __launch_bounds__(SCR_THREADS) k_screen(const RoundDesc R, HypOu
         for (int i = 0; i < SCR_TM; ++i) {
             const uint32_t c = warp_sum_u(cnt[i]);
             const float v = warp_sum_f(sc[i]);
+            const float ev = warp_sum_f(er[i]);
             if (lane == 0) {
                 red_c[warp][i] = c;
                 red_s[warp][i] = v;
+                red_e[warp][i] = ev;
             }
         }
         __syncthreads();
         if (tid < tm) {
             uint32_t ct = 0;
-            float st = 0.f;
+            float st = 0.f, et = 0.f;
 #pragma unroll
             for (int w = 0; w < SCR_WARPS; ++w) {
                 ct += red_c[w][tid];
                 st += red_s[w][tid];
+                et += red_e[w][tid];
             }
-            if (KIND == KIND_PNP) st += (float)(n - (int)ct) * thr;
-            else st += (float)n * thr; // the per-correspondence sums hold (r2 - thr) of the inliers only
+            st += (float)n * thr; // the per-correspondence sums hold (r2 - thr) of the inliers only
+            // + the rounding of the fp32 sums themselves: at most n/SCR_THREADS + 24 additions deep over terms of
+            //   magnitude <= thr each (ct of them), and the final n * thr product and addition
+            const float depth = (float)(n / SCR_THREADS + 24);
+            et = et * (1.f + 1e-5f) + scr::U * thr * (depth * (float)ct + 2.2f * (float)n);
             out.fcounts[seg + m0 + tid] = ct;
             out.fscores[seg + m0 + tid] = st;
-            out.fborder[seg + m0 + tid] = 5u + ct / 100u;
-            out.ferr[seg + m0 + tid] = 1e-3f * st;
+            out.fborder[seg + m0 + tid] = s_border[tid];
+            out.ferr[seg + m0 + tid] = et * (1.f + 1e-5f);
         }
     }
     } // problems of this CTA
@@ -1294,20 +1370,26 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
         const int use_smem = bytes <= 200 * 1024 ? 1 : 0;
         static bool attr_done_dev[MAX_DEVICES] = {false};
         bool &attr_done = attr_done_dev[cur_dev()];
+        static const bool packed = [] { // Blackwell FFMA2 streaming loop for the Sampson kinds (PLB_SCREEN_PACKED=0/1)
+            const char *e = std::getenv("PLB_SCREEN_PACKED");
+            return e ? std::atoi(e) != 0 : true;
+        }();
+        auto kern = packed ? k_screen<KIND, true> : k_screen<KIND, false>;
         if (!attr_done) {
-            cudaFuncSetAttribute(k_screen<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_screen<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_screen<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_done = true;
         }
         // one wave: resident CTAs per SM (occupancy API for this shared-memory size) x SMs; the kernel partitions the
         // (problem, tile) list over the CTAs by cost itself
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_screen<KIND>, SCR_THREADS, use_smem ? bytes : 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SCR_THREADS, use_smem ? bytes : 0);
         if (per_sm < 1) per_sm = 1;
         long long tiles = ((long long)out.max_seg_cap + SCR_TM - 1) / SCR_TM * (long long)R.n_active;
         int gx = per_sm * sm_count();
         if ((long long)gx > tiles) gx = (int)tiles;
         if (gx < 1) gx = 1;
-        k_screen<KIND><<<gx, SCR_THREADS, use_smem ? bytes : 0, stream>>>(R, out, use_smem);
+        kern<<<gx, SCR_THREADS, use_smem ? bytes : 0, stream>>>(R, out, use_smem);
     }
 }
 void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, int mode, int max_n_pad,
@@ -1412,6 +1494,17 @@ __global__ void k_inlier_mask(const ProblemDev *__restrict__ probs, const MaskDe
             inl = cheirality_ok(M + 9, M + 13, bearing(x1_0, x1_1), bearing(x2_0, x2_1), 0.01);
         mask[k] = inl ? 1 : 0;
     }
+}
+// One bit per correspondence for the trip over PCIe (the host expands them to the caller's char[n]).
+__global__ void k_pack_mask(const char *__restrict__ mask, uint32_t *__restrict__ bits, size_t n_bytes) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_bytes) return; // n_bytes is a multiple of 32: whole warps leave together
+    const unsigned b = __ballot_sync(0xffffffffu, mask[k] != 0);
+    if ((threadIdx.x & 31) == 0) bits[k >> 5] = b;
+}
+void launch_pack_mask(const char *mask, uint32_t *bits, size_t n_bytes, cudaStream_t stream) {
+    if (n_bytes == 0) return;
+    k_pack_mask<<<(unsigned)((n_bytes + 255) / 256), 256, 0, stream>>>(mask, bits, n_bytes);
 }
 void launch_inlier_masks(int kind, const ProblemDev *probs, const MaskDesc *descs_dev, int n_desc, int max_n,
                          char *mask_base, cudaStream_t stream) {

@@ -25,6 +25,7 @@ struct ProblemDev {
     int rfc;        // real focal check (fundamental)
     int n_pad;      // array stride of ts
     const double *ts;
+    const float *cmax; // max |coordinate| of every SoA array (fp64 values rounded up): error bounds of the fp32 screening
 };
 
 constexpr __host__ __device__ bool kind_is_relpose(int kind) { return kind == KIND_RELPOSE || kind == KIND_RELPOSE_TS; }
@@ -186,6 +187,7 @@ struct TransposeDesc {
     const double *a, *b; // 2n and b_dim*n doubles
     double *s64;
     float *s32;
+    float *cmax; // 5 floats, zeroed before the launch (or null): per-array max |coordinate| (atomicMax of the bit patterns)
     int n, n_pad, b_dim, mode;
     double scale;
     CamDev cam_a, cam_b;
@@ -233,6 +235,8 @@ void launch_pass1(const Pass1Args &A, cudaStream_t stream);
 // Final inlier masks (robust/utils.cc:331-351,374-383,434-513): one descriptor per mask, sq_thr from the problem.
 void launch_inlier_masks(int kind, const ProblemDev *probs, const MaskDesc *descs_dev, int n_desc, int max_n,
                          char *mask_base, cudaStream_t stream);
+// Inlier masks as bits (bit k & 31 of word k >> 5) for the device -> host copy; n_bytes is a multiple of 32.
+void launch_pack_mask(const char *mask, uint32_t *bits, size_t n_bytes, cudaStream_t stream);
 // Batched direct solver calls (solvers/*.h surface): one warp per instance.
 void launch_solver_batch(int kind, int variant, size_t count, const double *a, const double *b, double *out,
                          int *n_out, int flags, cudaStream_t stream);
