@@ -183,6 +183,118 @@ def reference_sources_leg(P, x1, x2, opts, me, threads, stats, cnts):
             "note": "PoseLib sources unmodified on mini-Eigen (no Eigen3 in this image); slower than a real-Eigen build"}
 
 
+# ---- the other BASELINE.json configs, single calls, config 5 ----------------------------------------------------
+def config_batches(cabi, rank, quick):
+    """Batches of BASELINE configs 1, 3 and 4 for plb_ransac_batch (ransac_* level, calibrated points), own data per rank."""
+    F = G.FOCAL
+    n1, n3, n4d, n4s = (256, 4, 2, 2) if quick else (1024, 16, 8, 4)
+    out = {}
+    probs = []
+    for i in range(n1):
+        p = G.config_c1(rank * n1 + i)
+        probs.append(dict(kind="pnp", a=p["x"] / F, b=p["X"], ransac=cabi.RansacOpt(seed=i, **p["ransac"]), max_error=12.0 / F))
+    out["c1"] = dict(problems=probs, n=200, bytes_per_corr=20, what=f"{n1} x p3p absolute pose C1 (200 corrs, 50% inliers, 1000 its)")
+    probs = []
+    for i in range(n3):
+        p = G.config_c3(rank * n3 + i)
+        probs.append(dict(kind="fundamental", a=p["x1"] / F, b=p["x2"] / F, ransac=cabi.RansacOpt(seed=i, **p["ransac"]),
+                          max_error=1.0 / F, rfc=True))
+    out["c3"] = dict(problems=probs, n=5000, bytes_per_corr=16,
+                     what=f"{n3} x relpose_7pt fundamental C3 (5000 corrs, 20% inliers, PROSAC, real_focal_check, max 100000 its)")
+    probs = []
+    for d in range(n4d):  # the plane generator is slow on the host: n4d data sets x n4s RANSAC seeds
+        p = G.config_c4(rank * n4d + d)
+        for sd in range(n4s):
+            probs.append(dict(kind="homography", a=p["x1"] / F, b=p["x2"] / F, ransac=cabi.RansacOpt(seed=sd, **p["ransac"]),
+                              max_error=1.0 / F))
+    out["c4"] = dict(problems=probs, n=20000, bytes_per_corr=16,
+                     what=f"{n4d * n4s} x homography_4pt C4 (20000 corrs, 60% inliers, LO refit TRUNCATED; {n4d} data sets x {n4s} seeds)")
+    return out
+
+
+def run_config(cabi, torch, flush, cfg, streams, steps):
+    """Timed passes of one config batch through plb_ransac_batch (host buffers) + one single-group pass for the kernel
+    shares (CUDA-event durations are not inflated by kernels of other groups when only one group is in flight)."""
+    probs = cfg["problems"]
+    cabi.ransac_batch(probs, streams=streams)  # buffers
+    t_tot, agg = 0.0, None
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = cabi.ransac_batch(probs, streams=streams)
+        torch.cuda.synchronize()
+        t_tot += time.perf_counter() - t0
+        c = {k: sum(r["counters"][k] for r in res) for k in res[0]["counters"]}
+        agg = c if agg is None else {k: agg[k] + c[k] for k in c}
+    cabi.ransac_batch(probs, streams=1)
+    flush.zero_()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res1 = cabi.ransac_batch(probs, streams=1)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter() - t0
+    k = {kk: sum(r["counters"][kk] for r in res1) for kk in res1[0]["counters"]}
+    return t_tot, agg, t1, k
+
+
+def single_calls(cabi, reps=7):
+    """Latency of ONE plb_estimate_* call (pixels in, model + inlier mask out, final bundle included) on one problem of
+    each BASELINE config 1-4: median of `reps` calls after two warm-up calls."""
+    F = G.FOCAL
+    cam = cabi.Camera("PINHOLE", (F, F, 0.0, 0.0))
+    bo = cabi.BundleOpt()
+    out = {}
+    cases = []
+    p = G.config_c1(0)
+    cases.append(("c1", "pnp", p["x"], p["X"], p, dict(cam1=cam), 12.0))
+    p = G.config_c2(0)
+    cases.append(("c2", "relpose", p["x1"], p["x2"], p, dict(cam1=cam, cam2=cam), 1.0))
+    p = G.config_c3(0)
+    cases.append(("c3", "fundamental", p["x1"], p["x2"], p, dict(rfc=True), 1.0))
+    p = G.config_c4(0)
+    cases.append(("c4", "homography", p["x1"], p["x2"], p, dict(), 1.0))
+    for name, kind, a, b, p, kw, me in cases:
+        ro = cabi.RansacOpt(**p["ransac"])
+        ts, last = [], None
+        for i in range(reps + 2):
+            t0 = time.perf_counter()
+            last = cabi.estimate(kind, a, b, ro, bo, me, **kw)
+            dt = time.perf_counter() - t0
+            if i >= 2:
+                ts.append(dt)
+        ts.sort()
+        c = last["counters"]
+        out[name] = {"entry": "plb_estimate_" + {"pnp": "absolute_pose", "relpose": "relative_pose", "fundamental": "fundamental",
+                                                  "homography": "homography"}[kind],
+                     "ms": 1e3 * ts[len(ts) // 2], "ms_min": 1e3 * ts[0], "iterations": last["stats"]["iterations"],
+                     "hypotheses": c["hypotheses"], "rounds": c["rounds"], "gpu_launches": c["gpu_launches"],
+                     "h2d_bytes": c["h2d_bytes"], "d2h_bytes": c["d2h_bytes"]}
+    return out
+
+
+def c5_costs(count):
+    from poselib_b200 import sharding
+    return [sharding.expected_cost("pnp", 200, 1000) if i % 2 == 0 else sharding.expected_cost("relpose", 10000, 100000)
+            for i in range(count)]
+
+
+def c5_problems(cabi, indices):
+    F = G.FOCAL
+    probs = []
+    for i in indices:
+        i = int(i)
+        if i % 2 == 0:
+            p = G.abspose_problem(200, 0.5, 5, i)
+            probs.append(dict(kind="pnp", a=p["x"] / F, b=p["X"], ransac=cabi.RansacOpt(max_iterations=1000, min_iterations=1000),
+                              max_error=12.0 / F))
+        else:
+            p = G.relpose_problem(10000, 0.3, 5, i)
+            probs.append(dict(kind="relpose", a=p["x1"] / F, b=p["x2"] / F,
+                              ransac=cabi.RansacOpt(max_iterations=100000, min_iterations=1000), max_error=1.0 / F))
+    return probs
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,7 +304,12 @@ def main():
     ap.add_argument("--streams", type=int, default=12, help="lock-step problem groups in flight per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="fast", choices=["exact", "fast"],
-                    help="fast: fp32 SMEM screening of every model + fp64 confirmation of candidates (identical results)")
+                    help="fast (the library default): fp32 SMEM screening of every model with rigorous error intervals + "
+                         "fp64 confirmation of candidates (identical results)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline only: skip the configs 1/3/4 batches, the single calls and the config-5 strong-scaling pass")
+    ap.add_argument("--c5", type=int, default=4096, help="problems of the config-5 batch (sharded over the ranks)")
+    ap.add_argument("--quick", action="store_true", help="small extras (smoke test of the bench itself)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -303,6 +420,89 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # ---- extras: BASELINE configs 1, 3, 4 (batched), single calls, config 5 (strong scaling over the ranks) -------------
+    # Local work sits in try blocks; the collectives that aggregate it run unconditionally on every rank afterwards.
+    extras = {}
+    if not args.no_extras:
+        peak_x, _ = load_peaks()
+        try:
+            batches = config_batches(cabi, rank, args.quick)
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"[bench] config batches failed: {e}\n")
+            batches = {}
+        cfg_out = {}
+        for name in ("c1", "c3", "c4"):
+            loc = dict(t=1e30, hyp=0.0, cor=0.0, t1=0.0, k=None, problems=0)
+            try:
+                cfg = batches[name]
+                t_tot, agg, t1, k = run_config(cabi, torch, flush, cfg, args.streams, 2 if args.quick else 3)
+                loc = dict(t=t_tot, hyp=float(agg["hypotheses"]), cor=float(agg["scored_corrs"]), t1=t1, k=k,
+                           problems=len(cfg["problems"]))
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write(f"[bench] config {name} failed: {e}\n")
+            T = allmax(loc["t"])
+            H, Cr, NPb = allsum(loc["hyp"]), allsum(loc["cor"]), allsum(loc["problems"])
+            if rank == 0 and loc["k"] is not None and T < 1e29:
+                k, cfg, st = loc["k"], batches[name], (2 if args.quick else 3)
+                score_s = k["gpu_seconds_score"]
+                ach = k["models_evaluated"] * cfg["n"] * cfg["bytes_per_corr"] / score_s / 1e9 if score_s > 0 else 0.0
+                cfg_out[name] = {
+                    "workload": cfg["what"] + " per GPU per step", "problems_per_step": int(NPb), "value": H / T,
+                    "unit": "hypotheses/s", "scored_corrs_per_s": Cr / T, "ms_per_step": 1e3 * T / st,
+                    "kernels_single_group_pass": {
+                        "wall_s": loc["t1"], "solve_s": k["gpu_seconds"] - k["gpu_seconds_score"] - k["gpu_seconds_select"],
+                        "score_s": score_s, "select_confirm_s": k["gpu_seconds_select"], "lo_s": k["gpu_seconds_lo"],
+                        "rounds": int(k["rounds"]), "launches": int(k["gpu_launches"])},
+                    "roofline": {"bound": "hbm", "kernel": "k_screen (fp32 MSAC screening)", "achieved": ach, "peak": peak_x,
+                                 "unit": "GB/s", "frac": ach / peak_x, "bytes_per_scored_corr": cfg["bytes_per_corr"]}}
+        extras["configs"] = cfg_out
+        if rank == 0:
+            try:
+                extras["single_call"] = single_calls(cabi, 3 if args.quick else 7)
+            except Exception as e:  # noqa: BLE001
+                extras["single_call"] = {"failed": str(e)}
+        barrier()
+        # config 5: `--c5` independent problems (even index: C1-type p3p, odd: C2-type 5pt), LPT-partitioned over the
+        # ranks, results (records + inlier masks) gathered on every rank: STRONG scaling, total work fixed
+        loc5 = dict(t=1e30, hyp=0.0, cor=0.0, n=0, ok=1.0)
+        c5_count = 64 if args.quick else args.c5
+        try:
+            from poselib_b200 import sharding as _sh
+            part = _sh.partition(c5_costs(c5_count), world)[rank]
+            p5 = c5_problems(cabi, part)
+            cabi.ransac_batch(p5, streams=args.streams)
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"[bench] config 5 setup failed: {e}\n")
+            p5, part, loc5["ok"] = None, [], 0.0
+        c5_steps = 2
+        barrier()
+        t5, hyp5, cor5, gathered = 0.0, 0.0, 0.0, 0
+        for _ in range(c5_steps):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            res5 = cabi.ransac_batch(p5, streams=args.streams) if p5 else []
+            if p5:
+                hyp5 += sum(r["counters"]["hypotheses"] for r in res5)
+                cor5 += sum(r["counters"]["scored_corrs"] for r in res5)
+            if dist is not None:  # the only inter-GPU traffic: fixed-size records + bit-packed masks over NCCL
+                rec = _sh.gather_records(_sh.pack_results(list(zip([int(i) for i in part], res5))), dist)
+                gathered = len(rec)
+                _sh.gather_masks([r["inliers"] for r in res5], [int(i) for i in part], dist)
+            else:
+                gathered = len(res5)
+            torch.cuda.synchronize()
+            t5 += time.perf_counter() - t0
+        T5 = allmax(t5 if loc5["ok"] else 1e30)
+        H5, C5 = allsum(hyp5), allsum(cor5)
+        if rank == 0 and T5 < 1e29:
+            extras["c5"] = {"workload": f"{c5_count} independent problems (even: p3p C1-type, odd: 5pt C2-type), own data seeds, "
+                                        f"LPT-sharded over {world} rank(s); records and inlier masks gathered",
+                            "scaling": "strong", "problems": c5_count, "seconds_per_pass": T5 / c5_steps,
+                            "problems_per_s": c5_count * c5_steps / T5, "value": H5 / T5, "unit": "hypotheses/s",
+                            "scored_corrs_per_s": C5 / T5, "records_gathered": int(gathered)}
+        barrier()
+
     T_res, T_e2e = allmax(t_res), allmax(t_e2e)
     T_other = allmax(t_other if t_other == t_other else 1e30)
     hyp_o = allsum(hyp_other)
@@ -327,6 +527,24 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic_scoring_kernel.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(args.mode, {}).get("dram_bytes_per_launch")
+        # The §8d yardstick is an HBM-read roofline, but the kernel does not stream from HBM: operands are staged once per
+        # CTA into shared memory by TMA and reused by every model.  What actually binds it is the instruction issue rate:
+        # thread-instructions per (model, correspondence) pair from the committed ncu capture x pairs/s vs the SM issue
+        # peak at the measured clock.
+        binding = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "issue_model.json")))[args.mode]
+            pairs_per_s = c_roof["models_evaluated"] * n / k_sec if k_sec > 0 else 0.0
+            clk = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+            peak_issue = 148 * 4 * 32 * clk  # thread-instructions/s: 4 warp-instructions per clock per SM
+            binding = {"resource": "instruction issue (fp32 FMA + compare/record per pair), not HBM",
+                       "thread_instr_per_pair": prof["thread_instr_per_pair"], "source": prof["source"],
+                       "pairs_per_s": pairs_per_s, "achieved_thread_instr_per_s": pairs_per_s * prof["thread_instr_per_pair"],
+                       "peak_thread_instr_per_s": peak_issue,
+                       "frac_of_issue_peak": pairs_per_s * prof["thread_instr_per_pair"] / peak_issue,
+                       "whole_step_hbm_frac": (c_res["models_evaluated"] * n * bpc / T_res / 1e9) / peak}
+        except Exception as e:  # noqa: BLE001
+            binding = {"resource": "instruction issue, not HBM", "unavailable": str(e)}
         line = {
             "metric": "RANSAC hypotheses/sec (5pt E, 10k corrs)", "value": hyp / T_res, "unit": "hypotheses/s",
             "scored_corrs_per_s": cor / T_res, "samples_per_s": smp / T_res,
@@ -347,12 +565,14 @@ def main():
                            "ms_per_step": (1e3 * T_other / steps_other) if T_other < 1e29 else None,
                            "results_identical_to_headline_mode": bool(same_o == world),
                            "note": "same resident batch; stats, model bits and inlier masks compared problem by problem"},
-            "roofline": {"bound": "hbm", "kernel": "k_screen<relpose> (fp32 MSAC screening, TMA-staged SMEM)" if args.mode == "fast"
+            "roofline": {"bound": "hbm", "binding": binding, "kernel": "k_screen<relpose> (fp32 MSAC screening, TMA-staged SMEM)" if args.mode == "fast"
                          else "k_score_tiled<relpose> (fp64 MSAC scoring)", "achieved": ach,
                          "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "bytes_per_scored_corr": bpc,
                          "algorithmic_bytes_per_step": alg_bytes / roof_steps, "kernel_seconds_per_step": k_sec / roof_steps,
-                         "solver_kernels_seconds_per_step": (k_sec_all - k_sec) / roof_steps,
+                         "solver_kernels_seconds_per_step": (k_sec_all - k_sec - c_roof["gpu_seconds_select"]) / roof_steps,
+                         "select_confirm_seconds_per_step": c_roof["gpu_seconds_select"] / roof_steps,
+                         "lo_seconds_per_step": c_roof["gpu_seconds_lo"] / roof_steps,
                          "kernel_share_of_step": k_sec / t_roof if t_roof > 0 else None,
                          "measured": f"{roof_steps} extra steps of the same workload with one lock-step group in flight "
                                      "(kernel durations by CUDA events on the engine's stream, no co-running kernels)",
@@ -363,6 +583,7 @@ def main():
                                  "slots, profiles/r01_v7_summary.md)"},
             "clocks": sampler.summary(),
         }
+        line.update(extras)
         # CPU baseline on this box's host cores: 1 thread (the reference's execution model), bounded sample
         try:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -80,12 +80,15 @@ typedef struct plb_counters {
     double lo_seconds;      /* host wall time spent waiting on LO kernels */
     uint64_t gpu_launches;  /* kernels launched for this call */
     uint64_t samples_evaluated; /* incl. speculative samples past the serial break point */
-    double gpu_seconds;     /* CUDA-event time of the hypothesis kernels (solve + score) */
+    double gpu_seconds;     /* CUDA-event time of the hypothesis kernels (sample + solve + score + select/confirm) */
     uint64_t h2d_bytes;     /* bytes copied host -> device for this call */
     uint64_t d2h_bytes;     /* bytes copied device -> host for this call */
     uint64_t models_evaluated; /* models scored by the hypothesis kernels incl. speculative samples */
     uint64_t models_confirmed; /* fast mode: models rescored in fp64 after the fp32 screening pass */
     double gpu_seconds_score;  /* CUDA-event time of the scoring / screening kernels alone (part of gpu_seconds) */
+    double gpu_seconds_select; /* candidate selection + fp64 confirmation of the candidates (part of gpu_seconds) */
+    double gpu_seconds_lo;     /* best-minimal pass + LO refinements (k_pass1 + k_lm) of the rounds, CUDA events */
+    uint64_t rounds;           /* lock-step rounds (= host synchronisations inside the loop) of the problem's group */
 } plb_counters;
 
 /* misc/camera_models.h:39-157 Camera, restricted to the six models on the path (others -> PLB_ERR_NYI, like the
@@ -182,6 +185,15 @@ int plb_relpose_7pt_batch(size_t count, const double *x1 /*count*7*3*/, const do
 int plb_homography_4pt_batch(size_t count, const double *x1 /*count*4*3*/, const double *x2,
                              double *H_out /*count*9*/, int32_t *n_out, int check_cheirality);
 
+/* solvers/relpose_8pt.h:45-53 (non-minimal): `count` instances of n >= 8 unit bearing pairs each (x1, x2: count*n*3).
+ * essential_matrix_8pt: E_out count*9, column-major (Eigen::Matrix3d).  relpose_8pt: the poses of motion_from_essential
+ * that pass the cheirality test on all n correspondences, poses_out count*4*7, n_out[i] = their number.
+ * n == 8 takes the Householder nullspace (relpose_8pt.cc:63-67); n > 8 the smallest eigenvector of A^T A (:68-72) — an
+ * iterative eigen-solver in the reference as here, so results agree to tolerance, not bit for bit. */
+int plb_essential_matrix_8pt_batch(size_t count, size_t n, const double *x1, const double *x2, double *E_out);
+int plb_relpose_8pt_batch(size_t count, size_t n, const double *x1, const double *x2, double *poses_out /*count*4*7*/,
+                          int32_t *n_out);
+
 /* ---- PoseLib/robust/bundle.h: bundle_adjust (calibrated, :41-43), refine_relpose (:84-86), refine_fundamental
  * (:132-134), refine_homography (:148-150) — the LM refiners the LO step and the final polish are built from.
  * Uniform weights.  bundle_stats_out (may be NULL): {iterations, initial_cost, cost}. ------------------------- */
@@ -223,6 +235,32 @@ int plb_ransac_batch(plb_problem *problems, size_t count, int streams);
  * (stats, models, inlier masks) are written straight into the caller's array.  No collective: image pairs are
  * independent (robust/ransac.cc:144-148).  Resident inputs stay on the device that holds them. */
 int plb_ransac_batch_multi(plb_problem *problems, size_t count, int n_gpus, int streams_per_gpu);
+
+/* Batch form of estimate_{absolute_pose,relative_pose,fundamental,homography} (robust.h:45-46,68-70,112-113,133-134):
+ * every problem takes what the single entry point takes — points in the pixel units of its cameras, RansacOptions,
+ * BundleOptions, max_error — so distorted cameras, the tangent-Sampson estimator and the F / H normalisation batch too. */
+typedef struct plb_estimate_problem {
+    int32_t kind;             /* PLB_KIND_* */
+    int32_t real_focal_check; /* fundamental only (RelativePoseOptions::real_focal_check) */
+    int32_t tangent_sampson;  /* relative pose only (RelativePoseOptions::tangent_sampson) */
+    int32_t reserved;
+    uint64_t n;
+    const double *a;          /* points2D (pnp) or x1: 2n doubles */
+    const double *b;          /* points3D (pnp): 3n doubles; else x2: 2n doubles */
+    plb_camera camera1;       /* pnp: the camera; relative pose: camera 1; ignored by fundamental / homography */
+    plb_camera camera2;       /* relative pose: camera 2 */
+    plb_ransac_opt ransac;
+    plb_bundle_opt bundle;
+    double max_error;         /* pixels (AbsolutePoseOptions / RelativePoseOptions / HomographyOptions::max_error) */
+    double model[9];          /* in/out */
+    char *inliers;            /* n bytes or NULL */
+    plb_ransac_stats stats;   /* out */
+    plb_counters counters;    /* out */
+    int32_t status;           /* out */
+    int32_t reserved2;
+} plb_estimate_problem;
+/* n_gpus: 0 = every device of the process, k > 0 = the first k, -1 = the calling thread's device (plb_set_device). */
+int plb_estimate_batch(plb_estimate_problem *problems, size_t count, int n_gpus, int streams_per_gpu);
 
 /* Correspondences kept resident in HBM across calls (measurement of the device-resident throughput, and callers
  * that run several estimations on the same matches).  kind: PLB_KIND_*; returns a handle > 0 or an error < 0. */

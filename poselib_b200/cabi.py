@@ -66,7 +66,8 @@ class Counters(C.Structure):
                 ("lo_calls", C.c_uint64), ("lo_seconds", C.c_double), ("gpu_launches", C.c_uint64),
                 ("samples_evaluated", C.c_uint64), ("gpu_seconds", C.c_double), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("models_evaluated", C.c_uint64), ("models_confirmed", C.c_uint64),
-                ("gpu_seconds_score", C.c_double)]
+                ("gpu_seconds_score", C.c_double), ("gpu_seconds_select", C.c_double), ("gpu_seconds_lo", C.c_double),
+                ("rounds", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -95,10 +96,18 @@ EXPORTS = [
     "plb_ransac_homography",
     "plb_estimate_absolute_pose", "plb_estimate_relative_pose", "plb_estimate_fundamental",
     "plb_estimate_homography", "plb_p3p_batch", "plb_relpose_5pt_batch", "plb_relpose_5pt_poses_batch",
-    "plb_relpose_7pt_batch", "plb_homography_4pt_batch", "plb_ransac_batch", "plb_ransac_batch_multi", "plb_bundle_adjust",
+    "plb_relpose_7pt_batch", "plb_homography_4pt_batch", "plb_essential_matrix_8pt_batch", "plb_relpose_8pt_batch", "plb_ransac_batch", "plb_ransac_batch_multi", "plb_estimate_batch", "plb_bundle_adjust",
     "plb_refine_relpose", "plb_refine_relpose_cameras", "plb_refine_fundamental", "plb_refine_homography", "plb_resident_create",
     "plb_resident_free",
 ]
+
+class EstimateProblem(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("real_focal_check", C.c_int32), ("tangent_sampson", C.c_int32), ("reserved", C.c_int32),
+                ("n", C.c_uint64), ("a", C.POINTER(C.c_double)), ("b", C.POINTER(C.c_double)),
+                ("camera1", Camera), ("camera2", Camera), ("ransac", RansacOpt), ("bundle", BundleOpt),
+                ("max_error", C.c_double), ("model", C.c_double * 9), ("inliers", C.c_char_p),
+                ("stats", RansacStats), ("counters", Counters), ("status", C.c_int32), ("reserved2", C.c_int32)]
+
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -305,6 +314,28 @@ def homography_4pt_batch(x1, x2, check_cheirality=True):
     return out.reshape(-1, 3, 3).transpose(0, 2, 1), n
 
 
+def essential_matrix_8pt_batch(x1, x2):
+    """solvers/relpose_8pt.h essential_matrix_8pt for [count, n, 3] unit bearings (n >= 8) -> E [count, 3, 3] ([r,c])."""
+    aa, ap = _d(x1)
+    ba, bp = _d(x2)
+    count, n = aa.shape[0], aa.shape[1]
+    out = np.zeros((count, 9))
+    _check(_lib.plb_essential_matrix_8pt_batch(C.c_size_t(count), C.c_size_t(n), ap, bp, out.ctypes.data_as(_P)))
+    return out.reshape(-1, 3, 3).transpose(0, 2, 1)
+
+
+def relpose_8pt_batch(x1, x2):
+    """solvers/relpose_8pt.h relpose_8pt for [count, n, 3] unit bearings -> (poses [count, 4, 7], n_poses [count])."""
+    aa, ap = _d(x1)
+    ba, bp = _d(x2)
+    count, n = aa.shape[0], aa.shape[1]
+    out = np.zeros((count, 28))
+    n_out = np.zeros(count, dtype=np.int32)
+    _check(_lib.plb_relpose_8pt_batch(C.c_size_t(count), C.c_size_t(n), ap, bp, out.ctypes.data_as(_P),
+                                      n_out.ctypes.data_as(C.POINTER(C.c_int32))))
+    return out.reshape(-1, 4, 7), n_out
+
+
 def resident_create(kind, a, b):
     """Uploads correspondences once and keeps them in HBM; returns a handle for ransac_batch(resident=...)."""
     aa, ap = _d(a)
@@ -353,6 +384,45 @@ def ransac_batch(problems, streams=8, n_gpus=None):
         _check(_lib.plb_ransac_batch(arr, C.c_size_t(count), int(streams)))
     else:
         _check(_lib.plb_ransac_batch_multi(arr, C.c_size_t(count), int(n_gpus), int(streams)))
+    out = []
+    for i, p in enumerate(problems):
+        q = arr[i]
+        kind = p["kind"]
+        m = np.array(q.model[:7] if kind in ("pnp", "relpose") else q.model[:9], dtype=np.float64)
+        out.append({"model": _model_out(kind, m), "inliers": keep[i][2][:q.n].copy(), "stats": q.stats.as_dict(),
+                    "counters": q.counters.as_dict(), "status": q.status})
+    return out
+
+
+def estimate_batch(problems, streams=8, n_gpus=-1):
+    """Batch form of estimate() (plb_estimate_batch).  problems: list of dict(kind, a, b, ransac=RansacOpt, bundle=BundleOpt,
+    max_error [pixels], cam1=None, cam2=None, rfc=False, tangent_sampson=False, init=None).  n_gpus: -1 current device,
+    0 all devices, k the first k.  Returns list of dict(model, inliers, stats, counters, status)."""
+    count = len(problems)
+    arr = (EstimateProblem * count)()
+    keep = []
+    for i, p in enumerate(problems):
+        q = arr[i]
+        aa, ap = _d(p["a"])
+        ba, bp = _d(p["b"])
+        npts = len(aa)
+        mask = np.zeros(max(npts, 1), dtype=np.int8)
+        keep.append((aa, ba, mask))
+        q.kind = KIND[p["kind"]]
+        q.real_focal_check = int(p.get("rfc", False))
+        q.tangent_sampson = int(p.get("tangent_sampson", False))
+        q.n = npts
+        q.a, q.b = ap, bp
+        q.camera1 = p.get("cam1") or Camera("NULL", ())
+        q.camera2 = p.get("cam2") or Camera("NULL", ())
+        q.ransac = p["ransac"]
+        q.bundle = p["bundle"]
+        q.max_error = p["max_error"]
+        m = _init_model(p["kind"], p.get("init"))
+        for k in range(len(m)):
+            q.model[k] = m[k]
+        q.inliers = C.cast(mask.ctypes.data_as(C.POINTER(C.c_char)), C.c_char_p)
+    _check(_lib.plb_estimate_batch(arr, C.c_size_t(count), int(n_gpus), int(streams)))
     out = []
     for i, p in enumerate(problems):
         q = arr[i]

@@ -36,11 +36,29 @@ CTL_DEV uint64_t splitmix_value(uint64_t st, uint32_t j) {
     z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
     return z ^ (z >> 31);
 }
-// sampling.cc:50: random_int returns `int`; `% N` happens after the conversion to size_t, i.e. after sign extension
-CTL_DEV uint32_t draw_mod(uint64_t z, uint32_t n) {
+// sampling.cc:50: random_int returns `int`; `% N` happens after the conversion to size_t, i.e. after sign extension:
+// a negative v is the 64-bit value 2^64 - |v|.  Both cases reduce to 32-bit remainders, computed without a division
+// (Lemire's fastmod: M = floor((2^64 - 1) / n) + 1, a mod n = hi64((M * a mod 2^64) * n), exact for 32-bit a and n).
+struct ModN {
+    uint64_t M;
+    uint32_t n, r64; // r64 = 2^64 mod n
+};
+CTL_DEV ModN make_mod(uint32_t n) {
+    ModN m;
+    m.n = n;
+    m.M = 0xFFFFFFFFFFFFFFFFull / n + 1ull;
+    m.r64 = (uint32_t)((0ull - (uint64_t)n) % (uint64_t)n); // (2^64 - n) mod n
+    return m;
+}
+CTL_DEV uint32_t fastmod(uint32_t a, const ModN &m) { return (uint32_t)__umul64hi(m.M * (uint64_t)a, (uint64_t)m.n); }
+CTL_DEV uint32_t draw_mod(uint64_t z, const ModN &m) {
     const int32_t v = (int32_t)(uint32_t)z;
-    if (v >= 0) return (uint32_t)v % n;
-    return (uint32_t)(((uint64_t)(int64_t)v) % (uint64_t)n);
+    if (v >= 0) return fastmod((uint32_t)v, m);
+    const uint32_t w = fastmod(0u - (uint32_t)v, m); // |v| mod n   (|v| <= 2^31)
+    uint32_t r = m.r64 + (m.n - w);                   // (2^64 - |v|) mod n  =  (r64 - w) mod n ;  r < 2n
+    if (r >= m.n) r -= m.n;
+    if (r >= m.n) r -= m.n;
+    return r;
 }
 // PROSAC subset size after one more sample has been drawn (sampling.cc:97-101); k_pre = sample_k before the draw
 CTL_DEV uint32_t prosac_step(const SamplerDev &S, uint32_t sub, uint64_t k_pre) {
@@ -50,23 +68,6 @@ CTL_DEV uint32_t prosac_step(const SamplerDev &S, uint32_t sub, uint64_t k_pre) 
             if (++sub > S.n) sub = S.n;
         }
     }
-    return sub;
-}
-// Subset size in force when sample_k == k (k < max_prosac), given the size `sub0` in force at k0 <= k.
-// growth[] strictly increasing from index sample_sz - 1 on (flag bit 1): the size is the smallest m >= sub0 with
-// growth[m-1] >= k, capped at n (the subset grows by at most one per sample, exactly when k passes growth[m-1]).
-CTL_DEV uint32_t prosac_subset(const SamplerDev &S, uint32_t sub0, uint64_t k0, uint64_t k) {
-    if (S.flags & 2u) {
-        uint32_t lo = sub0, hi = S.n; // answer in [lo, hi]
-        while (lo < hi) {
-            const uint32_t mid = lo + ((hi - lo) >> 1);
-            if (S.growth[mid - 1] >= k) hi = mid;
-            else lo = mid + 1;
-        }
-        return lo;
-    }
-    uint32_t sub = sub0;
-    for (uint64_t kk = k0; kk < k; ++kk) sub = prosac_step(S, sub, kk);
     return sub;
 }
 
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(128) k_sample(const RoundProb *__restrict__ rp
     const bool prosac = (S.flags & 1u) != 0;
     uint64_t state = S.state, sample_k = S.sample_k;
     uint32_t subset = S.subset_sz;
+    const ModN modN = make_mod(N);
     int s = 0;
     while (s < R.B) {
         const int my_s = s + lane;
@@ -93,31 +95,68 @@ __global__ void __launch_bounds__(128) k_sample(const RoundProb *__restrict__ rp
         }
         const bool pro = (uint32_t)lane < n_pro_window;
         const uint32_t n_pro_before = (uint32_t)lane < n_pro_window ? (uint32_t)lane : n_pro_window;
-        const uint32_t kd = pro ? K - 1 : K;  // draws this sample needs when nothing is rejected
+        const uint32_t kd = pro ? K - 1 : K; // draws this sample needs when nothing is rejected
         const uint32_t off = n_pro_before * (K - 1) + ((uint32_t)lane - n_pro_before) * K;
         const uint64_t my_k = sample_k + (uint64_t)lane;
+        // PROSAC subset size in force when sample_k == my_k (sampling.cc:97-101): the subset grows by at most one per
+        // sample, exactly when sample_k passes growth[subset - 1].  With growth[] strictly increasing (flag bit 1) the
+        // size at sample_k + l is  subset + #{j >= 0 : growth[subset - 1 + j] < sample_k + l}: lane j looks at entry j,
+        // the first lane index l that has passed it is d_j = growth[subset-1+j] - sample_k + 1, one OR-reduction of the
+        // bits 1 << d_j and a population count per lane give every lane its subset size.
         uint32_t my_subset = N;
-        if (pro && live) my_subset = prosac_subset(S, subset, sample_k, my_k);
+        if (n_pro_window) {
+            if (S.flags & 2u) {
+                uint32_t bit = 0u;
+                const uint64_t gi = (uint64_t)subset - 1ull + (uint64_t)lane;
+                if (gi < (uint64_t)N) {
+                    const uint64_t g = S.growth[gi];
+                    if (g < sample_k) bit = 1u; // already passed (cannot happen for j = 0; kept for safety)
+                    else if (g - sample_k + 1ull < 32ull) bit = 1u << (uint32_t)(g - sample_k + 1ull);
+                }
+                const uint32_t passed = __reduce_or_sync(FULL, bit);
+                const uint32_t le = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
+                my_subset = subset + (uint32_t)__popc(passed & le);
+                if (my_subset > N) my_subset = N;
+            } else { // general rule, step by step
+                uint32_t sub = subset;
+                for (uint64_t kk = sample_k; kk < my_k; ++kk) sub = prosac_step(S, sub, kk);
+                my_subset = sub;
+            }
+        }
         uint32_t idx[SAMPLE_MAX_K];
 #pragma unroll
-        for (int i = 0; i < SAMPLE_MAX_K; ++i) idx[i] = 0xffffffffu;
+        for (int i = 0; i < SAMPLE_MAX_K; ++i) idx[i] = 0xffffffffu - (uint32_t)i;
         uint32_t c = kd;
         if (live) {
-            const uint32_t nsub = pro ? my_subset - 1 : N; // sampling.cc:87 draws from the first subset_sz - 1 points
-            c = 0;
+            // sampling.cc:87 draws from the first subset_sz - 1 points
+            const ModN mod = pro ? make_mod(my_subset - 1) : modN;
+            // fast path: the first kd values of the stream, all computed before any is compared (independent chains)
+            bool distinct = true;
 #pragma unroll
-            for (int i = 0; i < SAMPLE_MAX_K; ++i) {
-                if ((uint32_t)i < kd) {
-                    for (;;) { // sampling.cc:46-61: redraw while the index is already in the sample
-                        ++c;
-                        const uint32_t v = draw_mod(splitmix_value(state, off + c), nsub);
-                        bool dup = false;
+            for (int i = 0; i < SAMPLE_MAX_K; ++i)
+                if ((uint32_t)i < kd) idx[i] = draw_mod(splitmix_value(state, off + 1u + (uint32_t)i), mod);
 #pragma unroll
-                        for (int j = 0; j < SAMPLE_MAX_K; ++j)
-                            if (j < i) dup |= (idx[j] == v);
-                        if (!dup) {
-                            idx[i] = v;
-                            break;
+            for (int i = 1; i < SAMPLE_MAX_K; ++i)
+#pragma unroll
+                for (int j = 0; j < i; ++j)
+                    if ((uint32_t)i < kd) distinct &= (idx[i] != idx[j]);
+            if (!distinct) {
+                // sampling.cc:46-61: redraw while the index is already in the sample
+                c = 0;
+#pragma unroll
+                for (int i = 0; i < SAMPLE_MAX_K; ++i) {
+                    if ((uint32_t)i < kd) {
+                        for (;;) {
+                            ++c;
+                            const uint32_t v = draw_mod(splitmix_value(state, off + c), mod);
+                            bool dup = false;
+#pragma unroll
+                            for (int j = 0; j < SAMPLE_MAX_K; ++j)
+                                if (j < i) dup |= (idx[j] == v);
+                            if (!dup) {
+                                idx[i] = v;
+                                break;
+                            }
                         }
                     }
                 }

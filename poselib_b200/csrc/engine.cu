@@ -203,7 +203,7 @@ __global__ void k_gather_models(const double *__restrict__ models, const int *__
 
 struct Engine {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;
     bool ready = false;
     int device = -1;
     DevBuf<double> in, soa64, px64, models, lm_in, s5_blk, s5_cpoly, s5_roots;
@@ -231,6 +231,9 @@ struct Engine {
     PinBuf<uint32_t> h_mask_bits;
     DevBuf<ProblemDev> probs;
     DevBuf<TransposeDesc> tdesc;
+    DevBuf<NormDesc> ndesc;
+    PinBuf<NormDesc> h_ndesc;
+    MapBuf<double> h_norm;
     DevBuf<MaskDesc> mdesc;
     DevBuf<LmJob> jobs;
     PinBuf<double> h_in, h_lm_in;
@@ -271,6 +274,7 @@ struct Engine {
         if (!ev1) PLB_CUDA(cudaEventCreate(&ev1));
         if (!ev2) PLB_CUDA(cudaEventCreate(&ev2));
         if (!ev3) PLB_CUDA(cudaEventCreate(&ev3));
+        if (!ev4) PLB_CUDA(cudaEventCreate(&ev4));
         {
             int r = h_work.ensure(8);
             if (r) return r;
@@ -422,6 +426,78 @@ struct FinalPolish { // the post-RANSAC refinement of PoseLib/robust.cc (estimat
     CamDev cam{CAMM_NULL, 0, {0, 0, 0, 0, 0, 0, 0, 0}};
 };
 
+// ---- small host-side 3x3 helpers for the estimate_* wrappers (column-major <-> row-major) ---------------------
+struct HM3 {
+    double m[3][3];
+};
+static HM3 hm_identity() {
+    HM3 r;
+    std::memset(&r, 0, sizeof(r));
+    r.m[0][0] = r.m[1][1] = r.m[2][2] = 1;
+    return r;
+}
+static HM3 hm_mul(const HM3 &A, const HM3 &B) {
+    HM3 C;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C.m[i][j] = A.m[i][0] * B.m[0][j] + A.m[i][1] * B.m[1][j] + A.m[i][2] * B.m[2][j];
+    return C;
+}
+static HM3 hm_T(const HM3 &A) {
+    HM3 C;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C.m[i][j] = A.m[j][i];
+    return C;
+}
+static HM3 hm_inv(const HM3 &M) {
+    const double(*m)[3] = M.m;
+    HM3 c;
+    c.m[0][0] = m[1][1] * m[2][2] - m[1][2] * m[2][1];
+    c.m[1][0] = m[1][2] * m[2][0] - m[1][0] * m[2][2];
+    c.m[2][0] = m[1][0] * m[2][1] - m[1][1] * m[2][0];
+    c.m[0][1] = m[0][2] * m[2][1] - m[0][1] * m[2][2];
+    c.m[1][1] = m[0][0] * m[2][2] - m[0][2] * m[2][0];
+    c.m[2][1] = m[0][1] * m[2][0] - m[0][0] * m[2][1];
+    c.m[0][2] = m[0][1] * m[1][2] - m[0][2] * m[1][1];
+    c.m[1][2] = m[0][2] * m[1][0] - m[0][0] * m[1][2];
+    c.m[2][2] = m[0][0] * m[1][1] - m[0][1] * m[1][0];
+    const double det = c.m[0][0] * m[0][0] + c.m[1][0] * m[0][1] + c.m[2][0] * m[0][2];
+    const double id = 1.0 / det;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) c.m[i][j] *= id;
+    return c;
+}
+static double hm_norm(const HM3 &A) {
+    double s = 0;
+    for (int j = 0; j < 3; ++j)
+        for (int i = 0; i < 3; ++i) s += A.m[i][j] * A.m[i][j];
+    return std::sqrt(s);
+}
+static HM3 hm_from_cm(const double *p) {
+    HM3 r;
+    for (int k = 0; k < 9; ++k) r.m[k % 3][k / 3] = p[k];
+    return r;
+}
+static void hm_to_cm(const HM3 &A, double *p) {
+    for (int k = 0; k < 9; ++k) p[k] = A.m[k % 3][k / 3];
+}
+
+// T1, T2 of normalize_points (utils.cc:596-600,622-643) from its centroids and scale: translation by -centroid, then the
+// first two rows scaled by 1 / scale
+static void norm_transforms(const double *o, HM3 &T1, HM3 &T2) {
+    T1 = hm_identity();
+    T2 = hm_identity();
+    T1.m[0][2] = -o[0];
+    T1.m[1][2] = -o[1];
+    T2.m[0][2] = -o[2];
+    T2.m[1][2] = -o[3];
+    const double scale = o[4];
+    for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 3; ++c) {
+            T1.m[r][c] *= 1.0 / scale;
+            T2.m[r][c] *= 1.0 / scale;
+        }
+}
+
 // One LO-RANSAC problem handed to the group engine (points already calibrated / normalised).
 struct Task {
     int kind = 0;
@@ -436,6 +512,13 @@ struct Task {
     plb_counters *cnt_out = nullptr;
     FinalPolish polish;
     const Resident *res = nullptr;
+    bool skip = false; // nothing to run (estimate_* with too few points): the batch runner leaves it alone
+    // normalize_points on the device before anything else (estimate_fundamental / estimate_homography, robust.cc:561,724):
+    // 0 none, 1 scale only (real_focal_check keeps the principal point at the origin), 2 centroid + scale.  max_error and
+    // the polish loss scale are then given in the units of the raw points and divided by the scale once it is known
+    // (robust.cc:562-564,725-727); norm_out receives centroid1, centroid2, scale for the caller's un-normalisation.
+    int norm_mode = 0;
+    double norm_out[5] = {0, 0, 0, 0, 1};
     // camera pre-step fused into the layout kernel (TransposeDesc modes): 0 none, 1 unproject to 2D, 2 tangent Sampson
     int pre_mode = 0;
     double pre_scale = 1.0;
@@ -459,6 +542,7 @@ struct PState {
     // per round
     size_t B = 0, g0 = 0;
     long long mask_off = 0;
+    long long in_off = -1; // offset of this problem's uploaded AoS input in Engine::in (not resident)
     int polish_pidx = -1;
 };
 
@@ -524,7 +608,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
     const uint64_t launches0 = E.launches;
     uint64_t h2d = 0, d2h = 0;
     double lo_wait = 0.0;
-    float gpu_ms_total = 0.f, gpu_ms_score = 0.f, gpu_ms_confirm = 0.f;
+    float gpu_ms_total = 0.f, gpu_ms_score = 0.f, gpu_ms_confirm = 0.f, gpu_ms_lo = 0.f;
     auto sync_timed = [&](double *acc) -> int {
         auto t0 = std::chrono::steady_clock::now();
         PLB_CUDA(cudaStreamSynchronize(st));
@@ -594,6 +678,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 }
                 P.cmax = S.t->res->cmax.p;
             } else {
+                S.in_off = (long long)in_off;
                 double *ha = E.h_in.p + in_off, *hb = ha + 2 * (size_t)S.n;
                 std::memcpy(ha, S.t->a, sizeof(double) * 2 * S.n);
                 std::memcpy(hb, S.t->b, sizeof(double) * (size_t)b_dim * S.n);
@@ -645,6 +730,49 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         if (px_elems) {
             PLB_CUDA(cudaMemcpyAsync(E.px64.p, E.h_in.p + in_doubles, sizeof(double) * px_elems, cudaMemcpyHostToDevice, st));
             h2d += sizeof(double) * px_elems;
+        }
+        // ---- normalize_points on the device (robust/utils.cc:584-644), then the thresholds that depend on its scale
+        {
+            std::vector<int> who;
+            for (int i = 0; i < NP; ++i)
+                if (PS[i].t->norm_mode != 0 && PS[i].in_off >= 0 && PS[i].n > 0) who.push_back(i);
+            const int nn = (int)who.size();
+            if (nn) {
+                if ((rc = E.ndesc.ensure(nn)) || (rc = E.h_ndesc.ensure(nn)) || (rc = E.h_norm.ensure(5 * (size_t)nn))) return rc;
+                for (int j = 0; j < nn; ++j) {
+                    const PState &S = PS[who[j]];
+                    NormDesc &D = E.h_ndesc.p[j];
+                    D.a = E.in.p + S.in_off;
+                    D.b = D.a + 2 * (size_t)S.n;
+                    D.out = E.h_norm.d + 5 * (size_t)j;
+                    D.n = S.n;
+                    D.centroid = S.t->norm_mode == 2 ? 1 : 0;
+                }
+                PLB_CUDA(cudaMemcpyAsync(E.ndesc.p, E.h_ndesc.p, sizeof(NormDesc) * nn, cudaMemcpyHostToDevice, st));
+                launch_normalize(E.ndesc.p, nn, st);
+                E.launches++;
+                if ((rc = sync_timed(nullptr))) return rc;
+                d2h += sizeof(double) * 5 * (size_t)nn;
+                for (int j = 0; j < nn; ++j) {
+                    Task &t = *PS[who[j]].t;
+                    std::copy(E.h_norm.p + 5 * (size_t)j, E.h_norm.p + 5 * (size_t)j + 5, t.norm_out);
+                    const double scale = t.norm_out[4];
+                    t.max_error = t.max_error / scale;                                 // robust.cc:562,725
+                    t.polish.bundle.loss_scale = t.polish.bundle.loss_scale / scale; // :563,726
+                    E.h_probs.p[who[j]].sq_thr = t.max_error * t.max_error;
+                    if (t.opt.score_initial_model) { // robust.cc:566-569 / 729-732: the start model in normalised coordinates
+                        HM3 T1, T2;
+                        norm_transforms(t.norm_out, T1, T2);
+                        HM3 M = (kind == KIND_FUND) ? hm_mul(hm_mul(hm_inv(hm_T(T2)), hm_from_cm(t.model)), hm_inv(T1))
+                                                    : hm_mul(hm_mul(T2, hm_from_cm(t.model)), hm_inv(T1));
+                        const double nm = hm_norm(M);
+                        for (int r = 0; r < 3; ++r)
+                            for (int c = 0; c < 3; ++c) M.m[r][c] /= nm;
+                        hm_to_cm(M, t.model);
+                        std::copy(t.model, t.model + 9, PS[who[j]].best_model);
+                    }
+                }
+            }
         }
         PLB_CUDA(cudaMemcpyAsync(E.probs.p, E.h_probs.p, sizeof(ProblemDev) * n_probdev, cudaMemcpyHostToDevice, st));
         if (n_up) {
@@ -885,6 +1013,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         PLB_CUDA(cudaMemcpyAsync(E.rp.p, E.h_rp.p, sizeof(RoundProb) * na, cudaMemcpyHostToDevice, st));
         h2d += sizeof(int) * (4 * na + 1) + sizeof(RoundProb) * na;
         PLB_CUDA(cudaMemsetAsync(E.work.p, 0, CTL_WORDS * sizeof(int), st));
+        PLB_CUDA(cudaEventRecord(E.ev0, st));
         launch_sample(E.rp.p, na, E.smp.p + (size_t)smp_cur * NP, E.smp.p + (size_t)(smp_cur ^ 1) * NP, E.samples.p, st);
         E.launches++;
         mark(PH_SAMPLE);
@@ -931,7 +1060,6 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             out.s5_roots = E.s5_roots.p;
             out.s5_nroots = E.s5_nroots.p;
         }
-        PLB_CUDA(cudaEventRecord(E.ev0, st));
         launch_hypotheses(kind, R, E.work.p, out, mode, max_n_pad, st, E.ev2);
         PLB_CUDA(cudaEventRecord(E.ev1, st));
         E.launches += kind_is_relpose(kind) ? 4 : 2; // k_solve (or k5_prep + k5_roots + k5_back) + scoring
@@ -980,6 +1108,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         launch_lm_round(kind, E.probs.p, E.lo_tmpl.p, E.job_src.p, E.models.p, E.work.p + CTL_JOB_TOTAL, (int)job_cap,
                         est_jobs, max_n, E.subset.p, max_n_pad, E.h_lm_out.d, st);
         E.launches += 2;
+        PLB_CUDA(cudaEventRecord(E.ev4, st));
         PLB_CUDA(cudaMemcpyAsync(E.h_work.p, E.work.p, CTL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
         mark(PH_LAUNCH);
         if ((rc = sync_timed(nullptr))) return rc;
@@ -1009,6 +1138,11 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         gpu_ms_total += ms + ms_cf;
         gpu_ms_score += ms_sc;
         gpu_ms_confirm += ms_cf;
+        {
+            float ms_lo = 0.f;
+            cudaEventElapsedTime(&ms_lo, E.ev3, E.ev4);
+            gpu_ms_lo += ms_lo;
+        }
 
         // ---- replay of the serial loop over this round, problem by problem (ransac_impl.h:106-154,180-188) --------
         // Only samples with an improving model change the state; between two of them the break test
@@ -1203,6 +1337,9 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
     PS[0].cnt.gpu_launches = E.launches - launches0;
     PS[0].cnt.gpu_seconds = gpu_ms_total * 1e-3;
     PS[0].cnt.gpu_seconds_score = gpu_ms_score * 1e-3;
+    PS[0].cnt.gpu_seconds_select = gpu_ms_confirm * 1e-3;
+    PS[0].cnt.gpu_seconds_lo = gpu_ms_lo * 1e-3;
+    PS[0].cnt.rounds = (uint64_t)n_rounds;
     PS[0].cnt.h2d_bytes = h2d;
     PS[0].cnt.d2h_bytes = d2h;
     finish();
@@ -1311,98 +1448,6 @@ static int run_refine(int kind, const double *a, const double *b, size_t n_pts, 
         bstats[2] = E.h_lm_out.p[0].cost;
     }
     return PLB_OK;
-}
-
-// ---- small host-side 3x3 helpers for the estimate_* wrappers (column-major <-> row-major) ---------------------
-struct HM3 {
-    double m[3][3];
-};
-static HM3 hm_identity() {
-    HM3 r;
-    std::memset(&r, 0, sizeof(r));
-    r.m[0][0] = r.m[1][1] = r.m[2][2] = 1;
-    return r;
-}
-static HM3 hm_mul(const HM3 &A, const HM3 &B) {
-    HM3 C;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) C.m[i][j] = A.m[i][0] * B.m[0][j] + A.m[i][1] * B.m[1][j] + A.m[i][2] * B.m[2][j];
-    return C;
-}
-static HM3 hm_T(const HM3 &A) {
-    HM3 C;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) C.m[i][j] = A.m[j][i];
-    return C;
-}
-static HM3 hm_inv(const HM3 &M) {
-    const double(*m)[3] = M.m;
-    HM3 c;
-    c.m[0][0] = m[1][1] * m[2][2] - m[1][2] * m[2][1];
-    c.m[1][0] = m[1][2] * m[2][0] - m[1][0] * m[2][2];
-    c.m[2][0] = m[1][0] * m[2][1] - m[1][1] * m[2][0];
-    c.m[0][1] = m[0][2] * m[2][1] - m[0][1] * m[2][2];
-    c.m[1][1] = m[0][0] * m[2][2] - m[0][2] * m[2][0];
-    c.m[2][1] = m[0][1] * m[2][0] - m[0][0] * m[2][1];
-    c.m[0][2] = m[0][1] * m[1][2] - m[0][2] * m[1][1];
-    c.m[1][2] = m[0][2] * m[1][0] - m[0][0] * m[1][2];
-    c.m[2][2] = m[0][0] * m[1][1] - m[0][1] * m[1][0];
-    const double det = c.m[0][0] * m[0][0] + c.m[1][0] * m[0][1] + c.m[2][0] * m[0][2];
-    const double id = 1.0 / det;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) c.m[i][j] *= id;
-    return c;
-}
-static double hm_norm(const HM3 &A) {
-    double s = 0;
-    for (int j = 0; j < 3; ++j)
-        for (int i = 0; i < 3; ++i) s += A.m[i][j] * A.m[i][j];
-    return std::sqrt(s);
-}
-static HM3 hm_from_cm(const double *p) {
-    HM3 r;
-    for (int k = 0; k < 9; ++k) r.m[k % 3][k / 3] = p[k];
-    return r;
-}
-static void hm_to_cm(const HM3 &A, double *p) {
-    for (int k = 0; k < 9; ++k) p[k] = A.m[k % 3][k / 3];
-}
-
-// robust/utils.cc:584-644 (shared scale only; the two in-scope callers pass shared_scale = true)
-static double normalize_points(std::vector<double> &x1, std::vector<double> &x2, size_t n, HM3 &T1, HM3 &T2,
-                               bool normalize_centroid) {
-    T1 = hm_identity();
-    T2 = hm_identity();
-    if (normalize_centroid) {
-        double c1[2] = {0, 0}, c2[2] = {0, 0};
-        for (size_t k = 0; k < n; ++k) {
-            c1[0] += x1[2 * k]; c1[1] += x1[2 * k + 1];
-            c2[0] += x2[2 * k]; c2[1] += x2[2 * k + 1];
-        }
-        c1[0] /= n; c1[1] /= n; c2[0] /= n; c2[1] /= n;
-        T1.m[0][2] = -c1[0]; T1.m[1][2] = -c1[1];
-        T2.m[0][2] = -c2[0]; T2.m[1][2] = -c2[1];
-        for (size_t k = 0; k < n; ++k) {
-            x1[2 * k] -= c1[0]; x1[2 * k + 1] -= c1[1];
-            x2[2 * k] -= c2[0]; x2[2 * k + 1] -= c2[1];
-        }
-    }
-    double scale = 0.0;
-    for (size_t k = 0; k < n; ++k) {
-        scale += std::sqrt(x1[2 * k] * x1[2 * k] + x1[2 * k + 1] * x1[2 * k + 1]);
-        scale += std::sqrt(x2[2 * k] * x2[2 * k] + x2[2 * k + 1] * x2[2 * k + 1]);
-    }
-    scale /= std::sqrt(2) * n;
-    for (size_t k = 0; k < 2 * n; ++k) {
-        x1[k] /= scale;
-        x2[k] /= scale;
-    }
-    for (int r = 0; r < 2; ++r)
-        for (int c = 0; c < 3; ++c) {
-            T1.m[r][c] *= 1.0 / scale;
-            T2.m[r][c] *= 1.0 / scale;
-        }
-    return scale;
 }
 
 // plb_camera -> CamDev; models outside the six on the path are rejected like Camera::unproject's "NYI"
@@ -1620,152 +1665,167 @@ int plb_ransac_homography(const double *x1, const double *x2, size_t n, const pl
     return run_ransac(KIND_HOMOG, x1, x2, n, *opt, max_error, 0, H, inliers, stats, counters, FinalPolish());
 }
 
-// PoseLib/robust.cc:36-126 (no focal estimation).  The camera pre-step (Camera::unproject of every 2D point) runs
-// on the device, fused into the layout kernel.
-int plb_estimate_absolute_pose(const double *points2D, const double *points3D, size_t n, const plb_ransac_opt *ransac,
-                               const plb_bundle_opt *bundle, double max_error, const plb_camera *camera,
-                               double pose[7], char *inliers, plb_ransac_stats *stats, plb_counters *counters) {
-    if (int r = check_ptrs(points2D, points3D, ransac, pose, n)) return r;
+// ---- PoseLib/robust.cc estimate_* : pre-step -> Task for the group engine -> post-step -------------------------------
+// One estimate_* call, prepared: the Task (points, scaled threshold, camera pre-step mode, final polish) plus what the
+// post-step needs (normalising transforms of F / H).  Used by the four single entry points and by plb_estimate_batch.
+struct EstimateJob {
+    Task t;
+    int api_kind = 0; // PLB_KIND_*
+    std::vector<double> px;
+    HM3 T1, T2;
+    bool normalised = false;
+    double *model = nullptr;
+};
+static void default_stats(plb_ransac_stats *stats, plb_counters *counters) {
+    if (stats) {
+        stats->refinements = stats->iterations = stats->num_inliers = 0;
+        stats->inlier_ratio = 0;
+        stats->model_score = std::numeric_limits<double>::max();
+    }
+    if (counters) std::memset(counters, 0, sizeof(*counters));
+}
+// robust.cc:36-126 (absolute pose, no focal estimation), :242-314 (relative pose; tangent_sampson keeps the scaled pixels
+// and runs the tangent-Sampson estimator with the cameras), :544-594 (fundamental), :712-757 (homography).
+// The camera pre-step (Camera::unproject / unproject_with_jac of every point) runs on the device, fused into the layout
+// kernel; normalize_points (F / H) runs here on the calling (worker) thread.
+static int estimate_prepare(int kind, const double *x1, const double *x2, size_t n, const plb_camera *camera1,
+                            const plb_camera *camera2, const plb_ransac_opt *ransac, const plb_bundle_opt *bundle,
+                            double max_error, int real_focal_check, int tangent_sampson, double *model, char *inliers,
+                            plb_ransac_stats *stats, plb_counters *counters, EstimateJob &J) {
+    if (int r = check_ptrs(x1, x2, ransac, model, n)) return r;
     if (!bundle) {
         g_err = "null bundle options";
         return PLB_ERR_ARG;
     }
-    CamDev cam;
-    if (int r = camera_dev(camera, &cam)) return r;
-    const double scale = 1.0 / camera_focal(cam);
-    FinalPolish fp;
+    if (kind < 0 || kind > 3) {
+        g_err = "unknown problem kind";
+        return PLB_ERR_ARG;
+    }
+    J.api_kind = kind;
+    J.model = model;
+    Task &t = J.t;
+    t.a = x1;
+    t.b = x2;
+    t.n = n;
+    t.opt = *ransac;
+    t.model = model;
+    t.inliers = inliers;
+    t.stats_out = stats;
+    t.cnt_out = counters;
+    FinalPolish &fp = t.polish;
     fp.enabled = true;
     fp.bundle = *bundle;
-    fp.bundle.loss_scale = bundle->loss_scale * scale;
-    fp.min_inliers = 3;
-    std::vector<double> px;
-    if (cam.model != CAMM_NULL) { // the polish runs on pixels*scale with the rescaled camera (robust.cc:103-123)
-        px.resize(2 * n);
-        for (size_t k = 0; k < 2 * n; ++k) px[k] = points2D[k] * scale;
-        fp.px_scaled = px.data();
-        fp.cam = cam;
-        camera_rescale(fp.cam, scale);
+    if (kind == PLB_KIND_PNP) {
+        CamDev cam;
+        if (int r = camera_dev(camera1, &cam)) return r;
+        const double scale = 1.0 / camera_focal(cam);
+        fp.bundle.loss_scale = bundle->loss_scale * scale;
+        fp.min_inliers = 3;
+        if (cam.model != CAMM_NULL) { // the polish runs on pixels*scale with the rescaled camera (robust.cc:103-123)
+            J.px.resize(2 * n);
+            for (size_t k = 0; k < 2 * n; ++k) J.px[k] = x1[k] * scale;
+            fp.px_scaled = J.px.data();
+            fp.cam = cam;
+            camera_rescale(fp.cam, scale);
+        }
+        t.kind = KIND_PNP;
+        t.max_error = max_error * scale;
+        t.pre_mode = cam.model != CAMM_NULL ? 1 : 0;
+        t.cam_a = cam;
+        return PLB_OK;
     }
-    return run_ransac(KIND_PNP, points2D, points3D, n, *ransac, max_error * scale, 0, pose, inliers, stats, counters, fp,
-                      nullptr, cam.model != CAMM_NULL ? 1 : 0, &cam, nullptr);
+    if (kind == PLB_KIND_RELPOSE) {
+        CamDev c1, c2;
+        if (int r = camera_dev(camera1, &c1)) return r;
+        if (int r = camera_dev(camera2, &c2)) return r;
+        const double scale = 0.5 * (1.0 / camera_focal(c1) + 1.0 / camera_focal(c2));
+        fp.bundle.loss_scale = bundle->loss_scale * scale;
+        fp.min_inliers = 5;
+        t.max_error = max_error * scale;
+        if (tangent_sampson) {
+            camera_rescale(c1, scale);
+            camera_rescale(c2, scale);
+            model[0] = 1.0; // ransac.cc:159-160: the start pose is reset even when score_initial_model is set
+            for (int i = 1; i < 7; ++i) model[i] = 0.0;
+            t.kind = KIND_RELPOSE_TS;
+            t.pre_mode = 2;
+            t.pre_scale = scale;
+        } else {
+            t.kind = KIND_RELPOSE;
+            t.pre_mode = (c1.model != CAMM_NULL || c2.model != CAMM_NULL) ? 1 : 0;
+        }
+        t.cam_a = c1;
+        t.cam_b = c2;
+        return PLB_OK;
+    }
+    const size_t min_pts = (kind == PLB_KIND_FUNDAMENTAL) ? 7 : 4; // robust.cc:548-550,716-718
+    if (n < min_pts) {
+        default_stats(stats, counters);
+        t.skip = true;
+        return PLB_OK;
+    }
+    // normalize_points(scale = true, centroid = !real_focal_check | true, shared = true) runs on the device (k_normalize);
+    // the engine divides max_error and the polish loss scale by the scale it finds (robust.cc:561-564,724-727)
+    const bool fund = kind == PLB_KIND_FUNDAMENTAL;
+    J.normalised = true;
+    fp.bundle.loss_scale = bundle->loss_scale;
+    fp.min_inliers = min_pts;
+    t.kind = fund ? KIND_FUND : KIND_HOMOG;
+    t.norm_mode = (fund && real_focal_check) ? 1 : 2;
+    t.max_error = max_error;
+    t.rfc = fund ? real_focal_check : 0;
+    return PLB_OK;
 }
-// PoseLib/robust.cc:242-314: tangent_sampson == 0 unprojects both images to calibrated 2D points and runs the Sampson
-// estimator; tangent_sampson != 0 keeps the (scaled) pixels and runs the tangent-Sampson estimator with the cameras.
+static void estimate_finish(EstimateJob &J, const Task &t) {
+    if (!J.normalised || t.skip) return;
+    // robust.cc:590-591: F = T2^T F T1 ; :753-754: H = T2^-1 H T1 ; both renormalised
+    norm_transforms(t.norm_out, J.T1, J.T2);
+    HM3 M = (J.api_kind == PLB_KIND_FUNDAMENTAL) ? hm_mul(hm_mul(hm_T(J.T2), hm_from_cm(J.model)), J.T1)
+                                                 : hm_mul(hm_mul(hm_inv(J.T2), hm_from_cm(J.model)), J.T1);
+    const double nm = hm_norm(M);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) M.m[i][j] /= nm;
+    hm_to_cm(M, J.model);
+}
+static int estimate_single(int kind, const double *x1, const double *x2, size_t n, const plb_camera *camera1,
+                           const plb_camera *camera2, const plb_ransac_opt *ransac, const plb_bundle_opt *bundle,
+                           double max_error, int real_focal_check, int tangent_sampson, double *model, char *inliers,
+                           plb_ransac_stats *stats, plb_counters *counters) {
+    EstimateJob J;
+    if (int r = estimate_prepare(kind, x1, x2, n, camera1, camera2, ransac, bundle, max_error, real_focal_check,
+                                 tangent_sampson, model, inliers, stats, counters, J))
+        return r;
+    if (J.t.skip) return PLB_OK;
+    std::vector<Task *> v{&J.t};
+    const int rc = run_group(J.t.kind, v);
+    if (rc != PLB_OK) return rc;
+    estimate_finish(J, J.t);
+    return PLB_OK;
+}
+int plb_estimate_absolute_pose(const double *points2D, const double *points3D, size_t n, const plb_ransac_opt *ransac,
+                               const plb_bundle_opt *bundle, double max_error, const plb_camera *camera,
+                               double pose[7], char *inliers, plb_ransac_stats *stats, plb_counters *counters) {
+    return estimate_single(PLB_KIND_PNP, points2D, points3D, n, camera, nullptr, ransac, bundle, max_error, 0, 0, pose,
+                           inliers, stats, counters);
+}
 int plb_estimate_relative_pose(const double *x1, const double *x2, size_t n, const plb_camera *camera1,
                                const plb_camera *camera2, const plb_ransac_opt *ransac, const plb_bundle_opt *bundle,
                                double max_error, int tangent_sampson, double pose[7], char *inliers,
                                plb_ransac_stats *stats, plb_counters *counters) {
-    if (int r = check_ptrs(x1, x2, ransac, pose, n)) return r;
-    if (!bundle) {
-        g_err = "null bundle options";
-        return PLB_ERR_ARG;
-    }
-    CamDev c1, c2;
-    if (int r = camera_dev(camera1, &c1)) return r;
-    if (int r = camera_dev(camera2, &c2)) return r;
-    const double scale = 0.5 * (1.0 / camera_focal(c1) + 1.0 / camera_focal(c2));
-    FinalPolish fp;
-    fp.enabled = true;
-    fp.bundle = *bundle;
-    fp.bundle.loss_scale = bundle->loss_scale * scale;
-    fp.min_inliers = 5;
-    if (tangent_sampson) {
-        camera_rescale(c1, scale);
-        camera_rescale(c2, scale);
-        pose[0] = 1.0; // ransac.cc:159-160: the start pose is reset even when score_initial_model is set
-        for (int i = 1; i < 7; ++i) pose[i] = 0.0;
-        return run_ransac(KIND_RELPOSE_TS, x1, x2, n, *ransac, max_error * scale, 0, pose, inliers, stats, counters, fp,
-                          nullptr, 2, &c1, &c2, scale);
-    }
-    const int pre = (c1.model != CAMM_NULL || c2.model != CAMM_NULL) ? 1 : 0;
-    return run_ransac(KIND_RELPOSE, x1, x2, n, *ransac, max_error * scale, 0, pose, inliers, stats, counters, fp,
-                      nullptr, pre, &c1, &c2);
+    return estimate_single(PLB_KIND_RELPOSE, x1, x2, n, camera1, camera2, ransac, bundle, max_error, 0, tangent_sampson,
+                           pose, inliers, stats, counters);
 }
-// PoseLib/robust.cc:544-594
 int plb_estimate_fundamental(const double *x1, const double *x2, size_t n, const plb_ransac_opt *ransac,
                              const plb_bundle_opt *bundle, double max_error, int real_focal_check, double F[9],
                              char *inliers, plb_ransac_stats *stats, plb_counters *counters) {
-    if (int r = check_ptrs(x1, x2, ransac, F, n)) return r;
-    if (!bundle) {
-        g_err = "null bundle options";
-        return PLB_ERR_ARG;
-    }
-    if (n < 7) {
-        if (stats) {
-            stats->refinements = stats->iterations = stats->num_inliers = 0;
-            stats->inlier_ratio = 0;
-            stats->model_score = std::numeric_limits<double>::max();
-        }
-        if (counters) std::memset(counters, 0, sizeof(*counters));
-        return PLB_OK;
-    }
-    std::vector<double> a(x1, x1 + 2 * n), b(x2, x2 + 2 * n);
-    HM3 T1, T2;
-    const double scale = normalize_points(a, b, n, T1, T2, !real_focal_check);
-    FinalPolish fp;
-    fp.enabled = true;
-    fp.bundle = *bundle;
-    fp.bundle.loss_scale = bundle->loss_scale / scale;
-    fp.min_inliers = 7;
-    if (ransac->score_initial_model) { // robust.cc:566-569
-        HM3 Fm = hm_mul(hm_mul(hm_inv(hm_T(T2)), hm_from_cm(F)), hm_inv(T1));
-        const double nf = hm_norm(Fm);
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) Fm.m[i][j] /= nf;
-        hm_to_cm(Fm, F);
-    }
-    int rc = run_ransac(KIND_FUND, a.data(), b.data(), n, *ransac, max_error / scale, real_focal_check, F, inliers,
-                        stats, counters, fp);
-    if (rc != PLB_OK) return rc;
-    HM3 Fm = hm_mul(hm_mul(hm_T(T2), hm_from_cm(F)), T1); // robust.cc:590-591
-    const double nf = hm_norm(Fm);
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) Fm.m[i][j] /= nf;
-    hm_to_cm(Fm, F);
-    return PLB_OK;
+    return estimate_single(PLB_KIND_FUNDAMENTAL, x1, x2, n, nullptr, nullptr, ransac, bundle, max_error,
+                           real_focal_check, 0, F, inliers, stats, counters);
 }
-// PoseLib/robust.cc:712-757
 int plb_estimate_homography(const double *x1, const double *x2, size_t n, const plb_ransac_opt *ransac,
                             const plb_bundle_opt *bundle, double max_error, double H[9], char *inliers,
                             plb_ransac_stats *stats, plb_counters *counters) {
-    if (int r = check_ptrs(x1, x2, ransac, H, n)) return r;
-    if (!bundle) {
-        g_err = "null bundle options";
-        return PLB_ERR_ARG;
-    }
-    if (n < 4) {
-        if (stats) {
-            stats->refinements = stats->iterations = stats->num_inliers = 0;
-            stats->inlier_ratio = 0;
-            stats->model_score = std::numeric_limits<double>::max();
-        }
-        if (counters) std::memset(counters, 0, sizeof(*counters));
-        return PLB_OK;
-    }
-    std::vector<double> a(x1, x1 + 2 * n), b(x2, x2 + 2 * n);
-    HM3 T1, T2;
-    const double scale = normalize_points(a, b, n, T1, T2, true);
-    FinalPolish fp;
-    fp.enabled = true;
-    fp.bundle = *bundle;
-    fp.bundle.loss_scale = bundle->loss_scale / scale;
-    fp.min_inliers = 4;
-    if (ransac->score_initial_model) { // robust.cc:729-732
-        HM3 Hm = hm_mul(hm_mul(T2, hm_from_cm(H)), hm_inv(T1));
-        const double nh = hm_norm(Hm);
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) Hm.m[i][j] /= nh;
-        hm_to_cm(Hm, H);
-    }
-    int rc = run_ransac(KIND_HOMOG, a.data(), b.data(), n, *ransac, max_error / scale, 0, H, inliers, stats, counters,
-                        fp);
-    if (rc != PLB_OK) return rc;
-    HM3 Hm = hm_mul(hm_mul(hm_inv(T2), hm_from_cm(H)), T1); // robust.cc:753-754
-    const double nh = hm_norm(Hm);
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) Hm.m[i][j] /= nh;
-    hm_to_cm(Hm, H);
-    return PLB_OK;
+    return estimate_single(PLB_KIND_HOMOGRAPHY, x1, x2, n, nullptr, nullptr, ransac, bundle, max_error, 0, 0, H, inliers,
+                           stats, counters);
 }
 
 // ---- robust/bundle.h refiners -------------------------------------------------------------------------------
@@ -1849,15 +1909,133 @@ int plb_homography_4pt_batch(size_t count, const double *x1, const double *x2, d
     return solver_batch(KIND_HOMOG, 0, count, x1, 12, x2, 12, H_out, 9, n_out, check_cheirality);
 }
 
+// solvers/relpose_8pt.h:45-53: `count` instances of n >= 8 unit bearing pairs; E_out count x 9 (column-major) or
+// poses_out count x 4 x 7 + n_out
+static int eightpt_batch(size_t count, size_t n, const double *x1, const double *x2, int want_poses, double *E_out,
+                         double *poses_out, int32_t *n_out) {
+    if (count == 0) return PLB_OK;
+    if (!x1 || !x2 || n < 8 || n > (1u << 24) || (want_poses ? (!poses_out || !n_out) : !E_out)) {
+        g_err = "bad argument";
+        return PLB_ERR_ARG;
+    }
+    Engine &E = *engine();
+    int rc = E.init();
+    if (rc != PLB_OK) return rc;
+    DevBuf<double> da, db, dout;
+    DevBuf<int> dn;
+    const size_t out_sz = want_poses ? 28 : 9;
+    if ((rc = da.ensure(count * n * 3)) || (rc = db.ensure(count * n * 3)) || (rc = dout.ensure(count * out_sz)) ||
+        (rc = dn.ensure(count)))
+        return rc;
+    PLB_CUDA(cudaMemcpyAsync(da.p, x1, sizeof(double) * count * n * 3, cudaMemcpyHostToDevice, E.stream));
+    PLB_CUDA(cudaMemcpyAsync(db.p, x2, sizeof(double) * count * n * 3, cudaMemcpyHostToDevice, E.stream));
+    PLB_CUDA(cudaMemsetAsync(dout.p, 0, sizeof(double) * count * out_sz, E.stream));
+    launch_eightpt(count, (int)n, da.p, db.p, want_poses, dout.p, dout.p, dn.p, E.stream);
+    E.launches++;
+    PLB_CUDA(cudaMemcpyAsync(want_poses ? poses_out : E_out, dout.p, sizeof(double) * count * out_sz, cudaMemcpyDeviceToHost, E.stream));
+    if (want_poses) PLB_CUDA(cudaMemcpyAsync(n_out, dn.p, sizeof(int) * count, cudaMemcpyDeviceToHost, E.stream));
+    PLB_CUDA(cudaStreamSynchronize(E.stream));
+    PLB_CUDA(cudaGetLastError());
+    return PLB_OK;
+}
+int plb_essential_matrix_8pt_batch(size_t count, size_t n, const double *x1, const double *x2, double *E_out) {
+    return eightpt_batch(count, n, x1, x2, 0, E_out, nullptr, nullptr);
+}
+int plb_relpose_8pt_batch(size_t count, size_t n, const double *x1, const double *x2, double *poses_out, int32_t *n_out) {
+    return eightpt_batch(count, n, x1, x2, 1, nullptr, poses_out, n_out);
+}
+
 // ---- batch of problems: `streams` lock-step groups in flight per device, each on its own engine / stream ----------
 // Problems of the same kind run in lock-step groups (one chain of launches per round for the whole group); the groups of
 // a device are spread over `streams` persistent worker threads.  devices[0..n_dev): the CUDA devices to use; problems
 // are assigned to devices by longest-processing-time-first on (correspondences x expected iterations), problems whose
 // correspondences are resident stay on the device that holds them.
-static double problem_cost(const plb_problem &p, size_t n) {
-    static const double its[4] = {4.0 * 1000, 0.5 * 14000, 2.0 * 30000, 1.0 * 1000}; // models x iterations, typical
-    const double cap = (double)std::max<uint64_t>(p.opt.max_iterations, 1) * 4.0;
-    return (double)std::max<size_t>(n, 1) * std::min(its[p.kind], cap);
+static double task_cost(const Task &t) {
+    static const double its[5] = {4.0 * 1000, 0.5 * 14000, 2.0 * 30000, 1.0 * 1000, 0.5 * 14000}; // models x iterations, typical
+    const double cap = (double)std::max<uint64_t>(t.opt.max_iterations, 1) * 4.0;
+    return (double)std::max<size_t>(t.n, 1) * std::min(its[t.kind], cap);
+}
+// Runs prepared tasks: dev_of[i] >= 0 pins task i to that device (resident inputs), -1 lets the partition place it.
+// Returns the first error; *err_msg receives its text.
+static int run_tasks(std::vector<Task> &tasks, std::vector<int> &dev_of, const int *devices, int n_dev, int streams) {
+    const size_t count = tasks.size();
+    // device assignment: LPT over the tasks that are free to move
+    {
+        std::vector<double> load(n_dev, 0.0);
+        std::vector<size_t> order;
+        for (size_t i = 0; i < count; ++i) {
+            if (dev_of[i] >= 0) {
+                for (int d = 0; d < n_dev; ++d)
+                    if (devices[d] == dev_of[i]) load[d] += task_cost(tasks[i]);
+            } else {
+                order.push_back(i);
+            }
+        }
+        if (n_dev == 1) {
+            for (size_t i : order) dev_of[i] = devices[0];
+        } else {
+            std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return task_cost(tasks[x]) > task_cost(tasks[y]); });
+            for (size_t i : order) {
+                int best = 0;
+                for (int d = 1; d < n_dev; ++d)
+                    if (load[d] < load[best]) best = d;
+                dev_of[i] = devices[best];
+                load[best] += task_cost(tasks[i]);
+            }
+        }
+    }
+    // groups per device: tasks of the same engine kind run in lock-step
+    const int nthreads_req = std::max(1, streams);
+    struct Job {
+        int device;
+        std::vector<std::vector<Task *>> groups;
+    };
+    std::vector<Job> jobs; // one per (device, worker)
+    for (int d = 0; d < n_dev; ++d) {
+        std::vector<std::vector<Task *>> groups;
+        for (int kind = 0; kind <= KIND_RELPOSE_TS; ++kind) {
+            std::vector<Task *> of_kind;
+            for (size_t i = 0; i < count; ++i)
+                if (tasks[i].kind == kind && dev_of[i] == devices[d] && !tasks[i].skip) of_kind.push_back(&tasks[i]);
+            if (of_kind.empty()) continue;
+            const size_t gsz = std::min<size_t>(256, std::max<size_t>(1, (of_kind.size() + nthreads_req - 1) / nthreads_req));
+            for (size_t o = 0; o < of_kind.size(); o += gsz)
+                groups.emplace_back(of_kind.begin() + o, of_kind.begin() + std::min(of_kind.size(), o + gsz));
+        }
+        const int nthreads = std::max(1, std::min<int>(nthreads_req, (int)groups.size()));
+        for (int t = 0; t < nthreads; ++t) {
+            Job j;
+            j.device = devices[d];
+            for (size_t gi = (size_t)t; gi < groups.size(); gi += (size_t)nthreads) j.groups.push_back(groups[gi]);
+            if (!j.groups.empty()) jobs.push_back(std::move(j));
+        }
+    }
+    if (jobs.empty()) return PLB_OK;
+    std::atomic<int> first_err(PLB_OK);
+    std::string err_msg;
+    std::mutex mtx;
+    const int mode = current_mode();
+    auto work = [&](int w) {
+        const int saved_dev = g_device, saved_mode = g_mode;
+        g_device = jobs[w].device;
+        g_mode = mode;
+        for (auto &grp : jobs[w].groups) {
+            const int rc = run_group(grp[0]->kind, grp);
+            if (rc != PLB_OK) {
+                int exp = PLB_OK;
+                if (first_err.compare_exchange_strong(exp, rc)) {
+                    std::lock_guard<std::mutex> lk(mtx);
+                    err_msg = g_err;
+                }
+            }
+        }
+        g_device = saved_dev;
+        g_mode = saved_mode;
+    };
+    if (jobs.size() == 1) work(0); // the caller's own thread and engine
+    else worker_pool().run((int)jobs.size(), work);
+    if (first_err.load() != PLB_OK) g_err = err_msg;
+    return first_err.load();
 }
 static int batch_impl(plb_problem *problems, size_t count, const int *devices, int n_dev, int streams) {
     if (count == 0) return PLB_OK;
@@ -1917,87 +2095,10 @@ static int batch_impl(plb_problem *problems, size_t count, const int *devices, i
             return fail_all(PLB_ERR_ARG, "null argument");
         }
     }
-    // device assignment: LPT over the problems that are free to move
-    {
-        std::vector<double> load(n_dev, 0.0);
-        std::vector<size_t> order;
-        for (size_t i = 0; i < count; ++i) {
-            if (dev_of[i] >= 0) {
-                for (int d = 0; d < n_dev; ++d)
-                    if (devices[d] == dev_of[i]) load[d] += problem_cost(problems[i], tasks[i].n);
-            } else {
-                order.push_back(i);
-            }
-        }
-        if (n_dev == 1) {
-            for (size_t i : order) dev_of[i] = devices[0];
-        } else {
-            std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
-                return problem_cost(problems[x], tasks[x].n) > problem_cost(problems[y], tasks[y].n);
-            });
-            for (size_t i : order) {
-                int best = 0;
-                for (int d = 1; d < n_dev; ++d)
-                    if (load[d] < load[best]) best = d;
-                dev_of[i] = devices[best];
-                load[best] += problem_cost(problems[i], tasks[i].n);
-            }
-        }
-    }
-    // groups per device
-    const int nthreads_req = std::max(1, streams);
-    struct Job {
-        int device;
-        std::vector<std::vector<Task *>> groups;
-    };
-    std::vector<Job> jobs; // one per (device, worker)
-    for (int d = 0; d < n_dev; ++d) {
-        std::vector<std::vector<Task *>> groups;
-        for (int kind = 0; kind < 4; ++kind) {
-            std::vector<Task *> of_kind;
-            for (size_t i = 0; i < count; ++i)
-                if (problems[i].kind == kind && dev_of[i] == devices[d]) of_kind.push_back(&tasks[i]);
-            if (of_kind.empty()) continue;
-            const size_t gsz = std::min<size_t>(256, std::max<size_t>(1, (of_kind.size() + nthreads_req - 1) / nthreads_req));
-            for (size_t o = 0; o < of_kind.size(); o += gsz)
-                groups.emplace_back(of_kind.begin() + o, of_kind.begin() + std::min(of_kind.size(), o + gsz));
-        }
-        const int nthreads = std::max(1, std::min<int>(nthreads_req, (int)groups.size()));
-        for (int t = 0; t < nthreads; ++t) {
-            Job j;
-            j.device = devices[d];
-            for (size_t gi = (size_t)t; gi < groups.size(); gi += (size_t)nthreads) j.groups.push_back(groups[gi]);
-            if (!j.groups.empty()) jobs.push_back(std::move(j));
-        }
-    }
-    std::atomic<int> first_err(PLB_OK);
-    std::string err_msg;
-    std::mutex mtx;
-    const int mode = current_mode();
-    auto work = [&](int w) {
-        const int saved_dev = g_device, saved_mode = g_mode;
-        g_device = jobs[w].device;
-        g_mode = mode;
-        for (auto &grp : jobs[w].groups) {
-            const int rc = run_group(grp[0]->kind, grp);
-            if (rc != PLB_OK) {
-                int exp = PLB_OK;
-                if (first_err.compare_exchange_strong(exp, rc)) {
-                    std::lock_guard<std::mutex> lk(mtx);
-                    err_msg = g_err;
-                }
-            }
-        }
-        g_device = saved_dev;
-        g_mode = saved_mode;
-    };
-    if (jobs.size() == 1) work(0); // the caller's own thread and engine
-    else worker_pool().run((int)jobs.size(), work);
-    if (first_err.load() != PLB_OK) {
-        g_err = err_msg;
-        for (size_t i = 0; i < count; ++i) problems[i].status = first_err.load();
-    }
-    return first_err.load();
+    const int rc = run_tasks(tasks, dev_of, devices, n_dev, streams);
+    if (rc != PLB_OK)
+        for (size_t i = 0; i < count; ++i) problems[i].status = rc;
+    return rc;
 }
 int plb_ransac_batch(plb_problem *problems, size_t count, int streams) {
     const int dev = g_device;
@@ -2020,6 +2121,65 @@ int plb_ransac_batch_multi(plb_problem *problems, size_t count, int n_gpus, int 
     std::vector<int> devs(n_gpus);
     for (int d = 0; d < n_gpus; ++d) devs[d] = d;
     return batch_impl(problems, count, devs.data(), n_gpus, streams_per_gpu);
+}
+
+// Batch form of the four estimate_* entry points (robust.h:45-46,68-70,112-113,133-134): pixels + cameras in, the
+// pre-step of every problem (threshold scaling, camera unprojection on the device, normalize_points on the worker
+// threads), LO-RANSAC in lock-step groups per kind (tangent-Sampson problems form their own groups), final bundle and
+// un-normalisation.  n_gpus: 0 = all devices of the process, k = the first k, -1 = the calling thread's device only.
+int plb_estimate_batch(plb_estimate_problem *problems, size_t count, int n_gpus, int streams_per_gpu) {
+    if (count == 0) return PLB_OK;
+    if (!problems) {
+        g_err = "null argument";
+        return PLB_ERR_ARG;
+    }
+    const int have = plb_device_count();
+    if (have == 0) {
+        g_err = "no usable CUDA device";
+        return PLB_ERR_CUDA;
+    }
+    if (n_gpus < -1 || n_gpus > have) {
+        g_err = "n_gpus out of range";
+        return PLB_ERR_ARG;
+    }
+    std::vector<int> devs;
+    if (n_gpus == -1) devs.push_back(g_device);
+    else
+        for (int d = 0; d < (n_gpus == 0 ? have : n_gpus); ++d) devs.push_back(d);
+    std::vector<EstimateJob> jobs(count);
+    std::vector<int> rcs(count, PLB_OK);
+    std::vector<std::string> msgs(count);
+    {
+        // the O(N) host part of the pre-step (normalize_points, pixel scaling) in parallel on the worker threads
+        const int nt = (int)std::min<size_t>(count, (size_t)std::max(1, usable_cpus()));
+        auto prep = [&](int w) {
+            for (size_t i = (size_t)w; i < count; i += (size_t)nt) {
+                plb_estimate_problem &p = problems[i];
+                rcs[i] = estimate_prepare(p.kind, p.a, p.b, (size_t)p.n, &p.camera1, &p.camera2, &p.ransac, &p.bundle,
+                                          p.max_error, p.real_focal_check, p.tangent_sampson, p.model, p.inliers, &p.stats,
+                                          &p.counters, jobs[i]);
+                if (rcs[i] != PLB_OK) msgs[i] = g_err;
+            }
+        };
+        if (nt == 1) prep(0);
+        else worker_pool().run(nt, prep);
+    }
+    for (size_t i = 0; i < count; ++i)
+        if (rcs[i] != PLB_OK) {
+            g_err = msgs[i];
+            for (size_t j = 0; j < count; ++j) problems[j].status = rcs[i];
+            return rcs[i];
+        }
+    // the tasks point into their EstimateJob (normalised copies, scaled pixels), which stays alive until the end of the call
+    std::vector<Task> tasks(count);
+    std::vector<int> dev_of(count, -1);
+    for (size_t i = 0; i < count; ++i) tasks[i] = jobs[i].t;
+    const int rc = run_tasks(tasks, dev_of, devs.data(), (int)devs.size(), streams_per_gpu);
+    for (size_t i = 0; i < count; ++i) {
+        problems[i].status = rc;
+        if (rc == PLB_OK) estimate_finish(jobs[i], tasks[i]);
+    }
+    return rc;
 }
 
 int plb_resident_create(int kind, const double *a, const double *b, size_t n_pts) {

@@ -88,6 +88,84 @@ __global__ void k_transpose(const TransposeDesc *__restrict__ descs) {
         coord_max(d.cmax, 2 + c, v);
     }
 }
+// normalize_points (robust/utils.cc:584-644, shared scale) of one problem per CTA, in place on the AoS doubles the caller
+// uploaded: optional centroid shift, then division by the mean norm / sqrt(2).  The two reductions run in the order of
+// the reference's loops — one thread adds the terms one after the other (centroid: x1[k], x2[k] for k = 0..n-1 in four
+// independent chains; scale: |x1[0]|, |x2[0]|, |x1[1]|, ... in one chain) — so the normalised coordinates, and with
+// them every inlier decision downstream, are the bits the CPU path produces.  Everything around the two chains (loads,
+// the subtraction, the norms, the division) is done by the whole CTA, tile by tile through shared memory.
+constexpr int NORM_THREADS = 256, NORM_TILE = 1024;
+__global__ void __launch_bounds__(NORM_THREADS) k_normalize(const NormDesc *__restrict__ descs) {
+    __shared__ double tile[4][NORM_TILE];
+    __shared__ double sh[5];
+    const NormDesc d = descs[blockIdx.x];
+    const int n = d.n, tid = threadIdx.x;
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
+    if (d.centroid) {
+        for (int t0 = 0; t0 < n; t0 += NORM_TILE) {
+            const int m = min_i(NORM_TILE, n - t0);
+            for (int i = tid; i < m; i += NORM_THREADS) {
+                tile[0][i] = d.a[2 * (size_t)(t0 + i)];
+                tile[1][i] = d.a[2 * (size_t)(t0 + i) + 1];
+                tile[2][i] = d.b[2 * (size_t)(t0 + i)];
+                tile[3][i] = d.b[2 * (size_t)(t0 + i) + 1];
+            }
+            __syncthreads();
+            if (tid == 0)
+                for (int i = 0; i < m; ++i) {
+                    c[0] += tile[0][i];
+                    c[1] += tile[1][i];
+                    c[2] += tile[2][i];
+                    c[3] += tile[3][i];
+                }
+            __syncthreads();
+        }
+        if (tid == 0)
+            for (int j = 0; j < 4; ++j) sh[j] = c[j] / (double)n; // centroid /= x.size()
+        __syncthreads();
+        for (int j = 0; j < 4; ++j) c[j] = sh[j];
+    }
+    double scale = 0.0;
+    for (int t0 = 0; t0 < n; t0 += NORM_TILE) {
+        const int m = min_i(NORM_TILE, n - t0);
+        for (int i = tid; i < m; i += NORM_THREADS) {
+            double x0 = d.a[2 * (size_t)(t0 + i)], x1 = d.a[2 * (size_t)(t0 + i) + 1];
+            double y0 = d.b[2 * (size_t)(t0 + i)], y1 = d.b[2 * (size_t)(t0 + i) + 1];
+            if (d.centroid) {
+                x0 -= c[0]; x1 -= c[1]; y0 -= c[2]; y1 -= c[3];
+                d.a[2 * (size_t)(t0 + i)] = x0;
+                d.a[2 * (size_t)(t0 + i) + 1] = x1;
+                d.b[2 * (size_t)(t0 + i)] = y0;
+                d.b[2 * (size_t)(t0 + i) + 1] = y1;
+            }
+            tile[0][i] = sqrt(x0 * x0 + x1 * x1);
+            tile[1][i] = sqrt(y0 * y0 + y1 * y1);
+        }
+        __syncthreads();
+        if (tid == 0)
+            for (int i = 0; i < m; ++i) {
+                scale += tile[0][i];
+                scale += tile[1][i];
+            }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        scale /= sqrt(2.0) * (double)n; // utils.cc: scale /= std::sqrt(2) * x1.size()
+        sh[4] = scale;
+        for (int j = 0; j < 4; ++j) d.out[j] = d.centroid ? c[j] : 0.0;
+        d.out[4] = scale;
+    }
+    __syncthreads();
+    scale = sh[4];
+    for (size_t i = tid; i < 2 * (size_t)n; i += NORM_THREADS) {
+        d.a[i] = d.a[i] / scale;
+        d.b[i] = d.b[i] / scale;
+    }
+}
+void launch_normalize(const NormDesc *descs_dev, int n_desc, cudaStream_t stream) {
+    if (n_desc <= 0) return;
+    k_normalize<<<n_desc, NORM_THREADS, 0, stream>>>(descs_dev);
+}
 void launch_transpose(const TransposeDesc *descs_dev, int n_desc, int max_n_pad, cudaStream_t stream) {
     if (n_desc <= 0) return;
     const int threads = 256;
@@ -805,6 +883,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
 constexpr int SCR_THREADS = 512;
 constexpr int SCR_WARPS = SCR_THREADS / 32;
 constexpr int SCR_TM = 8;
+constexpr int SCR_RQ_TAKE = 8; // cases a lane may queue per pass of the warp-compacted handling
 
 PLB_DEV uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 PLB_DEV void mbar_init(uint64_t *bar, int count) {
@@ -861,6 +940,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const RoundDesc R, Hy
     __shared__ float red_e[SCR_WARPS][SCR_TM];
     __shared__ uint32_t red_c[SCR_WARPS][SCR_TM];
     __shared__ uint32_t s_border[SCR_TM];
+    __shared__ uint16_t rq[SCR_WARPS][32 * SCR_RQ_TAKE]; // per-warp queue of recorded cases: lane << 8 | bit << 3 | model
     // packed-fp32 streaming loop (Sampson kinds): the 9 model constants and the two constants of the streaming test,
     // duplicated (m, m) so that one 64-bit broadcast load feeds both halves of an FFMA2
     constexpr bool PK = PACKED && (KIND == KIND_RELPOSE || KIND == KIND_FUND);
@@ -1129,24 +1209,47 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const RoundDesc R, Hy
                     }
                 }
                 }
-                // compacted handling of the recorded cases
+                // Handling of the recorded cases, compacted across the WARP: the lanes list their cases (model, bit, lane)
+                // in a per-warp queue in shared memory — at most SCR_RQ_TAKE per lane and pass, so the queue cannot
+                // overflow — and the warp then works through the queue 32 entries at a time.  A case is evaluated by
+                // whichever lane picks it up and lands in THAT lane's accumulators of the model (the per-model sums over
+                // lanes come later anyway).  Handling them lane-locally left most lanes idle: a model has a few dozen
+                // inliers among 10 000 correspondences, 1-5 lanes of a warp had work per iteration.
                 for (;;) {
-                    int mi = -1;
-                    uint32_t hm = 0u;
+                    int mine = 0;
 #pragma unroll
-                    for (int i = 0; i < SCR_TM; ++i)
-                        if (mi < 0 && hit[i] != 0u) {
-                            mi = i;
-                            hm = hit[i];
-                        }
-                    if (!__any_sync(0xffffffffu, mi >= 0)) break;
-                    if (mi >= 0) {
+                    for (int i = 0; i < SCR_TM; ++i) mine += __popc(hit[i]);
+                    if (!__any_sync(0xffffffffu, mine > 0)) break;
+                    const int take = mine < SCR_RQ_TAKE ? mine : SCR_RQ_TAKE;
+                    int incl = take;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    int wpos = incl - take;
+                    for (int t = 0; t < take; ++t) {
+                        int mi = 0;
+                        uint32_t hm = 0u;
+#pragma unroll
+                        for (int i = SCR_TM - 1; i >= 0; --i)
+                            if (hit[i] != 0u) {
+                                mi = i;
+                                hm = hit[i];
+                            }
                         const int q = __ffs((int)hm) - 1;
                         const uint32_t cleared = hm & (hm - 1u);
 #pragma unroll
                         for (int i = 0; i < SCR_TM; ++i)
                             if (i == mi) hit[i] = cleared;
-                        const int k = PK ? base + 2 * (tid + (q >> 1) * SCR_THREADS) + (q & 1) : base + tid + q * SCR_THREADS;
+                        rq[warp][wpos++] = (uint16_t)((lane << 8) | (q << 3) | mi);
+                    }
+                    __syncwarp();
+                    for (int eidx = lane; eidx < total; eidx += 32) {
+                        const uint32_t ent = rq[warp][eidx];
+                        const int mi = (int)(ent & 7u), q = (int)((ent >> 3) & 31u), otid = warp * 32 + (int)(ent >> 8);
+                        const int k = PK ? base + 2 * (otid + (q >> 1) * SCR_THREADS) + (q & 1) : base + otid + q * SCR_THREADS;
                         float p[NARR];
 #pragma unroll
                         for (int c = 0; c < NARR; ++c) p[c] = arr[c][k];
@@ -1185,6 +1288,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const RoundDesc R, Hy
                                 }
                         }
                     }
+                    __syncwarp();
                 }
             }
         }
@@ -2087,8 +2191,8 @@ template <int NP> PLB_DEV void llt_solve(const double *A, const double *rhs, dou
 // [r*chunk, (r+1)*chunk).  Every CTA runs the scalar LM logic (optim/lm_impl.h:56-140) redundantly on identical
 // cluster totals, so no broadcast between CTAs is needed.  The reference evaluates the residual of a trial step and,
 // if accepted, the Jacobian at the same parameters in a second pass; here both come from one pass.
-template <int KIND>
-__global__ void __launch_bounds__(LM_THREADS)
+template <int KIND, int MINB>
+__global__ void __launch_bounds__(LM_THREADS, MINB)
     k_lm(const ProblemDev *__restrict__ probs, const LmJob *__restrict__ jobs, const LoJobSrc *__restrict__ job_src,
          const double *__restrict__ models_in, const int *__restrict__ n_jobs_dev, int n_jobs, const char *mask_base,
          int *idx_scratch, int scratch_stride, LmJobOut *outs) {
@@ -2318,6 +2422,16 @@ __global__ void __launch_bounds__(LM_THREADS)
     } // jobs of this cluster
 }
 
+// CTAs of k_lm per SM: 2 caps the kernel at 128 registers so that two jobs share an SM — the LM passes are latency bound
+// (few correspondences per thread, a cluster-wide reduction and a scalar solve per iteration), what counts for the whole
+// job is how many of them are in flight.  PLB_LM_MINB=1 selects the 255-register build.
+static int lm_minb() {
+    static const int minb = [] {
+        const char *e = std::getenv("PLB_LM_MINB");
+        return (e && std::atoi(e) == 1) ? 1 : 2;
+    }();
+    return minb;
+}
 static int lm_cluster_size(int n_jobs, int max_n) {
     static const int per_cta = [] { // correspondences per CTA before another CTA of the cluster pays off
         const char *e = std::getenv("PLB_LM_PER_CTA");
@@ -2351,8 +2465,12 @@ static void launch_lm_t(const ProblemDev *probs, const LmJob *jobs, const LoJobS
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_lm<KIND>, probs, jobs, job_src, models_in, n_jobs_dev, n_jobs, mask_base, idx_scratch,
-                       scratch_stride, out);
+    if (lm_minb() == 2)
+        cudaLaunchKernelEx(&cfg, k_lm<KIND, 2>, probs, jobs, job_src, models_in, n_jobs_dev, n_jobs, mask_base, idx_scratch,
+                           scratch_stride, out);
+    else
+        cudaLaunchKernelEx(&cfg, k_lm<KIND, 1>, probs, jobs, job_src, models_in, n_jobs_dev, n_jobs, mask_base, idx_scratch,
+                           scratch_stride, out);
 }
 static void launch_lm_any(int kind, const ProblemDev *probs, const LmJob *jobs, const LoJobSrc *job_src,
                           const double *models_in, const int *n_jobs_dev, int n_jobs, int n_clusters, int csize,
@@ -2377,7 +2495,7 @@ int lm_round_max_clusters(int kind, int est_jobs, int max_n) {
     (void)kind;
     if (est_jobs < 1) est_jobs = 1;
     const int csize = lm_cluster_size(est_jobs, max_n);
-    int nc = sm_count() / csize;
+    int nc = lm_minb() * sm_count() / csize;
     if (nc > est_jobs) nc = est_jobs;
     return nc < 1 ? 1 : nc;
 }
@@ -2389,6 +2507,176 @@ void launch_lm_round(int kind, const ProblemDev *probs, const LmJob *tmpl, const
     const int nc = lm_round_max_clusters(kind, est_jobs, max_n);
     launch_lm_any(kind, probs, tmpl, job_src, models, n_jobs_dev, job_cap, nc, csize, nullptr, idx_scratch, scratch_stride,
                   out, stream);
+}
+
+// ============================================================================================================
+// relpose_8pt / essential_matrix_8pt (solvers/relpose_8pt.cc:52-95): non-minimal essential matrix from n >= 8 bearings
+// ============================================================================================================
+// One warp per instance.  Row i of the n x 9 system is [x2.x x1^T, x2.y x1^T, x2.z x1^T] (:41-49).
+//   n == 8: last column of the Householder Q of the transposed system (:63-67), no pivoting (lane 0, 9x8).
+//   n  > 8: eigenvector of the smallest eigenvalue of A^T A (:68-72).  Lane <-> entry (p, q) of the Gram matrix, every
+//           lane sums ITS entry over the correspondences in order (the summation order of a sequential loop); then a
+//           cyclic Jacobi eigen-iteration on lane 0 (Eigen's SelfAdjointEigenSolver is iterative too: parity to tolerance).
+// Then the closest essential matrix in Frobenius norm, singular values (a, b, c) -> ((a+b)/2, (a+b)/2, 0) (:74-81), and
+// for the pose variant motion_from_essential with the cheirality test on ALL n correspondences (misc/essential.cc:103-169).
+struct EightScratch {
+    double G[81];
+    double V[81];
+    double e[9];
+    double E[9];
+};
+PLB_DEV void sym_eigen_jacobi9(double *A /*9x9 row-major, symmetric, destroyed*/, double *V /*column c at V[9c..]*/, double *e_min) {
+    constexpr int N = 9;
+    for (int c = 0; c < N; ++c)
+        for (int r = 0; r < N; ++r) V[c * N + r] = (r == c) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < N; ++i) {
+            diag += A[i * N + i] * A[i * N + i];
+            for (int j = i + 1; j < N; ++j) off += A[i * N + j] * A[i * N + j];
+        }
+        if (off <= 1e-32 * diag || off == 0.0) break;
+        for (int p = 0; p < N - 1; ++p)
+            for (int q = p + 1; q < N; ++q) {
+                if (A[p * N + q] == 0.0) continue;
+                const double theta = (A[q * N + q] - A[p * N + p]) / (2.0 * A[p * N + q]);
+                const double t = ((theta >= 0) ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < N; ++k) { // A <- A J
+                    const double akp = A[k * N + p], akq = A[k * N + q];
+                    A[k * N + p] = c * akp - sn * akq;
+                    A[k * N + q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < N; ++k) { // A <- J^T A
+                    const double apk = A[p * N + k], aqk = A[q * N + k];
+                    A[p * N + k] = c * apk - sn * aqk;
+                    A[q * N + k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < N; ++k) {
+                    const double vkp = V[p * N + k], vkq = V[q * N + k];
+                    V[p * N + k] = c * vkp - sn * vkq;
+                    V[q * N + k] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    int best = 0; // first index of the smallest eigenvalue (ascending sort keeps the first of equal values in front)
+    for (int i = 1; i < N; ++i)
+        if (A[i * N + i] < A[best * N + best]) best = i;
+    for (int r = 0; r < N; ++r) e_min[r] = V[best * N + r];
+}
+// householderQr().householderQ().col(8) of the 9 x 8 matrix whose column i is row i of the system (column-major a[c*9+r])
+PLB_DEV void householder_lastcol_9x8(double *a, double *q8) {
+    constexpr int ROWS = 9, COLS = 8;
+    double hc[COLS];
+    for (int k = 0; k < COLS; ++k) {
+        double tail_sq = 0.0;
+        for (int r = k + 1; r < ROWS; ++r) tail_sq += a[k * ROWS + r] * a[k * ROWS + r];
+        const double c0 = a[k * ROWS + k];
+        double tau, beta;
+        if (tail_sq <= 2.2250738585072014e-308) {
+            tau = 0.0;
+            beta = c0;
+            for (int r = k + 1; r < ROWS; ++r) a[k * ROWS + r] = 0.0;
+        } else {
+            beta = sqrt(c0 * c0 + tail_sq);
+            if (c0 >= 0) beta = -beta;
+            for (int r = k + 1; r < ROWS; ++r) a[k * ROWS + r] = a[k * ROWS + r] / (c0 - beta);
+            tau = (beta - c0) / beta;
+        }
+        hc[k] = tau;
+        a[k * ROWS + k] = beta;
+        if (tau != 0.0) {
+            for (int c = k + 1; c < COLS; ++c) {
+                double tmp = 0.0;
+                for (int r = k + 1; r < ROWS; ++r) tmp += a[k * ROWS + r] * a[c * ROWS + r];
+                tmp += a[c * ROWS + k];
+                a[c * ROWS + k] -= tau * tmp;
+                for (int r = k + 1; r < ROWS; ++r) a[c * ROWS + r] -= tau * a[k * ROWS + r] * tmp;
+            }
+        }
+    }
+    for (int r = 0; r < ROWS; ++r) q8[r] = (r == 8) ? 1.0 : 0.0;
+    for (int k = COLS - 1; k >= 0; --k) {
+        const double tau = hc[k];
+        if (tau == 0.0) continue;
+        double tmp = 0.0;
+        for (int r = k + 1; r < ROWS; ++r) tmp += a[k * ROWS + r] * q8[r];
+        tmp += q8[k];
+        q8[k] -= tau * tmp;
+        for (int r = k + 1; r < ROWS; ++r) q8[r] -= tau * a[k * ROWS + r] * tmp;
+    }
+}
+// want_poses == 0: E_out (count x 9, COLUMN-major like Eigen::Matrix3d); else poses_out (count x 4 x 7) + n_out.
+__global__ void __launch_bounds__(128) k_eightpt(size_t count, int n, const double *__restrict__ x1, const double *__restrict__ x2,
+                                                 int want_poses, double *E_out, double *poses_out, int *n_out) {
+    __shared__ EightScratch scratch[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t inst = (size_t)blockIdx.x * 4 + w;
+    if (inst >= count) return;
+    EightScratch &S = scratch[w];
+    const double *a = x1 + inst * (size_t)n * 3, *b = x2 + inst * (size_t)n * 3;
+    if (n == 8) {
+        if (lane == 0) {
+            double At[72];
+            for (int i = 0; i < 8; ++i)
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) At[9 * i + 3 * r + c] = b[3 * i + r] * a[3 * i + c];
+            householder_lastcol_9x8(At, S.e);
+        }
+    } else {
+        for (int ent = lane; ent < 81; ent += 32) {
+            const int p = ent / 9, q = ent % 9;
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) {
+                const double rp = b[3 * i + p / 3] * a[3 * i + p % 3], rq = b[3 * i + q / 3] * a[3 * i + q % 3];
+                s = (i == 0) ? rp * rq : s + rp * rq;
+            }
+            S.G[ent] = s;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int i = 0; i < 9; ++i) // the solver reads the lower triangle
+                for (int j = i + 1; j < 9; ++j) S.G[i * 9 + j] = S.G[j * 9 + i];
+            sym_eigen_jacobi9(S.G, S.V, S.e);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        m3 E, U, V;
+        for (int k = 0; k < 9; ++k) E.a[k] = S.e[k]; // Map<const RowMajor 3x3>
+        double d[3];
+        svd3_dev(E, U, d, V);
+        const double m = (d[0] + d[1]) / 2.;
+        m3 UD;
+        for (int r = 0; r < 3; ++r) {
+            UD(r, 0) = U(r, 0) * m;
+            UD(r, 1) = U(r, 1) * m;
+            UD(r, 2) = U(r, 2) * 0.0;
+        }
+        m3 Vt;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) Vt(r, c) = V(c, r);
+        const m3 Ef = mmul(UD, Vt);
+        for (int k = 0; k < 9; ++k) S.E[k] = Ef.a[k];
+        if (!want_poses) {
+            for (int k = 0; k < 9; ++k) E_out[inst * 9 + k] = Ef.a[3 * (k % 3) + k / 3];
+        } else {
+            double cand[4][7];
+            const unsigned mask = motions_from_E(S.E, a, b, n, cand);
+            int cnt = 0;
+            for (int c = 0; c < 4; ++c)
+                if (mask & (1u << c)) {
+                    for (int k = 0; k < 7; ++k) poses_out[(inst * 4 + cnt) * 7 + k] = cand[c][k];
+                    ++cnt;
+                }
+            n_out[inst] = cnt;
+        }
+    }
+}
+void launch_eightpt(size_t count, int n, const double *x1, const double *x2, int want_poses, double *E_out, double *poses_out,
+                    int *n_out, cudaStream_t stream) {
+    if (count == 0) return;
+    k_eightpt<<<(unsigned)((count + 3) / 4), 128, 0, stream>>>(count, n, x1, x2, want_poses, E_out, poses_out, n_out);
 }
 
 // ============================================================================================================

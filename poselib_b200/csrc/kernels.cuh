@@ -192,6 +192,13 @@ struct TransposeDesc {
     double scale;
     CamDev cam_a, cam_b;
 };
+// normalize_points of one problem (robust/utils.cc:584-644, shared scale), in place on the uploaded AoS doubles.
+struct NormDesc {
+    double *a, *b;  // 2n doubles each
+    double *out;    // 5 doubles (mapped pinned host memory): centroid1 (2), centroid2 (2), scale
+    int n;
+    int centroid;   // normalize_centroid
+};
 struct MaskDesc {
     int pidx;
     int reserved;
@@ -200,6 +207,8 @@ struct MaskDesc {
 };
 
 // ---- launchers (all asynchronous on `stream`) --------------------------------------------------------------
+// normalize_points for n_desc problems (descriptors in device memory), one CTA each.
+void launch_normalize(const NormDesc *descs_dev, int n_desc, cudaStream_t stream);
 // AoS (caller layout) -> SoA fp64 + fp32 for n_desc problems (descriptors in device memory), camera pre-step fused.
 void launch_transpose(const TransposeDesc *descs_dev, int n_desc, int max_n_pad, cudaStream_t stream);
 // Solve + score kernels of one round (kind = kind of every problem of the group).  work: 3 ints of device scratch.
@@ -240,6 +249,9 @@ void launch_pack_mask(const char *mask, uint32_t *bits, size_t n_bytes, cudaStre
 // Batched direct solver calls (solvers/*.h surface): one warp per instance.
 void launch_solver_batch(int kind, int variant, size_t count, const double *a, const double *b, double *out,
                          int *n_out, int flags, cudaStream_t stream);
+// relpose_8pt / essential_matrix_8pt (solvers/relpose_8pt.cc:52-95): count instances of n >= 8 unit bearing pairs each.
+void launch_eightpt(size_t count, int n, const double *x1, const double *x2, int want_poses, double *E_out, double *poses_out,
+                    int *n_out, cudaStream_t stream);
 int device_sm_count();
 
 } // namespace plb

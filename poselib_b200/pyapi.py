@@ -217,3 +217,18 @@ def relpose_7pt(x1, x2):
 def homography_4pt(x1, x2, check_cheirality=True):
     Hs, n = cabi.homography_4pt_batch(_pts(x1, 3)[None], _pts(x2, 3)[None], check_cheirality)
     return [Hs[0].copy()] if n[0] else []
+
+
+def essential_matrix_8pt(x1, x2):
+    """poselib.essential_matrix_8pt (pybind/bindings/solvers.cc): n >= 8 bearing pairs -> E (3x3)."""
+    a = np.asarray(x1, dtype=np.float64).reshape(1, -1, 3)
+    b = np.asarray(x2, dtype=np.float64).reshape(1, -1, 3)
+    return cabi.essential_matrix_8pt_batch(a, b)[0]
+
+
+def relpose_8pt(x1, x2):
+    """poselib.relpose_8pt: n >= 8 bearing pairs -> list of CameraPose (cheirality-consistent motions of E)."""
+    a = np.asarray(x1, dtype=np.float64).reshape(1, -1, 3)
+    b = np.asarray(x2, dtype=np.float64).reshape(1, -1, 3)
+    poses, n = cabi.relpose_8pt_batch(a, b)
+    return [CameraPose(poses[0, i, :4], poses[0, i, 4:]) for i in range(int(n[0]))]

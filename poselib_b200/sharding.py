@@ -54,3 +54,41 @@ def gather_records(local_rec, dist=None):
         dist.all_gather(bufs, pad)
         out = np.concatenate([b[:int(c.item())].cpu().numpy() for b, c in zip(bufs, cnts)])
     return out[np.argsort(out[:, 0], kind="stable")]
+
+
+def gather_masks(local_masks, local_idx, dist=None):
+    """all_gather of the inlier masks as bits.  local_masks: list of 0/1 arrays (one per local problem), local_idx: their
+    global problem indices.  Returns {problem index: mask (uint8 0/1)} on every rank."""
+    sizes = np.array([len(m) for m in local_masks], dtype=np.int64)
+    bits = [np.packbits(np.asarray(m, dtype=np.uint8)) for m in local_masks]
+    blob = np.concatenate(bits) if bits else np.zeros(0, dtype=np.uint8)
+    head = np.stack([np.asarray(local_idx, dtype=np.int64), sizes], axis=1) if len(local_masks) else np.zeros((0, 2), np.int64)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        heads, blobs = [head], [blob]
+    else:
+        import torch
+        ws = dist.get_world_size()
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        meta = torch.tensor([head.shape[0], blob.shape[0]], dtype=torch.int64, device=dev)
+        metas = [torch.zeros_like(meta) for _ in range(ws)]
+        dist.all_gather(metas, meta)
+        mh = int(max(m[0].item() for m in metas))
+        mb = int(max(m[1].item() for m in metas))
+        hp = torch.zeros((max(mh, 1), 2), dtype=torch.int64, device=dev)
+        hp[:head.shape[0]] = torch.from_numpy(head).to(dev)
+        bp = torch.zeros(max(mb, 1), dtype=torch.uint8, device=dev)
+        bp[:blob.shape[0]] = torch.from_numpy(blob).to(dev)
+        hs = [torch.zeros_like(hp) for _ in range(ws)]
+        bs = [torch.zeros_like(bp) for _ in range(ws)]
+        dist.all_gather(hs, hp)
+        dist.all_gather(bs, bp)
+        heads = [h[:int(m[0].item())].cpu().numpy() for h, m in zip(hs, metas)]
+        blobs = [b[:int(m[1].item())].cpu().numpy() for b, m in zip(bs, metas)]
+    out = {}
+    for h, b in zip(heads, blobs):
+        off = 0
+        for idx, n in h:
+            nb = (int(n) + 7) // 8
+            out[int(idx)] = np.unpackbits(b[off:off + nb])[:int(n)]
+            off += nb
+    return out

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(cabi.RansacOpt) == 56
     assert C.sizeof(cabi.RansacStats) == 40
     assert C.sizeof(cabi.BundleOpt) == 72
-    assert C.sizeof(cabi.Counters) == 104
+    assert C.sizeof(cabi.Counters) == 128
     assert C.sizeof(cabi.Camera) == 80
     o = cabi.RansacOpt(1, 2, 9.0, 0.5, 77, True, True, 5)
     cabi.lib().plb_ransac_opt_default(C.byref(o))

@@ -35,8 +35,9 @@ def _worker(rank, world, port, q):
         k, a, b, me, kw = probs[int(i)]
         res.append((int(i), P.ransac(k, a, b, P.RansacOpt(**kw), me)))
     rec = sharding.gather_records(sharding.pack_results(res), dist)
+    masks = sharding.gather_masks([r["inliers"] for _, r in res], [i for i, _ in res], dist)
     if rank == 0:
-        q.put((rec, [p.tolist() for p in parts]))
+        q.put((rec, [p.tolist() for p in parts], {k: v.tolist() for k, v in masks.items()}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,7 +65,7 @@ def test_two_rank_gloo_shard_and_gather():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    rec, parts = q.get(timeout=300)
+    rec, parts, masks = q.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -81,3 +82,4 @@ def test_two_rank_gloo_shard_and_gather():
                          P.RansacOpt(max_iterations=500, min_iterations=100, seed=i), 1.0 / G.FOCAL)
         assert rec[i, 1] == o["stats"]["iterations"] and rec[i, 3] == o["stats"]["num_inliers"]
         assert np.allclose(rec[i, 5:12], o["model"], rtol=0, atol=0)
+        assert masks[i] == np.asarray(o["inliers"]).astype(int).tolist()  # bit-packed masks gathered from both ranks
