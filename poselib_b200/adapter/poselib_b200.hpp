@@ -357,4 +357,59 @@ int homography_4pt(const std::vector<V3> &x1, const std::vector<V3> &x2, Mat3 *H
     return n;
 }
 
+// essential_matrix_8pt / relpose_8pt (solvers/relpose_8pt.h:45-53): n >= 8 unit bearing pairs
+template <typename V3, typename Mat3> void essential_matrix_8pt(const std::vector<V3> &x1, const std::vector<V3> &x2, Mat3 *E) {
+    detail::check(plb_essential_matrix_8pt_batch(1, x1.size(), detail::raw(x1), detail::raw(x2), reinterpret_cast<double *>(E)));
+}
+template <typename V3, typename Pose> int relpose_8pt(const std::vector<V3> &x1, const std::vector<V3> &x2, std::vector<Pose> *output) {
+    double out[28];
+    int32_t n = 0;
+    detail::check(plb_relpose_8pt_batch(1, x1.size(), detail::raw(x1), detail::raw(x2), out, &n));
+    output->clear(); // relpose_8pt.cc:91
+    for (int i = 0; i < n; ++i) {
+        Pose p;
+        detail::pose_from(out + 7 * i, &p);
+        output->push_back(p);
+    }
+    return n;
+}
+
+// ---- batches of independent image pairs over the GPUs of the process (no reference counterpart: PoseLib callers loop) --
+// One estimate_relative_pose per element, all in ONE call: lock-step groups on every device (n_gpus = 0: all devices,
+// k: the first k, -1: the calling thread's device), results written back into poses / inliers / the returned stats.
+template <typename RansacStats, typename P2, typename Camera, typename Opt, typename Pose>
+std::vector<RansacStats> estimate_relative_pose_batch(const std::vector<std::vector<P2>> &x1, const std::vector<std::vector<P2>> &x2,
+                                                      const std::vector<Camera> &camera1, const std::vector<Camera> &camera2,
+                                                      const Opt &opt, std::vector<Pose> *poses,
+                                                      std::vector<std::vector<char>> *inliers, int n_gpus = 0, int streams = 8) {
+    const size_t count = x1.size();
+    std::vector<plb_estimate_problem> P(count);
+    poses->resize(count);
+    inliers->resize(count);
+    for (size_t i = 0; i < count; ++i) {
+        plb_estimate_problem &q = P[i];
+        q = plb_estimate_problem();
+        q.kind = PLB_KIND_RELPOSE;
+        q.tangent_sampson = opt.tangent_sampson ? 1 : 0;
+        q.n = x1[i].size();
+        q.a = detail::raw(x1[i]);
+        q.b = detail::raw(x2[i]);
+        q.camera1 = detail::camera_to_c(camera1[i]);
+        q.camera2 = detail::camera_to_c(camera2[i]);
+        q.ransac = detail::to_c(opt.ransac);
+        q.bundle = detail::bundle_to_c(opt.bundle);
+        q.max_error = opt.max_error;
+        detail::pose_to((*poses)[i], q.model);
+        (*inliers)[i].resize(x1[i].size());
+        q.inliers = (*inliers)[i].data();
+    }
+    detail::check(plb_estimate_batch(P.data(), count, n_gpus, streams));
+    std::vector<RansacStats> out(count);
+    for (size_t i = 0; i < count; ++i) {
+        detail::pose_from(P[i].model, &(*poses)[i]);
+        out[i] = detail::from_c<RansacStats>(P[i].stats);
+    }
+    return out;
+}
+
 } // namespace poselib_b200

@@ -2422,13 +2422,13 @@ __global__ void __launch_bounds__(LM_THREADS, MINB)
     } // jobs of this cluster
 }
 
-// CTAs of k_lm per SM: 2 caps the kernel at 128 registers so that two jobs share an SM — the LM passes are latency bound
-// (few correspondences per thread, a cluster-wide reduction and a scalar solve per iteration), what counts for the whole
-// job is how many of them are in flight.  PLB_LM_MINB=1 selects the 255-register build.
+// CTAs of k_lm per SM.  The 255-register build (one CTA per SM) is the default; PLB_LM_MINB=2 selects a build capped at
+// 128 registers so that two jobs share an SM.  Measured on B200 (profiles/r02_summary.md): the spills of the capped build
+// cost more than the second resident CTA gains (LO time per 256-pair step 9.5 ms vs 7.5 ms, C4 single call 2.3 vs 2.0 ms).
 static int lm_minb() {
     static const int minb = [] {
         const char *e = std::getenv("PLB_LM_MINB");
-        return (e && std::atoi(e) == 1) ? 1 : 2;
+        return (e && std::atoi(e) == 2) ? 2 : 1;
     }();
     return minb;
 }

@@ -132,6 +132,26 @@ int main(int argc, char **argv) {
         poselib_b200::relpose_7pt(b1, b2, &Ms);
         std::vector<Vector3d> b14(b1.begin(), b1.begin() + 4), b24(b2.begin(), b2.begin() + 4);
         poselib_b200::homography_4pt(b14, b24, &H);
+        // non-minimal solver and the batch / multi-GPU form
+        std::vector<Vector3d> b18(8), b28(8);
+        for (int i = 0; i < 8; ++i) {
+            b18[i] = {{x1[i](0), x1[i](1), 1.0}};
+            b28[i] = {{x2[i](0), x2[i](1), 1.0}};
+        }
+        Matrix3d E8{};
+        poselib_b200::essential_matrix_8pt(b18, b28, &E8);
+        poselib_b200::relpose_8pt(b18, b28, &poses);
+        std::vector<std::vector<Vector2d>> bx1(3, x1), bx2(3, x2);
+        std::vector<Camera> cams(3, cam);
+        std::vector<CameraPose> bposes;
+        std::vector<std::vector<char>> binl;
+        std::vector<RansacStats> bst =
+            poselib_b200::estimate_relative_pose_batch<RansacStats>(bx1, bx2, cams, cams, ro, &bposes, &binl, 0, 2);
+        RansacStats one = poselib_b200::estimate_relative_pose<RansacStats>(x1, x2, cam, cam, ro, &pose, &inl);
+        if (bst.size() != 3 || bst[0].iterations != one.iterations || bst[2].num_inliers != one.num_inliers || binl[1] != inl) {
+            std::printf("batch call differs from the single call\n");
+            return 1;
+        }
         std::printf("adapter run ok\n");
     } else {
         std::printf("adapter link ok (%d devices)\n", plb_device_count());
