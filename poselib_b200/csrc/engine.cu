@@ -928,7 +928,13 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         }
     }
     int smp_cur = 0; // sampler states of the current round: E.smp[smp_cur * NP ..]; the advanced ones land in the other half
-    const size_t CHUNK_MAX = 16384, ROUND_MAX = 32768, S_TOT_MAX = 262144;
+    // Round sizes.  A small group leaves the GPU mostly idle, so speculating further ahead costs no time while every
+    // round saved is a whole launch chain of latency: the first round and the per-round cap grow as the group shrinks
+    // (1 problem: 16384 then up to 65536 samples; >= 16 problems: 1024 doubling to 16384).
+    const size_t few = (size_t)std::max(1, std::min(NP, 16));
+    const size_t CHUNK_MAX = std::max<size_t>(16384, 65536 / few), ROUND_MAX = std::max<size_t>(32768, 65536 / few),
+                 S_TOT_MAX = 262144;
+    for (PState &S : PS) S.chunk = std::max<size_t>(1024, 16384 / few);
     // 0 exact, 1 fast (fp32 screen + fp64 confirmation of candidates); the tangent-Sampson kind has no fp32 copy
     const int mode = (kind == KIND_RELPOSE_TS) ? 0 : current_mode();
     int cap_factor = kind_is_relpose(kind) ? 8 : MAXM;
@@ -1013,10 +1019,6 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         PLB_CUDA(cudaMemcpyAsync(E.rp.p, E.h_rp.p, sizeof(RoundProb) * na, cudaMemcpyHostToDevice, st));
         h2d += sizeof(int) * (4 * na + 1) + sizeof(RoundProb) * na;
         PLB_CUDA(cudaMemsetAsync(E.work.p, 0, CTL_WORDS * sizeof(int), st));
-        PLB_CUDA(cudaEventRecord(E.ev0, st));
-        launch_sample(E.rp.p, na, E.smp.p + (size_t)smp_cur * NP, E.smp.p + (size_t)(smp_cur ^ 1) * NP, E.samples.p, st);
-        E.launches++;
-        mark(PH_SAMPLE);
         RoundDesc R;
         R.probs = E.probs.p;
         R.active = E.act.p;
@@ -1060,6 +1062,11 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             out.s5_roots = E.s5_roots.p;
             out.s5_nroots = E.s5_nroots.p;
         }
+        // (every buffer of the round is allocated by now: nothing between the events below can stall on cudaMalloc)
+        PLB_CUDA(cudaEventRecord(E.ev0, st));
+        launch_sample(E.rp.p, na, E.smp.p + (size_t)smp_cur * NP, E.smp.p + (size_t)(smp_cur ^ 1) * NP, E.samples.p, st);
+        E.launches++;
+        mark(PH_SAMPLE);
         launch_hypotheses(kind, R, E.work.p, out, mode, max_n_pad, st, E.ev2);
         PLB_CUDA(cudaEventRecord(E.ev1, st));
         E.launches += kind_is_relpose(kind) ? 4 : 2; // k_solve (or k5_prep + k5_roots + k5_back) + scoring

@@ -1327,8 +1327,10 @@ PLB_DEV void solve_5pt_poly_grp8(double *W, const MonoTables *T, int sl) {
         }
         __syncwarp();
     }
+    // back-substitution: only rows 4..9 of A^{-1} B enter the polynomial matrix below (:176-189), and row r depends on
+    // the rows below it only, so rows 0..3 (30 of the 45 inner-product terms per column) are never formed
     for (int c = 10 + sl; c < 20; c += 8) {
-        for (int r = 9; r >= 0; --r) {
+        for (int r = 9; r >= 4; --r) {
             double s = C[r * 20 + c];
             for (int k = r + 1; k < 10; ++k) s -= C[r * 20 + k] * C[k * 20 + c];
             C[r * 20 + c] = s / C[r * 20 + r];
