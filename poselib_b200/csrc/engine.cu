@@ -204,6 +204,7 @@ __global__ void k_gather_models(const double *__restrict__ models, const int *__
 struct Engine {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;
+    cudaEvent_t ev_block = nullptr; // cudaEventBlockingSync: the waiting thread sleeps instead of spinning
     bool ready = false;
     int device = -1;
     DevBuf<double> in, soa64, px64, models, lm_in, s5_blk, s5_cpoly, s5_roots;
@@ -275,6 +276,7 @@ struct Engine {
         if (!ev2) PLB_CUDA(cudaEventCreate(&ev2));
         if (!ev3) PLB_CUDA(cudaEventCreate(&ev3));
         if (!ev4) PLB_CUDA(cudaEventCreate(&ev4));
+        if (!ev_block) PLB_CUDA(cudaEventCreateWithFlags(&ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
         {
             int r = h_work.ensure(8);
             if (r) return r;
@@ -284,6 +286,11 @@ struct Engine {
         return PLB_OK;
     }
 };
+// Batch workers of an oversubscribed process (more lock-step groups in flight than cores this process may use: several
+// ranks sharing a host) wait for their round by sleeping on a blocking event; spinning threads would take the cores from
+// the threads that have a round to replay.  Single calls and small batches spin (lowest latency).
+static thread_local bool t_blocking_sync = false;
+
 // One engine (stream, events, grow-only buffers) per host thread AND device: a thread that switches devices with
 // plb_set_device gets a separate engine for each, so streams and buffers never cross devices.  Engines live as long as
 // the process (buffers are reused across calls).
@@ -611,7 +618,12 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
     float gpu_ms_total = 0.f, gpu_ms_score = 0.f, gpu_ms_confirm = 0.f, gpu_ms_lo = 0.f;
     auto sync_timed = [&](double *acc) -> int {
         auto t0 = std::chrono::steady_clock::now();
-        PLB_CUDA(cudaStreamSynchronize(st));
+        if (t_blocking_sync) { // more waiting threads than cores: sleep on an event instead of spinning on the stream
+            PLB_CUDA(cudaEventRecord(E.ev_block, st));
+            PLB_CUDA(cudaEventSynchronize(E.ev_block));
+        } else {
+            PLB_CUDA(cudaStreamSynchronize(st));
+        }
         if (acc) *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         return PLB_OK;
     };
@@ -928,13 +940,15 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         }
     }
     int smp_cur = 0; // sampler states of the current round: E.smp[smp_cur * NP ..]; the advanced ones land in the other half
-    // Round sizes.  A small group leaves the GPU mostly idle, so speculating further ahead costs no time while every
+    // Round sizes.  A small group leaves the GPU mostly idle, so speculating further ahead costs little time while every
     // round saved is a whole launch chain of latency: the first round and the per-round cap grow as the group shrinks
-    // (1 problem: 16384 then up to 65536 samples; >= 16 problems: 1024 doubling to 16384).
+    // (1 problem: 4096 doubling up to 65536 samples; >= 16 problems: 1024 doubling to 16384).  The first round stays
+    // moderate on purpose: a loop that stops right after min_iterations (high inlier ratio) would otherwise pay for
+    // thousands of speculative samples and their LO refits (measured: C4 single call 2.0 -> 3.3 ms with 16384).
     const size_t few = (size_t)std::max(1, std::min(NP, 16));
     const size_t CHUNK_MAX = std::max<size_t>(16384, 65536 / few), ROUND_MAX = std::max<size_t>(32768, 65536 / few),
                  S_TOT_MAX = 262144;
-    for (PState &S : PS) S.chunk = std::max<size_t>(1024, 16384 / few);
+    for (PState &S : PS) S.chunk = std::min<size_t>(4096, std::max<size_t>(1024, 16384 / few));
     // 0 exact, 1 fast (fp32 screen + fp64 confirmation of candidates); the tangent-Sampson kind has no fp32 copy
     const int mode = (kind == KIND_RELPOSE_TS) ? 0 : current_mode();
     int cap_factor = kind_is_relpose(kind) ? 8 : MAXM;
@@ -2022,10 +2036,13 @@ static int run_tasks(std::vector<Task> &tasks, std::vector<int> &dev_of, const i
     std::string err_msg;
     std::mutex mtx;
     const int mode = current_mode();
+    const bool oversubscribed = (int)jobs.size() > usable_cpus();
     auto work = [&](int w) {
         const int saved_dev = g_device, saved_mode = g_mode;
+        const bool saved_block = t_blocking_sync;
         g_device = jobs[w].device;
         g_mode = mode;
+        t_blocking_sync = oversubscribed;
         for (auto &grp : jobs[w].groups) {
             const int rc = run_group(grp[0]->kind, grp);
             if (rc != PLB_OK) {
@@ -2038,6 +2055,7 @@ static int run_tasks(std::vector<Task> &tasks, std::vector<int> &dev_of, const i
         }
         g_device = saved_dev;
         g_mode = saved_mode;
+        t_blocking_sync = saved_block;
     };
     if (jobs.size() == 1) work(0); // the caller's own thread and engine
     else worker_pool().run((int)jobs.size(), work);

@@ -14,6 +14,7 @@
 #include "solvers.cuh"
 #include "screen_math.cuh"
 #include <cooperative_groups.h>
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
@@ -1121,7 +1122,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const RoundDesc R, Hy
                     // Blackwell packed fp32 (FFMA2): lane-adjacent correspondences (2p, 2p+1) ride in the two halves of
                     // 64-bit registers; every instruction of the residual evaluates both.  Bit 2j+h of a hit mask is
                     // correspondence base + 2 (tid + j SCR_THREADS) + h.  The test is scr::sampson_maybe_x.
-                    auto pair_hits = [&](const float2 *M2, float2 a0, float2 a1, float2 b0, float2 b1, uint32_t bx, uint32_t by) -> uint32_t {
+                    auto pair_hits = [&](const float2 *M2, float2 a0, float2 a1, float2 b0, float2 b1, uint32_t bx, uint32_t by, uint32_t &h) {
                         const float2 e0 = __ffma2_rn(M2[0], a0, __ffma2_rn(M2[1], a1, M2[2]));
                         const float2 e1 = __ffma2_rn(M2[3], a0, __ffma2_rn(M2[4], a1, M2[5]));
                         const float2 e2 = __ffma2_rn(M2[6], a0, __ffma2_rn(M2[7], a1, M2[8]));
@@ -1131,8 +1132,20 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const RoundDesc R, Hy
                         const float2 D = __ffma2_rn(e0, e0, __ffma2_rn(e1, e1, __ffma2_rn(f0, f0, __fmul2_rn(f1, f1))));
                         const float2 q = __fmul2_rn(Cn, Cn);
                         const float2 rhs = __ffma2_rn(M2[9], D, M2[10]);
-                        return (q.x <= rhs.x ? bx : 0u) | (q.y <= rhs.y ? by : 0u);
+                        if (q.x <= rhs.x) h |= bx; // predicated ORs
+                        if (q.y <= rhs.y) h |= by;
                     };
+                    // the 11 duplicated constants of a model: six 128-bit loads (ctx2 rows are 16-byte aligned, 12 float2)
+                    auto load_m2 = [&](int i, float2 *M2) {
+                        float t[24];
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) lds_v4(reinterpret_cast<const float *>(&ctx2[i][0]) + 4 * k, t + 4 * k);
+#pragma unroll
+                        for (int k = 0; k < 11; ++k) M2[k] = make_float2(t[2 * k], t[2 * k + 1]);
+                    };
+                    // FULL: the tile holds SCR_TM models (all but the last tile of a problem) -> no per-model bound checks
+                    auto stream = [&](auto full_c) {
+                    constexpr bool FULL = decltype(full_c)::value;
                     int p0 = tid; // pair index inside the chunk
                     uint32_t sh = 0;
                     const int npairs = (lim - base + 1) >> 1;
@@ -1147,12 +1160,11 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const RoundDesc R, Hy
                         const uint32_t q0 = 1u << sh, q1 = 2u << sh, q2 = 4u << sh, q3 = 8u << sh;
 #pragma unroll
                         for (int i = 0; i < SCR_TM; ++i) {
-                            if (i < tm) {
+                            if (FULL || i < tm) {
                                 float2 M2[11];
-#pragma unroll
-                                for (int k = 0; k < 11; ++k) M2[k] = lds_f2(&ctx2[i][k]);
-                                hit[i] |= pair_hits(M2, pa[0][0], pa[0][1], pa[0][2], pa[0][3], q0, q1);
-                                hit[i] |= pair_hits(M2, pa[1][0], pa[1][1], pa[1][2], pa[1][3], q2, q3);
+                                load_m2(i, M2);
+                                pair_hits(M2, pa[0][0], pa[0][1], pa[0][2], pa[0][3], q0, q1, hit[i]);
+                                pair_hits(M2, pa[1][0], pa[1][1], pa[1][2], pa[1][3], q2, q3, hit[i]);
                             }
                         }
                     }
@@ -1164,14 +1176,16 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const RoundDesc R, Hy
                         const uint32_t q0 = 1u << sh, q1 = 2u << sh;
 #pragma unroll
                         for (int i = 0; i < SCR_TM; ++i) {
-                            if (i < tm) {
+                            if (FULL || i < tm) {
                                 float2 M2[11];
-#pragma unroll
-                                for (int k = 0; k < 11; ++k) M2[k] = lds_f2(&ctx2[i][k]);
-                                hit[i] |= pair_hits(M2, pa[0], pa[1], pa[2], pa[3], q0, q1);
+                                load_m2(i, M2);
+                                pair_hits(M2, pa[0], pa[1], pa[2], pa[3], q0, q1, hit[i]);
                             }
                         }
                     }
+                    };
+                    if (tm == SCR_TM) stream(std::true_type{});
+                    else stream(std::false_type{});
                 } else {
                 int k0 = base + tid;
                 uint32_t qbit = 1u;
