@@ -313,7 +313,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=256, help="independent C2 image pairs per GPU per step")
-    ap.add_argument("--streams", type=int, default=12, help="lock-step problem groups in flight per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="lock-step problem groups in flight per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="fast", choices=["exact", "fast"],
                     help="fast (the library default): fp32 SMEM screening of every model with rigorous error intervals + "

@@ -921,6 +921,10 @@ PLB_DEV void mbar_wait(uint64_t *bar, uint32_t phase) {
 PLB_DEV void lds_v4(const float *p, float *o) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(smem_u32(p)));
 }
+// the same from a 32-bit shared-memory address computed once (base + compile-time offset folds into the instruction)
+PLB_DEV void lds_v4_at(uint32_t addr, float *o) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(addr));
+}
 PLB_DEV float2 lds_f2(const float2 *p) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem_u32(p)));
@@ -1139,10 +1143,11 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const RoundDesc R, Hy
                         if (q.y <= rhs.y) h |= by;
                     };
                     // the 11 duplicated constants of a model: six 128-bit loads (ctx2 rows are 16-byte aligned, 12 float2)
+                    const uint32_t ctx2_addr = smem_u32(&ctx2[0][0]);
                     auto load_m2 = [&](int i, float2 *M2) {
                         float t[24];
 #pragma unroll
-                        for (int k = 0; k < 6; ++k) lds_v4(reinterpret_cast<const float *>(&ctx2[i][0]) + 4 * k, t + 4 * k);
+                        for (int k = 0; k < 6; ++k) lds_v4_at(ctx2_addr + (uint32_t)(i * 96 + k * 16), t + 4 * k);
 #pragma unroll
                         for (int k = 0; k < 11; ++k) M2[k] = make_float2(t[2 * k], t[2 * k + 1]);
                     };
