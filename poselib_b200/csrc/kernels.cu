@@ -285,73 +285,82 @@ struct ScoreRed {
     double s[SCORE_WARPS];
     uint32_t c[SCORE_WARPS];
 };
-template <int KIND>
+template <int KIND, int NT = SCORE_THREADS>
 PLB_DEV void cta_score(const ProblemDev &P, const double *model, double sq_thr, ScoreRed *red, uint32_t &count_out,
                        double &score_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // NT physical threads (256, or 128 in the two-jobs-per-SM LM build) stand for the SCORE_THREADS = 256 threads of the
+    // fixed summation order: thread tid accumulates the partial sums of the "virtual" threads tid, tid + NT, ... in
+    // separate registers and reduces them as the virtual warps they belong to — same bits for any NT.
+    static_assert(SCORE_THREADS % NT == 0 && NT % 32 == 0, "NT must divide the virtual thread count");
+    constexpr int VPT = SCORE_THREADS / NT;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int n = P.n;
-    uint32_t cnt = 0;
-    double score = 0.0;
-    if (tid < SCORE_THREADS) {
+    if (tid < NT) {
         ModelCtx<KIND> C;
         C.init(model);
-        if (KIND == KIND_PNP) {
-            const double *__restrict__ xx = P.p[0], *__restrict__ xy = P.p[1];
-            const double *__restrict__ Xx = P.p[2], *__restrict__ Xy = P.p[3], *__restrict__ Xz = P.p[4];
-            const double *Pm = reinterpret_cast<const double *>(&C);
-            for (int k = tid; k < n; k += SCORE_THREADS) {
-                const double X0 = Xx[k], X1 = Xy[k], X2 = Xz[k];
-                const double x0 = xx[k], x1 = xy[k];
-                const double z0 = Pm[0] * X0 + Pm[1] * X1 + Pm[2] * X2 + Pm[3];
-                const double z1 = Pm[4] * X0 + Pm[5] * X1 + Pm[6] * X2 + Pm[7];
-                const double z2 = Pm[8] * X0 + Pm[9] * X1 + Pm[10] * X2 + Pm[11];
-                if (z2 <= 0.0) continue;
-                const double inv_z2 = 1.0 / z2;
-                const double r_0 = z0 * inv_z2 - x0;
-                const double r_1 = z1 * inv_z2 - x1;
-                const double r_sq = r_0 * r_0 + r_1 * r_1;
-                if (r_sq < sq_thr) {
-                    ++cnt;
-                    score += r_sq;
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            const int vt = tid + v * NT;
+            uint32_t cnt = 0;
+            double score = 0.0;
+            if (KIND == KIND_PNP) {
+                const double *__restrict__ xx = P.p[0], *__restrict__ xy = P.p[1];
+                const double *__restrict__ Xx = P.p[2], *__restrict__ Xy = P.p[3], *__restrict__ Xz = P.p[4];
+                const double *Pm = reinterpret_cast<const double *>(&C);
+                for (int k = vt; k < n; k += SCORE_THREADS) {
+                    const double X0 = Xx[k], X1 = Xy[k], X2 = Xz[k];
+                    const double x0 = xx[k], x1 = xy[k];
+                    const double z0 = Pm[0] * X0 + Pm[1] * X1 + Pm[2] * X2 + Pm[3];
+                    const double z1 = Pm[4] * X0 + Pm[5] * X1 + Pm[6] * X2 + Pm[7];
+                    const double z2 = Pm[8] * X0 + Pm[9] * X1 + Pm[10] * X2 + Pm[11];
+                    if (z2 <= 0.0) continue;
+                    const double inv_z2 = 1.0 / z2;
+                    const double r_0 = z0 * inv_z2 - x0;
+                    const double r_1 = z1 * inv_z2 - x1;
+                    const double r_sq = r_0 * r_0 + r_1 * r_1;
+                    if (r_sq < sq_thr) {
+                        ++cnt;
+                        score += r_sq;
+                    }
+                }
+            } else if (KIND == KIND_RELPOSE_TS) {
+                const double *M = reinterpret_cast<const double *>(&C);
+                for (int k = vt; k < n; k += SCORE_THREADS) {
+                    double vv[TS_ARRAYS];
+                    load_ts(P, k, vv);
+                    const double r2 = tangent_r2(M, vv);
+                    bool inl = r2 < sq_thr;
+                    if (inl) inl = cheirality_ok(M + 9, M + 13, mk(vv[0], vv[1], vv[2]), mk(vv[3], vv[4], vv[5]), 0.01);
+                    if (inl) {
+                        ++cnt;
+                        score += r2;
+                    }
+                }
+            } else {
+                const double *__restrict__ ax = P.p[0], *__restrict__ ay = P.p[1];
+                const double *__restrict__ bx = P.p[2], *__restrict__ by = P.p[3];
+                const double *M = reinterpret_cast<const double *>(&C); // first 9 doubles: E / F / H row-major
+                for (int k = vt; k < n; k += SCORE_THREADS) {
+                    const double x1_0 = ax[k], x1_1 = ay[k], x2_0 = bx[k], x2_1 = by[k];
+                    double r2;
+                    if (KIND == KIND_HOMOG) r2 = homography_r2(M, x1_0, x1_1, x2_0, x2_1);
+                    else r2 = sampson_r2(M, x1_0, x1_1, x2_0, x2_1);
+                    bool inl = r2 < sq_thr;
+                    if (KIND == KIND_RELPOSE) {
+                        if (inl) inl = cheirality_ok(M + 9, M + 13, bearing(x1_0, x1_1), bearing(x2_0, x2_1), 0.01);
+                    }
+                    if (inl) {
+                        ++cnt;
+                        score += r2;
+                    }
                 }
             }
-        } else if (KIND == KIND_RELPOSE_TS) {
-            const double *M = reinterpret_cast<const double *>(&C);
-            for (int k = tid; k < n; k += SCORE_THREADS) {
-                double v[TS_ARRAYS];
-                load_ts(P, k, v);
-                const double r2 = tangent_r2(M, v);
-                bool inl = r2 < sq_thr;
-                if (inl) inl = cheirality_ok(M + 9, M + 13, mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), 0.01);
-                if (inl) {
-                    ++cnt;
-                    score += r2;
-                }
+            cnt = warp_sum_u(cnt);
+            score = warp_sum(score);
+            if (lane == 0) {
+                red->c[vt >> 5] = cnt;
+                red->s[vt >> 5] = score;
             }
-        } else {
-            const double *__restrict__ ax = P.p[0], *__restrict__ ay = P.p[1];
-            const double *__restrict__ bx = P.p[2], *__restrict__ by = P.p[3];
-            const double *M = reinterpret_cast<const double *>(&C); // first 9 doubles: E / F / H row-major
-            for (int k = tid; k < n; k += SCORE_THREADS) {
-                const double x1_0 = ax[k], x1_1 = ay[k], x2_0 = bx[k], x2_1 = by[k];
-                double r2;
-                if (KIND == KIND_HOMOG) r2 = homography_r2(M, x1_0, x1_1, x2_0, x2_1);
-                else r2 = sampson_r2(M, x1_0, x1_1, x2_0, x2_1);
-                bool inl = r2 < sq_thr;
-                if (KIND == KIND_RELPOSE) {
-                    if (inl) inl = cheirality_ok(M + 9, M + 13, bearing(x1_0, x1_1), bearing(x2_0, x2_1), 0.01);
-                }
-                if (inl) {
-                    ++cnt;
-                    score += r2;
-                }
-            }
-        }
-        cnt = warp_sum_u(cnt);
-        score = warp_sum(score);
-        if (lane == 0) {
-            red->c[warp] = cnt;
-            red->s[warp] = score;
         }
     }
     __syncthreads();
@@ -1983,7 +1992,7 @@ template <int NV> PLB_DEV void cluster_sum(LmShared *S, const double *v, int &bu
     __syncthreads();
     if (threadIdx.x < NV) {
         double s = 0.0;
-        for (int w = 0; w < LM_WARPS; ++w) s += S->red[w][threadIdx.x];
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += S->red[w][threadIdx.x];
         S->sums[buf][threadIdx.x] = s;
     }
     cluster.sync();
@@ -2021,7 +2030,7 @@ PLB_DEV void lm_eval_pass(const ProblemDev &P, const LmParams &prm, const LossFn
     JacAcc<NP> A;
     A.zero();
     double lsum = 0.0, rows = 0.0;
-    for (int i = threadIdx.x; i < na; i += LM_THREADS) {
+    for (int i = threadIdx.x; i < na; i += (int)blockDim.x) {
         const int k = list ? list[i] : lo + i;
         if (KIND == KIND_PNP) {
             const double X0 = P.p[2][k], X1 = P.p[3][k], X2 = P.p[4][k];
@@ -2214,7 +2223,7 @@ template <int NP> PLB_DEV void llt_solve(const double *A, const double *rhs, dou
 // cluster totals, so no broadcast between CTAs is needed.  The reference evaluates the residual of a trial step and,
 // if accepted, the Jacobian at the same parameters in a second pass; here both come from one pass.
 template <int KIND, int MINB>
-__global__ void __launch_bounds__(LM_THREADS, MINB)
+__global__ void __launch_bounds__(LM_THREADS / MINB, MINB)
     k_lm(const ProblemDev *__restrict__ probs, const LmJob *__restrict__ jobs, const LoJobSrc *__restrict__ job_src,
          const double *__restrict__ models_in, const int *__restrict__ n_jobs_dev, int n_jobs, const char *mask_base,
          int *idx_scratch, int scratch_stride, LmJobOut *outs) {
@@ -2261,7 +2270,7 @@ __global__ void __launch_bounds__(LM_THREADS, MINB)
         const double *M = reinterpret_cast<const double *>(&C);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         int base = 0;
-        for (int t0 = lo; t0 < hi; t0 += LM_THREADS) {
+        for (int t0 = lo; t0 < hi; t0 += (int)blockDim.x) {
             const int k = t0 + threadIdx.x;
             bool keep = false;
             if (k < hi) {
@@ -2280,7 +2289,7 @@ __global__ void __launch_bounds__(LM_THREADS, MINB)
             int off = base;
             for (int w = 0; w < warp; ++w) off += S.wcount[w];
             int tile = 0;
-            for (int w = 0; w < LM_WARPS; ++w) tile += S.wcount[w];
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tile += S.wcount[w];
             if (keep) mylist[off + __popc(bal & ((1u << lane) - 1u))] = k;
             base += tile;
             __syncthreads();
@@ -2434,7 +2443,7 @@ __global__ void __launch_bounds__(LM_THREADS, MINB)
         double mdl[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) mdl[k] = S.par_new[k];
-        cta_score<KIND>(P, mdl, P.sq_thr, &S.sred, cnt, score);
+        cta_score<KIND, LM_THREADS / MINB>(P, mdl, P.sq_thr, &S.sred, cnt, score);
         if (threadIdx.x == 0) {
             out->count = cnt;
             out->score = score;
@@ -2444,9 +2453,11 @@ __global__ void __launch_bounds__(LM_THREADS, MINB)
     } // jobs of this cluster
 }
 
-// CTAs of k_lm per SM.  The 255-register build (one CTA per SM) is the default; PLB_LM_MINB=2 selects a build capped at
-// 128 registers so that two jobs share an SM.  Measured on B200 (profiles/r02_summary.md): the spills of the capped build
-// cost more than the second resident CTA gains (LO time per 256-pair step 9.5 ms vs 7.5 ms, C4 single call 2.3 vs 2.0 ms).
+// CTAs of k_lm per SM.  k_lm needs ~255 registers per thread.  1: 256 threads, one CTA (one job, or one slice of a job's
+// cluster) per SM.  2 (PLB_LM_MINB=2): 128 threads per CTA, still 255 registers, two CTAs per SM — every job gets half the
+// threads but twice as many jobs are in flight; the LM passes are latency bound (few correspondences per thread, a
+// cluster-wide reduction and a scalar solve per iteration).  (A 256-thread build capped at 128 registers was measured
+// and rejected: its spills cost more than the second resident CTA gained, profiles/r02_summary.md.)
 static int lm_minb() {
     static const int minb = [] {
         const char *e = std::getenv("PLB_LM_MINB");
@@ -2477,7 +2488,7 @@ static void launch_lm_t(const ProblemDev *probs, const LmJob *jobs, const LoJobS
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(n_clusters * csize), 1, 1);
-    cfg.blockDim = dim3(LM_THREADS, 1, 1);
+    cfg.blockDim = dim3((unsigned)(LM_THREADS / lm_minb()), 1, 1);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];

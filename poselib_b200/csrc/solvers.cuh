@@ -1321,9 +1321,16 @@ PLB_DEV void solve_5pt_poly_grp8(double *W, const MonoTables *T, int sl) {
                 if (r > k) C[r * 20 + k] /= pv;
         }
         __syncwarp();
+        // the multipliers of this step are read once into registers (every column of the lane reuses them); rows are
+        // walked bottom-up with static register indices, each element is updated exactly as before
+        double lmul[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) lmul[j] = (9 - j > k) ? C[(9 - j) * 20 + k] : 0.0;
         for (int c = k + 1 + sl; c < 20; c += 8) {
             const double ckc = C[k * 20 + c];
-            for (int r = k + 1; r < 10; ++r) C[r * 20 + c] -= C[r * 20 + k] * ckc;
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                if (9 - j > k) C[(9 - j) * 20 + c] -= lmul[j] * ckc;
         }
         __syncwarp();
     }
