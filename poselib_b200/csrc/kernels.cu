@@ -945,8 +945,12 @@ PLB_DEV float warp_sum_f(float v) {
     return v;
 }
 
-template <int KIND, bool PACKED>
-__global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const RoundDesc R, HypOut out, int use_smem) {
+// NTHR: threads per CTA.  512 (one CTA per SM next to a 160 KB staging buffer) for the large problems the kernel was
+// shaped for; 128 (four CTAs per SM) for small ones (BASELINE config 1: 200 correspondences), where a 512-thread CTA
+// leaves most threads without a correspondence and the per-tile setup / reduction is what costs.
+template <int KIND, bool PACKED, int NTHR>
+__global__ void __launch_bounds__(NTHR, NTHR >= 512 ? 1 : 4) k_screen(const RoundDesc R, HypOut out, int use_smem) {
+    constexpr int SCR_THREADS = NTHR, SCR_WARPS = NTHR / 32; // shadow the file-scope defaults
     constexpr int MSZ = kind_model_size(KIND);
     constexpr int CTX = (KIND == KIND_PNP) ? 12 : kind_is_relpose(KIND) ? 16 : 9;
     constexpr int NARR = (KIND == KIND_PNP) ? 5 : 4;
@@ -1509,22 +1513,25 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
             const char *e = std::getenv("PLB_SCREEN_PACKED");
             return e ? std::atoi(e) != 0 : true;
         }();
-        auto kern = packed ? k_screen<KIND, true> : k_screen<KIND, false>;
+        const bool small = max_n_pad <= 2048; // few correspondences per problem: 128-thread CTAs, four per SM
+        auto kern = small ? (packed ? k_screen<KIND, true, 128> : k_screen<KIND, false, 128>)
+                          : (packed ? k_screen<KIND, true, 512> : k_screen<KIND, false, 512>);
+        const int nthr = small ? 128 : 512;
         if (!attr_done) {
-            cudaFuncSetAttribute(k_screen<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(k_screen<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_screen<KIND, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_screen<KIND, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_done = true;
         }
         // one wave: resident CTAs per SM (occupancy API for this shared-memory size) x SMs; the kernel partitions the
         // (problem, tile) list over the CTAs by cost itself
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SCR_THREADS, use_smem ? bytes : 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthr, use_smem ? bytes : 0);
         if (per_sm < 1) per_sm = 1;
         long long tiles = ((long long)out.max_seg_cap + SCR_TM - 1) / SCR_TM * (long long)R.n_active;
         int gx = per_sm * sm_count();
         if ((long long)gx > tiles) gx = (int)tiles;
         if (gx < 1) gx = 1;
-        kern<<<gx, SCR_THREADS, use_smem ? bytes : 0, stream>>>(R, out, use_smem);
+        kern<<<gx, nthr, use_smem ? bytes : 0, stream>>>(R, out, use_smem);
     }
 }
 void launch_hypotheses(int kind, const RoundDesc &R, int *work, const HypOut &out, int mode, int max_n_pad,
