@@ -532,6 +532,61 @@ __global__ void __launch_bounds__(HYP_WARPS * 32, 3) k_solve(const RoundDesc R, 
     }
 }
 
+// p3p and homography_4pt are closed forms without any use for a warp (solvers.cuh: in k_solve all 32 lanes evaluate the
+// same scalar program): here every THREAD solves its own minimal sample — 32 samples per warp instead of one.  Same
+// scalar code, hence the same model bits; the lanes of a warp diverge where their samples take different branches
+// (number of real roots, Newton iterations), which still leaves an order of magnitude over the warp-per-sample kernel
+// (BASELINE config 1: solve kernels 6.1 -> see profiles/r02_summary.md).
+template <int KIND>
+__global__ void __launch_bounds__(128) k_solve_lane(const RoundDesc R, HypOut out) {
+    static_assert(KIND == KIND_PNP || KIND == KIND_HOMOG, "closed-form solvers only");
+    constexpr int MSZ = kind_model_size(KIND), MAXM = kind_max_models(KIND);
+    const int g_raw = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const bool live = g_raw < R.n_total;
+    const int g = live ? g_raw : R.n_total - 1; // idle lanes redo the last sample, nothing is stored
+    const int aslot = sample_problem_slot(R, g);
+    const int pidx = __ldg(R.active + aslot);
+    const ProblemDev &P = R.probs[pidx];
+    double models[MAXM * MSZ];
+    int nm;
+    if (KIND == KIND_PNP) {
+        d3 xs[3], Xs[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const uint32_t id = R.samples[(size_t)g * 3 + i];
+            xs[i] = bearing(P.p[0][id], P.p[1][id]);
+            Xs[i] = mk(P.p[2][id], P.p[3][id], P.p[4][id]);
+        }
+        nm = solve_p3p(xs, Xs, models, 0, false);
+    } else {
+        d3 a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t id = R.samples[(size_t)g * 4 + i];
+            a[i] = bearing(P.p[0][id], P.p[1][id]);
+            b[i] = bearing(P.p[2][id], P.p[3][id]);
+        }
+        nm = solve_h4(a, b, models, 0, true, false);
+    }
+    if (!live) return;
+    int base = 0;
+    if (nm) {
+        const int loc = atomicAdd(out.prob_count + aslot, nm);
+        if (loc + nm > __ldg(out.seg_cap + aslot)) { // cannot happen with the worst-case capacity these kinds use
+            atomicExch(out.overflow, 1);
+            nm = 0;
+        }
+        base = __ldg(out.seg_base + aslot) + loc;
+    }
+    out.n_models[g] = nm;
+    out.first_slot[g] = base;
+    for (int m = 0; m < nm; ++m) {
+#pragma unroll
+        for (int k = 0; k < MSZ; ++k) out.models[(size_t)(base + m) * MSZ + k] = models[m * MSZ + k];
+        out.model_prob[base + m] = pidx;
+    }
+}
+
 // ---- relpose_5pt as three phase kernels -------------------------------------------------------------------------
 // The fused warp-per-sample 5-point solver is 181 KB of SASS and runs its Sturm root isolation on one lane; 16 warps
 // per SM at different places of that code starve on instruction fetch (profiles/r01_v2_batch64_summary.md).  The
@@ -1487,6 +1542,21 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
         k5_roots<<<(R.n_total + ROOTS_THREADS - 1) / ROOTS_THREADS, ROOTS_THREADS, 0, stream>>>(R.n_total, out);
         const int warps = (R.n_total + 31) / 32;
         k5_back<<<(warps * 32 + 127) / 128, 128, 0, stream>>>(R, out);
+    } else if constexpr (KIND == KIND_PNP || KIND == KIND_HOMOG) {
+        // closed-form solvers: one thread per minimal sample (PLB_SOLVE_LANE=0: the warp-per-sample kernel)
+        static const bool lane_solve = [] {
+            const char *e = std::getenv("PLB_SOLVE_LANE");
+            return e ? std::atoi(e) != 0 : true;
+        }();
+        if (lane_solve) {
+            k_solve_lane<KIND><<<(R.n_total + 127) / 128, 128, 0, stream>>>(R, out);
+        } else {
+            int blocks = solve_blocks_per_sm<KIND>() * sm_count();
+            const int need = (R.n_total + HYP_WARPS - 1) / HYP_WARPS;
+            if (blocks > need) blocks = need;
+            if (blocks < 1) blocks = 1;
+            k_solve<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(R, work, out);
+        }
     } else if constexpr (KIND != KIND_RELPOSE_TS) {
         int blocks = solve_blocks_per_sm<KIND>() * sm_count();
         const int need = (R.n_total + HYP_WARPS - 1) / HYP_WARPS;

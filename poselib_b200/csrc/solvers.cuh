@@ -120,7 +120,9 @@ PLB_DEV void p3p_refine_lambda(double &l1, double &l2, double &l3, double a12, d
 
 // Solves one P3P instance.  xs: 3 unit bearings, Xs: 3 world points.  Writes up to 4 poses (7 doubles each) to
 // `out` (lane 0 writes) and returns the count (uniform across the warp).   p3p.cc:39-202
-PLB_DEV int solve_p3p(const d3 *xs, const d3 *Xs, double *out, int lane) {
+// warp_uniform: all 32 lanes run the SAME instance (lane 0 publishes, warp barrier at the end); false: every lane runs
+// its own instance (call with lane = 0 and a per-lane `out`) — no barrier then, lanes leave at different times.
+PLB_DEV int solve_p3p(const d3 *xs, const d3 *Xs, double *out, int lane, bool warp_uniform = true) {
     d3 x0 = xs[0], x1 = xs[1], x2 = xs[2];
     d3 P0 = Xs[0], P1 = Xs[1], P2 = Xs[2];
     d3 X01 = P0 - P1, X02 = P0 - P2, X12 = P1 - P2;
@@ -242,13 +244,13 @@ PLB_DEV int solve_p3p(const d3 *xs, const d3 *Xs, double *out, int lane) {
         }
         if (n_sols > 0 && G) break;
     }
-    __syncwarp();
+    if (warp_uniform) __syncwarp();
     return n_sols;
 }
 
 // ================================ homography_4pt (SKS / ACA closed form) ===================================
 // homography_4pt.cc:36-128.  Writes H (9 doubles COLUMN-major) to out; returns 0/1.
-PLB_DEV int solve_h4(const d3 *x1, const d3 *x2, double *out, int lane, bool check_cheirality) {
+PLB_DEV int solve_h4(const d3 *x1, const d3 *x2, double *out, int lane, bool check_cheirality, bool warp_uniform = true) {
     if (check_cheirality) {
         d3 p = cross(x1[0], x1[1]), q = cross(x2[0], x2[1]);
         if (dot(p, x1[2]) * dot(q, x2[2]) < 0) return 0;
@@ -309,7 +311,7 @@ PLB_DEV int solve_h4(const d3 *x1, const d3 *x2, double *out, int lane, bool che
 #pragma unroll
         for (int k = 0; k < 9; ++k) out[k] = H(k % 3, k / 3);
     }
-    __syncwarp();
+    if (warp_uniform) __syncwarp();
     return 1;
 }
 
