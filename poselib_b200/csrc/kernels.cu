@@ -587,6 +587,109 @@ __global__ void __launch_bounds__(128) k_solve_lane(const RoundDesc R, HypOut ou
     }
 }
 
+// relpose_7pt with FOUR minimal samples per warp (8 lanes each), like k5_prep: the pivoted-QR nullspace of the 9 x 7
+// system is the group-of-8 routine of the 5-point solver (one lane per column), the cubic in the pencil of the two
+// nullspace vectors and its roots are scalar (every lane of the group evaluates them, lanes 0..2 build one F each), the
+// real-focal check keeps the surviving models in order (estimators/relative_pose.cc:393-398).  Same arithmetic as the
+// warp-per-sample solve_7pt (solvers.cuh), a quarter of the warps.
+constexpr int P7_M = 0, P7_N = 63, P7_XS = 81, P7_OUT = 123, P7_STRIDE = 152; // 152 = 8 (mod 16): see P5_STRIDE
+constexpr size_t K7_SMEM = sizeof(double) * P7_STRIDE * 4 * HYP_WARPS;
+__global__ void __launch_bounds__(HYP_WARPS * 32) k7_solve(const RoundDesc R, int *work_counter, HypOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, sl = lane & 7, grp = lane >> 3;
+    double *W = reinterpret_cast<double *>(smem_raw) + (size_t)((threadIdx.x >> 5) * 4 + grp) * P7_STRIDE;
+    const unsigned gmask = 0xffu << (8 * grp);
+    for (;;) {
+        int g0 = 0;
+        if (lane == 0) g0 = atomicAdd(work_counter, 4);
+        g0 = __shfl_sync(0xffffffffu, g0, 0);
+        if (g0 >= R.n_total) break;
+        int g = g0 + grp;
+        const bool live = g < R.n_total;
+        if (!live) g = R.n_total - 1; // idle groups redo the last sample (uniform control flow), nothing is stored
+        const int aslot = sample_problem_slot(R, g);
+        const int pidx = __ldg(R.active + aslot);
+        const ProblemDev &P = R.probs[pidx];
+        double *x1s = W + P7_XS, *x2s = W + P7_XS + 21;
+        for (int idx = sl; idx < 14; idx += 8) {
+            const int i = idx % 7, side = idx / 7;
+            const uint32_t id = R.samples[(size_t)g * 7 + i];
+            const d3 v = bearing(P.p[2 * side][id], P.p[2 * side + 1][id]);
+            double *o = W + P7_XS + 21 * side + 3 * i;
+            o[0] = v.x; o[1] = v.y; o[2] = v.z;
+        }
+        __syncwarp();
+        for (int e = sl; e < 63; e += 8) {
+            const int i = e / 9, k = e % 9;
+            W[P7_M + e] = x1s[3 * i + k / 3] * x2s[3 * i + k % 3];
+        }
+        __syncwarp();
+        grp8_nullspace_9xC<7>(W + P7_M, W + P7_N, sl);
+        const double *n0 = W + P7_N, *n1 = W + P7_N + 9;
+        // mixed determinants: column j of the 3x3 (col-major 9-vector) taken from a, b, c respectively
+        auto detc = [](const double *a, const double *b, const double *c) -> double {
+            const double *c0 = a, *c1 = b + 3, *c2 = c + 6;
+            return c0[0] * (c1[1] * c2[2] - c1[2] * c2[1]) - c1[0] * (c0[1] * c2[2] - c0[2] * c2[1]) +
+                   c2[0] * (c0[1] * c1[2] - c0[2] * c1[1]);
+        };
+        const double c3 = detc(n0, n0, n0);
+        const double c2 = detc(n1, n0, n0) + detc(n0, n1, n0) + detc(n0, n0, n1);
+        const double c1 = detc(n0, n1, n1) + detc(n1, n0, n1) + detc(n1, n1, n0);
+        const double c0 = detc(n1, n1, n1);
+        double roots[3];
+        int n_roots;
+        if (fabs(c3) < 1e-14) {
+            n_roots = quadratic_real(c2, c1, c0, roots);
+        } else {
+            const double inv_c3 = 1.0 / c3;
+            n_roots = cubic_real(c2 * inv_c3, c1 * inv_c3, c0 * inv_c3, roots);
+        }
+        bool keep = false;
+        double f[9];
+        if (sl < n_roots) {
+            double r = roots[0];
+            if (sl == 1) r = roots[1];
+            if (sl == 2) r = roots[2];
+            double n2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                f[k] = n0[k] * r + n1[k];
+                n2 += f[k] * f[k];
+            }
+            if (n2 > 0) {
+                const double nn = sqrt(n2);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) f[k] /= nn;
+            }
+            keep = P.rfc ? rfc_ok(f) : true;
+        }
+        const unsigned km = __ballot_sync(0xffffffffu, keep) & gmask;
+        const int nm_all = __popc(km);
+        int nm = nm_all, base = 0;
+        if (sl == 0 && live) {
+            if (nm) {
+                const int loc = atomicAdd(out.prob_count + aslot, nm);
+                if (loc + nm > __ldg(out.seg_cap + aslot)) { // cannot happen: this kind uses the worst-case capacity
+                    atomicExch(out.overflow, 1);
+                    nm = 0;
+                }
+                base = __ldg(out.seg_base + aslot) + loc;
+            }
+            out.n_models[g] = nm;
+            out.first_slot[g] = base;
+        }
+        base = __shfl_sync(0xffffffffu, base, 8 * grp);
+        nm = __shfl_sync(0xffffffffu, nm, 8 * grp);
+        if (keep && live && nm) {
+            const int pos = base + __popc(km & ((1u << lane) - 1u));
+#pragma unroll
+            for (int k = 0; k < 9; ++k) out.models[(size_t)pos * 9 + k] = f[k];
+            out.model_prob[pos] = pidx;
+        }
+        __syncwarp();
+    }
+}
+
 // ---- relpose_5pt as three phase kernels -------------------------------------------------------------------------
 // The fused warp-per-sample 5-point solver is 181 KB of SASS and runs its Sturm root isolation on one lane; 16 warps
 // per SM at different places of that code starve on instruction fetch (profiles/r01_v2_batch64_summary.md).  The
@@ -1550,6 +1653,31 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
         }();
         if (lane_solve) {
             k_solve_lane<KIND><<<(R.n_total + 127) / 128, 128, 0, stream>>>(R, out);
+        } else {
+            int blocks = solve_blocks_per_sm<KIND>() * sm_count();
+            const int need = (R.n_total + HYP_WARPS - 1) / HYP_WARPS;
+            if (blocks > need) blocks = need;
+            if (blocks < 1) blocks = 1;
+            k_solve<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(R, work, out);
+        }
+    } else if constexpr (KIND == KIND_FUND) {
+        // relpose_7pt: four samples per warp (PLB_SOLVE7_GRP=0: the warp-per-sample kernel)
+        static const bool grp7 = [] {
+            const char *e = std::getenv("PLB_SOLVE7_GRP");
+            return e ? std::atoi(e) != 0 : true;
+        }();
+        if (grp7) {
+            static int per_sm_dev[MAX_DEVICES] = {0};
+            int &per_sm = per_sm_dev[cur_dev()];
+            if (per_sm <= 0) {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k7_solve, HYP_WARPS * 32, K7_SMEM);
+                if (per_sm < 1) per_sm = 1;
+            }
+            int blocks = per_sm * sm_count();
+            const int need = (R.n_total + 4 * HYP_WARPS - 1) / (4 * HYP_WARPS);
+            if (blocks > need) blocks = need;
+            if (blocks < 1) blocks = 1;
+            k7_solve<<<blocks, HYP_WARPS * 32, K7_SMEM, stream>>>(R, work, out);
         } else {
             int blocks = solve_blocks_per_sm<KIND>() * sm_count();
             const int need = (R.n_total + HYP_WARPS - 1) / HYP_WARPS;
