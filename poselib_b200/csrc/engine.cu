@@ -302,6 +302,7 @@ static bool host_pinned(const void *p) {
 // ranks sharing a host) wait for their round by sleeping on a blocking event; spinning threads would take the cores from
 // the threads that have a round to replay.  Single calls and small batches spin (lowest latency).
 static thread_local bool t_blocking_sync = false;
+static thread_local bool t_batch_worker = false; // this thread runs one of several lock-step groups of a batch call
 
 // One engine (stream, events, grow-only buffers) per host thread AND device: a thread that switches devices with
 // plb_set_device gets a separate engine for each, so streams and buffers never cross devices.  Engines live as long as
@@ -623,6 +624,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
     }
     int rc = E.init();
     if (rc != PLB_OK) return rc;
+    lm_set_sm_share(t_batch_worker ? 50 : 100); // a lone call owns the GPU; batch groups share it
     cudaStream_t st = E.stream;
     const uint64_t launches0 = E.launches;
     uint64_t h2d = 0, d2h = 0;
@@ -1484,6 +1486,7 @@ static int run_refine(int kind, const double *a, const double *b, size_t n_pts, 
     PLB_CUDA(cudaMemcpyAsync(E.jobs.p, E.h_jobs.p, sizeof(LmJob), cudaMemcpyHostToDevice, st));
     PLB_CUDA(cudaMemcpyAsync(E.lm_in.p, E.h_lm_in.p, sizeof(double) * 9, cudaMemcpyHostToDevice, st));
     launch_transpose(E.tdesc.p, 1, n_pad, st);
+    lm_set_sm_share(100);
     launch_lm(kind, E.probs.p, E.jobs.p, E.lm_in.p, 1, n, nullptr, nullptr, 0, E.h_lm_out.d, st);
     E.launches += 2;
     PLB_CUDA(cudaStreamSynchronize(st));
@@ -2065,10 +2068,11 @@ static int run_tasks(std::vector<Task> &tasks, std::vector<int> &dev_of, const i
     const bool oversubscribed = (int)jobs.size() > usable_cpus();
     auto work = [&](int w) {
         const int saved_dev = g_device, saved_mode = g_mode;
-        const bool saved_block = t_blocking_sync;
+        const bool saved_block = t_blocking_sync, saved_worker = t_batch_worker;
         g_device = jobs[w].device;
         g_mode = mode;
         t_blocking_sync = oversubscribed;
+        t_batch_worker = jobs.size() > 1;
         for (auto &grp : jobs[w].groups) {
             const int rc = run_group(grp[0]->kind, grp);
             if (rc != PLB_OK) {
@@ -2082,6 +2086,7 @@ static int run_tasks(std::vector<Task> &tasks, std::vector<int> &dev_of, const i
         g_device = saved_dev;
         g_mode = saved_mode;
         t_blocking_sync = saved_block;
+        t_batch_worker = saved_worker;
     };
     if (jobs.size() == 1) work(0); // the caller's own thread and engine
     else worker_pool().run((int)jobs.size(), work);

@@ -2670,6 +2670,8 @@ static int lm_minb() {
     }();
     return minb;
 }
+static thread_local int t_lm_sm_share = 50;
+void lm_set_sm_share(int pct) { t_lm_sm_share = (pct > 0 && pct <= 100) ? pct : 50; }
 static int lm_cluster_size(int n_jobs, int max_n) {
     static const int per_cta = [] { // correspondences per CTA before another CTA of the cluster pays off
         const char *e = std::getenv("PLB_LM_PER_CTA");
@@ -2683,7 +2685,16 @@ static int lm_cluster_size(int n_jobs, int max_n) {
     if (csize == 3) csize = 2;
     // k_lm needs the whole register file of an SM per CTA: with many jobs in one launch (batch groups) wide clusters
     // only take SMs away from the co-running hypothesis kernels, so the cluster shrinks as the job count grows
-    while (csize > 1 && n_jobs * csize > sm_count() / 2) csize /= 2;
+    // SMs (percent of the device) the LO clusters of one launch may cover: half when other lock-step groups share the GPU
+    // (their hypothesis kernels want the other half: +5 % on the batch workload), all of it for a call that runs alone
+    // (C4 single call 2.7 -> 2.2 ms).  PLB_LM_SM_PCT overrides.
+    static const int forced = [] {
+        const char *e = std::getenv("PLB_LM_SM_PCT");
+        const int v = e ? std::atoi(e) : 0;
+        return (v > 0 && v <= 100) ? v : 0;
+    }();
+    const int sm_share = forced ? forced : t_lm_sm_share;
+    while (csize > 1 && n_jobs * csize > sm_count() * sm_share / 100) csize /= 2;
     return csize;
 }
 template <int KIND>

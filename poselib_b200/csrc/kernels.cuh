@@ -231,6 +231,8 @@ void launch_lm_round(int kind, const ProblemDev *probs, const LmJob *tmpl, const
                      const double *models, const int *n_jobs_dev, int job_cap, int est_jobs, int max_n,
                      int *idx_scratch, int scratch_stride, LmJobOut *out, cudaStream_t stream);
 int lm_round_max_clusters(int kind, int est_jobs, int max_n);
+// Share of the SMs (percent) the LO clusters launched from this host thread may cover (50: batch groups, 100: a lone call).
+void lm_set_sm_share(int pct);
 // Device-side sampling of a round: one warp per active problem draws its B samples into samples[(g0+s)*K ..] from
 // st_in[pidx] and leaves the advanced state in st_out[pidx] (robust/sampling.cc:46-61,85-103).
 void launch_sample(const RoundProb *rp, int na, const SamplerDev *st_in, SamplerDev *st_out, uint32_t *samples,
