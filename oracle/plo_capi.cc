@@ -7,6 +7,9 @@
 #include <thread>
 #include <atomic>
 
+namespace plo {
+extern thread_local double *g_relpose_5pt_stage_out; // plo_solvers.cc (test hook)
+}
 using namespace plo;
 
 extern "C" {
@@ -145,6 +148,14 @@ int plo_relpose_5pt_E(const double *x1, const double *x2, double *E_out) {
     std::vector<Mat3> out;
     int n = relpose_5pt(v3(x1, 5), v3(x2, 5), &out);
     for (int i = 0; i < n; ++i) mat_out(out[i], E_out + 9 * i);
+    return n;
+}
+// intermediates of relpose_5pt (test hook, see plo_solvers.cc): out86 = Nb (36) | A (39) | determinant polynomial (11)
+int plo_relpose_5pt_stages(const double *x1, const double *x2, double *out86) {
+    std::vector<Mat3> out;
+    g_relpose_5pt_stage_out = out86;
+    int n = relpose_5pt(v3(x1, 5), v3(x2, 5), &out);
+    g_relpose_5pt_stage_out = nullptr;
     return n;
 }
 int plo_relpose_5pt(const double *x1, const double *x2, double *poses_out) {

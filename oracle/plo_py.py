@@ -150,6 +150,16 @@ def relpose_5pt_E(x1, x2):
     return out[:n].reshape(n, 3, 3).transpose(0, 2, 1)  # column-major -> E[r,c]
 
 
+def relpose_5pt_stages(x1, x2):
+    """(Nb[36], A[39], cpoly[11]) of the oracle's relpose_5pt: the nullspace basis, the 3 x 13 polynomial matrix and the
+    determinant polynomial (ascending)."""
+    a, ap = _d(x1)
+    b, bp = _d(x2)
+    out = np.zeros(86)
+    lib().plo_relpose_5pt_stages(ap, bp, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out[:36], out[36:75], out[75:]
+
+
 def relpose_5pt(x1, x2):
     a, ap = _d(x1)
     b, bp = _d(x2)

@@ -628,6 +628,11 @@ inline void pmul(const double *a, int da, const double *b, int db, double *c) {
 }
 } // namespace
 
+// Test hook: when set, relpose_5pt copies its intermediate results there — Nb (36: Nb[4k + r]) | A (39, row-major
+// 3 x 13) | determinant polynomial (11, ascending).  tests/test_solver5_lane_host.py pins the device solver's
+// thread-per-sample first half (poselib_b200/csrc/solver5_lane.cuh, host build) to these bit for bit.
+thread_local double *g_relpose_5pt_stage_out = nullptr;
+
 // relpose_5pt.cc:159-395
 int relpose_5pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::vector<Mat3> *essential_matrices) {
     // 9x5 epipolar constraint matrix, column-major (:163-166)
@@ -711,6 +716,14 @@ int relpose_5pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::v
         for (int k = 0; k <= 6; ++k) minor2[k] = m3[k] - m4[k];
         pmul(p[0][2], 4, minor2, 6, term);
         for (int k = 0; k <= 10; ++k) c[k] += term[k];
+    }
+    if (g_relpose_5pt_stage_out) {
+        double *o = g_relpose_5pt_stage_out;
+        for (int k = 0; k < 9; ++k)
+            for (int r = 0; r < 4; ++r) o[4 * k + r] = Nb[k][r];
+        for (int i = 0; i < 3; ++i)
+            for (int k = 0; k < 13; ++k) o[36 + 13 * i + k] = A[i][k];
+        for (int k = 0; k <= 10; ++k) o[75 + k] = c[k];
     }
     double roots[10];
     const int n_sols = bisect_sturm10(c, roots); // :356

@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 #include "solvers.cuh"
 #include "screen_math.cuh"
+#include "solver5_lane.cuh"
 #include <cooperative_groups.h>
 #include <type_traits>
 #include <cstdlib>
@@ -735,13 +736,99 @@ __global__ void __launch_bounds__(HYP_WARPS * 32) k5_prep(const RoundDesc R, int
         __syncwarp();
         solve_5pt_poly_grp8(W, T, sl);
         if (live) {
-            double *blk = out.s5_blk + (size_t)g * S5_BLK;
-            for (int e = sl; e < 39; e += 8) blk[e] = W[P5_A + e];
-            for (int e = sl; e < 36; e += 8) blk[39 + e] = W[P5_NB + e];
-            for (int e = sl; e < 30; e += 8) blk[75 + e] = W[P5_XS + e];
+            double *blk = out.s5_blk + g; // entry-major: blk[e * n_total]
+            const size_t nt = (size_t)R.n_total;
+            for (int e = sl; e < 39; e += 8) blk[e * nt] = W[P5_A + e];
+            for (int e = sl; e < 36; e += 8) blk[(39 + e) * nt] = W[P5_NB + e];
+            for (int e = sl; e < 30; e += 8) blk[(75 + e) * nt] = W[P5_XS + e];
             for (int k = sl; k < 11; k += 8) out.s5_cpoly[(size_t)k * R.n_total + g] = W[P5_CPOLY + k];
         }
         __syncwarp();
+    }
+}
+
+// Bearings of the 5 sampled correspondences of every sample (estimators/relative_pose.cc:51-54,90-94) into the
+// entry-major per-sample block (entries 75..104).  Its chain of dependent global loads (problem slot -> problem ->
+// sample ids -> points) is a kernel of its own, at full occupancy: inside k5_prep_lane (4 warps per SM) it was 19 % of
+// that kernel's time.
+__global__ void __launch_bounds__(256) k5_gather(const RoundDesc R, HypOut out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= R.n_total) return;
+    const ProblemDev &P = R.probs[__ldg(R.active + sample_problem_slot(R, g))];
+    const size_t nt = (size_t)R.n_total;
+    double *blk = out.s5_blk + g;
+    uint32_t id[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) id[i] = R.samples[(size_t)g * 5 + i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            d3 v;
+            if (P.kind == KIND_RELPOSE_TS) {
+                const double *t = P.ts + (size_t)(3 * side) * P.n_pad + id[i];
+                v = mk(t[0], t[P.n_pad], t[2 * (size_t)P.n_pad]);
+            } else {
+                v = bearing(P.p[2 * side][id[i]], P.p[2 * side + 1][id[i]]);
+            }
+            blk[(75 + 15 * side + 3 * i) * nt] = v.x;
+            blk[(75 + 15 * side + 3 * i + 1) * nt] = v.y;
+            blk[(75 + 15 * side + 3 * i + 2) * nt] = v.z;
+        }
+    }
+}
+
+// The same phase with ONE THREAD PER SAMPLE (solver5_lane.cuh): the nullspace basis and the quadratic blocks live in
+// registers (compile-time monomial tables), only the 10 x 20 elimination matrix sits in the thread's slice of shared
+// memory.  128 threads x 201 doubles = 201 KB: one CTA per SM; the odd stride spreads the 32 lanes of a warp over all
+// bank pairs, so a 64-bit access of the warp at one static offset costs the minimum of two wavefronts.
+constexpr int PREPL_THREADS = 128;
+constexpr int PREPL_STRIDE = 201;
+constexpr size_t PREPL_SMEM = sizeof(double) * PREPL_STRIDE * PREPL_THREADS;
+__global__ void __launch_bounds__(PREPL_THREADS, 1) k5_prep_lane(const RoundDesc R, HypOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *W = reinterpret_cast<double *>(smem_raw) + (size_t)threadIdx.x * PREPL_STRIDE;
+    int g = blockIdx.x * PREPL_THREADS + threadIdx.x;
+    const bool live = g < R.n_total;
+    if (!live) g = R.n_total - 1; // idle threads of the last CTA redo the last sample, nothing is stored
+    const size_t nt = (size_t)R.n_total;
+    double *blk = out.s5_blk + g; // entry-major: blk[e * n_total]
+    {
+        double xs[30]; // the sample's bearings, written by k5_gather: 30 independent coalesced loads
+#pragma unroll
+        for (int e = 0; e < 30; ++e) xs[e] = blk[(75 + e) * nt];
+        // 9 x 5 epipolar constraints (relpose_5pt.cc:163-166): entry 3a+b of column i = x1[i][a] * x2[i][b]
+#pragma unroll
+        for (int e = 0; e < 45; ++e) {
+            const int i = e / 9, k = e % 9;
+            W[e] = xs[3 * i + k / 3] * xs[15 + 3 * i + k % 3];
+        }
+    }
+    lane5::nullspace_9x5(W, W + 45);
+    {
+        double Nb[36];
+#pragma unroll
+        for (int e = 0; e < 36; ++e) {
+            const int r = e / 9, k = e % 9;
+            Nb[4 * k + r] = W[45 + 9 * r + k];
+        }
+        if (live) {
+#pragma unroll
+            for (int e = 0; e < 36; ++e) blk[(39 + e) * nt] = Nb[e];
+        }
+        lane5::build_coeffs(Nb, W);
+    }
+    lane5::eliminate(W);
+    double A[39], cp[11];
+    lane5::poly_matrix(W, A);
+    if (live) {
+#pragma unroll
+        for (int e = 0; e < 39; ++e) blk[e * nt] = A[e];
+    }
+    lane5::det_poly(A, cp);
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < 11; ++k) out.s5_cpoly[(size_t)k * nt + g] = cp[k];
     }
 }
 
@@ -816,7 +903,7 @@ __global__ void __launch_bounds__(128) k5_back(const RoundDesc R, HypOut out) {
         double cand[4][7];
         unsigned mask = 0;
         if (valid) {
-            const double *blk = out.s5_blk + (size_t)g * S5_BLK;
+            const StridedD blk{out.s5_blk + g, (size_t)R.n_total}; // entry-major (k5_prep_lane)
             double E[9];
             backsub_5pt(blk, blk + 39, out.s5_roots[(size_t)g * 10 + r], E);
             mask = motions_from_E(E, blk + 75, blk + 90, 5, cand);
@@ -1636,12 +1723,27 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
     // than there is work for
     if constexpr (KIND == KIND_RELPOSE_TS) mode = 0; // no fp32 screening copy of the 18-array layout: exact scoring
     if (kind_is_relpose(KIND) && (KIND == KIND_RELPOSE_TS || out.s5_blk != nullptr)) {
-        int blocks = prep_blocks_per_sm() * sm_count();
-        const int per_cta = HYP_WARPS * PREP_SAMPLES_PER_WARP;
-        const int need = (R.n_total + per_cta - 1) / per_cta;
-        if (blocks > need) blocks = need;
-        if (blocks < 1) blocks = 1;
-        k5_prep<<<blocks, HYP_WARPS * 32, PREP_SMEM, stream>>>(R, work, out);
+        // first half: one thread per sample (PLB_PREP_LANE=0: four samples per warp, k5_prep)
+        static const bool lane_prep = [] {
+            const char *e = std::getenv("PLB_PREP_LANE");
+            return e ? std::atoi(e) != 0 : true;
+        }();
+        if (lane_prep) {
+            static bool attr_set[MAX_DEVICES] = {false};
+            if (!attr_set[cur_dev()]) {
+                cudaFuncSetAttribute(k5_prep_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREPL_SMEM);
+                attr_set[cur_dev()] = true;
+            }
+            k5_gather<<<(R.n_total + 255) / 256, 256, 0, stream>>>(R, out);
+            k5_prep_lane<<<(R.n_total + PREPL_THREADS - 1) / PREPL_THREADS, PREPL_THREADS, PREPL_SMEM, stream>>>(R, out);
+        } else {
+            int blocks = prep_blocks_per_sm() * sm_count();
+            const int per_cta = HYP_WARPS * PREP_SAMPLES_PER_WARP;
+            const int need = (R.n_total + per_cta - 1) / per_cta;
+            if (blocks > need) blocks = need;
+            if (blocks < 1) blocks = 1;
+            k5_prep<<<blocks, HYP_WARPS * 32, PREP_SMEM, stream>>>(R, work, out);
+        }
         k5_roots<<<(R.n_total + ROOTS_THREADS - 1) / ROOTS_THREADS, ROOTS_THREADS, 0, stream>>>(R.n_total, out);
         const int warps = (R.n_total + 31) / 32;
         k5_back<<<(warps * 32 + 127) / 128, 128, 0, stream>>>(R, out);

@@ -66,7 +66,7 @@ struct HypOut {
     uint32_t *fborder; // fast mode: correspondences whose fp32 inlier decision is within the error bound of the test
     float *ferr;       // fast mode: bound of |score32 - score64|
     // relpose_5pt phase buffers (device), sized for the round's n_total samples:
-    double *s5_blk;   // per sample 105 doubles: A (39) | Nb (36) | sample bearings x1s,x2s (30)
+    double *s5_blk;   // 105 x n_total, entry-major (blk[e * n_total + g]): A (39) | Nb (36) | sample bearings x1s,x2s (30)
     double *s5_cpoly; // 11 x n_total, coefficient-major (cpoly[c * n_total + g])
     double *s5_roots; // per sample 10 doubles
     int *s5_nroots;   // per sample

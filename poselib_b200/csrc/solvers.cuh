@@ -1412,7 +1412,14 @@ PLB_DEV void solve_5pt_poly_grp8(double *W, const MonoTables *T, int sl) {
 
 // Back-substitution for one root z of the determinant polynomial: E (row-major 9) from the polynomial matrix A (3x13)
 // and the nullspace basis Nb (relpose_5pt.cc:359-392).
-PLB_DEV void backsub_5pt(const double *A, const double *Nb, double z, double *E) {
+// A / Nb: anything indexable (plain pointers, or StridedD views of the entry-major per-sample blocks).
+struct StridedD {
+    const double *p;
+    size_t stride;
+    PLB_DEV double operator[](int i) const { return p[(size_t)i * stride]; }
+    PLB_DEV StridedD operator+(int o) const { return StridedD{p + (size_t)o * stride, stride}; }
+};
+template <class VA, class VN> PLB_DEV void backsub_5pt(VA A, VN Nb, double z, double *E) {
     {
         const double z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
         double B[3][2], bb[3];
@@ -1507,7 +1514,7 @@ PLB_DEV int solve_5pt_E(const double *x1s, const double *x2s, Scratch5 *S, const
 // Four motion hypotheses of an essential matrix, filtered by cheirality on the sample (misc/essential.cc:103-169).
 // E: row-major; x1s/x2s: ns unit bearings each.  Returns a 4-bit mask of accepted candidates and writes all four
 // candidate poses to cand[4][7] (registers of the calling lane).
-PLB_DEV unsigned motions_from_E(const double *E9, const double *x1s, const double *x2s, int ns, double cand[4][7]) {
+template <class VX> PLB_DEV unsigned motions_from_E(const double *E9, VX x1s, VX x2s, int ns, double cand[4][7]) {
     m3 E;
 #pragma unroll
     for (int k = 0; k < 9; ++k) E.a[k] = E9[k];
