@@ -207,7 +207,7 @@ struct Engine {
     cudaEvent_t ev_block = nullptr; // cudaEventBlockingSync: the waiting thread sleeps instead of spinning
     bool ready = false;
     int device = -1;
-    DevBuf<double> in, soa64, px64, models, lm_in, s5_blk, s5_cpoly, s5_roots;
+    DevBuf<double> in, soa64, px64, models, lm_in, s5_blk, s5_park, s5_cpoly, s5_roots;
     DevBuf<int> s5_nroots;
     DevBuf<float> soa32, cmax;
     DevBuf<uint32_t> samples;
@@ -1093,13 +1093,14 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             out.fborder = E.fborder.p;
             out.ferr = E.ferr.p;
         }
-        out.s5_blk = out.s5_cpoly = out.s5_roots = nullptr;
+        out.s5_blk = out.s5_park = out.s5_cpoly = out.s5_roots = nullptr;
         out.s5_nroots = nullptr;
         if (kind_is_relpose(kind)) { // phase buffers of the 3-kernel 5-point solver
-            if ((rc = E.s5_blk.ensure(total * 105)) || (rc = E.s5_cpoly.ensure(total * 11)) ||
+            if ((rc = E.s5_blk.ensure(total * 105)) || (rc = E.s5_park.ensure(total * 100)) || (rc = E.s5_cpoly.ensure(total * 11)) ||
                 (rc = E.s5_roots.ensure(total * 10)) || (rc = E.s5_nroots.ensure(total)))
                 return rc;
             out.s5_blk = E.s5_blk.p;
+            out.s5_park = E.s5_park.p;
             out.s5_cpoly = E.s5_cpoly.p;
             out.s5_roots = E.s5_roots.p;
             out.s5_nroots = E.s5_nroots.p;

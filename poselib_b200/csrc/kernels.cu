@@ -779,20 +779,23 @@ __global__ void __launch_bounds__(256) k5_gather(const RoundDesc R, HypOut out) 
 }
 
 // The same phase with ONE THREAD PER SAMPLE (solver5_lane.cuh): the nullspace basis and the quadratic blocks live in
-// registers (compile-time monomial tables), only the 10 x 20 elimination matrix sits in the thread's slice of shared
-// memory.  128 threads x 201 doubles = 201 KB: one CTA per SM; the odd stride spreads the 32 lanes of a warp over all
-// bank pairs, so a 64-bit access of the warp at one static offset costs the minimum of two wavefronts.
-constexpr int PREPL_THREADS = 128;
-constexpr int PREPL_STRIDE = 201;
+// registers (compile-time monomial tables); shared memory holds only the LEFT 10 x 10 block of the elimination matrix
+// (dynamic pivot rows) plus 10 doubles of scratch per thread, the right-hand sides are parked in global memory (L2)
+// while the block is factored and come back column by column.  111 doubles per thread (odd: the 32 lanes of a warp
+// spread over all bank pairs) x 256 threads = 222 KB: one CTA, 8 warps per SM.
+constexpr int PREPL_THREADS = 256;
+constexpr int PREPL_STRIDE = 111;
 constexpr size_t PREPL_SMEM = sizeof(double) * PREPL_STRIDE * PREPL_THREADS;
 __global__ void __launch_bounds__(PREPL_THREADS, 1) k5_prep_lane(const RoundDesc R, HypOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *W = reinterpret_cast<double *>(smem_raw) + (size_t)threadIdx.x * PREPL_STRIDE;
+    double *CL = W, *S = W + 100;
     int g = blockIdx.x * PREPL_THREADS + threadIdx.x;
     const bool live = g < R.n_total;
-    if (!live) g = R.n_total - 1; // idle threads of the last CTA redo the last sample, nothing is stored
+    if (!live) g = R.n_total - 1; // idle threads of the last CTA redo the last sample (same values, harmless stores)
     const size_t nt = (size_t)R.n_total;
-    double *blk = out.s5_blk + g; // entry-major: blk[e * n_total]
+    double *blk = out.s5_blk + g;   // entry-major: blk[e * n_total]
+    double *park = out.s5_park + g; // right-hand sides, entry-major: park[(row * 10 + column) * n_total]
     {
         double xs[30]; // the sample's bearings, written by k5_gather: 30 independent coalesced loads
 #pragma unroll
@@ -812,24 +815,24 @@ __global__ void __launch_bounds__(PREPL_THREADS, 1) k5_prep_lane(const RoundDesc
             const int r = e / 9, k = e % 9;
             Nb[4 * k + r] = W[45 + 9 * r + k];
         }
-        if (live) {
 #pragma unroll
-            for (int e = 0; e < 36; ++e) blk[(39 + e) * nt] = Nb[e];
-        }
-        lane5::build_coeffs(Nb, W);
+        for (int e = 0; e < 36; ++e) blk[(39 + e) * nt] = Nb[e];
+        lane5::build_coeffs(Nb, [&](int row, auto cc, double v) {
+            constexpr int ci = decltype(cc)::value;
+            if constexpr (ci < 10) CL[row * 10 + ci] = v;
+            else park[(size_t)(row * 10 + (ci - 10)) * nt] = v;
+        });
     }
-    lane5::eliminate(W);
+    int idx[10];
+    lane5::lu_left(CL, S, idx);
+    lane5::solve_rhs(CL, S, idx, [&](int r, int c) { return park[(size_t)(r * 10 + c) * nt]; }, CL);
     double A[39], cp[11];
-    lane5::poly_matrix(W, A);
-    if (live) {
+    lane5::poly_matrix(CL, A);
 #pragma unroll
-        for (int e = 0; e < 39; ++e) blk[e * nt] = A[e];
-    }
+    for (int e = 0; e < 39; ++e) blk[e * nt] = A[e];
     lane5::det_poly(A, cp);
-    if (live) {
 #pragma unroll
-        for (int k = 0; k < 11; ++k) out.s5_cpoly[(size_t)k * nt + g] = cp[k];
-    }
+    for (int k = 0; k < 11; ++k) out.s5_cpoly[(size_t)k * nt + g] = cp[k];
 }
 
 constexpr int ROOTS_THREADS = 64;

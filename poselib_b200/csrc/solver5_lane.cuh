@@ -246,7 +246,7 @@ template <int BLK> PLB_L5 void quad_block(const double *Nb, double *qv) {
 }
 
 // Rows 3 i .. 3 i + 2 of the coefficient matrix from the three blocks (E E^T - trace / 2)(i, 0..2)  (:146-154)
-template <int I> PLB_L5 void cubic_rows(const double *Nb, const double *q0, const double *q1, const double *q2, double *C) {
+template <int I, class Sink> PLB_L5 void cubic_rows(const double *Nb, const double *q0, const double *q1, const double *q2, Sink &&put) {
     static_for<20>([&](auto cc) {
         constexpr int ci = decltype(cc)::value;
         constexpr int np = TB.cub_n[ci];
@@ -262,12 +262,12 @@ template <int I> PLB_L5 void cubic_rows(const double *Nb, const double *q0, cons
                 if (np > 1) v += Q[a1] * PLB_L5_E(k, j, l1);
                 if (np > 2) v += Q[a2] * PLB_L5_E(k, j, l2);
             }
-            C[(3 * I + j) * 20 + ci] = v;
+            put(3 * I + j, cc, v);
         }
     });
 }
 // Row 9: det(E) = sum_t d_t E(2, t)  (:113-125)
-PLB_L5 void cubic_det_row(const double *Nb, const double *d0, const double *d1, const double *d2, double *C) {
+template <class Sink> PLB_L5 void cubic_det_row(const double *Nb, const double *d0, const double *d1, const double *d2, Sink &&put) {
     static_for<20>([&](auto cc) {
         constexpr int ci = decltype(cc)::value;
         constexpr int np = TB.cub_n[ci];
@@ -281,19 +281,19 @@ PLB_L5 void cubic_det_row(const double *Nb, const double *d0, const double *d1, 
             if (np > 1) v += Q[a1] * PLB_L5_E(2, t, l1);
             if (np > 2) v += Q[a2] * PLB_L5_E(2, t, l2);
         }
-        C[9 * 20 + ci] = v;
+        put(9, cc, v);
     });
 }
 
-// Nb (36, registers) -> C (10 x 20, row-major, the thread's scratch).  The blocks are formed group by group so that at
-// most three of them (plus the trace term) are live at a time.
-PLB_L5 void build_coeffs(const double *Nb, double *C) {
+// Nb (36, registers) -> the 10 x 20 coefficient matrix, entry by entry through put(row, integral_constant<ci>, value).
+// The blocks are formed group by group so that at most three of them (plus the trace term) are live at a time.
+template <class Sink> PLB_L5 void build_coeffs(const double *Nb, Sink &&put) {
     {
         double d0[10], d1[10], d2[10];
         quad_block<6>(Nb, d0);
         quad_block<7>(Nb, d1);
         quad_block<8>(Nb, d2);
-        cubic_det_row(Nb, d0, d1, d2, C);
+        cubic_det_row(Nb, d0, d1, d2, put);
     }
     double tr[10]; // half the trace of E E^T (:139-144)
     {
@@ -311,7 +311,7 @@ PLB_L5 void build_coeffs(const double *Nb, double *C) {
         quad_block<2>(Nb, q2);
 #pragma unroll
         for (int m = 0; m < 10; ++m) q0[m] -= tr[m];
-        cubic_rows<0>(Nb, q0, q1, q2, C);
+        cubic_rows<0>(Nb, q0, q1, q2, put);
     }
     {
         double q0[10], q1[10], q2[10];
@@ -320,7 +320,7 @@ PLB_L5 void build_coeffs(const double *Nb, double *C) {
         quad_block<4>(Nb, q2);
 #pragma unroll
         for (int m = 0; m < 10; ++m) q1[m] -= tr[m];
-        cubic_rows<1>(Nb, q0, q1, q2, C);
+        cubic_rows<1>(Nb, q0, q1, q2, put);
     }
     {
         double q0[10], q1[10], q2[10];
@@ -329,30 +329,41 @@ PLB_L5 void build_coeffs(const double *Nb, double *C) {
         quad_block<5>(Nb, q2);
 #pragma unroll
         for (int m = 0; m < 10; ++m) q2[m] -= tr[m];
-        cubic_rows<2>(Nb, q0, q1, q2, C);
+        cubic_rows<2>(Nb, q0, q1, q2, put);
     }
 }
 #undef PLB_L5_E
 
-// ---- [A | B] -> rows 4..9 of A^{-1} B (:173): partial-pivot LU with the forward substitution fused into the rank-1
-// updates, then the back substitution of the six rows that enter the polynomial matrix.  Row transpositions are done
-// in place on the columns still in use (what lies left of the diagonal is never read again).
-PLB_L5 void eliminate(double *C) {
+// ---- [A | B] -> rows 4..9 of A^{-1} B (:173) ---------------------------------------------------------------------------
+// Only the left 10 x 10 block is kept in the thread's scratch (CL, row-major, stride 10); the right-hand sides are
+// parked elsewhere (global memory on the device) while it is factored, and then come back one column at a time.
+//
+// lu_left: partial-pivot LU in place, full-row transpositions, multipliers stored below the diagonal (the LAPACK
+// arrangement).  idx[r] = original row that ends up at position r.  S: 10 doubles of scratch.
+PLB_L5 void lu_left(double *CL, double *S, int *idx) {
+    int *Si = reinterpret_cast<int *>(S);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) Si[r] = r;
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
         int p = k;
-        double best = fabs(C[k * 20 + k]);
+        double best = fabs(CL[k * 10 + k]);
 #pragma unroll
         for (int r = k + 1; r < 10; ++r) {
-            const double v = fabs(C[r * 20 + k]);
+            const double v = fabs(CL[r * 10 + k]);
             if (v > best) {
                 best = v;
                 p = r;
             }
         }
-        double *rk = C + k * 20, *rp = C + p * 20;
-#pragma unroll 4
-        for (int c = k; c < 20; ++c) { // p == k: no change
+        {
+            const int t = Si[k]; // p == k: no change
+            Si[k] = Si[p];
+            Si[p] = t;
+        }
+        double *rk = CL + k * 10, *rp = CL + p * 10;
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
             const double t = rk[c];
             rk[c] = rp[c];
             rp[c] = t;
@@ -362,46 +373,67 @@ PLB_L5 void eliminate(double *C) {
 #pragma unroll
         for (int r = 0; r < 10; ++r)
             if (r > k) {
-                const double v = C[r * 20 + k];
+                const double v = CL[r * 10 + k];
                 lmul[r] = (best != 0.0) ? v / pv : v;
+                CL[r * 10 + k] = lmul[r];
             }
-#pragma unroll 3
-        for (int c = k + 1; c < 20; ++c) {
-            const double ckc = rk[c];
 #pragma unroll
-            for (int r = 0; r < 10; ++r)
-                if (r > k) C[r * 20 + c] -= lmul[r] * ckc;
+        for (int c = 0; c < 10; ++c)
+            if (c > k) {
+                const double ckc = rk[c];
+#pragma unroll
+                for (int r = 0; r < 10; ++r)
+                    if (r > k) CL[r * 10 + c] -= lmul[r] * ckc;
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 10; ++r) idx[r] = Si[r];
+}
+
+// The right-hand sides: get(row, column) returns the parked entry; each column is permuted (through S), run through
+// the unit-lower solve (per element the same products, subtracted in the same order, as the rank-1 updates of the fused
+// form) and the back substitution of rows 9..4.  X (60 doubles, may alias CL: the factors are in registers by then)
+// receives rows 4..9 of A^{-1} B, X[(r - 4) * 10 + column].
+template <class Get> PLB_L5 void solve_rhs(const double *CL, double *S, const int *idx, Get &&get, double *X) {
+    double L[10][10], U[10][10], diag[10]; // static indices: 45 + 15 + 6 values in registers
+#pragma unroll
+    for (int r = 0; r < 10; ++r)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            if (k < r) L[r][k] = CL[r * 10 + k];
+            if (r >= 4 && k > r) U[r][k] = CL[r * 10 + k];
         }
-    }
-    double diag[10], up[10][10]; // the rows 4..9 of U (static indices: registers)
 #pragma unroll
-    for (int r = 4; r < 10; ++r) {
-        diag[r] = C[r * 20 + r];
+    for (int r = 4; r < 10; ++r) diag[r] = CL[r * 10 + r];
+#pragma unroll 2
+    for (int c = 0; c < 10; ++c) {
+        double b[10];
 #pragma unroll
-        for (int k = 0; k < 10; ++k)
-            if (k > r) up[r][k] = C[r * 20 + k];
-    }
-#pragma unroll 5
-    for (int c = 10; c < 20; ++c) { // five independent substitution chains per pass
-        double x[10];
+        for (int r = 0; r < 10; ++r) S[r] = get(r, c);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) b[r] = S[idx[r]];
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+#pragma unroll
+            for (int r = k + 1; r < 10; ++r) b[r] -= L[r][k] * b[k];
 #pragma unroll
         for (int r = 9; r >= 4; --r) {
-            double s = C[r * 20 + c];
+            double sum = b[r];
 #pragma unroll
             for (int k = 0; k < 10; ++k)
-                if (k > r) s -= up[r][k] * x[k];
-            x[r] = s / diag[r];
-            C[r * 20 + c] = x[r];
+                if (k > r) sum -= U[r][k] * b[k];
+            b[r] = sum / diag[r];
+            X[(r - 4) * 10 + c] = b[r];
         }
     }
 }
 
 // ---- 3 x 13 polynomial matrix (:176-189) and det(A(z)), ascending coefficients (:191-352) ----------------------------
-PLB_L5 void poly_matrix(const double *C, double *A) {
+PLB_L5 void poly_matrix(const double *X, double *A) {
 #pragma unroll
     for (int e = 0; e < 39; ++e) {
         const int i = e / 13, c = e % 13;
-        const double *top = C + (4 + 2 * i) * 20 + 10, *bot = C + (5 + 2 * i) * 20 + 10;
+        const double *top = X + (2 * i) * 10, *bot = X + (2 * i + 1) * 10;
         const int g0 = (c < 4) ? 0 : (c < 8 ? 4 : 8), src0 = (c < 4) ? 0 : (c < 8 ? 3 : 6);
         const int w = (c < 8) ? 3 : 4, o = c - g0;
         double v = 0.0;
@@ -465,8 +497,8 @@ PLB_L5 void det_poly(const double *A, double *cp) {
 }
 #undef PLB_L5_P
 
-// Whole first half.  W: >= 200 doubles private to the thread (its shared-memory slice on the device); xs: the 5 + 5
-// bearings (x1s | x2s, 3 doubles each).  Outputs: Nb (36), A (39), cp (11).
+// Whole first half on plain arrays (the host test's entry; the device kernel strings the same pieces together with its
+// shared-memory slice and a parking buffer in global memory).  W: >= 210 doubles; xs: the 5 + 5 bearings (x1s | x2s).
 PLB_L5 void solve_5pt_poly_lane(double *W, const double *xs, double *Nb, double *A, double *cp) {
     // 9 x 5 epipolar constraints (:163-166): entry 3a+b of column i = x1[i][a] * x2[i][b]
 #pragma unroll
@@ -480,9 +512,16 @@ PLB_L5 void solve_5pt_poly_lane(double *W, const double *xs, double *Nb, double 
         const int r = e / 9, k = e % 9;
         Nb[4 * k + r] = W[45 + 9 * r + k];
     }
-    build_coeffs(Nb, W);
-    eliminate(W);
-    poly_matrix(W, A);
+    double *CL = W, *S = W + 100, *park = W + 110;
+    build_coeffs(Nb, [&](int row, auto cc, double v) {
+        constexpr int ci = decltype(cc)::value;
+        if constexpr (ci < 10) CL[row * 10 + ci] = v;
+        else park[row * 10 + (ci - 10)] = v;
+    });
+    int idx[10];
+    lu_left(CL, S, idx);
+    solve_rhs(CL, S, idx, [&](int r, int c) { return park[r * 10 + c]; }, CL);
+    poly_matrix(CL, A);
     det_poly(A, cp);
 }
 

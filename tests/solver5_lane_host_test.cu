@@ -18,7 +18,7 @@ int main() {
             if (std::scanf("%63s", tok) != 1) return 2;
             xs[i] = std::strtod(tok, nullptr);
         }
-        std::vector<double> W(256);
+        std::vector<double> W(256);  // 100 left block | 10 scratch | 100 parked right-hand sides
         double Nb[36], A[39], cp[11];
         plb::lane5::solve_5pt_poly_lane(W.data(), xs, Nb, A, cp);
         for (int i = 0; i < 36; ++i) std::printf("%a ", Nb[i]);
