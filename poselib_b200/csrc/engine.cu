@@ -1112,7 +1112,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         mark(PH_SAMPLE);
         launch_hypotheses(kind, R, E.work.p, out, mode, max_n_pad, st, E.ev2);
         PLB_CUDA(cudaEventRecord(E.ev1, st));
-        E.launches += kind_is_relpose(kind) ? 4 : 2; // k_solve (or k5_prep + k5_roots + k5_back) + scoring
+        E.launches += kind_is_relpose(kind) ? 5 : 2; // k_solve (or k5_gather + k5_prep_lane + k5_roots + k5_back) + scoring
         SelectArgs SA;
         SA.rp = E.rp.p;
         SA.na = na;
