@@ -176,6 +176,11 @@ int plb_estimate_homography(const double *x1, const double *x2, size_t n, const 
  * outputs are padded to the per-solver maximum. */
 int plb_p3p_batch(size_t count, const double *x /*count*3*3*/, const double *X /*count*3*3*/,
                   double *poses_out /*count*4*7*/, int32_t *n_out);
+/* PoseLib/solvers/p3p_lambdatwist.h:44-45 (the alternative P3P of SURVEY row N2): same layout as plb_p3p_batch.  Its
+ * closed-form cubic root goes through cbrt / cos / acos (CUDA's, 1-2 ulp from glibc's) before a Newton step and the
+ * depth refinement: solutions agree with the CPU implementation to ~1e-12, not bit for bit. */
+int plb_p3p_lambdatwist_batch(size_t count, const double *x /*count*3*3*/, const double *X /*count*3*3*/,
+                              double *poses_out /*count*4*7*/, int32_t *n_out);
 int plb_relpose_5pt_batch(size_t count, const double *x1 /*count*5*3*/, const double *x2,
                           double *E_out /*count*10*9*/, int32_t *n_out);
 int plb_relpose_5pt_poses_batch(size_t count, const double *x1, const double *x2, double *poses_out /*count*40*7*/,

@@ -79,6 +79,7 @@ void motion_from_essential(const Mat3 &E, const std::vector<Vec3> &x1, const std
 
 // ---- solvers/ (inputs are unit bearing vectors) ----------------------------------------------
 int p3p(const std::vector<Vec3> &x, const std::vector<Vec3> &X, std::vector<CameraPose> *out);
+int p3p_lambdatwist(const std::vector<Vec3> &x, const std::vector<Vec3> &X, std::vector<CameraPose> *out); // p3p_lambdatwist.cc:68
 int relpose_5pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::vector<Mat3> *E);
 int relpose_5pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::vector<CameraPose> *out);
 int relpose_7pt(const std::vector<Vec3> &x1, const std::vector<Vec3> &x2, std::vector<Mat3> *F);

@@ -144,6 +144,12 @@ int plo_p3p(const double *x9, const double *X9, double *poses_out) {
     for (int i = 0; i < n; ++i) pose_out(out[i], poses_out + 7 * i);
     return n;
 }
+int plo_p3p_lambdatwist(const double *x9, const double *X9, double *poses_out) {
+    std::vector<CameraPose> out;
+    int n = p3p_lambdatwist(v3(x9, 3), v3(X9, 3), &out);
+    for (int i = 0; i < n; ++i) pose_out(out[i], poses_out + 7 * i);
+    return n;
+}
 int plo_relpose_5pt_E(const double *x1, const double *x2, double *E_out) {
     std::vector<Mat3> out;
     int n = relpose_5pt(v3(x1, 5), v3(x2, 5), &out);

@@ -142,6 +142,14 @@ def p3p(x, X):
     return out[:n]
 
 
+def p3p_lambdatwist(x, X):
+    xa, xp = _d(x)
+    Xa, Xp = _d(X)
+    out = np.zeros((4, 7))
+    n = lib().plo_p3p_lambdatwist(xp, Xp, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out[:n]
+
+
 def relpose_5pt_E(x1, x2):
     a, ap = _d(x1)
     b, bp = _d(x2)

@@ -447,6 +447,164 @@ int p3p(const std::vector<Vec3> &x_in, const std::vector<Vec3> &X_in, std::vecto
     return (int)output->size();
 }
 
+// ============================ solvers/p3p_lambdatwist.cc =====================================
+// Persson & Nordberg's Lambda Twist P3P as PoseLib implements it (an alternative to p3p above).
+// Eigen's reductions (dot, squaredNorm, array sum) are taken left to right / column-major, as everywhere in this file.
+namespace {
+// p3p_lambdatwist.cc:36-65: the two non-zero eigenvalues (|sig1| >= |sig2|) and their eigenvectors (columns e1, e2)
+// of a symmetric 3x3 matrix that has a zero eigenvalue.
+void eig3x3_known0(const Mat3 &M, Vec3 &e1, Vec3 &e2, double &sig1, double &sig2) {
+    const double p1 = -M(0, 0) - M(1, 1) - M(2, 2);
+    const double p0 =
+        -M(0, 1) * M(0, 1) - M(0, 2) * M(0, 2) - M(1, 2) * M(1, 2) + M(0, 0) * (M(1, 1) + M(2, 2)) + M(1, 1) * M(2, 2);
+    const double disc = std::sqrt(p1 * p1 / 4.0 - p0);
+    const double tmp = -p1 / 2.0;
+    sig1 = tmp + disc;
+    sig2 = tmp - disc;
+    if (std::abs(sig1) < std::abs(sig2)) std::swap(sig1, sig2);
+    auto vec = [&](double sig) {
+        const double c = sig * sig + M(0, 0) * M(1, 1) - sig * (M(0, 0) + M(1, 1)) - M(0, 1) * M(0, 1);
+        const double a1 = (sig * M(0, 2) + M(0, 1) * M(1, 2) - M(0, 2) * M(1, 1)) / c;
+        const double a2 = (sig * M(1, 2) + M(0, 1) * M(0, 2) - M(0, 0) * M(1, 2)) / c;
+        const double n = 1.0 / std::sqrt(1 + a1 * a1 + a2 * a2);
+        return mk3(a1 * n, a2 * n, n);
+    };
+    e1 = vec(sig1);
+    e2 = vec(sig2);
+}
+// sum over the entries (column-major) of the element-wise product
+double array_prod_sum(const Mat3 &A, const Mat3 &B) {
+    double s = 0.0;
+    bool first = true;
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) {
+            const double v = A(r, c) * B(r, c);
+            s = first ? v : s + v;
+            first = false;
+        }
+    return s;
+}
+// matrix of cofactor columns: [c1 x c2, c2 x c0, c0 x c1]  (:95-96)
+Mat3 cross_columns(const Mat3 &D) {
+    Mat3 R;
+    set_col(R, 0, cross(col(D, 1), col(D, 2)));
+    set_col(R, 1, cross(col(D, 2), col(D, 0)));
+    set_col(R, 2, cross(col(D, 0), col(D, 1)));
+    return R;
+}
+} // namespace
+
+// p3p_lambdatwist.cc:68-244.  lambda_i x_i = R X_i + t with positive lambda_i; x: unit bearings.
+int p3p_lambdatwist(const std::vector<Vec3> &x, const std::vector<Vec3> &X, std::vector<CameraPose> *output) {
+    const Vec3 dX12 = X[0] - X[1], dX13 = X[0] - X[2], dX23 = X[1] - X[2];
+    const double a12 = sqnorm(dX12), b12 = dot(x[0], x[1]);
+    const double a13 = sqnorm(dX13), b13 = dot(x[0], x[2]);
+    const double a23 = sqnorm(dX23), b23 = dot(x[1], x[2]);
+    const double a23b12 = a23 * b12, a12b23 = a12 * b23, a23b13 = a23 * b13, a13b23 = a13 * b23;
+    Mat3 D1, D2; // :89-92
+    D1(0, 0) = a23;     D1(0, 1) = -a23b12;   D1(0, 2) = 0.0;
+    D1(1, 0) = -a23b12; D1(1, 1) = a23 - a12; D1(1, 2) = a12b23;
+    D1(2, 0) = 0.0;     D1(2, 1) = a12b23;    D1(2, 2) = -a12;
+    D2(0, 0) = a23;     D2(0, 1) = 0.0;       D2(0, 2) = -a23b13;
+    D2(1, 0) = 0.0;     D2(1, 1) = -a13;      D2(1, 2) = a13b23;
+    D2(2, 0) = -a23b13; D2(2, 1) = a13b23;    D2(2, 2) = a23 - a13;
+    const Mat3 DX1 = cross_columns(D1), DX2 = cross_columns(D2);
+    // p(gamma) = det(D1 + gamma D2)  (:98-103)
+    const double c3 = dot(col(D2, 0), col(DX2, 0));
+    double c2 = array_prod_sum(D1, DX2);
+    double c1 = array_prod_sum(D2, DX1);
+    double c0 = dot(col(D1, 0), col(DX1, 0));
+    const double c3inv = 1.0 / c3;
+    c2 *= c3inv;
+    c1 *= c3inv;
+    c0 *= c3inv;
+    // one real root in closed form (:110-121), one Newton step (:123-126)
+    double a = c1 - c2 * c2 / 3.0;
+    double b = (2.0 * c2 * c2 * c2 - 9.0 * c2 * c1) / 27.0 + c0;
+    double c = b * b / 4.0 + a * a * a / 27.0;
+    double gamma;
+    if (c > 0) {
+        c = std::sqrt(c);
+        b *= -0.5;
+        gamma = std::cbrt(b + c) + std::cbrt(b - c) - c2 / 3.0;
+    } else {
+        c = 3.0 * b / (2.0 * a) * std::sqrt(-3.0 / a);
+        gamma = 2.0 * std::sqrt(-a / 3.0) * std::cos(std::acos(c) / 3.0) - c2 / 3.0;
+    }
+    const double f = gamma * gamma * gamma + c2 * gamma * gamma + c1 * gamma + c0;
+    const double df = 3.0 * gamma * gamma + 2.0 * c2 * gamma + c1;
+    gamma = gamma - f / df;
+
+    Mat3 D0;
+    for (int r = 0; r < 3; ++r)
+        for (int cc = 0; cc < 3; ++cc) D0(r, cc) = D1(r, cc) + gamma * D2(r, cc);
+    Vec3 e1, e2;
+    double sig1, sig2;
+    eig3x3_known0(D0, e1, e2, sig1, sig2);
+    double s = std::sqrt(-sig2 / sig1);
+
+    output->clear();
+    Mat3 XX;
+    set_col(XX, 0, dX12);
+    set_col(XX, 1, dX13);
+    set_col(XX, 2, cross(dX12, dX13));
+    XX = inverse3(XX);
+    const double TOL_DOUBLE_ROOT = 1e-12;
+    auto emit = [&](double l1, double l2, double l3) {
+        refine_lambda(l1, l2, l3, a12, a13, a23, b12, b13, b23);
+        const Vec3 v1 = l1 * x[0] - l2 * x[1];
+        const Vec3 v2 = l1 * x[0] - l3 * x[2];
+        Mat3 YY;
+        set_col(YY, 0, v1);
+        set_col(YY, 1, v2);
+        set_col(YY, 2, cross(v1, v2));
+        const Mat3 R = YY * XX;
+        output->push_back(pose_from_Rt(R, l1 * x[0] - R * X[0]));
+    };
+    for (int s_flip = 0; s_flip < 2; ++s_flip, s = -s) {
+        // [u1 u2 u3] [lambda1; lambda2; lambda3] = 0  (:153-155)
+        const double u1 = e1[0] - s * e2[0], u2 = e1[1] - s * e2[1], u3 = e1[2] - s * e2[2];
+        const bool switch_12 = std::abs(u1) < std::abs(u2);
+        double qa, qb, qc, w0, w1;
+        if (switch_12) { // solve for lambda2 (:164-205)
+            w0 = -u1 / u2;
+            w1 = -u3 / u2;
+            qa = -a13 * w1 * w1 + 2 * a13b23 * w1 - a13 + a23;
+            qb = 2 * a13b23 * w0 - 2 * a23b13 - 2 * a13 * w0 * w1;
+            qc = -a13 * w0 * w0 + a23;
+        } else { // lambda1 as a combination of lambda2 and lambda3 (:207-236)
+            w0 = -u2 / u1;
+            w1 = -u3 / u1;
+            qa = (a13 - a12) * w1 * w1 + 2.0 * a12 * b13 * w1 - a12;
+            qb = -2.0 * a13 * b12 * w1 + 2.0 * a12 * b13 * w0 - 2.0 * w0 * w1 * (a12 - a13);
+            qc = (a13 - a12) * w0 * w0 - 2.0 * a13 * b12 * w0 + a13;
+        }
+        const double b2m4ac = qb * qb - 4.0 * qa * qc;
+        if (b2m4ac < -TOL_DOUBLE_ROOT) continue; // slightly negative discriminants count as a double root
+        const double sq = std::sqrt(std::max(0.0, b2m4ac));
+        double tau = (qb > 0) ? (2.0 * qc) / (-qb - sq) : (2.0 * qc) / (-qb + sq);
+        for (int tau_flip = 0; tau_flip < 2; ++tau_flip, tau = qc / (qa * tau)) {
+            if (tau > 0) {
+                if (switch_12) {
+                    const double l1 = std::sqrt(a13 / (tau * (tau - 2.0 * b13) + 1.0));
+                    const double l3 = tau * l1;
+                    const double l2 = w0 * l1 + w1 * l3;
+                    if (l2 < 0) continue; // (the reference's `continue` still evaluates the loop increment)
+                    emit(l1, l2, l3);
+                } else {
+                    const double l2 = std::sqrt(a23 / (tau * (tau - 2.0 * b23) + 1.0));
+                    const double l3 = tau * l2;
+                    const double l1 = w0 * l2 + w1 * l3;
+                    if (l1 < 0) continue;
+                    emit(l1, l2, l3);
+                }
+            }
+            if (b2m4ac < TOL_DOUBLE_ROOT) break; // double root: the second tau is the same
+        }
+    }
+    return (int)output->size();
+}
+
 // ============================ solvers/relpose_5pt.cc ==========================================
 namespace {
 // Monomial bookkeeping for polynomials in (x,y,z) with homogenising slot 3 ("1").

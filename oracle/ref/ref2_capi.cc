@@ -21,6 +21,7 @@
 #include "PoseLib/robust/utils.h"
 #include "PoseLib/solvers/homography_4pt.h"
 #include "PoseLib/solvers/p3p.h"
+#include "PoseLib/solvers/p3p_lambdatwist.h"
 #include "PoseLib/solvers/relpose_5pt.h"
 #include "PoseLib/solvers/relpose_7pt.h"
 #include "PoseLib/solvers/relpose_8pt.h"
@@ -141,6 +142,12 @@ extern "C" {
 int plr2_p3p(const double *x9, const double *X9, double *poses_out) {
     std::vector<CameraPose> out;
     const int n = p3p(v3(x9, 3), v3(X9, 3), &out);
+    for (size_t k = 0; k < out.size(); ++k) pose_out(out[k], poses_out + 7 * k);
+    return n;
+}
+int plr2_p3p_lambdatwist(const double *x9, const double *X9, double *poses_out) {
+    std::vector<CameraPose> out;
+    const int n = p3p_lambdatwist(v3(x9, 3), v3(X9, 3), &out);
     for (size_t k = 0; k < out.size(); ++k) pose_out(out[k], poses_out + 7 * k);
     return n;
 }

@@ -4,7 +4,7 @@
 //   robust.h:45-46,68-70,112-113,133-134   estimate_absolute_pose / estimate_relative_pose / estimate_fundamental /
 //                                          estimate_homography
 //   robust/ransac.h:39-40,60-61,85-87,99-101  ransac_pnp / ransac_relpose / ransac_fundamental / ransac_homography
-//   solvers/p3p.h:42, relpose_5pt.h:40-43, relpose_7pt.h:39-40, homography_4pt.h:38-39
+//   solvers/p3p.h:42, p3p_lambdatwist.h:44, relpose_5pt.h:40-43, relpose_7pt.h:39-40, homography_4pt.h:38-39
 //
 // The adapter is templated on the vector / matrix types so that it compiles both
 //   (a) inside PoseLib (or user code) with Eigen:   poselib_b200::estimate_relative_pose(x1, x2, cam1, cam2, opt, &pose, &inl)
@@ -305,6 +305,19 @@ template <typename V3, typename Pose> int p3p(const std::vector<V3> &x, const st
     double poses[28];
     int32_t n = 0;
     detail::check(plb_p3p_batch(1, detail::raw(x), detail::raw(X), poses, &n));
+    for (int i = 0; i < n; ++i) {
+        Pose p;
+        detail::pose_from(poses + 7 * i, &p);
+        output->push_back(p);
+    }
+    return n;
+}
+// solvers/p3p_lambdatwist.h:44-45
+template <typename V3, typename Pose> int p3p_lambdatwist(const std::vector<V3> &x, const std::vector<V3> &X, std::vector<Pose> *output) {
+    output->clear(); // p3p_lambdatwist.cc:137
+    double poses[28];
+    int32_t n = 0;
+    detail::check(plb_p3p_lambdatwist_batch(1, detail::raw(x), detail::raw(X), poses, &n));
     for (int i = 0; i < n; ++i) {
         Pose p;
         detail::pose_from(poses + 7 * i, &p);

@@ -7,7 +7,8 @@
 //                             ransac_homography :99-101                                      (CPU bodies: robust/ransac.cc)
 //   PoseLib/robust/bundle.h   bundle_adjust :41-43, refine_relpose :84-86, refine_fundamental :132-134,
 //                             refine_homography :148-150                                     (CPU bodies: robust/bundle.cc)
-//   PoseLib/solvers/*.h       p3p, relpose_5pt (both overloads), relpose_7pt, homography_4pt  (CPU bodies: solvers/*.cc)
+//   PoseLib/solvers/*.h       p3p, p3p_lambdatwist, relpose_5pt (both overloads), relpose_7pt, homography_4pt
+//                                                                                        (CPU bodies: solvers/*.cc)
 // Build it INSTEAD of the CPU bodies of these symbols with PoseLib's include path and Eigen, and link
 // -lposelib_b200.  Because the declarations come from PoseLib's headers, a signature that drifts from the reference is a
 // compile or link error, not a silent overload: tests/test_dropin_reference_headers.py compiles this file against the
@@ -20,6 +21,7 @@
 #include "PoseLib/robust/ransac.h"
 #include "PoseLib/solvers/homography_4pt.h"
 #include "PoseLib/solvers/p3p.h"
+#include "PoseLib/solvers/p3p_lambdatwist.h"
 #include "PoseLib/solvers/relpose_5pt.h"
 #include "PoseLib/solvers/relpose_7pt.h"
 
@@ -93,6 +95,10 @@ BundleStats refine_homography(const std::vector<Point2D> &x1, const std::vector<
 // ---- PoseLib/solvers/*.h -------------------------------------------------------------------------------------------
 int p3p(const std::vector<Eigen::Vector3d> &x, const std::vector<Eigen::Vector3d> &X, std::vector<CameraPose> *output) {
     return poselib_b200::p3p(x, X, output);
+}
+int p3p_lambdatwist(const std::vector<Eigen::Vector3d> &x, const std::vector<Eigen::Vector3d> &X,
+                    std::vector<CameraPose> *output) {
+    return poselib_b200::p3p_lambdatwist(x, X, output);
 }
 int relpose_5pt(const std::vector<Eigen::Vector3d> &x1, const std::vector<Eigen::Vector3d> &x2,
                 std::vector<Eigen::Matrix3d> *essential_matrices) {

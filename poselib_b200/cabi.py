@@ -95,7 +95,7 @@ EXPORTS = [
     "plb_set_mode", "plb_host_sample_table", "plb_device_sample_table", "plb_host_dynamic_max_iter", "plb_ransac_pnp", "plb_ransac_relpose", "plb_ransac_relpose_cameras", "plb_ransac_fundamental",
     "plb_ransac_homography",
     "plb_estimate_absolute_pose", "plb_estimate_relative_pose", "plb_estimate_fundamental",
-    "plb_estimate_homography", "plb_p3p_batch", "plb_relpose_5pt_batch", "plb_relpose_5pt_poses_batch",
+    "plb_estimate_homography", "plb_p3p_batch", "plb_p3p_lambdatwist_batch", "plb_relpose_5pt_batch", "plb_relpose_5pt_poses_batch",
     "plb_relpose_7pt_batch", "plb_homography_4pt_batch", "plb_essential_matrix_8pt_batch", "plb_relpose_8pt_batch", "plb_ransac_batch", "plb_ransac_batch_multi", "plb_estimate_batch", "plb_bundle_adjust",
     "plb_refine_relpose", "plb_refine_relpose_cameras", "plb_refine_fundamental", "plb_refine_homography", "plb_resident_create",
     "plb_resident_free",
@@ -291,6 +291,11 @@ def _solver(fn, a, b, per_out, extra=()):
 
 def p3p_batch(x, X):
     out, n = _solver(_lib.plb_p3p_batch, x, X, 28)
+    return out.reshape(-1, 4, 7), n
+
+
+def p3p_lambdatwist_batch(x, X):
+    out, n = _solver(_lib.plb_p3p_lambdatwist_batch, x, X, 28)
     return out.reshape(-1, 4, 7), n
 
 

@@ -1946,6 +1946,9 @@ static int solver_batch(int kind, int variant, size_t count, const double *a, si
 int plb_p3p_batch(size_t count, const double *x, const double *X, double *poses_out, int32_t *n_out) {
     return solver_batch(KIND_PNP, 0, count, x, 9, X, 9, poses_out, 28, n_out, 0);
 }
+int plb_p3p_lambdatwist_batch(size_t count, const double *x, const double *X, double *poses_out, int32_t *n_out) {
+    return solver_batch(KIND_PNP, 1, count, x, 9, X, 9, poses_out, 28, n_out, 0);
+}
 int plb_relpose_5pt_batch(size_t count, const double *x1, const double *x2, double *E_out, int32_t *n_out) {
     return solver_batch(KIND_RELPOSE, 0, count, x1, 15, x2, 15, E_out, 90, n_out, 0);
 }

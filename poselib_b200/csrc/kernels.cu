@@ -3036,7 +3036,7 @@ void launch_eightpt(size_t count, int n, const double *x1, const double *x2, int
 // ============================================================================================================
 // direct solver surface: one warp per instance
 // ============================================================================================================
-// variant: 0 = native output (p3p poses / 5pt E / 7pt F / H), 1 = 5pt poses
+// variant: 0 = native output (p3p poses / 5pt E / 7pt F / H), 1 = 5pt poses / p3p_lambdatwist
 template <int KIND, int VARIANT>
 __global__ void __launch_bounds__(HYP_WARPS * 32)
     k_solver_batch(size_t count, const double *__restrict__ a, const double *__restrict__ b, double *out, int *n_out,
@@ -3059,7 +3059,7 @@ __global__ void __launch_bounds__(HYP_WARPS * 32)
                 Xs[k] = mk(b[9 * i + 3 * k], b[9 * i + 3 * k + 1], b[9 * i + 3 * k + 2]);
             }
             double *models = reinterpret_cast<double *>(W);
-            const int n = solve_p3p(xs, Xs, models, lane);
+            const int n = (VARIANT == 1) ? solve_p3p_lambdatwist(xs, Xs, models, lane) : solve_p3p(xs, Xs, models, lane);
             if (lane < 28) out[28 * i + lane] = (lane < 7 * n) ? models[lane] : 0.0;
             if (lane == 0) n_out[i] = n;
         } else if (KIND == KIND_HOMOG) {
@@ -3116,7 +3116,10 @@ void launch_solver_batch(int kind, int variant, size_t count, const double *a, c
                          int *n_out, int flags, cudaStream_t stream) {
     if (count == 0) return;
     switch (kind) {
-    case KIND_PNP: launch_solver_t<KIND_PNP, 0>(count, a, b, out, n_out, flags, stream); break;
+    case KIND_PNP:
+        if (variant == 0) launch_solver_t<KIND_PNP, 0>(count, a, b, out, n_out, flags, stream);
+        else launch_solver_t<KIND_PNP, 1>(count, a, b, out, n_out, flags, stream);
+        break;
     case KIND_RELPOSE:
         if (variant == 0) launch_solver_t<KIND_RELPOSE, 0>(count, a, b, out, n_out, flags, stream);
         else launch_solver_t<KIND_RELPOSE, 1>(count, a, b, out, n_out, flags, stream);

@@ -248,6 +248,164 @@ PLB_DEV int solve_p3p(const d3 *xs, const d3 *Xs, double *out, int lane, bool wa
     return n_sols;
 }
 
+// ---- p3p_lambdatwist (solvers/p3p_lambdatwist.cc:36-244): Persson & Nordberg's Lambda Twist, PoseLib's alternative P3P.
+// Same calling convention as solve_p3p.  cbrt / cos / acos are CUDA's (1-2 ulp from glibc's): the closed-form root only
+// seeds one Newton step on the cubic and the depths are polished by p3p_refine_lambda, so the poses agree with the CPU
+// restatement to ~1e-13, not bit for bit.
+PLB_DEV d3 lt_eigvec_known0(const m3 &M, double sig) {
+    const double c = sig * sig + M(0, 0) * M(1, 1) - sig * (M(0, 0) + M(1, 1)) - M(0, 1) * M(0, 1);
+    const double a1 = (sig * M(0, 2) + M(0, 1) * M(1, 2) - M(0, 2) * M(1, 1)) / c;
+    const double a2 = (sig * M(1, 2) + M(0, 1) * M(0, 2) - M(0, 0) * M(1, 2)) / c;
+    const double n = 1.0 / sqrt(1 + a1 * a1 + a2 * a2);
+    return mk(a1 * n, a2 * n, n);
+}
+PLB_DEV m3 lt_cross_columns(const m3 &D) {
+    m3 R;
+    set_col(R, 0, cross(mcol(D, 1), mcol(D, 2)));
+    set_col(R, 1, cross(mcol(D, 2), mcol(D, 0)));
+    set_col(R, 2, cross(mcol(D, 0), mcol(D, 1)));
+    return R;
+}
+// sum over the entries (column-major) of the element-wise product
+PLB_DEV double lt_array_prod_sum(const m3 &A, const m3 &B) {
+    double s = A(0, 0) * B(0, 0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            if (c + r > 0) s = s + A(r, c) * B(r, c);
+    return s;
+}
+PLB_DEV int solve_p3p_lambdatwist(const d3 *xs, const d3 *Xs, double *out, int lane, bool warp_uniform = true) {
+    const d3 x0 = xs[0], x1 = xs[1], x2 = xs[2];
+    const d3 dX12 = Xs[0] - Xs[1], dX13 = Xs[0] - Xs[2], dX23 = Xs[1] - Xs[2];
+    const double a12 = dot(dX12, dX12), b12 = dot(x0, x1);
+    const double a13 = dot(dX13, dX13), b13 = dot(x0, x2);
+    const double a23 = dot(dX23, dX23), b23 = dot(x1, x2);
+    const double a23b12 = a23 * b12, a12b23 = a12 * b23, a23b13 = a23 * b13, a13b23 = a13 * b23;
+    m3 D1, D2; // :89-92
+    D1(0, 0) = a23;     D1(0, 1) = -a23b12;   D1(0, 2) = 0.0;
+    D1(1, 0) = -a23b12; D1(1, 1) = a23 - a12; D1(1, 2) = a12b23;
+    D1(2, 0) = 0.0;     D1(2, 1) = a12b23;    D1(2, 2) = -a12;
+    D2(0, 0) = a23;     D2(0, 1) = 0.0;       D2(0, 2) = -a23b13;
+    D2(1, 0) = 0.0;     D2(1, 1) = -a13;      D2(1, 2) = a13b23;
+    D2(2, 0) = -a23b13; D2(2, 1) = a13b23;    D2(2, 2) = a23 - a13;
+    const m3 DX1 = lt_cross_columns(D1), DX2 = lt_cross_columns(D2);
+    // p(gamma) = det(D1 + gamma D2)  (:98-103), monic, one real root in closed form (:110-121) + one Newton step (:123-126)
+    const double c3 = dot(mcol(D2, 0), mcol(DX2, 0));
+    double c2 = lt_array_prod_sum(D1, DX2);
+    double c1 = lt_array_prod_sum(D2, DX1);
+    double c0 = dot(mcol(D1, 0), mcol(DX1, 0));
+    const double c3inv = 1.0 / c3;
+    c2 *= c3inv;
+    c1 *= c3inv;
+    c0 *= c3inv;
+    double a = c1 - c2 * c2 / 3.0;
+    double b = (2.0 * c2 * c2 * c2 - 9.0 * c2 * c1) / 27.0 + c0;
+    double c = b * b / 4.0 + a * a * a / 27.0;
+    double gamma;
+    if (c > 0) {
+        c = sqrt(c);
+        b *= -0.5;
+        gamma = cbrt(b + c) + cbrt(b - c) - c2 / 3.0;
+    } else {
+        c = 3.0 * b / (2.0 * a) * sqrt(-3.0 / a);
+        gamma = 2.0 * sqrt(-a / 3.0) * cos(acos(c) / 3.0) - c2 / 3.0;
+    }
+    const double f = gamma * gamma * gamma + c2 * gamma * gamma + c1 * gamma + c0;
+    const double df = 3.0 * gamma * gamma + 2.0 * c2 * gamma + c1;
+    gamma = gamma - f / df;
+
+    m3 D0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) D0.a[k] = D1.a[k] + gamma * D2.a[k];
+    double sig1, sig2;
+    { // compute_eig3x3known0 (:36-65)
+        const double p1 = -D0(0, 0) - D0(1, 1) - D0(2, 2);
+        const double p0 = -D0(0, 1) * D0(0, 1) - D0(0, 2) * D0(0, 2) - D0(1, 2) * D0(1, 2) + D0(0, 0) * (D0(1, 1) + D0(2, 2)) +
+                          D0(1, 1) * D0(2, 2);
+        const double disc = sqrt(p1 * p1 / 4.0 - p0);
+        const double tmp = -p1 / 2.0;
+        sig1 = tmp + disc;
+        sig2 = tmp - disc;
+        if (fabs(sig1) < fabs(sig2)) {
+            const double t = sig1;
+            sig1 = sig2;
+            sig2 = t;
+        }
+    }
+    const d3 e1 = lt_eigvec_known0(D0, sig1), e2 = lt_eigvec_known0(D0, sig2);
+    double s = sqrt(-sig2 / sig1);
+
+    m3 XX;
+    set_col(XX, 0, dX12);
+    set_col(XX, 1, dX13);
+    set_col(XX, 2, cross(dX12, dX13));
+    XX = inv3(XX);
+    const double TOL_DOUBLE_ROOT = 1e-12;
+    int n_sols = 0;
+#pragma unroll 1
+    for (int s_flip = 0; s_flip < 2; ++s_flip, s = -s) {
+        const double u1 = e1.x - s * e2.x, u2 = e1.y - s * e2.y, u3 = e1.z - s * e2.z;
+        const bool switch_12 = fabs(u1) < fabs(u2);
+        double qa, qb, qc, w0, w1;
+        if (switch_12) { // solve for lambda2 (:164-205)
+            w0 = -u1 / u2;
+            w1 = -u3 / u2;
+            qa = -a13 * w1 * w1 + 2 * a13b23 * w1 - a13 + a23;
+            qb = 2 * a13b23 * w0 - 2 * a23b13 - 2 * a13 * w0 * w1;
+            qc = -a13 * w0 * w0 + a23;
+        } else { // lambda1 as a combination of lambda2 and lambda3 (:207-236)
+            w0 = -u2 / u1;
+            w1 = -u3 / u1;
+            qa = (a13 - a12) * w1 * w1 + 2.0 * a12 * b13 * w1 - a12;
+            qb = -2.0 * a13 * b12 * w1 + 2.0 * a12 * b13 * w0 - 2.0 * w0 * w1 * (a12 - a13);
+            qc = (a13 - a12) * w0 * w0 - 2.0 * a13 * b12 * w0 + a13;
+        }
+        const double b2m4ac = qb * qb - 4.0 * qa * qc;
+        if (b2m4ac < -TOL_DOUBLE_ROOT) continue;
+        const double sq = sqrt(fmax(0.0, b2m4ac));
+        double tau = (qb > 0) ? (2.0 * qc) / (-qb - sq) : (2.0 * qc) / (-qb + sq);
+#pragma unroll 1
+        for (int tau_flip = 0; tau_flip < 2; ++tau_flip, tau = qc / (qa * tau)) {
+            if (tau > 0) {
+                double l1, l2, l3;
+                if (switch_12) {
+                    l1 = sqrt(a13 / (tau * (tau - 2.0 * b13) + 1.0));
+                    l3 = tau * l1;
+                    l2 = w0 * l1 + w1 * l3;
+                    if (l2 < 0) continue;
+                } else {
+                    l2 = sqrt(a23 / (tau * (tau - 2.0 * b23) + 1.0));
+                    l3 = tau * l2;
+                    l1 = w0 * l2 + w1 * l3;
+                    if (l1 < 0) continue;
+                }
+                p3p_refine_lambda(l1, l2, l3, a12, a13, a23, b12, b13, b23);
+                const d3 v1 = l1 * x0 - l2 * x1;
+                const d3 v2 = l1 * x0 - l3 * x2;
+                m3 YY;
+                set_col(YY, 0, v1);
+                set_col(YY, 1, v2);
+                set_col(YY, 2, cross(v1, v2));
+                const m3 R = mmul(YY, XX);
+                const d3 t = l1 * x0 - mvec(R, Xs[0]);
+                double q[4];
+                rot_to_quat(R, q);
+                if (lane == 0) {
+                    double *o = out + 7 * n_sols;
+                    o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3];
+                    o[4] = t.x; o[5] = t.y; o[6] = t.z;
+                }
+                ++n_sols;
+            }
+            if (b2m4ac < TOL_DOUBLE_ROOT) break;
+        }
+    }
+    if (warp_uniform) __syncwarp();
+    return n_sols;
+}
+
 // ================================ homography_4pt (SKS / ACA closed form) ===================================
 // homography_4pt.cc:36-128.  Writes H (9 doubles COLUMN-major) to out; returns 0/1.
 PLB_DEV int solve_h4(const d3 *x1, const d3 *x2, double *out, int lane, bool check_cheirality, bool warp_uniform = true) {

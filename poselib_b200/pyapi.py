@@ -14,7 +14,7 @@ import numpy as np
 from . import cabi
 
 __all__ = ["CameraPose", "Image", "estimate_absolute_pose", "estimate_relative_pose", "estimate_fundamental",
-           "estimate_homography", "p3p", "relpose_5pt", "essential_matrix_5pt", "relpose_7pt", "homography_4pt"]
+           "estimate_homography", "p3p", "p3p_lambdatwist", "relpose_5pt", "essential_matrix_5pt", "relpose_7pt", "homography_4pt"]
 
 _CAMERA_IDS = dict(cabi.CAMERA)
 
@@ -196,6 +196,11 @@ def estimate_homography(points2D_1, points2D_2, opt=None, initial_H=None):
 # ---- minimal solvers (pybind/bindings/solvers.cc:305,341,349): lists of solutions, unit bearings in ---------------
 def p3p(x, X):
     poses, n = cabi.p3p_batch(_pts(x, 3)[None], _pts(X, 3)[None])
+    return [CameraPose(p[:4], p[4:]) for p in poses[0, :n[0]]]
+
+
+def p3p_lambdatwist(x, X):
+    poses, n = cabi.p3p_lambdatwist_batch(_pts(x, 3)[None], _pts(X, 3)[None])
     return [CameraPose(p[:4], p[4:]) for p in poses[0, :n[0]]]
 
 

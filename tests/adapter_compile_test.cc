@@ -126,6 +126,7 @@ int main(int argc, char **argv) {
         std::vector<Matrix3d> Ms;
         std::vector<Vector3d> b13(b1.begin(), b1.begin() + 3), X3(X.begin(), X.begin() + 3);
         poselib_b200::p3p(b13, X3, &poses);
+        poselib_b200::p3p_lambdatwist(b13, X3, &poses);
         std::vector<Vector3d> b15(b1.begin(), b1.begin() + 5), b25(b2.begin(), b2.begin() + 5);
         poselib_b200::relpose_5pt(b15, b25, &Ms);
         poselib_b200::relpose_5pt_poses(b15, b25, &poses);

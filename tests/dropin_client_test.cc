@@ -9,6 +9,7 @@
 #include <PoseLib/robust/ransac.h>
 #include <PoseLib/solvers/homography_4pt.h>
 #include <PoseLib/solvers/p3p.h>
+#include <PoseLib/solvers/p3p_lambdatwist.h>
 #include <PoseLib/solvers/relpose_5pt.h>
 #include <PoseLib/solvers/relpose_7pt.h>
 
@@ -88,9 +89,11 @@ int main(int argc, char **argv) {
                   std::vector<Eigen::Matrix3d> *) = &relpose_7pt;
         int (*s5)(const std::vector<Eigen::Vector3d> &, const std::vector<Eigen::Vector3d> &, Eigen::Matrix3d *, bool) =
             &homography_4pt;
+        int (*s6)(const std::vector<Eigen::Vector3d> &, const std::vector<Eigen::Vector3d> &, std::vector<CameraPose> *) =
+            &p3p_lambdatwist;
         const void *all[] = {(void *)e1, (void *)e2, (void *)e3, (void *)e4, (void *)r1, (void *)r2, (void *)r3,
                              (void *)r4, (void *)r5, (void *)b1, (void *)b2, (void *)b3, (void *)b4, (void *)s1,
-                             (void *)s2, (void *)s3, (void *)s4, (void *)s5};
+                             (void *)s2, (void *)s3, (void *)s4, (void *)s5, (void *)s6};
         for (const void *p : all)
             if (!p) return fail("null entry point");
         std::printf("dropin link ok: %zu PoseLib entry points resolved\n", sizeof(all) / sizeof(all[0]));

@@ -1,6 +1,6 @@
 """The drop-in translation unit (poselib_b200/adapter/poselib_dropin.cc) is compiled against the REFERENCE'S OWN headers
 (PoseLib/robust.h, robust/ransac.h, robust/bundle.h, solvers/*.h) and linked, together with libposelib_b200.so, into a
-client that includes PoseLib's headers only.  Its 18 definitions must match PoseLib's declarations exactly, otherwise the
+client that includes PoseLib's headers only.  Its 19 definitions must match PoseLib's declarations exactly, otherwise the
 client does not link.  Eigen3 is not installed here; the Eigen stand-in of the oracle tree (oracle/ref/mini) is used at
 compile time only.  Needs /root/reference (CPU container); the compiled client also has a `run` mode for a GPU box."""
 import os
@@ -19,7 +19,7 @@ def test_dropin_defines_poselibs_own_declarations():
     import __graft_entry__ as ge
     ge.build()  # builds the library and, where the reference is mounted, tests/_dropin_client (build_dropin_client)
     out = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
-    assert out.returncode == 0 and "dropin link ok: 18 PoseLib entry points resolved" in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and "dropin link ok: 19 PoseLib entry points resolved" in out.stdout, out.stdout + out.stderr
 
 
 def test_the_same_client_passes_on_poselibs_own_cpu_implementation():

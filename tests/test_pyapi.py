@@ -93,6 +93,7 @@ def test_pyapi_matches_oracle_through_the_poselib_call_surface():
     # solvers
     x, X, R, t = G.minimal_abspose(1)
     assert len(poselib.p3p(x, X)) == len(P.p3p(x, X))
+    assert len(poselib.p3p_lambdatwist(x, X)) == len(P.p3p_lambdatwist(x, X))
     x1, x2, R, t = G.minimal_relpose(1, 5)
     assert len(poselib.relpose_5pt(x1, x2)) == len(P.relpose_5pt(x1, x2))
     assert np.allclose(np.array(poselib.essential_matrix_5pt(x1, x2)), P.relpose_5pt_E(x1, x2), atol=1e-12)

@@ -63,6 +63,25 @@ def maxdiff(a, b):
 
 
 # ---- minimal solvers ---------------------------------------------------------------------------------------------
+def test_p3p_lambdatwist_is_bit_identical_and_finds_the_pose():
+    """solvers/p3p_lambdatwist.cc (SURVEY row N2's alternative P3P) compiled from the reference on mini-Eigen == the
+    oracle restatement, bit for bit (libm is the same on both sides); the true pose is among the solutions."""
+    found = 0
+    for s in range(400):
+        x, X, R, t = G.minimal_abspose(s)
+        a, b = both(lambda: P.p3p_lambdatwist(x, X))
+        assert a.shape == b.shape and np.array_equal(a, b), s
+        for p in a:
+            q = p[:4]
+            Rq = np.array([[1 - 2 * (q[2]**2 + q[3]**2), 2 * (q[1] * q[2] - q[0] * q[3]), 2 * (q[1] * q[3] + q[0] * q[2])],
+                           [2 * (q[1] * q[2] + q[0] * q[3]), 1 - 2 * (q[1]**2 + q[3]**2), 2 * (q[2] * q[3] - q[0] * q[1])],
+                           [2 * (q[1] * q[3] - q[0] * q[2]), 2 * (q[2] * q[3] + q[0] * q[1]), 1 - 2 * (q[1]**2 + q[2]**2)]])
+            if np.abs(p[4:] - t).max() < 1e-6 and np.abs(Rq - R).max() < 1e-6:
+                found += 1
+                break
+    assert found >= 396, found
+
+
 def test_p3p_and_homography_4pt_are_bit_identical():
     for s in range(300):
         x, X, _, _ = G.minimal_abspose(s)
