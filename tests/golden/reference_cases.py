@@ -200,7 +200,7 @@ def _noisy_samples(npts, count, seed, outliers=True):
 
 def solver_instances(name, n_min=40, n_noisy=12):
     """(a, b) arrays [count, k, 3]: the first n_min minimal instances and the first n_noisy noisy samples of the GPU test."""
-    if name == "p3p":
+    if name in ("p3p", "p3p_lambdatwist"):
         xs, Xs = [], []
         for i in range(n_min):
             x, X, _, _ = G.minimal_abspose(i)
@@ -225,13 +225,15 @@ def solver_instances(name, n_min=40, n_noisy=12):
     return np.concatenate([np.array(x1s), a[:n_noisy]]), np.concatenate([np.array(x2s), b[:n_noisy]])
 
 
-SOLVERS = ("p3p", "relpose_7pt", "homography_4pt")
+SOLVERS = ("p3p", "p3p_lambdatwist", "relpose_7pt", "homography_4pt")
 
 
 def solve_one(api, name, a, b):
     """One instance through the oracle-style wrapper; -> array of solutions (k, 7) / (k, 3, 3)."""
     if name == "p3p":
         return np.asarray(api.p3p(a, b))
+    if name == "p3p_lambdatwist":
+        return np.asarray(api.p3p_lambdatwist(a, b))
     if name == "relpose_7pt":
         return np.asarray(api.relpose_7pt(a, b))
     n, H = api.homography_4pt(a, b)

@@ -52,7 +52,7 @@ SOLVER_GOLD = json.load(open(os.path.join(HERE, "golden", "reference_sources.jso
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", RC.SOLVERS)
 def test_cuda_solvers_reproduce_the_reference_sources_solver_outputs(name):
-    """plb_p3p_batch / plb_relpose_7pt_batch / plb_homography_4pt_batch against the solutions the reference's sources
+    """plb_p3p_batch / plb_p3p_lambdatwist_batch / plb_relpose_7pt_batch / plb_homography_4pt_batch against the solutions the reference's sources
     returned for the first instances of tests/test_gpu_parity.py's solver tests — solution counts exactly, values with
     that file's tolerances (p3p 1e-9, 7pt 1e-8 relative, homography 1e-10 relative)."""
     import numpy as np
@@ -61,14 +61,14 @@ def test_cuda_solvers_reproduce_the_reference_sources_solver_outputs(name):
         pytest.fail("no CUDA device: the GPU tests must run on the B200 box")
     cabi.set_device(0)
     a, b = RC.solver_instances(name)
-    fn = {"p3p": cabi.p3p_batch, "relpose_7pt": cabi.relpose_7pt_batch, "homography_4pt": cabi.homography_4pt_batch}[name]
+    fn = {"p3p": cabi.p3p_batch, "p3p_lambdatwist": cabi.p3p_lambdatwist_batch, "relpose_7pt": cabi.relpose_7pt_batch, "homography_4pt": cabi.homography_4pt_batch}[name]
     out, n = fn(a, b)
-    like = (7,) if name == "p3p" else (3, 3)
+    like = (7,) if name.startswith("p3p") else (3, 3)
     for i in range(len(a)):
         flat = np.array([float.fromhex(v) for v in SOLVER_GOLD[name][i]])
         g = flat.reshape((-1,) + like)
         assert n[i] == len(g), (name, i, n[i], len(g))
-        if name == "p3p":
+        if name.startswith("p3p"):
             assert np.allclose(out[i, :n[i]], g, rtol=1e-9, atol=1e-9, equal_nan=True), i
         elif name == "relpose_7pt":
             assert np.allclose(out[i, :n[i]], g, rtol=1e-8, atol=1e-9, equal_nan=True), i
