@@ -786,6 +786,7 @@ __global__ void __launch_bounds__(256) k5_gather(const RoundDesc R, HypOut out) 
 constexpr int PREPL_THREADS = 256;
 constexpr int PREPL_STRIDE = 111;
 constexpr size_t PREPL_SMEM = sizeof(double) * PREPL_STRIDE * PREPL_THREADS;
+template <int UNR>
 __global__ void __launch_bounds__(PREPL_THREADS, 1) k5_prep_lane(const RoundDesc R, HypOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *W = reinterpret_cast<double *>(smem_raw) + (size_t)threadIdx.x * PREPL_STRIDE;
@@ -825,7 +826,7 @@ __global__ void __launch_bounds__(PREPL_THREADS, 1) k5_prep_lane(const RoundDesc
     }
     int idx[10];
     lane5::lu_left(CL, S, idx);
-    lane5::solve_rhs(CL, S, idx, [&](int r, int c) { return park[(size_t)(r * 10 + c) * nt]; }, CL);
+    lane5::solve_rhs<UNR>(CL, S, idx, [&](int r, int c) { return park[(size_t)(r * 10 + c) * nt]; }, CL);
     double A[39], cp[11];
     lane5::poly_matrix(CL, A);
 #pragma unroll
@@ -1732,13 +1733,20 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
             return e ? std::atoi(e) != 0 : true;
         }();
         if (lane_prep) {
+            static const int unr = [] {
+                const char *e = std::getenv("PLB_PREP_UNR"); // columns of the right-hand side solved per loop pass
+                return e ? std::atoi(e) : 1;
+            }();
             static bool attr_set[MAX_DEVICES] = {false};
             if (!attr_set[cur_dev()]) {
-                cudaFuncSetAttribute(k5_prep_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREPL_SMEM);
+                cudaFuncSetAttribute(k5_prep_lane<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREPL_SMEM);
+                cudaFuncSetAttribute(k5_prep_lane<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREPL_SMEM);
                 attr_set[cur_dev()] = true;
             }
             k5_gather<<<(R.n_total + 255) / 256, 256, 0, stream>>>(R, out);
-            k5_prep_lane<<<(R.n_total + PREPL_THREADS - 1) / PREPL_THREADS, PREPL_THREADS, PREPL_SMEM, stream>>>(R, out);
+            const unsigned grid = (unsigned)((R.n_total + PREPL_THREADS - 1) / PREPL_THREADS);
+            if (unr == 1) k5_prep_lane<1><<<grid, PREPL_THREADS, PREPL_SMEM, stream>>>(R, out);
+            else k5_prep_lane<2><<<grid, PREPL_THREADS, PREPL_SMEM, stream>>>(R, out);
         } else {
             int blocks = prep_blocks_per_sm() * sm_count();
             const int per_cta = HYP_WARPS * PREP_SAMPLES_PER_WARP;

@@ -394,7 +394,7 @@ PLB_L5 void lu_left(double *CL, double *S, int *idx) {
 // the unit-lower solve (per element the same products, subtracted in the same order, as the rank-1 updates of the fused
 // form) and the back substitution of rows 9..4.  X (60 doubles, may alias CL: the factors are in registers by then)
 // receives rows 4..9 of A^{-1} B, X[(r - 4) * 10 + column].
-template <class Get> PLB_L5 void solve_rhs(const double *CL, double *S, const int *idx, Get &&get, double *X) {
+template <int UNR = 1, class Get> PLB_L5 void solve_rhs(const double *CL, double *S, const int *idx, Get &&get, double *X) {
     double L[10][10], U[10][10], diag[10]; // static indices: 45 + 15 + 6 values in registers
 #pragma unroll
     for (int r = 0; r < 10; ++r)
@@ -405,7 +405,7 @@ template <class Get> PLB_L5 void solve_rhs(const double *CL, double *S, const in
         }
 #pragma unroll
     for (int r = 4; r < 10; ++r) diag[r] = CL[r * 10 + r];
-#pragma unroll 2
+#pragma unroll UNR
     for (int c = 0; c < 10; ++c) {
         double b[10];
 #pragma unroll

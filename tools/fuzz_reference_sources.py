@@ -4,7 +4,7 @@ bit-identical; the script prints the number of mismatches per section.
 
     python tools/fuzz_reference_sources.py [scale]     # scale 1.0: ~6000 estimate_* problems, 60000 minimal scenes, 3000 cameras
 Last full run (round 1): 0 mismatches in 6000 estimate_* problems (sizes 5..100, all four kinds and losses, PROSAC, degenerate
-data), 42168 minimal scenes x 6 solver entry points (planar, pure rotation, collinear, duplicated, noisy), 9000 camera calls.
+data), 42168 minimal scenes x 6 solver entry points (round 2: + p3p_lambdatwist, 0 mismatches in 14155 scenes) (planar, pure rotation, collinear, duplicated, noisy), 9000 camera calls.
 """
 import os
 import sys
@@ -105,7 +105,8 @@ def fuzz_minimal(count):
         x1, x2 = unit(X), unit(Y)
         if mode == 5:
             x2 = unit(Y + rng.normal(0, 0.01, Y.shape))
-        for name, f in (("p3p", lambda: P.p3p(x2[:3], X[:3])), ("relpose_5pt_E", lambda: P.relpose_5pt_E(x1[:5], x2[:5])),
+        for name, f in (("p3p", lambda: P.p3p(x2[:3], X[:3])), ("p3p_lambdatwist", lambda: P.p3p_lambdatwist(x2[:3], X[:3])),
+                        ("relpose_5pt_E", lambda: P.relpose_5pt_E(x1[:5], x2[:5])),
                         ("relpose_5pt", lambda: P.relpose_5pt(x1[:5], x2[:5])), ("relpose_7pt", lambda: P.relpose_7pt(x1[:7], x2[:7])),
                         ("homography_4pt", lambda: P.homography_4pt(x1[:4], x2[:4])[1]),
                         ("essential_matrix_8pt", lambda: P.essential_matrix_8pt(x1, x2))):
