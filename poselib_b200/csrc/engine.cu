@@ -302,6 +302,10 @@ static bool host_pinned(const void *p) {
 // ranks sharing a host) wait for their round by sleeping on a blocking event; spinning threads would take the cores from
 // the threads that have a round to replay.  Single calls and small batches spin (lowest latency).
 static thread_local bool t_blocking_sync = false;
+static std::mutex &upload_mutex(int device) {
+    static std::mutex m[64];
+    return m[(device >= 0 && device < 64) ? device : 0];
+}
 static thread_local bool t_batch_worker = false; // this thread runs one of several lock-step groups of a batch call
 
 // One engine (stream, events, grow-only buffers) per host thread AND device: a thread that switches devices with
@@ -683,6 +687,11 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         (rc = E.h_tdesc.ensure(std::max(n_up, 1))))
         return rc;
     {
+        // The lock-step groups of a batch call start together; left alone, their host->device copies interleave on the
+        // one copy engine and every group waits for (nearly) the whole batch to cross PCIe before its first kernel.
+        // Issued group by group, the first group computes while the others' inputs are still in flight.
+        std::unique_lock<std::mutex> upload_turn(upload_mutex(E.device), std::defer_lock);
+        if (t_batch_worker) upload_turn.lock();
         size_t in_off = 0, soa_off = 0, px_off = 0;
         std::vector<std::pair<size_t, size_t>> staged; // (offset, doubles) of the inputs that went through the staging buffer
         int iu = 0, ipol = 0;
@@ -771,6 +780,7 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
             PLB_CUDA(cudaMemcpyAsync(E.px64.p, E.h_in.p + in_doubles, sizeof(double) * px_elems, cudaMemcpyHostToDevice, st));
             h2d += sizeof(double) * px_elems;
         }
+        if (upload_turn.owns_lock()) upload_turn.unlock();
         // ---- normalize_points on the device (robust/utils.cc:584-644), then the thresholds that depend on its scale
         {
             std::vector<int> who;
