@@ -691,6 +691,107 @@ __global__ void __launch_bounds__(HYP_WARPS * 32) k7_solve(const RoundDesc R, in
     }
 }
 
+// relpose_7pt with ONE THREAD PER SAMPLE: the scalar nullspace routine of solver5_lane.cuh on a 63-double slice of shared
+// memory (odd stride: conflict-free), the rest is the scalar code of k7_solve.  Same arithmetic, same model bits.
+constexpr int K7L_THREADS = 256;
+constexpr int K7L_STRIDE = 63;
+constexpr size_t K7L_SMEM = sizeof(double) * K7L_STRIDE * K7L_THREADS;
+__global__ void __launch_bounds__(K7L_THREADS) k7_solve_lane(const RoundDesc R, HypOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *W = reinterpret_cast<double *>(smem_raw) + (size_t)threadIdx.x * K7L_STRIDE;
+    const int g_raw = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const bool live = g_raw < R.n_total;
+    const int g = live ? g_raw : R.n_total - 1; // idle lanes redo the last sample, nothing is stored
+    const int aslot = sample_problem_slot(R, g);
+    const int pidx = __ldg(R.active + aslot);
+    const ProblemDev &P = R.probs[pidx];
+    {
+        double x1s[21], x2s[21];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const uint32_t id = R.samples[(size_t)g * 7 + i];
+            const d3 a = bearing(P.p[0][id], P.p[1][id]), b = bearing(P.p[2][id], P.p[3][id]);
+            x1s[3 * i] = a.x; x1s[3 * i + 1] = a.y; x1s[3 * i + 2] = a.z;
+            x2s[3 * i] = b.x; x2s[3 * i + 1] = b.y; x2s[3 * i + 2] = b.z;
+        }
+#pragma unroll
+        for (int e = 0; e < 63; ++e) {
+            const int i = e / 9, k = e % 9;
+            W[e] = x1s[3 * i + k / 3] * x2s[3 * i + k % 3];
+        }
+    }
+    double nn[18];
+    lane5::nullspace_9xC<7>(W, nn);
+    const double *n0 = nn, *n1 = nn + 9;
+    // mixed determinants: column j of the 3x3 (col-major 9-vector) taken from a, b, c respectively
+    auto detc = [](const double *a, const double *b, const double *c) -> double {
+        const double *c0 = a, *c1 = b + 3, *c2 = c + 6;
+        return c0[0] * (c1[1] * c2[2] - c1[2] * c2[1]) - c1[0] * (c0[1] * c2[2] - c0[2] * c2[1]) +
+               c2[0] * (c0[1] * c1[2] - c0[2] * c1[1]);
+    };
+    const double c3 = detc(n0, n0, n0);
+    const double c2 = detc(n1, n0, n0) + detc(n0, n1, n0) + detc(n0, n0, n1);
+    const double c1 = detc(n0, n1, n1) + detc(n1, n0, n1) + detc(n1, n1, n0);
+    const double c0 = detc(n1, n1, n1);
+    double roots[3];
+    int n_roots;
+    if (fabs(c3) < 1e-14) {
+        n_roots = quadratic_real(c2, c1, c0, roots);
+    } else {
+        const double inv_c3 = 1.0 / c3;
+        n_roots = cubic_real(c2 * inv_c3, c1 * inv_c3, c0 * inv_c3, roots);
+    }
+    if (!live) return;
+    double F[3][9];
+    int nm = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (j < n_roots) {
+            const double r = roots[j];
+            double f[9];
+            double n2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                f[k] = n0[k] * r + n1[k];
+                n2 += f[k] * f[k];
+            }
+            if (n2 > 0) {
+                const double nrm = sqrt(n2);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) f[k] /= nrm;
+            }
+            if (P.rfc ? rfc_ok(f) : true) {
+                // nm is 0, 1 or 2 here: predicated copies keep F in registers
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+                    if (m == nm) {
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) F[m][k] = f[k];
+                    }
+                ++nm;
+            }
+        }
+    }
+    int base = 0;
+    if (nm) {
+        const int loc = atomicAdd(out.prob_count + aslot, nm);
+        if (loc + nm > __ldg(out.seg_cap + aslot)) { // cannot happen: this kind uses the worst-case capacity
+            atomicExch(out.overflow, 1);
+            nm = 0;
+        }
+        base = __ldg(out.seg_base + aslot) + loc;
+    }
+    out.n_models[g] = nm;
+    out.first_slot[g] = base;
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+        if (m < nm) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) out.models[(size_t)(base + m) * 9 + k] = F[m][k];
+            out.model_prob[base + m] = pidx;
+        }
+}
+
 // ---- relpose_5pt as three phase kernels -------------------------------------------------------------------------
 // The fused warp-per-sample 5-point solver is 181 KB of SASS and runs its Sturm root isolation on one lane; 16 warps
 // per SM at different places of that code starve on instruction fetch (profiles/r01_v2_batch64_summary.md).  The
@@ -1774,12 +1875,24 @@ static void launch_hyp_t(const RoundDesc &R, int *work, const HypOut &out, int m
             k_solve<KIND><<<blocks, HYP_WARPS * 32, hyp_smem_bytes<KIND>(), stream>>>(R, work, out);
         }
     } else if constexpr (KIND == KIND_FUND) {
-        // relpose_7pt: four samples per warp (PLB_SOLVE7_GRP=0: the warp-per-sample kernel)
+        // relpose_7pt: one thread per sample (PLB_SOLVE7_LANE=0: four samples per warp; PLB_SOLVE7_GRP=0: the
+        // warp-per-sample kernel)
+        static const bool lane7 = [] {
+            const char *e = std::getenv("PLB_SOLVE7_LANE");
+            return e ? std::atoi(e) != 0 : true;
+        }();
         static const bool grp7 = [] {
             const char *e = std::getenv("PLB_SOLVE7_GRP");
             return e ? std::atoi(e) != 0 : true;
         }();
-        if (grp7) {
+        if (lane7) {
+            static bool attr_set[MAX_DEVICES] = {false};
+            if (!attr_set[cur_dev()]) {
+                cudaFuncSetAttribute(k7_solve_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K7L_SMEM);
+                attr_set[cur_dev()] = true;
+            }
+            k7_solve_lane<<<(R.n_total + K7L_THREADS - 1) / K7L_THREADS, K7L_THREADS, K7L_SMEM, stream>>>(R, out);
+        } else if (grp7) {
             static int per_sm_dev[MAX_DEVICES] = {0};
             int &per_sm = per_sm_dev[cur_dev()];
             if (per_sm <= 0) {

@@ -67,13 +67,13 @@ constexpr Tables make_tables() {
 }
 constexpr Tables TB = make_tables();
 
-// ---- nullspace of the 9 x 5 epipolar matrix --------------------------------------------------------------------------
-// a: 45 doubles, column-major (a[c * 9 + r]), overwritten; qn: 36 doubles, qn[9 * s + r] = entry r of the s-th basis
-// vector = column 5 + s of the Householder Q of the full-pivoting QR (relpose_5pt.cc:167-168).  The scalar form of
+// ---- nullspace of the 9 x C epipolar matrix (C = 5: relpose_5pt, C = 7: relpose_7pt) --------------------------------------------------------------------------
+// a: 9 C doubles, column-major (a[c * 9 + r]), overwritten; qn: 9 (9 - C) doubles, qn[9 * s + r] = entry r of the s-th
+// basis vector = column C + s of the Householder Q of the full-pivoting QR (relpose_5pt.cc:167-168).  The scalar form of
 // grp8_nullspace_9xC<5> (solvers.cuh): same pivot rule (largest |entry|, first in column-major order on ties), same
 // reflectors, same order of the row transpositions.
-PLB_L5 void nullspace_9x5(double *a, double *qn) {
-    constexpr int ROWS = 9, COLS = 5;
+template <int COLS> PLB_L5 void nullspace_9xC(double *a, double *qn) {
+    constexpr int ROWS = 9;
     double tau_k[COLS];
     int rt_k[COLS];
     const double precision = 2.220446049250313e-16 * double(COLS);
@@ -211,6 +211,7 @@ PLB_L5 void nullspace_9x5(double *a, double *qn) {
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) qn[s * ROWS + r] = q[s][r];
 }
+PLB_L5 void nullspace_9x5(double *a, double *qn) { nullspace_9xC<5>(a, qn); }
 
 // ---- constraints -> 10 x 20 coefficient matrix ---------------------------------------------------------------------
 // Nb[4 * k + r]: coefficient of basis r (x, y, z, 1) in entry k (column-major) of E.  E(i, j) as a linear polynomial:
