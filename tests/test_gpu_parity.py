@@ -549,3 +549,45 @@ def test_p3p_lambdatwist_matches_oracle(cabi):
             assert np.abs(poses[i, :n[i]] - ref).max() <= 1e-9 * scale, (i, poses[i, :n[i]], ref)
     assert count_diff <= 5, count_diff
     assert n.sum() > 600
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["pnp", "homography", "fundamental"])
+def test_fast_mode_on_badly_scaled_inputs(cabi, kind):
+    """The inputs the fp32 screening copy likes least: 3D points a few thousand units from the origin with a tight
+    threshold (PnP), and pixel-unit coordinates of a few thousand with a one-pixel threshold (homography, fundamental
+    matrix).  The screening intervals are derived from the data (per-problem coordinate maxima), so the default mode must
+    still reproduce the all-fp64 mode bit for bit and follow the oracle's trajectory; what may change is how many models
+    need the fp64 confirmation."""
+    for seed in range(2):
+        if kind == "pnp":
+            p = G.abspose_problem(600, 0.45, 51, seed)
+            off = np.array([4000.0, -2500.0, 6000.0])
+            a, b, me = p["x"] / G.FOCAL, p["X"] + off, 2.0 / G.FOCAL  # (the pose absorbs the offset: t -> t - R off)
+            kw = dict(max_iterations=3000, min_iterations=300, seed=seed)
+        elif kind == "homography":
+            p = G.homography_problem(3000, 0.5, 54, seed)
+            # pixels, principal point not removed: coordinates up to ~1100 with a one-pixel threshold (the minimal
+            # solver itself is poorly conditioned in these units — few inliers, like the reference — which is beside the
+            # point here)
+            a, b, me = p["x1"] + 300.0, p["x2"] + 300.0, 1.0
+            kw = dict(max_iterations=4000, min_iterations=300, seed=seed)
+        else:
+            p = G.relpose_problem(2500, 0.4, 52, seed)
+            a, b, me = p["x1"] + 1200.0, p["x2"] + 1200.0, 1.0
+            kw = dict(max_iterations=8000, min_iterations=300, seed=seed)
+        cabi.set_mode("exact")
+        e = cabi.ransac(kind, a, b, cabi.RansacOpt(**kw), me)
+        cabi.set_mode("fast")
+        try:
+            f = cabi.ransac(kind, a, b, cabi.RansacOpt(**kw), me)
+        finally:
+            cabi.set_mode("exact")
+        assert f["stats"] == e["stats"], (f["stats"], e["stats"])
+        assert np.array_equal(f["inliers"], e["inliers"])
+        assert np.array_equal(np.asarray(f["model"]), np.asarray(e["model"]), equal_nan=True)
+        assert f["counters"]["hypotheses"] == e["counters"]["hypotheses"]
+        o = P.ransac(kind, a, b, P.RansacOpt(**kw), me)
+        for k in ("iterations", "refinements", "num_inliers"):
+            assert f["stats"][k] == o["stats"][k], (k, f["stats"], o["stats"])
+        assert np.array_equal(f["inliers"], o["inliers"])
