@@ -1709,25 +1709,44 @@ template <class VX> PLB_DEV unsigned motions_from_E(const double *E9, VX x1s, VX
         UW(r, 1) = -UW(r, 1);
     }
     rot_to_quat(mmul(UW, Vt), qb);
-    unsigned mask = 0;
+    // The four candidates are (qa, t), (qa, -t), (qb, -t), (qb, t) (reference order).  check_cheirality
+    // (misc/essential.cc:40-57) of (q, -t) yields exactly the negated depths of (q, t): dot products, products and the
+    // two-term sums are symmetric under negation in round-to-nearest, and min_depth = 0 makes the bound a signed zero.
+    // So one evaluation per (rotation, point) decides both translation signs — half the work, and without the
+    // per-candidate early exits that kept half the lanes of k5_back idle.
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const double *q = (c < 2) ? qa : qb;
-        // translation signs: +t, -t, then (after the second `pose.t = -pose.t`) -(-t) = +t ... follow the
-        // reference literally: cand0 = (qa, t), cand1 = (qa,-t), cand2 = (qb,-t), cand3 = (qb, t)
         const double sgn = (c == 0 || c == 3) ? 1.0 : -1.0;
         cand[c][0] = q[0]; cand[c][1] = q[1]; cand[c][2] = q[2]; cand[c][3] = q[3];
         cand[c][4] = sgn * c2.x; cand[c][5] = sgn * c2.y; cand[c][6] = sgn * c2.z;
-        bool ok = true;
+    }
+    unsigned mask = 0;
+#pragma unroll
+    for (int rot = 0; rot < 2; ++rot) {
+        const double *q = rot ? qb : qa;
+        bool okp = true, okm = true; // translation +c2 / -c2
         for (int i = 0; i < ns; ++i) {
             const d3 a = mk(x1s[3 * i], x1s[3 * i + 1], x1s[3 * i + 2]);
             const d3 b = mk(x2s[3 * i], x2s[3 * i + 1], x2s[3 * i + 2]);
-            if (!cheirality_ok(cand[c], cand[c] + 4, a, b, 0.0)) {
-                ok = false;
-                break;
-            }
+            const d3 Rx1 = quat_rotate(q, a);
+            const double ca = -dot(Rx1, b);
+            const double b1 = -dot(Rx1, c2);
+            const double b2 = dot(b, c2);
+            const double lambda1 = b1 - ca * b2;
+            const double lambda2 = -ca * b1 + b2;
+            const double md = 0.0 * (1 - ca * ca);
+            okp = okp && (lambda1 > md && lambda2 > md);
+            okm = okm && (-lambda1 > md && -lambda2 > md);
+            if (!okp && !okm) break;
         }
-        if (ok) mask |= 1u << c;
+        if (rot == 0) {
+            if (okp) mask |= 1u;
+            if (okm) mask |= 2u;
+        } else {
+            if (okm) mask |= 4u;
+            if (okp) mask |= 8u;
+        }
     }
     return mask;
 }
