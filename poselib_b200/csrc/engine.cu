@@ -687,11 +687,12 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
         (rc = E.h_tdesc.ensure(std::max(n_up, 1))))
         return rc;
     {
-        // The lock-step groups of a batch call start together; left alone, their host->device copies interleave on the
-        // one copy engine and every group waits for (nearly) the whole batch to cross PCIe before its first kernel.
-        // Issued group by group, the first group computes while the others' inputs are still in flight.
-        std::unique_lock<std::mutex> upload_turn(upload_mutex(E.device), std::defer_lock);
-        if (t_batch_worker) upload_turn.lock();
+        struct DirectCopy {
+            double *dst;
+            const double *src;
+            size_t bytes;
+        };
+        std::vector<DirectCopy> direct; // page-locked caller arrays: DMA straight from them (issued below, in one turn)
         size_t in_off = 0, soa_off = 0, px_off = 0;
         std::vector<std::pair<size_t, size_t>> staged; // (offset, doubles) of the inputs that went through the staging buffer
         int iu = 0, ipol = 0;
@@ -717,9 +718,8 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 S.in_off = (long long)in_off;
                 if (host_pinned(S.t->a) && host_pinned(S.t->b)) {
                     // the caller's arrays are page-locked: DMA straight from them, no staging copy on the host
-                    PLB_CUDA(cudaMemcpyAsync(E.in.p + in_off, S.t->a, sizeof(double) * 2 * S.n, cudaMemcpyHostToDevice, st));
-                    PLB_CUDA(cudaMemcpyAsync(E.in.p + in_off + 2 * (size_t)S.n, S.t->b, sizeof(double) * (size_t)b_dim * S.n,
-                                             cudaMemcpyHostToDevice, st));
+                    direct.push_back({E.in.p + in_off, S.t->a, sizeof(double) * 2 * S.n});
+                    direct.push_back({E.in.p + in_off + 2 * (size_t)S.n, S.t->b, sizeof(double) * (size_t)b_dim * S.n});
                     h2d += sizeof(double) * (size_t)in_arr * S.n;
                 } else {
                     staged.emplace_back(in_off, (size_t)in_arr * S.n);
@@ -768,6 +768,13 @@ static int run_group(int kind, std::vector<Task *> &tasks) {
                 ++ipol;
             }
         }
+        // The lock-step groups of a batch call start together; left alone, their host->device copies interleave on the
+        // one copy engine and every group waits for (nearly) the whole batch to cross PCIe before its first kernel.
+        // Issued group by group (the host-side staging above stays parallel), the first group computes while the others'
+        // inputs are still in flight.
+        std::unique_lock<std::mutex> upload_turn(upload_mutex(E.device), std::defer_lock);
+        if (t_batch_worker) upload_turn.lock();
+        for (const DirectCopy &c : direct) PLB_CUDA(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyHostToDevice, st));
         // staged (pageable) inputs: contiguous runs of the pinned staging buffer go up in one copy each
         for (size_t i = 0; i < staged.size();) {
             size_t j = i, off = staged[i].first, len = 0;
