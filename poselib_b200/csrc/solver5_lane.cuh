@@ -342,9 +342,9 @@ template <class Sink> PLB_L5 void build_coeffs(const double *Nb, Sink &&put) {
 // lu_left: partial-pivot LU in place, full-row transpositions, multipliers stored below the diagonal (the LAPACK
 // arrangement).  idx[r] = original row that ends up at position r.  S: 10 doubles of scratch.
 PLB_L5 void lu_left(double *CL, double *S, int *idx) {
-    int *Si = reinterpret_cast<int *>(S);
+    // row bookkeeping in the double scratch (small integers are exact; no second type aliasing the same bytes)
 #pragma unroll
-    for (int r = 0; r < 10; ++r) Si[r] = r;
+    for (int r = 0; r < 10; ++r) S[r] = (double)r;
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
         int p = k;
@@ -358,9 +358,9 @@ PLB_L5 void lu_left(double *CL, double *S, int *idx) {
             }
         }
         {
-            const int t = Si[k]; // p == k: no change
-            Si[k] = Si[p];
-            Si[p] = t;
+            const double t = S[k]; // p == k: no change
+            S[k] = S[p];
+            S[p] = t;
         }
         double *rk = CL + k * 10, *rp = CL + p * 10;
 #pragma unroll
@@ -388,7 +388,7 @@ PLB_L5 void lu_left(double *CL, double *S, int *idx) {
             }
     }
 #pragma unroll
-    for (int r = 0; r < 10; ++r) idx[r] = Si[r];
+    for (int r = 0; r < 10; ++r) idx[r] = (int)S[r];
 }
 
 // The right-hand sides: get(row, column) returns the parked entry; each column is permuted (through S), run through
