@@ -32,6 +32,7 @@ int main(int argc, char **argv) {
     p3p_opt.n_point_point_ = 3;
     p3p_opt.n_point_line_ = 0;
     report(poselib::benchmark<poselib::SolverP3P>(n, p3p_opt, tol));
+    report(poselib::benchmark<poselib::SolverP3P_lambdatwist>(n, p3p_opt, tol));
 
     poselib::ProblemOptions rel8pt_opt = options;
     rel8pt_opt.n_point_point_ = 8;

@@ -49,7 +49,7 @@ def _bench_available():
 def test_the_references_solver_benchmark_criteria_hold_on_the_mini_eigen_build():
     """The reference's own benchmark harness (benchmark/solver_benchmark.cc + problem_generator.cc, unmodified; its main()
     replaced by one that repeats its configuration of the path's solvers, oracle/ref/ref_solver_bench.cc): on 2000
-    noise-free instances of the reference's generator per solver, every returned solution of p3p, relpose_8pt (8 and 100
+    noise-free instances of the reference's generator per solver, every returned solution of p3p, p3p_lambdatwist, relpose_8pt (8 and 100
     points) and homography_4pt is valid at 1e-6 and the ground truth is always found; relpose_5pt — a degree-10 root finder
     on instances of arbitrary conditioning — reaches 98 % on both counts (no published figure to compare with)."""
     out = subprocess.run([BENCH, "2000"], capture_output=True, text=True, timeout=600)
@@ -59,8 +59,8 @@ def test_the_references_solver_benchmark_criteria_hold_on_the_mini_eigen_build()
         m = re.match(r"\s*(.+?) instances=(\d+) solutions=(\d+) valid=(\d+) found_gt=(\d+)\s*$", line)
         if m:
             res[m.group(1).strip()] = tuple(int(v) for v in m.groups()[1:])
-    assert set(res) == {"p3p", "Rel8pt", "Rel8pt(100 pts)", "Rel5pt", "Homography4pt", "Homography4pt(C)"}, res
-    for name in ("p3p", "Rel8pt", "Rel8pt(100 pts)", "Homography4pt"):
+    assert set(res) == {"p3p", "p3p_lambdatwist", "Rel8pt", "Rel8pt(100 pts)", "Rel5pt", "Homography4pt", "Homography4pt(C)"}, res
+    for name in ("p3p", "p3p_lambdatwist", "Rel8pt", "Rel8pt(100 pts)", "Homography4pt"):
         inst, sols, valid, gt = res[name]
         assert inst == 2000 and valid == sols and gt == inst, (name, res[name])
     inst, sols, valid, gt = res["Homography4pt(C)"]  # the cheirality pre-check rejects some instances outright
